@@ -1,0 +1,44 @@
+"""Shared test plumbing: rebuild weights / inputs / dropout plans from a golden recipe."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle.synth import (LSA, SMA, DecoderDims, make_decoder_weights, make_dropout_plan,
+                          make_inputs, weights_checksum)
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def load_golden(name: str):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    recipe = json.loads(str(z["recipe"]))
+    out = {k: torch.from_numpy(z[k]) for k in z.files if k not in ("recipe", "weights_checksum")}
+    return recipe, out, str(z["weights_checksum"])
+
+
+def materialise(recipe: dict):
+    """(weights, inputs, plan) exactly as oracle/make_golden.py built them."""
+    seed = recipe["seed"]
+    w = make_decoder_weights(recipe["attention"], seed=seed, gate_bias=recipe.get("gate_bias"))
+    B, T_in, T_sub = recipe["B"], recipe["T_in"], recipe["T_sub"]
+    if recipe["mode"] == "tf":
+        T = recipe["T"]
+        inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=recipe["ragged"])
+        plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, recipe["training"], seed=seed + 1)
+    else:
+        ms = recipe["max_steps"]
+        inp = make_inputs(B, T_in, T_sub, 1, seed=seed)
+        plan = make_dropout_plan(B, ms, ms, T_in, T_sub, False, seed=seed + 1)
+    return w, inp, plan
+
+
+def maxabs(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float((a.double() - b.double()).abs().max()) if a.numel() else 0.0
