@@ -1,0 +1,182 @@
+/*
+ * taco2dec.h -- C ABI of the B200-native Tacotron2 dual-stream mel decoder.
+ *
+ * Drop-in boundary for ONE hot path of PhucNguyenAH/tacotron2_subword: the per-frame
+ * loop of model.Decoder.  The reference has no native boundary of its own (it is pure
+ * Python/PyTorch); the seam this library replaces is the nn.Module method:
+ *
+ *   taco2dec_forward_teacher_forced  <->  Decoder.forward   (/root/reference/model.py:392-428)
+ *   taco2dec_infer                   <->  Decoder.inference (/root/reference/model.py:430-492)
+ *   taco2dec_set_weights             <->  Decoder.__init__ parameters / load_state_dict
+ *                                         (model.py:142-207, attention.py:7-37, 305-322)
+ *   taco2dec_config                  <->  hparams.py:55,67,72-90 fields read by Decoder
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless its name ends in
+ *     _host; tensors are dense, row-major, fp32 unless stated; sizes are element counts;
+ *   - the caller owns all memory (inputs, outputs, weights, workspace); the library borrows
+ *     pointers for the duration of the enqueued work.  Weights passed to
+ *     taco2dec_set_weights must stay alive and unchanged until the next set_weights / destroy;
+ *   - calls enqueue on the given cudaStream_t (pass the caller's current stream) and return
+ *     without synchronising, except where documented;
+ *   - return value: 0 = ok, <0 = error (see TACO2DEC_E_*), text via taco2dec_last_error();
+ *   - the device must be compute capability 10.x (B200, sm_100a); there is NO CPU fallback;
+ *   - one handle per (process, device); a handle is not re-entrant.
+ */
+#ifndef TACO2DEC_H_
+#define TACO2DEC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TACO2DEC_ABI_VERSION 1
+
+#define TACO2DEC_ATTN_SMA 0 /* StepwiseMonotonicAttention   (attention.py:291-398, hparams default) */
+#define TACO2DEC_ATTN_LSA 1 /* LocationSensitiveAttention   (attention.py:7-85)                      */
+
+#define TACO2DEC_E_ARG (-1)     /* bad argument / shape                      */
+#define TACO2DEC_E_ARCH (-2)    /* device is not sm_100                      */
+#define TACO2DEC_E_CUDA (-3)    /* CUDA runtime error                        */
+#define TACO2DEC_E_STATE (-4)   /* weights not set, workspace too small, ... */
+#define TACO2DEC_E_ABORTED (-5) /* in-kernel watchdog fired (grid barrier timeout) */
+
+typedef struct taco2dec_handle taco2dec_handle;
+
+/* hparams.py fields the decoder reads (model.py:131-140, 158-207). */
+typedef struct taco2dec_config {
+  int n_mel;        /* n_mel_channels * n_frames_per_step (n_frames_per_step must be 1) */
+  int enc_dim;      /* encoder_embedding_dim            512  */
+  int attn_rnn_dim; /* attention_rnn_dim                1024 */
+  int dec_rnn_dim;  /* decoder_rnn_dim                  1024 */
+  int prenet_dim;   /* prenet_dim                       256  */
+  int attn_dim;     /* attention_dim                    128  */
+  int loc_filters;  /* attention_location_n_filters     32   (LSA only) */
+  int loc_kernel;   /* attention_location_kernel_size   31   (LSA only) */
+  int attention;    /* TACO2DEC_ATTN_*                            */
+  int n_streams;    /* 2 = BERT_Tacotron2 (char + sub-word), 1 = Tacotron2 compat */
+  float p_attention_dropout; /* 0.1, applied to h AND c of the attention LSTMs (model.py:341-346) */
+  float p_decoder_dropout;   /* 0.1, applied to h AND c of the decoder LSTM   (model.py:372-373) */
+} taco2dec_config;
+
+/* Per-stream weights; index 0 = char/phoneme stream, 1 = sub-word ("bert") stream.
+ * PyTorch layouts exactly as in the reference state_dict. */
+typedef struct taco2dec_stream_weights {
+  const float* prenet_w0;    /* prenet{,_bert}.layers.0.linear_layer.weight   [prenet, n_mel]   */
+  const float* prenet_w1;    /* prenet{,_bert}.layers.1.linear_layer.weight   [prenet, prenet]  */
+  const float* arnn_w_ih;    /* attention_rnn{,_bert}.weight_ih               [4H, prenet+enc]  */
+  const float* arnn_w_hh;    /* attention_rnn{,_bert}.weight_hh               [4H, H]           */
+  const float* arnn_b_ih;    /* attention_rnn{,_bert}.bias_ih                 [4H]              */
+  const float* arnn_b_hh;    /* attention_rnn{,_bert}.bias_hh                 [4H]              */
+  const float* query_w;      /* attention_layer{,_bert}.query_layer.linear_layer.weight  [A, H]   */
+  const float* memory_w;     /* attention_layer{,_bert}.memory_layer.linear_layer.weight [A, enc] */
+  const float* v;            /* SMA: ...v.weight   LSA: ...v.linear_layer.weight          [1, A]   */
+  const float* loc_conv_w;   /* LSA: ...location_layer.location_conv.conv.weight  [F, 2, K]  (else NULL) */
+  const float* loc_dense_w;  /* LSA: ...location_layer.location_dense.linear_layer.weight [A, F] (else NULL) */
+} taco2dec_stream_weights;
+
+typedef struct taco2dec_weights {
+  taco2dec_stream_weights stream[2];
+  const float* drnn_w_ih; /* decoder_rnn.weight_ih  [4D, n_streams*(H+enc)]  input order h,ctx,h_bert,ctx_bert (model.py:362) */
+  const float* drnn_w_hh; /* decoder_rnn.weight_hh  [4D, D]  */
+  const float* drnn_b_ih; /* [4D] */
+  const float* drnn_b_hh; /* [4D] */
+  const float* proj_w;    /* linear_projection.linear_layer.weight [n_mel, D + n_streams*enc]  input order h2,ctx,ctx_bert (model.py:382) */
+  const float* proj_b;    /* [n_mel] */
+  const float* gate_w;    /* gate_layer.linear_layer.weight [1, D + n_streams*enc] */
+  const float* gate_b;    /* [1] */
+  /* decoder_rnn_bert.* is dead in decode() (model.py:375-378): never passed, never read. */
+} taco2dec_weights;
+
+/* Dropout / noise source.  Any pointer may be NULL: the kernel then draws that mask from
+ * Philox4x32-10 keyed by `seed` (production mode).  Non-NULL = replay of externally drawn
+ * masks (parity mode).  uint8 keep-masks: 1 = keep (scaled by 1/(1-p)). */
+typedef struct taco2dec_rng {
+  uint64_t seed;
+  const uint8_t* prenet_keep[2][2]; /* [stream][layer] -> [rows, B, prenet]; teacher-forced rows = T+1
+                                       (model.py:412-413), free-running rows = max_decoder_steps
+                                       (model.py:449-450, 470-471).  Prenet dropout is ALWAYS on (model.py:23). */
+  const uint8_t* lstm_keep;         /* training only: [T, 6, B, H] order attn_h, attn_c, attn_h_bert,
+                                       attn_c_bert, dec_h, dec_c (model.py:341-346, 372-373) */
+  const float* sma_noise[2];        /* training + SMA only: [T, B, T_stream] N(0,1) (attention.py:346-348) */
+} taco2dec_rng;
+
+/* Decoder.forward (teacher-forced).  Outputs are written in final layout. */
+typedef struct taco2dec_tf_args {
+  int B, T, T_in, T_sub;
+  const float* memory;           /* [B, T_in, enc]   encoder outputs (char stream)            */
+  const float* embeddings;       /* [B, T_sub, enc]  sub-word stream (NULL when n_streams==1) */
+  const float* decoder_inputs;   /* [B, n_mel, T]    teacher-forcing targets (model.py:283-287 reads this layout) */
+  const int64_t* memory_lengths; /* [B] or NULL (= all T_in).  max must equal T_in (utils.py:11) */
+  const int64_t* bert_lengths;   /* [B] or NULL */
+  int training;                  /* 1 = LSTM-state dropout + SMA noise on (module.training) */
+  taco2dec_rng rng;
+  float* mel;        /* [B, T, n_mel]  (== the storage behind the reference's [B, n_mel, T] transposed view, model.py:314-318) */
+  float* gate;       /* [B, T]          gate energies (logits) */
+  float* align;      /* [B, T, T_in]    */
+  float* align_bert; /* [B, T, T_sub]   (NULL when n_streams==1) */
+  void* workspace;
+  size_t workspace_bytes;
+} taco2dec_tf_args;
+
+/* Decoder.inference (free-running).  The reference is batch-1 only (model.py:461,480);
+ * B > 1 here means B independent utterances, each defined as its own batch-1 run on its
+ * un-padded memory (positions >= length do not exist). */
+typedef struct taco2dec_infer_args {
+  int B, T_in, T_sub;
+  int max_decoder_steps;         /* hparams.max_decoder_steps; also the T capacity of the outputs */
+  float gate_threshold;          /* stop when sigmoid(gate) > gate_threshold (strict, model.py:480) */
+  const float* memory;           /* [B, T_in, enc]  */
+  const float* embeddings;       /* [B, T_sub, enc] */
+  const int64_t* memory_lengths; /* [B] or NULL */
+  const int64_t* bert_lengths;   /* [B] or NULL */
+  taco2dec_rng rng;
+  float* mel;        /* [B, max_decoder_steps, n_mel]; rows >= n_frames[b] are unspecified */
+  float* gate;       /* [B, max_decoder_steps]        */
+  float* align;      /* [B, max_decoder_steps, T_in]  */
+  float* align_bert; /* [B, max_decoder_steps, T_sub] */
+  int32_t* n_frames; /* [B] frames produced (stop frame included, model.py:475-481)  */
+  int32_t* reached_max; /* [B] 1 = hit max_decoder_steps without the gate firing (INFER_FLAG = False, model.py:482-485) */
+  void* workspace;
+  size_t workspace_bytes;
+} taco2dec_infer_args;
+
+int taco2dec_abi_version(void);
+const char* taco2dec_last_error(void);
+
+/* device = CUDA ordinal.  Fails with TACO2DEC_E_ARCH unless the device is sm_100. */
+int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** out);
+int taco2dec_destroy(taco2dec_handle* h);
+
+/* Borrow the fp32 weights (no copy, no repack in this version). */
+int taco2dec_set_weights(taco2dec_handle* h, const taco2dec_weights* w, void* cuda_stream);
+
+/* Scratch the caller must provide (state, processed memory, prenet activations). */
+size_t taco2dec_workspace_bytes(const taco2dec_handle* h, int B, int T_in, int T_sub, int T_or_max_steps,
+                                int teacher_forced);
+
+int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* a, void* cuda_stream);
+int taco2dec_infer(taco2dec_handle* h, const taco2dec_infer_args* a, void* cuda_stream);
+
+/* Synchronises the stream and reports TACO2DEC_E_ABORTED if the in-kernel watchdog fired
+ * during any call since the last check (asynchronous CUDA faults surface here too). */
+int taco2dec_check(taco2dec_handle* h, void* cuda_stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t taco2dec_launch_count(const taco2dec_handle* h);
+
+/* The Philox keep-mask the kernels draw when a replay pointer is NULL: out[row*n + i] for
+ * mask_id (prenet: stream*2+layer; lstm: 4+k) -- lets tests replay production masks. */
+int taco2dec_philox_keep_mask(uint64_t seed, int mask_id, int rows, int n, float p_drop, uint8_t* out,
+                              void* cuda_stream);
+
+/* Persistent-kernel launch geometry actually used (for DESIGN.md / bench bookkeeping). */
+int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* block, int* smem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACO2DEC_H_ */

@@ -1,0 +1,117 @@
+"""ctypes binding of ``include/taco2dec.h`` (the C-ABI drop-in boundary).
+
+There is NO fallback: if the shared library is missing or the device is not sm_100 the
+decoder raises.  Build with ``python -m tacotron2_subword_b200.build`` (or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtaco2dec.so")
+
+ATTN_SMA, ATTN_LSA = 0, 1
+ABI_VERSION = 1
+
+EXPORTED_SYMBOLS = (
+    "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
+    "taco2dec_set_weights", "taco2dec_workspace_bytes", "taco2dec_forward_teacher_forced",
+    "taco2dec_infer", "taco2dec_check", "taco2dec_launch_count", "taco2dec_philox_keep_mask",
+    "taco2dec_launch_geometry",
+)
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class Config(C.Structure):
+    _fields_ = [("n_mel", C.c_int), ("enc_dim", C.c_int), ("attn_rnn_dim", C.c_int), ("dec_rnn_dim", C.c_int),
+                ("prenet_dim", C.c_int), ("attn_dim", C.c_int), ("loc_filters", C.c_int), ("loc_kernel", C.c_int),
+                ("attention", C.c_int), ("n_streams", C.c_int),
+                ("p_attention_dropout", C.c_float), ("p_decoder_dropout", C.c_float)]
+
+
+class StreamWeights(C.Structure):
+    _fields_ = [(n, _fp) for n in ("prenet_w0", "prenet_w1", "arnn_w_ih", "arnn_w_hh", "arnn_b_ih", "arnn_b_hh",
+                                   "query_w", "memory_w", "v", "loc_conv_w", "loc_dense_w")]
+
+
+class Weights(C.Structure):
+    _fields_ = [("stream", StreamWeights * 2)] + [(n, _fp) for n in (
+        "drnn_w_ih", "drnn_w_hh", "drnn_b_ih", "drnn_b_hh", "proj_w", "proj_b", "gate_w", "gate_b")]
+
+
+class Rng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("prenet_keep", (_fp * 2) * 2), ("lstm_keep", _fp), ("sma_noise", _fp * 2)]
+
+
+class TFArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("T", C.c_int), ("T_in", C.c_int), ("T_sub", C.c_int),
+                ("memory", _fp), ("embeddings", _fp), ("decoder_inputs", _fp),
+                ("memory_lengths", _fp), ("bert_lengths", _fp), ("training", C.c_int), ("rng", Rng),
+                ("mel", _fp), ("gate", _fp), ("align", _fp), ("align_bert", _fp),
+                ("workspace", _fp), ("workspace_bytes", C.c_size_t)]
+
+
+class InferArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("T_in", C.c_int), ("T_sub", C.c_int), ("max_decoder_steps", C.c_int),
+                ("gate_threshold", C.c_float), ("memory", _fp), ("embeddings", _fp),
+                ("memory_lengths", _fp), ("bert_lengths", _fp), ("rng", Rng),
+                ("mel", _fp), ("gate", _fp), ("align", _fp), ("align_bert", _fp),
+                ("n_frames", _fp), ("reached_max", _fp), ("workspace", _fp), ("workspace_bytes", C.c_size_t)]
+
+
+class Taco2DecError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library and declare prototypes.  Loud failure if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise Taco2DecError(
+            f"{LIB_PATH} not found: the CUDA decoder has not been built and there is no CPU fallback. "
+            "Run `python -m tacotron2_subword_b200.build`.")
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    lib.taco2dec_abi_version.restype = C.c_int
+    lib.taco2dec_abi_version.argtypes = []
+    lib.taco2dec_last_error.restype = C.c_char_p
+    lib.taco2dec_last_error.argtypes = []
+    lib.taco2dec_create.restype = C.c_int
+    lib.taco2dec_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(H)]
+    lib.taco2dec_destroy.restype = C.c_int
+    lib.taco2dec_destroy.argtypes = [H]
+    lib.taco2dec_set_weights.restype = C.c_int
+    lib.taco2dec_set_weights.argtypes = [H, C.POINTER(Weights), C.c_void_p]
+    lib.taco2dec_workspace_bytes.restype = C.c_size_t
+    lib.taco2dec_workspace_bytes.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.taco2dec_forward_teacher_forced.restype = C.c_int
+    lib.taco2dec_forward_teacher_forced.argtypes = [H, C.POINTER(TFArgs), C.c_void_p]
+    lib.taco2dec_infer.restype = C.c_int
+    lib.taco2dec_infer.argtypes = [H, C.POINTER(InferArgs), C.c_void_p]
+    lib.taco2dec_check.restype = C.c_int
+    lib.taco2dec_check.argtypes = [H, C.c_void_p]
+    lib.taco2dec_launch_count.restype = C.c_int64
+    lib.taco2dec_launch_count.argtypes = [H]
+    lib.taco2dec_philox_keep_mask.restype = C.c_int
+    lib.taco2dec_philox_keep_mask.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    lib.taco2dec_launch_geometry.restype = C.c_int
+    lib.taco2dec_launch_geometry.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    if lib.taco2dec_abi_version() != ABI_VERSION:
+        raise Taco2DecError("libtaco2dec.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().taco2dec_last_error()
+        raise Taco2DecError(f"taco2dec error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,1129 @@
+// taco2dec.cu -- B200 (sm_100a) persistent Tacotron2 dual-stream mel decoder, fp32 exact path.
+//
+// One cooperative launch runs ALL frames of Decoder.forward / Decoder.inference
+// (/root/reference/model.py:392-492).  148 CTAs stay resident; every frame is a fixed
+// sequence of phases separated by a hand-written grid barrier:
+//
+//   [free-running only]  P0a prenet layer 0 -> P0b prenet layer 1          (model.py:13-24)
+//   A  attention LSTM cells, both streams                                  (model.py:337-346)
+//   Q  query projection  q = Wq h                                          (attention.py:56, 368)
+//   B  energies -> (sigmoid + stepwise-monotonic | location conv + softmax) -> context
+//                                                                          (attention.py:330-398, 7-85)
+//   C  decoder LSTM cell                                                   (model.py:362-373)
+//   D  mel / gate projection (+ stop test when free-running)               (model.py:382-388, 480-485)
+//
+// GEMV phases: one warp owns one hidden unit (its 4 gate rows), lanes stride over K with
+// 16-byte streaming loads (ld.global.nc.L1::no_allocate), the activation vectors are staged
+// once per CTA in shared memory, warp-shuffle reductions, LSTM pointwise fused in the warp.
+// This is the bandwidth-bound small-batch path; weights are read in the reference's own
+// PyTorch layouts (no repack) in fp32, so results agree with the fp32 oracle to ~1e-6.
+//
+// No CPU fallback, no multi-backend dispatch: the host API refuses non-sm_100 devices.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+
+#include "taco2dec.h"
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxStreams = 2;
+constexpr long long kBarrierTimeoutClocks = 6000000000LL;  // ~3 s at 1.9 GHz: watchdog, never hit in a healthy run
+
+// ------------------------------------------------------------------------------------------
+// Kernel parameter block
+// ------------------------------------------------------------------------------------------
+struct StreamParams {
+  const float *pre_w0, *pre_w1, *w_ih, *w_hh, *b_ih, *b_hh, *wq, *wm, *v, *loc_conv, *loc_dense;
+  const float* mem;         // [B, Ts, E]
+  const long long* len;     // [B] or null
+  const float* noise;       // [T, B, Ts] or null
+  const uint8_t* keep0;     // prenet keep masks [rows, B, P] or null
+  const uint8_t* keep1;
+  float* pm;                // [B, Ts, A] processed memory
+  float* pre;               // TF: [T+1, B, P] prenet output; FR: [B, P]
+  float* pre0;              // FR: [B, P] prenet layer-0 output
+  float* a_prev;            // [B, Ts]  SMA: alignment state; LSA: previous attention weights
+  float* a_cum;             // [B, Ts]  LSA cumulative weights
+  float* align;             // [B, Tcap, Ts] output
+  int Ts;
+};
+
+struct Params {
+  int B, T, S, H, D, E, P, A, M, LF, LK;
+  int attention, free_running, training, max_steps, Tcap;
+  float gate_thr, p_att, p_dec;
+  unsigned thresh_pre, thresh_att, thresh_dec;  // Philox keep thresholds (u32 >= thresh -> keep)
+  unsigned long long seed;
+  StreamParams st[kMaxStreams];
+  const float *d_w_ih, *d_w_hh, *d_b_ih, *d_b_hh, *proj_w, *proj_b, *gate_w, *gate_b;
+  const float* dec_in;       // TF targets [B, M, T]
+  const uint8_t* lstm_keep;  // [T, 6, B, H] or null
+  float *h1, *c1;            // h1: [2 bufs][S][B][H], c1: [S][B][H]
+  float *h2, *c2;            // h2: [2 bufs][B][D],    c2: [B][D]
+  float* ctx;                // [S][B][E]
+  float* q;                  // [S][B][A]
+  float *mel, *gate;         // [B, Tcap, M], [B, Tcap]
+  int *n_frames, *reached_max;  // [B] (free-running)
+  unsigned* sync_ctr;        // grid barrier counter (zeroed by the host before launch)
+  int* abort_flag;           // watchdog
+  int* done_count;           // free-running: utterances that have stopped
+};
+
+// ------------------------------------------------------------------------------------------
+// Small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Philox4x32-10, counter = (idx, row, mask_id, 0), key = seed.
+__host__ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                                       unsigned k0, unsigned k1, unsigned out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned long long p0 = 0xD2511F53ull * c0;
+    unsigned long long p1 = 0xCD9E8D57ull * c2;
+    unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0;
+    unsigned n1 = (unsigned)p1;
+    unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+    unsigned n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ bool philox_keep(unsigned long long seed, int mask_id, int row, int idx, unsigned thresh) {
+  unsigned o[4];
+  philox4x32_10((unsigned)idx, (unsigned)row, (unsigned)mask_id, 0u, (unsigned)seed, (unsigned)(seed >> 32), o);
+  return o[0] >= thresh;
+}
+__device__ __forceinline__ float philox_normal(unsigned long long seed, int mask_id, int row, int idx) {
+  unsigned o[4];
+  philox4x32_10((unsigned)idx, (unsigned)row, (unsigned)mask_id, 0u, (unsigned)seed, (unsigned)(seed >> 32), o);
+  float u1 = ((float)o[0] + 0.5f) * 2.3283064365386963e-10f;
+  float u2 = ((float)o[1] + 0.5f) * 2.3283064365386963e-10f;
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// keep-mask lookup: replay array if given, else Philox.  Returns the multiplier (0 or scale).
+__device__ __forceinline__ float keep_mult(const uint8_t* replay, size_t replay_index, unsigned long long seed,
+                                           int mask_id, int row, int idx, unsigned thresh, float scale) {
+  bool k = replay ? (replay[replay_index] != 0) : philox_keep(seed, mask_id, row, idx, thresh);
+  return k ? scale : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// Grid barrier (all CTAs co-resident: cooperative launch).  Monotonic counter; thread 0 of
+// each CTA arrives with a release-add and spins with acquire loads.  A clock watchdog turns
+// a would-be hang into an abort flag every CTA observes.
+// ------------------------------------------------------------------------------------------
+struct GridBarrier {
+  unsigned* ctr;
+  int* abort_flag;
+  unsigned target;
+  unsigned nblocks;
+};
+
+__device__ __forceinline__ bool grid_sync(GridBarrier& gb, int* s_flag) {
+  __syncthreads();
+  gb.target += gb.nblocks;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    red_release_add(gb.ctr, 1u);
+    const long long t0 = clock64();
+    int aborted = 0;
+    unsigned spins = 0;
+    while ((int)(ld_acquire_u32(gb.ctr) - gb.target) < 0) {
+      if ((++spins & 1023u) == 0u) {
+        if (*((volatile int*)gb.abort_flag) != 0) { aborted = 1; break; }
+        if (clock64() - t0 > kBarrierTimeoutClocks) { atomicExch(gb.abort_flag, 1); aborted = 1; break; }
+      }
+    }
+    __threadfence();
+    *s_flag = aborted;
+  }
+  __syncthreads();
+  return *s_flag == 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-level multi-row dot product: acc[r][b] += sum_k rows[r][k] * xs[b*ldx + k]
+// rows: global fp32 (streamed, 16-byte loads), xs: shared (or global) fp32, K4 = K/4.
+// ------------------------------------------------------------------------------------------
+template <int R, int BT>
+__device__ __forceinline__ void warp_dot(const float* const (&rows)[R], const float* xs, int ldx, int K4, int lane,
+                                         float (&acc)[R][BT]) {
+#pragma unroll 4
+  for (int k4 = lane; k4 < K4; k4 += 32) {
+    float4 w[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) w[r] = ld_stream4(rows[r] + 4 * k4);
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      const float4 x = *reinterpret_cast<const float4*>(xs + (size_t)b * ldx + 4 * k4);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r][b] = fmaf(w[r].x, x.x, acc[r][b]);
+        acc[r][b] = fmaf(w[r].y, x.y, acc[r][b]);
+        acc[r][b] = fmaf(w[r].z, x.z, acc[r][b]);
+        acc[r][b] = fmaf(w[r].w, x.w, acc[r][b]);
+      }
+    }
+  }
+}
+
+template <int R, int BT>
+__device__ __forceinline__ void warp_reduce_all(float (&acc)[R][BT]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[r][b] = warp_sum(acc[r][b]);
+}
+
+// ------------------------------------------------------------------------------------------
+// LSTM cell phase: tasks are hidden units; warp computes the 4 gate rows for a batch tile.
+//   n_cells cells, each with its own weights / x layout in shared memory.
+// ------------------------------------------------------------------------------------------
+struct CellDesc {
+  const float *w_ih, *w_hh, *b_ih, *b_hh;
+  int Kx, Kh, Hn;            // input width, hidden width (recurrent), number of hidden units
+  float* c;                  // [B][Hn]
+  float* h_out;              // [B][Hn]
+  const uint8_t* keep_h;     // replay [B][Hn] slices for this frame or null
+  const uint8_t* keep_c;
+  int mask_id_h, mask_id_c;  // Philox ids
+  unsigned thresh;
+  float scale;
+  int xs_off;                // offset of this cell's x block in shared: [BT][Kx+Kh]
+};
+
+template <int BT>
+__device__ __forceinline__ void lstm_phase(const CellDesc* cells, int n_cells, const float* xs, int b0, int nb,
+                                           int training, unsigned long long seed, int t, int B) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int total = 0;
+  for (int c = 0; c < n_cells; ++c) total += cells[c].Hn;
+  // task i -> CTA (i % grid), warp slot (i / grid): spreads units evenly over SMs
+  for (int slot = warp;; slot += kWarps) {
+    const int task = slot * gridDim.x + blockIdx.x;
+    if (task >= total) break;
+    int ci = 0, j = task;
+    while (j >= cells[ci].Hn) { j -= cells[ci].Hn; ++ci; }
+    const CellDesc& cd = cells[ci];
+    const int ldx = cd.Kx + cd.Kh;
+    const float* x = xs + cd.xs_off;
+    float acc[4][BT];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int b = 0; b < BT; ++b) acc[g][b] = 0.0f;
+    {
+      const float* rows[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rows[g] = cd.w_ih + (size_t)(g * cd.Hn + j) * cd.Kx;
+      warp_dot<4, BT>(rows, x, ldx, cd.Kx >> 2, lane, acc);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rows[g] = cd.w_hh + (size_t)(g * cd.Hn + j) * cd.Kh;
+      warp_dot<4, BT>(rows, x + cd.Kx, ldx, cd.Kh >> 2, lane, acc);
+    }
+    warp_reduce_all<4, BT>(acc);
+    float bias[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bias[g] = cd.b_ih[g * cd.Hn + j] + cd.b_hh[g * cd.Hn + j];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      if (lane == b && b < nb) {
+        const int bb = b0 + b;
+        // nn.LSTMCell: gate order i, f, g, o
+        const float ig = sigmoidf_(acc[0][b] + bias[0]);
+        const float fg = sigmoidf_(acc[1][b] + bias[1]);
+        const float gg = tanhf(acc[2][b] + bias[2]);
+        const float og = sigmoidf_(acc[3][b] + bias[3]);
+        const size_t idx = (size_t)bb * cd.Hn + j;
+        float cn = fg * cd.c[idx] + ig * gg;
+        float hn = og * tanhf(cn);
+        if (training) {  // dropout on h AND c (model.py:341-346, 372-373); the dropped c feeds back
+          hn *= keep_mult(cd.keep_h, idx, seed, cd.mask_id_h, t, (int)idx, cd.thresh, cd.scale);
+          cn *= keep_mult(cd.keep_c, idx, seed, cd.mask_id_c, t, (int)idx, cd.thresh, cd.scale);
+        }
+        cd.c[idx] = cn;
+        cd.h_out[idx] = hn;
+      }
+    }
+  }
+}
+
+// generic "rows x batch-tile" linear phase: out(row, b) = dot(W[row], x_b); epilogue by functor
+template <int BT, typename Epi>
+__device__ __forceinline__ void linear_phase(const float* W, int n_rows, int K, const float* xs, int ldx, int task_base,
+                                             int task_total, Epi epi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int slot = warp;; slot += kWarps) {
+    const int task = slot * gridDim.x + blockIdx.x;  // global task id across the whole phase
+    if (task >= task_total) break;
+    const int row = task - task_base;
+    if (row < 0 || row >= n_rows) continue;
+    float acc[1][BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[0][b] = 0.0f;
+    const float* rows[1] = {W + (size_t)row * K};
+    warp_dot<1, BT>(rows, xs, ldx, K >> 2, lane, acc);
+    warp_reduce_all<1, BT>(acc);
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+      if (lane == b) epi(row, b, acc[0][b]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention task (one CTA per (batch, stream)): energies, probabilities, context.
+// ------------------------------------------------------------------------------------------
+__device__ void attention_task(const Params& p, int s, int b, int t, float* sm) {
+  const StreamParams& sp = p.st[s];
+  const int Ts = sp.Ts, A = p.A, E = p.E;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+  const int len = sp.len ? (int)sp.len[b] : Ts;
+  const int pad = (p.attention == TACO2DEC_ATTN_LSA) ? (p.LK - 1) / 2 : 1;
+  const int Tp = Ts + 2 * pad;
+  // shared layout: 16-byte-aligned fixed-size blocks first, T-dependent scalar arrays last
+  const int E4_ = E >> 2;
+  const int NJ_ = kThreads / E4_ > 0 ? kThreads / E4_ : 1;
+  float* red_s = sm;                                  // max(NJ*E, 64) partial contexts / block-reduce scratch
+  float* q_s = red_s + (NJ_ * E > 64 ? NJ_ * E : 64); // A
+  float* v_s = q_s + A;                               // A
+  float* wd_s = v_s + A;                              // LF*A    : location_dense^T [f][a]   (LSA)
+  float* wc_s = wd_s + p.LF * A;                      // 2*LK*LF : location_conv [c][k][f]   (LSA)
+  float* e_s = wc_s + 2 * p.LK * p.LF;                // Ts : energies -> probabilities
+  float* an_s = e_s + Ts;                             // Ts : new alignment
+  float* ap_s = an_s + Ts;                            // Tp : padded previous alignment
+  float* ac_s = ap_s + Tp;                            // Tp : padded cumulative (LSA)
+
+  for (int i = tid; i < A; i += kThreads) {
+    q_s[i] = __ldcg(p.q + ((size_t)s * p.B + b) * A + i);
+    v_s[i] = sp.v[i];
+  }
+  for (int i = tid; i < Tp; i += kThreads) {
+    const int j = i - pad;
+    const bool in = (j >= 0 && j < Ts);
+    ap_s[i] = in ? __ldcg(sp.a_prev + (size_t)b * Ts + j) : 0.0f;
+    if (p.attention == TACO2DEC_ATTN_LSA) ac_s[i] = in ? __ldcg(sp.a_cum + (size_t)b * Ts + j) : 0.0f;
+  }
+  if (p.attention == TACO2DEC_ATTN_LSA) {
+    for (int i = tid; i < p.LF * A; i += kThreads) {  // dense [A][LF] -> [LF][A]
+      const int f = i / A, a = i - f * A;
+      wd_s[i] = sp.loc_dense[(size_t)a * p.LF + f];
+    }
+    for (int i = tid; i < 2 * p.LK * p.LF; i += kThreads) {  // conv [LF][2][LK] -> [2][LK][LF]
+      const int f = i % p.LF, ck = i / p.LF;
+      wc_s[i] = sp.loc_conv[(size_t)f * 2 * p.LK + ck];
+    }
+  }
+  __syncthreads();
+
+  // ---- energies: one warp per position ----------------------------------------------
+  const float* pm_b = sp.pm + (size_t)b * Ts * A;
+  for (int j = warp; j < Ts; j += kWarps) {
+    float feat = 0.0f;
+    if (p.attention == TACO2DEC_ATTN_LSA) {
+      // location conv (attention.py:12-15,20): lane f computes filter f at position j
+      if (lane < p.LF) {
+        for (int k = 0; k < p.LK; ++k) {
+          feat = fmaf(wc_s[(0 * p.LK + k) * p.LF + lane], ap_s[j + k], feat);
+          feat = fmaf(wc_s[(1 * p.LK + k) * p.LF + lane], ac_s[j + k], feat);
+        }
+      }
+    }
+    float part = 0.0f;
+    for (int a = lane; a < A; a += 32) {
+      float z = q_s[a] + __ldg(pm_b + (size_t)j * A + a);
+      if (p.attention == TACO2DEC_ATTN_LSA) {
+        float loc = 0.0f;  // location dense (attention.py:16-17,22)
+        for (int f = 0; f < p.LF; ++f) loc = fmaf(wd_s[f * A + a], __shfl_sync(0xffffffffu, feat, f), loc);
+        z += loc;
+      }
+      part = fmaf(v_s[a], tanhf(z), part);
+    }
+    part = warp_sum(part);
+    if (lane == 0) e_s[j] = (j >= len) ? -INFINITY : part;  // masked_fill_(mask, -inf), attention.py:79,389
+  }
+  __syncthreads();
+
+  float* align_out = sp.align + ((size_t)b * p.Tcap + t) * Ts;
+  if (p.attention == TACO2DEC_ATTN_SMA) {
+    // p_j = sigmoid(e_j [+ 2 N(0,1)])  (attention.py:340-352)
+    for (int j = tid; j < Ts; j += kThreads) {
+      float e = e_s[j];
+      if (p.training) {
+        const size_t ni = ((size_t)t * p.B + b) * Ts + j;
+        const float nz = sp.noise ? sp.noise[ni] : philox_normal(p.seed, 10 + s, t, b * Ts + j);
+        e = e + nz * 2.0f;
+      }
+      e_s[j] = sigmoidf_(e);
+    }
+    __syncthreads();
+    // alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1})  (attention.py:330-338)
+    for (int j = tid; j < Ts; j += kThreads) {
+      float a = ap_s[pad + j] * e_s[j];
+      if (j > 0) a += ap_s[pad + j - 1] * (1.0f - e_s[j - 1]);
+      if (p.free_running && j >= len) a = 0.0f;  // batched free-running: padded positions do not exist
+      an_s[j] = a;
+      sp.a_prev[(size_t)b * Ts + j] = a;
+      align_out[j] = a;
+    }
+  } else {
+    // softmax over positions (attention.py:81)
+    float m = -INFINITY;
+    for (int j = tid; j < Ts; j += kThreads) m = fmaxf(m, e_s[j]);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    if (lane == 0) red_s[warp] = m;
+    __syncthreads();
+    m = red_s[0];
+    for (int w = 1; w < kWarps; ++w) m = fmaxf(m, red_s[w]);
+    __syncthreads();
+    float sum = 0.0f;
+    for (int j = tid; j < Ts; j += kThreads) {
+      const float ex = expf(e_s[j] - m);
+      e_s[j] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red_s[warp] = sum;
+    __syncthreads();
+    sum = 0.0f;
+    for (int w = 0; w < kWarps; ++w) sum += red_s[w];
+    __syncthreads();
+    for (int j = tid; j < Ts; j += kThreads) {
+      const float a = e_s[j] / sum;
+      an_s[j] = a;
+      sp.a_prev[(size_t)b * Ts + j] = a;
+      sp.a_cum[(size_t)b * Ts + j] = ac_s[pad + j] + a;  // model.py:358-359
+      align_out[j] = a;
+    }
+  }
+  __syncthreads();
+
+  // ---- context = alpha' . memory  (attention.py:82, 395) ------------------------------
+  // thread (jg, d4): float4 feature column d4, positions j = jg (mod NJ); partials reduced in smem
+  const int E4 = E >> 2;
+  const int NJ = kThreads / E4 > 0 ? kThreads / E4 : 1;  // 4 for E=512
+  const float* mem_b = sp.mem + (size_t)b * Ts * E;
+  if (tid < NJ * E4) {
+    const int jg = tid / E4, d4 = tid - jg * E4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int j = jg; j < Ts; j += NJ) {
+      const float a = an_s[j];
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j * E) + d4);
+      acc.x = fmaf(a, m4.x, acc.x);
+      acc.y = fmaf(a, m4.y, acc.y);
+      acc.z = fmaf(a, m4.z, acc.z);
+      acc.w = fmaf(a, m4.w, acc.w);
+    }
+    reinterpret_cast<float4*>(red_s)[jg * E4 + d4] = acc;
+  }
+  __syncthreads();
+  for (int d = tid; d < E; d += kThreads) {
+    float c = 0.0f;
+    for (int jg = 0; jg < NJ; ++jg) c += red_s[jg * E + d];
+    p.ctx[((size_t)s * p.B + b) * E + d] = c;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// The persistent decoder kernel
+// ------------------------------------------------------------------------------------------
+template <int BT>
+__global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int s_flag;
+  __shared__ CellDesc s_cells[3];
+  GridBarrier gb{p.sync_ctr, p.abort_flag, 0u, gridDim.x};
+  const int tid = threadIdx.x;
+  const int gtid = blockIdx.x * kThreads + tid, gthreads = gridDim.x * kThreads;
+  const int B = p.B, S = p.S, H = p.H, D = p.D, E = p.E, P = p.P, A = p.A, M = p.M;
+  const int KA = P + E + H;            // attention-LSTM x block: [prenet | ctx | h]
+  const int KC = S * (H + E) + D;      // decoder-LSTM x block:   [h, ctx, h_bert, ctx_bert | h2]
+  const int KD = D + S * E;            // projection x block:     [h2, ctx, ctx_bert]
+  const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
+
+  // ---- init state (model.py:223-270): zeros; SMA alignment one-hot at 0 ------------------
+  for (int i = gtid; i < 2 * S * B * H; i += gthreads) p.h1[i] = 0.0f;
+  for (int i = gtid; i < S * B * H; i += gthreads) p.c1[i] = 0.0f;
+  for (int i = gtid; i < 2 * B * D; i += gthreads) p.h2[i] = 0.0f;
+  for (int i = gtid; i < B * D; i += gthreads) p.c2[i] = 0.0f;
+  for (int i = gtid; i < S * B * E; i += gthreads) p.ctx[i] = 0.0f;
+  for (int s = 0; s < S; ++s) {
+    const int Ts = p.st[s].Ts;
+    for (int i = gtid; i < B * Ts; i += gthreads) {
+      p.st[s].a_prev[i] = (p.attention == TACO2DEC_ATTN_SMA && (i % Ts) == 0) ? 1.0f : 0.0f;
+      p.st[s].a_cum[i] = 0.0f;
+    }
+  }
+  if (p.free_running) {
+    for (int i = gtid; i < B; i += gthreads) { p.n_frames[i] = 0; p.reached_max[i] = 0; }
+    if (gtid == 0) *p.done_count = 0;
+  }
+  if (!grid_sync(gb, &s_flag)) return;
+
+  const int n_steps = p.free_running ? p.max_steps : p.T;
+  int cur = 0;  // h1/h2 buffer holding the previous frame's hidden state
+  for (int t = 0; t <= n_steps; ++t) {
+    const bool last_tf_tail = (!p.free_running && t == n_steps);  // only the projection of frame T-1 is left
+    if (p.free_running && t == n_steps) break;
+    const int nxt = cur ^ 1;
+
+    // ================= P0 (free-running): prenet on the previous mel (model.py:449-450, 470-471) =====
+    if (p.free_running) {
+      for (int layer = 0; layer < 2; ++layer) {
+        const int K = layer == 0 ? M : P;
+        for (int b0 = 0; b0 < B; b0 += BT) {
+          const int nb = min(BT, B - b0);
+          // x block: layer 0: [BT][M] shared by both streams; layer 1: [S][BT][P]
+          if (layer == 0) {
+            for (int i = tid; i < BT * M; i += kThreads) {
+              const int b = i / M, m = i - b * M;
+              smem[i] = (b < nb && t > 0) ? __ldcg(p.mel + ((size_t)(b0 + b) * p.Tcap + (t - 1)) * M + m) : 0.0f;
+            }
+          } else {
+            for (int i = tid; i < S * BT * P; i += kThreads) {
+              const int s = i / (BT * P), r = i - s * BT * P, b = r / P, k = r - b * P;
+              smem[i] = (b < nb) ? __ldcg(p.st[s].pre0 + (size_t)(b0 + b) * P + k) : 0.0f;
+            }
+          }
+          __syncthreads();
+          for (int s = 0; s < S; ++s) {
+            const StreamParams& sp = p.st[s];
+            const float* W = layer == 0 ? sp.pre_w0 : sp.pre_w1;
+            const uint8_t* keep = layer == 0 ? sp.keep0 : sp.keep1;
+            float* out = layer == 0 ? sp.pre0 : sp.pre;
+            const float* xs = layer == 0 ? smem : smem + (size_t)s * BT * P;
+            auto epi = [&](int row, int b, float v) {
+              if (b >= nb) return;
+              const int bb = b0 + b;
+              const size_t ki = ((size_t)t * B + bb) * P + row;
+              const float mult = keep_mult(keep, ki, p.seed, s * 2 + layer, t, bb * P + row, p.thresh_pre, 2.0f);
+              out[(size_t)bb * P + row] = fmaxf(v, 0.0f) * mult;  // dropout(relu(.), p=0.5, training=True)
+            };
+            linear_phase<BT>(W, P, K, xs, K, s * P, S * P, epi);
+          }
+          __syncthreads();
+        }
+        if (!grid_sync(gb, &s_flag)) return;
+      }
+    }
+
+    // ================= A: attention LSTM cells (+ D of the previous frame when teacher-forced) ========
+    if (!last_tf_tail) {
+      for (int b0 = 0; b0 < B; b0 += BT) {
+        const int nb = min(BT, B - b0);
+        for (int i = tid; i < S * BT * KA; i += kThreads) {
+          const int s = i / (BT * KA), r = i - s * BT * KA, b = r / KA, k = r - b * KA;
+          float v = 0.0f;
+          if (b < nb) {
+            const int bb = b0 + b;
+            if (k < P) {
+              const size_t row = p.free_running ? 0 : (size_t)t * B;
+              v = __ldcg(p.st[s].pre + (row + bb) * P + k);
+            } else if (k < P + E) {
+              v = __ldcg(p.ctx + ((size_t)s * B + bb) * E + (k - P));
+            } else {
+              v = __ldcg(p.h1 + (((size_t)cur * S + s) * B + bb) * H + (k - P - E));
+            }
+          }
+          smem[i] = v;
+        }
+        if (tid < S) {
+          const StreamParams& sp = p.st[tid];
+          CellDesc cd;
+          cd.w_ih = sp.w_ih; cd.w_hh = sp.w_hh; cd.b_ih = sp.b_ih; cd.b_hh = sp.b_hh;
+          cd.Kx = P + E; cd.Kh = H; cd.Hn = H;
+          cd.c = p.c1 + (size_t)tid * B * H;
+          cd.h_out = p.h1 + ((size_t)nxt * S + tid) * B * H;
+          cd.keep_h = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * tid) * B * H : nullptr;
+          cd.keep_c = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * tid + 1) * B * H : nullptr;
+          cd.mask_id_h = 4 + 2 * tid; cd.mask_id_c = 5 + 2 * tid;
+          cd.thresh = p.thresh_att; cd.scale = sc_att;
+          cd.xs_off = tid * BT * KA;
+          s_cells[tid] = cd;
+        }
+        __syncthreads();
+        lstm_phase<BT>(s_cells, S, smem, b0, nb, p.training, p.seed, t, B);
+        __syncthreads();
+      }
+    }
+    if (!p.free_running && t > 0) {
+      // D(t-1): mel / gate projection of the previous frame rides along (no dependency on phase A)
+      for (int b0 = 0; b0 < B; b0 += BT) {
+        const int nb = min(BT, B - b0);
+        for (int i = tid; i < BT * KD; i += kThreads) {
+          const int b = i / KD, k = i - b * KD;
+          float v = 0.0f;
+          if (b < nb) {
+            const int bb = b0 + b;
+            if (k < D) v = __ldcg(p.h2 + ((size_t)cur * B + bb) * D + k);
+            else { const int s = (k - D) / E, d = (k - D) - s * E; v = __ldcg(p.ctx + ((size_t)s * B + bb) * E + d); }
+          }
+          smem[i] = v;
+        }
+        __syncthreads();
+        auto epi_mel = [&](int row, int b, float v) {
+          if (b < nb) p.mel[((size_t)(b0 + b) * p.Tcap + (t - 1)) * M + row] = v + p.proj_b[row];
+        };
+        linear_phase<BT>(p.proj_w, M, KD, smem, KD, 0, M + 1, epi_mel);
+        auto epi_gate = [&](int row, int b, float v) {
+          if (b < nb) p.gate[(size_t)(b0 + b) * p.Tcap + (t - 1)] = v + p.gate_b[0];
+        };
+        linear_phase<BT>(p.gate_w, 1, KD, smem, KD, M, M + 1, epi_gate);
+        __syncthreads();
+      }
+    }
+    if (last_tf_tail) break;
+    if (!grid_sync(gb, &s_flag)) return;
+
+    // ================= Q: query projections (attention.py:56, 368) =================================
+    for (int b0 = 0; b0 < B; b0 += BT) {
+      const int nb = min(BT, B - b0);
+      for (int i = tid; i < S * BT * H; i += kThreads) {
+        const int s = i / (BT * H), r = i - s * BT * H, b = r / H, k = r - b * H;
+        smem[i] = (b < nb) ? __ldcg(p.h1 + (((size_t)nxt * S + s) * B + b0 + b) * H + k) : 0.0f;
+      }
+      __syncthreads();
+      for (int s = 0; s < S; ++s) {
+        auto epi = [&](int row, int b, float v) {
+          if (b < nb) p.q[((size_t)s * B + b0 + b) * A + row] = v;
+        };
+        linear_phase<BT>(p.st[s].wq, A, H, smem + (size_t)s * BT * H, H, s * A, S * A, epi);
+      }
+      __syncthreads();
+    }
+    if (!grid_sync(gb, &s_flag)) return;
+
+    // ================= B: attention (one CTA per (batch, stream)) ==================================
+    for (int task = blockIdx.x; task < S * B; task += gridDim.x) attention_task(p, task % S, task / S, t, smem);
+    if (!grid_sync(gb, &s_flag)) return;
+
+    // ================= C: decoder LSTM cell (model.py:362-373) =====================================
+    for (int b0 = 0; b0 < B; b0 += BT) {
+      const int nb = min(BT, B - b0);
+      for (int i = tid; i < BT * KC; i += kThreads) {
+        const int b = i / KC, k = i - b * KC;
+        float v = 0.0f;
+        if (b < nb) {
+          const int bb = b0 + b;
+          if (k < S * (H + E)) {
+            const int s = k / (H + E), r = k - s * (H + E);
+            v = (r < H) ? __ldcg(p.h1 + (((size_t)nxt * S + s) * B + bb) * H + r)
+                        : __ldcg(p.ctx + ((size_t)s * B + bb) * E + (r - H));
+          } else {
+            v = __ldcg(p.h2 + ((size_t)cur * B + bb) * D + (k - S * (H + E)));
+          }
+        }
+        smem[i] = v;
+      }
+      if (tid == 0) {
+        CellDesc cd;
+        cd.w_ih = p.d_w_ih; cd.w_hh = p.d_w_hh; cd.b_ih = p.d_b_ih; cd.b_hh = p.d_b_hh;
+        cd.Kx = S * (H + E); cd.Kh = D; cd.Hn = D;
+        cd.c = p.c2;
+        cd.h_out = p.h2 + (size_t)nxt * B * D;
+        cd.keep_h = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * B * H : nullptr;
+        cd.keep_c = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * B * H : nullptr;
+        cd.mask_id_h = 8; cd.mask_id_c = 9;
+        cd.thresh = p.thresh_dec; cd.scale = sc_dec;
+        cd.xs_off = 0;
+        s_cells[2] = cd;
+      }
+      __syncthreads();
+      lstm_phase<BT>(&s_cells[2], 1, smem, b0, nb, p.training, p.seed, t, B);
+      __syncthreads();
+    }
+    if (!grid_sync(gb, &s_flag)) return;
+    cur = nxt;
+
+    // ================= D (free-running): projection + stop test (model.py:382-388, 480-485) ========
+    if (p.free_running) {
+      for (int b0 = 0; b0 < B; b0 += BT) {
+        const int nb = min(BT, B - b0);
+        for (int i = tid; i < BT * KD; i += kThreads) {
+          const int b = i / KD, k = i - b * KD;
+          float v = 0.0f;
+          if (b < nb) {
+            const int bb = b0 + b;
+            if (k < D) v = __ldcg(p.h2 + ((size_t)cur * B + bb) * D + k);
+            else { const int s = (k - D) / E, d = (k - D) - s * E; v = __ldcg(p.ctx + ((size_t)s * B + bb) * E + d); }
+          }
+          smem[i] = v;
+        }
+        __syncthreads();
+        auto epi_mel = [&](int row, int b, float v) {
+          if (b < nb) p.mel[((size_t)(b0 + b) * p.Tcap + t) * M + row] = v + p.proj_b[row];
+        };
+        linear_phase<BT>(p.proj_w, M, KD, smem, KD, 0, M + 1, epi_mel);
+        auto epi_gate = [&](int row, int b, float v) {
+          if (b >= nb) return;
+          const int bb = b0 + b;
+          const float g = v + p.gate_b[0];
+          p.gate[(size_t)bb * p.Tcap + t] = g;
+          if (p.n_frames[bb] == 0) {
+            if (sigmoidf_(g) > p.gate_thr) {            // strict >, stop frame kept (model.py:480-481)
+              p.n_frames[bb] = t + 1;
+              atomicAdd(p.done_count, 1);
+            } else if (t + 1 == p.max_steps) {          // model.py:482-485 -> INFER_FLAG = False
+              p.n_frames[bb] = t + 1;
+              p.reached_max[bb] = 1;
+              atomicAdd(p.done_count, 1);
+            }
+          }
+        };
+        linear_phase<BT>(p.gate_w, 1, KD, smem, KD, M, M + 1, epi_gate);
+        __syncthreads();
+      }
+      if (!grid_sync(gb, &s_flag)) return;
+      if (__ldcg(p.done_count) >= B) break;  // uniform: every CTA reads it after the same barrier
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
+// (model.py:412-413).  Warp per output row, same warp_dot as the persistent kernel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) processed_memory_kernel(const float* __restrict__ mem, const float* __restrict__ wm,
+                                                               float* __restrict__ pm, int n_rows, int E, int A) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int n = gw; n < n_rows; n += nw) {
+    const float* x = mem + (size_t)n * E;
+    for (int a = 0; a < A; a += 4) {
+      float acc[4][1] = {{0.f}, {0.f}, {0.f}, {0.f}};
+      const float* rows[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) rows[r] = wm + (size_t)min(a + r, A - 1) * E;
+      warp_dot<4, 1>(rows, x, E, E >> 2, lane, acc);
+      warp_reduce_all<4, 1>(acc);
+      if (lane < 4 && a + lane < A) {
+        float v = lane == 0 ? acc[0][0] : lane == 1 ? acc[1][0] : lane == 2 ? acc[2][0] : acc[3][0];
+        pm[(size_t)n * A + a + lane] = v;
+      }
+    }
+  }
+}
+
+// rows = (T+1)*B frames; frame 0 is the all-zero go-frame (model.py:407-411); frame r>0 reads
+// decoder_inputs[b, :, r-1] (the [B, M, T] layout the reference transposes at model.py:283-287).
+__global__ void __launch_bounds__(256) prenet_tf_kernel(const float* __restrict__ dec_in, const float* __restrict__ w0,
+                                                        const float* __restrict__ w1, const uint8_t* keep0,
+                                                        const uint8_t* keep1, float* __restrict__ out, int B, int T,
+                                                        int M, int P, unsigned long long seed, int stream_id,
+                                                        unsigned thresh) {
+  extern __shared__ __align__(16) float sm[];  // per warp: x[M4] + h0[P]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int Mp = (M + 3) & ~3;
+  float* x = sm + (size_t)warp * (Mp + P);
+  float* h0 = x + Mp;
+  const int n_rows = (T + 1) * B;
+  for (int n = blockIdx.x * wpb + warp; n < n_rows; n += gridDim.x * wpb) {
+    const int r = n / B, b = n - r * B;
+    for (int m = lane; m < Mp; m += 32)
+      x[m] = (r > 0 && m < M) ? dec_in[((size_t)b * M + m) * T + (r - 1)] : 0.0f;
+    __syncwarp();
+    for (int layer = 0; layer < 2; ++layer) {
+      const float* W = layer == 0 ? w0 : w1;
+      const float* in = layer == 0 ? x : h0;
+      const int K = layer == 0 ? M : P;
+      const uint8_t* keep = layer == 0 ? keep0 : keep1;
+      for (int i = 0; i < P; i += 4) {
+        float acc[4][1] = {{0.f}, {0.f}, {0.f}, {0.f}};
+        const float* rows[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rows[q] = W + (size_t)min(i + q, P - 1) * K;
+        warp_dot<4, 1>(rows, in, K, K >> 2, lane, acc);
+        warp_reduce_all<4, 1>(acc);
+        if (lane < 4 && i + lane < P) {
+          float v = lane == 0 ? acc[0][0] : lane == 1 ? acc[1][0] : lane == 2 ? acc[2][0] : acc[3][0];
+          const int col = i + lane;
+          const float mult = keep_mult(keep, (size_t)n * P + col, seed, stream_id * 2 + layer, r, b * P + col, thresh, 2.0f);
+          v = fmaxf(v, 0.0f) * mult;
+          if (layer == 0) h0[col] = v; else out[(size_t)n * P + col] = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void philox_mask_kernel(unsigned long long seed, int mask_id, int rows, int n, unsigned thresh, uint8_t* out) {
+  const size_t total = (size_t)rows * n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / n), idx = (int)(i - (size_t)row * n);
+    out[i] = philox_keep(seed, mask_id, row, idx, thresh) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(TACO2DEC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+unsigned keep_threshold(double p_drop) {
+  double v = p_drop * 4294967296.0;
+  if (v < 0) v = 0;
+  if (v > 4294967295.0) v = 4294967295.0;
+  return (unsigned)v;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WorkspaceLayout {
+  size_t pm[2], pre[2], pre0[2], a_prev[2], a_cum[2], h1, c1, h2, c2, ctx, q, ctl, total;
+};
+
+}  // namespace
+
+struct taco2dec_handle {
+  taco2dec_config cfg;
+  int device;
+  int num_sms;
+  int max_smem_optin;
+  bool have_weights;
+  taco2dec_weights w;
+  int64_t launches;
+  int* last_abort_flag;  // device address of the watchdog flag of the most recent call
+};
+
+namespace {
+
+WorkspaceLayout plan_workspace(const taco2dec_config& c, int B, int T_in, int T_sub, int T, bool tf) {
+  WorkspaceLayout L;
+  size_t off = 0;
+  auto take = [&](size_t n_floats) { size_t o = off; off = align_up(off + n_floats * sizeof(float), 256); return o; };
+  const int Ts[2] = {T_in, T_sub};
+  for (int s = 0; s < 2; ++s) {
+    const bool on = s < c.n_streams;
+    L.pm[s] = take(on ? (size_t)B * Ts[s] * c.attn_dim : 0);
+    L.pre[s] = take(on ? (tf ? (size_t)(T + 1) * B * c.prenet_dim : (size_t)B * c.prenet_dim) : 0);
+    L.pre0[s] = take(on ? (size_t)B * c.prenet_dim : 0);
+    L.a_prev[s] = take(on ? (size_t)B * Ts[s] : 0);
+    L.a_cum[s] = take(on ? (size_t)B * Ts[s] : 0);
+  }
+  L.h1 = take((size_t)2 * c.n_streams * B * c.attn_rnn_dim);
+  L.c1 = take((size_t)c.n_streams * B * c.attn_rnn_dim);
+  L.h2 = take((size_t)2 * B * c.dec_rnn_dim);
+  L.c2 = take((size_t)B * c.dec_rnn_dim);
+  L.ctx = take((size_t)c.n_streams * B * c.enc_dim);
+  L.q = take((size_t)c.n_streams * B * c.attn_dim);
+  L.ctl = take(64);
+  L.total = off;
+  return L;
+}
+
+int pick_bt(int B) { return B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : 8; }
+
+size_t persistent_smem_bytes(const taco2dec_config& c, int BT, int T_in, int T_sub) {
+  const int S = c.n_streams;
+  size_t ka = (size_t)S * BT * (c.prenet_dim + c.enc_dim + c.attn_rnn_dim);
+  size_t kc = (size_t)BT * (S * (c.attn_rnn_dim + c.enc_dim) + c.dec_rnn_dim);
+  size_t kq = (size_t)S * BT * c.attn_rnn_dim;
+  size_t kd = (size_t)BT * (c.dec_rnn_dim + S * c.enc_dim);
+  size_t kp = (size_t)S * BT * std::max(c.prenet_dim, c.n_mel);
+  const int Tm = std::max(T_in, T_sub);
+  const int pad = c.attention == TACO2DEC_ATTN_LSA ? (c.loc_kernel - 1) / 2 : 1;
+  size_t att = (size_t)2 * c.attn_dim + 2 * (size_t)Tm + 2 * (size_t)(Tm + 2 * pad) +
+               (size_t)c.loc_filters * c.attn_dim + 2 * (size_t)c.loc_kernel * c.loc_filters +
+               std::max<size_t>((size_t)(kThreads / (c.enc_dim / 4) > 0 ? kThreads / (c.enc_dim / 4) : 1) * c.enc_dim, 64) + 64;
+  size_t m = std::max({ka, kc, kq, kd, kp, att});
+  return align_up(m * sizeof(float), 16);
+}
+
+template <int BT>
+int launch_persistent(taco2dec_handle* h, const Params& p, size_t smem, cudaStream_t st) {
+  auto kern = decoder_persistent<BT>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) return fail(TACO2DEC_E_STATE, "persistent kernel does not fit on an SM");
+  void* args[] = {(void*)&p};
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(h->num_sms), dim3(kThreads), args, smem, st));
+  h->launches++;
+  return 0;
+}
+
+int check_cfg(const taco2dec_config& c) {
+  if (c.n_streams < 1 || c.n_streams > 2) return fail(TACO2DEC_E_ARG, "n_streams must be 1 or 2");
+  if (c.attention != TACO2DEC_ATTN_SMA && c.attention != TACO2DEC_ATTN_LSA)
+    return fail(TACO2DEC_E_ARG, "attention must be SMA or LSA");
+  const int dims4[] = {c.n_mel, c.enc_dim, c.attn_rnn_dim, c.dec_rnn_dim, c.prenet_dim, c.attn_dim};
+  for (int d : dims4)
+    if (d <= 0 || d % 4) return fail(TACO2DEC_E_ARG, "all feature dims must be positive multiples of 4");
+  if (c.attn_rnn_dim != c.dec_rnn_dim)
+    return fail(TACO2DEC_E_ARG, "attention_rnn_dim must equal decoder_rnn_dim (lstm_keep layout)");
+  if (c.attention == TACO2DEC_ATTN_LSA && (c.loc_filters < 1 || c.loc_filters > 32 || c.loc_kernel % 2 == 0))
+    return fail(TACO2DEC_E_ARG, "LSA needs 1..32 location filters and an odd kernel size");
+  if (c.enc_dim / 4 > kThreads) return fail(TACO2DEC_E_ARG, "encoder_embedding_dim too large");
+  if (c.attn_dim % 32) return fail(TACO2DEC_E_ARG, "attention_dim must be a multiple of 32");
+  if (c.p_attention_dropout < 0 || c.p_attention_dropout >= 1 || c.p_decoder_dropout < 0 || c.p_decoder_dropout >= 1)
+    return fail(TACO2DEC_E_ARG, "dropout probabilities must be in [0,1)");
+  return 0;
+}
+
+int fill_common(taco2dec_handle* h, Params& p, int B, int T_in, int T_sub, const float* memory, const float* embeddings,
+                const int64_t* mlen, const int64_t* blen, const taco2dec_rng& rng, char* ws, const WorkspaceLayout& L) {
+  const taco2dec_config& c = h->cfg;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.S = c.n_streams; p.H = c.attn_rnn_dim; p.D = c.dec_rnn_dim; p.E = c.enc_dim; p.P = c.prenet_dim;
+  p.A = c.attn_dim; p.M = c.n_mel; p.LF = c.attention == TACO2DEC_ATTN_LSA ? c.loc_filters : 0;
+  p.LK = c.attention == TACO2DEC_ATTN_LSA ? c.loc_kernel : 1;
+  p.attention = c.attention;
+  p.p_att = c.p_attention_dropout; p.p_dec = c.p_decoder_dropout;
+  p.thresh_pre = keep_threshold(0.5);
+  p.thresh_att = keep_threshold(c.p_attention_dropout);
+  p.thresh_dec = keep_threshold(c.p_decoder_dropout);
+  p.seed = rng.seed;
+  const int Ts[2] = {T_in, T_sub};
+  const float* mems[2] = {memory, embeddings};
+  const int64_t* lens[2] = {mlen, blen};
+  for (int s = 0; s < c.n_streams; ++s) {
+    const taco2dec_stream_weights& sw = h->w.stream[s];
+    StreamParams& sp = p.st[s];
+    sp.pre_w0 = sw.prenet_w0; sp.pre_w1 = sw.prenet_w1; sp.w_ih = sw.arnn_w_ih; sp.w_hh = sw.arnn_w_hh;
+    sp.b_ih = sw.arnn_b_ih; sp.b_hh = sw.arnn_b_hh; sp.wq = sw.query_w; sp.wm = sw.memory_w; sp.v = sw.v;
+    sp.loc_conv = sw.loc_conv_w; sp.loc_dense = sw.loc_dense_w;
+    sp.mem = mems[s]; sp.len = (const long long*)lens[s]; sp.noise = rng.sma_noise[s];
+    sp.keep0 = rng.prenet_keep[s][0]; sp.keep1 = rng.prenet_keep[s][1];
+    sp.pm = (float*)(ws + L.pm[s]); sp.pre = (float*)(ws + L.pre[s]); sp.pre0 = (float*)(ws + L.pre0[s]);
+    sp.a_prev = (float*)(ws + L.a_prev[s]); sp.a_cum = (float*)(ws + L.a_cum[s]);
+    sp.Ts = Ts[s];
+  }
+  p.d_w_ih = h->w.drnn_w_ih; p.d_w_hh = h->w.drnn_w_hh; p.d_b_ih = h->w.drnn_b_ih; p.d_b_hh = h->w.drnn_b_hh;
+  p.proj_w = h->w.proj_w; p.proj_b = h->w.proj_b; p.gate_w = h->w.gate_w; p.gate_b = h->w.gate_b;
+  p.lstm_keep = rng.lstm_keep;
+  p.h1 = (float*)(ws + L.h1); p.c1 = (float*)(ws + L.c1); p.h2 = (float*)(ws + L.h2); p.c2 = (float*)(ws + L.c2);
+  p.ctx = (float*)(ws + L.ctx); p.q = (float*)(ws + L.q);
+  p.sync_ctr = (unsigned*)(ws + L.ctl);
+  p.abort_flag = (int*)(ws + L.ctl) + 1;
+  p.done_count = (int*)(ws + L.ctl) + 2;
+  return 0;
+}
+
+int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, const WorkspaceLayout& L, cudaStream_t st) {
+  const taco2dec_config& c = h->cfg;
+  // control words: barrier counter, watchdog flag, done counter
+  CUDA_TRY(cudaMemsetAsync(ws + L.ctl, 0, 64 * sizeof(float), st));
+  h->last_abort_flag = p.abort_flag;
+  // processed memory, once per call (model.py:258-261)
+  for (int s = 0; s < c.n_streams; ++s) {
+    const int n_rows = p.B * p.st[s].Ts;
+    const int blocks = std::min((n_rows + 7) / 8, h->num_sms * 8);
+    processed_memory_kernel<<<blocks, 256, 0, st>>>(p.st[s].mem, p.st[s].wm, p.st[s].pm, n_rows, c.enc_dim, c.attn_dim);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  const int BT = pick_bt(p.B);
+  const size_t smem = persistent_smem_bytes(c, BT, T_in, T_sub);
+  if ((int)smem > h->max_smem_optin)
+    return fail(TACO2DEC_E_ARG, "sequence too long for the attention shared-memory plan");
+  switch (BT) {
+    case 1: return launch_persistent<1>(h, p, smem, st);
+    case 2: return launch_persistent<2>(h, p, smem, st);
+    case 4: return launch_persistent<4>(h, p, smem, st);
+    default: return launch_persistent<8>(h, p, smem, st);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int taco2dec_abi_version(void) { return TACO2DEC_ABI_VERSION; }
+const char* taco2dec_last_error(void) { return g_err.c_str(); }
+
+int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** out) {
+  if (!cfg || !out) return fail(TACO2DEC_E_ARG, "null argument");
+  if (int rc = check_cfg(*cfg)) return rc;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(TACO2DEC_E_ARCH, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                     "; this library is built for sm_100a (B200) only and has no fallback");
+  int coop = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (!coop) return fail(TACO2DEC_E_ARCH, "device does not support cooperative launch");
+  taco2dec_handle* h = new (std::nothrow) taco2dec_handle();
+  if (!h) return fail(TACO2DEC_E_STATE, "out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  h->have_weights = false;
+  h->launches = 0;
+  h->last_abort_flag = nullptr;
+  *out = h;
+  return 0;
+}
+
+int taco2dec_destroy(taco2dec_handle* h) {
+  delete h;
+  return 0;
+}
+
+int taco2dec_set_weights(taco2dec_handle* h, const taco2dec_weights* w, void* /*cuda_stream*/) {
+  if (!h || !w) return fail(TACO2DEC_E_ARG, "null argument");
+  auto bad = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
+  for (int s = 0; s < h->cfg.n_streams; ++s) {
+    const taco2dec_stream_weights& sw = w->stream[s];
+    const void* req[] = {sw.prenet_w0, sw.prenet_w1, sw.arnn_w_ih, sw.arnn_w_hh, sw.query_w, sw.memory_w};
+    for (const void* p : req)
+      if (bad(p)) return fail(TACO2DEC_E_ARG, "stream weight pointer is null or not 16-byte aligned");
+    if (!sw.arnn_b_ih || !sw.arnn_b_hh || !sw.v) return fail(TACO2DEC_E_ARG, "stream bias / v pointer is null");
+    if (h->cfg.attention == TACO2DEC_ATTN_LSA && (!sw.loc_conv_w || !sw.loc_dense_w))
+      return fail(TACO2DEC_E_ARG, "LSA needs location conv / dense weights");
+  }
+  const void* req[] = {w->drnn_w_ih, w->drnn_w_hh, w->proj_w, w->gate_w};
+  for (const void* p : req)
+    if (bad(p)) return fail(TACO2DEC_E_ARG, "decoder weight pointer is null or not 16-byte aligned");
+  if (!w->drnn_b_ih || !w->drnn_b_hh || !w->proj_b || !w->gate_b) return fail(TACO2DEC_E_ARG, "bias pointer is null");
+  h->w = *w;
+  h->have_weights = true;
+  return 0;
+}
+
+size_t taco2dec_workspace_bytes(const taco2dec_handle* h, int B, int T_in, int T_sub, int T, int teacher_forced) {
+  if (!h || B < 1 || T_in < 1 || T < 1) return 0;
+  return plan_workspace(h->cfg, B, T_in, std::max(T_sub, 1), T, teacher_forced != 0).total;
+}
+
+int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* a, void* cuda_stream) {
+  if (!h || !a) return fail(TACO2DEC_E_ARG, "null argument");
+  if (!h->have_weights) return fail(TACO2DEC_E_STATE, "weights not set");
+  const taco2dec_config& c = h->cfg;
+  if (a->B < 1 || a->T < 1 || a->T_in < 1 || (c.n_streams == 2 && a->T_sub < 1))
+    return fail(TACO2DEC_E_ARG, "B, T, T_in, T_sub must be >= 1");
+  if (!a->memory || !a->decoder_inputs || !a->mel || !a->gate || !a->align || !a->workspace)
+    return fail(TACO2DEC_E_ARG, "null tensor pointer");
+  if (c.n_streams == 2 && (!a->embeddings || !a->align_bert)) return fail(TACO2DEC_E_ARG, "sub-word stream tensors missing");
+  if ((reinterpret_cast<uintptr_t>(a->memory) & 15u) || (c.n_streams == 2 && (reinterpret_cast<uintptr_t>(a->embeddings) & 15u)))
+    return fail(TACO2DEC_E_ARG, "memory / embeddings must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const WorkspaceLayout L = plan_workspace(c, a->B, a->T_in, std::max(a->T_sub, 1), a->T, true);
+  if (a->workspace_bytes < L.total) return fail(TACO2DEC_E_STATE, "workspace too small");
+  Params p;
+  char* ws = (char*)a->workspace;
+  fill_common(h, p, a->B, a->T_in, a->T_sub, a->memory, a->embeddings, a->memory_lengths, a->bert_lengths, a->rng, ws, L);
+  p.T = a->T; p.Tcap = a->T; p.free_running = 0; p.training = a->training ? 1 : 0; p.max_steps = a->T;
+  p.dec_in = a->decoder_inputs;
+  p.mel = a->mel; p.gate = a->gate;
+  p.st[0].align = a->align;
+  if (c.n_streams == 2) p.st[1].align = a->align_bert;
+  // hoisted prenet over the go-frame + all T targets (model.py:407-413)
+  for (int s = 0; s < c.n_streams; ++s) {
+    const int n_rows = (a->T + 1) * a->B;
+    const int wpb = 8;
+    const int blocks = std::min((n_rows + wpb - 1) / wpb, h->num_sms * 8);
+    const size_t sm = (size_t)wpb * (((c.n_mel + 3) & ~3) + c.prenet_dim) * sizeof(float);
+    prenet_tf_kernel<<<blocks, wpb * 32, sm, st>>>(a->decoder_inputs, h->w.stream[s].prenet_w0, h->w.stream[s].prenet_w1,
+                                                   a->rng.prenet_keep[s][0], a->rng.prenet_keep[s][1], p.st[s].pre, a->B,
+                                                   a->T, c.n_mel, c.prenet_dim, a->rng.seed, s, p.thresh_pre);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return run_common(h, p, a->T_in, std::max(a->T_sub, 1), ws, L, st);
+}
+
+int taco2dec_infer(taco2dec_handle* h, const taco2dec_infer_args* a, void* cuda_stream) {
+  if (!h || !a) return fail(TACO2DEC_E_ARG, "null argument");
+  if (!h->have_weights) return fail(TACO2DEC_E_STATE, "weights not set");
+  const taco2dec_config& c = h->cfg;
+  if (a->B < 1 || a->max_decoder_steps < 1 || a->T_in < 1 || (c.n_streams == 2 && a->T_sub < 1))
+    return fail(TACO2DEC_E_ARG, "B, max_decoder_steps, T_in, T_sub must be >= 1");
+  if (!a->memory || !a->mel || !a->gate || !a->align || !a->n_frames || !a->reached_max || !a->workspace)
+    return fail(TACO2DEC_E_ARG, "null tensor pointer");
+  if (c.n_streams == 2 && (!a->embeddings || !a->align_bert)) return fail(TACO2DEC_E_ARG, "sub-word stream tensors missing");
+  if ((reinterpret_cast<uintptr_t>(a->memory) & 15u) || (c.n_streams == 2 && (reinterpret_cast<uintptr_t>(a->embeddings) & 15u)))
+    return fail(TACO2DEC_E_ARG, "memory / embeddings must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const WorkspaceLayout L = plan_workspace(c, a->B, a->T_in, std::max(a->T_sub, 1), a->max_decoder_steps, false);
+  if (a->workspace_bytes < L.total) return fail(TACO2DEC_E_STATE, "workspace too small");
+  Params p;
+  char* ws = (char*)a->workspace;
+  fill_common(h, p, a->B, a->T_in, a->T_sub, a->memory, a->embeddings, a->memory_lengths, a->bert_lengths, a->rng, ws, L);
+  p.T = a->max_decoder_steps; p.Tcap = a->max_decoder_steps; p.free_running = 1; p.training = 0;
+  p.max_steps = a->max_decoder_steps; p.gate_thr = a->gate_threshold;
+  p.mel = a->mel; p.gate = a->gate;
+  p.st[0].align = a->align;
+  if (c.n_streams == 2) p.st[1].align = a->align_bert;
+  p.n_frames = a->n_frames; p.reached_max = a->reached_max;
+  return run_common(h, p, a->T_in, std::max(a->T_sub, 1), ws, L, st);
+}
+
+int taco2dec_check(taco2dec_handle* h, void* cuda_stream) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null handle");
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  CUDA_TRY(cudaGetLastError());
+  if (h->last_abort_flag) {
+    int flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, h->last_abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return fail(TACO2DEC_E_ABORTED, "persistent decoder kernel aborted: grid barrier watchdog fired");
+  }
+  return 0;
+}
+
+int64_t taco2dec_launch_count(const taco2dec_handle* h) { return h ? h->launches : 0; }
+
+int taco2dec_philox_keep_mask(uint64_t seed, int mask_id, int rows, int n, float p_drop, uint8_t* out, void* cuda_stream) {
+  if (!out || rows < 1 || n < 1) return fail(TACO2DEC_E_ARG, "bad argument");
+  philox_mask_kernel<<<256, 256, 0, (cudaStream_t)cuda_stream>>>(seed, mask_id, rows, n, keep_threshold(p_drop), out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* block, int* smem_bytes) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null handle");
+  if (grid) *grid = h->num_sms;
+  if (block) *block = kThreads;
+  if (smem_bytes) *smem_bytes = (int)persistent_smem_bytes(h->cfg, pick_bt(B), 256, 128);
+  return 0;
+}
+
+}  // extern "C"

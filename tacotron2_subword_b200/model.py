@@ -1,0 +1,521 @@
+"""Drop-in model classes: same constructor arguments, method signatures, hparams fields and
+state_dict layout as /root/reference/model.py -- with the decoder's per-frame loop replaced
+by the persistent sm_100a kernel behind the C ABI (include/taco2dec.h).
+
+  Decoder.forward    <- model.py:392-428      Decoder.inference  <- model.py:430-492
+  BERT_Tacotron2     <- model.py:494-582      Tacotron2 (compat) <- GTA.py:21,57-59 / inference.py:302,334
+
+Encoder / Postnet / embeddings are plain PyTorch exactly as in the reference (out of scope for
+the kernel work); they exist here so the wrapper classes are usable as a drop-in.
+There is no CPU decoder: calling the decoder without the built library or a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from math import sqrt
+from typing import Optional
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _cabi
+from .attention import LSA, SMA, LocationSensitiveAttention, StepwiseMonotonicAttention
+from .layers import ConvNorm, LinearNorm
+from .utils import get_mask_from_lengths, to_gpu
+
+
+class Prenet(nn.Module):
+    """Weights of the 2-layer prenet (model.py:13-24).  ``forward`` is the plain PyTorch
+    definition (dropout p=0.5 always on) for callers that use the module stand-alone; the
+    decoder evaluates it inside the CUDA path."""
+
+    def __init__(self, in_dim, sizes):
+        super().__init__()
+        dims = [in_dim] + list(sizes)
+        self.layers = nn.ModuleList(LinearNorm(a, b, bias=False) for a, b in zip(dims[:-1], dims[1:]))
+
+    def forward(self, x):
+        for lin in self.layers:
+            x = F.dropout(F.relu(lin(x)), p=0.5, training=True)
+        return x
+
+
+class DropoutReplay:
+    """Externally drawn masks for parity runs (see include/taco2dec.h ``taco2dec_rng``).
+    prenet_keep[s][l]: uint8 [rows,B,prenet]; lstm_keep: uint8 [T,6,B,H]; sma_noise[s]: f32 [T,B,T_s]."""
+
+    def __init__(self, prenet_keep=None, lstm_keep=None, sma_noise=None):
+        self.prenet_keep, self.lstm_keep, self.sma_noise = prenet_keep, lstm_keep, sma_noise
+
+    def to(self, device):
+        mv = lambda t, dt: None if t is None else t.to(device=device, dtype=dt).contiguous()
+        pk = None if self.prenet_keep is None else [[mv(m, torch.uint8) for m in row] for row in self.prenet_keep]
+        nz = None if self.sma_noise is None else [mv(n, torch.float32) for n in self.sma_noise]
+        return DropoutReplay(pk, mv(self.lstm_keep, torch.uint8), nz)
+
+
+class _Engine:
+    """One C-ABI handle per (Decoder, device) + a reusable workspace."""
+
+    def __init__(self, cfg: _cabi.Config, device: torch.device):
+        self.lib = _cabi.load_library()
+        self.device = device
+        self.handle = C.c_void_p()
+        _cabi.check(self.lib.taco2dec_create(C.byref(cfg), device.index or 0, C.byref(self.handle)))
+        self.workspace: Optional[torch.Tensor] = None
+
+    def get_workspace(self, B, T_in, T_sub, T, tf) -> torch.Tensor:
+        need = int(self.lib.taco2dec_workspace_bytes(self.handle, B, T_in, T_sub, T, int(tf)))
+        if need == 0:
+            raise _cabi.Taco2DecError("invalid shape for workspace query")
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.workspace
+
+    def launch_count(self) -> int:
+        return int(self.lib.taco2dec_launch_count(self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.taco2dec_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _NoBackward(torch.autograd.Function):
+    """Marks decoder outputs as differentiable so training code fails LOUDLY at backward()
+    instead of silently skipping the decoder: the BPTT kernel is not part of this round."""
+
+    @staticmethod
+    def forward(ctx, anchor, *outs):
+        return tuple(o.view_as(o) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError(
+            "tacotron2_subword_b200: the decoder backward (BPTT) kernel is not implemented yet; "
+            "teacher-forced forward and free-running inference are.")
+
+
+class Decoder(nn.Module):
+    """model.py:128-492.  Same parameters / state_dict; the loop runs on the GPU."""
+
+    def __init__(self, hparams, n_streams: int = 2):
+        super().__init__()
+        hp = hparams
+        self.n_streams = n_streams
+        self.n_mel_channels = hp.n_mel_channels
+        self.n_frames_per_step = hp.n_frames_per_step
+        if self.n_frames_per_step != 1:
+            raise ValueError("only n_frames_per_step == 1 is supported (as in the reference, hparams.py:76)")
+        self.encoder_embedding_dim = hp.encoder_embedding_dim
+        self.attention_rnn_dim = hp.attention_rnn_dim
+        self.decoder_rnn_dim = hp.decoder_rnn_dim
+        self.prenet_dim = hp.prenet_dim
+        self.max_decoder_steps = hp.max_decoder_steps
+        self.gate_threshold = hp.gate_threshold
+        self.p_attention_dropout = hp.p_attention_dropout
+        self.p_decoder_dropout = hp.p_decoder_dropout
+        self.attention_dim = hp.attention_dim
+        self.loc_filters = hp.attention_location_n_filters
+        self.loc_kernel = hp.attention_location_kernel_size
+        self.attention_kind = SMA if hp.attention == SMA else LSA
+        if hp.attention not in (SMA, LSA):
+            # every other choice crashes inside the reference's decode()
+            raise ValueError(f"attention '{hp.attention}' is not runnable in the reference either; use SMA or LSA")
+        att_cls = StepwiseMonotonicAttention if self.attention_kind == SMA else LocationSensitiveAttention
+        sfx = ["", "_bert"][:n_streams]
+        mel_in = hp.n_mel_channels * hp.n_frames_per_step
+        for s in sfx:
+            setattr(self, "prenet" + s, Prenet(mel_in, [hp.prenet_dim, hp.prenet_dim]))
+        for s in sfx:
+            setattr(self, "attention_rnn" + s,
+                    nn.LSTMCell(hp.prenet_dim + hp.encoder_embedding_dim, hp.attention_rnn_dim))
+        for s in sfx:
+            # NB: the reference only builds attention_layer_bert for SMA (model.py:158-191) and
+            # crashes otherwise; building it for LSA too is the fix SURVEY.md 0.4 prescribes.
+            setattr(self, "attention_layer" + s,
+                    att_cls(hp.attention_rnn_dim, hp.encoder_embedding_dim, hp.attention_dim,
+                            hp.attention_location_n_filters, hp.attention_location_kernel_size))
+        self.decoder_rnn = nn.LSTMCell(n_streams * (hp.attention_rnn_dim + hp.encoder_embedding_dim),
+                                       hp.decoder_rnn_dim)
+        if n_streams == 2:
+            # dead in decode() (model.py:375-378) but part of the checkpoint layout
+            self.decoder_rnn_bert = nn.LSTMCell(hp.attention_rnn_dim + hp.encoder_embedding_dim, hp.decoder_rnn_dim)
+        proj_in = hp.decoder_rnn_dim + n_streams * hp.encoder_embedding_dim
+        self.linear_projection = LinearNorm(proj_in, mel_in)
+        self.gate_layer = LinearNorm(proj_in, 1, bias=True, w_init_gain="sigmoid")
+        # -- extensions (not in the reference) --------------------------------------------
+        self.dropout_replay: Optional[DropoutReplay] = None  # parity runs: externally drawn masks
+        self.rng_seed: Optional[int] = None                  # fixed Philox seed; None = fresh per call
+        self.validate_lengths = True
+        self._engines = {}
+
+    # ------------------------------------------------------------------------------------
+    def _sfx(self):
+        return ["", "_bert"][: self.n_streams]
+
+    def _engine(self, device: torch.device) -> _Engine:
+        if device.type != "cuda":
+            raise _cabi.Taco2DecError(
+                "the decoder runs only on a CUDA sm_100 device (no CPU fallback); move the module with .cuda()")
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        eng = self._engines.get(key)
+        if eng is None:
+            cfg = _cabi.Config(self.n_mel_channels, self.encoder_embedding_dim, self.attention_rnn_dim,
+                               self.decoder_rnn_dim, self.prenet_dim, self.attention_dim, self.loc_filters,
+                               self.loc_kernel, _cabi.ATTN_SMA if self.attention_kind == SMA else _cabi.ATTN_LSA,
+                               self.n_streams, float(self.p_attention_dropout), float(self.p_decoder_dropout))
+            eng = _Engine(cfg, torch.device("cuda", key))
+            self._engines[key] = eng
+        return eng
+
+    @staticmethod
+    def _w(t: torch.Tensor) -> torch.Tensor:
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.data_ptr() % 16:
+            raise _cabi.Taco2DecError("decoder parameters must be contiguous, 16-byte aligned fp32")
+        return t
+
+    def _bind_weights(self, eng: _Engine) -> None:
+        w = _cabi.Weights()
+        for i, s in enumerate(self._sfx()):
+            pre, rnn, att = getattr(self, "prenet" + s), getattr(self, "attention_rnn" + s), getattr(self, "attention_layer" + s)
+            sw = w.stream[i]
+            sw.prenet_w0 = _ptr(self._w(pre.layers[0].linear_layer.weight))
+            sw.prenet_w1 = _ptr(self._w(pre.layers[1].linear_layer.weight))
+            sw.arnn_w_ih, sw.arnn_w_hh = _ptr(self._w(rnn.weight_ih)), _ptr(self._w(rnn.weight_hh))
+            sw.arnn_b_ih, sw.arnn_b_hh = _ptr(self._w(rnn.bias_ih)), _ptr(self._w(rnn.bias_hh))
+            sw.query_w = _ptr(self._w(att.query_layer.linear_layer.weight))
+            sw.memory_w = _ptr(self._w(att.memory_layer.linear_layer.weight))
+            sw.v = _ptr(self._w(att.v_weight()))
+            if self.attention_kind == LSA:
+                sw.loc_conv_w = _ptr(self._w(att.location_layer.location_conv.conv.weight))
+                sw.loc_dense_w = _ptr(self._w(att.location_layer.location_dense.linear_layer.weight))
+        w.drnn_w_ih, w.drnn_w_hh = _ptr(self._w(self.decoder_rnn.weight_ih)), _ptr(self._w(self.decoder_rnn.weight_hh))
+        w.drnn_b_ih, w.drnn_b_hh = _ptr(self._w(self.decoder_rnn.bias_ih)), _ptr(self._w(self.decoder_rnn.bias_hh))
+        w.proj_w = _ptr(self._w(self.linear_projection.linear_layer.weight))
+        w.proj_b = _ptr(self._w(self.linear_projection.linear_layer.bias))
+        w.gate_w = _ptr(self._w(self.gate_layer.linear_layer.weight))
+        w.gate_b = _ptr(self._w(self.gate_layer.linear_layer.bias))
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        _cabi.check(eng.lib.taco2dec_set_weights(eng.handle, C.byref(w), C.c_void_p(stream)))
+
+    def _rng(self, device, keepalive: list) -> _cabi.Rng:
+        r = _cabi.Rng()
+        seed = self.rng_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())  # follows torch.manual_seed
+        r.seed = seed
+        rp = self.dropout_replay
+        if rp is not None:
+            rp = rp.to(device)
+            keepalive.append(rp)
+            if rp.prenet_keep is not None:
+                for s in range(self.n_streams):
+                    for l in range(2):
+                        r.prenet_keep[s][l] = rp.prenet_keep[s][l].data_ptr()
+            if rp.lstm_keep is not None:
+                r.lstm_keep = rp.lstm_keep.data_ptr()
+            if rp.sma_noise is not None:
+                for s in range(self.n_streams):
+                    r.sma_noise[s] = rp.sma_noise[s].data_ptr()
+        return r
+
+    def _prep(self, t: Optional[torch.Tensor], device, dtype=torch.float32) -> Optional[torch.Tensor]:
+        if t is None:
+            return None
+        t = t.detach().to(device=device, dtype=dtype, non_blocking=True).contiguous()
+        if t.data_ptr() % 16:
+            t = t.clone()
+        return t
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths=None):
+        """Teacher-forced pass (model.py:392-428).
+
+        memory [B,T_in,E], embeddings [B,T_sub,E], decoder_inputs [B,n_mel,T], lengths int64 [B]
+        -> mel [B,n_mel,T], gate [B,T], alignments [B,T,T_in], alignments_bert [B,T,T_sub]."""
+        dev = self.gate_layer.linear_layer.weight.device
+        eng = self._engine(dev)
+        two = self.n_streams == 2
+        mem = self._prep(memory, dev)
+        emb = self._prep(embeddings, dev) if two else None
+        dec_in = self._prep(decoder_inputs, dev)
+        mlen = self._prep(memory_lengths, dev, torch.int64)
+        blen = self._prep(bert_lengths, dev, torch.int64) if two else None
+        B, T_in, _ = mem.shape
+        T_sub = emb.shape[1] if two else 0
+        T = dec_in.shape[2]
+        if self.validate_lengths:
+            # same host sync as the reference's get_mask_from_lengths (utils.py:11)
+            if mlen is not None and int(mlen.max()) != T_in:
+                raise ValueError("memory.size(1) must equal max(memory_lengths) (utils.py:11, model.py:414)")
+            if blen is not None and int(blen.max()) != T_sub:
+                raise ValueError("embeddings.size(1) must equal max(bert_lengths)")
+        mel = torch.empty(B, T, self.n_mel_channels, device=dev)
+        gate = torch.empty(B, T, device=dev)
+        align = torch.empty(B, T, T_in, device=dev)
+        align_b = torch.empty(B, T, T_sub, device=dev) if two else None
+        ws = eng.get_workspace(B, T_in, T_sub, T, True)
+        keep = []
+        a = _cabi.TFArgs()
+        a.B, a.T, a.T_in, a.T_sub = B, T, T_in, T_sub
+        a.memory, a.embeddings, a.decoder_inputs = _ptr(mem), _ptr(emb), _ptr(dec_in)
+        a.memory_lengths, a.bert_lengths = _ptr(mlen), _ptr(blen)
+        a.training = int(self.training)
+        a.rng = self._rng(dev, keep)
+        a.mel, a.gate, a.align, a.align_bert = _ptr(mel), _ptr(gate), _ptr(align), _ptr(align_b)
+        a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        with torch.cuda.device(dev):
+            self._bind_weights(eng)
+            stream = torch.cuda.current_stream(dev)
+            _cabi.check(eng.lib.taco2dec_forward_teacher_forced(eng.handle, C.byref(a), C.c_void_p(stream.cuda_stream)))
+        outs = (mel.transpose(1, 2), gate, align, align_b)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            live = [o for o in outs if o is not None]
+            marked = list(_NoBackward.apply(self.gate_layer.linear_layer.weight, *live))
+            outs = tuple(marked.pop(0) if o is not None else None for o in outs)
+        return outs
+
+    def inference_batched(self, memory, embeddings, memory_lengths=None, bert_lengths=None,
+                          max_decoder_steps: Optional[int] = None):
+        """B independent free-running utterances in one persistent launch (extension; the
+        reference is batch-1 only, model.py:461,480).  Utterance b is *defined* as its own
+        batch-1 run on ``memory[b, :memory_lengths[b]]``.
+
+        Returns mel [B,n_mel,Tmax], gate [B,Tmax,1], align [B,Tmax,T_in], align_bert, n_frames [B] (int32),
+        reached_max [B] (int32); frames >= n_frames[b] are zeroed (gate there = 1e3 as in parse_output)."""
+        dev = self.gate_layer.linear_layer.weight.device
+        eng = self._engine(dev)
+        two = self.n_streams == 2
+        mem = self._prep(memory, dev)
+        emb = self._prep(embeddings, dev) if two else None
+        mlen = self._prep(memory_lengths, dev, torch.int64)
+        blen = self._prep(bert_lengths, dev, torch.int64) if two else None
+        B, T_in, _ = mem.shape
+        T_sub = emb.shape[1] if two else 0
+        steps = int(max_decoder_steps if max_decoder_steps is not None else self.max_decoder_steps)
+        mel = torch.empty(B, steps, self.n_mel_channels, device=dev)
+        gate = torch.empty(B, steps, device=dev)
+        align = torch.empty(B, steps, T_in, device=dev)
+        align_b = torch.empty(B, steps, T_sub, device=dev) if two else None
+        n_frames = torch.zeros(B, dtype=torch.int32, device=dev)
+        reached = torch.zeros(B, dtype=torch.int32, device=dev)
+        ws = eng.get_workspace(B, T_in, T_sub, steps, False)
+        keep = []
+        a = _cabi.InferArgs()
+        a.B, a.T_in, a.T_sub, a.max_decoder_steps = B, T_in, T_sub, steps
+        a.gate_threshold = float(self.gate_threshold)
+        a.memory, a.embeddings = _ptr(mem), _ptr(emb)
+        a.memory_lengths, a.bert_lengths = _ptr(mlen), _ptr(blen)
+        a.rng = self._rng(dev, keep)
+        a.mel, a.gate, a.align, a.align_bert = _ptr(mel), _ptr(gate), _ptr(align), _ptr(align_b)
+        a.n_frames, a.reached_max = _ptr(n_frames), _ptr(reached)
+        a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        with torch.cuda.device(dev):
+            self._bind_weights(eng)
+            stream = torch.cuda.current_stream(dev)
+            _cabi.check(eng.lib.taco2dec_infer(eng.handle, C.byref(a), C.c_void_p(stream.cuda_stream)))
+        # one device->host read per call (the reference does one per FRAME, model.py:480)
+        nf = n_frames.cpu()
+        _cabi.check(eng.lib.taco2dec_check(eng.handle, C.c_void_p(stream.cuda_stream)))
+        Tmax = int(nf.max())
+        frame_ids = torch.arange(Tmax, device=dev).unsqueeze(0)
+        dead = frame_ids >= n_frames.unsqueeze(1).to(torch.int64)                # [B,Tmax]
+        mel = mel[:, :Tmax].masked_fill(dead.unsqueeze(2), 0.0).transpose(1, 2)
+        gate = gate[:, :Tmax].masked_fill(dead, 1e3).unsqueeze(2)
+        align = align[:, :Tmax].masked_fill(dead.unsqueeze(2), 0.0)
+        if two:
+            align_b = align_b[:, :Tmax].masked_fill(dead.unsqueeze(2), 0.0)
+        return mel, gate, align, align_b, n_frames, reached
+
+    def inference(self, memory, embeddings=None):
+        """Free-running decode (model.py:430-492): mel [B,n_mel,T], gate [B,T,1], alignments,
+        alignments_bert, INFER_FLAG (False when max_decoder_steps was reached)."""
+        if memory.shape[0] != 1:
+            raise ValueError("Decoder.inference is batch-1 as in the reference (model.py:461,480); "
+                             "use inference_batched for B > 1")
+        mel, gate, align, align_b, n_frames, reached = self.inference_batched(memory, embeddings)
+        flag = not bool(int(reached[0]))
+        if not flag:
+            print("Warning! Reached max decoder steps")
+        return mel, gate, align, align_b, flag
+
+
+class Postnet(nn.Module):
+    """model.py:27-70: five conv1d(k=5)+BatchNorm, tanh on all but the last, dropout 0.5 in training."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        hp = hparams
+        n, k, c = hp.postnet_n_convolutions, hp.postnet_kernel_size, hp.postnet_embedding_dim
+        chans = [hp.n_mel_channels] + [c] * (n - 1) + [hp.n_mel_channels]
+        self.convolutions = nn.ModuleList(
+            nn.Sequential(ConvNorm(chans[i], chans[i + 1], kernel_size=k, stride=1, padding=(k - 1) // 2, dilation=1,
+                                   w_init_gain="tanh" if i < n - 1 else "linear"),
+                          nn.BatchNorm1d(chans[i + 1]))
+            for i in range(n))
+
+    def forward(self, x):
+        last = len(self.convolutions) - 1
+        for i, conv in enumerate(self.convolutions):
+            x = conv(x)
+            x = F.dropout(torch.tanh(x) if i < last else x, 0.5, self.training)
+        return x
+
+
+class Encoder(nn.Module):
+    """model.py:73-125: 3x (conv1d k=5 + BatchNorm + ReLU + dropout) then a BiLSTM."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        hp = hparams
+        d, k = hp.encoder_embedding_dim, hp.encoder_kernel_size
+        self.convolutions = nn.ModuleList(
+            nn.Sequential(ConvNorm(d, d, kernel_size=k, stride=1, padding=(k - 1) // 2, dilation=1, w_init_gain="relu"),
+                          nn.BatchNorm1d(d))
+            for _ in range(hp.encoder_n_convolutions))
+        self.lstm = nn.LSTM(d, d // 2, 1, batch_first=True, bidirectional=True)
+
+    def _convs(self, x):
+        for conv in self.convolutions:
+            x = F.dropout(F.relu(conv(x)), 0.5, self.training)
+        return x.transpose(1, 2)
+
+    def forward(self, x, input_lengths):
+        x = self._convs(x)
+        packed = nn.utils.rnn.pack_padded_sequence(x, input_lengths.cpu().numpy(), batch_first=True,
+                                                   enforce_sorted=False)
+        self.lstm.flatten_parameters()
+        out, _ = self.lstm(packed)
+        out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True)
+        return out
+
+    def inference(self, x):
+        x = self._convs(x)
+        self.lstm.flatten_parameters()
+        out, _ = self.lstm(x)
+        return out
+
+
+def _uniform_embedding(n, dim, n_symbols_for_std):
+    emb = nn.Embedding(n, dim)
+    val = sqrt(3.0) * sqrt(2.0 / (n_symbols_for_std + dim))  # model.py:503-506
+    emb.weight.data.uniform_(-val, val)
+    return emb
+
+
+def _mask_outputs(outputs, output_lengths, n_mel, enabled):
+    """model.py:531-541: beyond output_lengths mel(s) <- 0, gate <- 1e3."""
+    if enabled and output_lengths is not None:
+        dead = ~get_mask_from_lengths(output_lengths)
+        outputs[0].data.masked_fill_(dead.unsqueeze(1), 0.0)
+        outputs[1].data.masked_fill_(dead.unsqueeze(1), 0.0)
+        outputs[2].data.masked_fill_(dead, 1e3)
+    return outputs
+
+
+class BERT_Tacotron2(nn.Module):
+    """model.py:494-582 -- dual-stream Tacotron2 (phoneme stream + sub-word stream)."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        hp = hparams
+        self.mask_padding = hp.mask_padding
+        self.fp16_run = hp.fp16_run
+        self.n_mel_channels = hp.n_mel_channels
+        self.n_frames_per_step = hp.n_frames_per_step
+        self.embedding = _uniform_embedding(hp.n_symbols, hp.symbols_embedding_dim, hp.n_symbols)
+        self.embedding_sub = _uniform_embedding(hp.sub_n_symbols, hp.symbols_embedding_dim, hp.n_symbols)
+        self.encoder = Encoder(hp)
+        self.encoder_sub = Encoder(hp)
+        self.linear_converter = LinearNorm(hp.encoder_embedding_dim + hp.BERT_embedding_dim, hp.encoder_embedding_dim)
+        self.linear_converter_sub = LinearNorm(hp.encoder_embedding_dim + hp.BERT_embedding_dim,
+                                               hp.encoder_embedding_dim)
+        self.decoder = Decoder(hp)
+        self.postnet = Postnet(hp)
+
+    def parse_batch(self, batch):
+        (text_padded, input_lengths, input_lengths_bert, mel_padded, gate_padded, output_lengths, embeddings,
+         phoneme_embeddings_cls, bert_embeddings_cls, align_padded) = batch
+        text_padded = to_gpu(text_padded).long()
+        input_lengths = to_gpu(input_lengths).long()
+        input_lengths_bert = to_gpu(input_lengths_bert).long()
+        max_input_len = torch.max(torch.cat((input_lengths, input_lengths_bert), 0).data).item()
+        max_output_len = torch.max(output_lengths.data).item()
+        mel_padded = to_gpu(mel_padded).float()
+        gate_padded = to_gpu(gate_padded).float()
+        output_lengths = to_gpu(output_lengths).long()
+        align_padded = to_gpu(align_padded).float()
+        x = (text_padded, input_lengths, input_lengths_bert, mel_padded, (max_input_len, max_output_len),
+             output_lengths, embeddings, phoneme_embeddings_cls, bert_embeddings_cls)
+        return x, (mel_padded, gate_padded, align_padded)
+
+    def parse_output(self, outputs, output_lengths=None):
+        return _mask_outputs(outputs, output_lengths, self.n_mel_channels, self.mask_padding)
+
+    def _memories(self, text, sub, pcls, bcls, text_lengths=None, bert_lengths=None):
+        e = self.embedding(text).transpose(1, 2)
+        es = self.embedding_sub(sub).transpose(1, 2)
+        if text_lengths is None:
+            enc, enc_s = self.encoder.inference(e), self.encoder_sub.inference(es)
+        else:
+            enc, enc_s = self.encoder(e, text_lengths), self.encoder_sub(es, bert_lengths)
+        mem = self.linear_converter(torch.cat([enc, pcls], 2))          # model.py:548-549
+        mem_s = self.linear_converter_sub(torch.cat([enc_s, bcls], 2))  # model.py:553-554
+        return mem, mem_s
+
+    def forward(self, inputs):
+        (text_inputs, text_lengths, bert_lengths, mels, _max_lens, output_lengths, embeddings,
+         phoneme_embeddings_cls, bert_embeddings_cls) = inputs
+        text_lengths, bert_lengths, output_lengths = text_lengths.data, bert_lengths.data, output_lengths.data
+        mem, mem_s = self._memories(text_inputs, embeddings, phoneme_embeddings_cls, bert_embeddings_cls,
+                                    text_lengths, bert_lengths)
+        mel, gate, align, align_b = self.decoder(mem, mem_s, mels, text_lengths, bert_lengths)   # model.py:556
+        mel_post = mel + self.postnet(mel)
+        return self.parse_output([mel, mel_post, gate, align, align_b], output_lengths)
+
+    def inference(self, inputs, embeddings, phoneme_embeddings_cls, bert_embeddings_cls):
+        mem, mem_s = self._memories(inputs, embeddings, phoneme_embeddings_cls, bert_embeddings_cls)
+        mel, gate, align, align_b, flag = self.decoder.inference(mem, mem_s)                      # model.py:574-575
+        mel_post = mel + self.postnet(mel)
+        return self.parse_output([mel, mel_post, gate, align, align_b, flag])
+
+
+class Tacotron2(nn.Module):
+    """Single-stream compat class for the reference's stale callers (GTA.py:21,57-59;
+    inference.py:302,334; streamlitNews.py:121,150), with the upstream-NVIDIA signature they use:
+    ``forward((text, input_lengths, mel, max_len, output_lengths)) -> (mel, mel_postnet, gate, align)`` and
+    ``inference(sequence) -> (mel, mel_postnet, gate, align)``.  The reference itself defines no such
+    class, so its parity is pinned against the oracle only."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        hp = hparams
+        self.mask_padding = hp.mask_padding
+        self.n_mel_channels = hp.n_mel_channels
+        self.embedding = _uniform_embedding(hp.n_symbols, hp.symbols_embedding_dim, hp.n_symbols)
+        self.encoder = Encoder(hp)
+        self.decoder = Decoder(hp, n_streams=1)
+        self.postnet = Postnet(hp)
+
+    def forward(self, inputs):
+        text, input_lengths, mels, _max_len, output_lengths = inputs
+        input_lengths, output_lengths = input_lengths.data, output_lengths.data
+        mem = self.encoder(self.embedding(text).transpose(1, 2), input_lengths)
+        mel, gate, align, _ = self.decoder(mem, None, mels, input_lengths, None)
+        mel_post = mel + self.postnet(mel)
+        out = _mask_outputs([mel, mel_post, gate, align], output_lengths, self.n_mel_channels, self.mask_padding)
+        return tuple(out)
+
+    def inference(self, sequence):
+        mem = self.encoder.inference(self.embedding(sequence).transpose(1, 2))
+        mel, gate, align, _, _flag = self.decoder.inference(mem, None)
+        mel_post = mel + self.postnet(mel)
+        return mel, mel_post, gate, align

@@ -1,0 +1,214 @@
+"""GPU parity (run with -m gpu on a B200): the CUDA decoder, called through the C ABI,
+against (1) the committed reference goldens and (2) the CPU oracle on seeded inputs.
+
+Tolerances (north_star: teacher-forced mel max-abs <= 1e-3, alignments <= 1e-5, integer
+outputs exact).  The fp32 path is held to a much tighter bound so regressions show."""
+import pytest
+import torch
+
+from oracle.decoder_oracle import DecoderOracle
+from oracle.synth import LSA, SMA, make_decoder_weights, make_dropout_plan, make_inputs
+from tests.gpu_util import make_decoder, replay_of
+from tests.helpers import golden_names, load_golden, materialise, maxabs
+
+pytestmark = pytest.mark.gpu
+
+TOL_MEL = 1e-4     # stated bar 1e-3
+TOL_GATE = 1e-4
+TOL_ALIGN = 1e-5   # stated bar 1e-5
+
+
+def _cmp(got, want, tag=""):
+    names = ("mel", "gate", "align", "align_bert")
+    tols = (TOL_MEL, TOL_GATE, TOL_ALIGN, TOL_ALIGN)
+    for n, t, g, w in zip(names, tols, got, want):
+        if w is None:
+            continue
+        g = g.detach().float().cpu()
+        assert g.shape == w.shape, (tag, n, g.shape, w.shape)
+        assert torch.isfinite(g).all(), (tag, n)
+        d = maxabs(g, w)
+        assert d <= t, (tag, n, d)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_reference_golden(name):
+    recipe, gold, _ = load_golden(name)
+    w, inp, plan = materialise(recipe)
+    dec = make_decoder(w, recipe["attention"])
+    dec.dropout_replay = replay_of(plan)
+    want = (gold["mel"], gold["gate"], gold["align"], gold["align_bert"])
+    with torch.no_grad():
+        if recipe["mode"] == "tf":
+            dec.train(recipe["training"])
+            got = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(),
+                      inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+            _cmp(got, want, name)
+        else:
+            dec.eval()
+            dec.max_decoder_steps = recipe["max_steps"]
+            mel, gate, al, alb, flag = dec.inference(inp["memory"].cuda(), inp["embeddings"].cuda())
+            assert mel.shape[2] == int(gold["n_frames"]), "stop frame must match exactly"
+            assert int(flag) == int(gold["flag"]), "INFER_FLAG must match exactly"
+            _cmp((mel, gate, al, alb), want, name)
+
+
+@pytest.mark.parametrize("attention", [SMA, LSA])
+@pytest.mark.parametrize("B,training", [(1, False), (2, True), (5, False), (9, True)])
+def test_cuda_teacher_forced_vs_oracle(attention, B, training):
+    """Batch tiles 1/2/8 and the B > 8 multi-tile path, ragged lengths, eval and train."""
+    T_in, T_sub, T, seed = 31, 11, 7, 100 + B
+    w = make_decoder_weights(attention, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=True)
+    plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, training, seed=seed + 1)
+    want = DecoderOracle(w, attention).forward(inp["memory"], inp["embeddings"], inp["mels"], inp["memory_lengths"],
+                                               inp["bert_lengths"], plan, training=training)
+    dec = make_decoder(w, attention)
+    dec.dropout_replay = replay_of(plan)
+    dec.train(training)
+    with torch.no_grad():
+        got = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(),
+                  inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+    _cmp(got, want, f"{attention} B={B}")
+    # alignment invariants: SMA rows are a sub-probability vector, LSA rows sum to 1
+    rows = got[2].float().cpu().sum(-1)
+    if attention == LSA:
+        assert float((rows - 1).abs().max()) < 1e-5
+    else:
+        assert float(rows.max()) <= 1 + 1e-5 and float(got[2].min()) >= 0.0
+
+
+@pytest.mark.parametrize("attention", [SMA, LSA])
+def test_cuda_batched_free_running_vs_oracle(attention):
+    """B independent utterances with ragged memory lengths: each equals its batch-1 oracle run;
+    stop indices / reached-max flags exact."""
+    B, T_in, T_sub, steps, seed = 3, 19, 7, 12, 21
+    w = make_decoder_weights(attention, seed=seed, gate_bias=-20.0)
+    inp = make_inputs(B, T_in, T_sub, 1, seed=seed, ragged=True)
+    plan = make_dropout_plan(B, steps, steps, T_in, T_sub, False, seed=seed + 1)
+    outs = DecoderOracle(w, attention).inference_batched(inp["memory"], inp["embeddings"], inp["memory_lengths"],
+                                                         inp["bert_lengths"], plan, max_decoder_steps=steps)
+    dec = make_decoder(w, attention).eval()
+    dec.dropout_replay = replay_of(plan)
+    with torch.no_grad():
+        mel, gate, al, alb, nf, reached = dec.inference_batched(inp["memory"].cuda(), inp["embeddings"].cuda(),
+                                                                inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda(),
+                                                                max_decoder_steps=steps)
+    for b, (omel, ogate, oal, oalb, oflag) in enumerate(outs):
+        n = omel.shape[2]
+        assert int(nf[b]) == n and bool(reached[b]) == (not oflag)
+        Lm, Lb = int(inp["memory_lengths"][b]), int(inp["bert_lengths"][b])
+        _cmp((mel[b:b + 1, :, :n], gate[b:b + 1, :n], al[b:b + 1, :n, :Lm], alb[b:b + 1, :n, :Lb]),
+             (omel, ogate, oal, oalb), f"utt {b}")
+        assert float(al[b, :n, Lm:].abs().max() if Lm < T_in else 0.0) == 0.0   # padded positions do not exist
+
+
+def test_cuda_single_stream_compat_vs_oracle():
+    """Tacotron2 compat decoder (1 stream, LSA as in upstream NVIDIA Tacotron2)."""
+    from oracle.synth import DecoderDims
+    dims = DecoderDims(streams=1)
+    B, T_in, T, seed = 2, 27, 6, 5
+    w = make_decoder_weights(LSA, seed=seed, dims=dims)
+    inp = make_inputs(B, T_in, 1, T, seed=seed, ragged=True, dims=dims)
+    plan = make_dropout_plan(B, T + 1, T, T_in, 1, False, seed=seed + 1, dims=dims)
+    want = DecoderOracle(w, LSA, dims=dims).forward(inp["memory"], None, inp["mels"], inp["memory_lengths"], None, plan)
+    dec = make_decoder(w, LSA, n_streams=1).eval()
+    dec.dropout_replay = replay_of(plan)
+    with torch.no_grad():
+        got = dec(inp["memory"].cuda(), None, inp["mels"].cuda(), inp["memory_lengths"].cuda(), None)
+    _cmp(got, want, "single-stream")
+
+
+def test_teacher_forcing_own_output_reproduces_free_run():
+    """Size-independent property at BASELINE cfg-2 scale (B=1, 150 phones / 50 sub-words, 1000 steps,
+    gate bias -20): feeding the free-running mels back as teacher-forcing targets with the same
+    prenet masks must reproduce the free run; never-stopping run hits max_decoder_steps exactly."""
+    T_in, T_sub, steps, seed = 150, 50, 1000, 1234
+    w = make_decoder_weights(SMA, seed=seed, gate_bias=-20.0)
+    inp = make_inputs(1, T_in, T_sub, 1, seed=seed)
+    plan = make_dropout_plan(1, steps + 1, steps, T_in, T_sub, False, seed=seed + 1)
+    dec = make_decoder(w, SMA).eval()
+    dec.dropout_replay = replay_of(plan)
+    with torch.no_grad():
+        mel, gate, al, alb, flag = dec.inference(inp["memory"].cuda(), inp["embeddings"].cuda())
+        assert mel.shape == (1, 80, steps) and flag is False
+        assert torch.isfinite(mel).all()
+        tf = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), mel.contiguous(),
+                 torch.tensor([T_in]).cuda(), torch.tensor([T_sub]).cuda())
+    assert maxabs(tf[0].cpu(), mel.cpu()) <= 1e-5
+    assert maxabs(tf[1].cpu(), gate.squeeze(2).cpu()) <= 1e-5
+    assert maxabs(tf[2].cpu(), al.cpu()) <= 1e-6
+    # SMA mass only moves forward / leaks: row sums are non-increasing over time
+    rows = al[0].sum(-1).cpu()
+    assert float((rows[1:] - rows[:-1]).max()) <= 1e-5
+    # first 60 frames against the CPU oracle (the full 1000-frame oracle run is bench.py's cpu_baseline)
+    plan60 = make_dropout_plan(1, steps + 1, steps, T_in, T_sub, False, seed=seed + 1)
+    omel, ogate, oal, oalb, oflag = DecoderOracle(w, SMA).inference(inp["memory"], inp["embeddings"], plan60,
+                                                                    max_decoder_steps=60)
+    _cmp((mel[:, :, :60], gate[:, :60], al[:, :60], alb[:, :60]), (omel, ogate, oal, oalb), "cfg2 head")
+
+
+def test_philox_production_masks_equal_replay():
+    """Production mode draws dropout masks in-kernel (Philox); replaying the same masks through
+    the parity interface must give bit-identical outputs, and the masks must be Bernoulli(0.5)."""
+    import ctypes as C
+    from tacotron2_subword_b200 import DropoutReplay, _cabi
+    T_in, T_sub, steps, seed = 14, 5, 9, 77
+    w = make_decoder_weights(SMA, seed=3, gate_bias=-20.0)
+    inp = make_inputs(2, T_in, T_sub, 1, seed=3)
+    dec = make_decoder(w, SMA).eval()
+    dec.rng_seed = seed
+    dec.max_decoder_steps = steps
+    with torch.no_grad():
+        a = dec.inference_batched(inp["memory"].cuda(), inp["embeddings"].cuda())
+    lib = _cabi.load_library()
+    masks = [[torch.empty(steps, 2, 256, dtype=torch.uint8, device="cuda") for _ in range(2)] for _ in range(2)]
+    for s in range(2):
+        for l in range(2):
+            _cabi.check(lib.taco2dec_philox_keep_mask(seed, s * 2 + l, steps, 2 * 256, 0.5,
+                                                      C.c_void_p(masks[s][l].data_ptr()),
+                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    big = torch.empty(4096, 4096, dtype=torch.uint8, device="cuda")
+    _cabi.check(lib.taco2dec_philox_keep_mask(seed, 0, 4096, 4096, 0.5, C.c_void_p(big.data_ptr()),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    rate = float(big.float().mean())
+    assert abs(rate - 0.5) < 1e-3, rate
+    dec.dropout_replay = DropoutReplay(prenet_keep=masks)
+    with torch.no_grad():
+        b = dec.inference_batched(inp["memory"].cuda(), inp["embeddings"].cuda())
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    # a different seed gives a different trajectory
+    dec.dropout_replay = None
+    dec.rng_seed = seed + 1
+    with torch.no_grad():
+        c = dec.inference_batched(inp["memory"].cuda(), inp["embeddings"].cuda())
+    assert not torch.equal(a[0], c[0])
+
+
+def test_model_wrapper_forward_and_inference_shapes():
+    """BERT_Tacotron2 drop-in: forward (9-tuple input, 5 outputs, padded outputs masked exactly)
+    and batch-1 inference (6 outputs) run end to end on the GPU decoder."""
+    from tacotron2_subword_b200 import BERT_Tacotron2, create_hparams
+    torch.manual_seed(1234)
+    hp = create_hparams()
+    model = BERT_Tacotron2(hp).cuda().eval()
+    B, T_in, T_sub, T = 2, 13, 5, 9
+    text = torch.randint(0, hp.n_symbols, (B, T_in)).cuda()
+    sub = torch.randint(0, hp.sub_n_symbols, (B, T_sub)).cuda()
+    in_len = torch.tensor([T_in, T_in - 3]).cuda()
+    sub_len = torch.tensor([T_sub, T_sub - 1]).cuda()
+    out_len = torch.tensor([T, T - 4]).cuda()
+    mels = torch.randn(B, 80, T).cuda()
+    pcls = torch.randn(B, T_in, hp.BERT_embedding_dim).cuda()
+    bcls = torch.randn(B, T_sub, hp.BERT_embedding_dim).cuda()
+    with torch.no_grad():
+        mel, mel_post, gate, al, alb = model((text, in_len, sub_len, mels, (T_in, T), out_len, sub, pcls, bcls))
+    assert mel.shape == (B, 80, T) and mel_post.shape == (B, 80, T) and gate.shape == (B, T)
+    assert al.shape == (B, T, T_in) and alb.shape == (B, T, T_sub)
+    assert float(mel[1, :, T - 4:].abs().max()) == 0.0 and float(mel_post[1, :, T - 4:].abs().max()) == 0.0
+    assert gate[1, T - 4:].tolist() == [1e3] * 4                      # model.py:539, exact
+    model.decoder.max_decoder_steps = 7
+    with torch.no_grad():
+        outs = model.inference(text[:1], sub[:1], pcls[:1], bcls[:1])
+    assert len(outs) == 6 and outs[0].shape[1] == 80 and outs[2].shape[2] == 1
