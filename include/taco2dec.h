@@ -173,6 +173,17 @@ int64_t taco2dec_launch_count(const taco2dec_handle* h);
 int taco2dec_philox_keep_mask(uint64_t seed, int mask_id, int rows, int n, float p_drop, uint8_t* out,
                               void* cuda_stream);
 
+/* Optional: record CUDA events on the launching stream around the persistent decoder kernel
+ * (only that kernel, not the one-off prologue kernels); taco2dec_last_kernel_ms waits for the
+ * most recent profiled launch and returns its device duration. */
+int taco2dec_set_profiling(taco2dec_handle* h, int on);
+int taco2dec_last_kernel_ms(taco2dec_handle* h, float* ms);
+
+/* Diagnostics: SM-clock cycles CTA 0 spent in each phase of the most recent persistent launch.
+ * out16_host[2k] = work of phase k, [2k+1] = the grid barrier after it, k = P0a,P0b,A,Q,B,C,D;
+ * [15] = state init + first barrier.  Synchronises the stream. */
+int taco2dec_read_phase_clocks(taco2dec_handle* h, void* cuda_stream, long long* out16_host);
+
 /* Persistent-kernel launch geometry actually used (for DESIGN.md / bench bookkeeping). */
 int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* block, int* smem_bytes);
 

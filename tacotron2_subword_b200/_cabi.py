@@ -20,7 +20,8 @@ EXPORTED_SYMBOLS = (
     "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
     "taco2dec_set_weights", "taco2dec_workspace_bytes", "taco2dec_forward_teacher_forced",
     "taco2dec_infer", "taco2dec_check", "taco2dec_launch_count", "taco2dec_philox_keep_mask",
-    "taco2dec_launch_geometry",
+    "taco2dec_launch_geometry", "taco2dec_set_profiling", "taco2dec_last_kernel_ms",
+    "taco2dec_read_phase_clocks",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -105,6 +106,12 @@ def load_library() -> C.CDLL:
     lib.taco2dec_philox_keep_mask.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
     lib.taco2dec_launch_geometry.restype = C.c_int
     lib.taco2dec_launch_geometry.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.taco2dec_set_profiling.restype = C.c_int
+    lib.taco2dec_set_profiling.argtypes = [H, C.c_int]
+    lib.taco2dec_last_kernel_ms.restype = C.c_int
+    lib.taco2dec_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float)]
+    lib.taco2dec_read_phase_clocks.restype = C.c_int
+    lib.taco2dec_read_phase_clocks.argtypes = [H, C.c_void_p, C.POINTER(C.c_longlong)]
     if lib.taco2dec_abi_version() != ABI_VERSION:
         raise Taco2DecError("libtaco2dec.so ABI version mismatch; rebuild")
     _lib = lib

@@ -76,6 +76,7 @@ struct Params {
   unsigned* sync_ctr;        // grid barrier counter (zeroed by the host before launch)
   int* abort_flag;           // watchdog
   int* done_count;           // free-running: utterances that have stopped
+  long long* phase_clocks;   // [16] SM-clock cycles CTA 0 spent per phase / per barrier (diagnostics)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -470,6 +471,16 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
   extern __shared__ __align__(16) float smem[];
   __shared__ int s_flag;
   __shared__ CellDesc s_cells[3];
+  __shared__ long long s_ph[16];
+  long long ph_t = clock64();
+  if (threadIdx.x < 16) s_ph[threadIdx.x] = 0;
+  // slot 2k = work of phase k, 2k+1 = the grid barrier that follows it (P0a,P0b,A,Q,B,C,D = k 0..6)
+#define PH_MARK(slot)                                             \
+  if (blockIdx.x == 0 && threadIdx.x == 0) {                      \
+    const long long n_ = clock64();                               \
+    s_ph[slot] += n_ - ph_t;                                      \
+    ph_t = n_;                                                    \
+  }
   GridBarrier gb{p.sync_ctr, p.abort_flag, 0u, gridDim.x};
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * kThreads + tid, gthreads = gridDim.x * kThreads;
@@ -497,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
     if (gtid == 0) *p.done_count = 0;
   }
   if (!grid_sync(gb, &s_flag)) return;
+  PH_MARK(15)
 
   const int n_steps = p.free_running ? p.max_steps : p.T;
   int cur = 0;  // h1/h2 buffer holding the previous frame's hidden state
@@ -541,7 +553,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
           }
           __syncthreads();
         }
+        PH_MARK(2 * layer)
         if (!grid_sync(gb, &s_flag)) return;
+        PH_MARK(2 * layer + 1)
       }
     }
 
@@ -611,7 +625,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
       }
     }
     if (last_tf_tail) break;
+    PH_MARK(4)
     if (!grid_sync(gb, &s_flag)) return;
+    PH_MARK(5)
 
     // ================= Q: query projections (attention.py:56, 368) =================================
     for (int b0 = 0; b0 < B; b0 += BT) {
@@ -629,11 +645,15 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
       }
       __syncthreads();
     }
+    PH_MARK(6)
     if (!grid_sync(gb, &s_flag)) return;
+    PH_MARK(7)
 
     // ================= B: attention (one CTA per (batch, stream)) ==================================
     for (int task = blockIdx.x; task < S * B; task += gridDim.x) attention_task(p, task % S, task / S, t, smem);
+    PH_MARK(8)
     if (!grid_sync(gb, &s_flag)) return;
+    PH_MARK(9)
 
     // ================= C: decoder LSTM cell (model.py:362-373) =====================================
     for (int b0 = 0; b0 < B; b0 += BT) {
@@ -670,7 +690,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
       lstm_phase<BT>(&s_cells[2], 1, smem, b0, nb, p.training, p.seed, t, B);
       __syncthreads();
     }
+    PH_MARK(10)
     if (!grid_sync(gb, &s_flag)) return;
+    PH_MARK(11)
     cur = nxt;
 
     // ================= D (free-running): projection + stop test (model.py:382-388, 480-485) ========
@@ -711,10 +733,15 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
         linear_phase<BT>(p.gate_w, 1, KD, smem, KD, M, M + 1, epi_gate);
         __syncthreads();
       }
+      PH_MARK(12)
       if (!grid_sync(gb, &s_flag)) return;
+      PH_MARK(13)
       if (__ldcg(p.done_count) >= B) break;  // uniform: every CTA reads it after the same barrier
     }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int i = 0; i < 16; ++i) p.phase_clocks[i] = s_ph[i];
+#undef PH_MARK
 }
 
 // ------------------------------------------------------------------------------------------
@@ -829,6 +856,10 @@ struct taco2dec_handle {
   taco2dec_weights w;
   int64_t launches;
   int* last_abort_flag;  // device address of the watchdog flag of the most recent call
+  long long* last_phase_clocks;
+  bool profiling;        // record CUDA events around the persistent launch
+  cudaEvent_t ev0, ev1;
+  bool ev_valid;
 };
 
 namespace {
@@ -883,7 +914,9 @@ int launch_persistent(taco2dec_handle* h, const Params& p, size_t smem, cudaStre
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   if (per_sm < 1) return fail(TACO2DEC_E_STATE, "persistent kernel does not fit on an SM");
   void* args[] = {(void*)&p};
+  if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0, st));
   CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(h->num_sms), dim3(kThreads), args, smem, st));
+  if (h->profiling) { CUDA_TRY(cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
   h->launches++;
   return 0;
 }
@@ -942,6 +975,7 @@ int fill_common(taco2dec_handle* h, Params& p, int B, int T_in, int T_sub, const
   p.sync_ctr = (unsigned*)(ws + L.ctl);
   p.abort_flag = (int*)(ws + L.ctl) + 1;
   p.done_count = (int*)(ws + L.ctl) + 2;
+  p.phase_clocks = (long long*)(ws + L.ctl + 64);
   return 0;
 }
 
@@ -950,6 +984,7 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
   // control words: barrier counter, watchdog flag, done counter
   CUDA_TRY(cudaMemsetAsync(ws + L.ctl, 0, 64 * sizeof(float), st));
   h->last_abort_flag = p.abort_flag;
+  h->last_phase_clocks = p.phase_clocks;
   // processed memory, once per call (model.py:258-261)
   for (int s = 0; s < c.n_streams; ++s) {
     const int n_rows = p.B * p.st[s].Ts;
@@ -997,12 +1032,44 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   h->have_weights = false;
   h->launches = 0;
   h->last_abort_flag = nullptr;
+  h->last_phase_clocks = nullptr;
+  h->profiling = false;
+  h->ev_valid = false;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
   *out = h;
   return 0;
 }
 
 int taco2dec_destroy(taco2dec_handle* h) {
+  if (h) {
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+  }
   delete h;
+  return 0;
+}
+
+int taco2dec_read_phase_clocks(taco2dec_handle* h, void* cuda_stream, long long* out16_host) {
+  if (!h || !out16_host) return fail(TACO2DEC_E_ARG, "null argument");
+  if (!h->last_phase_clocks) return fail(TACO2DEC_E_STATE, "no launch recorded");
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  CUDA_TRY(cudaMemcpy(out16_host, h->last_phase_clocks, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int taco2dec_set_profiling(taco2dec_handle* h, int on) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null handle");
+  h->profiling = on != 0;
+  return 0;
+}
+
+int taco2dec_last_kernel_ms(taco2dec_handle* h, float* ms) {
+  if (!h || !ms) return fail(TACO2DEC_E_ARG, "null argument");
+  if (!h->ev_valid) return fail(TACO2DEC_E_STATE, "no profiled launch recorded");
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return 0;
 }
 

@@ -76,6 +76,20 @@ class _Engine:
     def launch_count(self) -> int:
         return int(self.lib.taco2dec_launch_count(self.handle))
 
+    def set_profiling(self, on: bool) -> None:
+        _cabi.check(self.lib.taco2dec_set_profiling(self.handle, int(on)))
+
+    def phase_clocks(self):
+        buf = (C.c_longlong * 16)()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _cabi.check(self.lib.taco2dec_read_phase_clocks(self.handle, C.c_void_p(stream), buf))
+        return list(buf)
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        _cabi.check(self.lib.taco2dec_last_kernel_ms(self.handle, C.byref(ms)))
+        return float(ms.value)
+
     def __del__(self):
         try:
             if self.handle:
