@@ -44,6 +44,14 @@ extern "C" {
 #define TACO2DEC_E_STATE (-4)   /* weights not set, workspace too small, ... */
 #define TACO2DEC_E_ABORTED (-5) /* in-kernel watchdog fired (grid barrier timeout) */
 
+/* Kernel family selection (taco2dec_set_mode).  AUTO = latency path when eligible (B == 1, SMA,
+ * default decoder dims), else the generic any-shape path. */
+#define TACO2DEC_PATH_AUTO 0
+#define TACO2DEC_PATH_GENERIC 1 /* grid-barrier persistent kernel, fp32 weights in PyTorch layout, any B / SMA+LSA */
+#define TACO2DEC_PATH_LATENCY 2 /* role-specialised persistent kernel, TMA-streamed packed weights (batch 1) */
+#define TACO2DEC_W_FP32 0       /* packed LSTM weights stay fp32 (parity ~1e-6)                           */
+#define TACO2DEC_W_FP16 1       /* the three LSTM matrices stored fp16, fp32 accumulate (parity ~5e-5)   */
+
 typedef struct taco2dec_handle taco2dec_handle;
 
 /* hparams.py fields the decoder reads (model.py:131-140, 158-207). */
@@ -172,6 +180,11 @@ int64_t taco2dec_launch_count(const taco2dec_handle* h);
  * mask_id (prenet: stream*2+layer; lstm: 4+k) -- lets tests replay production masks. */
 int taco2dec_philox_keep_mask(uint64_t seed, int mask_id, int rows, int n, float p_drop, uint8_t* out,
                               void* cuda_stream);
+
+/* Select the kernel family and the storage type of the packed LSTM weights (latency path). */
+int taco2dec_set_mode(taco2dec_handle* h, int path, int weight_dtype);
+/* TACO2DEC_PATH_GENERIC or TACO2DEC_PATH_LATENCY: the path the most recent call actually took. */
+int taco2dec_last_path(const taco2dec_handle* h);
 
 /* Optional: record CUDA events on the launching stream around the persistent decoder kernel
  * (only that kernel, not the one-off prologue kernels); taco2dec_last_kernel_ms waits for the

@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtaco2dec.so")
 
 ATTN_SMA, ATTN_LSA = 0, 1
+PATH_AUTO, PATH_GENERIC, PATH_LATENCY = 0, 1, 2
+W_FP32, W_FP16 = 0, 1
 ABI_VERSION = 1
 
 EXPORTED_SYMBOLS = (
@@ -21,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "taco2dec_set_weights", "taco2dec_workspace_bytes", "taco2dec_forward_teacher_forced",
     "taco2dec_infer", "taco2dec_check", "taco2dec_launch_count", "taco2dec_philox_keep_mask",
     "taco2dec_launch_geometry", "taco2dec_set_profiling", "taco2dec_last_kernel_ms",
-    "taco2dec_read_phase_clocks",
+    "taco2dec_read_phase_clocks", "taco2dec_set_mode", "taco2dec_last_path",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -110,6 +112,10 @@ def load_library() -> C.CDLL:
     lib.taco2dec_set_profiling.argtypes = [H, C.c_int]
     lib.taco2dec_last_kernel_ms.restype = C.c_int
     lib.taco2dec_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float)]
+    lib.taco2dec_set_mode.restype = C.c_int
+    lib.taco2dec_set_mode.argtypes = [H, C.c_int, C.c_int]
+    lib.taco2dec_last_path.restype = C.c_int
+    lib.taco2dec_last_path.argtypes = [H]
     lib.taco2dec_read_phase_clocks.restype = C.c_int
     lib.taco2dec_read_phase_clocks.argtypes = [H, C.c_void_p, C.POINTER(C.c_longlong)]
     if lib.taco2dec_abi_version() != ABI_VERSION:

@@ -20,6 +20,7 @@
 //
 // No CPU fallback, no multi-backend dispatch: the host API refuses non-sm_100 devices.
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -28,6 +29,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "taco2dec.h"
 
@@ -140,6 +142,12 @@ __device__ __forceinline__ float keep_mult(const uint8_t* replay, size_t replay_
   bool k = replay ? (replay[replay_index] != 0) : philox_keep(seed, mask_id, row, idx, thresh);
   return k ? scale : 0.0f;
 }
+
+}  // namespace
+namespace {
+#include "latency.cuh"
+}  // namespace
+namespace {
 
 // ------------------------------------------------------------------------------------------
 // Grid barrier (all CTAs co-resident: cooperative launch).  Monotonic counter; thread 0 of
@@ -857,6 +865,15 @@ struct taco2dec_handle {
   int64_t launches;
   int* last_abort_flag;  // device address of the watchdog flag of the most recent call
   long long* last_phase_clocks;
+  int path_mode;         // TACO2DEC_PATH_*
+  int weight_dtype;      // TACO2DEC_W_*
+  unsigned char* packed; // latency path: per-LSTM-CTA packed weight streams (library-owned)
+  size_t packed_bytes;
+  int packed_wbytes;     // 0 = not packed yet
+  unsigned long long* packed_off;  // device [NL+1]
+  unsigned long long* ll_buf;      // latency path LL exchange region (library-owned)
+  size_t ll_bytes;
+  int last_path;         // path actually taken by the most recent call (1 generic, 2 latency)
   bool profiling;        // record CUDA events around the persistent launch
   cudaEvent_t ev0, ev1;
   bool ev_valid;
@@ -979,6 +996,139 @@ int fill_common(taco2dec_handle* h, Params& p, int B, int T_in, int T_sub, const
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Latency path (latency.cuh): eligibility, weight packing, launch
+// ------------------------------------------------------------------------------------------
+struct LatGeometry {
+  int NL, NL1, wbytes, slot_bytes, n_slots, res_budget;
+  size_t smem;
+};
+
+constexpr size_t kLatFixedSmem = 31744;   // activation segments, query slice, accumulators, barriers
+constexpr size_t kLatDynSmem = 231424;    // 226 KB of the 227 KB opt-in maximum
+
+bool lat_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
+  const taco2dec_config& c = h->cfg;
+  if (B != 1 || c.attention != TACO2DEC_ATTN_SMA) return false;
+  if (c.attn_rnn_dim != lat::H || c.dec_rnn_dim != lat::H || c.enc_dim != lat::E || c.prenet_dim != lat::P ||
+      c.attn_dim != lat::A || c.n_mel != lat::M)
+    return false;
+  if (h->num_sms < 64 || (size_t)h->max_smem_optin < kLatDynSmem) return false;
+  const int Tm = std::max(T_in, c.n_streams == 2 ? T_sub : 1);
+  const size_t att = ((size_t)Tm * lat::A + (size_t)Tm * (lat::E / lat::kAttnPerStream) + 5 * lat::A +
+                      8 * (lat::E / lat::kAttnPerStream) + 3 * (size_t)Tm) * sizeof(float);
+  return att <= kLatDynSmem;
+}
+
+LatGeometry lat_geometry(const taco2dec_handle* h, int wbytes) {
+  LatGeometry g;
+  const int S = h->cfg.n_streams;
+  int NL = h->num_sms - S * lat::kAttnPerStream - lat::kAux;
+  NL = NL / S * S;
+  g.NL = NL; g.NL1 = NL / S; g.wbytes = wbytes;
+  g.slot_bytes = 4 * lat::H * wbytes;
+  g.n_slots = wbytes == 4 ? 6 : 8;
+  g.res_budget = (int)((kLatDynSmem - kLatFixedSmem - (size_t)g.n_slots * g.slot_bytes) / 128 * 128);
+  g.smem = kLatDynSmem;
+  return g;
+}
+
+size_t lat_ll_words(const taco2dec_handle* h) {
+  const size_t d = lat::kLLDepth;
+  return d * 2 * lat::H + d * lat::H + d * 2 * lat::E + d * 2 * (size_t)h->num_sms * lat::A + d * 2 * (lat::P + 8) +
+         d * (lat::M + 16) + d * 2 * lat::P + 64;
+}
+
+int lat_pack_weights(taco2dec_handle* h, const LatGeometry& g, cudaStream_t st) {
+  if (h->packed_wbytes == g.wbytes) return 0;
+  const int S = h->cfg.n_streams;
+  std::vector<unsigned long long> off(g.NL + 1, 0);
+  for (int lc = 0; lc < g.NL; ++lc) {
+    const int i1 = lc % g.NL1;
+    const long long nu1 = (long long)(i1 + 1) * lat::H / g.NL1 - (long long)i1 * lat::H / g.NL1;
+    const long long nu2 = (long long)(lc + 1) * lat::H / g.NL - (long long)lc * lat::H / g.NL;
+    if (nu1 > lat::kMaxU1 || nu2 > lat::kMaxU2) return fail(TACO2DEC_E_STATE, "too few SMs for the latency path");
+    const long long elems = nu1 * 4 * (lat::H + lat::E + lat::P) + nu2 * 4 * ((long long)lat::H + S * lat::H + S * lat::E);
+    off[lc + 1] = off[lc] + (unsigned long long)elems * g.wbytes;
+  }
+  const size_t total = off[g.NL];
+  if (h->packed_bytes < total) {
+    if (h->packed) CUDA_TRY(cudaFree(h->packed));
+    h->packed = nullptr; h->packed_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->packed, total));
+    h->packed_bytes = total;
+  }
+  if (!h->packed_off) CUDA_TRY(cudaMalloc(&h->packed_off, sizeof(unsigned long long) * (h->num_sms + 1)));
+  CUDA_TRY(cudaMemcpyAsync(h->packed_off, off.data(), sizeof(unsigned long long) * (g.NL + 1), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // `off` is a host temporary
+  lat::PackSrc src;
+  for (int s = 0; s < 2; ++s) { src.w_ih[s] = h->w.stream[s].arnn_w_ih; src.w_hh[s] = h->w.stream[s].arnn_w_hh; }
+  src.d_w_ih = h->w.drnn_w_ih; src.d_w_hh = h->w.drnn_w_hh;
+  if (g.wbytes == 4)
+    lat::pack_weights_kernel<float><<<g.NL, 512, 0, st>>>(src, S, g.NL, g.NL1, h->packed_off, h->packed);
+  else
+    lat::pack_weights_kernel<__half><<<g.NL, 512, 0, st>>>(src, S, g.NL, g.NL1, h->packed_off, h->packed);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  h->packed_wbytes = g.wbytes;
+  return 0;
+}
+
+int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
+  const taco2dec_config& c = h->cfg;
+  const LatGeometry g = lat_geometry(h, h->weight_dtype == TACO2DEC_W_FP16 ? 2 : 4);
+  if (int rc = lat_pack_weights(h, g, st)) return rc;
+  const size_t words = lat_ll_words(h);
+  if (!h->ll_buf) {
+    CUDA_TRY(cudaMalloc(&h->ll_buf, words * sizeof(unsigned long long)));
+    h->ll_bytes = words * sizeof(unsigned long long);
+  }
+  CUDA_TRY(cudaMemsetAsync(h->ll_buf, 0, h->ll_bytes, st));
+  lat::LatParams p;
+  memset(&p, 0, sizeof(p));
+  p.S = c.n_streams; p.NL = g.NL; p.NL1 = g.NL1;
+  p.free_running = gp.free_running; p.training = gp.training; p.n_steps = gp.free_running ? gp.max_steps : gp.T;
+  p.Tcap = gp.Tcap; p.gate_thr = gp.gate_thr; p.p_att = gp.p_att; p.p_dec = gp.p_dec;
+  p.thresh_pre = gp.thresh_pre; p.thresh_att = gp.thresh_att; p.thresh_dec = gp.thresh_dec; p.seed = gp.seed;
+  p.wbytes = g.wbytes; p.packed = h->packed; p.packed_off = h->packed_off;
+  p.slot_bytes = g.slot_bytes; p.n_slots = g.n_slots; p.res_budget = g.res_budget;
+  for (int s = 0; s < c.n_streams; ++s) {
+    const StreamParams& sp = gp.st[s];
+    lat::LatStream& ls = p.st[s];
+    ls.b_ih = sp.b_ih; ls.b_hh = sp.b_hh; ls.wq = sp.wq; ls.v = sp.v; ls.pre_w0 = sp.pre_w0; ls.pre_w1 = sp.pre_w1;
+    ls.mem = sp.mem; ls.pm = sp.pm; ls.pre_tf = sp.pre; ls.noise = sp.noise; ls.keep0 = sp.keep0; ls.keep1 = sp.keep1;
+    ls.align = sp.align; ls.Ts = sp.Ts; ls.len = sp.len;
+  }
+  p.d_b_ih = gp.d_b_ih; p.d_b_hh = gp.d_b_hh; p.proj_w = gp.proj_w; p.proj_b = gp.proj_b; p.gate_w = gp.gate_w;
+  p.gate_b = gp.gate_b; p.lstm_keep = gp.lstm_keep; p.mel = gp.mel; p.gate = gp.gate; p.n_frames = gp.n_frames;
+  p.reached_max = gp.reached_max;
+  unsigned long long* w = h->ll_buf;
+  const size_t d = lat::kLLDepth;
+  p.ll_h1 = w; w += d * 2 * lat::H;
+  p.ll_h2 = w; w += d * lat::H;
+  p.ll_ctx = w; w += d * 2 * lat::E;
+  p.ll_q = w; w += d * 2 * (size_t)h->num_sms * lat::A;
+  p.ll_pre = w; w += d * 2 * (lat::P + 8);
+  p.ll_mel = w; w += d * (lat::M + 16);
+  p.ll_l0 = w; w += d * 2 * lat::P;
+  p.aux_done = (unsigned*)w;
+  p.abort_flag = gp.abort_flag;
+  p.phase_clocks = gp.phase_clocks;
+  void* args[] = {(void*)&p};
+  void* kern = g.wbytes == 4 ? (void*)lat::decoder_latency<4> : (void*)lat::decoder_latency<2>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  int per_sm = 0;
+  if (g.wbytes == 4) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lat::decoder_latency<4>, lat::kThreads, g.smem));
+  else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lat::decoder_latency<2>, lat::kThreads, g.smem));
+  if (per_sm < 1) return fail(TACO2DEC_E_STATE, "latency kernel does not fit on an SM");
+  if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(h->num_sms), dim3(lat::kThreads), args, g.smem, st));
+  if (h->profiling) { CUDA_TRY(cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
+  h->launches++;
+  h->last_path = TACO2DEC_PATH_LATENCY;
+  return 0;
+}
+
 int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, const WorkspaceLayout& L, cudaStream_t st) {
   const taco2dec_config& c = h->cfg;
   // control words: barrier counter, watchdog flag, done counter
@@ -993,6 +1143,11 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  const bool want_lat = h->path_mode != TACO2DEC_PATH_GENERIC && lat_shape_ok(h, p.B, T_in, T_sub);
+  if (h->path_mode == TACO2DEC_PATH_LATENCY && !want_lat)
+    return fail(TACO2DEC_E_ARG, "latency path needs B=1, SMA, default decoder dims and a short enough memory");
+  if (want_lat) return run_latency(h, p, st);
+  h->last_path = TACO2DEC_PATH_GENERIC;
   const int BT = pick_bt(p.B);
   const size_t smem = persistent_smem_bytes(c, BT, T_in, T_sub);
   if ((int)smem > h->max_smem_optin)
@@ -1033,6 +1188,10 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   h->launches = 0;
   h->last_abort_flag = nullptr;
   h->last_phase_clocks = nullptr;
+  h->path_mode = TACO2DEC_PATH_AUTO;
+  h->weight_dtype = TACO2DEC_W_FP32;
+  h->packed = nullptr; h->packed_bytes = 0; h->packed_wbytes = 0; h->packed_off = nullptr;
+  h->ll_buf = nullptr; h->ll_bytes = 0; h->last_path = 0;
   h->profiling = false;
   h->ev_valid = false;
   CUDA_TRY(cudaSetDevice(device));
@@ -1046,6 +1205,9 @@ int taco2dec_destroy(taco2dec_handle* h) {
   if (h) {
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
+    if (h->packed) cudaFree(h->packed);
+    if (h->packed_off) cudaFree(h->packed_off);
+    if (h->ll_buf) cudaFree(h->ll_buf);
   }
   delete h;
   return 0;
@@ -1058,6 +1220,17 @@ int taco2dec_read_phase_clocks(taco2dec_handle* h, void* cuda_stream, long long*
   CUDA_TRY(cudaMemcpy(out16_host, h->last_phase_clocks, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
+
+int taco2dec_set_mode(taco2dec_handle* h, int path, int weight_dtype) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null handle");
+  if (path < TACO2DEC_PATH_AUTO || path > TACO2DEC_PATH_LATENCY) return fail(TACO2DEC_E_ARG, "bad path");
+  if (weight_dtype != TACO2DEC_W_FP32 && weight_dtype != TACO2DEC_W_FP16) return fail(TACO2DEC_E_ARG, "bad weight dtype");
+  h->path_mode = path;
+  h->weight_dtype = weight_dtype;
+  return 0;
+}
+
+int taco2dec_last_path(const taco2dec_handle* h) { return h ? h->last_path : 0; }
 
 int taco2dec_set_profiling(taco2dec_handle* h, int on) {
   if (!h) return fail(TACO2DEC_E_ARG, "null handle");
@@ -1091,6 +1264,7 @@ int taco2dec_set_weights(taco2dec_handle* h, const taco2dec_weights* w, void* /*
   if (!w->drnn_b_ih || !w->drnn_b_hh || !w->proj_b || !w->gate_b) return fail(TACO2DEC_E_ARG, "bias pointer is null");
   h->w = *w;
   h->have_weights = true;
+  h->packed_wbytes = 0;  // latency-path weight streams are re-packed on next use
   return 0;
 }
 

@@ -64,6 +64,8 @@ class _Engine:
         self.handle = C.c_void_p()
         _cabi.check(self.lib.taco2dec_create(C.byref(cfg), device.index or 0, C.byref(self.handle)))
         self.workspace: Optional[torch.Tensor] = None
+        self.weights_key = None   # (data_ptr, version) of every bound tensor; re-bind only on change
+        self.mode = None
 
     def get_workspace(self, B, T_in, T_sub, T, tf) -> torch.Tensor:
         need = int(self.lib.taco2dec_workspace_bytes(self.handle, B, T_in, T_sub, T, int(tf)))
@@ -75,6 +77,17 @@ class _Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.taco2dec_launch_count(self.handle))
+
+    def set_mode(self, path: str, weight_dtype: str) -> None:
+        paths = {"auto": _cabi.PATH_AUTO, "generic": _cabi.PATH_GENERIC, "latency": _cabi.PATH_LATENCY}
+        dts = {"fp32": _cabi.W_FP32, "fp16": _cabi.W_FP16}
+        if (path, weight_dtype) != self.mode:
+            _cabi.check(self.lib.taco2dec_set_mode(self.handle, paths[path], dts[weight_dtype]))
+            self.mode = (path, weight_dtype)
+            self.weights_key = None   # packed streams depend on the storage type
+
+    def last_path(self) -> str:
+        return {0: "none", 1: "generic", 2: "latency"}[int(self.lib.taco2dec_last_path(self.handle))]
 
     def set_profiling(self, on: bool) -> None:
         _cabi.check(self.lib.taco2dec_set_profiling(self.handle, int(on)))
@@ -166,6 +179,8 @@ class Decoder(nn.Module):
         self.linear_projection = LinearNorm(proj_in, mel_in)
         self.gate_layer = LinearNorm(proj_in, 1, bias=True, w_init_gain="sigmoid")
         # -- extensions (not in the reference) --------------------------------------------
+        self.decoder_path = "auto"      # "auto" | "generic" | "latency"  (see include/taco2dec.h)
+        self.weight_dtype = "fp32"      # storage of the packed LSTM matrices on the latency path: "fp32" | "fp16"
         self.dropout_replay: Optional[DropoutReplay] = None  # parity runs: externally drawn masks
         self.rng_seed: Optional[int] = None                  # fixed Philox seed; None = fresh per call
         self.validate_lengths = True
@@ -196,7 +211,26 @@ class Decoder(nn.Module):
             raise _cabi.Taco2DecError("decoder parameters must be contiguous, 16-byte aligned fp32")
         return t
 
+    def _weight_tensors(self):
+        ts = []
+        for s in self._sfx():
+            pre, rnn, att = getattr(self, "prenet" + s), getattr(self, "attention_rnn" + s), getattr(self, "attention_layer" + s)
+            ts += [pre.layers[0].linear_layer.weight, pre.layers[1].linear_layer.weight, rnn.weight_ih, rnn.weight_hh,
+                   rnn.bias_ih, rnn.bias_hh, att.query_layer.linear_layer.weight, att.memory_layer.linear_layer.weight,
+                   att.v_weight()]
+            if self.attention_kind == LSA:
+                ts += [att.location_layer.location_conv.conv.weight, att.location_layer.location_dense.linear_layer.weight]
+        ts += [self.decoder_rnn.weight_ih, self.decoder_rnn.weight_hh, self.decoder_rnn.bias_ih, self.decoder_rnn.bias_hh,
+               self.linear_projection.linear_layer.weight, self.linear_projection.linear_layer.bias,
+               self.gate_layer.linear_layer.weight, self.gate_layer.linear_layer.bias]
+        return ts
+
     def _bind_weights(self, eng: _Engine) -> None:
+        eng.set_mode(self.decoder_path, self.weight_dtype)
+        key = tuple((t.data_ptr(), t._version) for t in self._weight_tensors())
+        if key == eng.weights_key:
+            return
+        eng.weights_key = key
         w = _cabi.Weights()
         for i, s in enumerate(self._sfx()):
             pre, rnn, att = getattr(self, "prenet" + s), getattr(self, "attention_rnn" + s), getattr(self, "attention_layer" + s)

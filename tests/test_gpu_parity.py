@@ -31,11 +31,75 @@ def _cmp(got, want, tag=""):
         assert d <= t, (tag, n, d)
 
 
+# (decoder_path, weight_dtype, mel/gate tolerance, alignment tolerance).  The fp16 rows state their
+# looser bound explicitly: only the three LSTM matrices are rounded to fp16 (fp32 accumulate);
+# SURVEY.md section 7 measured 5e-5 for that on the reference itself; the north-star bar is 1e-3.
+PATHS = [("generic", "fp32", TOL_MEL, TOL_ALIGN), ("latency", "fp32", TOL_MEL, TOL_ALIGN),
+         ("latency", "fp16", 1e-3, 2e-4)]
+
+
+def _cmp_tol(got, want, tol_mel, tol_align, tag=""):
+    for n, t, g, w in zip(("mel", "gate", "align", "align_bert"), (tol_mel, tol_mel, tol_align, tol_align), got, want):
+        g = g.detach().float().cpu()
+        assert g.shape == w.shape, (tag, n, g.shape, w.shape)
+        assert torch.isfinite(g).all(), (tag, n)
+        d = maxabs(g, w)
+        assert d <= t, (tag, n, d)
+
+
+@pytest.mark.parametrize("path,wdtype,tol_mel,tol_align", PATHS)
+@pytest.mark.parametrize("name", [n for n in golden_names() if "lsa" not in n])
+def test_latency_path_matches_reference_golden(name, path, wdtype, tol_mel, tol_align):
+    """Batch-1 SMA goldens through the role-specialised latency kernel (fp32 and fp16 weight storage)
+    and, for comparison, the generic kernel.  Stop frames / INFER_FLAG exact in every mode."""
+    recipe, gold, _ = load_golden(name)
+    if recipe["B"] != 1:
+        pytest.skip("latency path is batch-1")
+    w, inp, plan = materialise(recipe)
+    dec = make_decoder(w, recipe["attention"])
+    dec.decoder_path, dec.weight_dtype = path, wdtype
+    dec.dropout_replay = replay_of(plan)
+    want = (gold["mel"], gold["gate"], gold["align"], gold["align_bert"])
+    with torch.no_grad():
+        if recipe["mode"] == "tf":
+            dec.train(recipe["training"])
+            got = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(),
+                      inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+        else:
+            dec.eval()
+            dec.max_decoder_steps = recipe["max_steps"]
+            mel, gate, al, alb, flag = dec.inference(inp["memory"].cuda(), inp["embeddings"].cuda())
+            assert mel.shape[2] == int(gold["n_frames"]), "stop frame must match exactly"
+            assert int(flag) == int(gold["flag"]), "INFER_FLAG must match exactly"
+            got = (mel, gate, al, alb)
+    assert dec._engine(torch.device("cuda", 0)).last_path() == path
+    _cmp_tol(got, want, tol_mel, tol_align, f"{name} {path}/{wdtype}")
+
+
+@pytest.mark.parametrize("path,wdtype,tol_mel,tol_align", PATHS[1:])
+def test_latency_path_training_mode_vs_oracle(path, wdtype, tol_mel, tol_align):
+    """B=1 teacher-forced train() (LSTM-state dropout on h and c + SMA noise, replayed) on the latency path."""
+    T_in, T_sub, T, seed = 37, 12, 24, 9
+    w = make_decoder_weights(SMA, seed=seed)
+    inp = make_inputs(1, T_in, T_sub, T, seed=seed)
+    plan = make_dropout_plan(1, T + 1, T, T_in, T_sub, True, seed=seed + 1)
+    want = DecoderOracle(w, SMA).forward(inp["memory"], inp["embeddings"], inp["mels"], inp["memory_lengths"],
+                                         inp["bert_lengths"], plan, training=True)
+    dec = make_decoder(w, SMA).train()
+    dec.decoder_path, dec.weight_dtype = path, wdtype
+    dec.dropout_replay = replay_of(plan)
+    with torch.no_grad():
+        got = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(),
+                  inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+    _cmp_tol(got, want, tol_mel, tol_align, f"train {path}/{wdtype}")
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_cuda_matches_reference_golden(name):
     recipe, gold, _ = load_golden(name)
     w, inp, plan = materialise(recipe)
     dec = make_decoder(w, recipe["attention"])
+    dec.decoder_path = "generic"
     dec.dropout_replay = replay_of(plan)
     want = (gold["mel"], gold["gate"], gold["align"], gold["align_bert"])
     with torch.no_grad():
@@ -119,7 +183,8 @@ def test_cuda_single_stream_compat_vs_oracle():
     _cmp(got, want, "single-stream")
 
 
-def test_teacher_forcing_own_output_reproduces_free_run():
+@pytest.mark.parametrize("path,wdtype", [("generic", "fp32"), ("latency", "fp32"), ("latency", "fp16")])
+def test_teacher_forcing_own_output_reproduces_free_run(path, wdtype):
     """Size-independent property at BASELINE cfg-2 scale (B=1, 150 phones / 50 sub-words, 1000 steps,
     gate bias -20): feeding the free-running mels back as teacher-forcing targets with the same
     prenet masks must reproduce the free run; never-stopping run hits max_decoder_steps exactly."""
@@ -128,7 +193,9 @@ def test_teacher_forcing_own_output_reproduces_free_run():
     inp = make_inputs(1, T_in, T_sub, 1, seed=seed)
     plan = make_dropout_plan(1, steps + 1, steps, T_in, T_sub, False, seed=seed + 1)
     dec = make_decoder(w, SMA).eval()
+    dec.decoder_path, dec.weight_dtype = path, wdtype
     dec.dropout_replay = replay_of(plan)
+    head_tol = (TOL_MEL, TOL_ALIGN) if wdtype == "fp32" else (1e-3, 2e-4)
     with torch.no_grad():
         mel, gate, al, alb, flag = dec.inference(inp["memory"].cuda(), inp["embeddings"].cuda())
         assert mel.shape == (1, 80, steps) and flag is False
@@ -145,7 +212,8 @@ def test_teacher_forcing_own_output_reproduces_free_run():
     plan60 = make_dropout_plan(1, steps + 1, steps, T_in, T_sub, False, seed=seed + 1)
     omel, ogate, oal, oalb, oflag = DecoderOracle(w, SMA).inference(inp["memory"], inp["embeddings"], plan60,
                                                                     max_decoder_steps=60)
-    _cmp((mel[:, :, :60], gate[:, :60], al[:, :60], alb[:, :60]), (omel, ogate, oal, oalb), "cfg2 head")
+    _cmp_tol((mel[:, :, :60], gate[:, :60], al[:, :60], alb[:, :60]), (omel, ogate, oal, oalb), head_tol[0], head_tol[1],
+             f"cfg2 head {path}/{wdtype}")
 
 
 def test_philox_production_masks_equal_replay():
