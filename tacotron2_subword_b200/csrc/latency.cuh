@@ -71,6 +71,9 @@ struct LatParams {
   const unsigned char* packed;   // per-LSTM-CTA weight streams
   const unsigned long long* packed_off;  // [NL+1] byte offsets
   int slot_bytes, n_slots, res_budget;   // TMA ring geometry, bytes available for resident chunks
+  int debug_direct;              // diagnostics: 1 = consumers read streamed chunks straight from global memory,
+                                 // 2 = ring on, every streamed row is verified against global memory
+  unsigned long long* dbg;       // [0] = mismatch count, then 8 words per record
   LatStream st[2];
   const float *d_b_ih, *d_b_hh;  // decoder LSTM biases [4H]
   const float *proj_w, *proj_b, *gate_w, *gate_b;
@@ -118,6 +121,23 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ long long lds_acquire_s64(const volatile long long* p) {
+  long long v;
+  asm volatile("ld.acquire.cta.shared.s64 %0, [%1];" : "=l"(v) : "r"(smem_u32((const void*)p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_release_s64(volatile long long* p, long long v) {
+  asm volatile("st.release.cta.shared.s64 [%0], %1;" ::"r"(smem_u32((const void*)p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_acquire_u32(const volatile unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void reds_release_inc(volatile unsigned* p) {
+  asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_u32((const void*)p)) : "memory");
+}
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
@@ -237,9 +257,14 @@ struct LstmShared {
   float *wq_s;                              // [A][kMaxU1] query-weight slice of this CTA's units
   float *acc1, *acc2, *c1, *c2, *hloc;      // gate accumulators / cell state / fresh h1 of own units
   float *bias1, *bias2;                     // b_ih + b_hh of own units [u][4]
-  uint64_t *full, *empty, *res_bar;         // mbarriers
+  uint64_t *full, *res_bar;                 // mbarriers (TMA completion); observed in order by the producer only
+  volatile unsigned* consumed;              // [slot] rows consumed so far (4 per use) -> frees the slot
+  volatile long long* landed;               // chunks whose TMA copy has landed (monotonic, published by the producer)
   StepPlan* plan;                           // [kSteps]
   volatile int* exit_flag;
+  const unsigned char* gstream;             // this CTA's packed stream in global memory
+  int direct;
+  unsigned long long* dbg;
 };
 
 // consume one step: every (chunk, gate-row) item is one warp-level dot product of KSEG columns
@@ -247,6 +272,7 @@ template <int WB, int KSEG>
 __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
                                              long long frame_stream_base, int n_slots, int slot_bytes, int warp,
                                              int lane, Watch& wd, bool& ok) {
+  unsigned long long* p_dbg = sh.dbg;
   constexpr int EPU = RowDot<WB>::kElemsPerUnit;
   constexpr int NU = KSEG / (32 * EPU);
   static_assert(NU >= 1, "segment too short");
@@ -262,26 +288,69 @@ __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPla
   for (int it = warp; it < n_items; it += kConsumerWarps) {
     const int ci = it >> 2, g = it & 3;
     const unsigned char* base;
-    uint64_t* release = nullptr;
+    volatile unsigned* release = nullptr;
     if (ci < sp.n_res) {
       base = sh.resident + sp.res_off + (size_t)ci * sp.chunk_bytes;
+    } else if (sh.direct == 1) {
+      base = sh.gstream + sp.src_off + (size_t)ci * sp.chunk_bytes;
     } else {
       const long long seq = frame_stream_base + sp.stream_base + (ci - sp.n_res);
       const int slot = (int)(seq % n_slots);
-      const unsigned parity = (unsigned)((seq / n_slots) & 1);
       wd.arm();
-      while (!mbar_try_wait(&sh.full[slot], parity)) {
+      // Only the producer thread looks at the TMA mbarriers (it sees every use of every slot in order,
+      // so phase parity is exact); it republishes completion as a monotonic chunk counter.
+      while (lds_acquire_s64(sh.landed) <= seq) {
         if (wd.expired()) { ok = false; break; }
       }
       if (!ok) break;
       base = sh.ring + (size_t)slot * slot_bytes;
-      release = &sh.empty[slot];
+      release = &sh.consumed[slot];
+      if (sh.direct == 2) {
+        // verify this row against the packed stream in global memory
+        const unsigned char* gsrc = sh.gstream + sp.src_off + (size_t)ci * sp.chunk_bytes + (size_t)g * KSEG * WB;
+        const unsigned char* ssrc = base + (size_t)g * KSEG * WB;
+        int bad = 0;
+        for (int i = lane; i < KSEG * WB / 16; i += 32) {
+          const uint4 a = *reinterpret_cast<const uint4*>(ssrc + (size_t)i * 16);
+          const uint4 b = *reinterpret_cast<const uint4*>(gsrc + (size_t)i * 16);
+          if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) ++bad;
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, bad != 0);
+        if (any) {
+          // re-check after a delay: does it become right (early read) or stay wrong (overwritten / wrong data)?
+          const long long t0 = clock64();
+          while (clock64() - t0 < 200000) {}
+          int bad2 = 0, prev_match = 0, next_match = 0;
+          const long long step_bytes = sp.chunk_bytes;
+          for (int i = lane; i < KSEG * WB / 16; i += 32) {
+            const uint4 a = *reinterpret_cast<const uint4*>(ssrc + (size_t)i * 16);
+            const uint4 b = *reinterpret_cast<const uint4*>(gsrc + (size_t)i * 16);
+            if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) ++bad2;
+          }
+          const unsigned any2 = __ballot_sync(0xffffffffu, bad2 != 0);
+          if (lane == 0) {
+            const unsigned long long k = atomicAdd(p_dbg, 1ull);
+            if (k < 60) {
+              unsigned long long* r = p_dbg + 8 + k * 8;
+              r[0] = ((unsigned long long)blockIdx.x << 32) | (unsigned)(seq / 1);
+              r[1] = ((unsigned long long)(unsigned)slot << 32) | (unsigned)it;
+              r[2] = ((unsigned long long)any << 32) | any2;
+              r[3] = (unsigned long long)(*sh.landed);
+              r[4] = (unsigned long long)sp.kseg;
+              r[5] = (unsigned long long)frame_stream_base;
+              r[6] = (unsigned long long)sp.stream_base;
+              r[7] = (unsigned long long)step_bytes;
+            }
+          }
+          (void)prev_match; (void)next_match;
+        }
+      }
     }
     float v = RowDot<WB>::template run<NU>(base + (size_t)g * KSEG * WB, x, lane);
     v = warp_sum(v);
     if (lane == 0) {
       acc[it] += v;
-      if (release) mbar_arrive(release);   // 4 arrivals (one per gate row) free the slot
+      if (release) reds_release_inc(release);   // 4 rows per use free the slot
     }
   }
 }
@@ -334,10 +403,11 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   sh.bias1 = (float*)take(sizeof(float) * kMaxU1 * 4);
   sh.bias2 = (float*)take(sizeof(float) * kMaxU2 * 4);
   sh.full = (uint64_t*)take(sizeof(uint64_t) * kMaxSlots);
-  sh.empty = (uint64_t*)take(sizeof(uint64_t) * kMaxSlots);
+  sh.consumed = (volatile unsigned*)take(sizeof(unsigned) * kMaxSlots);
   sh.res_bar = (uint64_t*)take(sizeof(uint64_t));
   sh.plan = (StepPlan*)take(sizeof(StepPlan) * kSteps);
   sh.exit_flag = (volatile int*)take(sizeof(int));
+  sh.landed = (volatile long long*)take(sizeof(long long));
 
   // ---- step plan (thread 0) ---------------------------------------------------------------
   if (tid == 0) {
@@ -363,9 +433,10 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     }
     int sb = 0;
     for (int s = 0; s < kSteps; ++s) { sh.plan[s].stream_base = sb; sb += sh.plan[s].n_chunks - sh.plan[s].n_res; }
-    for (int i = 0; i < p.n_slots; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 4); }
+    for (int i = 0; i < p.n_slots; ++i) { mbar_init(&sh.full[i], 1); sh.consumed[i] = 0u; }
     mbar_init(sh.res_bar, 1);
     *sh.exit_flag = 0;
+    *sh.landed = 0;
     fence_barrier_init();
   }
   // zero state, load biases and the query-weight slice
@@ -392,6 +463,9 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   __syncthreads();
 
   const unsigned char* my_stream = p.packed + p.packed_off[lc];
+  sh.gstream = my_stream;
+  sh.direct = p.debug_direct;
+  sh.dbg = p.dbg;
   int streamed_per_frame = 0;
   for (int s = 0; s < kSteps; ++s) streamed_per_frame += sh.plan[s].n_chunks - sh.plan[s].n_res;
   const int n_steps = p.n_steps;
@@ -414,36 +488,60 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       } else {
         mbar_arrive(sh.res_bar);
       }
-      long long seq = 0;
-      bool live = true;
-      for (int t = 0; t < n_steps && live; ++t) {
-        for (int s = 0; s < kSteps && live; ++s) {
-          const StepPlan& sp = sh.plan[s];
-          for (int c = sp.n_res; c < sp.n_chunks; ++c, ++seq) {
-            const int slot = (int)(seq % p.n_slots);
-            const unsigned parity = (unsigned)(((seq / p.n_slots) & 1) ^ 1);
-            wd.arm();
-            while (!mbar_try_wait(&sh.empty[slot], parity)) {
-              if (*sh.exit_flag || wd.expired()) { live = false; break; }
-            }
-            if (!live) break;
+      // event loop: issue the next chunk when its slot is free, confirm landings strictly in order
+      const long long total = p.debug_direct == 1 ? 0 : (long long)n_steps * streamed_per_frame;
+      long long issue = 0, land = 0;
+      int it_s = 0, it_c = 0;            // iterator over (step, chunk) of the next chunk to issue
+      auto advance = [&]() {             // move (it_s, it_c) to the next streamed chunk (wraps per frame)
+        for (;;) {
+          const StepPlan& sp = sh.plan[it_s];
+          if (it_c < sp.n_res) it_c = sp.n_res;
+          if (it_c < sp.n_chunks) return;
+          it_c = 0;
+          it_s = (it_s + 1) % kSteps;
+        }
+      };
+      wd.arm();
+      bool live = total > 0;
+      if (live) advance();
+      while (live && land < total) {
+        bool progressed = false;
+        if (issue < total) {
+          const int slot = (int)(issue % p.n_slots);
+          const unsigned need = 4u * (unsigned)(issue / p.n_slots);
+          if (lds_acquire_u32(&sh.consumed[slot]) >= need) {
+            const StepPlan& sp = sh.plan[it_s];
             mbar_expect_tx(&sh.full[slot], (unsigned)sp.chunk_bytes);
-            tma_load_1d(sh.ring + (size_t)slot * p.slot_bytes, my_stream + sp.src_off + (size_t)c * sp.chunk_bytes,
+            tma_load_1d(sh.ring + (size_t)slot * p.slot_bytes, my_stream + sp.src_off + (size_t)it_c * sp.chunk_bytes,
                         (unsigned)sp.chunk_bytes, &sh.full[slot]);
+            ++issue;
+            ++it_c;
+            advance();
+            progressed = true;
           }
         }
-      }
-      // drain: every issued copy must have landed before this CTA may exit
-      // (consumers that stopped early never wait on these slots)
-      const long long issued = seq;
-      const long long first = issued > p.n_slots ? issued - p.n_slots : 0;
-      for (long long q = first; q < issued; ++q) {
-        const int slot = (int)(q % p.n_slots);
-        const unsigned parity = (unsigned)((q / p.n_slots) & 1);
-        wd.arm();
-        while (!mbar_try_wait(&sh.full[slot], parity)) {
-          if (wd.expired()) break;
+        if (land < issue) {
+          const int slot = (int)(land % p.n_slots);
+          const unsigned parity = (unsigned)((land / p.n_slots) & 1);
+          if (mbar_try_wait(&sh.full[slot], parity)) {
+            ++land;
+            sts_release_s64(sh.landed, land);
+            progressed = true;
+          }
         }
+        if (progressed) { wd.arm(); continue; }
+        if (*sh.exit_flag) {
+          // consumers are gone: stop issuing, but every issued copy must land before the CTA exits
+          wd.arm();
+          while (land < issue) {
+            const int sl = (int)(land % p.n_slots);
+            const unsigned par = (unsigned)((land / p.n_slots) & 1);
+            if (mbar_try_wait(&sh.full[sl], par)) { ++land; continue; }
+            if (wd.expired()) break;
+          }
+          break;
+        }
+        if (wd.expired()) live = false;
       }
       wd.arm();
       while (!mbar_try_wait(sh.res_bar, 0)) {

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1092,6 +1093,11 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   p.thresh_pre = gp.thresh_pre; p.thresh_att = gp.thresh_att; p.thresh_dec = gp.thresh_dec; p.seed = gp.seed;
   p.wbytes = g.wbytes; p.packed = h->packed; p.packed_off = h->packed_off;
   p.slot_bytes = g.slot_bytes; p.n_slots = g.n_slots; p.res_budget = g.res_budget;
+  { const char* e = getenv("TACO2DEC_DEBUG_DIRECT"); p.debug_direct = e ? atoi(e) : 0; }
+  static unsigned long long* s_dbg = nullptr;
+  if (!s_dbg) CUDA_TRY(cudaMalloc(&s_dbg, 8192));
+  CUDA_TRY(cudaMemsetAsync(s_dbg, 0, 8192, st));
+  p.dbg = s_dbg;
   for (int s = 0; s < c.n_streams; ++s) {
     const StreamParams& sp = gp.st[s];
     lat::LatStream& ls = p.st[s];
@@ -1126,6 +1132,17 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   if (h->profiling) { CUDA_TRY(cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
   h->launches++;
   h->last_path = TACO2DEC_PATH_LATENCY;
+  if (p.debug_direct == 2) {
+    unsigned long long host[8 + 60 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, s_dbg, sizeof(host), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[dbg] ring mismatches: %llu (slots %d, streamed chunks differ per CTA)\n", host[0], g.n_slots);
+    for (unsigned long long k = 0; k < host[0] && k < 60; ++k) {
+      unsigned long long* r = host + 8 + k * 8;
+      fprintf(stderr, "[dbg] cta %llu seq %llu slot %llu item %llu lanes_bad %08llx after_delay %08llx issued %llu kseg %llu fbase %llu sbase %llu\n",
+              r[0] >> 32, r[0] & 0xffffffffull, r[1] >> 32, r[1] & 0xffffffffull, r[2] >> 32, r[2] & 0xffffffffull, r[3], r[4], r[5], r[6]);
+    }
+  }
   return 0;
 }
 
