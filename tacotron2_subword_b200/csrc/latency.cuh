@@ -71,6 +71,8 @@ struct LatParams {
   const unsigned char* packed;   // per-LSTM-CTA weight streams
   const unsigned long long* packed_off;  // [NL+1] byte offsets
   int slot_bytes, n_slots, res_budget;   // TMA ring geometry, bytes available for resident chunks
+  int units_per_block;           // hidden units (4-row chunks) moved by one TMA bulk copy
+  int poll_sleep_ns;             // back-off between LL polls
   int debug_direct;              // diagnostics: 1 = consumers read streamed chunks straight from global memory,
                                  // 2 = ring on, every streamed row is verified against global memory
   unsigned long long* dbg;       // [0] = mismatch count, then 8 words per record
@@ -106,6 +108,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a system-defined time; the producer must not)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -156,6 +170,7 @@ struct Watch {
   int* abort_flag;
   long long t0;
   unsigned spins;
+  unsigned sleep_ns;
   __device__ __forceinline__ void arm() { t0 = clock64(); spins = 0; }
   // returns true when the kernel must bail out
   __device__ __forceinline__ bool expired() {
@@ -172,6 +187,7 @@ __device__ __forceinline__ bool ll_wait(const unsigned long long* p, unsigned ta
   for (;;) {
     const unsigned long long x = ll_load(p);
     if ((unsigned)(x >> 32) == tag) { v = __uint_as_float((unsigned)x); return true; }
+    if (w.sleep_ns) __nanosleep(w.sleep_ns);
     if (w.expired()) return false;
   }
 }
@@ -199,7 +215,8 @@ struct StepPlan {
   int n_res;         // first n_res chunks are resident in shared memory
   int res_off;       // byte offset of the step's resident chunks inside the resident region
   long long src_off; // byte offset of the step's first chunk inside this CTA's packed stream
-  int stream_base;   // index of the step's first streamed chunk within a frame's streamed sequence
+  int n_blocks;      // TMA blocks (groups of units_per_block streamed chunks) in this step
+  int block_base;    // index of the step's first block within a frame's block sequence
 };
 
 template <int WB>  // bytes per weight element
@@ -265,13 +282,15 @@ struct LstmShared {
   const unsigned char* gstream;             // this CTA's packed stream in global memory
   int direct;
   unsigned long long* dbg;
+  int units_per_block;
 };
 
 // consume one step: every (chunk, gate-row) item is one warp-level dot product of KSEG columns
 template <int WB, int KSEG>
 __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
-                                             long long frame_stream_base, int n_slots, int slot_bytes, int warp,
+                                             long long frame_block_base, int n_slots, int slot_bytes, int warp,
                                              int lane, Watch& wd, bool& ok) {
+  const int G = sh.units_per_block;
   unsigned long long* p_dbg = sh.dbg;
   constexpr int EPU = RowDot<WB>::kElemsPerUnit;
   constexpr int NU = KSEG / (32 * EPU);
@@ -294,7 +313,8 @@ __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPla
     } else if (sh.direct == 1) {
       base = sh.gstream + sp.src_off + (size_t)ci * sp.chunk_bytes;
     } else {
-      const long long seq = frame_stream_base + sp.stream_base + (ci - sp.n_res);
+      const int rs = ci - sp.n_res;                       // index among the step's streamed chunks
+      const long long seq = frame_block_base + sp.block_base + rs / G;
       const int slot = (int)(seq % n_slots);
       wd.arm();
       // Only the producer thread looks at the TMA mbarriers (it sees every use of every slot in order,
@@ -303,7 +323,7 @@ __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPla
         if (wd.expired()) { ok = false; break; }
       }
       if (!ok) break;
-      base = sh.ring + (size_t)slot * slot_bytes;
+      base = sh.ring + (size_t)slot * slot_bytes + (size_t)(rs % G) * sp.chunk_bytes;
       release = &sh.consumed[slot];
       if (sh.direct == 2) {
         // verify this row against the packed stream in global memory
@@ -337,8 +357,8 @@ __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPla
               r[2] = ((unsigned long long)any << 32) | any2;
               r[3] = (unsigned long long)(*sh.landed);
               r[4] = (unsigned long long)sp.kseg;
-              r[5] = (unsigned long long)frame_stream_base;
-              r[6] = (unsigned long long)sp.stream_base;
+              r[5] = (unsigned long long)frame_block_base;
+              r[6] = (unsigned long long)sp.block_base;
               r[7] = (unsigned long long)step_bytes;
             }
           }
@@ -431,8 +451,13 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       sp.n_res = n; sp.res_off = roff;
       roff += n * sp.chunk_bytes; left -= n * sp.chunk_bytes;
     }
-    int sb = 0;
-    for (int s = 0; s < kSteps; ++s) { sh.plan[s].stream_base = sb; sb += sh.plan[s].n_chunks - sh.plan[s].n_res; }
+    int bb = 0;
+    for (int s = 0; s < kSteps; ++s) {
+      StepPlan& sp = sh.plan[s];
+      sp.n_blocks = (sp.n_chunks - sp.n_res + p.units_per_block - 1) / p.units_per_block;
+      sp.block_base = bb;
+      bb += sp.n_blocks;
+    }
     for (int i = 0; i < p.n_slots; ++i) { mbar_init(&sh.full[i], 1); sh.consumed[i] = 0u; }
     mbar_init(sh.res_bar, 1);
     *sh.exit_flag = 0;
@@ -465,15 +490,16 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   const unsigned char* my_stream = p.packed + p.packed_off[lc];
   sh.gstream = my_stream;
   sh.direct = p.debug_direct;
+  sh.units_per_block = p.units_per_block;
   sh.dbg = p.dbg;
-  int streamed_per_frame = 0;
-  for (int s = 0; s < kSteps; ++s) streamed_per_frame += sh.plan[s].n_chunks - sh.plan[s].n_res;
+  int blocks_per_frame = 0;
+  for (int s = 0; s < kSteps; ++s) blocks_per_frame += sh.plan[s].n_blocks;
   const int n_steps = p.n_steps;
 
   // ======================= producer warp: TMA weight streaming =============================
   if (warp == kConsumerWarps) {
     if (lane == 0) {
-      Watch wd{p.abort_flag, 0, 0};
+      Watch wd{p.abort_flag, 0, 0, (unsigned)p.poll_sleep_ns};
       // resident prefix: loaded once, lives for the whole utterance
       unsigned res_total = 0;
       for (int s = 0; s < kSteps; ++s) res_total += (unsigned)(sh.plan[s].n_res * sh.plan[s].chunk_bytes);
@@ -488,46 +514,49 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       } else {
         mbar_arrive(sh.res_bar);
       }
-      // event loop: issue the next chunk when its slot is free, confirm landings strictly in order
-      const long long total = p.debug_direct == 1 ? 0 : (long long)n_steps * streamed_per_frame;
+      // event loop: issue the next block when its slot is free, confirm landings strictly in order
+      const int G = p.units_per_block;
+      const long long total = p.debug_direct == 1 ? 0 : (long long)n_steps * blocks_per_frame;
       long long issue = 0, land = 0;
-      int it_s = 0, it_c = 0;            // iterator over (step, chunk) of the next chunk to issue
-      auto advance = [&]() {             // move (it_s, it_c) to the next streamed chunk (wraps per frame)
-        for (;;) {
-          const StepPlan& sp = sh.plan[it_s];
-          if (it_c < sp.n_res) it_c = sp.n_res;
-          if (it_c < sp.n_chunks) return;
-          it_c = 0;
-          it_s = (it_s + 1) % kSteps;
-        }
+      int it_s = 0, it_b = 0;            // (step, block) of the next block to issue
+      unsigned exp_rows[kMaxSlots];      // rows the consumers must have retired before a slot may be refilled
+#pragma unroll
+      for (int i = 0; i < kMaxSlots; ++i) exp_rows[i] = 0u;
+      auto advance = [&]() {             // skip steps without streamed blocks (wraps per frame)
+        while (it_b >= sh.plan[it_s].n_blocks) { it_b = 0; it_s = (it_s + 1) % kSteps; }
       };
       wd.arm();
       bool live = total > 0;
       if (live) advance();
       while (live && land < total) {
         bool progressed = false;
-        if (issue < total) {
+        while (issue < total && issue - land < p.n_slots) {
           const int slot = (int)(issue % p.n_slots);
-          const unsigned need = 4u * (unsigned)(issue / p.n_slots);
-          if (lds_acquire_u32(&sh.consumed[slot]) >= need) {
-            const StepPlan& sp = sh.plan[it_s];
-            mbar_expect_tx(&sh.full[slot], (unsigned)sp.chunk_bytes);
-            tma_load_1d(sh.ring + (size_t)slot * p.slot_bytes, my_stream + sp.src_off + (size_t)it_c * sp.chunk_bytes,
-                        (unsigned)sp.chunk_bytes, &sh.full[slot]);
-            ++issue;
-            ++it_c;
-            advance();
-            progressed = true;
-          }
+          if (lds_acquire_u32(&sh.consumed[slot]) < exp_rows[slot]) break;
+          const StepPlan& sp = sh.plan[it_s];
+          const int first = sp.n_res + it_b * G;
+          const int units = min(G, sp.n_chunks - first);
+          const unsigned bytes = (unsigned)(units * sp.chunk_bytes);
+          mbar_expect_tx(&sh.full[slot], bytes);
+          tma_load_1d(sh.ring + (size_t)slot * p.slot_bytes, my_stream + sp.src_off + (size_t)first * sp.chunk_bytes, bytes,
+                      &sh.full[slot]);
+          exp_rows[slot] += 4u * (unsigned)units;
+          ++issue;
+          ++it_b;
+          advance();
+          progressed = true;
         }
-        if (land < issue) {
-          const int slot = (int)(land % p.n_slots);
-          const unsigned parity = (unsigned)((land / p.n_slots) & 1);
-          if (mbar_try_wait(&sh.full[slot], parity)) {
-            ++land;
-            sts_release_s64(sh.landed, land);
-            progressed = true;
+        {
+          // probe up to 4 in-flight blocks with independent (overlapping) test_waits, accept the landed prefix
+          bool f[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const long long q = land + k;
+            f[k] = q < issue && mbar_test_wait(&sh.full[(int)(q % p.n_slots)], (unsigned)((q / p.n_slots) & 1));
           }
+          int n = 0;
+          if (f[0]) { n = 1; if (f[1]) { n = 2; if (f[2]) { n = 3; if (f[3]) n = 4; } } }
+          if (n) { land += n; sts_release_s64(sh.landed, land); progressed = true; }
         }
         if (progressed) { wd.arm(); continue; }
         if (*sh.exit_flag) {
@@ -552,7 +581,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   }
 
   // ======================= consumer warps ===================================================
-  Watch wd{p.abort_flag, 0, 0};
+  Watch wd{p.abort_flag, 0, 0, (unsigned)p.poll_sleep_ns};
   bool ok = true;
   const int ctid = tid;  // 0..479
   const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
@@ -574,7 +603,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
 
   const StepPlan* pl = sh.plan;
   for (int t = 0; t < n_steps && ok; ++t) {
-    const long long fbase = (long long)t * streamed_per_frame;
+    const long long fbase = (long long)t * blocks_per_frame;
     const unsigned tag_prev = (unsigned)t;        // values produced during frame t-1
     const unsigned tag_cur = (unsigned)t + 1u;    // values produced during frame t
     const int rb = t % kLLDepth, rb_prev = (t + kLLDepth - 1) % kLLDepth;
@@ -728,7 +757,7 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
   if (tid == 0) s_stop = 0;
   __syncthreads();
 
-  Watch wd{p.abort_flag, 0, 0};
+  Watch wd{p.abort_flag, 0, 0, (unsigned)p.poll_sleep_ns};
   const int NL1 = p.NL1;
   for (int t = 0; t < p.n_steps; ++t) {
     const unsigned tag = (unsigned)t + 1u;
@@ -844,7 +873,7 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
   if (tid == 0) s_stop = 0;
   __syncthreads();
 
-  Watch wd{p.abort_flag, 0, 0};
+  Watch wd{p.abort_flag, 0, 0, (unsigned)p.poll_sleep_ns};
   // prenet of frame 0 = prenet(go-frame of zeros) = zeros (model.py:444-450); stop word = 0
   if (p.free_running) {
     for (int i = tid; i < S * PR; i += kThreads) {

@@ -1001,7 +1001,7 @@ int fill_common(taco2dec_handle* h, Params& p, int B, int T_in, int T_sub, const
 // Latency path (latency.cuh): eligibility, weight packing, launch
 // ------------------------------------------------------------------------------------------
 struct LatGeometry {
-  int NL, NL1, wbytes, slot_bytes, n_slots, res_budget;
+  int NL, NL1, wbytes, slot_bytes, n_slots, res_budget, units_per_block;
   size_t smem;
 };
 
@@ -1027,8 +1027,11 @@ LatGeometry lat_geometry(const taco2dec_handle* h, int wbytes) {
   int NL = h->num_sms - S * lat::kAttnPerStream - lat::kAux;
   NL = NL / S * S;
   g.NL = NL; g.NL1 = NL / S; g.wbytes = wbytes;
-  g.slot_bytes = 4 * lat::H * wbytes;
-  g.n_slots = wbytes == 4 ? 6 : 8;
+  g.units_per_block = 2;
+  { const char* e = getenv("TACO2DEC_UNITS_PER_BLOCK"); if (e && atoi(e) >= 1 && atoi(e) <= 4) g.units_per_block = atoi(e); }
+  g.slot_bytes = g.units_per_block * 4 * lat::H * wbytes;
+  g.n_slots = (wbytes == 4 ? 98304 : 65536) / g.slot_bytes;
+  { const char* e = getenv("TACO2DEC_RING_SLOTS"); if (e && atoi(e) >= 2 && atoi(e) <= lat::kMaxSlots) g.n_slots = atoi(e); }
   g.res_budget = (int)((kLatDynSmem - kLatFixedSmem - (size_t)g.n_slots * g.slot_bytes) / 128 * 128);
   g.smem = kLatDynSmem;
   return g;
@@ -1092,8 +1095,9 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   p.Tcap = gp.Tcap; p.gate_thr = gp.gate_thr; p.p_att = gp.p_att; p.p_dec = gp.p_dec;
   p.thresh_pre = gp.thresh_pre; p.thresh_att = gp.thresh_att; p.thresh_dec = gp.thresh_dec; p.seed = gp.seed;
   p.wbytes = g.wbytes; p.packed = h->packed; p.packed_off = h->packed_off;
-  p.slot_bytes = g.slot_bytes; p.n_slots = g.n_slots; p.res_budget = g.res_budget;
+  p.slot_bytes = g.slot_bytes; p.n_slots = g.n_slots; p.res_budget = g.res_budget; p.units_per_block = g.units_per_block;
   { const char* e = getenv("TACO2DEC_DEBUG_DIRECT"); p.debug_direct = e ? atoi(e) : 0; }
+  { const char* e = getenv("TACO2DEC_POLL_SLEEP_NS"); p.poll_sleep_ns = e ? atoi(e) : 0; }
   static unsigned long long* s_dbg = nullptr;
   if (!s_dbg) CUDA_TRY(cudaMalloc(&s_dbg, 8192));
   CUDA_TRY(cudaMemsetAsync(s_dbg, 0, 8192, st));
