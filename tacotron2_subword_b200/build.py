@@ -15,7 +15,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libtaco2dec.so")
 SOURCES = [os.path.join(CSRC, "taco2dec.cu")]
-HEADERS = [os.path.join(ROOT, "include", "taco2dec.h")]
+HEADERS = [os.path.join(ROOT, "include", "taco2dec.h")] + sorted(
+    os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -2,28 +2,33 @@
 //
 // One cooperative launch, 148 co-resident CTAs, NO grid-wide barriers.  CTAs take roles:
 //
-//   LSTM CTAs (NL = #SM - 8*S - 8)   own a fixed slice of hidden units of the attention LSTM(s)
-//       and of the decoder LSTM.  Their weights are pre-packed (fp32 or fp16) into one contiguous
-//       per-CTA stream in consumption order; a producer thread streams it with TMA bulk copies
-//       (cp.async.bulk + mbarrier) through a shared-memory ring, while a prefix of the stream
-//       stays RESIDENT in shared memory for the whole utterance.  15 consumer warps do row dot
-//       products out of shared memory with the activation slice held in registers.
-//   attention CTAs (8 per stream)    keep processed_memory, a 64-feature slice of the encoder
-//       memory and the alignment state resident in shared memory; fused energy -> sigmoid ->
-//       stepwise-monotonic update -> context reduction with warp shuffles.
-//   aux CTAs (8)                     keep the mel/gate projection and prenet weights resident and
-//       run projection -> stop test -> prenet layer 0 -> layer 1 for the next frame.
+//   LSTM CTAs (128 on a B200)   own a fixed slice of hidden units of the attention LSTM(s) and of the
+//       decoder LSTM.  Their weights are pre-packed (fp32 or fp16) into one contiguous per-CTA stream
+//       in consumption order.  A prefix of the stream (critical-path segments first) is staged ONCE
+//       with TMA bulk copies (cp.async.bulk + mbarrier) and stays RESIDENT in ~195 KB of shared memory
+//       for the whole utterance; the rest is streamed every frame straight from L2/HBM with 16-byte
+//       read-only loads issued 8 deep per lane.  One warp = one hidden unit (4 gate rows at once),
+//       activation slice in registers, 6-shuffle butterfly reduction of the 4 gate sums.
+//   attention CTAs (8 + 4)      keep processed_memory, a feature slice of the encoder memory and the
+//       alignment state resident in shared memory; fused energy -> sigmoid -> stepwise-monotonic
+//       update -> context reduction with warp shuffles.
+//   aux CTAs (8)                keep the mel/gate projection and prenet weights resident and run
+//       projection -> stop test -> prenet layer 0 -> layer 1 for the next frame.
 //
-// Vectors that cross CTAs (h, context, query partials, prenet, mel) travel through global memory
-// in an "LL" protocol: each element is one 64-bit word {fp32 value, frame tag}, written with a
-// single 8-byte store and polled by the consumers -- no fences, no barriers; one L2 round trip
-// per dependency instead of a grid barrier.
+// Vectors that cross CTAs (h, context, query partials, prenet, mel) travel through global memory in an
+// "LL" protocol: each element is one 64-bit word {fp32 value, frame tag}, written with a single 8-byte
+// store and polled by the consumers (all of a thread's words are requested before any is checked) --
+// no fences, no barriers; one L2 round trip per dependency instead of a grid barrier.
 //
 // Per-frame program of an LSTM CTA (segments ordered by when their inputs become available;
 // reference arithmetic: model.py:337-346 attention LSTM, :362-373 decoder LSTM):
 //   a  attn-LSTM  W_hh . h1[t-1]          d  attn-LSTM  W_ih[:, :P] . prenet[t]   -> h1[t], q partials
 //   b  attn-LSTM  W_ih[:, P:] . ctx[t-1]  e  dec-LSTM   W_ih[:, h cols] . h1[t]   (one step per stream)
 //   c  dec-LSTM   W_hh . h2[t-1]          f  dec-LSTM   W_ih[:, ctx cols] . ctx[t] -> h2[t]
+//
+// (An earlier revision streamed the non-resident weights through a TMA ring as well; measured on B200 the
+// single producer thread + 64-96 KB ring capped a CTA at ~10-20 B/clk, below what plain deep LDG streams
+// reach, so the ring was removed -- see DESIGN.md "what did not work".)
 #pragma once
 
 #include <cuda_fp16.h>
@@ -33,14 +38,11 @@
 namespace lat {
 
 constexpr int kThreads = 512;
-constexpr int kConsumerWarps = 15;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kLLDepth = 8;            // ring depth of every LL vector (frames)
-constexpr int kAttnPerStream = 8;      // attention CTAs per stream
-constexpr int kAux = 8;                // aux CTAs
+constexpr int kWarps = kThreads / 32;
+constexpr int kLLDepth = 8;             // ring depth of every LL vector (frames)
+constexpr int kAux = 8;                 // aux CTAs
 constexpr int kMaxU1 = 20, kMaxU2 = 12; // max hidden units per LSTM CTA (attention / decoder LSTM)
-constexpr int kSteps = 7;              // a b c d e0 e1 f
-constexpr int kMaxSlots = 12;
+constexpr int kSteps = 7;               // a b c d e0 e1 f
 constexpr long long kWatchdogClocks = 6000000000LL;
 
 // fixed model dims of this path (hparams defaults); other shapes use the generic kernel
@@ -59,6 +61,7 @@ struct LatStream {
   float *align;                  // [Tcap, T_s]
   const long long* len;          // [1] valid length or null
   int Ts;                        // padded width
+  int na;                        // attention CTAs serving this stream (feature slice = E / na)
 };
 
 struct LatParams {
@@ -70,12 +73,7 @@ struct LatParams {
   int wbytes;                    // bytes per packed weight element (4 = fp32, 2 = fp16)
   const unsigned char* packed;   // per-LSTM-CTA weight streams
   const unsigned long long* packed_off;  // [NL+1] byte offsets
-  int slot_bytes, n_slots, res_budget;   // TMA ring geometry, bytes available for resident chunks
-  int units_per_block;           // hidden units (4-row chunks) moved by one TMA bulk copy
-  int poll_sleep_ns;             // back-off between LL polls
-  int debug_direct;              // diagnostics: 1 = consumers read streamed chunks straight from global memory,
-                                 // 2 = ring on, every streamed row is verified against global memory
-  unsigned long long* dbg;       // [0] = mismatch count, then 8 words per record
+  int res_budget;                // shared-memory bytes available for the resident prefix
   LatStream st[2];
   const float *d_b_ih, *d_b_hh;  // decoder LSTM biases [4H]
   const float *proj_w, *proj_b, *gate_w, *gate_b;
@@ -114,18 +112,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// non-blocking probe (try_wait may suspend the thread for a system-defined time; the producer must not)
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -134,26 +120,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ long long lds_acquire_s64(const volatile long long* p) {
-  long long v;
-  asm volatile("ld.acquire.cta.shared.s64 %0, [%1];" : "=l"(v) : "r"(smem_u32((const void*)p)) : "memory");
-  return v;
+// streamed weights: read-only, do not pollute L1
+__device__ __forceinline__ uint4 ldg_stream(const unsigned char* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
 }
-__device__ __forceinline__ void sts_release_s64(volatile long long* p, long long v) {
-  asm volatile("st.release.cta.shared.s64 [%0], %1;" ::"r"(smem_u32((const void*)p)), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned lds_acquire_u32(const volatile unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void reds_release_inc(volatile unsigned* p) {
-  asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_u32((const void*)p)) : "memory");
-}
-
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
 // LL protocol: one 64-bit word = {value bits (low), tag (high)}
 __device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned tag) {
@@ -170,7 +145,6 @@ struct Watch {
   int* abort_flag;
   long long t0;
   unsigned spins;
-  unsigned sleep_ns;
   __device__ __forceinline__ void arm() { t0 = clock64(); spins = 0; }
   // returns true when the kernel must bail out
   __device__ __forceinline__ bool expired() {
@@ -187,9 +161,35 @@ __device__ __forceinline__ bool ll_wait(const unsigned long long* p, unsigned ta
   for (;;) {
     const unsigned long long x = ll_load(p);
     if ((unsigned)(x >> 32) == tag) { v = __uint_as_float((unsigned)x); return true; }
-    if (w.sleep_ns) __nanosleep(w.sleep_ns);
     if (w.expired()) return false;
   }
+}
+
+// Every thread owns the words i = tid + k * kThreads (k < KMAX) of an n-word LL vector.  All owned words
+// are requested back to back before the first tag is inspected, so a thread pays ONE L2 round trip
+// per poll round instead of one per word.  Values land in dst[i].
+template <int KMAX>
+__device__ __forceinline__ bool poll_vector(const unsigned long long* src, int n, unsigned tag, float* dst, int tid,
+                                            Watch& wd) {
+  unsigned pending = 0;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (tid + k * kThreads < n) pending |= 1u << k;
+  wd.arm();
+  while (pending) {
+    unsigned long long w[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (pending & (1u << k)) w[k] = ll_load(src + tid + k * kThreads);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if ((pending & (1u << k)) && (unsigned)(w[k] >> 32) == tag) {
+        dst[tid + k * kThreads] = __uint_as_float((unsigned)w[k]);
+        pending &= ~(1u << k);
+      }
+    if (pending && wd.expired()) return false;
+  }
+  return true;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -197,199 +197,160 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// fast transcendental forms (ex2.approx / rcp.approx): abs error ~1e-6, used on the attention
-// energies where T*A evaluations per frame sit on the critical path.
+// Reduce four per-lane partial sums over the warp with 6 shuffles (instead of 20): afterwards lanes
+// 0-7 hold the total of v0, 8-15 of v1, 16-23 of v2, 24-31 of v3.
+__device__ __forceinline__ float butterfly4(float v0, float v1, float v2, float v3, int lane) {
+  const bool hi = (lane & 16) != 0;
+  float a = hi ? v2 : v0, b = hi ? v3 : v1;
+  const float sa = hi ? v0 : v2, sb = hi ? v1 : v3;
+  a += __shfl_xor_sync(0xffffffffu, sa, 16);
+  b += __shfl_xor_sync(0xffffffffu, sb, 16);
+  const bool h8 = (lane & 8) != 0;
+  float c = h8 ? b : a;
+  const float sc = h8 ? a : b;
+  c += __shfl_xor_sync(0xffffffffu, sc, 8);
+  c += __shfl_xor_sync(0xffffffffu, c, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
+// fast transcendental forms (ex2 / fast divide): abs error ~1e-6, used on the attention energies where
+// T*A evaluations per frame sit on the critical path.
 __device__ __forceinline__ float fast_tanh(float x) {
   const float e = exp2f(x * 2.8853900817779268f);  // e^(2x)
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// philox_keep / philox_normal come from the including translation unit (taco2dec.cu)
+__device__ __forceinline__ bool philox_keep_l(unsigned long long seed, int mask_id, int row, int idx, unsigned thresh) {
+  return philox_keep(seed, mask_id, row, idx, thresh);
+}
+
 // ---------------------------------------------------------------------------------------------
 // LSTM CTA
 // ---------------------------------------------------------------------------------------------
 struct StepPlan {
-  int n_chunks;      // chunks (hidden units) in this step
-  int kseg;          // columns per row in this step
-  int chunk_bytes;   // 4 rows * kseg * wbytes
-  int n_res;         // first n_res chunks are resident in shared memory
+  int n_units;       // hidden units (4-row chunks) in this step
+  int K;             // columns per row
+  int ksplit;        // column split: items = n_units * ksplit, one item per warp when it fits
+  int chunk_bytes;   // 4 rows * K * wbytes
+  int n_res;         // first n_res units are resident in shared memory
   int res_off;       // byte offset of the step's resident chunks inside the resident region
   long long src_off; // byte offset of the step's first chunk inside this CTA's packed stream
-  int n_blocks;      // TMA blocks (groups of units_per_block streamed chunks) in this step
-  int block_base;    // index of the step's first block within a frame's block sequence
 };
 
-template <int WB>  // bytes per weight element
-struct RowDot;
-
+// 16-byte unit -> multiply-accumulate against the activation registers
+template <int WB>
+struct Mac;
 template <>
-struct RowDot<4> {
-  template <int NU>  // 16-byte units per lane
-  static __device__ __forceinline__ float run(const unsigned char* row, const float* x, int lane) {
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      const float4 w = *reinterpret_cast<const float4*>(row + (size_t)(lane + 32 * i) * 16);
-      acc0 = fmaf(w.x, x[4 * i + 0], acc0);
-      acc1 = fmaf(w.y, x[4 * i + 1], acc1);
-      acc0 = fmaf(w.z, x[4 * i + 2], acc0);
-      acc1 = fmaf(w.w, x[4 * i + 3], acc1);
-    }
-    return acc0 + acc1;
+struct Mac<4> {
+  static constexpr int kElems = 4;
+  static __device__ __forceinline__ void run(const uint4& w, const float* x, float& a0, float& a1) {
+    a0 = fmaf(__uint_as_float(w.x), x[0], a0);
+    a1 = fmaf(__uint_as_float(w.y), x[1], a1);
+    a0 = fmaf(__uint_as_float(w.z), x[2], a0);
+    a1 = fmaf(__uint_as_float(w.w), x[3], a1);
   }
-  static constexpr int kElemsPerUnit = 4;
 };
-
 template <>
-struct RowDot<2> {
-  template <int NU>
-  static __device__ __forceinline__ float run(const unsigned char* row, const float* x, int lane) {
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      const uint4 w = *reinterpret_cast<const uint4*>(row + (size_t)(lane + 32 * i) * 16);
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
-      const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.z));
-      const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
-      acc0 = fmaf(a.x, x[8 * i + 0], acc0);
-      acc1 = fmaf(a.y, x[8 * i + 1], acc1);
-      acc0 = fmaf(b.x, x[8 * i + 2], acc0);
-      acc1 = fmaf(b.y, x[8 * i + 3], acc1);
-      acc0 = fmaf(c.x, x[8 * i + 4], acc0);
-      acc1 = fmaf(c.y, x[8 * i + 5], acc1);
-      acc0 = fmaf(d.x, x[8 * i + 6], acc0);
-      acc1 = fmaf(d.y, x[8 * i + 7], acc1);
-    }
-    return acc0 + acc1;
+struct Mac<2> {
+  static constexpr int kElems = 8;
+  static __device__ __forceinline__ void run(const uint4& w, const float* x, float& a0, float& a1) {
+    const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+    const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+    const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z));
+    const float2 p3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+    a0 = fmaf(p0.x, x[0], a0); a1 = fmaf(p0.y, x[1], a1);
+    a0 = fmaf(p1.x, x[2], a0); a1 = fmaf(p1.y, x[3], a1);
+    a0 = fmaf(p2.x, x[4], a0); a1 = fmaf(p2.y, x[5], a1);
+    a0 = fmaf(p3.x, x[6], a0); a1 = fmaf(p3.y, x[7], a1);
   }
-  static constexpr int kElemsPerUnit = 8;
 };
 
 struct LstmShared {
-  // carved from dynamic shared memory by lstm_cta()
-  unsigned char* ring;
   unsigned char* resident;
-  float *xh1, *xctx, *xh2, *xpre;           // activation segments [S*H], [S*E], [H], [P]
+  const unsigned char* gstream;             // this CTA's packed stream in global memory
+  float *xh1, *xctx, *xh2, *xpre;           // activation segments [2H], [2E], [H], [P]
   float *wq_s;                              // [A][kMaxU1] query-weight slice of this CTA's units
-  float *acc1, *acc2, *c1, *c2, *hloc;      // gate accumulators / cell state / fresh h1 of own units
+  float *acc1, *acc2;                       // gate pre-activations [ksplit 2][unit][4]
+  float *c1, *c2, *hloc;                    // cell state / fresh h1 of own units
   float *bias1, *bias2;                     // b_ih + b_hh of own units [u][4]
-  uint64_t *full, *res_bar;                 // mbarriers (TMA completion); observed in order by the producer only
-  volatile unsigned* consumed;              // [slot] rows consumed so far (4 per use) -> frees the slot
-  volatile long long* landed;               // chunks whose TMA copy has landed (monotonic, published by the producer)
+  uint64_t* res_bar;                        // mbarrier of the one-off resident TMA load
   StepPlan* plan;                           // [kSteps]
   volatile int* exit_flag;
-  const unsigned char* gstream;             // this CTA's packed stream in global memory
-  int direct;
-  unsigned long long* dbg;
-  int units_per_block;
 };
 
-// consume one step: every (chunk, gate-row) item is one warp-level dot product of KSEG columns
-template <int WB, int KSEG>
-__device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
-                                             long long frame_block_base, int n_slots, int slot_bytes, int warp,
-                                             int lane, Watch& wd, bool& ok) {
-  const int G = sh.units_per_block;
-  unsigned long long* p_dbg = sh.dbg;
-  constexpr int EPU = RowDot<WB>::kElemsPerUnit;
-  constexpr int NU = KSEG / (32 * EPU);
-  static_assert(NU >= 1, "segment too short");
-  float x[NU * EPU];
+// One item = one hidden unit (4 gate rows) x one column range of KLEN columns, done by one warp.
+// All 4 * PU sixteen-byte weight loads of a pass are issued before the first is used (memory-level
+// parallelism is what hides the L2/HBM latency of the streamed part); the activation slice is read from
+// shared memory right behind them.
+template <int WB, int KLEN, int PU, bool kGlobal>
+__device__ __forceinline__ void dot4(const unsigned char* base, int row_bytes, const float* xs, int lane, float (&s)[4]) {
+  constexpr int EPU = Mac<WB>::kElems;
+  constexpr int NU = KLEN / (32 * EPU);
+  static_assert(NU >= 1 && NU % PU == 0, "bad pass width");
+  float a[4][2];
 #pragma unroll
-  for (int i = 0; i < NU; ++i)
+  for (int g = 0; g < 4; ++g) a[g][0] = a[g][1] = 0.f;
 #pragma unroll
-    for (int e = 0; e < EPU; e += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)(lane + 32 * i) * EPU + e);
-      x[i * EPU + e + 0] = v.x; x[i * EPU + e + 1] = v.y; x[i * EPU + e + 2] = v.z; x[i * EPU + e + 3] = v.w;
+  for (int i0 = 0; i0 < NU; i0 += PU) {
+    uint4 w[4][PU];
+#pragma unroll
+    for (int i = 0; i < PU; ++i)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const unsigned char* ptr = base + (size_t)g * row_bytes + (size_t)(lane + 32 * (i0 + i)) * 16;
+        w[g][i] = kGlobal ? ldg_stream(ptr) : *reinterpret_cast<const uint4*>(ptr);
+      }
+#pragma unroll
+    for (int i = 0; i < PU; ++i) {
+      float x[EPU];
+#pragma unroll
+      for (int e = 0; e < EPU; e += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)(lane + 32 * (i0 + i)) * EPU + e);
+        x[e + 0] = v.x; x[e + 1] = v.y; x[e + 2] = v.z; x[e + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) Mac<WB>::run(w[g][i], x, a[g][0], a[g][1]);
     }
-  const int n_items = sp.n_chunks * 4;
-  for (int it = warp; it < n_items; it += kConsumerWarps) {
-    const int ci = it >> 2, g = it & 3;
-    const unsigned char* base;
-    volatile unsigned* release = nullptr;
-    if (ci < sp.n_res) {
-      base = sh.resident + sp.res_off + (size_t)ci * sp.chunk_bytes;
-    } else if (sh.direct == 1) {
-      base = sh.gstream + sp.src_off + (size_t)ci * sp.chunk_bytes;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) s[g] = a[g][0] + a[g][1];
+}
+
+template <int WB, int KLEN>
+__device__ __forceinline__ void consume_items(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
+                                              int max_units, int warp, int lane) {
+  constexpr int EPU = Mac<WB>::kElems;
+  constexpr int NU = KLEN / (32 * EPU);
+  constexpr int PU = NU >= 4 ? 4 : NU;
+  const int n_items = sp.n_units * sp.ksplit;
+  for (int it = warp; it < n_items; it += kWarps) {
+    const int unit = it / sp.ksplit, kh = it - unit * sp.ksplit;
+    const float* xk = xs + (size_t)kh * KLEN;
+    float s[4];
+    const int row_bytes = sp.K * WB;
+    const size_t col_off = (size_t)kh * KLEN * WB;
+    if (unit < sp.n_res) {
+      dot4<WB, KLEN, PU, false>(sh.resident + sp.res_off + (size_t)unit * sp.chunk_bytes + col_off, row_bytes, xk, lane, s);
     } else {
-      const int rs = ci - sp.n_res;                       // index among the step's streamed chunks
-      const long long seq = frame_block_base + sp.block_base + rs / G;
-      const int slot = (int)(seq % n_slots);
-      wd.arm();
-      // Only the producer thread looks at the TMA mbarriers (it sees every use of every slot in order,
-      // so phase parity is exact); it republishes completion as a monotonic chunk counter.
-      while (lds_acquire_s64(sh.landed) <= seq) {
-        if (wd.expired()) { ok = false; break; }
-      }
-      if (!ok) break;
-      base = sh.ring + (size_t)slot * slot_bytes + (size_t)(rs % G) * sp.chunk_bytes;
-      release = &sh.consumed[slot];
-      if (sh.direct == 2) {
-        // verify this row against the packed stream in global memory
-        const unsigned char* gsrc = sh.gstream + sp.src_off + (size_t)ci * sp.chunk_bytes + (size_t)g * KSEG * WB;
-        const unsigned char* ssrc = base + (size_t)g * KSEG * WB;
-        int bad = 0;
-        for (int i = lane; i < KSEG * WB / 16; i += 32) {
-          const uint4 a = *reinterpret_cast<const uint4*>(ssrc + (size_t)i * 16);
-          const uint4 b = *reinterpret_cast<const uint4*>(gsrc + (size_t)i * 16);
-          if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) ++bad;
-        }
-        const unsigned any = __ballot_sync(0xffffffffu, bad != 0);
-        if (any) {
-          // re-check after a delay: does it become right (early read) or stay wrong (overwritten / wrong data)?
-          const long long t0 = clock64();
-          while (clock64() - t0 < 200000) {}
-          int bad2 = 0, prev_match = 0, next_match = 0;
-          const long long step_bytes = sp.chunk_bytes;
-          for (int i = lane; i < KSEG * WB / 16; i += 32) {
-            const uint4 a = *reinterpret_cast<const uint4*>(ssrc + (size_t)i * 16);
-            const uint4 b = *reinterpret_cast<const uint4*>(gsrc + (size_t)i * 16);
-            if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) ++bad2;
-          }
-          const unsigned any2 = __ballot_sync(0xffffffffu, bad2 != 0);
-          if (lane == 0) {
-            const unsigned long long k = atomicAdd(p_dbg, 1ull);
-            if (k < 60) {
-              unsigned long long* r = p_dbg + 8 + k * 8;
-              r[0] = ((unsigned long long)blockIdx.x << 32) | (unsigned)(seq / 1);
-              r[1] = ((unsigned long long)(unsigned)slot << 32) | (unsigned)it;
-              r[2] = ((unsigned long long)any << 32) | any2;
-              r[3] = (unsigned long long)(*sh.landed);
-              r[4] = (unsigned long long)sp.kseg;
-              r[5] = (unsigned long long)frame_block_base;
-              r[6] = (unsigned long long)sp.block_base;
-              r[7] = (unsigned long long)step_bytes;
-            }
-          }
-          (void)prev_match; (void)next_match;
-        }
-      }
+      dot4<WB, KLEN, PU, true>(sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + col_off, row_bytes, xk, lane, s);
     }
-    float v = RowDot<WB>::template run<NU>(base + (size_t)g * KSEG * WB, x, lane);
-    v = warp_sum(v);
-    if (lane == 0) {
-      acc[it] += v;
-      if (release) reds_release_inc(release);   // 4 rows per use free the slot
-    }
+    const float c = butterfly4(s[0], s[1], s[2], s[3], lane);
+    if ((lane & 7) == 0) acc[((size_t)kh * max_units + unit) * 4 + (lane >> 3)] += c;
   }
 }
 
-// all consumer threads poll an LL vector into shared memory
-__device__ __forceinline__ bool poll_vector(const unsigned long long* src, int n, unsigned tag, float* dst, int ctid,
-                                            Watch& wd) {
-  bool ok = true;
-  for (int i = ctid; i < n && ok; i += kConsumerThreads) {
-    float v;
-    ok = ll_wait(src + i, tag, v, wd);
-    dst[i] = v;
-  }
-  return ok;
-}
-
-// philox_keep / philox_normal come from the including translation unit (taco2dec.cu)
-__device__ __forceinline__ bool philox_keep_l(unsigned long long seed, int mask_id, int row, int idx, unsigned thresh) {
-  return philox_keep(seed, mask_id, row, idx, thresh);
+// runtime column-length dispatch (K / ksplit is one of 1024, 512, 256)
+template <int WB>
+__device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
+                                             int max_units, int warp, int lane) {
+  if (sp.n_units == 0) return;
+  const int klen = sp.K / sp.ksplit;
+  if (klen == 1024) consume_items<WB, 1024>(sh, sp, xs, acc, max_units, warp, lane);
+  else if (klen == 512) consume_items<WB, 512>(sh, sp, xs, acc, max_units, warp, lane);
+  else consume_items<WB, 256>(sh, sp, xs, acc, max_units, warp, lane);
 }
 
 template <int WB>
@@ -408,38 +369,36 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   LstmShared sh;
   size_t off = 0;
   auto take = [&](size_t bytes) { unsigned char* q = smem + off; off += (bytes + 127) & ~(size_t)127; return q; };
-  sh.ring = take((size_t)p.n_slots * p.slot_bytes);
   sh.resident = take((size_t)p.res_budget);
   sh.xh1 = (float*)take(sizeof(float) * 2 * H);
   sh.xctx = (float*)take(sizeof(float) * 2 * E);
   sh.xh2 = (float*)take(sizeof(float) * H);
   sh.xpre = (float*)take(sizeof(float) * P);
   sh.wq_s = (float*)take(sizeof(float) * A * kMaxU1);
-  sh.acc1 = (float*)take(sizeof(float) * kMaxU1 * 4);
-  sh.acc2 = (float*)take(sizeof(float) * kMaxU2 * 4);
+  sh.acc1 = (float*)take(sizeof(float) * 2 * kMaxU1 * 4);
+  sh.acc2 = (float*)take(sizeof(float) * 2 * kMaxU2 * 4);
   sh.c1 = (float*)take(sizeof(float) * kMaxU1);
   sh.c2 = (float*)take(sizeof(float) * kMaxU2);
   sh.hloc = (float*)take(sizeof(float) * kMaxU1);
   sh.bias1 = (float*)take(sizeof(float) * kMaxU1 * 4);
   sh.bias2 = (float*)take(sizeof(float) * kMaxU2 * 4);
-  sh.full = (uint64_t*)take(sizeof(uint64_t) * kMaxSlots);
-  sh.consumed = (volatile unsigned*)take(sizeof(unsigned) * kMaxSlots);
   sh.res_bar = (uint64_t*)take(sizeof(uint64_t));
   sh.plan = (StepPlan*)take(sizeof(StepPlan) * kSteps);
   sh.exit_flag = (volatile int*)take(sizeof(int));
-  sh.landed = (volatile long long*)take(sizeof(long long));
+  sh.gstream = p.packed + p.packed_off[lc];
 
-  // ---- step plan (thread 0) ---------------------------------------------------------------
+  // ---- step plan + one-off TMA load of the resident prefix (thread 0) ---------------------
   if (tid == 0) {
     // steps:            a     b     c     d     e0    e1            f
-    const int nch[kSteps] = {nu1, nu1, nu2, nu1, nu2, S == 2 ? nu2 : 0, nu2};
+    const int nun[kSteps] = {nu1, nu1, nu2, nu1, nu2, S == 2 ? nu2 : 0, nu2};
     const int ks[kSteps] = {H, E, H, P, H, H, S * E};
     long long src = 0;
     for (int s = 0; s < kSteps; ++s) {
       StepPlan& sp = sh.plan[s];
-      sp.n_chunks = nch[s]; sp.kseg = ks[s]; sp.chunk_bytes = 4 * ks[s] * WB; sp.n_res = 0; sp.res_off = 0;
+      sp.n_units = nun[s]; sp.K = ks[s]; sp.chunk_bytes = 4 * ks[s] * WB; sp.n_res = 0; sp.res_off = 0;
+      sp.ksplit = (nun[s] * 2 <= kWarps && ks[s] >= 512) ? 2 : 1;   // keep every warp busy
       sp.src_off = src;
-      src += (long long)nch[s] * sp.chunk_bytes;
+      src += (long long)nun[s] * sp.chunk_bytes;
     }
     // residency: critical-path steps first (d, f), then e1, e0, c, b, a
     const int prio[kSteps] = {3, 6, 5, 4, 2, 1, 0};
@@ -447,36 +406,40 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     for (int k = 0; k < kSteps; ++k) {
       StepPlan& sp = sh.plan[prio[k]];
       int n = sp.chunk_bytes > 0 ? left / sp.chunk_bytes : 0;
-      if (n > sp.n_chunks) n = sp.n_chunks;
+      if (n > sp.n_units) n = sp.n_units;
       sp.n_res = n; sp.res_off = roff;
       roff += n * sp.chunk_bytes; left -= n * sp.chunk_bytes;
     }
-    int bb = 0;
-    for (int s = 0; s < kSteps; ++s) {
-      StepPlan& sp = sh.plan[s];
-      sp.n_blocks = (sp.n_chunks - sp.n_res + p.units_per_block - 1) / p.units_per_block;
-      sp.block_base = bb;
-      bb += sp.n_blocks;
-    }
-    for (int i = 0; i < p.n_slots; ++i) { mbar_init(&sh.full[i], 1); sh.consumed[i] = 0u; }
     mbar_init(sh.res_bar, 1);
-    *sh.exit_flag = 0;
-    *sh.landed = 0;
     fence_barrier_init();
+    *sh.exit_flag = 0;
+    unsigned res_total = 0;
+    for (int s = 0; s < kSteps; ++s) res_total += (unsigned)(sh.plan[s].n_res * sh.plan[s].chunk_bytes);
+    if (res_total) {
+      mbar_expect_tx(sh.res_bar, res_total);
+      for (int s = 0; s < kSteps; ++s) {
+        const StepPlan& sp = sh.plan[s];
+        for (int c = 0; c < sp.n_res; ++c)
+          tma_load_1d(sh.resident + sp.res_off + (size_t)c * sp.chunk_bytes,
+                      sh.gstream + sp.src_off + (size_t)c * sp.chunk_bytes, (unsigned)sp.chunk_bytes, sh.res_bar);
+      }
+    } else {
+      mbar_arrive(sh.res_bar);
+    }
   }
   // zero state, load biases and the query-weight slice
   for (int i = tid; i < 2 * H; i += kThreads) sh.xh1[i] = 0.f;
   for (int i = tid; i < 2 * E; i += kThreads) sh.xctx[i] = 0.f;
   for (int i = tid; i < H; i += kThreads) sh.xh2[i] = 0.f;
   for (int i = tid; i < P; i += kThreads) sh.xpre[i] = 0.f;
+  for (int i = tid; i < 2 * kMaxU1 * 4; i += kThreads) sh.acc1[i] = 0.f;
+  for (int i = tid; i < 2 * kMaxU2 * 4; i += kThreads) sh.acc2[i] = 0.f;
   for (int i = tid; i < kMaxU1 * 4; i += kThreads) {
     const int u = i >> 2, g = i & 3;
-    sh.acc1[i] = 0.f;
     sh.bias1[i] = u < nu1 ? p.st[s1].b_ih[g * H + u1_0 + u] + p.st[s1].b_hh[g * H + u1_0 + u] : 0.f;
   }
   for (int i = tid; i < kMaxU2 * 4; i += kThreads) {
     const int u = i >> 2, g = i & 3;
-    sh.acc2[i] = 0.f;
     sh.bias2[i] = u < nu2 ? p.d_b_ih[g * H + u2_0 + u] + p.d_b_hh[g * H + u2_0 + u] : 0.f;
   }
   for (int i = tid; i < kMaxU1; i += kThreads) { sh.c1[i] = 0.f; sh.hloc[i] = 0.f; }
@@ -487,109 +450,15 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   }
   __syncthreads();
 
-  const unsigned char* my_stream = p.packed + p.packed_off[lc];
-  sh.gstream = my_stream;
-  sh.direct = p.debug_direct;
-  sh.units_per_block = p.units_per_block;
-  sh.dbg = p.dbg;
-  int blocks_per_frame = 0;
-  for (int s = 0; s < kSteps; ++s) blocks_per_frame += sh.plan[s].n_blocks;
-  const int n_steps = p.n_steps;
-
-  // ======================= producer warp: TMA weight streaming =============================
-  if (warp == kConsumerWarps) {
-    if (lane == 0) {
-      Watch wd{p.abort_flag, 0, 0, (unsigned)p.poll_sleep_ns};
-      // resident prefix: loaded once, lives for the whole utterance
-      unsigned res_total = 0;
-      for (int s = 0; s < kSteps; ++s) res_total += (unsigned)(sh.plan[s].n_res * sh.plan[s].chunk_bytes);
-      if (res_total) {
-        mbar_expect_tx(sh.res_bar, res_total);
-        for (int s = 0; s < kSteps; ++s) {
-          const StepPlan& sp = sh.plan[s];
-          for (int c = 0; c < sp.n_res; ++c)
-            tma_load_1d(sh.resident + sp.res_off + (size_t)c * sp.chunk_bytes,
-                        my_stream + sp.src_off + (size_t)c * sp.chunk_bytes, (unsigned)sp.chunk_bytes, sh.res_bar);
-        }
-      } else {
-        mbar_arrive(sh.res_bar);
-      }
-      // event loop: issue the next block when its slot is free, confirm landings strictly in order
-      const int G = p.units_per_block;
-      const long long total = p.debug_direct == 1 ? 0 : (long long)n_steps * blocks_per_frame;
-      long long issue = 0, land = 0;
-      int it_s = 0, it_b = 0;            // (step, block) of the next block to issue
-      unsigned exp_rows[kMaxSlots];      // rows the consumers must have retired before a slot may be refilled
-#pragma unroll
-      for (int i = 0; i < kMaxSlots; ++i) exp_rows[i] = 0u;
-      auto advance = [&]() {             // skip steps without streamed blocks (wraps per frame)
-        while (it_b >= sh.plan[it_s].n_blocks) { it_b = 0; it_s = (it_s + 1) % kSteps; }
-      };
-      wd.arm();
-      bool live = total > 0;
-      if (live) advance();
-      while (live && land < total) {
-        bool progressed = false;
-        while (issue < total && issue - land < p.n_slots) {
-          const int slot = (int)(issue % p.n_slots);
-          if (lds_acquire_u32(&sh.consumed[slot]) < exp_rows[slot]) break;
-          const StepPlan& sp = sh.plan[it_s];
-          const int first = sp.n_res + it_b * G;
-          const int units = min(G, sp.n_chunks - first);
-          const unsigned bytes = (unsigned)(units * sp.chunk_bytes);
-          mbar_expect_tx(&sh.full[slot], bytes);
-          tma_load_1d(sh.ring + (size_t)slot * p.slot_bytes, my_stream + sp.src_off + (size_t)first * sp.chunk_bytes, bytes,
-                      &sh.full[slot]);
-          exp_rows[slot] += 4u * (unsigned)units;
-          ++issue;
-          ++it_b;
-          advance();
-          progressed = true;
-        }
-        {
-          // probe up to 4 in-flight blocks with independent (overlapping) test_waits, accept the landed prefix
-          bool f[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const long long q = land + k;
-            f[k] = q < issue && mbar_test_wait(&sh.full[(int)(q % p.n_slots)], (unsigned)((q / p.n_slots) & 1));
-          }
-          int n = 0;
-          if (f[0]) { n = 1; if (f[1]) { n = 2; if (f[2]) { n = 3; if (f[3]) n = 4; } } }
-          if (n) { land += n; sts_release_s64(sh.landed, land); progressed = true; }
-        }
-        if (progressed) { wd.arm(); continue; }
-        if (*sh.exit_flag) {
-          // consumers are gone: stop issuing, but every issued copy must land before the CTA exits
-          wd.arm();
-          while (land < issue) {
-            const int sl = (int)(land % p.n_slots);
-            const unsigned par = (unsigned)((land / p.n_slots) & 1);
-            if (mbar_try_wait(&sh.full[sl], par)) { ++land; continue; }
-            if (wd.expired()) break;
-          }
-          break;
-        }
-        if (wd.expired()) live = false;
-      }
-      wd.arm();
-      while (!mbar_try_wait(sh.res_bar, 0)) {
-        if (wd.expired()) break;
-      }
-    }
-    return;
-  }
-
-  // ======================= consumer warps ===================================================
-  Watch wd{p.abort_flag, 0, 0, (unsigned)p.poll_sleep_ns};
+  Watch wd{p.abort_flag, 0, 0};
   bool ok = true;
-  const int ctid = tid;  // 0..479
-  const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
-  // wait for the resident prefix
+  // wait for the resident prefix (async-proxy writes become visible through the mbarrier)
   wd.arm();
   while (!mbar_try_wait(sh.res_bar, 0)) {
     if (wd.expired()) { ok = false; break; }
   }
+  const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
+  const int n_steps = p.n_steps;
   long long ph_t = clock64();
   long long ph[16];
 #pragma unroll
@@ -602,49 +471,45 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   }
 
   const StepPlan* pl = sh.plan;
-  for (int t = 0; t < n_steps && ok; ++t) {
-    const long long fbase = (long long)t * blocks_per_frame;
+  for (int t = 0; t < n_steps; ++t) {
     const unsigned tag_prev = (unsigned)t;        // values produced during frame t-1
     const unsigned tag_cur = (unsigned)t + 1u;    // values produced during frame t
     const int rb = t % kLLDepth, rb_prev = (t + kLLDepth - 1) % kLLDepth;
 
-    // a: W_hh . h1[t-1]  (own stream)            b: W_ih[:, P:] . ctx[t-1]
-    consume_step<WB, H>(sh, pl[0], sh.xh1 + s1 * H, sh.acc1, fbase, p.n_slots, p.slot_bytes, warp, lane, wd, ok);
-    consume_step<WB, E>(sh, pl[1], sh.xctx + s1 * E, sh.acc1, fbase, p.n_slots, p.slot_bytes, warp, lane, wd, ok);
+    // b: W_ih[:, P:] . ctx[t-1]      (a: W_hh . h1[t-1] already ran during the previous frame's attention wait)
+    consume_step<WB>(sh, pl[1], sh.xctx + s1 * E, sh.acc1, kMaxU1, warp, lane);
     LPH(0)
     // c: W_hh(dec) . h2[t-1]
-    if (t > 0) ok = ok && poll_vector(p.ll_h2 + (size_t)rb_prev * H, H, tag_prev, sh.xh2, ctid, wd);
-    consumer_sync();
+    if (t > 0) ok = poll_vector<2>(p.ll_h2 + (size_t)rb_prev * H, H, tag_prev, sh.xh2, tid, wd) && ok;
+    __syncthreads();
     LPH(1)
-    consume_step<WB, H>(sh, pl[2], sh.xh2, sh.acc2, fbase, p.n_slots, p.slot_bytes, warp, lane, wd, ok);
+    consume_step<WB>(sh, pl[2], sh.xh2, sh.acc2, kMaxU2, warp, lane);
     LPH(2)
     // d: W_ih[:, :P] . prenet[t]
     if (p.free_running) {
       // stop word first: the aux CTAs publish it with the prenet of frame t
-      int stop = 0;
-      if (ctid == 0) {
+      if (tid == 0) {
         float sv = 0.f;
-        ok = ll_wait(p.ll_pre + ((size_t)rb * 2 + 0) * (P + 8) + P, tag_cur, sv, wd) && ok;
-        stop = sv != 0.f;
-        if (stop || !ok) *sh.exit_flag = 1;
+        const bool got = ll_wait(p.ll_pre + ((size_t)rb * 2 + 0) * (P + 8) + P, tag_cur, sv, wd);
+        if (!got || sv != 0.f) *sh.exit_flag = 1;
       }
-      consumer_sync();
+      __syncthreads();
       if (*sh.exit_flag) break;
-      ok = ok && poll_vector(p.ll_pre + ((size_t)rb * 2 + s1) * (P + 8), P, tag_cur, sh.xpre, ctid, wd);
+      ok = poll_vector<1>(p.ll_pre + ((size_t)rb * 2 + s1) * (P + 8), P, tag_cur, sh.xpre, tid, wd) && ok;
     } else {
-      for (int i = ctid; i < P; i += kConsumerThreads) sh.xpre[i] = __ldg(p.st[s1].pre_tf + (size_t)t * P + i);
+      for (int i = tid; i < P; i += kThreads) sh.xpre[i] = __ldg(p.st[s1].pre_tf + (size_t)t * P + i);
     }
-    consumer_sync();
+    __syncthreads();
     LPH(3)
-    consume_step<WB, P>(sh, pl[3], sh.xpre, sh.acc1, fbase, p.n_slots, p.slot_bytes, warp, lane, wd, ok);
-    consumer_sync();
+    consume_step<WB>(sh, pl[3], sh.xpre, sh.acc1, kMaxU1, warp, lane);
+    __syncthreads();
     // attention-LSTM pointwise (gate order i,f,g,o), dropout on h and c when training
-    if (ctid < nu1) {
-      const int u = ctid, j = u1_0 + u;
-      const float ig = sigmoid_acc(sh.acc1[u * 4 + 0] + sh.bias1[u * 4 + 0]);
-      const float fg = sigmoid_acc(sh.acc1[u * 4 + 1] + sh.bias1[u * 4 + 1]);
-      const float gg = tanhf(sh.acc1[u * 4 + 2] + sh.bias1[u * 4 + 2]);
-      const float og = sigmoid_acc(sh.acc1[u * 4 + 3] + sh.bias1[u * 4 + 3]);
+    if (tid < nu1) {
+      const int u = tid, j = u1_0 + u;
+      float pre[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pre[g] = (sh.acc1[u * 4 + g] + sh.acc1[(kMaxU1 + u) * 4 + g]) + sh.bias1[u * 4 + g];
+      const float ig = sigmoid_acc(pre[0]), fg = sigmoid_acc(pre[1]), gg = tanhf(pre[2]), og = sigmoid_acc(pre[3]);
       float cn = fg * sh.c1[u] + ig * gg;
       float hn = og * tanhf(cn);
       if (p.training) {
@@ -659,32 +524,35 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       sh.hloc[u] = hn;
       ll_store(p.ll_h1 + ((size_t)rb * 2 + s1) * H + j, hn, tag_cur);
     }
-    consumer_sync();
-    if (ctid >= A && ctid < A + kMaxU1 * 4) sh.acc1[ctid - A] = 0.f;   // next write is after two more syncs
+    __syncthreads();
     // query partials: q_part[a] = sum_u Wq[a, u] h1[u]  (attention.py:56, 368), one row of the reduction tree
-    if (ctid < A) {
+    if (tid < A) {
       float qv = 0.f;
-      for (int u = 0; u < nu1; ++u) qv = fmaf(sh.wq_s[ctid * kMaxU1 + u], sh.hloc[u], qv);
-      ll_store(p.ll_q + (((size_t)rb * 2 + s1) * p.NL1 + i1) * A + ctid, qv, tag_cur);
+      for (int u = 0; u < nu1; ++u) qv = fmaf(sh.wq_s[tid * kMaxU1 + u], sh.hloc[u], qv);
+      ll_store(p.ll_q + (((size_t)rb * 2 + s1) * p.NL1 + i1) * A + tid, qv, tag_cur);
+    } else if (tid - A < 2 * kMaxU1 * 4) {
+      sh.acc1[tid - A] = 0.f;   // next accumulation is several barriers away
     }
     LPH(4)
     // e: W_ih(dec)[:, h cols] . h1[t]   (all streams)
-    ok = ok && poll_vector(p.ll_h1 + (size_t)rb * 2 * H, S * H, tag_cur, sh.xh1, ctid, wd);
-    consumer_sync();
+    ok = poll_vector<4>(p.ll_h1 + (size_t)rb * 2 * H, S * H, tag_cur, sh.xh1, tid, wd) && ok;
+    __syncthreads();
     LPH(5)
-    consume_step<WB, H>(sh, pl[4], sh.xh1, sh.acc2, fbase, p.n_slots, p.slot_bytes, warp, lane, wd, ok);
-    if (S == 2) consume_step<WB, H>(sh, pl[5], sh.xh1 + H, sh.acc2, fbase, p.n_slots, p.slot_bytes, warp, lane, wd, ok);
+    consume_step<WB>(sh, pl[4], sh.xh1, sh.acc2, kMaxU2, warp, lane);
+    consume_step<WB>(sh, pl[5], sh.xh1 + H, sh.acc2, kMaxU2, warp, lane);
     LPH(6)
+    // a of the NEXT frame: W_hh . h1[t] needs only h1[t]; it fills the wait for the attention CTAs
+    consume_step<WB>(sh, pl[0], sh.xh1 + s1 * H, sh.acc1, kMaxU1, warp, lane);
+    LPH(9)
     // f: W_ih(dec)[:, ctx cols] . ctx[t]
-    ok = ok && poll_vector(p.ll_ctx + (size_t)rb * 2 * E, S * E, tag_cur, sh.xctx, ctid, wd);
-    consumer_sync();
+    ok = poll_vector<2>(p.ll_ctx + (size_t)rb * 2 * E, S * E, tag_cur, sh.xctx, tid, wd) && ok;
+    __syncthreads();
     LPH(7)
-    if (S == 2) consume_step<WB, 2 * E>(sh, pl[6], sh.xctx, sh.acc2, fbase, p.n_slots, p.slot_bytes, warp, lane, wd, ok);
-    else        consume_step<WB, E>(sh, pl[6], sh.xctx, sh.acc2, fbase, p.n_slots, p.slot_bytes, warp, lane, wd, ok);
-    consumer_sync();
+    consume_step<WB>(sh, pl[6], sh.xctx, sh.acc2, kMaxU2, warp, lane);
+    __syncthreads();
     // flow control (teacher-forced only): the aux CTAs are not in the dependency loop, so do not
     // overwrite LL slot t % depth before they have consumed frame t - depth
-    if (!p.free_running && t >= kLLDepth && ctid == 0) {
+    if (!p.free_running && t >= kLLDepth && tid == 0) {
       const unsigned need = (unsigned)kAux * (unsigned)(t - kLLDepth + 1);
       wd.arm();
       for (;;) {
@@ -694,12 +562,12 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
         if (wd.expired()) { ok = false; break; }
       }
     }
-    if (ctid < nu2) {
-      const int u = ctid, j = u2_0 + u;
-      const float ig = sigmoid_acc(sh.acc2[u * 4 + 0] + sh.bias2[u * 4 + 0]);
-      const float fg = sigmoid_acc(sh.acc2[u * 4 + 1] + sh.bias2[u * 4 + 1]);
-      const float gg = tanhf(sh.acc2[u * 4 + 2] + sh.bias2[u * 4 + 2]);
-      const float og = sigmoid_acc(sh.acc2[u * 4 + 3] + sh.bias2[u * 4 + 3]);
+    if (tid < nu2) {
+      const int u = tid, j = u2_0 + u;
+      float pre[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pre[g] = (sh.acc2[u * 4 + g] + sh.acc2[(kMaxU2 + u) * 4 + g]) + sh.bias2[u * 4 + g];
+      const float ig = sigmoid_acc(pre[0]), fg = sigmoid_acc(pre[1]), gg = tanhf(pre[2]), og = sigmoid_acc(pre[3]);
       float cn = fg * sh.c2[u] + ig * gg;
       float hn = og * tanhf(cn);
       if (p.training) {
@@ -713,15 +581,12 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       sh.c2[u] = cn;
       ll_store(p.ll_h2 + (size_t)rb * H + j, hn, tag_cur);
     }
-    consumer_sync();
-    if (ctid < kMaxU2 * 4) sh.acc2[ctid] = 0.f;
-    LPH(8)
-    // a CTA-uniform view of `ok` (a warp may have hit the watchdog)
     if (!ok) *sh.exit_flag = 1;
-    consumer_sync();
+    __syncthreads();
+    if (tid < 2 * kMaxU2 * 4) sh.acc2[tid] = 0.f;
+    LPH(8)
     if (*sh.exit_flag) break;
   }
-  if (tid == 0) *sh.exit_flag = 1;  // releases the producer if it is parked on an empty slot
   if (lc == 0 && tid == 0)
     for (int i = 0; i < 16; ++i) p.phase_clocks[i] = ph[i];
 #undef LPH
@@ -735,16 +600,17 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ts = sp.Ts;
   const int Teff = sp.len ? min((int)sp.len[0], Ts) : Ts;
-  constexpr int FS = E / kAttnPerStream;  // 64 features per CTA
+  const int FS = E / sp.na;                 // context features owned by this CTA (64 or 128)
+  const int NJ = kThreads / FS;             // position groups in the context reduction
   float* sm = reinterpret_cast<float*>(smem_raw);
   float* pm_s = sm;                         // [Ts][A]
   float* mem_s = pm_s + (size_t)Ts * A;     // [Ts][FS]
   float* q_s = mem_s + (size_t)Ts * FS;     // [4][A] partial sums, then q in row 0
   float* v_s = q_s + 4 * A;                 // [A]
-  float* red_s = v_s + A;                   // [8][FS]
-  float* al_s = red_s + 8 * FS;             // [Ts] alignment state
-  float* pr_s = al_s + Ts;                  // [Ts] probabilities
-  float* an_s = pr_s + Ts;                  // [Ts] new alignment
+  float* red_s = v_s + A;                   // [NJ][FS] = kThreads
+  float* al_s = red_s + kThreads;           // [Ts] alignment state
+  float* pr_s = al_s + Ts;                  // [Ts + 4] probabilities
+  float* an_s = pr_s + Ts + 4;              // [Ts] new alignment
   __shared__ int s_stop;
 
   for (int i = tid; i < Ts * A; i += kThreads) pm_s[i] = sp.pm[i];
@@ -757,7 +623,7 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
   if (tid == 0) s_stop = 0;
   __syncthreads();
 
-  Watch wd{p.abort_flag, 0, 0, (unsigned)p.poll_sleep_ns};
+  Watch wd{p.abort_flag, 0, 0};
   const int NL1 = p.NL1;
   for (int t = 0; t < p.n_steps; ++t) {
     const unsigned tag = (unsigned)t + 1u;
@@ -765,45 +631,72 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
     if (p.free_running) {
       if (tid == 0) {
         float sv = 0.f;
-        const bool ok = ll_wait(p.ll_pre + ((size_t)rb * 2 + 0) * (P + 8) + P, tag, sv, wd);
-        if (!ok || sv != 0.f) s_stop = 1;
+        const bool got = ll_wait(p.ll_pre + ((size_t)rb * 2 + 0) * (P + 8) + P, tag, sv, wd);
+        if (!got || sv != 0.f) s_stop = 1;
       }
       __syncthreads();
       if (s_stop) break;
     }
-    // ---- q = sum over LSTM CTAs of their partials ---------------------------------------
+    // ---- q = sum over LSTM CTAs of their partials: thread (part, a) owns CTAs part, part+4, ... ----
     {
-      const int part = tid >> 7, a = tid & (A - 1);  // 4 parts x 128
-      const unsigned long long* src = p.ll_q + ((size_t)rb * 2 + s) * NL1 * A;
+      const int part = tid >> 7, a = tid & (A - 1);
+      const unsigned long long* src = p.ll_q + ((size_t)rb * 2 + s) * NL1 * A + a;
+      constexpr int KQ = 16;                       // words in flight per thread per round
       float acc = 0.f;
-      bool ok = true;
-      for (int c = part; c < NL1 && ok; c += 4) {
-        float v;
-        ok = ll_wait(src + (size_t)c * A + a, tag, v, wd);
-        acc += v;
+      bool good = true;
+      for (int c0 = part; c0 < NL1 && good; c0 += 4 * KQ) {
+        unsigned pending = 0;
+        float val[KQ];
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          val[k] = 0.f;
+          if (c0 + 4 * k < NL1) pending |= 1u << k;
+        }
+        wd.arm();
+        while (pending) {
+          unsigned long long w[KQ];
+#pragma unroll
+          for (int k = 0; k < KQ; ++k)
+            if (pending & (1u << k)) w[k] = ll_load(src + (size_t)(c0 + 4 * k) * A);
+#pragma unroll
+          for (int k = 0; k < KQ; ++k)
+            if ((pending & (1u << k)) && (unsigned)(w[k] >> 32) == tag) {
+              val[k] = __uint_as_float((unsigned)w[k]);
+              pending &= ~(1u << k);
+            }
+          if (pending && wd.expired()) { good = false; break; }
+        }
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) acc += val[k];      // fixed order: deterministic
       }
-      if (!ok) s_stop = 1;
+      if (!good) s_stop = 1;
       q_s[part * A + a] = acc;
     }
     __syncthreads();
     if (s_stop) break;
     if (tid < A) q_s[tid] = (q_s[tid] + q_s[A + tid]) + (q_s[2 * A + tid] + q_s[3 * A + tid]);
     __syncthreads();
-    // ---- energies e_j = v . tanh(q + pm_j), p_j = sigmoid(e_j [+ 2 N(0,1)]) ---------------
+    // ---- energies e_j = v . tanh(q + pm_j), p_j = sigmoid(e_j [+ 2 N(0,1)]); a warp does 4 positions ----
     {
       const float q0 = q_s[lane], q1 = q_s[lane + 32], q2 = q_s[lane + 64], q3 = q_s[lane + 96];
       const float v0 = v_s[lane], v1 = v_s[lane + 32], v2 = v_s[lane + 64], v3 = v_s[lane + 96];
-      for (int j = warp; j < Teff; j += kThreads / 32) {
-        const float* r = pm_s + (size_t)j * A;
-        float e = v0 * fast_tanh(q0 + r[lane]) + v1 * fast_tanh(q1 + r[lane + 32]) +
+      for (int j0 = warp * 4; j0 < Teff; j0 += kWarps * 4) {
+        float e[4];
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+          const int j = min(j0 + pp, Teff - 1);
+          const float* r = pm_s + (size_t)j * A;
+          e[pp] = v0 * fast_tanh(q0 + r[lane]) + v1 * fast_tanh(q1 + r[lane + 32]) +
                   v2 * fast_tanh(q2 + r[lane + 64]) + v3 * fast_tanh(q3 + r[lane + 96]);
-        e = warp_sum(e);
-        if (lane == 0) {
+        }
+        float ev = butterfly4(e[0], e[1], e[2], e[3], lane);
+        const int j = j0 + (lane >> 3);
+        if ((lane & 7) == 0 && j < Teff) {
           if (p.training) {
             const float nz = sp.noise ? sp.noise[(size_t)t * Ts + j] : philox_normal(p.seed, 10 + s, t, j);
-            e += 2.0f * nz;
+            ev += 2.0f * nz;
           }
-          pr_s[j] = sigmoid_acc(e);
+          pr_s[j] = sigmoid_acc(ev);
         }
       }
       for (int j = Teff + tid; j < Ts; j += kThreads) pr_s[j] = 0.f;   // sigmoid(-inf), attention.py:388-391
@@ -818,19 +711,18 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
       if (g == 0) sp.align[(size_t)t * Ts + j] = a;
     }
     __syncthreads();
-    // ---- context slice: 8 position groups x 64 features ----------------------------------
+    // ---- context slice: NJ position groups x FS features ----------------------------------
     {
-      const int f = tid & (FS - 1), jg = tid >> 6;
+      const int f = tid % FS, jg = tid / FS;
       float acc = 0.f;
-      for (int j = jg; j < Ts; j += 8) acc = fmaf(an_s[j], mem_s[(size_t)j * FS + f], acc);
+      for (int j = jg; j < Ts; j += NJ) acc = fmaf(an_s[j], mem_s[(size_t)j * FS + f], acc);
       red_s[jg * FS + f] = acc;
     }
     for (int j = tid; j < Ts; j += kThreads) al_s[j] = an_s[j];
     __syncthreads();
     if (tid < FS) {
       float c = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) c += red_s[k * FS + tid];
+      for (int k = 0; k < NJ; ++k) c += red_s[k * FS + tid];
       ll_store(p.ll_ctx + ((size_t)rb * 2 + s) * E + g * FS + tid, c, tag);
     }
     __syncthreads();
@@ -873,7 +765,7 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
   if (tid == 0) s_stop = 0;
   __syncthreads();
 
-  Watch wd{p.abort_flag, 0, 0, (unsigned)p.poll_sleep_ns};
+  Watch wd{p.abort_flag, 0, 0};
   // prenet of frame 0 = prenet(go-frame of zeros) = zeros (model.py:444-450); stop word = 0
   if (p.free_running) {
     for (int i = tid; i < S * PR; i += kThreads) {
@@ -887,22 +779,21 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
     const unsigned tag = (unsigned)t + 1u;
     const int rb = t % kLLDepth, rbn = (t + 1) % kLLDepth;
     // ---- y = [h2_t | ctx_t | ctx_bert_t] ---------------------------------------------------
-    bool ok = true;
-    for (int i = tid; i < H && ok; i += kThreads) { float v; ok = ll_wait(p.ll_h2 + (size_t)rb * H + i, tag, v, wd); y_s[i] = v; }
-    for (int i = tid; i < S * E && ok; i += kThreads) { float v; ok = ll_wait(p.ll_ctx + (size_t)rb * 2 * E + i, tag, v, wd); y_s[H + i] = v; }
+    bool ok = poll_vector<2>(p.ll_h2 + (size_t)rb * H, H, tag, y_s, tid, wd);
+    ok = poll_vector<2>(p.ll_ctx + (size_t)rb * 2 * E, S * E, tag, y_s + H, tid, wd) && ok;
     if (!ok) s_stop = 1;
     __syncthreads();
     if (s_stop) break;
     // ---- projection rows (one warp per row) ------------------------------------------------
     if (warp < nr) {
       const float* w = wp_s + (size_t)warp * KD;
-      float acc = 0.f;
+      float acc0 = 0.f, acc1 = 0.f;
       for (int k = lane * 4; k < KD; k += 128) {
         const float4 a = *reinterpret_cast<const float4*>(w + k);
         const float4 b = *reinterpret_cast<const float4*>(y_s + k);
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+        acc0 = fmaf(a.x, b.x, acc0); acc1 = fmaf(a.y, b.y, acc1); acc0 = fmaf(a.z, b.z, acc0); acc1 = fmaf(a.w, b.w, acc1);
       }
-      acc = warp_sum(acc);
+      const float acc = warp_sum(acc0 + acc1);
       if (lane == 0) {
         const int row = r0 + warp;
         if (row < M) {
@@ -928,8 +819,7 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
       continue;
     }
     // ---- mel_t (+ stop word) from all aux CTAs ----------------------------------------------
-    ok = true;
-    for (int i = tid; i < M + 1 && ok; i += kThreads) { float v; ok = ll_wait(p.ll_mel + (size_t)rb * (M + 16) + i, tag, v, wd); mel_s[i] = v; }
+    ok = poll_vector<1>(p.ll_mel + (size_t)rb * (M + 16), M + 1, tag, mel_s, tid, wd);
     if (!ok) s_stop = 1;
     __syncthreads();
     if (s_stop) break;
@@ -937,7 +827,7 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
     if (x == 0 && tid == 0) ll_store(p.ll_pre + ((size_t)rbn * 2 + 0) * (P + 8) + P, stop ? 1.f : 0.f, tag + 1u);
     if (stop) break;
     // ---- prenet layer 0 rows of this CTA: relu(W0 mel) * keep * 2 ----------------------------
-    for (int it = warp; it < S * PR; it += kThreads / 32) {
+    for (int it = warp; it < S * PR; it += kWarps) {
       const int s = it / PR, r = it - s * PR, row = x * PR + r;
       const float* w = w0_s + ((size_t)s * PR + r) * M;
       float acc = 0.f;
@@ -950,12 +840,11 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
       }
     }
     // ---- prenet layer 1 -------------------------------------------------------------------
-    ok = true;
-    for (int i = tid; i < S * P && ok; i += kThreads) { float v; ok = ll_wait(p.ll_l0 + (size_t)rbn * 2 * P + i, tag + 1u, v, wd); l0_s[i] = v; }
+    ok = poll_vector<1>(p.ll_l0 + (size_t)rbn * 2 * P, S * P, tag + 1u, l0_s, tid, wd);
     if (!ok) s_stop = 1;
     __syncthreads();
     if (s_stop) break;
-    for (int it = warp; it < S * PR; it += kThreads / 32) {
+    for (int it = warp; it < S * PR; it += kWarps) {
       const int s = it / PR, r = it - s * PR, row = x * PR + r;
       const float* w = w1_s + ((size_t)s * PR + r) * P;
       const float* in = l0_s + (size_t)s * P;
@@ -980,13 +869,15 @@ template <int WB>
 __global__ void __launch_bounds__(kThreads, 1) decoder_latency(const __grid_constant__ LatParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   const int b = blockIdx.x;
+  const int na = p.st[0].na + (p.S == 2 ? p.st[1].na : 0);
   if (b < p.NL) {
     lstm_cta<WB>(p, b, dyn_smem);
-  } else if (b < p.NL + p.S * kAttnPerStream) {
+  } else if (b < p.NL + na) {
     const int k = b - p.NL;
-    attention_cta(p, k / kAttnPerStream, k % kAttnPerStream, dyn_smem);
-  } else if (b < p.NL + p.S * kAttnPerStream + kAux) {
-    aux_cta(p, b - p.NL - p.S * kAttnPerStream, dyn_smem);
+    if (k < p.st[0].na) attention_cta(p, 0, k, dyn_smem);
+    else attention_cta(p, 1, k - p.st[0].na, dyn_smem);
+  } else if (b < p.NL + na + kAux) {
+    aux_cta(p, b - p.NL - na, dyn_smem);
   }
 }
 

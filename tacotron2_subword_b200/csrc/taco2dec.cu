@@ -1001,12 +1001,26 @@ int fill_common(taco2dec_handle* h, Params& p, int B, int T_in, int T_sub, const
 // Latency path (latency.cuh): eligibility, weight packing, launch
 // ------------------------------------------------------------------------------------------
 struct LatGeometry {
-  int NL, NL1, wbytes, slot_bytes, n_slots, res_budget, units_per_block;
+  int NL, NL1, wbytes, res_budget, na[2];
   size_t smem;
 };
 
 constexpr size_t kLatFixedSmem = 31744;   // activation segments, query slice, accumulators, barriers
 constexpr size_t kLatDynSmem = 231424;    // 226 KB of the 227 KB opt-in maximum
+
+LatGeometry lat_geometry(const taco2dec_handle* h, int wbytes) {
+  LatGeometry g;
+  const int S = h->cfg.n_streams;
+  // attention CTAs: 8 feature slices for the phoneme stream, 4 for the (about 3x shorter) sub-word stream
+  g.na[0] = 8; g.na[1] = S == 2 ? 4 : 0;
+  int NL = h->num_sms - g.na[0] - g.na[1] - lat::kAux;
+  if (NL > 128) NL = 128;               // 1024 hidden units / 128 CTAs = 8 (decoder) and 16 (attention) per CTA
+  NL = NL / (2 * S) * (2 * S);
+  g.NL = NL; g.NL1 = NL / S; g.wbytes = wbytes;
+  g.res_budget = (int)((kLatDynSmem - kLatFixedSmem) / 128 * 128);
+  g.smem = kLatDynSmem;
+  return g;
+}
 
 bool lat_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
   const taco2dec_config& c = h->cfg;
@@ -1014,27 +1028,15 @@ bool lat_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
   if (c.attn_rnn_dim != lat::H || c.dec_rnn_dim != lat::H || c.enc_dim != lat::E || c.prenet_dim != lat::P ||
       c.attn_dim != lat::A || c.n_mel != lat::M)
     return false;
-  if (h->num_sms < 64 || (size_t)h->max_smem_optin < kLatDynSmem) return false;
-  const int Tm = std::max(T_in, c.n_streams == 2 ? T_sub : 1);
-  const size_t att = ((size_t)Tm * lat::A + (size_t)Tm * (lat::E / lat::kAttnPerStream) + 5 * lat::A +
-                      8 * (lat::E / lat::kAttnPerStream) + 3 * (size_t)Tm) * sizeof(float);
-  return att <= kLatDynSmem;
-}
-
-LatGeometry lat_geometry(const taco2dec_handle* h, int wbytes) {
-  LatGeometry g;
-  const int S = h->cfg.n_streams;
-  int NL = h->num_sms - S * lat::kAttnPerStream - lat::kAux;
-  NL = NL / S * S;
-  g.NL = NL; g.NL1 = NL / S; g.wbytes = wbytes;
-  g.units_per_block = 2;
-  { const char* e = getenv("TACO2DEC_UNITS_PER_BLOCK"); if (e && atoi(e) >= 1 && atoi(e) <= 4) g.units_per_block = atoi(e); }
-  g.slot_bytes = g.units_per_block * 4 * lat::H * wbytes;
-  g.n_slots = (wbytes == 4 ? 98304 : 65536) / g.slot_bytes;
-  { const char* e = getenv("TACO2DEC_RING_SLOTS"); if (e && atoi(e) >= 2 && atoi(e) <= lat::kMaxSlots) g.n_slots = atoi(e); }
-  g.res_budget = (int)((kLatDynSmem - kLatFixedSmem - (size_t)g.n_slots * g.slot_bytes) / 128 * 128);
-  g.smem = kLatDynSmem;
-  return g;
+  if (h->num_sms < 84 || (size_t)h->max_smem_optin < kLatDynSmem) return false;
+  const LatGeometry g = lat_geometry(h, 4);
+  const int Ts[2] = {T_in, T_sub};
+  for (int s = 0; s < c.n_streams; ++s) {
+    const size_t fs = lat::E / g.na[s];
+    const size_t att = ((size_t)Ts[s] * (lat::A + fs) + 5 * lat::A + lat::kThreads + 3 * (size_t)Ts[s] + 8) * sizeof(float);
+    if (att > kLatDynSmem) return false;
+  }
+  return true;
 }
 
 size_t lat_ll_words(const taco2dec_handle* h) {
@@ -1095,19 +1097,13 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   p.Tcap = gp.Tcap; p.gate_thr = gp.gate_thr; p.p_att = gp.p_att; p.p_dec = gp.p_dec;
   p.thresh_pre = gp.thresh_pre; p.thresh_att = gp.thresh_att; p.thresh_dec = gp.thresh_dec; p.seed = gp.seed;
   p.wbytes = g.wbytes; p.packed = h->packed; p.packed_off = h->packed_off;
-  p.slot_bytes = g.slot_bytes; p.n_slots = g.n_slots; p.res_budget = g.res_budget; p.units_per_block = g.units_per_block;
-  { const char* e = getenv("TACO2DEC_DEBUG_DIRECT"); p.debug_direct = e ? atoi(e) : 0; }
-  { const char* e = getenv("TACO2DEC_POLL_SLEEP_NS"); p.poll_sleep_ns = e ? atoi(e) : 0; }
-  static unsigned long long* s_dbg = nullptr;
-  if (!s_dbg) CUDA_TRY(cudaMalloc(&s_dbg, 8192));
-  CUDA_TRY(cudaMemsetAsync(s_dbg, 0, 8192, st));
-  p.dbg = s_dbg;
+  p.res_budget = g.res_budget;
   for (int s = 0; s < c.n_streams; ++s) {
     const StreamParams& sp = gp.st[s];
     lat::LatStream& ls = p.st[s];
     ls.b_ih = sp.b_ih; ls.b_hh = sp.b_hh; ls.wq = sp.wq; ls.v = sp.v; ls.pre_w0 = sp.pre_w0; ls.pre_w1 = sp.pre_w1;
     ls.mem = sp.mem; ls.pm = sp.pm; ls.pre_tf = sp.pre; ls.noise = sp.noise; ls.keep0 = sp.keep0; ls.keep1 = sp.keep1;
-    ls.align = sp.align; ls.Ts = sp.Ts; ls.len = sp.len;
+    ls.align = sp.align; ls.Ts = sp.Ts; ls.len = sp.len; ls.na = g.na[s];
   }
   p.d_b_ih = gp.d_b_ih; p.d_b_hh = gp.d_b_hh; p.proj_w = gp.proj_w; p.proj_b = gp.proj_b; p.gate_w = gp.gate_w;
   p.gate_b = gp.gate_b; p.lstm_keep = gp.lstm_keep; p.mel = gp.mel; p.gate = gp.gate; p.n_frames = gp.n_frames;
@@ -1136,17 +1132,6 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   if (h->profiling) { CUDA_TRY(cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
   h->launches++;
   h->last_path = TACO2DEC_PATH_LATENCY;
-  if (p.debug_direct == 2) {
-    unsigned long long host[8 + 60 * 8];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(host, s_dbg, sizeof(host), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[dbg] ring mismatches: %llu (slots %d, streamed chunks differ per CTA)\n", host[0], g.n_slots);
-    for (unsigned long long k = 0; k < host[0] && k < 60; ++k) {
-      unsigned long long* r = host + 8 + k * 8;
-      fprintf(stderr, "[dbg] cta %llu seq %llu slot %llu item %llu lanes_bad %08llx after_delay %08llx issued %llu kseg %llu fbase %llu sbase %llu\n",
-              r[0] >> 32, r[0] & 0xffffffffull, r[1] >> 32, r[1] & 0xffffffffull, r[2] >> 32, r[2] & 0xffffffffull, r[3], r[4], r[5], r[6]);
-    }
-  }
   return 0;
 }
 

@@ -29,7 +29,7 @@ if eng.last_path() == "generic":
     for k, n in enumerate(names):
         print(f"  {n:4s} work {pc[2*k]/1e6:8.2f} kcyc/frame ({100*pc[2*k]/tot:5.1f}%)   barrier {pc[2*k+1]/1e6:8.2f} kcyc/frame ({100*pc[2*k+1]/tot:5.1f}%)")
 else:
-    names = ["a+b compute", "wait h2[t-1]", "c compute", "wait prenet[t] (aux chain)", "d compute + pointwise + q",
-             "wait h1[t]", "e compute", "wait ctx[t] (attention)", "f compute + pointwise"]
+    names = ["b compute", "wait h2[t-1]", "c compute", "wait prenet[t] (aux chain)", "d compute + pointwise + q",
+             "wait h1[t]", "e compute", "wait ctx[t] (attention)", "f compute + pointwise", "a(t+1) compute"]
     for k, n in enumerate(names):
         print(f"  {n:32s} {pc[k]/1e6:8.2f} kcyc/frame ({100*pc[k]/tot:5.1f}%)")
