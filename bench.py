@@ -161,6 +161,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--weights", default="fp32", choices=["fp32", "fp16"],
+                    help="storage of the packed LSTM matrices on the latency path (headline = fp32, the reference's dtype)")
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "latency"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -192,6 +195,7 @@ def main():
     dec.load_state_dict(w, strict=True)
     dec = dec.to(dev).eval()
     dec.rng_seed = 2024 + rank               # production mode: Philox prenet dropout in-kernel
+    dec.decoder_path, dec.weight_dtype = args.path, args.weights
     frames = CFG["max_steps"]
 
     mem_host = inp["memory"].pin_memory()
@@ -221,6 +225,8 @@ def main():
         out = resident_step()
         assert int(out[4][0]) == frames and int(out[5][0]) == 1
     e2e_step()
+    path_taken = eng.last_path()
+    mel_ref = out[0].clone()
 
     # ---------------- value: inputs resident in HBM, device-timed ----------------
     sampler = ClockSampler(local_rank)
@@ -268,9 +274,28 @@ def main():
     h2d = mem_host.numel() * 4 + emb_host.numel() * 4
     d2h = mel_h.numel() * 4 + gate_h.numel() * 4
 
+    # ---------------- secondary variant: fp16 storage of the three LSTM matrices (same kernel family) ------
+    variant = None
+    if args.weights == "fp32" and path_taken == "latency":
+        dec.weight_dtype = "fp16"
+        for _ in range(3):
+            out16 = resident_step()
+        v_ms = []
+        for _ in range(max(3, args.steps // 2)):
+            flush.fill_(1)
+            resident_step()
+            v_ms.append(eng.last_kernel_ms())
+        torch.cuda.synchronize(dev)
+        err = float((out16[0] - mel_ref).abs().max())
+        dec.weight_dtype = "fp32"
+        variant = {"weights": "fp16 LSTM matrices (fp32 accumulate, everything else fp32)", "kernel_ms": statistics.mean(v_ms),
+                   "us_per_frame": 1e3 * statistics.mean(v_ms) / frames, "frames_per_sec_1gpu": frames / (statistics.mean(v_ms) * 1e-3),
+                   "mel_max_abs_vs_fp32_over_1000_free_running_frames": err}
     if rank == 0:
         peak, peak_src = measured_peaks()
-        bpf = algorithmic_bytes_per_frame(1, CFG["T_in"], CFG["T_sub"], 4)
+        wb = 4 if args.weights == "fp32" else 2
+        bpf = (algorithmic_bytes_per_frame(1, CFG["T_in"], CFG["T_sub"], 4) if wb == 4
+               else 31_457_280 * 2 + 624_977 * 4 + (algorithmic_bytes_per_frame(1, CFG["T_in"], CFG["T_sub"], 4) - W_ACT * 4))
         k_ms = statistics.mean(kern_ms)
         achieved = bpf * frames / (k_ms * 1e-3) / 1e9
         traffic = None
@@ -282,16 +307,21 @@ def main():
         line = {
             "metric": "mel_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": statistics.mean(step_ms), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+            "vs_baseline": None, "dtype": "f32" if args.weights == "fp32" else "f16-weights/f32-accumulate",
+            "data": "synthetic", "config": dict(workload_config(), kernel_path=path_taken, weights=args.weights),
             "latency_ms_p50": statistics.median(step_ms), "us_per_frame": 1e3 * k_ms / frames,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "latency_ms_p50": statistics.median(e2e_ms)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "decoder_persistent<1>", "kernel_ms": k_ms,
+                         "traffic": traffic if (args.weights == "fp32" and path_taken == "latency") else None,
+                         "kernel": ("lat::decoder_latency<%d>" % wb) if path_taken == "latency" else "decoder_persistent<1>",
+                         "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": bpf * frames, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)"},
         }
+        if variant is not None:
+            line["variants"] = [variant]
         if n_gpus == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             time_cpu_port(w, inp, 20, 1, threads)

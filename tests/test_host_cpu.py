@@ -1,0 +1,137 @@
+"""CPU: host-side logic of the drop-in boundary (no GPU compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tacotron2_subword_b200 import BERT_Tacotron2, Decoder, Tacotron2, _cabi, create_hparams
+from tacotron2_subword_b200.utils import get_mask_from_lengths
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI shared library loads and exports exactly what include/taco2dec.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "taco2dec.h")).read()
+    declared = set(re.findall(r"\b(taco2dec_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "header declares no functions?"
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
+    lib.taco2dec_abi_version.restype = ctypes.c_int
+    assert lib.taco2dec_abi_version() == _cabi.ABI_VERSION
+
+
+def test_ctypes_structs_match_header_field_order():
+    hdr = open(os.path.join(ROOT, "include", "taco2dec.h")).read()
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                m = re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*(\[[^\]]*\])*\s*$", part.strip())
+                names.append(m.group(1))
+        return names
+
+    assert fields("taco2dec_config") == [f[0] for f in _cabi.Config._fields_]
+    assert fields("taco2dec_stream_weights") == [f[0] for f in _cabi.StreamWeights._fields_]
+    assert fields("taco2dec_weights") == [f[0] for f in _cabi.Weights._fields_]
+    assert fields("taco2dec_rng") == [f[0] for f in _cabi.Rng._fields_]
+    assert fields("taco2dec_tf_args") == [f[0] for f in _cabi.TFArgs._fields_]
+    assert fields("taco2dec_infer_args") == [f[0] for f in _cabi.InferArgs._fields_]
+
+
+def test_create_refuses_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    lib = _cabi.load_library()
+    cfg = _cabi.Config(80, 512, 1024, 1024, 256, 128, 32, 31, 0, 2, 0.1, 0.1)
+    h = ctypes.c_void_p()
+    rc = lib.taco2dec_create(ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc != 0 and lib.taco2dec_last_error()          # no device -> loud error, never a CPU fallback
+
+
+def test_create_rejects_bad_config():
+    lib = _cabi.load_library()
+    cfg = _cabi.Config(80, 512, 1024, 1024, 256, 128, 32, 31, 7, 2, 0.1, 0.1)   # attention kind 7
+    h = ctypes.c_void_p()
+    assert lib.taco2dec_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
+    assert b"attention" in lib.taco2dec_last_error()
+
+
+def test_decoder_has_no_cpu_path():
+    dec = Decoder(create_hparams())
+    with pytest.raises(_cabi.Taco2DecError):
+        dec(torch.zeros(1, 3, 512), torch.zeros(1, 2, 512), torch.zeros(1, 80, 4), torch.tensor([3]), torch.tensor([2]))
+    with pytest.raises(ValueError):
+        dec.inference(torch.zeros(2, 3, 512), torch.zeros(2, 2, 512))          # batch-1 only, model.py:461
+
+
+def test_get_mask_from_lengths_exact():
+    lens = torch.tensor([3, 5, 1])
+    m = get_mask_from_lengths(lens)
+    assert m.dtype == torch.bool and m.shape == (3, 5)
+    assert m.tolist() == [[1, 1, 1, 0, 0], [1, 1, 1, 1, 1], [1, 0, 0, 0, 0]]
+
+
+def test_hparams_string_override_keeps_reference_semantics():
+    hp = create_hparams("{attention:LocationSensitiveAttention-batch_size:16}}")
+    assert hp.attention == "LocationSensitiveAttention"
+    assert hp.batch_size == "16"            # values stay strings (hparams.py:108-114)
+    assert hp.max_decoder_steps == 1000 and hp.gate_threshold == 0.001 and hp.p_attention_dropout == 0.1
+
+
+def test_attention_choice_and_stream_variants():
+    hp = create_hparams()
+    sma = Decoder(hp).state_dict()
+    assert "attention_layer_bert.v.weight" in sma and sma["decoder_rnn.weight_ih"].shape == (4096, 3072)
+    assert "decoder_rnn_bert.weight_ih" in sma            # dead cell stays in the checkpoint layout
+    hp.attention = "LocationSensitiveAttention"
+    lsa = Decoder(hp).state_dict()
+    assert lsa["attention_layer_bert.location_layer.location_conv.conv.weight"].shape == (32, 2, 31)
+    assert "attention_layer.v.linear_layer.weight" in lsa
+    one = Decoder(hp, n_streams=1).state_dict()
+    assert one["decoder_rnn.weight_ih"].shape == (4096, 1536) and one["linear_projection.linear_layer.weight"].shape == (80, 1536)
+    hp.attention = "GMMAttention"
+    with pytest.raises(ValueError):
+        Decoder(hp)
+    assert sum(p.numel() for p in Tacotron2(create_hparams()).parameters()) > 2e7
+
+
+@pytest.mark.reference
+def test_state_dict_layout_identical_to_reference():
+    import contextlib, io
+    from oracle.ref_shim import import_reference
+    ref_model, _, ref_hp = import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ref_model.BERT_Tacotron2(ref_hp.create_hparams())
+    mine = BERT_Tacotron2(create_hparams())
+    a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    assert list(a) == list(b) and a == b
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    assert dict(ref_hp.create_hparams()) == dict(create_hparams())
+
+
+@pytest.mark.reference
+def test_oracle_vs_live_reference():
+    """Re-run the unmodified reference live (build container only) against the oracle on a fresh case."""
+    from oracle.decoder_oracle import DecoderOracle
+    from oracle.make_golden import run_reference
+    from oracle.synth import SMA
+    from tests.helpers import materialise, maxabs
+    case = dict(mode="tf", attention=SMA, B=2, T_in=14, T_sub=5, T=5, ragged=True, training=True, seed=77)
+    ref = run_reference(case)
+    w, inp, plan = materialise(case)
+    out = DecoderOracle(w, SMA).forward(inp["memory"], inp["embeddings"], inp["mels"], inp["memory_lengths"],
+                                        inp["bert_lengths"], plan, training=True)
+    for k, v in zip(("mel", "gate", "align", "align_bert"), out):
+        assert maxabs(v, torch.from_numpy(ref[k])) <= 2e-6, k

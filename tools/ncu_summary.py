@@ -1,0 +1,22 @@
+"""Summarise an .ncu-rep (raw page) to the handful of counters DESIGN.md / profiles/ cite."""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_bytes.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_lsu.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg",
+        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+for r in rows[2:]:
+    name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+    print("kernel:", name[:80])
+    for k in keys:
+        if k in hdr:
+            i = hdr.index(k)
+            print(f"  {k:75s} {r[i]:>18s} {units[i]}")
