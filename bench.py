@@ -20,6 +20,7 @@ reference decoder timed on this box's host cores.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -218,7 +219,8 @@ def main():
         with torch.no_grad():
             m = mem_host.to(dev, non_blocking=True)
             e = emb_host.to(dev, non_blocking=True)
-            mel, gate, al, alb, flag = dec.inference(m, e)
+            with contextlib.redirect_stdout(sys.stderr):      # the API prints "Warning! Reached max decoder steps"
+                mel, gate, al, alb, flag = dec.inference(m, e)
             return mel.cpu(), gate.cpu(), flag
 
     for _ in range(args.warmup):
