@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtaco2dec.so")
+LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtaco2dec.so")  # env override: A/B builds
 
 ATTN_SMA, ATTN_LSA = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_LATENCY = 0, 1, 2

@@ -41,6 +41,7 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kLLDepth = 8;             // ring depth of every LL vector (frames)
 constexpr int kAux = 8;                 // aux CTAs
+constexpr int kRep = 8;                 // replicas of every vector polled by all LSTM CTAs (spreads the L2 hot spot)
 constexpr int kMaxU1 = 20, kMaxU2 = 12; // max hidden units per LSTM CTA (attention / decoder LSTM)
 constexpr int kSteps = 7;               // a b c d e0 e1 f
 constexpr long long kWatchdogClocks = 6000000000LL;
@@ -74,6 +75,7 @@ struct LatParams {
   const unsigned char* packed;   // per-LSTM-CTA weight streams
   const unsigned long long* packed_off;  // [NL+1] byte offsets
   int res_budget;                // shared-memory bytes available for the resident prefix
+  int l2_keep_mask;              // bit s set: step s's streamed weights use L2 evict_last, else evict_first
   LatStream st[2];
   const float *d_b_ih, *d_b_hh;  // decoder LSTM biases [4H]
   const float *proj_w, *proj_b, *gate_w, *gate_b;
@@ -121,13 +123,23 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// streamed weights: read-only, do not pollute L1
-__device__ __forceinline__ uint4 ldg_stream(const unsigned char* p) {
+// streamed weights: read-only, do not pollute L1, explicit L2 eviction policy per segment
+__device__ __forceinline__ uint4 ldg_stream(const unsigned char* p, unsigned long long policy) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
+               : "l"(p), "l"(policy));
   return r;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 
 // LL protocol: one 64-bit word = {value bits (low), tag (high)}
@@ -140,6 +152,12 @@ __device__ __forceinline__ unsigned long long ll_load(const unsigned long long* 
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return w;
 }
+
+// replica r of a replicated LL vector (layout [rep][depth][...])
+__device__ __forceinline__ unsigned long long* rep_h1(const LatParams& p, int r) { return p.ll_h1 + (size_t)r * kLLDepth * 2 * H; }
+__device__ __forceinline__ unsigned long long* rep_h2(const LatParams& p, int r) { return p.ll_h2 + (size_t)r * kLLDepth * H; }
+__device__ __forceinline__ unsigned long long* rep_ctx(const LatParams& p, int r) { return p.ll_ctx + (size_t)r * kLLDepth * 2 * E; }
+__device__ __forceinline__ unsigned long long* rep_pre(const LatParams& p, int r) { return p.ll_pre + (size_t)r * kLLDepth * 2 * (P + 8); }
 
 struct Watch {
   int* abort_flag;
@@ -238,6 +256,7 @@ struct StepPlan {
   int n_res;         // first n_res units are resident in shared memory
   int res_off;       // byte offset of the step's resident chunks inside the resident region
   long long src_off; // byte offset of the step's first chunk inside this CTA's packed stream
+  unsigned long long policy;  // L2 eviction policy of the step's streamed loads
 };
 
 // 16-byte unit -> multiply-accumulate against the activation registers
@@ -286,7 +305,8 @@ struct LstmShared {
 // parallelism is what hides the L2/HBM latency of the streamed part); the activation slice is read from
 // shared memory right behind them.
 template <int WB, int KLEN, int PU, bool kGlobal>
-__device__ __forceinline__ void dot4(const unsigned char* base, int row_bytes, const float* xs, int lane, float (&s)[4]) {
+__device__ __forceinline__ void dot4(const unsigned char* base, int row_bytes, const float* xs, int lane, float (&s)[4],
+                                     unsigned long long policy) {
   constexpr int EPU = Mac<WB>::kElems;
   constexpr int NU = KLEN / (32 * EPU);
   static_assert(NU >= 1 && NU % PU == 0, "bad pass width");
@@ -301,7 +321,7 @@ __device__ __forceinline__ void dot4(const unsigned char* base, int row_bytes, c
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const unsigned char* ptr = base + (size_t)g * row_bytes + (size_t)(lane + 32 * (i0 + i)) * 16;
-        w[g][i] = kGlobal ? ldg_stream(ptr) : *reinterpret_cast<const uint4*>(ptr);
+        w[g][i] = kGlobal ? ldg_stream(ptr, policy) : *reinterpret_cast<const uint4*>(ptr);
       }
 #pragma unroll
     for (int i = 0; i < PU; ++i) {
@@ -324,7 +344,11 @@ __device__ __forceinline__ void consume_items(const LstmShared& sh, const StepPl
                                               int max_units, int warp, int lane) {
   constexpr int EPU = Mac<WB>::kElems;
   constexpr int NU = KLEN / (32 * EPU);
-  constexpr int PU = NU >= 4 ? 4 : NU;
+#ifndef TACO2DEC_STREAM_PU
+#define TACO2DEC_STREAM_PU 4
+#endif
+  constexpr int PU = NU >= 4 ? 4 : NU;                                  // resident (shared memory) pass width
+  constexpr int PUG = NU >= TACO2DEC_STREAM_PU ? TACO2DEC_STREAM_PU : NU;   // streamed (L2/HBM) pass width
   const int n_items = sp.n_units * sp.ksplit;
   for (int it = warp; it < n_items; it += kWarps) {
     const int unit = it / sp.ksplit, kh = it - unit * sp.ksplit;
@@ -333,9 +357,10 @@ __device__ __forceinline__ void consume_items(const LstmShared& sh, const StepPl
     const int row_bytes = sp.K * WB;
     const size_t col_off = (size_t)kh * KLEN * WB;
     if (unit < sp.n_res) {
-      dot4<WB, KLEN, PU, false>(sh.resident + sp.res_off + (size_t)unit * sp.chunk_bytes + col_off, row_bytes, xk, lane, s);
+      dot4<WB, KLEN, PU, false>(sh.resident + sp.res_off + (size_t)unit * sp.chunk_bytes + col_off, row_bytes, xk, lane, s, 0ull);
     } else {
-      dot4<WB, KLEN, PU, true>(sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + col_off, row_bytes, xk, lane, s);
+      dot4<WB, KLEN, PUG, true>(sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + col_off, row_bytes, xk, lane, s,
+                                 sp.policy);
     }
     const float c = butterfly4(s[0], s[1], s[2], s[3], lane);
     if ((lane & 7) == 0) acc[((size_t)kh * max_units + unit) * 4 + (lane >> 3)] += c;
@@ -351,6 +376,28 @@ __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPla
   if (klen == 1024) consume_items<WB, 1024>(sh, sp, xs, acc, max_units, warp, lane);
   else if (klen == 512) consume_items<WB, 512>(sh, sp, xs, acc, max_units, warp, lane);
   else consume_items<WB, 256>(sh, sp, xs, acc, max_units, warp, lane);
+}
+
+// LSTM pointwise for nu hidden units: lane 4u+g evaluates gate g (i, f, g, o), the 4-lane group combines
+// them with shuffles; returns true in the lanes (g == 0) that own (hn, cn) of unit u.
+__device__ __forceinline__ bool lstm_pointwise(const float* acc, int max_units, const float* bias, const float* c_state,
+                                               int nu, int tid, int& u_out, float& hn, float& cn) {
+  const int nact = nu * 4;
+  if ((tid & ~31) >= nact) return false;                 // whole warp idle
+  const bool valid = tid < nact;
+  const int u = valid ? (tid >> 2) : 0, g = tid & 3;
+  const float pre = (acc[u * 4 + g] + acc[(max_units + u) * 4 + g]) + bias[u * 4 + g];
+  const float act = (g == 2) ? tanhf(pre) : sigmoid_acc(pre);
+  const int base = (tid & 31) & ~3;
+  const float ig = __shfl_sync(0xffffffffu, act, base + 0);
+  const float fg = __shfl_sync(0xffffffffu, act, base + 1);
+  const float gg = __shfl_sync(0xffffffffu, act, base + 2);
+  const float og = __shfl_sync(0xffffffffu, act, base + 3);
+  if (!valid || g != 0) return false;
+  cn = fg * c_state[u] + ig * gg;
+  hn = og * tanhf(cn);
+  u_out = u;
+  return true;
 }
 
 template <int WB>
@@ -373,7 +420,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   sh.xh1 = (float*)take(sizeof(float) * 2 * H);
   sh.xctx = (float*)take(sizeof(float) * 2 * E);
   sh.xh2 = (float*)take(sizeof(float) * H);
-  sh.xpre = (float*)take(sizeof(float) * P);
+  sh.xpre = (float*)take(sizeof(float) * (P + 8));
   sh.wq_s = (float*)take(sizeof(float) * A * kMaxU1);
   sh.acc1 = (float*)take(sizeof(float) * 2 * kMaxU1 * 4);
   sh.acc2 = (float*)take(sizeof(float) * 2 * kMaxU2 * 4);
@@ -397,6 +444,9 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       StepPlan& sp = sh.plan[s];
       sp.n_units = nun[s]; sp.K = ks[s]; sp.chunk_bytes = 4 * ks[s] * WB; sp.n_res = 0; sp.res_off = 0;
       sp.ksplit = (nun[s] * 2 <= kWarps && ks[s] >= 512) ? 2 : 1;   // keep every warp busy
+      // segments marked in l2_keep_mask are asked to stay in L2 across frames, the others are streamed
+      // through (evict-first) so they do not push the kept ones out
+      sp.policy = ((p.l2_keep_mask >> s) & 1) ? l2_policy_evict_last() : l2_policy_evict_first();
       sp.src_off = src;
       src += (long long)nun[s] * sp.chunk_bytes;
     }
@@ -431,7 +481,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   for (int i = tid; i < 2 * H; i += kThreads) sh.xh1[i] = 0.f;
   for (int i = tid; i < 2 * E; i += kThreads) sh.xctx[i] = 0.f;
   for (int i = tid; i < H; i += kThreads) sh.xh2[i] = 0.f;
-  for (int i = tid; i < P; i += kThreads) sh.xpre[i] = 0.f;
+  for (int i = tid; i < P + 8; i += kThreads) sh.xpre[i] = 0.f;
   for (int i = tid; i < 2 * kMaxU1 * 4; i += kThreads) sh.acc1[i] = 0.f;
   for (int i = tid; i < 2 * kMaxU2 * 4; i += kThreads) sh.acc2[i] = 0.f;
   for (int i = tid; i < kMaxU1 * 4; i += kThreads) {
@@ -452,6 +502,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
 
   Watch wd{p.abort_flag, 0, 0};
   bool ok = true;
+  const int rep = lc % kRep;
   // wait for the resident prefix (async-proxy writes become visible through the mbarrier)
   wd.arm();
   while (!mbar_try_wait(sh.res_bar, 0)) {
@@ -480,49 +531,43 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     consume_step<WB>(sh, pl[1], sh.xctx + s1 * E, sh.acc1, kMaxU1, warp, lane);
     LPH(0)
     // c: W_hh(dec) . h2[t-1]
-    if (t > 0) ok = poll_vector<2>(p.ll_h2 + (size_t)rb_prev * H, H, tag_prev, sh.xh2, tid, wd) && ok;
+    if (t > 0) ok = poll_vector<2>(rep_h2(p, rep) + (size_t)rb_prev * H, H, tag_prev, sh.xh2, tid, wd) && ok;
     __syncthreads();
     LPH(1)
     consume_step<WB>(sh, pl[2], sh.xh2, sh.acc2, kMaxU2, warp, lane);
     LPH(2)
     // d: W_ih[:, :P] . prenet[t]
     if (p.free_running) {
-      // stop word first: the aux CTAs publish it with the prenet of frame t
-      if (tid == 0) {
-        float sv = 0.f;
-        const bool got = ll_wait(p.ll_pre + ((size_t)rb * 2 + 0) * (P + 8) + P, tag_cur, sv, wd);
-        if (!got || sv != 0.f) *sh.exit_flag = 1;
-      }
-      __syncthreads();
-      if (*sh.exit_flag) break;
-      ok = poll_vector<1>(p.ll_pre + ((size_t)rb * 2 + s1) * (P + 8), P, tag_cur, sh.xpre, tid, wd) && ok;
+      // prenet of frame t; word P of the block is the stop word the aux CTAs publish with it
+      ok = poll_vector<1>(rep_pre(p, rep) + ((size_t)rb * 2 + s1) * (P + 8), P + 1, tag_cur, sh.xpre, tid, wd) && ok;
+      if (!ok) *sh.exit_flag = 1;
     } else {
       for (int i = tid; i < P; i += kThreads) sh.xpre[i] = __ldg(p.st[s1].pre_tf + (size_t)t * P + i);
+      if (tid == 0) sh.xpre[P] = 0.f;
     }
     __syncthreads();
+    if (sh.xpre[P] != 0.f || *sh.exit_flag) break;
     LPH(3)
     consume_step<WB>(sh, pl[3], sh.xpre, sh.acc1, kMaxU1, warp, lane);
     __syncthreads();
     // attention-LSTM pointwise (gate order i,f,g,o), dropout on h and c when training
-    if (tid < nu1) {
-      const int u = tid, j = u1_0 + u;
-      float pre[4];
+    {
+      int u = 0; float hn = 0.f, cn = 0.f;
+      if (lstm_pointwise(sh.acc1, kMaxU1, sh.bias1, sh.c1, nu1, tid, u, hn, cn)) {
+        const int j = u1_0 + u;
+        if (p.training) {
+          const bool kh = p.lstm_keep ? p.lstm_keep[((size_t)t * 6 + 2 * s1) * H + j] != 0
+                                      : philox_keep_l(p.seed, 4 + 2 * s1, t, j, p.thresh_att);
+          const bool kc = p.lstm_keep ? p.lstm_keep[((size_t)t * 6 + 2 * s1 + 1) * H + j] != 0
+                                      : philox_keep_l(p.seed, 5 + 2 * s1, t, j, p.thresh_att);
+          hn = kh ? hn * sc_att : 0.f;
+          cn = kc ? cn * sc_att : 0.f;
+        }
+        sh.c1[u] = cn;
+        sh.hloc[u] = hn;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) pre[g] = (sh.acc1[u * 4 + g] + sh.acc1[(kMaxU1 + u) * 4 + g]) + sh.bias1[u * 4 + g];
-      const float ig = sigmoid_acc(pre[0]), fg = sigmoid_acc(pre[1]), gg = tanhf(pre[2]), og = sigmoid_acc(pre[3]);
-      float cn = fg * sh.c1[u] + ig * gg;
-      float hn = og * tanhf(cn);
-      if (p.training) {
-        const bool kh = p.lstm_keep ? p.lstm_keep[((size_t)t * 6 + 2 * s1) * H + j] != 0
-                                    : philox_keep_l(p.seed, 4 + 2 * s1, t, j, p.thresh_att);
-        const bool kc = p.lstm_keep ? p.lstm_keep[((size_t)t * 6 + 2 * s1 + 1) * H + j] != 0
-                                    : philox_keep_l(p.seed, 5 + 2 * s1, t, j, p.thresh_att);
-        hn = kh ? hn * sc_att : 0.f;
-        cn = kc ? cn * sc_att : 0.f;
+        for (int r = 0; r < kRep; ++r) ll_store(rep_h1(p, r) + ((size_t)rb * 2 + s1) * H + j, hn, tag_cur);
       }
-      sh.c1[u] = cn;
-      sh.hloc[u] = hn;
-      ll_store(p.ll_h1 + ((size_t)rb * 2 + s1) * H + j, hn, tag_cur);
     }
     __syncthreads();
     // query partials: q_part[a] = sum_u Wq[a, u] h1[u]  (attention.py:56, 368), one row of the reduction tree
@@ -535,7 +580,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     }
     LPH(4)
     // e: W_ih(dec)[:, h cols] . h1[t]   (all streams)
-    ok = poll_vector<4>(p.ll_h1 + (size_t)rb * 2 * H, S * H, tag_cur, sh.xh1, tid, wd) && ok;
+    ok = poll_vector<4>(rep_h1(p, rep) + (size_t)rb * 2 * H, S * H, tag_cur, sh.xh1, tid, wd) && ok;
     __syncthreads();
     LPH(5)
     consume_step<WB>(sh, pl[4], sh.xh1, sh.acc2, kMaxU2, warp, lane);
@@ -545,7 +590,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     consume_step<WB>(sh, pl[0], sh.xh1 + s1 * H, sh.acc1, kMaxU1, warp, lane);
     LPH(9)
     // f: W_ih(dec)[:, ctx cols] . ctx[t]
-    ok = poll_vector<2>(p.ll_ctx + (size_t)rb * 2 * E, S * E, tag_cur, sh.xctx, tid, wd) && ok;
+    ok = poll_vector<2>(rep_ctx(p, rep) + (size_t)rb * 2 * E, S * E, tag_cur, sh.xctx, tid, wd) && ok;
     __syncthreads();
     LPH(7)
     consume_step<WB>(sh, pl[6], sh.xctx, sh.acc2, kMaxU2, warp, lane);
@@ -562,24 +607,22 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
         if (wd.expired()) { ok = false; break; }
       }
     }
-    if (tid < nu2) {
-      const int u = tid, j = u2_0 + u;
-      float pre[4];
+    {
+      int u = 0; float hn = 0.f, cn = 0.f;
+      if (lstm_pointwise(sh.acc2, kMaxU2, sh.bias2, sh.c2, nu2, tid, u, hn, cn)) {
+        const int j = u2_0 + u;
+        if (p.training) {
+          const bool kh = p.lstm_keep ? p.lstm_keep[((size_t)t * 6 + 4) * H + j] != 0
+                                      : philox_keep_l(p.seed, 8, t, j, p.thresh_dec);
+          const bool kc = p.lstm_keep ? p.lstm_keep[((size_t)t * 6 + 5) * H + j] != 0
+                                      : philox_keep_l(p.seed, 9, t, j, p.thresh_dec);
+          hn = kh ? hn * sc_dec : 0.f;
+          cn = kc ? cn * sc_dec : 0.f;
+        }
+        sh.c2[u] = cn;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) pre[g] = (sh.acc2[u * 4 + g] + sh.acc2[(kMaxU2 + u) * 4 + g]) + sh.bias2[u * 4 + g];
-      const float ig = sigmoid_acc(pre[0]), fg = sigmoid_acc(pre[1]), gg = tanhf(pre[2]), og = sigmoid_acc(pre[3]);
-      float cn = fg * sh.c2[u] + ig * gg;
-      float hn = og * tanhf(cn);
-      if (p.training) {
-        const bool kh = p.lstm_keep ? p.lstm_keep[((size_t)t * 6 + 4) * H + j] != 0
-                                    : philox_keep_l(p.seed, 8, t, j, p.thresh_dec);
-        const bool kc = p.lstm_keep ? p.lstm_keep[((size_t)t * 6 + 5) * H + j] != 0
-                                    : philox_keep_l(p.seed, 9, t, j, p.thresh_dec);
-        hn = kh ? hn * sc_dec : 0.f;
-        cn = kc ? cn * sc_dec : 0.f;
+        for (int r = 0; r < kRep; ++r) ll_store(rep_h2(p, r) + (size_t)rb * H + j, hn, tag_cur);
       }
-      sh.c2[u] = cn;
-      ll_store(p.ll_h2 + (size_t)rb * H + j, hn, tag_cur);
     }
     if (!ok) *sh.exit_flag = 1;
     __syncthreads();
@@ -631,7 +674,7 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
     if (p.free_running) {
       if (tid == 0) {
         float sv = 0.f;
-        const bool got = ll_wait(p.ll_pre + ((size_t)rb * 2 + 0) * (P + 8) + P, tag, sv, wd);
+        const bool got = ll_wait(rep_pre(p, (g + 3 * s) % kRep) + ((size_t)rb * 2 + s) * (P + 8) + P, tag, sv, wd);
         if (!got || sv != 0.f) s_stop = 1;
       }
       __syncthreads();
@@ -723,7 +766,8 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
     if (tid < FS) {
       float c = 0.f;
       for (int k = 0; k < NJ; ++k) c += red_s[k * FS + tid];
-      ll_store(p.ll_ctx + ((size_t)rb * 2 + s) * E + g * FS + tid, c, tag);
+#pragma unroll
+      for (int r = 0; r < kRep; ++r) ll_store(rep_ctx(p, r) + ((size_t)rb * 2 + s) * E + g * FS + tid, c, tag);
     }
     __syncthreads();
   }
@@ -738,49 +782,52 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
   const int S = p.S;
   const int KD = H + S * E;
   constexpr int RPX = (M + 1 + kAux - 1) / kAux;      // projection rows per aux CTA (11)
-  constexpr int PR = P / kAux;                        // prenet rows per aux CTA per stream (32)
+  constexpr int PR = P / kAux;                        // prenet layer-1 rows per aux CTA per stream (32)
+  constexpr int LW = 2 * P + 8;                       // words per aux block of the layer-0 partial exchange
   const int r0 = x * RPX, r1 = min(M + 1, r0 + RPX), nr = r1 - r0;
+  const int nmel = min(M, r1) - r0;                   // mel rows among them (the last CTA also owns the gate row)
   float* sm = reinterpret_cast<float*>(smem_raw);
-  float* wp_s = sm;                                   // [RPX][KD]
-  float* w0_s = wp_s + (size_t)RPX * (H + 2 * E);     // [S][PR][M]
-  float* w1_s = w0_s + 2 * PR * M;                    // [S][PR][P]
+  float* wp_s = sm;                                   // [RPX][KD]           projection / gate rows
+  float* w0c_s = wp_s + (size_t)RPX * (H + 2 * E);    // [S*P][RPX]          prenet layer-0 COLUMNS of the own mel rows
+  float* w1_s = w0c_s + 2 * P * RPX;                  // [S][PR][P]          prenet layer-1 rows
   float* y_s = w1_s + 2 * PR * P;                     // [KD]
-  float* mel_s = y_s + (H + 2 * E);                   // [M + 16]
-  float* l0_s = mel_s + M + 16;                       // [S][P]
-  __shared__ int s_stop;
+  float* own_s = y_s + (H + 2 * E);                   // [16] own mel values
+  float* l0_s = own_s + 16;                           // [S][P]
+  __shared__ int s_stop, s_stopval;
 
   for (int i = tid; i < nr * KD; i += kThreads) {
     const int r = i / KD, k = i - r * KD;
     const int row = r0 + r;
     wp_s[(size_t)r * KD + k] = row < M ? p.proj_w[(size_t)row * KD + k] : p.gate_w[k];
   }
-  for (int i = tid; i < S * PR * M; i += kThreads) {
-    const int s = i / (PR * M), r = (i - s * PR * M) / M, k = i - s * PR * M - r * M;
-    w0_s[i] = p.st[s].pre_w0[(size_t)(x * PR + r) * M + k];
+  for (int i = tid; i < S * P * RPX; i += kThreads) {
+    const int si = i / RPX, r = i - si * RPX, s = si / P, o = si - s * P;
+    w0c_s[i] = r < nmel ? p.st[s].pre_w0[(size_t)o * M + r0 + r] : 0.f;
   }
   for (int i = tid; i < S * PR * P; i += kThreads) {
     const int s = i / (PR * P), r = (i - s * PR * P) / P, k = i - s * PR * P - r * P;
     w1_s[i] = p.st[s].pre_w1[(size_t)(x * PR + r) * P + k];
   }
-  if (tid == 0) s_stop = 0;
+  if (tid == 0) { s_stop = 0; s_stopval = 0; }
+  if (tid < 16) own_s[tid] = 0.f;
   __syncthreads();
 
   Watch wd{p.abort_flag, 0, 0};
   // prenet of frame 0 = prenet(go-frame of zeros) = zeros (model.py:444-450); stop word = 0
   if (p.free_running) {
-    for (int i = tid; i < S * PR; i += kThreads) {
-      const int s = i / PR, r = i - s * PR;
-      ll_store(p.ll_pre + ((size_t)0 * 2 + s) * (P + 8) + x * PR + r, 0.f, 1u);
+    for (int i = tid; i < S * PR * kRep; i += kThreads) {
+      const int rr = i / (S * PR), k = i - rr * S * PR, s = k / PR, r = k - s * PR;
+      ll_store(rep_pre(p, rr) + ((size_t)0 * 2 + s) * (P + 8) + x * PR + r, 0.f, 1u);
     }
-    if (x == 0 && tid == 0) ll_store(p.ll_pre + (size_t)P, 0.f, 1u);
+    if (x == 0 && tid < S * kRep) ll_store(rep_pre(p, tid / S) + ((size_t)0 * 2 + tid % S) * (P + 8) + P, 0.f, 1u);
   }
 
   for (int t = 0; t < p.n_steps; ++t) {
     const unsigned tag = (unsigned)t + 1u;
     const int rb = t % kLLDepth, rbn = (t + 1) % kLLDepth;
-    // ---- y = [h2_t | ctx_t | ctx_bert_t] ---------------------------------------------------
-    bool ok = poll_vector<2>(p.ll_h2 + (size_t)rb * H, H, tag, y_s, tid, wd);
-    ok = poll_vector<2>(p.ll_ctx + (size_t)rb * 2 * E, S * E, tag, y_s + H, tid, wd) && ok;
+    // ---- y = [h2_t | ctx_t | ctx_bert_t]; the context is published long before h2, poll it first ----
+    bool ok = poll_vector<2>(rep_ctx(p, x % kRep) + (size_t)rb * 2 * E, S * E, tag, y_s + H, tid, wd);
+    ok = poll_vector<2>(rep_h2(p, x % kRep) + (size_t)rb * H, H, tag, y_s, tid, wd) && ok;
     if (!ok) s_stop = 1;
     __syncthreads();
     if (s_stop) break;
@@ -799,7 +846,7 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
         if (row < M) {
           const float v = acc + p.proj_b[row];
           p.mel[(size_t)t * M + row] = v;
-          if (p.free_running) ll_store(p.ll_mel + (size_t)rb * (M + 16) + row, v, tag);
+          own_s[warp] = v;
         } else {
           const float gv = acc + p.gate_b[0];
           p.gate[t] = gv;
@@ -807,43 +854,79 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
             int stop = 0;
             if (sigmoid_acc(gv) > p.gate_thr) { stop = 1; p.n_frames[0] = t + 1; }            // model.py:480-481
             else if (t + 1 == p.n_steps) { stop = 1; p.n_frames[0] = t + 1; p.reached_max[0] = 1; }  // :482-485
-            ll_store(p.ll_mel + (size_t)rb * (M + 16) + M, stop ? 1.f : 0.f, tag);
+            s_stopval = stop;
           }
         }
       }
     }
+    __syncthreads();
     if (!p.free_running) {
       // nobody waits for the projection when teacher forcing: report progress for LL flow control
-      __syncthreads();
       if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.aux_done), "r"(1u) : "memory");
       continue;
     }
-    // ---- mel_t (+ stop word) from all aux CTAs ----------------------------------------------
-    ok = poll_vector<1>(p.ll_mel + (size_t)rb * (M + 16), M + 1, tag, mel_s, tid, wd);
-    if (!ok) s_stop = 1;
-    __syncthreads();
-    if (s_stop) break;
-    const bool stop = mel_s[M] != 0.f;
-    if (x == 0 && tid == 0) ll_store(p.ll_pre + ((size_t)rbn * 2 + 0) * (P + 8) + P, stop ? 1.f : 0.f, tag + 1u);
-    if (stop) break;
-    // ---- prenet layer 0 rows of this CTA: relu(W0 mel) * keep * 2 ----------------------------
-    for (int it = warp; it < S * PR; it += kWarps) {
-      const int s = it / PR, r = it - s * PR, row = x * PR + r;
-      const float* w = w0_s + ((size_t)s * PR + r) * M;
-      float acc = 0.f;
-      for (int k = lane; k < M; k += 32) acc = fmaf(w[k], mel_s[k], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        const uint8_t* keep = p.st[s].keep0;
-        const bool kp = keep ? keep[(size_t)(t + 1) * P + row] != 0 : philox_keep_l(p.seed, s * 2 + 0, t + 1, row, p.thresh_pre);
-        ll_store(p.ll_l0 + ((size_t)rbn * 2 + s) * P + row, kp ? fmaxf(acc, 0.f) * 2.0f : 0.f, tag + 1u);
+    // ---- prenet layer 0, PARTIAL over the own mel rows: W0[:, rows] . mel[rows]  (saves the mel exchange) ----
+    {
+      unsigned long long* blk = p.ll_l0 + ((size_t)rbn * kAux + x) * LW;
+      if (tid < S * P) {
+        const float* w = w0c_s + (size_t)tid * RPX;
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < RPX; ++r) acc = fmaf(w[r], own_s[r], acc);
+        ll_store(blk + tid, acc, tag + 1u);
       }
+      if (tid == 0) ll_store(blk + 2 * P, s_stopval ? 1.f : 0.f, tag + 1u);   // meaningful in the gate owner's block
     }
-    // ---- prenet layer 1 -------------------------------------------------------------------
-    ok = poll_vector<1>(p.ll_l0 + (size_t)rbn * 2 * P, S * P, tag + 1u, l0_s, tid, wd);
-    if (!ok) s_stop = 1;
+    // ---- gather the kAux partials (fixed order), relu + dropout(0.5) -> layer-0 activations -------------
+    {
+      const unsigned long long* base = p.ll_l0 + (size_t)rbn * kAux * LW;
+      bool good = true;
+      float sum = 0.f;
+      if (tid < S * P) {
+        unsigned pending = (1u << kAux) - 1u;
+        float val[kAux];
+        wd.arm();
+        while (pending) {
+          unsigned long long w[kAux];
+#pragma unroll
+          for (int k = 0; k < kAux; ++k)
+            if (pending & (1u << k)) w[k] = ll_load(base + (size_t)k * LW + tid);
+#pragma unroll
+          for (int k = 0; k < kAux; ++k)
+            if ((pending & (1u << k)) && (unsigned)(w[k] >> 32) == tag + 1u) {
+              val[k] = __uint_as_float((unsigned)w[k]);
+              pending &= ~(1u << k);
+            }
+          if (pending && wd.expired()) { good = false; break; }
+        }
+#pragma unroll
+        for (int k = 0; k < kAux; ++k) sum += val[k];
+        const int s = tid / P, o = tid - s * P;
+        const uint8_t* keep = p.st[s].keep0;
+        const bool kp = keep ? keep[(size_t)(t + 1) * P + o] != 0 : philox_keep_l(p.seed, s * 2 + 0, t + 1, o, p.thresh_pre);
+        l0_s[tid] = kp ? fmaxf(sum, 0.f) * 2.0f : 0.f;
+      }
+      if (tid == 0) {
+        float sv = 0.f;
+        good = ll_wait(base + (size_t)(kAux - 1) * LW + 2 * P, tag + 1u, sv, wd) && good;
+        s_stopval = sv != 0.f;
+      }
+      if (!good) s_stop = 1;
+    }
     __syncthreads();
     if (s_stop) break;
+    const bool stop = s_stopval != 0;
+    if (x == 0 && tid < S * kRep)   // the stop word rides in every replica / stream block of the next frame's prenet
+      ll_store(rep_pre(p, tid / S) + ((size_t)rbn * 2 + tid % S) * (P + 8) + P, stop ? 1.f : 0.f, tag + 1u);
+    if (stop) {
+      // release everybody polling the next frame's prenet block (they read the stop word with it)
+      for (int i = tid; i < S * PR * kRep; i += kThreads) {
+        const int rr = i / (S * PR), k = i - rr * S * PR, s = k / PR, r = k - s * PR;
+        ll_store(rep_pre(p, rr) + ((size_t)rbn * 2 + s) * (P + 8) + x * PR + r, 0.f, tag + 1u);
+      }
+      break;
+    }
+    // ---- prenet layer 1 rows of this CTA ------------------------------------------------------------------
     for (int it = warp; it < S * PR; it += kWarps) {
       const int s = it / PR, r = it - s * PR, row = x * PR + r;
       const float* w = w1_s + ((size_t)s * PR + r) * P;
@@ -858,7 +941,9 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
       if (lane == 0) {
         const uint8_t* keep = p.st[s].keep1;
         const bool kp = keep ? keep[(size_t)(t + 1) * P + row] != 0 : philox_keep_l(p.seed, s * 2 + 1, t + 1, row, p.thresh_pre);
-        ll_store(p.ll_pre + ((size_t)rbn * 2 + s) * (P + 8) + row, kp ? fmaxf(acc, 0.f) * 2.0f : 0.f, tag + 1u);
+        const float pv = kp ? fmaxf(acc, 0.f) * 2.0f : 0.f;
+#pragma unroll
+        for (int rr = 0; rr < kRep; ++rr) ll_store(rep_pre(p, rr) + ((size_t)rbn * 2 + s) * (P + 8) + row, pv, tag + 1u);
       }
     }
     __syncthreads();

@@ -1040,9 +1040,9 @@ bool lat_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
 }
 
 size_t lat_ll_words(const taco2dec_handle* h) {
-  const size_t d = lat::kLLDepth;
-  return d * 2 * lat::H + d * lat::H + d * 2 * lat::E + d * 2 * (size_t)h->num_sms * lat::A + d * 2 * (lat::P + 8) +
-         d * (lat::M + 16) + d * 2 * lat::P + 64;
+  const size_t d = lat::kLLDepth, r = lat::kRep;
+  return r * (d * 2 * lat::H + d * lat::H + d * 2 * lat::E + d * 2 * (lat::P + 8)) + d * 2 * (size_t)h->num_sms * lat::A +
+         d * (lat::M + 16) + d * lat::kAux * (2 * lat::P + 8) + 64;
 }
 
 int lat_pack_weights(taco2dec_handle* h, const LatGeometry& g, cudaStream_t st) {
@@ -1098,6 +1098,12 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   p.thresh_pre = gp.thresh_pre; p.thresh_att = gp.thresh_att; p.thresh_dec = gp.thresh_dec; p.seed = gp.seed;
   p.wbytes = g.wbytes; p.packed = h->packed; p.packed_off = h->packed_off;
   p.res_budget = g.res_budget;
+  // L2 policy per segment (a b c d e0 e1 f).  fp16: the whole streamed set (37 MB) fits in L2 -> keep all.
+  // fp32: 98 MB are streamed per frame; keep a, e0, e1 (65 MB; they sit on the critical path) and let b, c
+  // (33 MB; they run while the aux CTAs compute the next prenet) stream through from HBM.  Measured:
+  // 29.3 us/frame with no hint, 26.4 keep-all, 25.4 keep a/b/c, 22.2 keep a/e0/e1.
+  p.l2_keep_mask = g.wbytes == 2 ? 0x7f : 0x31;
+  { const char* e = getenv("TACO2DEC_L2_KEEP_MASK"); if (e) p.l2_keep_mask = (int)strtol(e, nullptr, 0); }
   for (int s = 0; s < c.n_streams; ++s) {
     const StreamParams& sp = gp.st[s];
     lat::LatStream& ls = p.st[s];
@@ -1110,13 +1116,14 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   p.reached_max = gp.reached_max;
   unsigned long long* w = h->ll_buf;
   const size_t d = lat::kLLDepth;
-  p.ll_h1 = w; w += d * 2 * lat::H;
-  p.ll_h2 = w; w += d * lat::H;
-  p.ll_ctx = w; w += d * 2 * lat::E;
+  const size_t r = lat::kRep;
+  p.ll_h1 = w; w += r * d * 2 * lat::H;
+  p.ll_h2 = w; w += r * d * lat::H;
+  p.ll_ctx = w; w += r * d * 2 * lat::E;
   p.ll_q = w; w += d * 2 * (size_t)h->num_sms * lat::A;
-  p.ll_pre = w; w += d * 2 * (lat::P + 8);
+  p.ll_pre = w; w += r * d * 2 * (lat::P + 8);
   p.ll_mel = w; w += d * (lat::M + 16);
-  p.ll_l0 = w; w += d * 2 * lat::P;
+  p.ll_l0 = w; w += d * lat::kAux * (2 * lat::P + 8);
   p.aux_done = (unsigned*)w;
   p.abort_flag = gp.abort_flag;
   p.phase_clocks = gp.phase_clocks;
