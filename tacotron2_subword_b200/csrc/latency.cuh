@@ -339,9 +339,12 @@ __device__ __forceinline__ void dot4(const unsigned char* base, int row_bytes, c
   for (int g = 0; g < 4; ++g) s[g] = a[g][0] + a[g][1];
 }
 
+// NOT inlined on purpose: the seven call sites per frame share three instantiations, which keeps the per-frame
+// instruction footprint inside the instruction cache (inlined, the kernel was 280 KB of SASS and every step
+// paid instruction-fetch misses).
 template <int WB, int KLEN>
-__device__ __forceinline__ void consume_items(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
-                                              int max_units, int warp, int lane) {
+__device__ __noinline__ void consume_items(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
+                                           int max_units, int warp, int lane) {
   constexpr int EPU = Mac<WB>::kElems;
   constexpr int NU = KLEN / (32 * EPU);
 #ifndef TACO2DEC_STREAM_PU
@@ -549,7 +552,9 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     if (sh.xpre[P] != 0.f || *sh.exit_flag) break;
     LPH(3)
     consume_step<WB>(sh, pl[3], sh.xpre, sh.acc1, kMaxU1, warp, lane);
+    LPH(13)
     __syncthreads();
+    LPH(14)
     // attention-LSTM pointwise (gate order i,f,g,o), dropout on h and c when training
     {
       int u = 0; float hn = 0.f, cn = 0.f;
@@ -594,7 +599,9 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     __syncthreads();
     LPH(7)
     consume_step<WB>(sh, pl[6], sh.xctx, sh.acc2, kMaxU2, warp, lane);
+    LPH(10)
     __syncthreads();
+    LPH(11)
     // flow control (teacher-forced only): the aux CTAs are not in the dependency loop, so do not
     // overwrite LL slot t % depth before they have consumed frame t - depth
     if (!p.free_running && t >= kLLDepth && tid == 0) {
@@ -624,6 +631,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
         for (int r = 0; r < kRep; ++r) ll_store(rep_h2(p, r) + (size_t)rb * H + j, hn, tag_cur);
       }
     }
+    LPH(12)
     if (!ok) *sh.exit_flag = 1;
     __syncthreads();
     if (tid < 2 * kMaxU2 * 4) sh.acc2[tid] = 0.f;

@@ -29,7 +29,8 @@ if eng.last_path() == "generic":
     for k, n in enumerate(names):
         print(f"  {n:4s} work {pc[2*k]/1e6:8.2f} kcyc/frame ({100*pc[2*k]/tot:5.1f}%)   barrier {pc[2*k+1]/1e6:8.2f} kcyc/frame ({100*pc[2*k+1]/tot:5.1f}%)")
 else:
-    names = ["b compute", "wait h2[t-1]", "c compute", "wait prenet[t] (aux chain)", "d compute + pointwise + q",
-             "wait h1[t]", "e compute", "wait ctx[t] (attention)", "f compute + pointwise", "a(t+1) compute"]
+    names = ["b compute", "wait h2[t-1]", "c compute", "wait prenet[t] (aux chain)", "d: pointwise + sync + q partials",
+             "wait h1[t]", "e compute", "wait ctx[t] (attention)", "f: last sync + zero", "a(t+1) compute", "f: consume (warp 0)", "f: barrier after consume",
+             "f: pointwise + publish", "d: consume (warp 0)", "d: barrier after consume"]
     for k, n in enumerate(names):
         print(f"  {n:32s} {pc[k]/1e6:8.2f} kcyc/frame ({100*pc[k]/tot:5.1f}%)")
