@@ -181,6 +181,11 @@ int64_t taco2dec_launch_count(const taco2dec_handle* h);
 int taco2dec_philox_keep_mask(uint64_t seed, int mask_id, int rows, int n, float p_drop, uint8_t* out,
                               void* cuda_stream);
 
+/* Test hook for the tcgen05 GEMM building block of the batched path: out[M][N] = A[M][K] . X[N][K]^T with
+ * fp16-rounded operands and fp32 accumulation (device pointers, fp32 row-major).  M % 128 == 0,
+ * K % (64*splits) == 0, 1 <= N <= 128.  Synchronises the stream. */
+int taco2dec_test_gemm(int M, int N, int K, int splits, const float* A, const float* X, float* out, void* cuda_stream);
+
 /* Select the kernel family and the storage type of the packed LSTM weights (latency path). */
 int taco2dec_set_mode(taco2dec_handle* h, int path, int weight_dtype);
 /* TACO2DEC_PATH_GENERIC or TACO2DEC_PATH_LATENCY: the path the most recent call actually took. */

@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "taco2dec_infer", "taco2dec_check", "taco2dec_launch_count", "taco2dec_philox_keep_mask",
     "taco2dec_launch_geometry", "taco2dec_set_profiling", "taco2dec_last_kernel_ms",
     "taco2dec_read_phase_clocks", "taco2dec_set_mode", "taco2dec_last_path",
+    "taco2dec_test_gemm",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -116,6 +117,8 @@ def load_library() -> C.CDLL:
     lib.taco2dec_set_mode.argtypes = [H, C.c_int, C.c_int]
     lib.taco2dec_last_path.restype = C.c_int
     lib.taco2dec_last_path.argtypes = [H]
+    lib.taco2dec_test_gemm.restype = C.c_int
+    lib.taco2dec_test_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.taco2dec_read_phase_clocks.restype = C.c_int
     lib.taco2dec_read_phase_clocks.argtypes = [H, C.c_void_p, C.POINTER(C.c_longlong)]
     if lib.taco2dec_abi_version() != ABI_VERSION:

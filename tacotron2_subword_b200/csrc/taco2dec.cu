@@ -147,6 +147,7 @@ __device__ __forceinline__ float keep_mult(const uint8_t* replay, size_t replay_
 }  // namespace
 namespace {
 #include "latency.cuh"
+#include "gemm_tc.cuh"
 }  // namespace
 namespace {
 
@@ -1175,6 +1176,35 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
 
 }  // namespace
 
+namespace {
+__global__ void sum_splits_kernel(const float* part, int splits, int M, int NPAD, int N, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int m = i / N, n = i - m * N;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += part[((size_t)k * M + m) * NPAD + n];
+  out[i] = s;
+}
+template <int NPAD>
+int run_test_gemm(int M, int N, int K, int splits, const float* A, const float* X, float* out, cudaStream_t st) {
+  unsigned char *a_t = nullptr, *x_t = nullptr;
+  float* part = nullptr;
+  CUDA_TRY(cudaMalloc(&a_t, (size_t)M * K * 2));
+  CUDA_TRY(cudaMalloc(&x_t, (size_t)NPAD * K * 2));
+  CUDA_TRY(cudaMalloc(&part, (size_t)splits * M * NPAD * sizeof(float)));
+  tc::pack_tiles_kernel<<<1024, 256, 0, st>>>(A, M, K, tc::kBlockM, M / tc::kBlockM, a_t);
+  tc::pack_tiles_kernel<<<256, 256, 0, st>>>(X, N, K, NPAD, 1, x_t);
+  tc::GemmParams gp{a_t, x_t, part, M, K, splits, 1};
+  CUDA_TRY(tc::launch_gemm<NPAD>(gp, st));
+  sum_splits_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(part, splits, M, NPAD, N, out);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(a_t); cudaFree(x_t); cudaFree(part);
+  return 0;
+}
+}  // namespace
+
+
 extern "C" {
 
 int taco2dec_abi_version(void) { return TACO2DEC_ABI_VERSION; }
@@ -1232,6 +1262,18 @@ int taco2dec_read_phase_clocks(taco2dec_handle* h, void* cuda_stream, long long*
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
   CUDA_TRY(cudaMemcpy(out16_host, h->last_phase_clocks, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
+}
+
+/* Test hook for the tcgen05 GEMM building block: out[M][N] = A[M][K] . X[N][K]^T with fp16-rounded operands,
+ * fp32 accumulation.  M % 128 == 0, K % (64*splits) == 0, 1 <= N <= 128.  Synchronises the stream. */
+int taco2dec_test_gemm(int M, int N, int K, int splits, const float* A, const float* X, float* out, void* cuda_stream) {
+  if (!A || !X || !out || M < 128 || M % 128 || N < 1 || N > 128 || splits < 1 || K % (64 * splits))
+    return fail(TACO2DEC_E_ARG, "bad GEMM shape");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (N <= 16) return run_test_gemm<16>(M, N, K, splits, A, X, out, st);
+  if (N <= 32) return run_test_gemm<32>(M, N, K, splits, A, X, out, st);
+  if (N <= 64) return run_test_gemm<64>(M, N, K, splits, A, X, out, st);
+  return run_test_gemm<128>(M, N, K, splits, A, X, out, st);
 }
 
 int taco2dec_set_mode(taco2dec_handle* h, int path, int weight_dtype) {
