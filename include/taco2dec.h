@@ -48,7 +48,8 @@ extern "C" {
  * default decoder dims), else the generic any-shape path. */
 #define TACO2DEC_PATH_AUTO 0
 #define TACO2DEC_PATH_GENERIC 1 /* grid-barrier persistent kernel, fp32 weights in PyTorch layout, any B / SMA+LSA */
-#define TACO2DEC_PATH_LATENCY 2 /* role-specialised persistent kernel, TMA-streamed packed weights (batch 1) */
+#define TACO2DEC_PATH_LATENCY 2 /* role-specialised persistent kernel, packed weights resident/streamed (batch 1) */
+#define TACO2DEC_PATH_TENSOR 3  /* batched (16 <= B <= 128): LSTM / query products on tcgen05, fp16 operands, fp32 accumulate */
 #define TACO2DEC_W_FP32 0       /* packed LSTM weights stay fp32 (parity ~1e-6)                           */
 #define TACO2DEC_W_FP16 1       /* the three LSTM matrices stored fp16, fp32 accumulate (parity ~5e-5)   */
 
@@ -188,7 +189,7 @@ int taco2dec_test_gemm(int M, int N, int K, int splits, const float* A, const fl
 
 /* Select the kernel family and the storage type of the packed LSTM weights (latency path). */
 int taco2dec_set_mode(taco2dec_handle* h, int path, int weight_dtype);
-/* TACO2DEC_PATH_GENERIC or TACO2DEC_PATH_LATENCY: the path the most recent call actually took. */
+/* TACO2DEC_PATH_GENERIC / _LATENCY / _TENSOR: the path the most recent call actually took. */
 int taco2dec_last_path(const taco2dec_handle* h);
 
 /* Optional: record CUDA events on the launching stream around the persistent decoder kernel

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtaco2dec.so")  # env override: A/B builds
 
 ATTN_SMA, ATTN_LSA = 0, 1
-PATH_AUTO, PATH_GENERIC, PATH_LATENCY = 0, 1, 2
+PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR = 0, 1, 2, 3
 W_FP32, W_FP16 = 0, 1
 ABI_VERSION = 1
 

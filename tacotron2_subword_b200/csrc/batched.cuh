@@ -1,0 +1,225 @@
+// batched.cuh -- tensor-core path for batched decoding (B >= 16), included by taco2dec.cu.
+//
+// Once batch x hidden makes the LSTM gate products genuine dense contractions they run on tcgen05
+// (gemm_tc.cuh): gates[4096, B] = [W_ih | W_hh][4096, K] x [x | h][B, K]^T with fp16 operands and fp32
+// accumulation in TMEM, 128 CTAs per GEMM (32 row tiles x split-K).  A frame is a short sequence of
+// kernels on one stream (no host synchronisation inside the loop):
+//
+//   x1 <- prenet[t]            bt_prenet_tf_to_x1 / bt_prenet_fr          (model.py:412-413 / 470-471)
+//   G1  = A1 . X1^T            tcgen05 GEMM, 2 streams x split-K 2        (model.py:337-344)
+//   pointwise LSTM 1           -> c1, h1 (fp32) + fp16 tiles of X1', X2   (model.py:340-346)
+//   Q   = Wq . h1^T            tcgen05 GEMM (128 rows), split-K 4         (attention.py:56, 368)
+//   attention                  generic attention_task (fast energies) per (batch, stream) CTA
+//   G2  = A2 . X2^T            tcgen05 GEMM, split-K 4                    (model.py:362-371)
+//   pointwise LSTM 2           -> c2, h2                                  (model.py:371-373)
+//   projection + stop test     mel, gate                                  (model.py:382-388, 480-485)
+//
+// Every producer writes its fp16 output straight into the pre-tiled operand buffers of the GEMMs that
+// consume it (core-matrix layout of gemm_tc.cuh), so no separate packing pass exists.
+#pragma once
+
+namespace bt {
+
+constexpr int H = 1024, E = 512, P = 256, A = 128, M = 80;
+constexpr int K1 = P + E + H;            // 1792: [prenet | ctx | h1]
+constexpr int SPLITS1 = 2, SPLITS2 = 4, SPLITSQ = 4;
+
+struct Bufs {
+  // tiled fp16 operands
+  unsigned char* a1;    // [S][32 m-tiles][28 kb] attention LSTM weights [W_ih | W_hh]
+  unsigned char* a2;    // [32][K2/64]            decoder LSTM weights   [W_ih | W_hh]
+  unsigned char* aq;    // [S][1][16]             query weights
+  unsigned char* x1;    // [S][28 kb][NPAD x 64]
+  unsigned char* x2;    // [K2/64][NPAD x 64]     [h1_0 | ctx_0 | h1_1 | ctx_1 | h2]
+  // GEMM partial outputs (fp32)
+  float* g1;            // [S][SPLITS1][4096][NPAD]
+  float* g2;            // [SPLITS2][4096][NPAD]
+  float* gq;            // [S][SPLITSQ][128][NPAD]
+  // fp32 state
+  float *c1, *c2, *h2f; // [S][B][H], [B][H], [B][H]
+  int NPAD, K2;
+};
+
+__device__ __forceinline__ void x_store(unsigned char* xbase, int NPAD, int b, int k, float v) {
+  const size_t off = (size_t)(k >> 6) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63);
+  *reinterpret_cast<__half*>(xbase + off) = __float2half(v);
+}
+
+// weights: rows x (K0 + K1c) from two row-major fp32 sources -> [row tiles of 128][kb] fp16 tiles
+__global__ void pack_concat_tiles_kernel(const float* __restrict__ src0, int K0, const float* __restrict__ src1, int K1c,
+                                         int rows, unsigned char* __restrict__ dst) {
+  const int K = K0 + K1c, kb_total = K / tc::kBlockK;
+  const int rows_pad = (rows + 127) / 128 * 128;
+  const size_t total = (size_t)rows_pad * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K), r = (int)(i / K);
+    float v = 0.f;
+    if (r < rows) v = k < K0 ? src0[(size_t)r * K0 + k] : src1[(size_t)r * K1c + (k - K0)];
+    const size_t tile = ((size_t)(r / 128) * kb_total + (k / tc::kBlockK)) * tc::kATileBytes;
+    *reinterpret_cast<__half*>(dst + tile + tc::tile_offset_bytes(128, r % 128, k % tc::kBlockK)) = __float2half(v);
+  }
+}
+
+__global__ void bt_init_kernel(Params p, Bufs bf) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
+  for (int i = gtid; i < p.S * p.B * H; i += n) bf.c1[i] = 0.f;
+  for (int i = gtid; i < p.B * H; i += n) { bf.c2[i] = 0.f; bf.h2f[i] = 0.f; }
+  for (int i = gtid; i < p.S * p.B * E; i += n) p.ctx[i] = 0.f;
+  for (int s = 0; s < p.S; ++s) {
+    const int Ts = p.st[s].Ts;
+    for (int i = gtid; i < p.B * Ts; i += n) {
+      p.st[s].a_prev[i] = (p.attention == TACO2DEC_ATTN_SMA && (i % Ts) == 0) ? 1.0f : 0.0f;
+      p.st[s].a_cum[i] = 0.f;
+    }
+  }
+  if (p.free_running) {
+    for (int i = gtid; i < p.B; i += n) { p.n_frames[i] = 0; p.reached_max[i] = 0; }
+    if (gtid == 0) *p.done_count = 0;
+  }
+}
+
+// teacher-forced: hoisted prenet output of frame t -> X1 columns [0, P)
+__global__ void bt_prenet_tf_to_x1(Params p, Bufs bf, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.S * p.B * P) return;
+  const int s = i / (p.B * P), r = i - s * p.B * P, b = r / P, k = r - b * P;
+  const float v = p.st[s].pre[((size_t)t * p.B + b) * P + k];
+  x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, k, v);
+}
+
+// free-running: prenet(mel[t-1]) for both streams; one CTA per (stream, batch); writes X1 columns [0, P)
+__global__ void __launch_bounds__(256) bt_prenet_fr(Params p, Bufs bf, int t) {
+  __shared__ float x_s[M], h_s[P];
+  if (__ldcg(p.done_count) >= p.B) return;
+  const int s = blockIdx.x / p.B, b = blockIdx.x - s * p.B, tid = threadIdx.x;
+  const StreamParams& sp = p.st[s];
+  for (int m = tid; m < M; m += 256) x_s[m] = t > 0 ? p.mel[((size_t)b * p.Tcap + (t - 1)) * M + m] : 0.f;
+  __syncthreads();
+  {
+    float acc = 0.f;
+    const float* w = sp.pre_w0 + (size_t)tid * M;
+    for (int k = 0; k < M; ++k) acc = fmaf(w[k], x_s[k], acc);
+    const float mult = keep_mult(sp.keep0, ((size_t)t * p.B + b) * P + tid, p.seed, s * 2 + 0, t, b * P + tid, p.thresh_pre, 2.0f);
+    h_s[tid] = fmaxf(acc, 0.f) * mult;
+  }
+  __syncthreads();
+  {
+    float acc = 0.f;
+    const float* w = sp.pre_w1 + (size_t)tid * P;
+    for (int k = 0; k < P; ++k) acc = fmaf(w[k], h_s[k], acc);
+    const float mult = keep_mult(sp.keep1, ((size_t)t * p.B + b) * P + tid, p.seed, s * 2 + 1, t, b * P + tid, p.thresh_pre, 2.0f);
+    x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, tid, fmaxf(acc, 0.f) * mult);
+  }
+}
+
+// attention-LSTM pointwise: sums the split-K partials, gate order i,f,g,o (nn.LSTMCell), dropout on h and c
+__global__ void bt_pointwise1(Params p, Bufs bf, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.S * p.B * H) return;
+  if (p.free_running && __ldcg(p.done_count) >= p.B) return;
+  const int s = i / (p.B * H), r = i - s * p.B * H, j = r / p.B, b = r - j * p.B;   // b fastest: coalesced partial reads
+  const StreamParams& sp = p.st[s];
+  float pre[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float a = sp.b_ih[g * H + j] + sp.b_hh[g * H + j];
+#pragma unroll
+    for (int k = 0; k < SPLITS1; ++k) a += bf.g1[(((size_t)s * SPLITS1 + k) * 4 * H + g * H + j) * bf.NPAD + b];
+    pre[g] = a;
+  }
+  const size_t idx = (size_t)b * H + j;
+  float cn = sigmoidf_(pre[1]) * bf.c1[(size_t)s * p.B * H + idx] + sigmoidf_(pre[0]) * tanhf(pre[2]);
+  float hn = sigmoidf_(pre[3]) * tanhf(cn);
+  if (p.training) {
+    const float sc = 1.0f / (1.0f - p.p_att);
+    const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s) * p.B * H : nullptr;
+    const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s + 1) * p.B * H : nullptr;
+    hn *= keep_mult(kh, idx, p.seed, 4 + 2 * s, t, (int)idx, p.thresh_att, sc);
+    cn *= keep_mult(kc, idx, p.seed, 5 + 2 * s, t, (int)idx, p.thresh_att, sc);
+  }
+  bf.c1[(size_t)s * p.B * H + idx] = cn;
+  x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, P + E + j, hn);     // next frame's LSTM-1 input
+  x_store(bf.x2, bf.NPAD, b, s * (H + E) + j, hn);                                        // this frame's LSTM-2 / query input
+}
+
+// attention: q = sum of the query-GEMM partials, then the generic attention task; context -> fp32 + tiles
+template <bool kDummy>
+__global__ void __launch_bounds__(kThreads, 1) bt_attention(Params p, Bufs bf, int t) {
+  extern __shared__ __align__(16) float att_smem[];
+  if (p.free_running && __ldcg(p.done_count) >= p.B) return;
+  const int s = blockIdx.x % p.S, b = blockIdx.x / p.S, tid = threadIdx.x;
+  if (tid < A) {
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPLITSQ; ++k) q += bf.gq[(((size_t)s * SPLITSQ + k) * 128 + tid) * bf.NPAD + b];
+    p.q[((size_t)s * p.B + b) * A + tid] = q;
+  }
+  __syncthreads();
+  attention_task<true>(p, s, b, t, att_smem);
+  for (int d = tid; d < E; d += kThreads) {
+    const float c = __ldcg(p.ctx + ((size_t)s * p.B + b) * E + d);
+    x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, P + d, c);          // next frame's LSTM-1 input
+    x_store(bf.x2, bf.NPAD, b, s * (H + E) + H + d, c);                                     // this frame's LSTM-2 input
+  }
+}
+
+__global__ void bt_pointwise2(Params p, Bufs bf, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * H) return;
+  if (p.free_running && __ldcg(p.done_count) >= p.B) return;
+  const int j = i / p.B, b = i - j * p.B;
+  float pre[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float a = p.d_b_ih[g * H + j] + p.d_b_hh[g * H + j];
+#pragma unroll
+    for (int k = 0; k < SPLITS2; ++k) a += bf.g2[((size_t)k * 4 * H + g * H + j) * bf.NPAD + b];
+    pre[g] = a;
+  }
+  const size_t idx = (size_t)b * H + j;
+  float cn = sigmoidf_(pre[1]) * bf.c2[idx] + sigmoidf_(pre[0]) * tanhf(pre[2]);
+  float hn = sigmoidf_(pre[3]) * tanhf(cn);
+  if (p.training) {
+    const float sc = 1.0f / (1.0f - p.p_dec);
+    const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * p.B * H : nullptr;
+    const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * p.B * H : nullptr;
+    hn *= keep_mult(kh, idx, p.seed, 8, t, (int)idx, p.thresh_dec, sc);
+    cn *= keep_mult(kc, idx, p.seed, 9, t, (int)idx, p.thresh_dec, sc);
+  }
+  bf.c2[idx] = cn;
+  bf.h2f[idx] = hn;
+  x_store(bf.x2, bf.NPAD, b, p.S * (H + E) + j, hn);     // next frame's recurrent input
+}
+
+// mel / gate projection (one warp per (row, batch)) + stop test
+__global__ void __launch_bounds__(256) bt_proj(Params p, Bufs bf, int t) {
+  if (p.free_running && __ldcg(p.done_count) >= p.B) return;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= (M + 1) * p.B) return;
+  const int row = gw / p.B, b = gw - row * p.B;
+  const int KD = H + p.S * E;
+  const float* w = row < M ? p.proj_w + (size_t)row * KD : p.gate_w;
+  float acc = 0.f;
+  for (int k = lane * 4; k < KD; k += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(w + k);
+    float4 x;
+    if (k < H) x = *reinterpret_cast<const float4*>(bf.h2f + (size_t)b * H + k);
+    else { const int kk = k - H, s = kk / E, d = kk - s * E; x = *reinterpret_cast<const float4*>(p.ctx + ((size_t)s * p.B + b) * E + d); }
+    acc = fmaf(a.x, x.x, acc); acc = fmaf(a.y, x.y, acc); acc = fmaf(a.z, x.z, acc); acc = fmaf(a.w, x.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane != 0) return;
+  if (row < M) {
+    p.mel[((size_t)b * p.Tcap + t) * M + row] = acc + p.proj_b[row];
+  } else {
+    const float g = acc + p.gate_b[0];
+    p.gate[(size_t)b * p.Tcap + t] = g;
+    if (p.free_running && p.n_frames[b] == 0) {
+      if (sigmoidf_(g) > p.gate_thr) { p.n_frames[b] = t + 1; atomicAdd(p.done_count, 1); }
+      else if (t + 1 == p.max_steps) { p.n_frames[b] = t + 1; p.reached_max[b] = 1; atomicAdd(p.done_count, 1); }
+    }
+  }
+}
+
+}  // namespace bt

@@ -91,9 +91,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 struct GemmParams {
   const unsigned char* a_tiles;   // [groups][M/128][K/64] tiles of 16 KB
-  const unsigned char* x_tiles;   // [groups][K/64] tiles of NPAD*128 B
+  const unsigned char* x_tiles;   // per group: k-block tiles of NPAD*128 B
   float* out;                     // [groups][splits][M][NPAD]
   int M, K, splits, groups;       // K per group; each split covers K/splits columns (multiple of 64)
+  long long x_group_stride;       // bytes between the X operands of consecutive groups (0 = shared buffer)
+  int x_kb_base, x_kb_group_step; // first k-block of X inside its buffer = x_kb_base + group * x_kb_group_step
+  const int* done;                // optional early-exit: skip when *done >= done_target (free-running decode)
+  int done_target;
 };
 
 template <int NPAD>
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
 
+  if (p.done != nullptr && __ldcg(p.done) >= p.done_target) return;   // uniform: nothing in this launch changes it
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, split = blockIdx.y, group = blockIdx.z;
   const int m_tiles = p.M / kBlockM, kb_total = p.K / kBlockK, kb_per_split = kb_total / p.splits;
@@ -129,7 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
     // ===== TMA producer =====
     if (lane == 0) {
       const unsigned char* a_src = p.a_tiles + ((size_t)group * m_tiles + mt) * kb_total * kATileBytes;
-      const unsigned char* x_src = p.x_tiles + (size_t)group * kb_total * kXTileBytes;
+      const unsigned char* x_src = p.x_tiles + (size_t)group * p.x_group_stride +
+                                   (size_t)(p.x_kb_base + group * p.x_kb_group_step) * kXTileBytes;
       for (int i = 0; i < kb_per_split; ++i) {
         const int s = i % kStages;
         mbar_wait(&empty_bar[s], (uint32_t)(((i / kStages) & 1) ^ 1));

@@ -317,6 +317,7 @@ __device__ __forceinline__ void linear_phase(const float* W, int n_rows, int K, 
 // ------------------------------------------------------------------------------------------
 // Attention task (one CTA per (batch, stream)): energies, probabilities, context.
 // ------------------------------------------------------------------------------------------
+template <bool kFast>   // kFast: ex2-based tanh + 4 positions per warp (batched tensor path; error ~1e-6)
 __device__ void attention_task(const Params& p, int s, int b, int t, float* sm) {
   const StreamParams& sp = p.st[s];
   const int Ts = sp.Ts, A = p.A, E = p.E;
@@ -361,6 +362,22 @@ __device__ void attention_task(const Params& p, int s, int b, int t, float* sm) 
 
   // ---- energies: one warp per position ----------------------------------------------
   const float* pm_b = sp.pm + (size_t)b * Ts * A;
+  if (kFast && p.attention == TACO2DEC_ATTN_SMA && A == 128) {
+    const float q0 = q_s[lane], q1 = q_s[lane + 32], q2 = q_s[lane + 64], q3 = q_s[lane + 96];
+    const float v0 = v_s[lane], v1 = v_s[lane + 32], v2 = v_s[lane + 64], v3 = v_s[lane + 96];
+    for (int j0 = warp * 4; j0 < Ts; j0 += kWarps * 4) {
+      float e[4];
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        const float* r = pm_b + (size_t)min(j0 + pp, Ts - 1) * A;
+        e[pp] = v0 * lat::fast_tanh(q0 + __ldg(r + lane)) + v1 * lat::fast_tanh(q1 + __ldg(r + lane + 32)) +
+                v2 * lat::fast_tanh(q2 + __ldg(r + lane + 64)) + v3 * lat::fast_tanh(q3 + __ldg(r + lane + 96));
+      }
+      const float ev = lat::butterfly4(e[0], e[1], e[2], e[3], lane);
+      const int j = j0 + (lane >> 3);
+      if ((lane & 7) == 0 && j < Ts) e_s[j] = (j >= len) ? -INFINITY : ev;
+    }
+  } else
   for (int j = warp; j < Ts; j += kWarps) {
     float feat = 0.0f;
     if (p.attention == TACO2DEC_ATTN_LSA) {
@@ -380,7 +397,7 @@ __device__ void attention_task(const Params& p, int s, int b, int t, float* sm) 
         for (int f = 0; f < p.LF; ++f) loc = fmaf(wd_s[f * A + a], __shfl_sync(0xffffffffu, feat, f), loc);
         z += loc;
       }
-      part = fmaf(v_s[a], tanhf(z), part);
+      part = fmaf(v_s[a], kFast ? lat::fast_tanh(z) : tanhf(z), part);
     }
     part = warp_sum(part);
     if (lane == 0) e_s[j] = (j >= len) ? -INFINITY : part;  // masked_fill_(mask, -inf), attention.py:79,389
@@ -660,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
     PH_MARK(7)
 
     // ================= B: attention (one CTA per (batch, stream)) ==================================
-    for (int task = blockIdx.x; task < S * B; task += gridDim.x) attention_task(p, task % S, task / S, t, smem);
+    for (int task = blockIdx.x; task < S * B; task += gridDim.x) attention_task<false>(p, task % S, task / S, t, smem);
     PH_MARK(8)
     if (!grid_sync(gb, &s_flag)) return;
     PH_MARK(9)
@@ -753,6 +770,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
     for (int i = 0; i < 16; ++i) p.phase_clocks[i] = s_ph[i];
 #undef PH_MARK
 }
+
+#include "batched.cuh"
 
 // ------------------------------------------------------------------------------------------
 // One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
@@ -875,7 +894,9 @@ struct taco2dec_handle {
   unsigned long long* packed_off;  // device [NL+1]
   unsigned long long* ll_buf;      // latency path LL exchange region (library-owned)
   size_t ll_bytes;
-  int last_path;         // path actually taken by the most recent call (1 generic, 2 latency)
+  int last_path;         // path actually taken by the most recent call (1 generic, 2 latency, 3 tensor)
+  bt::Bufs bt_bufs;      // batched tensor path: library-owned tiled operands / partials / state
+  bool bt_alloc, bt_tiles_valid;
   bool profiling;        // record CUDA events around the persistent launch
   cudaEvent_t ev0, ev1;
   bool ev_valid;
@@ -1143,6 +1164,103 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Batched tensor-core path (batched.cuh + gemm_tc.cuh): eligibility, buffers, per-frame launch sequence
+// ------------------------------------------------------------------------------------------
+size_t attention_smem_bytes(const taco2dec_config& c, int T_in, int T_sub) {
+  const int Tm = std::max(T_in, T_sub);
+  const int pad = c.attention == TACO2DEC_ATTN_LSA ? (c.loc_kernel - 1) / 2 : 1;
+  const size_t nj = (size_t)(kThreads / (c.enc_dim / 4) > 0 ? kThreads / (c.enc_dim / 4) : 1);
+  const size_t att = (size_t)2 * c.attn_dim + 2 * (size_t)Tm + 2 * (size_t)(Tm + 2 * pad) + (size_t)c.loc_filters * c.attn_dim +
+                     2 * (size_t)c.loc_kernel * c.loc_filters + std::max<size_t>(nj * c.enc_dim, 64) + 64;
+  return align_up(att * sizeof(float), 16);
+}
+
+bool bt_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
+  const taco2dec_config& c = h->cfg;
+  if (B < 16 || B > 128) return false;
+  if (c.attn_rnn_dim != bt::H || c.dec_rnn_dim != bt::H || c.enc_dim != bt::E || c.prenet_dim != bt::P ||
+      c.attn_dim != bt::A || c.n_mel != bt::M)
+    return false;
+  return attention_smem_bytes(c, T_in, T_sub) <= (size_t)h->max_smem_optin;
+}
+
+int bt_prepare(taco2dec_handle* h, cudaStream_t st) {
+  const int S = h->cfg.n_streams;
+  bt::Bufs& b = h->bt_bufs;
+  const int K2 = S * (bt::H + bt::E) + bt::H;
+  if (!h->bt_alloc) {
+    const size_t NP = 128;
+    CUDA_TRY(cudaMalloc(&b.a1, (size_t)S * 32 * (bt::K1 / 64) * tc::kATileBytes));
+    CUDA_TRY(cudaMalloc(&b.a2, (size_t)32 * (K2 / 64) * tc::kATileBytes));
+    CUDA_TRY(cudaMalloc(&b.aq, (size_t)S * (bt::H / 64) * tc::kATileBytes));
+    CUDA_TRY(cudaMalloc(&b.x1, (size_t)S * (bt::K1 / 64) * NP * 128));
+    CUDA_TRY(cudaMalloc(&b.x2, (size_t)(K2 / 64) * NP * 128));
+    CUDA_TRY(cudaMalloc(&b.g1, (size_t)S * bt::SPLITS1 * 4 * bt::H * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.g2, (size_t)bt::SPLITS2 * 4 * bt::H * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.gq, (size_t)S * bt::SPLITSQ * 128 * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.c1, (size_t)S * NP * bt::H * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.c2, (size_t)NP * bt::H * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.h2f, (size_t)NP * bt::H * sizeof(float)));
+    h->bt_alloc = true;
+  }
+  b.K2 = K2;
+  if (!h->bt_tiles_valid) {
+    for (int s = 0; s < S; ++s) {
+      bt::pack_concat_tiles_kernel<<<2048, 256, 0, st>>>(h->w.stream[s].arnn_w_ih, bt::P + bt::E, h->w.stream[s].arnn_w_hh, bt::H,
+                                                         4 * bt::H, b.a1 + (size_t)s * 32 * (bt::K1 / 64) * tc::kATileBytes);
+      bt::pack_concat_tiles_kernel<<<256, 256, 0, st>>>(h->w.stream[s].query_w, bt::H, nullptr, 0, bt::A,
+                                                        b.aq + (size_t)s * (bt::H / 64) * tc::kATileBytes);
+    }
+    bt::pack_concat_tiles_kernel<<<4096, 256, 0, st>>>(h->w.drnn_w_ih, S * (bt::H + bt::E), h->w.drnn_w_hh, bt::H, 4 * bt::H, b.a2);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2 * S + 1;
+    h->bt_tiles_valid = true;
+  }
+  return 0;
+}
+
+template <int NPAD>
+int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStream_t st) {
+  bt::Bufs bf = h->bt_bufs;
+  bf.NPAD = NPAD;
+  const int S = p.S, B = p.B;
+  const int n_steps = p.free_running ? p.max_steps : p.T;
+  CUDA_TRY(cudaMemsetAsync(bf.x1, 0, (size_t)S * (bt::K1 / 64) * NPAD * 128, st));
+  CUDA_TRY(cudaMemsetAsync(bf.x2, 0, (size_t)(bf.K2 / 64) * NPAD * 128, st));
+  bt::bt_init_kernel<<<h->num_sms, 256, 0, st>>>(p, bf);
+  CUDA_TRY(cudaFuncSetAttribute(bt::bt_attention<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  const int* done = p.free_running ? p.done_count : nullptr;
+  tc::GemmParams g1{bf.a1, bf.x1, bf.g1, 4 * bt::H, bt::K1, bt::SPLITS1, S, (long long)(bt::K1 / 64) * NPAD * 128, 0, 0, done, B};
+  tc::GemmParams gq{bf.aq, bf.x2, bf.gq, 128, bt::H, bt::SPLITSQ, S, 0, 0, (bt::H + bt::E) / 64, done, B};
+  tc::GemmParams g2{bf.a2, bf.x2, bf.g2, 4 * bt::H, bf.K2, bt::SPLITS2, 1, 0, 0, 0, done, B};
+  for (int t = 0; t < n_steps; ++t) {
+    if (p.free_running) bt::bt_prenet_fr<<<S * B, 256, 0, st>>>(p, bf, t);
+    else bt::bt_prenet_tf_to_x1<<<(S * B * bt::P + 255) / 256, 256, 0, st>>>(p, bf, t);
+    CUDA_TRY(tc::launch_gemm<NPAD>(g1, st));
+    bt::bt_pointwise1<<<(S * B * bt::H + 255) / 256, 256, 0, st>>>(p, bf, t);
+    CUDA_TRY(tc::launch_gemm<NPAD>(gq, st));
+    bt::bt_attention<true><<<S * B, kThreads, att_smem, st>>>(p, bf, t);
+    CUDA_TRY(tc::launch_gemm<NPAD>(g2, st));
+    bt::bt_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, st>>>(p, bf, t);
+    bt::bt_proj<<<((bt::M + 1) * B * 32 + 255) / 256, 256, 0, st>>>(p, bf, t);
+    h->launches += 8;
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  h->last_path = TACO2DEC_PATH_TENSOR;
+  return 0;
+}
+
+int run_batched(taco2dec_handle* h, const Params& p, int T_in, int T_sub, cudaStream_t st) {
+  if (int rc = bt_prepare(h, st)) return rc;
+  const size_t att = attention_smem_bytes(h->cfg, T_in, T_sub);
+  if (p.B <= 16) return bt_run_frames<16>(h, p, att, st);
+  if (p.B <= 32) return bt_run_frames<32>(h, p, att, st);
+  if (p.B <= 64) return bt_run_frames<64>(h, p, att, st);
+  return bt_run_frames<128>(h, p, att, st);
+}
+
 int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, const WorkspaceLayout& L, cudaStream_t st) {
   const taco2dec_config& c = h->cfg;
   // control words: barrier counter, watchdog flag, done counter
@@ -1157,10 +1275,18 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
-  const bool want_lat = h->path_mode != TACO2DEC_PATH_GENERIC && lat_shape_ok(h, p.B, T_in, T_sub);
+  const bool want_lat = (h->path_mode == TACO2DEC_PATH_AUTO || h->path_mode == TACO2DEC_PATH_LATENCY) &&
+                        lat_shape_ok(h, p.B, T_in, T_sub);
   if (h->path_mode == TACO2DEC_PATH_LATENCY && !want_lat)
     return fail(TACO2DEC_E_ARG, "latency path needs B=1, SMA, default decoder dims and a short enough memory");
   if (want_lat) return run_latency(h, p, st);
+  const bool tensor_ok = bt_shape_ok(h, p.B, T_in, T_sub);
+  if (h->path_mode == TACO2DEC_PATH_TENSOR && !tensor_ok)
+    return fail(TACO2DEC_E_ARG, "tensor path needs 16 <= B <= 128 and default decoder dims");
+  // AUTO takes the tensor-core path only when fp16 operands were asked for (it rounds weights AND x/h to fp16)
+  if (tensor_ok && (h->path_mode == TACO2DEC_PATH_TENSOR ||
+                    (h->path_mode == TACO2DEC_PATH_AUTO && h->weight_dtype == TACO2DEC_W_FP16)))
+    return run_batched(h, p, T_in, T_sub, st);
   h->last_path = TACO2DEC_PATH_GENERIC;
   const int BT = pick_bt(p.B);
   const size_t smem = persistent_smem_bytes(c, BT, T_in, T_sub);
@@ -1194,7 +1320,7 @@ int run_test_gemm(int M, int N, int K, int splits, const float* A, const float* 
   CUDA_TRY(cudaMalloc(&part, (size_t)splits * M * NPAD * sizeof(float)));
   tc::pack_tiles_kernel<<<1024, 256, 0, st>>>(A, M, K, tc::kBlockM, M / tc::kBlockM, a_t);
   tc::pack_tiles_kernel<<<256, 256, 0, st>>>(X, N, K, NPAD, 1, x_t);
-  tc::GemmParams gp{a_t, x_t, part, M, K, splits, 1};
+  tc::GemmParams gp{a_t, x_t, part, M, K, splits, 1, 0, 0, 0, nullptr, 0};
   CUDA_TRY(tc::launch_gemm<NPAD>(gp, st));
   sum_splits_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(part, splits, M, NPAD, N, out);
   CUDA_TRY(cudaGetLastError());
@@ -1235,6 +1361,7 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   h->weight_dtype = TACO2DEC_W_FP32;
   h->packed = nullptr; h->packed_bytes = 0; h->packed_wbytes = 0; h->packed_off = nullptr;
   h->ll_buf = nullptr; h->ll_bytes = 0; h->last_path = 0;
+  memset(&h->bt_bufs, 0, sizeof(h->bt_bufs)); h->bt_alloc = false; h->bt_tiles_valid = false;
   h->profiling = false;
   h->ev_valid = false;
   CUDA_TRY(cudaSetDevice(device));
@@ -1251,6 +1378,11 @@ int taco2dec_destroy(taco2dec_handle* h) {
     if (h->packed) cudaFree(h->packed);
     if (h->packed_off) cudaFree(h->packed_off);
     if (h->ll_buf) cudaFree(h->ll_buf);
+    if (h->bt_alloc) {
+      bt::Bufs& b = h->bt_bufs;
+      void* ptrs[] = {b.a1, b.a2, b.aq, b.x1, b.x2, b.g1, b.g2, b.gq, b.c1, b.c2, b.h2f};
+      for (void* q : ptrs) if (q) cudaFree(q);
+    }
   }
   delete h;
   return 0;
@@ -1278,7 +1410,7 @@ int taco2dec_test_gemm(int M, int N, int K, int splits, const float* A, const fl
 
 int taco2dec_set_mode(taco2dec_handle* h, int path, int weight_dtype) {
   if (!h) return fail(TACO2DEC_E_ARG, "null handle");
-  if (path < TACO2DEC_PATH_AUTO || path > TACO2DEC_PATH_LATENCY) return fail(TACO2DEC_E_ARG, "bad path");
+  if (path < TACO2DEC_PATH_AUTO || path > TACO2DEC_PATH_TENSOR) return fail(TACO2DEC_E_ARG, "bad path");
   if (weight_dtype != TACO2DEC_W_FP32 && weight_dtype != TACO2DEC_W_FP16) return fail(TACO2DEC_E_ARG, "bad weight dtype");
   h->path_mode = path;
   h->weight_dtype = weight_dtype;
@@ -1320,6 +1452,7 @@ int taco2dec_set_weights(taco2dec_handle* h, const taco2dec_weights* w, void* /*
   h->w = *w;
   h->have_weights = true;
   h->packed_wbytes = 0;  // latency-path weight streams are re-packed on next use
+  h->bt_tiles_valid = false;
   return 0;
 }
 

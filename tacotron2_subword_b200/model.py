@@ -79,7 +79,8 @@ class _Engine:
         return int(self.lib.taco2dec_launch_count(self.handle))
 
     def set_mode(self, path: str, weight_dtype: str) -> None:
-        paths = {"auto": _cabi.PATH_AUTO, "generic": _cabi.PATH_GENERIC, "latency": _cabi.PATH_LATENCY}
+        paths = {"auto": _cabi.PATH_AUTO, "generic": _cabi.PATH_GENERIC, "latency": _cabi.PATH_LATENCY,
+                 "tensor": _cabi.PATH_TENSOR}
         dts = {"fp32": _cabi.W_FP32, "fp16": _cabi.W_FP16}
         if (path, weight_dtype) != self.mode:
             _cabi.check(self.lib.taco2dec_set_mode(self.handle, paths[path], dts[weight_dtype]))
@@ -87,7 +88,7 @@ class _Engine:
             self.weights_key = None   # packed streams depend on the storage type
 
     def last_path(self) -> str:
-        return {0: "none", 1: "generic", 2: "latency"}[int(self.lib.taco2dec_last_path(self.handle))]
+        return {0: "none", 1: "generic", 2: "latency", 3: "tensor"}[int(self.lib.taco2dec_last_path(self.handle))]
 
     def set_profiling(self, on: bool) -> None:
         _cabi.check(self.lib.taco2dec_set_profiling(self.handle, int(on)))
@@ -179,7 +180,7 @@ class Decoder(nn.Module):
         self.linear_projection = LinearNorm(proj_in, mel_in)
         self.gate_layer = LinearNorm(proj_in, 1, bias=True, w_init_gain="sigmoid")
         # -- extensions (not in the reference) --------------------------------------------
-        self.decoder_path = "auto"      # "auto" | "generic" | "latency"  (see include/taco2dec.h)
+        self.decoder_path = "auto"      # "auto" | "generic" | "latency" | "tensor"  (see include/taco2dec.h)
         self.weight_dtype = "fp32"      # storage of the packed LSTM matrices on the latency path: "fp32" | "fp16"
         self.dropout_replay: Optional[DropoutReplay] = None  # parity runs: externally drawn masks
         self.rng_seed: Optional[int] = None                  # fixed Philox seed; None = fresh per call
