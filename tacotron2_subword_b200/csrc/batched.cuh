@@ -37,6 +37,7 @@ struct Bufs {
   float* gq;            // [S][SPLITSQ][128][NPAD]
   // fp32 state
   float *c1, *c2, *h2f; // [S][B][H], [B][H], [B][H]
+  float *w0t[2], *w1t[2]; // transposed prenet weights [M][P], [P][P] (coalesced column reads)
   int NPAD, K2;
 };
 
@@ -79,7 +80,8 @@ __global__ void bt_init_kernel(Params p, Bufs bf) {
 }
 
 // teacher-forced: hoisted prenet output of frame t -> X1 columns [0, P)
-__global__ void bt_prenet_tf_to_x1(Params p, Bufs bf, int t) {
+__global__ void bt_prenet_tf_to_x1(Params p, Bufs bf, const int* t_ptr) {
+  const int t = *t_ptr;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.S * p.B * P) return;
   const int s = i / (p.B * P), r = i - s * p.B * P, b = r / P, k = r - b * P;
@@ -87,33 +89,74 @@ __global__ void bt_prenet_tf_to_x1(Params p, Bufs bf, int t) {
   x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, k, v);
 }
 
-// free-running: prenet(mel[t-1]) for both streams; one CTA per (stream, batch); writes X1 columns [0, P)
-__global__ void __launch_bounds__(256) bt_prenet_fr(Params p, Bufs bf, int t) {
-  __shared__ float x_s[M], h_s[P];
+__global__ void transpose_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) { const int r = i / cols, c = i - r * cols; dst[(size_t)c * rows + r] = src[i]; }
+}
+
+// free-running: prenet(mel[t-1]) for both streams.  Block = (stream, tile of kPreBT utterances), 1024 threads =
+// 4 k-quarters x 256 outputs; weights are read transposed (coalesced across outputs) and shared by the tile.
+constexpr int kPreBT = 4;
+__global__ void __launch_bounds__(1024) bt_prenet_fr(Params p, Bufs bf, const int* t_ptr) {
+  __shared__ float x_s[kPreBT][M], h_s[kPreBT][P], part_s[4][kPreBT][P];
+  const int t = *t_ptr;
   if (__ldcg(p.done_count) >= p.B) return;
-  const int s = blockIdx.x / p.B, b = blockIdx.x - s * p.B, tid = threadIdx.x;
+  const int tiles = (p.B + kPreBT - 1) / kPreBT;
+  const int s = blockIdx.x / tiles, b0 = (blockIdx.x - s * tiles) * kPreBT, tid = threadIdx.x;
+  const int kq = tid >> 8, o = tid & 255;
   const StreamParams& sp = p.st[s];
-  for (int m = tid; m < M; m += 256) x_s[m] = t > 0 ? p.mel[((size_t)b * p.Tcap + (t - 1)) * M + m] : 0.f;
-  __syncthreads();
-  {
-    float acc = 0.f;
-    const float* w = sp.pre_w0 + (size_t)tid * M;
-    for (int k = 0; k < M; ++k) acc = fmaf(w[k], x_s[k], acc);
-    const float mult = keep_mult(sp.keep0, ((size_t)t * p.B + b) * P + tid, p.seed, s * 2 + 0, t, b * P + tid, p.thresh_pre, 2.0f);
-    h_s[tid] = fmaxf(acc, 0.f) * mult;
+  for (int i = tid; i < kPreBT * M; i += 1024) {
+    const int bb = i / M, m = i - bb * M, b = b0 + bb;
+    x_s[bb][m] = (t > 0 && b < p.B) ? p.mel[((size_t)b * p.Tcap + (t - 1)) * M + m] : 0.f;
   }
   __syncthreads();
   {
-    float acc = 0.f;
-    const float* w = sp.pre_w1 + (size_t)tid * P;
-    for (int k = 0; k < P; ++k) acc = fmaf(w[k], h_s[k], acc);
-    const float mult = keep_mult(sp.keep1, ((size_t)t * p.B + b) * P + tid, p.seed, s * 2 + 1, t, b * P + tid, p.thresh_pre, 2.0f);
-    x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, tid, fmaxf(acc, 0.f) * mult);
+    float acc[kPreBT] = {0.f, 0.f, 0.f, 0.f};
+    const float* w = bf.w0t[s] + o;
+#pragma unroll 5
+    for (int k = kq * (M / 4); k < (kq + 1) * (M / 4); ++k) {
+      const float wv = __ldg(w + (size_t)k * P);
+#pragma unroll
+      for (int bb = 0; bb < kPreBT; ++bb) acc[bb] = fmaf(wv, x_s[bb][k], acc[bb]);
+    }
+#pragma unroll
+    for (int bb = 0; bb < kPreBT; ++bb) part_s[kq][bb][o] = acc[bb];
+  }
+  __syncthreads();
+  if (tid < kPreBT * P) {
+    const int bb = tid >> 8, b = b0 + bb;
+    const float v = (part_s[0][bb][o] + part_s[1][bb][o]) + (part_s[2][bb][o] + part_s[3][bb][o]);
+    float mult = 0.f;
+    if (b < p.B) mult = keep_mult(sp.keep0, ((size_t)t * p.B + b) * P + o, p.seed, s * 2 + 0, t, b * P + o, p.thresh_pre, 2.0f);
+    h_s[bb][o] = fmaxf(v, 0.f) * mult;
+  }
+  __syncthreads();
+  {
+    float acc[kPreBT] = {0.f, 0.f, 0.f, 0.f};
+    const float* w = bf.w1t[s] + o;
+#pragma unroll 8
+    for (int k = kq * (P / 4); k < (kq + 1) * (P / 4); ++k) {
+      const float wv = __ldg(w + (size_t)k * P);
+#pragma unroll
+      for (int bb = 0; bb < kPreBT; ++bb) acc[bb] = fmaf(wv, h_s[bb][k], acc[bb]);
+    }
+#pragma unroll
+    for (int bb = 0; bb < kPreBT; ++bb) part_s[kq][bb][o] = acc[bb];
+  }
+  __syncthreads();
+  if (tid < kPreBT * P) {
+    const int bb = tid >> 8, b = b0 + bb;
+    if (b < p.B) {
+      const float v = (part_s[0][bb][o] + part_s[1][bb][o]) + (part_s[2][bb][o] + part_s[3][bb][o]);
+      const float mult = keep_mult(sp.keep1, ((size_t)t * p.B + b) * P + o, p.seed, s * 2 + 1, t, b * P + o, p.thresh_pre, 2.0f);
+      x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, o, fmaxf(v, 0.f) * mult);
+    }
   }
 }
 
 // attention-LSTM pointwise: sums the split-K partials, gate order i,f,g,o (nn.LSTMCell), dropout on h and c
-__global__ void bt_pointwise1(Params p, Bufs bf, int t) {
+__global__ void bt_pointwise1(Params p, Bufs bf, const int* t_ptr) {
+  const int t = *t_ptr;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.S * p.B * H) return;
   if (p.free_running && __ldcg(p.done_count) >= p.B) return;
@@ -144,8 +187,9 @@ __global__ void bt_pointwise1(Params p, Bufs bf, int t) {
 
 // attention: q = sum of the query-GEMM partials, then the generic attention task; context -> fp32 + tiles
 template <bool kDummy>
-__global__ void __launch_bounds__(kThreads, 1) bt_attention(Params p, Bufs bf, int t) {
+__global__ void __launch_bounds__(kThreads, 1) bt_attention(Params p, Bufs bf, const int* t_ptr) {
   extern __shared__ __align__(16) float att_smem[];
+  const int t = *t_ptr;
   if (p.free_running && __ldcg(p.done_count) >= p.B) return;
   const int s = blockIdx.x % p.S, b = blockIdx.x / p.S, tid = threadIdx.x;
   if (tid < A) {
@@ -163,7 +207,8 @@ __global__ void __launch_bounds__(kThreads, 1) bt_attention(Params p, Bufs bf, i
   }
 }
 
-__global__ void bt_pointwise2(Params p, Bufs bf, int t) {
+__global__ void bt_pointwise2(Params p, Bufs bf, const int* t_ptr) {
+  const int t = *t_ptr;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B * H) return;
   if (p.free_running && __ldcg(p.done_count) >= p.B) return;
@@ -192,7 +237,8 @@ __global__ void bt_pointwise2(Params p, Bufs bf, int t) {
 }
 
 // mel / gate projection (one warp per (row, batch)) + stop test
-__global__ void __launch_bounds__(256) bt_proj(Params p, Bufs bf, int t) {
+__global__ void __launch_bounds__(256) bt_proj(Params p, Bufs bf, const int* t_ptr) {
+  const int t = *t_ptr;
   if (p.free_running && __ldcg(p.done_count) >= p.B) return;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -221,5 +267,8 @@ __global__ void __launch_bounds__(256) bt_proj(Params p, Bufs bf, int t) {
     }
   }
 }
+
+// frame counter lives in device memory so that one captured CUDA graph serves every frame
+__global__ void bt_advance(int* t_ptr) { *t_ptr += 1; }
 
 }  // namespace bt

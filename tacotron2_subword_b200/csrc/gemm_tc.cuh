@@ -210,10 +210,14 @@ __global__ void pack_tiles_kernel(const float* __restrict__ src, int n_rows, int
 }
 
 template <int NPAD>
+inline cudaError_t prepare_gemm() {   // once per process / NPAD (not a stream operation)
+  const size_t smem = (size_t)kStages * (kATileBytes + NPAD * kBlockK * 2);
+  return cudaFuncSetAttribute(gemm_f16_tn_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int NPAD>
 inline cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st) {
   const size_t smem = (size_t)kStages * (kATileBytes + NPAD * kBlockK * 2);
-  cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   dim3 grid(p.M / kBlockM, p.splits, p.groups);
   gemm_f16_tn_kernel<NPAD><<<grid, kThreads, smem, st>>>(p);
   return cudaGetLastError();

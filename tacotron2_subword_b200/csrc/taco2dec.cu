@@ -897,6 +897,7 @@ struct taco2dec_handle {
   int last_path;         // path actually taken by the most recent call (1 generic, 2 latency, 3 tensor)
   bt::Bufs bt_bufs;      // batched tensor path: library-owned tiled operands / partials / state
   bool bt_alloc, bt_tiles_valid;
+  cudaStream_t cap_stream;   // private stream used only to capture the per-frame CUDA graph
   bool profiling;        // record CUDA events around the persistent launch
   cudaEvent_t ev0, ev1;
   bool ev_valid;
@@ -1202,6 +1203,10 @@ int bt_prepare(taco2dec_handle* h, cudaStream_t st) {
     CUDA_TRY(cudaMalloc(&b.c1, (size_t)S * NP * bt::H * sizeof(float)));
     CUDA_TRY(cudaMalloc(&b.c2, (size_t)NP * bt::H * sizeof(float)));
     CUDA_TRY(cudaMalloc(&b.h2f, (size_t)NP * bt::H * sizeof(float)));
+    for (int s = 0; s < S; ++s) {
+      CUDA_TRY(cudaMalloc(&b.w0t[s], (size_t)bt::M * bt::P * sizeof(float)));
+      CUDA_TRY(cudaMalloc(&b.w1t[s], (size_t)bt::P * bt::P * sizeof(float)));
+    }
     h->bt_alloc = true;
   }
   b.K2 = K2;
@@ -1211,6 +1216,10 @@ int bt_prepare(taco2dec_handle* h, cudaStream_t st) {
                                                          4 * bt::H, b.a1 + (size_t)s * 32 * (bt::K1 / 64) * tc::kATileBytes);
       bt::pack_concat_tiles_kernel<<<256, 256, 0, st>>>(h->w.stream[s].query_w, bt::H, nullptr, 0, bt::A,
                                                         b.aq + (size_t)s * (bt::H / 64) * tc::kATileBytes);
+    }
+    for (int s = 0; s < S; ++s) {
+      bt::transpose_kernel<<<(bt::P * bt::M + 255) / 256, 256, 0, st>>>(h->w.stream[s].prenet_w0, bt::P, bt::M, b.w0t[s]);
+      bt::transpose_kernel<<<(bt::P * bt::P + 255) / 256, 256, 0, st>>>(h->w.stream[s].prenet_w1, bt::P, bt::P, b.w1t[s]);
     }
     bt::pack_concat_tiles_kernel<<<4096, 256, 0, st>>>(h->w.drnn_w_ih, S * (bt::H + bt::E), h->w.drnn_w_hh, bt::H, 4 * bt::H, b.a2);
     CUDA_TRY(cudaGetLastError());
@@ -1234,18 +1243,45 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   tc::GemmParams g1{bf.a1, bf.x1, bf.g1, 4 * bt::H, bt::K1, bt::SPLITS1, S, (long long)(bt::K1 / 64) * NPAD * 128, 0, 0, done, B};
   tc::GemmParams gq{bf.aq, bf.x2, bf.gq, 128, bt::H, bt::SPLITSQ, S, 0, 0, (bt::H + bt::E) / 64, done, B};
   tc::GemmParams g2{bf.a2, bf.x2, bf.g2, 4 * bt::H, bf.K2, bt::SPLITS2, 1, 0, 0, 0, done, B};
-  for (int t = 0; t < n_steps; ++t) {
-    if (p.free_running) bt::bt_prenet_fr<<<S * B, 256, 0, st>>>(p, bf, t);
-    else bt::bt_prenet_tf_to_x1<<<(S * B * bt::P + 255) / 256, 256, 0, st>>>(p, bf, t);
-    CUDA_TRY(tc::launch_gemm<NPAD>(g1, st));
-    bt::bt_pointwise1<<<(S * B * bt::H + 255) / 256, 256, 0, st>>>(p, bf, t);
-    CUDA_TRY(tc::launch_gemm<NPAD>(gq, st));
-    bt::bt_attention<true><<<S * B, kThreads, att_smem, st>>>(p, bf, t);
-    CUDA_TRY(tc::launch_gemm<NPAD>(g2, st));
-    bt::bt_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, st>>>(p, bf, t);
-    bt::bt_proj<<<((bt::M + 1) * B * 32 + 255) / 256, 256, 0, st>>>(p, bf, t);
-    h->launches += 8;
+  CUDA_TRY(tc::prepare_gemm<NPAD>());
+  // One frame = 9 kernels; the frame index is read from device memory, so the sequence is captured ONCE into
+  // a CUDA graph and replayed n_steps times (one graph launch per frame instead of nine kernel launches).
+  // Capture happens on a private stream (the caller's stream may be the legacy default stream, which cannot
+  // be captured); the instantiated graph is launched on the caller's stream.
+  int* t_ptr = p.done_count + 1;                      // control block word, zeroed by run_common
+  if (!h->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t cs = h->cap_stream;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+  if (p.free_running) bt::bt_prenet_fr<<<S * ((B + bt::kPreBT - 1) / bt::kPreBT), 1024, 0, cs>>>(p, bf, t_ptr);
+  else bt::bt_prenet_tf_to_x1<<<(S * B * bt::P + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
+  cudaError_t ce = tc::launch_gemm<NPAD>(g1, cs);
+  bt::bt_pointwise1<<<(S * B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
+  if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(gq, cs);
+  bt::bt_attention<true><<<S * B, kThreads, att_smem, cs>>>(p, bf, t_ptr);
+  if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(g2, cs);
+  bt::bt_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
+  bt::bt_proj<<<((bt::M + 1) * B * 32 + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
+  bt::bt_advance<<<1, 1, 0, cs>>>(t_ptr);
+  const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
+  if (ce != cudaSuccess || ee != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    return fail(TACO2DEC_E_CUDA, std::string("graph capture of the frame sequence failed: ") +
+                                     cudaGetErrorString(ce != cudaSuccess ? ce : ee));
   }
+  CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+  for (int t = 0; t < n_steps; ++t) {
+    const cudaError_t le = cudaGraphLaunch(exec, st);
+    if (le != cudaSuccess) {
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+      return fail(TACO2DEC_E_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
+    }
+  }
+  h->launches += 9LL * n_steps;
+  // the executable graph may be destroyed once its launches are enqueued; CUDA keeps it alive until they finish
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   h->last_path = TACO2DEC_PATH_TENSOR;
@@ -1321,6 +1357,7 @@ int run_test_gemm(int M, int N, int K, int splits, const float* A, const float* 
   tc::pack_tiles_kernel<<<1024, 256, 0, st>>>(A, M, K, tc::kBlockM, M / tc::kBlockM, a_t);
   tc::pack_tiles_kernel<<<256, 256, 0, st>>>(X, N, K, NPAD, 1, x_t);
   tc::GemmParams gp{a_t, x_t, part, M, K, splits, 1, 0, 0, 0, nullptr, 0};
+  CUDA_TRY(tc::prepare_gemm<NPAD>());
   CUDA_TRY(tc::launch_gemm<NPAD>(gp, st));
   sum_splits_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(part, splits, M, NPAD, N, out);
   CUDA_TRY(cudaGetLastError());
@@ -1361,7 +1398,7 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   h->weight_dtype = TACO2DEC_W_FP32;
   h->packed = nullptr; h->packed_bytes = 0; h->packed_wbytes = 0; h->packed_off = nullptr;
   h->ll_buf = nullptr; h->ll_bytes = 0; h->last_path = 0;
-  memset(&h->bt_bufs, 0, sizeof(h->bt_bufs)); h->bt_alloc = false; h->bt_tiles_valid = false;
+  memset(&h->bt_bufs, 0, sizeof(h->bt_bufs)); h->bt_alloc = false; h->bt_tiles_valid = false; h->cap_stream = nullptr;
   h->profiling = false;
   h->ev_valid = false;
   CUDA_TRY(cudaSetDevice(device));
@@ -1378,9 +1415,10 @@ int taco2dec_destroy(taco2dec_handle* h) {
     if (h->packed) cudaFree(h->packed);
     if (h->packed_off) cudaFree(h->packed_off);
     if (h->ll_buf) cudaFree(h->ll_buf);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->bt_alloc) {
       bt::Bufs& b = h->bt_bufs;
-      void* ptrs[] = {b.a1, b.a2, b.aq, b.x1, b.x2, b.g1, b.g2, b.gq, b.c1, b.c2, b.h2f};
+      void* ptrs[] = {b.a1, b.a2, b.aq, b.x1, b.x2, b.g1, b.g2, b.gq, b.c1, b.c2, b.h2f, b.w0t[0], b.w0t[1], b.w1t[0], b.w1t[1]};
       for (void* q : ptrs) if (q) cudaFree(q);
     }
   }

@@ -1,0 +1,20 @@
+"""Short tensor-path run for ncu launch lists: python tools/tensor_probe.py [B] [T] [fr|tf]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from oracle.synth import SMA, make_decoder_weights, make_inputs
+from tacotron2_subword_b200 import Decoder, create_hparams
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+mode = sys.argv[3] if len(sys.argv) > 3 else "fr"
+w = make_decoder_weights(SMA, seed=1234, gate_bias=-20.0)
+dec = Decoder(create_hparams()); dec.load_state_dict(w); dec = dec.cuda().eval(); dec.rng_seed = 7
+dec.decoder_path, dec.weight_dtype = "tensor", "fp16"
+inp = make_inputs(B, 120, 40, T, seed=3, ragged=True)
+a = [inp[k].cuda() for k in ("memory", "embeddings", "mels", "memory_lengths", "bert_lengths")]
+with torch.no_grad():
+    for _ in range(2):
+        if mode == "tf": dec(a[0], a[1], a[2], a[3], a[4])
+        else: dec.inference_batched(a[0], a[1], a[3], a[4], max_decoder_steps=T)
+torch.cuda.synchronize()
+print("ok")
