@@ -160,7 +160,8 @@ const char* taco2dec_last_error(void);
 int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** out);
 int taco2dec_destroy(taco2dec_handle* h);
 
-/* Borrow the fp32 weights (no copy, no repack in this version). */
+/* Borrow the fp32 weights (the generic path reads them in place).  The latency path and the tensor path also
+ * keep library-owned re-layouts (per-CTA streams, fp16 UMMA tiles) built here: call again after the weights change. */
 int taco2dec_set_weights(taco2dec_handle* h, const taco2dec_weights* w, void* cuda_stream);
 
 /* Scratch the caller must provide (state, processed memory, prenet activations). */
