@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TACO2DEC_ABI_VERSION 1
+#define TACO2DEC_ABI_VERSION 2
 
 #define TACO2DEC_ATTN_SMA 0 /* StepwiseMonotonicAttention   (attention.py:291-398, hparams default) */
 #define TACO2DEC_ATTN_LSA 1 /* LocationSensitiveAttention   (attention.py:7-85)                      */
@@ -129,7 +129,68 @@ typedef struct taco2dec_tf_args {
   float* align_bert; /* [B, T, T_sub]   (NULL when n_streams==1) */
   void* workspace;
   size_t workspace_bytes;
+  void* saved;        /* NULL, or a buffer of taco2dec_saved_layout_query().total bytes: the call keeps the activations
+                         taco2dec_backward needs (tensor path only: 16 <= B <= 128, SMA, default dims) */
+  size_t saved_bytes;
 } taco2dec_tf_args;
+
+/* Byte offsets of the arrays inside the `saved` buffer (fp32).  State arrays have T+1 slots: slot 0 = the zero
+ * initial state (model.py:237-256), slot t+1 = frame t.  s = stream index. */
+typedef struct taco2dec_saved_layout {
+  size_t gates1;   /* [T][S][5][H][B]   attention LSTMs: i, f, g, o (activated), new cell state before dropout */
+  size_t gates2;   /* [T][5][D][B]      decoder LSTM */
+  size_t h1;       /* [T+1][S][B][H]    attention-LSTM hidden state after dropout  (model.py:340-346) */
+  size_t ctx;      /* [T+1][S][B][enc]  attention contexts                          (attention.py:395) */
+  size_t h2;       /* [T+1][B][D]       decoder-LSTM hidden state after dropout    (model.py:371-373) */
+  size_t q;        /* [T][S][B][A]      processed queries                           (attention.py:368) */
+  size_t p[2];     /* [T][B][T_s]       SMA selection probabilities sigmoid(e)      (attention.py:352) */
+  size_t pm[2];    /* [B][T_s][A]       processed memory                            (model.py:258-261) */
+  size_t pre[2];   /* [T+1][B][prenet]  prenet output                               (model.py:412-413) */
+  size_t pre0[2];  /* [T+1][B][prenet]  prenet layer-0 output (after dropout) */
+  size_t total;
+} taco2dec_saved_layout;
+
+/* Byte offsets inside the `grads` buffer taco2dec_backward fills (fp32).  G = 4H gate rows, order i,f,g,o.
+ * The per-frame rows are contracted with the saved activations by the caller (plain GEMMs):
+ *   dW_ih[s] = dg1[s]^T . [pre[s][t] | ctx[s][t-1]],  dW_hh[s] = dg1[s]^T . h1[s][t-1],  db = sum dg1[s]
+ *   dWd_ih = dg2^T . [h1[0][t] | ctx[0][t] | h1[1][t] | ctx[1][t]],  dWd_hh = dg2^T . h2[t-1]
+ *   dWq[s] = dq[s]^T . h1[s][t],  dv[s] = sum_b dv[s][b],  dWm[s] = dpm[s]^T . memory[s]
+ *   dmemory[s][b] = align[s][b]^T . dctx[s][:, b] + dpm[s][b] . Wm[s]
+ *   prenet: dpre[s] back through the two bias-free ReLU/dropout layers (model.py:13-24). */
+typedef struct taco2dec_grad_layout {
+  size_t dg1;      /* [S][T][B][G]    attention-LSTM gate pre-activation gradients */
+  size_t dg2;      /* [T][B][G]       decoder-LSTM gate pre-activation gradients   */
+  size_t dq;       /* [S][T][B][A]    */
+  size_t dctx;     /* [S][T][B][enc]  total gradient of each frame's context       */
+  size_t dpre;     /* [S][T][B][prenet] gradient of the prenet output fed to frame t */
+  size_t dv;       /* [S][B][A]       */
+  size_t dpm[2];   /* [B][T_s][A]     gradient of the processed memory             */
+  size_t scratch;  /* internal carries (d alignment state, d cell states) */
+  size_t total;
+} taco2dec_grad_layout;
+
+/* Back-propagation through the teacher-forced pass (the reference obtains it from autograd over
+ * Decoder.forward, model.py:392-428, under train.py's loss.backward()).  Must follow a
+ * taco2dec_forward_teacher_forced call with the same shapes, rng and `saved` buffer. */
+typedef struct taco2dec_bwd_args {
+  int B, T, T_in, T_sub;
+  const float* memory;           /* as in the forward call */
+  const float* embeddings;
+  const int64_t* memory_lengths;
+  const int64_t* bert_lengths;
+  int training;
+  taco2dec_rng rng;              /* same masks / seed as the forward call (LSTM-state dropout is re-drawn) */
+  const float* align;            /* [B, T, T_in]   forward outputs */
+  const float* align_bert;       /* [B, T, T_sub]  */
+  const float* d_mel;            /* [B, T, n_mel]  gradient of the mel output (same layout as the forward output) */
+  const float* d_gate;           /* [B, T] */
+  const float* d_align;          /* [B, T, T_in]  or NULL */
+  const float* d_align_bert;     /* [B, T, T_sub] or NULL */
+  const void* saved;
+  size_t saved_bytes;
+  void* grads;
+  size_t grads_bytes;
+} taco2dec_bwd_args;
 
 /* Decoder.inference (free-running).  The reference is batch-1 only (model.py:461,480);
  * B > 1 here means B independent utterances, each defined as its own batch-1 run on its
@@ -169,6 +230,9 @@ size_t taco2dec_workspace_bytes(const taco2dec_handle* h, int B, int T_in, int T
                                 int teacher_forced);
 
 int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* a, void* cuda_stream);
+int taco2dec_saved_layout_query(const taco2dec_handle* h, int B, int T_in, int T_sub, int T, taco2dec_saved_layout* out);
+int taco2dec_grad_layout_query(const taco2dec_handle* h, int B, int T_in, int T_sub, int T, taco2dec_grad_layout* out);
+int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda_stream);
 int taco2dec_infer(taco2dec_handle* h, const taco2dec_infer_args* a, void* cuda_stream);
 
 /* Synchronises the stream and reports TACO2DEC_E_ABORTED if the in-kernel watchdog fired

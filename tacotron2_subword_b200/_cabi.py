@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtac
 ATTN_SMA, ATTN_LSA = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR = 0, 1, 2, 3
 W_FP32, W_FP16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTED_SYMBOLS = (
     "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "taco2dec_infer", "taco2dec_check", "taco2dec_launch_count", "taco2dec_philox_keep_mask",
     "taco2dec_launch_geometry", "taco2dec_set_profiling", "taco2dec_last_kernel_ms",
     "taco2dec_read_phase_clocks", "taco2dec_set_mode", "taco2dec_last_path",
-    "taco2dec_test_gemm",
+    "taco2dec_test_gemm", "taco2dec_saved_layout_query", "taco2dec_grad_layout_query", "taco2dec_backward",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -56,7 +56,29 @@ class TFArgs(C.Structure):
                 ("memory", _fp), ("embeddings", _fp), ("decoder_inputs", _fp),
                 ("memory_lengths", _fp), ("bert_lengths", _fp), ("training", C.c_int), ("rng", Rng),
                 ("mel", _fp), ("gate", _fp), ("align", _fp), ("align_bert", _fp),
-                ("workspace", _fp), ("workspace_bytes", C.c_size_t)]
+                ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+                ("saved", _fp), ("saved_bytes", C.c_size_t)]
+
+
+class SavedLayout(C.Structure):
+    _fields_ = [("gates1", C.c_size_t), ("gates2", C.c_size_t), ("h1", C.c_size_t), ("ctx", C.c_size_t),
+                ("h2", C.c_size_t), ("q", C.c_size_t), ("p", C.c_size_t * 2), ("pm", C.c_size_t * 2),
+                ("pre", C.c_size_t * 2), ("pre0", C.c_size_t * 2), ("total", C.c_size_t)]
+
+
+class GradLayout(C.Structure):
+    _fields_ = [("dg1", C.c_size_t), ("dg2", C.c_size_t), ("dq", C.c_size_t), ("dctx", C.c_size_t),
+                ("dpre", C.c_size_t), ("dv", C.c_size_t), ("dpm", C.c_size_t * 2), ("scratch", C.c_size_t),
+                ("total", C.c_size_t)]
+
+
+class BwdArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("T", C.c_int), ("T_in", C.c_int), ("T_sub", C.c_int),
+                ("memory", _fp), ("embeddings", _fp), ("memory_lengths", _fp), ("bert_lengths", _fp),
+                ("training", C.c_int), ("rng", Rng),
+                ("align", _fp), ("align_bert", _fp), ("d_mel", _fp), ("d_gate", _fp),
+                ("d_align", _fp), ("d_align_bert", _fp),
+                ("saved", _fp), ("saved_bytes", C.c_size_t), ("grads", _fp), ("grads_bytes", C.c_size_t)]
 
 
 class InferArgs(C.Structure):
@@ -101,6 +123,12 @@ def load_library() -> C.CDLL:
     lib.taco2dec_forward_teacher_forced.argtypes = [H, C.POINTER(TFArgs), C.c_void_p]
     lib.taco2dec_infer.restype = C.c_int
     lib.taco2dec_infer.argtypes = [H, C.POINTER(InferArgs), C.c_void_p]
+    lib.taco2dec_saved_layout_query.restype = C.c_int
+    lib.taco2dec_saved_layout_query.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SavedLayout)]
+    lib.taco2dec_grad_layout_query.restype = C.c_int
+    lib.taco2dec_grad_layout_query.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GradLayout)]
+    lib.taco2dec_backward.restype = C.c_int
+    lib.taco2dec_backward.argtypes = [H, C.POINTER(BwdArgs), C.c_void_p]
     lib.taco2dec_check.restype = C.c_int
     lib.taco2dec_check.argtypes = [H, C.c_void_p]
     lib.taco2dec_launch_count.restype = C.c_int64

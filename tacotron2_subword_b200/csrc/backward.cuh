@@ -1,0 +1,305 @@
+// backward.cuh -- back-propagation through time for the teacher-forced decoder (tensor path), included by
+// taco2dec.cu after batched.cuh.
+//
+// The reference gets this pass from autograd over the per-frame Python loop (model.py:392-428 run under
+// train.py:245-256: loss.backward()).  Here the recurrent part is a reverse-time frame loop, again one CUDA graph
+// replayed per frame (frame index counts down in device memory):
+//
+//   bw_pointwise2   dh2[t] (from frame t+1's GEMM + the projection rows) -> decoder-LSTM gate gradients dG2[t]
+//   GEMM            dX2 = [Wd_ih | Wd_hh]^T . dG2^T        tcgen05, bf16 operands, fp32 accumulate  (model.py:362-371)
+//   bw_attention    d ctx[t] -> d alpha' -> stepwise-monotonic recurrence -> d energies -> dq, dv, d processed_memory
+//                                                                                     (attention.py:330-398)
+//   bw_pointwise1   dh1[t] (frame t+1's GEMM + dX2 + Wq^T dq) -> attention-LSTM gate gradients dG1[t]
+//   GEMM            dX1 = [W_ih | W_hh]^T . dG1^T          tcgen05                           (model.py:337-346)
+//   bw_save_dpre    d prenet[t] out of dX1
+//
+// Everything that is a plain sum over (frame, utterance) -- all weight gradients, d memory, the hoisted prenet -- is
+// left as saved per-frame gradient rows (dG1, dG2, dq, d ctx, d prenet) that the host wrapper contracts with the saved
+// activations in a handful of large library GEMMs after the loop.
+//
+// Gate gradients are handed to the tensor cores in bf16 (fp32 range: no loss scaling), weights in bf16 as well.
+#pragma once
+
+#include <cuda_bf16.h>
+
+namespace bw {
+
+using bt::A;
+using bt::E;
+using bt::H;
+using bt::M;
+using bt::P;
+using bt::K1;
+constexpr int G = 4 * H;                  // gate rows = K of the backward GEMMs
+constexpr int SPLITSB1 = 4, SPLITSB2 = 4;
+
+struct Bufs {
+  unsigned char* a1t;   // [S][K1/128][G/64] tiles: rows = [prenet | ctx | h1] input features, K = gate rows
+  unsigned char* a2t;   // [K2/128][G/64]
+  unsigned char* dg1;   // [S][G/64][NPAD x 64] bf16 tiles of dG1[t]
+  unsigned char* dg2;   // [G/64][NPAD x 64]
+  float* dx1;           // [S][SPLITSB1][K1][NPAD]
+  float* dx2;           // [SPLITSB2][K2][NPAD]
+  int NPAD, K2;
+};
+
+struct Grads {
+  bt::Saved sv;
+  const float* p_saved[2];   // [T][B][Ts]
+  const float* align[2];     // [B][T][Ts] forward outputs
+  const float* d_align[2];   // [B][T][Ts] or null
+  const float *d_mel, *d_gate;   // [B][T][M], [B][T]
+  float* dg1;      // [S][T][B][G]
+  float* dg2;      // [T][B][G]
+  float* dq;       // [S][T][B][A]
+  float* dctx;     // [S][T][B][E]
+  float* dpre;     // [S][T][B][P]
+  float* dv;       // [S][B][A]      per-utterance partial sums
+  float* dpm[2];   // [B][Ts][A]     d processed_memory
+  float* dalpha[2];// [B][Ts]        carry: d alignment state
+  float *dc1, *dc2;// [S][B][H], [B][H] carry: d cell state
+};
+
+__device__ __forceinline__ void xb_store(unsigned char* xbase, int NPAD, int b, int k, float v) {
+  const size_t off = (size_t)(k >> 6) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63);
+  *reinterpret_cast<__nv_bfloat16*>(xbase + off) = __float2bfloat16(v);
+}
+
+// transposed weights: dst rows r = feature of the concatenation [src0 cols | src1 cols], K = source row (gate)
+__global__ void pack_concat_tiles_T_kernel(const float* __restrict__ src0, int K0, const float* __restrict__ src1, int K1c,
+                                           int gates, unsigned char* __restrict__ dst) {
+  const int R = K0 + K1c, kb_total = gates / tc::kBlockK;
+  const size_t total = (size_t)R * gates;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % R), k = (int)(i / R);       // r fastest: coalesced source reads
+    const float v = r < K0 ? src0[(size_t)k * K0 + r] : src1[(size_t)k * K1c + (r - K0)];
+    const size_t tile = ((size_t)(r / 128) * kb_total + (k / tc::kBlockK)) * tc::kATileBytes;
+    *reinterpret_cast<__nv_bfloat16*>(dst + tile + tc::tile_offset_bytes(128, r % 128, k % tc::kBlockK)) = __float2bfloat16(v);
+  }
+}
+
+// one LSTM cell backwards (nn.LSTMCell + the dropout on h and c, model.py:340-346 / 371-373).
+//   dh: gradient w.r.t. the post-dropout hidden state, *dc_carry: w.r.t. the post-dropout cell state (updated
+//   in place to the gradient w.r.t. the previous frame's post-dropout cell state).
+__device__ __forceinline__ void lstm_cell_backward(const float* sv, size_t gs, float c_prev, float mh, float mc, float dh,
+                                                   float* dc_carry, float (&dgate)[4]) {
+  const float gi = sv[0], gf = sv[gs], gg = sv[2 * gs], go = sv[3 * gs], cn = sv[4 * gs];
+  const float tcn = tanhf(cn);
+  const float dhp = dh * mh;
+  const float dcn = *dc_carry * mc + dhp * go * (1.0f - tcn * tcn);
+  *dc_carry = dcn * gf;
+  dgate[0] = dcn * gg * gi * (1.0f - gi);
+  dgate[1] = dcn * c_prev * gf * (1.0f - gf);
+  dgate[2] = dcn * gi * (1.0f - gg * gg);
+  dgate[3] = dhp * tcn * go * (1.0f - go);
+}
+
+// d(mel, gate)/d y for one input column k of the projection (model.py:382-388): sum_row dmel[row] W[row][k] + dgate wg[k]
+__device__ __forceinline__ float proj_backward_col(const Params& p, const Grads& g, int b, int t, int k) {
+  const int KD = H + p.S * E;
+  const float* dm = g.d_mel + ((size_t)b * p.T + t) * M;
+  float acc = g.d_gate[(size_t)b * p.T + t] * __ldg(p.gate_w + k);
+#pragma unroll 8
+  for (int r = 0; r < M; ++r) acc = fmaf(__ldg(dm + r), __ldg(p.proj_w + (size_t)r * KD + k), acc);
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) bw_pointwise2(Params p, Bufs bb, Grads g, const int* t_ptr) {
+  const int t = *t_ptr;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * H) return;
+  const int j = i / p.B, b = i - j * p.B;
+  const size_t idx = (size_t)b * H + j;
+  float dh = proj_backward_col(p, g, b, t, j);
+#pragma unroll
+  for (int k = 0; k < SPLITSB2; ++k) dh += bb.dx2[((size_t)k * bb.K2 + p.S * (H + E) + j) * bb.NPAD + b];
+  const size_t gs = (size_t)H * p.B;
+  const float* sv = g.sv.gates2 + ((size_t)t * 5 * H + j) * p.B + b;
+  float mh = 1.f, mc = 1.f, mc_prev = 1.f;
+  if (p.training) {
+    const float sc = 1.0f / (1.0f - p.p_dec);
+    const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * p.B * H : nullptr;
+    const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * p.B * H : nullptr;
+    mh = keep_mult(kh, idx, p.seed, 8, t, (int)idx, p.thresh_dec, sc);
+    mc = keep_mult(kc, idx, p.seed, 9, t, (int)idx, p.thresh_dec, sc);
+    if (t > 0) {
+      const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 5) * p.B * H : nullptr;
+      mc_prev = keep_mult(kcp, idx, p.seed, 9, t - 1, (int)idx, p.thresh_dec, sc);
+    }
+  }
+  const float c_prev = t > 0 ? mc_prev * (sv - 5 * gs)[4 * gs] : 0.f;
+  float dgate[4];
+  lstm_cell_backward(sv, gs, c_prev, mh, mc, dh, g.dc2 + idx, dgate);
+  float* out = g.dg2 + ((size_t)t * p.B + b) * G + j;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    out[q * H] = dgate[q];
+    xb_store(bb.dg2, bb.NPAD, b, q * H + j, dgate[q]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bw_pointwise1(Params p, Bufs bb, Grads g, const int* t_ptr) {
+  const int t = *t_ptr;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.S * p.B * H) return;
+  const int s = i / (p.B * H), r = i - s * p.B * H, j = r / p.B, b = r - j * p.B;
+  const size_t idx = (size_t)b * H + j;
+  float dh = 0.f;
+#pragma unroll
+  for (int k = 0; k < SPLITSB1; ++k) dh += bb.dx1[(((size_t)s * SPLITSB1 + k) * K1 + P + E + j) * bb.NPAD + b];
+#pragma unroll
+  for (int k = 0; k < SPLITSB2; ++k) dh += bb.dx2[((size_t)k * bb.K2 + s * (H + E) + j) * bb.NPAD + b];
+  {  // query layer: dh1 += Wq^T dq  (attention.py:56, 368)
+    const float4* dq4 = reinterpret_cast<const float4*>(g.dq + (((size_t)s * p.T + t) * p.B + b) * A);
+    const float* wq = p.st[s].wq + j;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int a4 = 0; a4 < A / 4; ++a4) {
+      const float4 d = dq4[a4];
+      acc = fmaf(d.x, __ldg(wq + (size_t)(4 * a4) * H), acc);
+      acc = fmaf(d.y, __ldg(wq + (size_t)(4 * a4 + 1) * H), acc);
+      acc = fmaf(d.z, __ldg(wq + (size_t)(4 * a4 + 2) * H), acc);
+      acc = fmaf(d.w, __ldg(wq + (size_t)(4 * a4 + 3) * H), acc);
+    }
+    dh += acc;
+  }
+  const size_t gs = (size_t)H * p.B;
+  const float* sv = g.sv.gates1 + (((size_t)t * p.S + s) * 5 * H + j) * p.B + b;
+  float mh = 1.f, mc = 1.f, mc_prev = 1.f;
+  if (p.training) {
+    const float sc = 1.0f / (1.0f - p.p_att);
+    const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s) * p.B * H : nullptr;
+    const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s + 1) * p.B * H : nullptr;
+    mh = keep_mult(kh, idx, p.seed, 4 + 2 * s, t, (int)idx, p.thresh_att, sc);
+    mc = keep_mult(kc, idx, p.seed, 5 + 2 * s, t, (int)idx, p.thresh_att, sc);
+    if (t > 0) {
+      const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 2 * s + 1) * p.B * H : nullptr;
+      mc_prev = keep_mult(kcp, idx, p.seed, 5 + 2 * s, t - 1, (int)idx, p.thresh_att, sc);
+    }
+  }
+  const float c_prev = t > 0 ? mc_prev * (sv - (size_t)p.S * 5 * gs)[4 * gs] : 0.f;
+  float dgate[4];
+  lstm_cell_backward(sv, gs, c_prev, mh, mc, dh, g.dc1 + (size_t)s * p.B * H + idx, dgate);
+  float* out = g.dg1 + (((size_t)s * p.T + t) * p.B + b) * G + j;
+  unsigned char* tiles = bb.dg1 + (size_t)s * (G / 64) * bb.NPAD * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    out[q * H] = dgate[q];
+    xb_store(tiles, bb.NPAD, b, q * H + j, dgate[q]);
+  }
+}
+
+// stepwise monotonic attention backwards, one CTA per (utterance, stream)
+constexpr int kBwThreads = 512;
+__host__ __device__ inline size_t bw_attention_smem_floats(int Ts) { return (size_t)E + 4 * A + 4 * (size_t)(Ts + 4); }
+
+__global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb, Grads g, const int* t_ptr) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = *t_ptr;
+  const int s = blockIdx.x % p.S, b = blockIdx.x / p.S, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kW = kBwThreads / 32;
+  const StreamParams& sp = p.st[s];
+  const int Ts = sp.Ts;
+  const int len = sp.len ? (int)sp.len[b] : Ts;
+  float* dctx_s = sm;                 // E
+  float* q_s = dctx_s + E;            // A
+  float* v_s = q_s + A;               // A
+  float* dq_s = v_s + A;              // A
+  float* dv_s = dq_s + A;             // A
+  float* p_s = dv_s + A;              // Ts+4
+  float* ap_s = p_s + Ts + 4;         // Ts+4   alignment state entering frame t
+  float* dan_s = ap_s + Ts + 4;       // Ts+4   d alpha'[t]
+  float* de_s = dan_s + Ts + 4;       // Ts+4
+
+  // d ctx[t] = next frame's attention-LSTM input gradient + this frame's decoder-LSTM input and projection gradients
+  for (int d = tid; d < E; d += kBwThreads) {
+    float acc = proj_backward_col(p, g, b, t, H + s * E + d);
+#pragma unroll
+    for (int k = 0; k < SPLITSB1; ++k) acc += bb.dx1[(((size_t)s * SPLITSB1 + k) * K1 + P + d) * bb.NPAD + b];
+#pragma unroll
+    for (int k = 0; k < SPLITSB2; ++k) acc += bb.dx2[((size_t)k * bb.K2 + s * (H + E) + H + d) * bb.NPAD + b];
+    dctx_s[d] = acc;
+    g.dctx[(((size_t)s * p.T + t) * p.B + b) * E + d] = acc;
+  }
+  for (int a = tid; a < A; a += kBwThreads) {
+    q_s[a] = g.sv.q[(((size_t)t * p.S + s) * p.B + b) * A + a];
+    v_s[a] = sp.v[a];
+    dq_s[a] = 0.f;
+    dv_s[a] = 0.f;
+  }
+  for (int j = tid; j < Ts; j += kBwThreads) {
+    p_s[j] = g.p_saved[s][((size_t)t * p.B + b) * Ts + j];
+    ap_s[j] = t > 0 ? g.align[s][((size_t)b * p.T + (t - 1)) * Ts + j] : (j == 0 ? 1.f : 0.f);   // attention.py:324-328
+  }
+  __syncthreads();
+
+  // d alpha'_j = d ctx . memory_j + carry from frame t+1 (+ external alignment gradient)   (attention.py:395)
+  const float* mem_b = sp.mem + (size_t)b * Ts * E;
+  for (int j = warp; j < Ts; j += kW) {
+    const float4* m4 = reinterpret_cast<const float4*>(mem_b + (size_t)j * E);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < E / 128; ++q) {
+      const float4 mv = __ldg(m4 + lane + 32 * q);
+      const float4 dv = reinterpret_cast<const float4*>(dctx_s)[lane + 32 * q];
+      acc = fmaf(mv.x, dv.x, acc); acc = fmaf(mv.y, dv.y, acc); acc = fmaf(mv.z, dv.z, acc); acc = fmaf(mv.w, dv.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float d = acc + g.dalpha[s][(size_t)b * Ts + j];
+      if (g.d_align[s]) d += g.d_align[s][((size_t)b * p.T + t) * Ts + j];
+      dan_s[j] = d;
+    }
+  }
+  __syncthreads();
+  // alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1})   (attention.py:330-338), p = sigmoid(e)
+  for (int j = tid; j < Ts; j += kBwThreads) {
+    const float dn = dan_s[j], dn1 = j + 1 < Ts ? dan_s[j + 1] : 0.f, pj = p_s[j];
+    g.dalpha[s][(size_t)b * Ts + j] = dn * pj + dn1 * (1.0f - pj);
+    de_s[j] = ap_s[j] * (dn - dn1) * pj * (1.0f - pj);
+  }
+  __syncthreads();
+  // e_j = v . tanh(q + pm_j)   (attention.py:340-345); positions >= len have p = 0, hence de = 0
+  {
+    const float* pm_b = sp.pm + (size_t)b * Ts * A;
+    float* dpm_b = g.dpm[s] + (size_t)b * Ts * A;
+    float dq_acc[4] = {0.f, 0.f, 0.f, 0.f}, dv_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = warp; j < len; j += kW) {
+      const float de = de_s[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int a = lane + 32 * q;
+        const float u = tanhf(q_s[a] + __ldg(pm_b + (size_t)j * A + a));
+        const float dz = de * v_s[a] * (1.0f - u * u);
+        dq_acc[q] += dz;
+        dv_acc[q] = fmaf(de, u, dv_acc[q]);
+        dpm_b[(size_t)j * A + a] += dz;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      atomicAdd(&dq_s[lane + 32 * q], dq_acc[q]);
+      atomicAdd(&dv_s[lane + 32 * q], dv_acc[q]);
+    }
+  }
+  __syncthreads();
+  for (int a = tid; a < A; a += kBwThreads) {
+    g.dq[(((size_t)s * p.T + t) * p.B + b) * A + a] = dq_s[a];
+    g.dv[((size_t)s * p.B + b) * A + a] += dv_s[a];
+  }
+}
+
+__global__ void bw_save_dpre(Params p, Bufs bb, Grads g, const int* t_ptr) {
+  const int t = *t_ptr;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.S * p.B * P) return;
+  const int s = i / (p.B * P), r = i - s * p.B * P, k = r / p.B, b = r - k * p.B;
+  float acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < SPLITSB1; ++q) acc += bb.dx1[(((size_t)s * SPLITSB1 + q) * K1 + k) * bb.NPAD + b];
+  g.dpre[(((size_t)s * p.T + t) * p.B + b) * P + k] = acc;
+}
+
+__global__ void bw_retreat(int* t_ptr) { *t_ptr -= 1; }
+
+}  // namespace bw

@@ -24,6 +24,17 @@ constexpr int H = 1024, E = 512, P = 256, A = 128, M = 80;
 constexpr int K1 = P + E + H;            // 1792: [prenet | ctx | h1]
 constexpr int SPLITS1 = 2, SPLITS2 = 4, SPLITSQ = 4;
 
+// Activations a training-mode forward keeps for the backward pass (caller-provided "saved" buffer; all null
+// when nothing is saved).  State arrays have T+1 slots: slot 0 = the zero initial state, slot t+1 = frame t.
+struct Saved {
+  float* gates1;   // [T][S][5][H][B]  i, f, g, o (activated) and the new cell state before dropout
+  float* gates2;   // [T][5][H][B]
+  float* h1;       // [T+1][S][B][H]   post-dropout attention-LSTM hidden
+  float* ctx;      // [T+1][S][B][E]
+  float* h2;       // [T+1][B][H]      post-dropout decoder-LSTM hidden
+  float* q;        // [T][S][B][A]
+};
+
 struct Bufs {
   // tiled fp16 operands
   unsigned char* a1;    // [S][32 m-tiles][28 kb] attention LSTM weights [W_ih | W_hh]
@@ -39,6 +50,7 @@ struct Bufs {
   float *c1, *c2, *h2f; // [S][B][H], [B][H], [B][H]
   float *w0t[2], *w1t[2]; // transposed prenet weights [M][P], [P][P] (coalesced column reads)
   int NPAD, K2;
+  Saved sv;
 };
 
 __device__ __forceinline__ void x_store(unsigned char* xbase, int NPAD, int b, int k, float v) {
@@ -171,8 +183,14 @@ __global__ void bt_pointwise1(Params p, Bufs bf, const int* t_ptr) {
     pre[g] = a;
   }
   const size_t idx = (size_t)b * H + j;
-  float cn = sigmoidf_(pre[1]) * bf.c1[(size_t)s * p.B * H + idx] + sigmoidf_(pre[0]) * tanhf(pre[2]);
-  float hn = sigmoidf_(pre[3]) * tanhf(cn);
+  const float gi = sigmoidf_(pre[0]), gf = sigmoidf_(pre[1]), gg = tanhf(pre[2]), go = sigmoidf_(pre[3]);
+  float cn = gf * bf.c1[(size_t)s * p.B * H + idx] + gi * gg;
+  float hn = go * tanhf(cn);
+  if (bf.sv.gates1) {
+    float* sv = bf.sv.gates1 + (((size_t)t * p.S + s) * 5 * H + j) * p.B + b;
+    const size_t gs = (size_t)H * p.B;
+    sv[0] = gi; sv[gs] = gf; sv[2 * gs] = gg; sv[3 * gs] = go; sv[4 * gs] = cn;
+  }
   if (p.training) {
     const float sc = 1.0f / (1.0f - p.p_att);
     const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s) * p.B * H : nullptr;
@@ -181,6 +199,7 @@ __global__ void bt_pointwise1(Params p, Bufs bf, const int* t_ptr) {
     cn *= keep_mult(kc, idx, p.seed, 5 + 2 * s, t, (int)idx, p.thresh_att, sc);
   }
   bf.c1[(size_t)s * p.B * H + idx] = cn;
+  if (bf.sv.h1) bf.sv.h1[(((size_t)(t + 1) * p.S + s) * p.B) * H + idx] = hn;
   x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, P + E + j, hn);     // next frame's LSTM-1 input
   x_store(bf.x2, bf.NPAD, b, s * (H + E) + j, hn);                                        // this frame's LSTM-2 / query input
 }
@@ -197,11 +216,13 @@ __global__ void __launch_bounds__(kThreads, 1) bt_attention(Params p, Bufs bf, c
 #pragma unroll
     for (int k = 0; k < SPLITSQ; ++k) q += bf.gq[(((size_t)s * SPLITSQ + k) * 128 + tid) * bf.NPAD + b];
     p.q[((size_t)s * p.B + b) * A + tid] = q;
+    if (bf.sv.q) bf.sv.q[(((size_t)t * p.S + s) * p.B + b) * A + tid] = q;
   }
   __syncthreads();
   attention_task<true>(p, s, b, t, att_smem);
   for (int d = tid; d < E; d += kThreads) {
     const float c = __ldcg(p.ctx + ((size_t)s * p.B + b) * E + d);
+    if (bf.sv.ctx) bf.sv.ctx[(((size_t)(t + 1) * p.S + s) * p.B + b) * E + d] = c;
     x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, P + d, c);          // next frame's LSTM-1 input
     x_store(bf.x2, bf.NPAD, b, s * (H + E) + H + d, c);                                     // this frame's LSTM-2 input
   }
@@ -222,8 +243,14 @@ __global__ void bt_pointwise2(Params p, Bufs bf, const int* t_ptr) {
     pre[g] = a;
   }
   const size_t idx = (size_t)b * H + j;
-  float cn = sigmoidf_(pre[1]) * bf.c2[idx] + sigmoidf_(pre[0]) * tanhf(pre[2]);
-  float hn = sigmoidf_(pre[3]) * tanhf(cn);
+  const float gi = sigmoidf_(pre[0]), gf = sigmoidf_(pre[1]), gg = tanhf(pre[2]), go = sigmoidf_(pre[3]);
+  float cn = gf * bf.c2[idx] + gi * gg;
+  float hn = go * tanhf(cn);
+  if (bf.sv.gates2) {
+    float* sv = bf.sv.gates2 + ((size_t)t * 5 * H + j) * p.B + b;
+    const size_t gs = (size_t)H * p.B;
+    sv[0] = gi; sv[gs] = gf; sv[2 * gs] = gg; sv[3 * gs] = go; sv[4 * gs] = cn;
+  }
   if (p.training) {
     const float sc = 1.0f / (1.0f - p.p_dec);
     const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * p.B * H : nullptr;
@@ -233,6 +260,7 @@ __global__ void bt_pointwise2(Params p, Bufs bf, const int* t_ptr) {
   }
   bf.c2[idx] = cn;
   bf.h2f[idx] = hn;
+  if (bf.sv.h2) bf.sv.h2[(size_t)(t + 1) * p.B * H + idx] = hn;
   x_store(bf.x2, bf.NPAD, b, p.S * (H + E) + j, hn);     // next frame's recurrent input
 }
 

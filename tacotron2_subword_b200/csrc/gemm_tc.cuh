@@ -75,6 +75,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// operand format fields of the kind::f16 descriptor: a_format bits [7,10), b_format bits [10,13); 0 = f16, 1 = bf16
+constexpr uint32_t kFmtF16 = 0u;
+constexpr uint32_t kFmtBF16 = (1u << 7) | (1u << 10);
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -98,6 +101,7 @@ struct GemmParams {
   int x_kb_base, x_kb_group_step; // first k-block of X inside its buffer = x_kb_base + group * x_kb_group_step
   const int* done;                // optional early-exit: skip when *done >= done_target (free-running decode)
   int done_target;
+  uint32_t fmt;                   // operand formats OR-ed into the instruction descriptor (kFmtF16 / kFmtBF16)
 };
 
 template <int NPAD>
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
   } else if (warp == 5) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kBlockM, NPAD);
+      const uint32_t idesc = make_idesc_f16(kBlockM, NPAD) | p.fmt;
       constexpr uint32_t lbo_a = (kBlockM / 8) * 128, lbo_x = (NPAD / 8) * 128, sbo = 128;
       for (int i = 0; i < kb_per_split; ++i) {
         const int s = i % kStages;

@@ -20,6 +20,7 @@
 //
 // No CPU fallback, no multi-backend dispatch: the host API refuses non-sm_100 devices.
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -57,6 +58,7 @@ struct StreamParams {
   float* a_prev;            // [B, Ts]  SMA: alignment state; LSA: previous attention weights
   float* a_cum;             // [B, Ts]  LSA cumulative weights
   float* align;             // [B, Tcap, Ts] output
+  float* p_save;            // [T, B, Ts] SMA selection probabilities kept for the backward pass, or null
   int Ts;
 };
 
@@ -415,6 +417,7 @@ __device__ void attention_task(const Params& p, int s, int b, int t, float* sm) 
         e = e + nz * 2.0f;
       }
       e_s[j] = sigmoidf_(e);
+      if (sp.p_save) sp.p_save[((size_t)t * p.B + b) * Ts + j] = e_s[j];
     }
     __syncthreads();
     // alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1})  (attention.py:330-338)
@@ -772,6 +775,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
 }
 
 #include "batched.cuh"
+#include "backward.cuh"
 
 // ------------------------------------------------------------------------------------------
 // One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
@@ -802,7 +806,8 @@ __global__ void __launch_bounds__(256) processed_memory_kernel(const float* __re
 // decoder_inputs[b, :, r-1] (the [B, M, T] layout the reference transposes at model.py:283-287).
 __global__ void __launch_bounds__(256) prenet_tf_kernel(const float* __restrict__ dec_in, const float* __restrict__ w0,
                                                         const float* __restrict__ w1, const uint8_t* keep0,
-                                                        const uint8_t* keep1, float* __restrict__ out, int B, int T,
+                                                        const uint8_t* keep1, float* __restrict__ out,
+                                                        float* __restrict__ out0, int B, int T,
                                                         int M, int P, unsigned long long seed, int stream_id,
                                                         unsigned thresh) {
   extern __shared__ __align__(16) float sm[];  // per warp: x[M4] + h0[P]
@@ -833,7 +838,8 @@ __global__ void __launch_bounds__(256) prenet_tf_kernel(const float* __restrict_
           const int col = i + lane;
           const float mult = keep_mult(keep, (size_t)n * P + col, seed, stream_id * 2 + layer, r, b * P + col, thresh, 2.0f);
           v = fmaxf(v, 0.0f) * mult;
-          if (layer == 0) h0[col] = v; else out[(size_t)n * P + col] = v;
+          if (layer == 0) { h0[col] = v; if (out0) out0[(size_t)n * P + col] = v; }
+          else out[(size_t)n * P + col] = v;
         }
       }
       __syncwarp();
@@ -897,6 +903,10 @@ struct taco2dec_handle {
   int last_path;         // path actually taken by the most recent call (1 generic, 2 latency, 3 tensor)
   bt::Bufs bt_bufs;      // batched tensor path: library-owned tiled operands / partials / state
   bool bt_alloc, bt_tiles_valid;
+  bt::Saved cur_sv;      // where the current teacher-forced call keeps activations for backward (null = nowhere)
+  bw::Bufs bw_bufs;      // backward pass: transposed bf16 weight tiles, gate-gradient tiles, GEMM partials
+  bool bw_alloc, bw_tiles_valid;
+  int* bw_ctl;           // device word: frame counter of the backward graph
   cudaStream_t cap_stream;   // private stream used only to capture the per-frame CUDA graph
   bool profiling;        // record CUDA events around the persistent launch
   cudaEvent_t ev0, ev1;
@@ -1233,8 +1243,14 @@ template <int NPAD>
 int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStream_t st) {
   bt::Bufs bf = h->bt_bufs;
   bf.NPAD = NPAD;
+  bf.sv = h->cur_sv;
   const int S = p.S, B = p.B;
   const int n_steps = p.free_running ? p.max_steps : p.T;
+  if (bf.sv.h1) {   // slot 0 of the saved state arrays = the zero initial state (model.py:237-256)
+    CUDA_TRY(cudaMemsetAsync(bf.sv.h1, 0, (size_t)S * B * bt::H * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(bf.sv.ctx, 0, (size_t)S * B * bt::E * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(bf.sv.h2, 0, (size_t)B * bt::H * sizeof(float), st));
+  }
   CUDA_TRY(cudaMemsetAsync(bf.x1, 0, (size_t)S * (bt::K1 / 64) * NPAD * 128, st));
   CUDA_TRY(cudaMemsetAsync(bf.x2, 0, (size_t)(bf.K2 / 64) * NPAD * 128, st));
   bt::bt_init_kernel<<<h->num_sms, 256, 0, st>>>(p, bf);
@@ -1297,6 +1313,150 @@ int run_batched(taco2dec_handle* h, const Params& p, int T_in, int T_sub, cudaSt
   return bt_run_frames<128>(h, p, att, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward pass (backward.cuh): buffer layouts, transposed weight tiles, reverse-time frame graph
+// ------------------------------------------------------------------------------------------
+taco2dec_saved_layout plan_saved(const taco2dec_config& c, int B, int T_in, int T_sub, int T) {
+  taco2dec_saved_layout L;
+  memset(&L, 0, sizeof(L));
+  size_t off = 0;
+  auto take = [&](size_t n_floats) { size_t o = off; off = align_up(off + n_floats * sizeof(float), 256); return o; };
+  const int S = c.n_streams, H = c.attn_rnn_dim, D = c.dec_rnn_dim;
+  const int Ts[2] = {T_in, T_sub};
+  L.gates1 = take((size_t)T * S * 5 * H * B);
+  L.gates2 = take((size_t)T * 5 * D * B);
+  L.h1 = take((size_t)(T + 1) * S * B * H);
+  L.ctx = take((size_t)(T + 1) * S * B * c.enc_dim);
+  L.h2 = take((size_t)(T + 1) * B * D);
+  L.q = take((size_t)T * S * B * c.attn_dim);
+  for (int s = 0; s < 2; ++s) {
+    const bool on = s < S;
+    L.p[s] = take(on ? (size_t)T * B * Ts[s] : 0);
+    L.pm[s] = take(on ? (size_t)B * Ts[s] * c.attn_dim : 0);
+    L.pre[s] = take(on ? (size_t)(T + 1) * B * c.prenet_dim : 0);
+    L.pre0[s] = take(on ? (size_t)(T + 1) * B * c.prenet_dim : 0);
+  }
+  L.total = off;
+  return L;
+}
+
+struct GradScratch { size_t dalpha[2], dc1, dc2, zero_begin, zero_end; };
+
+taco2dec_grad_layout plan_grads(const taco2dec_config& c, int B, int T_in, int T_sub, int T, GradScratch* gs) {
+  taco2dec_grad_layout L;
+  memset(&L, 0, sizeof(L));
+  size_t off = 0;
+  auto take = [&](size_t n_floats) { size_t o = off; off = align_up(off + n_floats * sizeof(float), 256); return o; };
+  const int S = c.n_streams, H = c.attn_rnn_dim, D = c.dec_rnn_dim;
+  const int Ts[2] = {T_in, T_sub};
+  L.dg1 = take((size_t)S * T * B * 4 * H);
+  L.dg2 = take((size_t)T * B * 4 * D);
+  L.dq = take((size_t)S * T * B * c.attn_dim);
+  L.dctx = take((size_t)S * T * B * c.enc_dim);
+  L.dpre = take((size_t)S * T * B * c.prenet_dim);
+  // accumulators and carries: zeroed by taco2dec_backward before the frame loop
+  const size_t zero_begin = off;
+  L.dv = take((size_t)S * B * c.attn_dim);
+  for (int s = 0; s < 2; ++s) L.dpm[s] = take(s < S ? (size_t)B * Ts[s] * c.attn_dim : 0);
+  L.scratch = off;
+  GradScratch g;
+  for (int s = 0; s < 2; ++s) g.dalpha[s] = take(s < S ? (size_t)B * Ts[s] : 0);
+  g.dc1 = take((size_t)S * B * H);
+  g.dc2 = take((size_t)B * D);
+  g.zero_begin = zero_begin;
+  g.zero_end = off;
+  L.total = off;
+  if (gs) *gs = g;
+  return L;
+}
+
+bool bw_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
+  return h->cfg.attention == TACO2DEC_ATTN_SMA && bt_shape_ok(h, B, T_in, T_sub);
+}
+
+int bw_prepare(taco2dec_handle* h, cudaStream_t st) {
+  const int S = h->cfg.n_streams;
+  bw::Bufs& b = h->bw_bufs;
+  const int K2 = S * (bt::H + bt::E) + bt::H;
+  if (!h->bw_alloc) {
+    const size_t NP = 128;
+    CUDA_TRY(cudaMalloc(&b.a1t, (size_t)S * (bt::K1 / 128) * (bw::G / 64) * tc::kATileBytes));
+    CUDA_TRY(cudaMalloc(&b.a2t, (size_t)(K2 / 128) * (bw::G / 64) * tc::kATileBytes));
+    CUDA_TRY(cudaMalloc(&b.dg1, (size_t)S * (bw::G / 64) * NP * 128));
+    CUDA_TRY(cudaMalloc(&b.dg2, (size_t)(bw::G / 64) * NP * 128));
+    CUDA_TRY(cudaMalloc(&b.dx1, (size_t)S * bw::SPLITSB1 * bt::K1 * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.dx2, (size_t)bw::SPLITSB2 * K2 * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->bw_ctl, 64));
+    h->bw_alloc = true;
+  }
+  b.K2 = K2;
+  if (!h->bw_tiles_valid) {
+    for (int s = 0; s < S; ++s)
+      bw::pack_concat_tiles_T_kernel<<<2048, 256, 0, st>>>(h->w.stream[s].arnn_w_ih, bt::P + bt::E, h->w.stream[s].arnn_w_hh, bt::H,
+                                                           bw::G, b.a1t + (size_t)s * (bt::K1 / 128) * (bw::G / 64) * tc::kATileBytes);
+    bw::pack_concat_tiles_T_kernel<<<4096, 256, 0, st>>>(h->w.drnn_w_ih, S * (bt::H + bt::E), h->w.drnn_w_hh, bt::H, bw::G, b.a2t);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += S + 1;
+    h->bw_tiles_valid = true;
+  }
+  return 0;
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+template <int NPAD>
+int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaStream_t st) {
+  bw::Bufs bb = h->bw_bufs;
+  bb.NPAD = NPAD;
+  const int S = p.S, B = p.B;
+  // frame T-1 has no successor: every carry starts at zero
+  CUDA_TRY(cudaMemsetAsync(bb.dg1, 0, (size_t)S * (bw::G / 64) * NPAD * 128, st));
+  CUDA_TRY(cudaMemsetAsync(bb.dg2, 0, (size_t)(bw::G / 64) * NPAD * 128, st));
+  CUDA_TRY(cudaMemsetAsync(bb.dx1, 0, (size_t)S * bw::SPLITSB1 * bt::K1 * NPAD * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(bb.dx2, 0, (size_t)bw::SPLITSB2 * bb.K2 * NPAD * sizeof(float), st));
+  int* t_ptr = h->bw_ctl;
+  set_int_kernel<<<1, 1, 0, st>>>(t_ptr, p.T - 1);
+  int max_ts = 0;
+  for (int s = 0; s < S; ++s) max_ts = std::max(max_ts, p.st[s].Ts);
+  const size_t att_smem = bw::bw_attention_smem_floats(max_ts) * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(bw::bw_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  tc::GemmParams gb2{bb.a2t, bb.dg2, bb.dx2, bb.K2, bw::G, bw::SPLITSB2, 1, 0, 0, 0, nullptr, 0, tc::kFmtBF16};
+  tc::GemmParams gb1{bb.a1t, bb.dg1, bb.dx1, bt::K1, bw::G, bw::SPLITSB1, S, (long long)(bw::G / 64) * NPAD * 128, 0, 0,
+                     nullptr, 0, tc::kFmtBF16};
+  CUDA_TRY(tc::prepare_gemm<NPAD>());
+  if (!h->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t cs = h->cap_stream;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+  bw::bw_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, cs>>>(p, bb, g, t_ptr);
+  cudaError_t ce = tc::launch_gemm<NPAD>(gb2, cs);
+  bw::bw_attention<<<S * B, bw::kBwThreads, att_smem, cs>>>(p, bb, g, t_ptr);
+  bw::bw_pointwise1<<<(S * B * bt::H + 255) / 256, 256, 0, cs>>>(p, bb, g, t_ptr);
+  if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(gb1, cs);
+  bw::bw_save_dpre<<<(S * B * bt::P + 255) / 256, 256, 0, cs>>>(p, bb, g, t_ptr);
+  bw::bw_retreat<<<1, 1, 0, cs>>>(t_ptr);
+  const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
+  if (ce != cudaSuccess || ee != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    return fail(TACO2DEC_E_CUDA, std::string("graph capture of the backward frame sequence failed: ") +
+                                     cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+  }
+  CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+  for (int t = 0; t < p.T; ++t) {
+    const cudaError_t le = cudaGraphLaunch(exec, st);
+    if (le != cudaSuccess) {
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+      return fail(TACO2DEC_E_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
+    }
+  }
+  h->launches += 7LL * p.T + 1;
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, const WorkspaceLayout& L, cudaStream_t st) {
   const taco2dec_config& c = h->cfg;
   // control words: barrier counter, watchdog flag, done counter
@@ -1311,6 +1471,11 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  if (h->cur_sv.gates1) {   // activations are kept for backward: only the tensor path produces them
+    if (!bw_shape_ok(h, p.B, T_in, T_sub) || (h->path_mode != TACO2DEC_PATH_AUTO && h->path_mode != TACO2DEC_PATH_TENSOR))
+      return fail(TACO2DEC_E_ARG, "saving activations for backward needs the tensor path: 16 <= B <= 128, SMA, default decoder dims");
+    return run_batched(h, p, T_in, T_sub, st);
+  }
   const bool want_lat = (h->path_mode == TACO2DEC_PATH_AUTO || h->path_mode == TACO2DEC_PATH_LATENCY) &&
                         lat_shape_ok(h, p.B, T_in, T_sub);
   if (h->path_mode == TACO2DEC_PATH_LATENCY && !want_lat)
@@ -1399,6 +1564,8 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   h->packed = nullptr; h->packed_bytes = 0; h->packed_wbytes = 0; h->packed_off = nullptr;
   h->ll_buf = nullptr; h->ll_bytes = 0; h->last_path = 0;
   memset(&h->bt_bufs, 0, sizeof(h->bt_bufs)); h->bt_alloc = false; h->bt_tiles_valid = false; h->cap_stream = nullptr;
+  memset(&h->cur_sv, 0, sizeof(h->cur_sv));
+  memset(&h->bw_bufs, 0, sizeof(h->bw_bufs)); h->bw_alloc = false; h->bw_tiles_valid = false; h->bw_ctl = nullptr;
   h->profiling = false;
   h->ev_valid = false;
   CUDA_TRY(cudaSetDevice(device));
@@ -1419,6 +1586,11 @@ int taco2dec_destroy(taco2dec_handle* h) {
     if (h->bt_alloc) {
       bt::Bufs& b = h->bt_bufs;
       void* ptrs[] = {b.a1, b.a2, b.aq, b.x1, b.x2, b.g1, b.g2, b.gq, b.c1, b.c2, b.h2f, b.w0t[0], b.w0t[1], b.w1t[0], b.w1t[1]};
+      for (void* q : ptrs) if (q) cudaFree(q);
+    }
+    if (h->bw_alloc) {
+      bw::Bufs& b = h->bw_bufs;
+      void* ptrs[] = {b.a1t, b.a2t, b.dg1, b.dg2, b.dx1, b.dx2, h->bw_ctl};
       for (void* q : ptrs) if (q) cudaFree(q);
     }
   }
@@ -1491,6 +1663,7 @@ int taco2dec_set_weights(taco2dec_handle* h, const taco2dec_weights* w, void* /*
   h->have_weights = true;
   h->packed_wbytes = 0;  // latency-path weight streams are re-packed on next use
   h->bt_tiles_valid = false;
+  h->bw_tiles_valid = false;
   return 0;
 }
 
@@ -1522,6 +1695,23 @@ int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* 
   p.mel = a->mel; p.gate = a->gate;
   p.st[0].align = a->align;
   if (c.n_streams == 2) p.st[1].align = a->align_bert;
+  memset(&h->cur_sv, 0, sizeof(h->cur_sv));
+  float* pre0_save[2] = {nullptr, nullptr};
+  if (a->saved) {
+    const taco2dec_saved_layout SL = plan_saved(c, a->B, a->T_in, std::max(a->T_sub, 1), a->T);
+    if (a->saved_bytes < SL.total) return fail(TACO2DEC_E_STATE, "saved-activation buffer too small");
+    if (reinterpret_cast<uintptr_t>(a->saved) & 255u) return fail(TACO2DEC_E_ARG, "saved buffer must be 256-byte aligned");
+    char* sb = (char*)a->saved;
+    h->cur_sv.gates1 = (float*)(sb + SL.gates1); h->cur_sv.gates2 = (float*)(sb + SL.gates2);
+    h->cur_sv.h1 = (float*)(sb + SL.h1); h->cur_sv.ctx = (float*)(sb + SL.ctx); h->cur_sv.h2 = (float*)(sb + SL.h2);
+    h->cur_sv.q = (float*)(sb + SL.q);
+    for (int s = 0; s < c.n_streams; ++s) {
+      p.st[s].p_save = (float*)(sb + SL.p[s]);
+      p.st[s].pm = (float*)(sb + SL.pm[s]);
+      p.st[s].pre = (float*)(sb + SL.pre[s]);
+      pre0_save[s] = (float*)(sb + SL.pre0[s]);
+    }
+  }
   // hoisted prenet over the go-frame + all T targets (model.py:407-413)
   for (int s = 0; s < c.n_streams; ++s) {
     const int n_rows = (a->T + 1) * a->B;
@@ -1529,12 +1719,86 @@ int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* 
     const int blocks = std::min((n_rows + wpb - 1) / wpb, h->num_sms * 8);
     const size_t sm = (size_t)wpb * (((c.n_mel + 3) & ~3) + c.prenet_dim) * sizeof(float);
     prenet_tf_kernel<<<blocks, wpb * 32, sm, st>>>(a->decoder_inputs, h->w.stream[s].prenet_w0, h->w.stream[s].prenet_w1,
-                                                   a->rng.prenet_keep[s][0], a->rng.prenet_keep[s][1], p.st[s].pre, a->B,
-                                                   a->T, c.n_mel, c.prenet_dim, a->rng.seed, s, p.thresh_pre);
+                                                   a->rng.prenet_keep[s][0], a->rng.prenet_keep[s][1], p.st[s].pre,
+                                                   pre0_save[s], a->B, a->T, c.n_mel, c.prenet_dim, a->rng.seed, s,
+                                                   p.thresh_pre);
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
-  return run_common(h, p, a->T_in, std::max(a->T_sub, 1), ws, L, st);
+  const int rc = run_common(h, p, a->T_in, std::max(a->T_sub, 1), ws, L, st);
+  memset(&h->cur_sv, 0, sizeof(h->cur_sv));
+  return rc;
+}
+
+int taco2dec_saved_layout_query(const taco2dec_handle* h, int B, int T_in, int T_sub, int T, taco2dec_saved_layout* out) {
+  if (!h || !out || B < 1 || T_in < 1 || T < 1) return fail(TACO2DEC_E_ARG, "bad argument");
+  *out = plan_saved(h->cfg, B, T_in, std::max(T_sub, 1), T);
+  return 0;
+}
+
+int taco2dec_grad_layout_query(const taco2dec_handle* h, int B, int T_in, int T_sub, int T, taco2dec_grad_layout* out) {
+  if (!h || !out || B < 1 || T_in < 1 || T < 1) return fail(TACO2DEC_E_ARG, "bad argument");
+  *out = plan_grads(h->cfg, B, T_in, std::max(T_sub, 1), T, nullptr);
+  return 0;
+}
+
+int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda_stream) {
+  if (!h || !a) return fail(TACO2DEC_E_ARG, "null argument");
+  if (!h->have_weights) return fail(TACO2DEC_E_STATE, "weights not set");
+  const taco2dec_config& c = h->cfg;
+  if (a->B < 1 || a->T < 1 || a->T_in < 1 || (c.n_streams == 2 && a->T_sub < 1))
+    return fail(TACO2DEC_E_ARG, "B, T, T_in, T_sub must be >= 1");
+  if (!a->memory || !a->align || !a->d_mel || !a->d_gate || !a->saved || !a->grads)
+    return fail(TACO2DEC_E_ARG, "null tensor pointer");
+  if (c.n_streams == 2 && (!a->embeddings || !a->align_bert)) return fail(TACO2DEC_E_ARG, "sub-word stream tensors missing");
+  const int T_sub = std::max(a->T_sub, 1);
+  if (!bw_shape_ok(h, a->B, a->T_in, T_sub))
+    return fail(TACO2DEC_E_ARG, "backward needs the tensor path: 16 <= B <= 128, SMA, default decoder dims");
+  if ((reinterpret_cast<uintptr_t>(a->saved) & 255u) || (reinterpret_cast<uintptr_t>(a->grads) & 255u))
+    return fail(TACO2DEC_E_ARG, "saved / grads buffers must be 256-byte aligned");
+  const taco2dec_saved_layout SL = plan_saved(c, a->B, a->T_in, T_sub, a->T);
+  GradScratch gs;
+  const taco2dec_grad_layout GL = plan_grads(c, a->B, a->T_in, T_sub, a->T, &gs);
+  if (a->saved_bytes < SL.total) return fail(TACO2DEC_E_STATE, "saved-activation buffer too small");
+  if (a->grads_bytes < GL.total) return fail(TACO2DEC_E_STATE, "gradient buffer too small");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  Params p;
+  WorkspaceLayout L0;
+  memset(&L0, 0, sizeof(L0));
+  fill_common(h, p, a->B, a->T_in, a->T_sub, a->memory, a->embeddings, a->memory_lengths, a->bert_lengths, a->rng, nullptr, L0);
+  p.h1 = p.c1 = p.h2 = p.c2 = p.ctx = p.q = nullptr;
+  p.sync_ctr = nullptr; p.abort_flag = nullptr; p.done_count = nullptr; p.phase_clocks = nullptr;
+  p.T = a->T; p.Tcap = a->T; p.free_running = 0; p.training = a->training ? 1 : 0; p.max_steps = a->T;
+  char* sb = (char*)const_cast<void*>(a->saved);
+  char* gb = (char*)a->grads;
+  bw::Grads g;
+  memset(&g, 0, sizeof(g));
+  g.sv.gates1 = (float*)(sb + SL.gates1); g.sv.gates2 = (float*)(sb + SL.gates2);
+  g.sv.h1 = (float*)(sb + SL.h1); g.sv.ctx = (float*)(sb + SL.ctx); g.sv.h2 = (float*)(sb + SL.h2);
+  g.sv.q = (float*)(sb + SL.q);
+  const float* aligns[2] = {a->align, a->align_bert};
+  const float* d_aligns[2] = {a->d_align, a->d_align_bert};
+  for (int s = 0; s < c.n_streams; ++s) {
+    p.st[s].pm = (float*)(sb + SL.pm[s]);
+    p.st[s].pre = nullptr; p.st[s].pre0 = nullptr; p.st[s].a_prev = nullptr; p.st[s].a_cum = nullptr;
+    g.p_saved[s] = (const float*)(sb + SL.p[s]);
+    g.align[s] = aligns[s];
+    g.d_align[s] = d_aligns[s];
+    g.dpm[s] = (float*)(gb + GL.dpm[s]);
+    g.dalpha[s] = (float*)(gb + gs.dalpha[s]);
+  }
+  g.d_mel = a->d_mel; g.d_gate = a->d_gate;
+  g.dg1 = (float*)(gb + GL.dg1); g.dg2 = (float*)(gb + GL.dg2); g.dq = (float*)(gb + GL.dq);
+  g.dctx = (float*)(gb + GL.dctx); g.dpre = (float*)(gb + GL.dpre); g.dv = (float*)(gb + GL.dv);
+  g.dc1 = (float*)(gb + gs.dc1); g.dc2 = (float*)(gb + gs.dc2);
+  CUDA_TRY(cudaMemsetAsync(gb + gs.zero_begin, 0, gs.zero_end - gs.zero_begin, st));
+  h->last_abort_flag = nullptr;
+  if (int rc = bw_prepare(h, st)) return rc;
+  if (a->B <= 16) return bw_run_frames<16>(h, p, g, st);
+  if (a->B <= 32) return bw_run_frames<32>(h, p, g, st);
+  if (a->B <= 64) return bw_run_frames<64>(h, p, g, st);
+  return bw_run_frames<128>(h, p, g, st);
 }
 
 int taco2dec_infer(taco2dec_handle* h, const taco2dec_infer_args* a, void* cuda_stream) {

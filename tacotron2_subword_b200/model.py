@@ -118,7 +118,8 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class _NoBackward(torch.autograd.Function):
     """Marks decoder outputs as differentiable so training code fails LOUDLY at backward()
-    instead of silently skipping the decoder: the BPTT kernel is not part of this round."""
+    instead of silently skipping the decoder when the shape has no backward kernel (the BPTT
+    kernels cover the tensor path: 16 <= B <= 128, SMA, default dims)."""
 
     @staticmethod
     def forward(ctx, anchor, *outs):
@@ -127,8 +128,124 @@ class _NoBackward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         raise NotImplementedError(
-            "tacotron2_subword_b200: the decoder backward (BPTT) kernel is not implemented yet; "
-            "teacher-forced forward and free-running inference are.")
+            "tacotron2_subword_b200: decoder backward is implemented for the tensor path only "
+            "(16 <= batch <= 128, StepwiseMonotonicAttention, default decoder dims)")
+
+
+def _fview(buf: torch.Tensor, off: int, *shape) -> torch.Tensor:
+    n = 1
+    for d in shape:
+        n *= d
+    return buf[off: off + 4 * n].view(torch.float32).view(*shape)
+
+
+class _DecoderTF(torch.autograd.Function):
+    """Teacher-forced decoder pass with a hand-written backward (the reference relies on autograd over
+    its per-frame Python loop, model.py:392-428 + train.py:245-256).  The reverse-time recurrence runs in
+    ``taco2dec_backward``; the sums over (frame, utterance) that remain -- weight gradients, d memory, the
+    hoisted prenet -- are plain GEMMs over the rows it leaves behind (see ``taco2dec_grad_layout``)."""
+
+    @staticmethod
+    def forward(ctx, dec, memory, embeddings, dec_in, mlen, blen, *params):
+        ctx.set_materialize_grads(False)
+        outs, state = dec._run_tf(memory, embeddings, dec_in, mlen, blen, save=True)
+        ctx.dec, ctx.state = dec, state
+        ctx.n_params = len(params)
+        mel, gate, align, align_b = outs
+        return (mel, gate, align) + ((align_b,) if align_b is not None else ())
+
+    @staticmethod
+    def backward(ctx, d_mel, d_gate, d_align=None, d_align_b=None):
+        dec, st = ctx.dec, ctx.state
+        eng, dev = st["eng"], st["dev"]
+        B, T, T_in, T_sub = st["B"], st["T"], st["T_in"], st["T_sub"]
+        S, H, E, P, A, M = dec.n_streams, dec.attention_rnn_dim, dec.encoder_embedding_dim, dec.prenet_dim, \
+            dec.attention_dim, dec.n_mel_channels
+        G = 4 * H
+        z = lambda g, *shape: torch.zeros(*shape, device=dev) if g is None else g.to(torch.float32).contiguous()
+        d_mel, d_gate = z(d_mel, B, T, M), z(d_gate, B, T)
+        d_align = None if d_align is None else d_align.contiguous()
+        d_align_b = None if d_align_b is None else d_align_b.contiguous()
+        GL = _cabi.GradLayout()
+        _cabi.check(eng.lib.taco2dec_grad_layout_query(eng.handle, B, T_in, T_sub, T, C.byref(GL)))
+        gbuf = torch.empty(int(GL.total), dtype=torch.uint8, device=dev)
+        a = _cabi.BwdArgs()
+        a.B, a.T, a.T_in, a.T_sub = B, T, T_in, T_sub
+        a.memory, a.embeddings = _ptr(st["mem"]), _ptr(st["emb"])
+        a.memory_lengths, a.bert_lengths = _ptr(st["mlen"]), _ptr(st["blen"])
+        a.training = st["training"]
+        a.rng = st["rng"]
+        a.align, a.align_bert = _ptr(st["align"]), _ptr(st["align_b"])
+        a.d_mel, a.d_gate, a.d_align, a.d_align_bert = _ptr(d_mel), _ptr(d_gate), _ptr(d_align), _ptr(d_align_b)
+        a.saved, a.saved_bytes = _ptr(st["saved"]), st["saved"].numel()
+        a.grads, a.grads_bytes = _ptr(gbuf), gbuf.numel()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            _cabi.check(eng.lib.taco2dec_backward(eng.handle, C.byref(a), C.c_void_p(stream.cuda_stream)))
+
+        # ---- contractions over (frame, utterance): library GEMMs on the rows the kernels left behind ----
+        SL, sv = st["SL"], st["saved"]
+        h1 = _fview(sv, SL.h1, T + 1, S, B, H)
+        cx = _fview(sv, SL.ctx, T + 1, S, B, E)
+        h2 = _fview(sv, SL.h2, T + 1, B, H)
+        dg1 = _fview(gbuf, GL.dg1, S, T * B, G)
+        dg2 = _fview(gbuf, GL.dg2, T * B, G)
+        dq = _fview(gbuf, GL.dq, S, T * B, A)
+        dctx = _fview(gbuf, GL.dctx, S, T, B, E)
+        dpre = _fview(gbuf, GL.dpre, S, T, B, P)
+        dv = _fview(gbuf, GL.dv, S, B, A)
+        Ts = [T_in, T_sub]
+        mems = [st["mem"], st["emb"]]
+        aligns = [st["align"], st["align_b"]]
+        x_frames = F.pad(st["dec_in"].permute(2, 0, 1), (0, 0, 0, 0, 1, 0))[:T].reshape(T * B, M)   # go frame + targets
+        grads = {}
+        d_mems = [None, None]
+        tf32 = dec.grad_gemm_tf32 if dec.grad_gemm_tf32 is not None else dec.weight_dtype == "fp16"
+        old_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+        try:
+            for s, sfx in enumerate(dec._sfx()):
+                pre_m, rnn, att = getattr(dec, "prenet" + sfx), getattr(dec, "attention_rnn" + sfx), \
+                    getattr(dec, "attention_layer" + sfx)
+                pre = _fview(sv, SL.pre[s], T + 1, B, P)[:T].reshape(T * B, P)
+                pre0 = _fview(sv, SL.pre0[s], T + 1, B, P)[:T].reshape(T * B, P)
+                g1t = dg1[s].t()
+                x1 = torch.cat([pre, cx[:T, s].reshape(T * B, E)], dim=1)
+                grads[rnn.weight_ih] = g1t @ x1
+                grads[rnn.weight_hh] = g1t @ h1[:T, s].reshape(T * B, H)
+                db = dg1[s].sum(0)
+                grads[rnn.bias_ih], grads[rnn.bias_hh] = db, db.clone()
+                grads[att.query_layer.linear_layer.weight] = dq[s].t() @ h1[1:, s].reshape(T * B, H)
+                grads[att.v_weight()] = dv[s].sum(0).view(1, A)
+                dpm = _fview(gbuf, GL.dpm[s], B, Ts[s], A)
+                wm = att.memory_layer.linear_layer.weight
+                grads[wm] = dpm.reshape(-1, A).t() @ mems[s].reshape(-1, E)
+                d_mems[s] = torch.bmm(aligns[s].transpose(1, 2), dctx[s].transpose(0, 1)) + dpm @ wm.detach()
+                # prenet: two bias-free linear + ReLU + always-on dropout layers (model.py:13-24); kept <=> output > 0
+                w0, w1 = pre_m.layers[0].linear_layer.weight, pre_m.layers[1].linear_layer.weight
+                dz1 = dpre[s].reshape(T * B, P) * 2.0 * (pre > 0)
+                grads[w1] = dz1.t() @ pre0
+                dz0 = (dz1 @ w1.detach()) * 2.0 * (pre0 > 0)
+                grads[w0] = dz0.t() @ x_frames
+            g2t = dg2.t()
+            x2 = torch.cat([t_ for s in range(S) for t_ in (h1[1:, s].reshape(T * B, H), cx[1:, s].reshape(T * B, E))], dim=1)
+            grads[dec.decoder_rnn.weight_ih] = g2t @ x2
+            grads[dec.decoder_rnn.weight_hh] = g2t @ h2[:T].reshape(T * B, H)
+            db = dg2.sum(0)
+            grads[dec.decoder_rnn.bias_ih], grads[dec.decoder_rnn.bias_hh] = db, db.clone()
+            y = torch.cat([h2[1:].reshape(T * B, H)] + [cx[1:, s].reshape(T * B, E) for s in range(S)], dim=1)
+            dm = d_mel.transpose(0, 1).reshape(T * B, M)
+            dgt = d_gate.t().reshape(T * B, 1)
+            grads[dec.linear_projection.linear_layer.weight] = dm.t() @ y
+            grads[dec.linear_projection.linear_layer.bias] = dm.sum(0)
+            grads[dec.gate_layer.linear_layer.weight] = dgt.t() @ y
+            grads[dec.gate_layer.linear_layer.bias] = dgt.sum(0)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        param_grads = tuple(grads.get(p_) if p_.requires_grad else None for p_ in st["params"])
+        need = ctx.needs_input_grad
+        return (None, d_mems[0] if need[1] else None, d_mems[1] if (S == 2 and need[2]) else None, None, None, None) \
+            + param_grads
 
 
 class Decoder(nn.Module):
@@ -185,6 +302,7 @@ class Decoder(nn.Module):
         self.dropout_replay: Optional[DropoutReplay] = None  # parity runs: externally drawn masks
         self.rng_seed: Optional[int] = None                  # fixed Philox seed; None = fresh per call
         self.validate_lengths = True
+        self.grad_gemm_tf32: Optional[bool] = None   # weight-gradient GEMMs in TF32; None = only with weight_dtype "fp16"
         self._engines = {}
 
     # ------------------------------------------------------------------------------------
@@ -289,7 +407,36 @@ class Decoder(nn.Module):
         """Teacher-forced pass (model.py:392-428).
 
         memory [B,T_in,E], embeddings [B,T_sub,E], decoder_inputs [B,n_mel,T], lengths int64 [B]
-        -> mel [B,n_mel,T], gate [B,T], alignments [B,T,T_in], alignments_bert [B,T,T_sub]."""
+        -> mel [B,n_mel,T], gate [B,T], alignments [B,T,T_in], alignments_bert [B,T,T_sub].
+
+        With autograd enabled the outputs carry a hand-written backward (``_DecoderTF``) when the shape is
+        covered by the tensor path (16 <= B <= 128, SMA, default dims); other shapes raise at backward()."""
+        wants_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in self.parameters()) or memory.requires_grad or
+            (embeddings is not None and embeddings.requires_grad))
+        if wants_grad and self._backward_supported(memory):
+            params = self._weight_tensors()
+            outs = _DecoderTF.apply(self, memory, embeddings if self.n_streams == 2 else None, decoder_inputs,
+                                    memory_lengths, bert_lengths if self.n_streams == 2 else None, *params)
+            mel, gate, align = outs[0], outs[1], outs[2]
+            align_b = outs[3] if self.n_streams == 2 else None
+            return mel.transpose(1, 2), gate, align, align_b
+        outs, _ = self._run_tf(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save=False)
+        mel, gate, align, align_b = outs
+        outs = (mel.transpose(1, 2), gate, align, align_b)
+        if wants_grad:
+            live = [o for o in outs if o is not None]
+            marked = list(_NoBackward.apply(self.gate_layer.linear_layer.weight, *live))
+            outs = tuple(marked.pop(0) if o is not None else None for o in outs)
+        return outs
+
+    def _backward_supported(self, memory) -> bool:
+        return (self.attention_kind == SMA and 16 <= memory.shape[0] <= 128 and self.decoder_path in ("auto", "tensor")
+                and (self.attention_rnn_dim, self.decoder_rnn_dim, self.encoder_embedding_dim, self.prenet_dim,
+                     self.attention_dim, self.n_mel_channels) == (1024, 1024, 512, 256, 128, 80))
+
+    def _run_tf(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save: bool):
+        """One ``taco2dec_forward_teacher_forced`` call; mel is returned in its storage layout [B,T,n_mel]."""
         dev = self.gate_layer.linear_layer.weight.device
         eng = self._engine(dev)
         two = self.n_streams == 2
@@ -321,16 +468,20 @@ class Decoder(nn.Module):
         a.rng = self._rng(dev, keep)
         a.mel, a.gate, a.align, a.align_bert = _ptr(mel), _ptr(gate), _ptr(align), _ptr(align_b)
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        state = None
+        if save:
+            SL = _cabi.SavedLayout()
+            _cabi.check(eng.lib.taco2dec_saved_layout_query(eng.handle, B, T_in, T_sub, T, C.byref(SL)))
+            saved = torch.empty(int(SL.total), dtype=torch.uint8, device=dev)
+            a.saved, a.saved_bytes = _ptr(saved), saved.numel()
+            state = dict(eng=eng, dev=dev, B=B, T=T, T_in=T_in, T_sub=T_sub, mem=mem, emb=emb, dec_in=dec_in, mlen=mlen,
+                         blen=blen, training=int(self.training), rng=a.rng, keep=keep, align=align, align_b=align_b,
+                         saved=saved, SL=SL, params=self._weight_tensors())
         with torch.cuda.device(dev):
             self._bind_weights(eng)
             stream = torch.cuda.current_stream(dev)
             _cabi.check(eng.lib.taco2dec_forward_teacher_forced(eng.handle, C.byref(a), C.c_void_p(stream.cuda_stream)))
-        outs = (mel.transpose(1, 2), gate, align, align_b)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            live = [o for o in outs if o is not None]
-            marked = list(_NoBackward.apply(self.gate_layer.linear_layer.weight, *live))
-            outs = tuple(marked.pop(0) if o is not None else None for o in outs)
-        return outs
+        return (mel, gate, align, align_b), state
 
     def inference_batched(self, memory, embeddings, memory_lengths=None, bert_lengths=None,
                           max_decoder_steps: Optional[int] = None):

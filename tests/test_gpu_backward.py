@@ -1,0 +1,126 @@
+"""-m gpu: decoder backward (BPTT kernels, tensor path) vs autograd through the CPU oracle.
+
+The reference obtains these gradients from torch.autograd over its per-frame loop (model.py:392-428); the oracle
+is the same arithmetic in fp32 on the CPU (pinned to the reference in tests/test_oracle_golden.py and
+tests/test_host_cpu.py).  The CUDA path runs the recurrent products with fp16 (forward) / bf16 (backward) operands and
+fp32 accumulation, so gradients are compared relative to each tensor's own scale:
+    max|got - want| <= TOL_GRAD * max|want|        TOL_GRAD = 1e-2 (bf16 operands: 8-bit mantissa; measured <= 3e-3)
+"""
+import pytest
+import torch
+
+from oracle.decoder_oracle import DecoderOracle
+from oracle.synth import SMA, DecoderDims, make_decoder_weights, make_dropout_plan, make_inputs
+from tests.gpu_util import make_decoder, replay_of
+
+pytestmark = pytest.mark.gpu
+
+TOL_GRAD = 1e-2
+
+
+def _loss(outs, seed):
+    g = torch.Generator().manual_seed(seed)
+    total = 0.0
+    for o in outs:
+        if o is None:
+            continue
+        wgt = torch.randn(o.shape, generator=g).to(o.device)
+        total = total + (o * wgt).sum()
+    return total
+
+
+def _oracle_grads(w, inp, plan, training, dims=DecoderDims()):
+    orc = DecoderOracle(w, SMA, dims=dims)
+    orc.w = {k: v.clone().requires_grad_(True) for k, v in orc.w.items()}
+    mem = inp["memory"].clone().requires_grad_(True)
+    emb = inp["embeddings"].clone().requires_grad_(True) if dims.streams == 2 else None
+    outs = orc.forward(mem, emb, inp["mels"], inp["memory_lengths"], inp["bert_lengths"] if emb is not None else None,
+                       plan, training=training)
+    _loss(outs, 5).backward()
+    grads = {k: v.grad for k, v in orc.w.items()}
+    return grads, mem.grad, (emb.grad if emb is not None else None), outs
+
+
+@pytest.mark.parametrize("B,T,training,tf32", [(16, 5, False, False), (24, 7, True, False), (64, 4, True, True)])
+def test_backward_vs_oracle_autograd(B, T, training, tf32):
+    T_in, T_sub, seed = 24, 8, 500 + B
+    w = make_decoder_weights(SMA, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=True)
+    plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, training, seed=seed + 1)
+    want, want_dmem, want_demb, want_outs = _oracle_grads(w, inp, plan, training)
+
+    dec = make_decoder(w, SMA)
+    dec.decoder_path, dec.weight_dtype = "tensor", "fp16"
+    dec.grad_gemm_tf32 = tf32
+    dec.dropout_replay = replay_of(plan)
+    dec.train(training)
+    mem = inp["memory"].cuda().requires_grad_(True)
+    emb = inp["embeddings"].cuda().requires_grad_(True)
+    outs = dec(mem, emb, inp["mels"].cuda(), inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+    for o, wo in zip(outs, want_outs):
+        assert (o.detach().cpu() - wo.detach()).abs().max() < 1e-3
+    _loss(outs, 5).backward()
+    torch.cuda.synchronize()
+    sd = dict(dec.named_parameters())
+    worst = {}
+    for name, gw in want.items():
+        got = sd[name].grad
+        if gw is None:
+            assert got is None, f"{name}: dead parameter must not receive a gradient"
+            continue
+        assert got is not None, f"{name}: no gradient"
+        err = float((got.cpu() - gw).abs().max() / gw.abs().max())
+        worst[name] = err
+    for name, gw, got in (("memory", want_dmem, mem.grad), ("embeddings", want_demb, emb.grad)):
+        worst[name] = float((got.cpu() - gw).abs().max() / gw.abs().max())
+    bad = {k: v for k, v in worst.items() if not v < TOL_GRAD}
+    print({k: f"{v:.2e}" for k, v in worst.items()})
+    assert not bad, f"relative gradient error above {TOL_GRAD}: {bad}"
+
+
+def test_backward_philox_masks_match_forward():
+    """Production mode (no replay): backward re-draws the LSTM-state dropout masks from Philox.  Materialising the
+    same masks through taco2dec_philox_keep_mask and replaying them must give the same outputs and gradients."""
+    import ctypes as C
+    from tacotron2_subword_b200 import DropoutReplay, _cabi
+    B, T, T_in, T_sub, seed, H = 16, 4, 20, 7, 91, 1024
+    w = make_decoder_weights(SMA, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=True)
+    dec = make_decoder(w, SMA).train()
+    dec.decoder_path, dec.weight_dtype, dec.rng_seed = "tensor", "fp16", 1234
+    args = (inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(), inp["memory_lengths"].cuda(),
+            inp["bert_lengths"].cuda())
+    outs = dec(*args)
+    _loss(outs, 3).backward()
+    g1 = {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None}
+    assert len(g1) == 26
+    dec.zero_grad(set_to_none=True)
+
+    lib = _cabi.load_library()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pk = [[torch.empty(T + 1, B, 256, dtype=torch.uint8, device="cuda") for _ in range(2)] for _ in range(2)]
+    for s_ in range(2):
+        for l in range(2):
+            _cabi.check(lib.taco2dec_philox_keep_mask(1234, s_ * 2 + l, T + 1, B * 256, 0.5, C.c_void_p(pk[s_][l].data_ptr()), st))
+    lk = torch.empty(6, T, B, H, dtype=torch.uint8, device="cuda")
+    for k in range(6):
+        _cabi.check(lib.taco2dec_philox_keep_mask(1234, 4 + k, T, B * H, 0.1, C.c_void_p(lk[k].data_ptr()), st))
+    dec.dropout_replay = DropoutReplay(prenet_keep=pk, lstm_keep=lk.permute(1, 0, 2, 3).contiguous())
+    outs2 = dec(*args)
+    for o, o2 in zip(outs, outs2):
+        assert torch.equal(o, o2)
+    _loss(outs2, 3).backward()
+    for n, p in dec.named_parameters():
+        if p.grad is not None:
+            assert float((p.grad - g1[n]).abs().max()) <= 1e-3 * float(g1[n].abs().max()), n   # atomics reorder fp32 sums; bf16 rounding of the gate gradients amplifies it
+
+
+def test_backward_unsupported_shape_raises():
+    B, T, T_in, T_sub, seed = 2, 3, 12, 4, 7
+    w = make_decoder_weights(SMA, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed)
+    dec = make_decoder(w, SMA).train()
+    outs = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(), inp["memory_lengths"].cuda(),
+               inp["bert_lengths"].cuda())
+    with pytest.raises(NotImplementedError):
+        outs[0].sum().backward()

@@ -47,6 +47,9 @@ def test_ctypes_structs_match_header_field_order():
     assert fields("taco2dec_rng") == [f[0] for f in _cabi.Rng._fields_]
     assert fields("taco2dec_tf_args") == [f[0] for f in _cabi.TFArgs._fields_]
     assert fields("taco2dec_infer_args") == [f[0] for f in _cabi.InferArgs._fields_]
+    assert fields("taco2dec_saved_layout") == [f[0] for f in _cabi.SavedLayout._fields_]
+    assert fields("taco2dec_grad_layout") == [f[0] for f in _cabi.GradLayout._fields_]
+    assert fields("taco2dec_bwd_args") == [f[0] for f in _cabi.BwdArgs._fields_]
 
 
 def test_create_refuses_without_gpu():
