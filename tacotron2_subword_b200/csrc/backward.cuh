@@ -94,104 +94,147 @@ __device__ __forceinline__ void lstm_cell_backward(const float* sv, size_t gs, f
   dgate[3] = dhp * tcn * go * (1.0f - go);
 }
 
-// d(mel, gate)/d y for one input column k of the projection (model.py:382-388): sum_row dmel[row] W[row][k] + dgate wg[k]
-__device__ __forceinline__ float proj_backward_col(const Params& p, const Grads& g, int b, int t, int k) {
+// ---- LSTM pointwise kernels: block = 32 utterances x 8 hidden units, thread (bl = tid & 31, jl = tid >> 5) ----------
+// Lanes run along the batch, so the split-K partials ([row][NPAD]) and the saved gates ([unit][B]) are read coalesced;
+// the results are transposed through shared memory so that every (utterance, gate) writes its 8 consecutive units as
+// one 16-byte bf16 core-matrix row of the GEMM operand tile and 32 contiguous bytes of the fp32 gradient rows.
+constexpr int kPwB = 32, kPwJ = 8;
+
+// d(mel, gate) of the block's utterances at frame t -> shared memory [32][M+1] (odd stride: conflict-free per lane)
+__device__ __forceinline__ void stage_dout(const Params& p, const Grads& g, int t, int b0, float (*dm_s)[M + 1]) {
+  for (int i = threadIdx.x; i < kPwB * (M + 1); i += blockDim.x) {
+    const int bb = i / (M + 1), r = i - bb * (M + 1), b = b0 + bb;
+    float v = 0.f;
+    if (b < p.B) v = r < M ? g.d_mel[((size_t)b * p.T + t) * M + r] : g.d_gate[(size_t)b * p.T + t];
+    dm_s[bb][r] = v;
+  }
+}
+// projection backwards for input column k (model.py:382-388): sum_row dmel[row] Wp[row][k] + dgate wg[k]
+__device__ __forceinline__ float proj_backward_col(const Params& p, const float* dm_row, int k) {
   const int KD = H + p.S * E;
-  const float* dm = g.d_mel + ((size_t)b * p.T + t) * M;
-  float acc = g.d_gate[(size_t)b * p.T + t] * __ldg(p.gate_w + k);
+  float acc = dm_row[M] * __ldg(p.gate_w + k);
 #pragma unroll 8
-  for (int r = 0; r < M; ++r) acc = fmaf(__ldg(dm + r), __ldg(p.proj_w + (size_t)r * KD + k), acc);
+  for (int r = 0; r < M; ++r) acc = fmaf(dm_row[r], __ldg(p.proj_w + (size_t)r * KD + k), acc);
   return acc;
+}
+// gate gradients of the block -> bf16 operand tile + fp32 rows [.., b, G]
+__device__ __forceinline__ void store_gate_grads(const float (*out_s)[kPwB][kPwJ + 1], int NPAD, int B, int b0, int j0,
+                                                 unsigned char* tiles, float* rows /* + t*B*G */) {
+  const int tid = threadIdx.x;
+  if (tid < 4 * kPwB) {
+    const int q = tid >> 5, bl = tid & 31, b = b0 + bl;
+    if (b < B) {
+      const float* v = out_s[q][bl];
+      const int k = q * H + j0;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<unsigned*>(&h0); pk.y = *reinterpret_cast<unsigned*>(&h1);
+      pk.z = *reinterpret_cast<unsigned*>(&h2); pk.w = *reinterpret_cast<unsigned*>(&h3);
+      *reinterpret_cast<uint4*>(tiles + (size_t)(k >> 6) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63)) = pk;
+      float4* dst = reinterpret_cast<float4*>(rows + (size_t)b * G + k);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) bw_pointwise2(Params p, Bufs bb, Grads g, const int* t_ptr) {
+  __shared__ float dm_s[kPwB][M + 1];
+  __shared__ float out_s[4][kPwB][kPwJ + 1];
   const int t = *t_ptr;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.B * H) return;
-  const int j = i / p.B, b = i - j * p.B;
-  const size_t idx = (size_t)b * H + j;
-  float dh = proj_backward_col(p, g, b, t, j);
+  const int nbt = (p.B + kPwB - 1) / kPwB;
+  const int b0 = (blockIdx.x % nbt) * kPwB, j0 = (blockIdx.x / nbt) * kPwJ;
+  const int bl = threadIdx.x & 31, jl = threadIdx.x >> 5, b = b0 + bl, j = j0 + jl;
+  stage_dout(p, g, t, b0, dm_s);
+  __syncthreads();
+  if (b < p.B) {
+    const size_t idx = (size_t)b * H + j;
+    float dh = proj_backward_col(p, dm_s[bl], j);
 #pragma unroll
-  for (int k = 0; k < SPLITSB2; ++k) dh += bb.dx2[((size_t)k * bb.K2 + p.S * (H + E) + j) * bb.NPAD + b];
-  const size_t gs = (size_t)H * p.B;
-  const float* sv = g.sv.gates2 + ((size_t)t * 5 * H + j) * p.B + b;
-  float mh = 1.f, mc = 1.f, mc_prev = 1.f;
-  if (p.training) {
-    const float sc = 1.0f / (1.0f - p.p_dec);
-    const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * p.B * H : nullptr;
-    const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * p.B * H : nullptr;
-    mh = keep_mult(kh, idx, p.seed, 8, t, (int)idx, p.thresh_dec, sc);
-    mc = keep_mult(kc, idx, p.seed, 9, t, (int)idx, p.thresh_dec, sc);
-    if (t > 0) {
-      const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 5) * p.B * H : nullptr;
-      mc_prev = keep_mult(kcp, idx, p.seed, 9, t - 1, (int)idx, p.thresh_dec, sc);
+    for (int k = 0; k < SPLITSB2; ++k) dh += bb.dx2[((size_t)k * bb.K2 + p.S * (H + E) + j) * bb.NPAD + b];
+    const size_t gs = (size_t)H * p.B;
+    const float* sv = g.sv.gates2 + ((size_t)t * 5 * H + j) * p.B + b;
+    float mh = 1.f, mc = 1.f, mc_prev = 1.f;
+    if (p.training) {
+      const float sc = 1.0f / (1.0f - p.p_dec);
+      const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * p.B * H : nullptr;
+      const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * p.B * H : nullptr;
+      mh = keep_mult(kh, idx, p.seed, 8, t, (int)idx, p.thresh_dec, sc);
+      mc = keep_mult(kc, idx, p.seed, 9, t, (int)idx, p.thresh_dec, sc);
+      if (t > 0) {
+        const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 5) * p.B * H : nullptr;
+        mc_prev = keep_mult(kcp, idx, p.seed, 9, t - 1, (int)idx, p.thresh_dec, sc);
+      }
     }
-  }
-  const float c_prev = t > 0 ? mc_prev * (sv - 5 * gs)[4 * gs] : 0.f;
-  float dgate[4];
-  lstm_cell_backward(sv, gs, c_prev, mh, mc, dh, g.dc2 + idx, dgate);
-  float* out = g.dg2 + ((size_t)t * p.B + b) * G + j;
+    const float c_prev = t > 0 ? mc_prev * (sv - 5 * gs)[4 * gs] : 0.f;
+    float dgate[4];
+    lstm_cell_backward(sv, gs, c_prev, mh, mc, dh, g.dc2 + idx, dgate);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    out[q * H] = dgate[q];
-    xb_store(bb.dg2, bb.NPAD, b, q * H + j, dgate[q]);
+    for (int q = 0; q < 4; ++q) out_s[q][bl][jl] = dgate[q];
   }
+  __syncthreads();
+  store_gate_grads(out_s, bb.NPAD, p.B, b0, j0, bb.dg2, g.dg2 + (size_t)t * p.B * G);
 }
 
 __global__ void __launch_bounds__(256) bw_pointwise1(Params p, Bufs bb, Grads g, const int* t_ptr) {
+  __shared__ float dq_s[A][kPwB + 1];
+  __shared__ float out_s[4][kPwB][kPwJ + 1];
   const int t = *t_ptr;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.S * p.B * H) return;
-  const int s = i / (p.B * H), r = i - s * p.B * H, j = r / p.B, b = r - j * p.B;
-  const size_t idx = (size_t)b * H + j;
-  float dh = 0.f;
+  const int nbt = (p.B + kPwB - 1) / kPwB, njt = H / kPwJ;
+  const int s = blockIdx.x / (nbt * njt), rem = blockIdx.x - s * nbt * njt;
+  const int b0 = (rem % nbt) * kPwB, j0 = (rem / nbt) * kPwJ;
+  const int bl = threadIdx.x & 31, jl = threadIdx.x >> 5, b = b0 + bl, j = j0 + jl;
+  for (int i = threadIdx.x; i < kPwB * A; i += blockDim.x) {
+    const int bb_ = i / A, a = i - bb_ * A;
+    dq_s[a][bb_] = (b0 + bb_ < p.B) ? g.dq[(((size_t)s * p.T + t) * p.B + b0 + bb_) * A + a] : 0.f;
+  }
+  __syncthreads();
+  if (b < p.B) {
+    const size_t idx = (size_t)b * H + j;
+    float dh = 0.f;
 #pragma unroll
-  for (int k = 0; k < SPLITSB1; ++k) dh += bb.dx1[(((size_t)s * SPLITSB1 + k) * K1 + P + E + j) * bb.NPAD + b];
+    for (int k = 0; k < SPLITSB1; ++k) dh += bb.dx1[(((size_t)s * SPLITSB1 + k) * K1 + P + E + j) * bb.NPAD + b];
 #pragma unroll
-  for (int k = 0; k < SPLITSB2; ++k) dh += bb.dx2[((size_t)k * bb.K2 + s * (H + E) + j) * bb.NPAD + b];
-  {  // query layer: dh1 += Wq^T dq  (attention.py:56, 368)
-    const float4* dq4 = reinterpret_cast<const float4*>(g.dq + (((size_t)s * p.T + t) * p.B + b) * A);
-    const float* wq = p.st[s].wq + j;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int a4 = 0; a4 < A / 4; ++a4) {
-      const float4 d = dq4[a4];
-      acc = fmaf(d.x, __ldg(wq + (size_t)(4 * a4) * H), acc);
-      acc = fmaf(d.y, __ldg(wq + (size_t)(4 * a4 + 1) * H), acc);
-      acc = fmaf(d.z, __ldg(wq + (size_t)(4 * a4 + 2) * H), acc);
-      acc = fmaf(d.w, __ldg(wq + (size_t)(4 * a4 + 3) * H), acc);
+    for (int k = 0; k < SPLITSB2; ++k) dh += bb.dx2[((size_t)k * bb.K2 + s * (H + E) + j) * bb.NPAD + b];
+    {  // query layer: dh1 += Wq^T dq  (attention.py:56, 368)
+      const float* wq = p.st[s].wq + j;
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
+      for (int a = 0; a < A; a += 2) {
+        acc0 = fmaf(dq_s[a][bl], __ldg(wq + (size_t)a * H), acc0);
+        acc1 = fmaf(dq_s[a + 1][bl], __ldg(wq + (size_t)(a + 1) * H), acc1);
+      }
+      dh += acc0 + acc1;
     }
-    dh += acc;
-  }
-  const size_t gs = (size_t)H * p.B;
-  const float* sv = g.sv.gates1 + (((size_t)t * p.S + s) * 5 * H + j) * p.B + b;
-  float mh = 1.f, mc = 1.f, mc_prev = 1.f;
-  if (p.training) {
-    const float sc = 1.0f / (1.0f - p.p_att);
-    const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s) * p.B * H : nullptr;
-    const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s + 1) * p.B * H : nullptr;
-    mh = keep_mult(kh, idx, p.seed, 4 + 2 * s, t, (int)idx, p.thresh_att, sc);
-    mc = keep_mult(kc, idx, p.seed, 5 + 2 * s, t, (int)idx, p.thresh_att, sc);
-    if (t > 0) {
-      const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 2 * s + 1) * p.B * H : nullptr;
-      mc_prev = keep_mult(kcp, idx, p.seed, 5 + 2 * s, t - 1, (int)idx, p.thresh_att, sc);
+    const size_t gs = (size_t)H * p.B;
+    const float* sv = g.sv.gates1 + (((size_t)t * p.S + s) * 5 * H + j) * p.B + b;
+    float mh = 1.f, mc = 1.f, mc_prev = 1.f;
+    if (p.training) {
+      const float sc = 1.0f / (1.0f - p.p_att);
+      const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s) * p.B * H : nullptr;
+      const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s + 1) * p.B * H : nullptr;
+      mh = keep_mult(kh, idx, p.seed, 4 + 2 * s, t, (int)idx, p.thresh_att, sc);
+      mc = keep_mult(kc, idx, p.seed, 5 + 2 * s, t, (int)idx, p.thresh_att, sc);
+      if (t > 0) {
+        const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 2 * s + 1) * p.B * H : nullptr;
+        mc_prev = keep_mult(kcp, idx, p.seed, 5 + 2 * s, t - 1, (int)idx, p.thresh_att, sc);
+      }
     }
-  }
-  const float c_prev = t > 0 ? mc_prev * (sv - (size_t)p.S * 5 * gs)[4 * gs] : 0.f;
-  float dgate[4];
-  lstm_cell_backward(sv, gs, c_prev, mh, mc, dh, g.dc1 + (size_t)s * p.B * H + idx, dgate);
-  float* out = g.dg1 + (((size_t)s * p.T + t) * p.B + b) * G + j;
-  unsigned char* tiles = bb.dg1 + (size_t)s * (G / 64) * bb.NPAD * 128;
+    const float c_prev = t > 0 ? mc_prev * (sv - (size_t)p.S * 5 * gs)[4 * gs] : 0.f;
+    float dgate[4];
+    lstm_cell_backward(sv, gs, c_prev, mh, mc, dh, g.dc1 + (size_t)s * p.B * H + idx, dgate);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    out[q * H] = dgate[q];
-    xb_store(tiles, bb.NPAD, b, q * H + j, dgate[q]);
+    for (int q = 0; q < 4; ++q) out_s[q][bl][jl] = dgate[q];
   }
+  __syncthreads();
+  store_gate_grads(out_s, bb.NPAD, p.B, b0, j0, bb.dg1 + (size_t)s * (G / 64) * bb.NPAD * 128,
+                   g.dg1 + ((size_t)s * p.T + t) * p.B * G);
 }
 
 // stepwise monotonic attention backwards, one CTA per (utterance, stream)
 constexpr int kBwThreads = 512;
-__host__ __device__ inline size_t bw_attention_smem_floats(int Ts) { return (size_t)E + 4 * A + 4 * (size_t)(Ts + 4); }
+__host__ __device__ inline size_t bw_attention_smem_floats(int Ts) { return (size_t)E + 4 * A + 4 * (size_t)(Ts + 4) + M + 4; }
 
 __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb, Grads g, const int* t_ptr) {
   extern __shared__ __align__(16) float sm[];
@@ -210,10 +253,14 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
   float* ap_s = p_s + Ts + 4;         // Ts+4   alignment state entering frame t
   float* dan_s = ap_s + Ts + 4;       // Ts+4   d alpha'[t]
   float* de_s = dan_s + Ts + 4;       // Ts+4
+  float* dm_s = de_s + Ts + 4;        // M+1
 
+  for (int r = tid; r <= M; r += kBwThreads)
+    dm_s[r] = r < M ? g.d_mel[((size_t)b * p.T + t) * M + r] : g.d_gate[(size_t)b * p.T + t];
+  __syncthreads();
   // d ctx[t] = next frame's attention-LSTM input gradient + this frame's decoder-LSTM input and projection gradients
   for (int d = tid; d < E; d += kBwThreads) {
-    float acc = proj_backward_col(p, g, b, t, H + s * E + d);
+    float acc = proj_backward_col(p, dm_s, H + s * E + d);
 #pragma unroll
     for (int k = 0; k < SPLITSB1; ++k) acc += bb.dx1[(((size_t)s * SPLITSB1 + k) * K1 + P + d) * bb.NPAD + b];
 #pragma unroll

@@ -296,6 +296,70 @@ __global__ void __launch_bounds__(256) bt_proj(Params p, Bufs bf, const int* t_p
   }
 }
 
+// Teacher-forced mode: nothing inside the frame loop consumes mel / gate (the next prenet input is the target frame,
+// model.py:417-424), so the projection of ALL frames is one pass after the loop over the stored h2 / context rows:
+//   [mel | gate][(t,b)][81] = [h2 | ctx | ctx_bert][(t,b)][KD] . [Wp ; wg]^T + bias          (model.py:382-388)
+// fp32 on the CUDA cores (exact like the in-loop version): 64-row x 81-column tile per block, K in chunks of 32.
+constexpr int kPaRows = 64, kPaK = 32, kPaCols = 96;
+__global__ void __launch_bounds__(256) bt_proj_all(Params p, Bufs bf) {
+  __shared__ float y_s[kPaRows][kPaK + 1];
+  __shared__ float w_s[kPaCols][kPaK + 1];
+  const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
+  const int KD = H + p.S * E, R = p.T * p.B;
+  const int r0 = blockIdx.x * kPaRows;
+  float acc[8][3];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = 0.f; }
+  // Blocks start at staggered K chunks: in lockstep they would all read the same 128-byte column of rows that lie
+  // 2-4 KB apart, which camps on a few HBM channels (measured: 1 ms vs 39 ms for the same launch).
+  const int n_chunks = KD / kPaK;
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    const int k0 = ((kc + blockIdx.x * 5) % n_chunks) * kPaK;
+    // activations: row (t, b) of slot t+1; the chunk lies inside one of the segments h2 | ctx_0 | ctx_1
+#pragma unroll
+    for (int pass = 0; pass < kPaRows / 8; ++pass) {
+      const int rl = pass * 8 + rg, r = r0 + rl;
+      float v = 0.f;
+      if (r < R) {
+        const int t = r / p.B, b = r - t * p.B, k = k0 + lane;
+        if (k < H) v = bf.sv.h2[((size_t)(t + 1) * p.B + b) * H + k];
+        else { const int kk = k - H, s = kk / E, d = kk - s * E; v = bf.sv.ctx[(((size_t)(t + 1) * p.S + s) * p.B + b) * E + d]; }
+      }
+      y_s[rl][lane] = v;
+    }
+#pragma unroll
+    for (int pass = 0; pass < kPaCols / 8; ++pass) {
+      const int c = pass * 8 + rg;
+      float v = 0.f;
+      if (c < M) v = __ldg(p.proj_w + (size_t)c * KD + k0 + lane);
+      else if (c == M) v = __ldg(p.gate_w + k0 + lane);
+      w_s[c][lane] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < kPaK; ++kk) {
+      const float w0 = w_s[lane][kk], w1 = w_s[lane + 32][kk], w2 = w_s[lane + 64][kk];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = y_s[rg * 8 + i][kk];
+        acc[i][0] = fmaf(y, w0, acc[i][0]); acc[i][1] = fmaf(y, w1, acc[i][1]); acc[i][2] = fmaf(y, w2, acc[i][2]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + rg * 8 + i;
+    if (r >= R) continue;
+    const int t = r / p.B, b = r - t * p.B;
+    float* mel = p.mel + ((size_t)b * p.Tcap + t) * M;
+    mel[lane] = acc[i][0] + p.proj_b[lane];
+    mel[lane + 32] = acc[i][1] + p.proj_b[lane + 32];
+    if (lane + 64 < M) mel[lane + 64] = acc[i][2] + p.proj_b[lane + 64];
+    else if (lane + 64 == M) p.gate[(size_t)b * p.Tcap + t] = acc[i][2] + p.gate_b[0];
+  }
+}
+
 // frame counter lives in device memory so that one captured CUDA graph serves every frame
 __global__ void bt_advance(int* t_ptr) { *t_ptr += 1; }
 

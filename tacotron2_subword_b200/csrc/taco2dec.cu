@@ -877,7 +877,7 @@ unsigned keep_threshold(double p_drop) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WorkspaceLayout {
-  size_t pm[2], pre[2], pre0[2], a_prev[2], a_cum[2], h1, c1, h2, c2, ctx, q, ctl, total;
+  size_t pm[2], pre[2], pre0[2], a_prev[2], a_cum[2], h1, c1, h2, c2, ctx, q, ctl, h2_all, ctx_all, total;
 };
 
 }  // namespace
@@ -935,6 +935,10 @@ WorkspaceLayout plan_workspace(const taco2dec_config& c, int B, int T_in, int T_
   L.ctx = take((size_t)c.n_streams * B * c.enc_dim);
   L.q = take((size_t)c.n_streams * B * c.attn_dim);
   L.ctl = take(64);
+  // tensor path, teacher-forced: h2 / context rows of every frame for the hoisted projection (bt_proj_all)
+  const bool rows = tf && B >= 16 && B <= 128;
+  L.h2_all = take(rows ? (size_t)(T + 1) * B * c.dec_rnn_dim : 0);
+  L.ctx_all = take(rows ? (size_t)(T + 1) * c.n_streams * B * c.enc_dim : 0);
   L.total = off;
   return L;
 }
@@ -1246,11 +1250,11 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   bf.sv = h->cur_sv;
   const int S = p.S, B = p.B;
   const int n_steps = p.free_running ? p.max_steps : p.T;
-  if (bf.sv.h1) {   // slot 0 of the saved state arrays = the zero initial state (model.py:237-256)
-    CUDA_TRY(cudaMemsetAsync(bf.sv.h1, 0, (size_t)S * B * bt::H * sizeof(float), st));
-    CUDA_TRY(cudaMemsetAsync(bf.sv.ctx, 0, (size_t)S * B * bt::E * sizeof(float), st));
-    CUDA_TRY(cudaMemsetAsync(bf.sv.h2, 0, (size_t)B * bt::H * sizeof(float), st));
-  }
+  // slot 0 of the stored state arrays = the zero initial state (model.py:237-256)
+  if (bf.sv.h1) CUDA_TRY(cudaMemsetAsync(bf.sv.h1, 0, (size_t)S * B * bt::H * sizeof(float), st));
+  if (bf.sv.ctx) CUDA_TRY(cudaMemsetAsync(bf.sv.ctx, 0, (size_t)S * B * bt::E * sizeof(float), st));
+  if (bf.sv.h2) CUDA_TRY(cudaMemsetAsync(bf.sv.h2, 0, (size_t)B * bt::H * sizeof(float), st));
+  const bool hoist_proj = !p.free_running && bf.sv.h2 && bf.sv.ctx && !getenv("TACO2DEC_NO_HOIST");
   CUDA_TRY(cudaMemsetAsync(bf.x1, 0, (size_t)S * (bt::K1 / 64) * NPAD * 128, st));
   CUDA_TRY(cudaMemsetAsync(bf.x2, 0, (size_t)(bf.K2 / 64) * NPAD * 128, st));
   bt::bt_init_kernel<<<h->num_sms, 256, 0, st>>>(p, bf);
@@ -1278,7 +1282,7 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   bt::bt_attention<true><<<S * B, kThreads, att_smem, cs>>>(p, bf, t_ptr);
   if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(g2, cs);
   bt::bt_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
-  bt::bt_proj<<<((bt::M + 1) * B * 32 + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
+  if (!hoist_proj) bt::bt_proj<<<((bt::M + 1) * B * 32 + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
   bt::bt_advance<<<1, 1, 0, cs>>>(t_ptr);
   const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
   if (ce != cudaSuccess || ee != cudaSuccess || graph == nullptr) {
@@ -1294,10 +1298,14 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
       return fail(TACO2DEC_E_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
     }
   }
-  h->launches += 9LL * n_steps;
+  h->launches += (hoist_proj ? 8LL : 9LL) * n_steps;
   // the executable graph may be destroyed once its launches are enqueued; CUDA keeps it alive until they finish
   cudaGraphExecDestroy(exec);
   cudaGraphDestroy(graph);
+  if (hoist_proj) {
+    bt::bt_proj_all<<<(p.T * B + bt::kPaRows - 1) / bt::kPaRows, 256, 0, st>>>(p, bf);
+    h->launches++;
+  }
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   h->last_path = TACO2DEC_PATH_TENSOR;
@@ -1429,10 +1437,11 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
-  bw::bw_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, cs>>>(p, bb, g, t_ptr);
+  const int pw_blocks = ((B + bw::kPwB - 1) / bw::kPwB) * (bt::H / bw::kPwJ);
+  bw::bw_pointwise2<<<pw_blocks, 256, 0, cs>>>(p, bb, g, t_ptr);
   cudaError_t ce = tc::launch_gemm<NPAD>(gb2, cs);
   bw::bw_attention<<<S * B, bw::kBwThreads, att_smem, cs>>>(p, bb, g, t_ptr);
-  bw::bw_pointwise1<<<(S * B * bt::H + 255) / 256, 256, 0, cs>>>(p, bb, g, t_ptr);
+  bw::bw_pointwise1<<<S * pw_blocks, 256, 0, cs>>>(p, bb, g, t_ptr);
   if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(gb1, cs);
   bw::bw_save_dpre<<<(S * B * bt::P + 255) / 256, 256, 0, cs>>>(p, bb, g, t_ptr);
   bw::bw_retreat<<<1, 1, 0, cs>>>(t_ptr);
@@ -1711,6 +1720,9 @@ int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* 
       p.st[s].pre = (float*)(sb + SL.pre[s]);
       pre0_save[s] = (float*)(sb + SL.pre0[s]);
     }
+  } else if (a->B >= 16 && a->B <= 128) {
+    h->cur_sv.h2 = (float*)(ws + L.h2_all);
+    h->cur_sv.ctx = (float*)(ws + L.ctx_all);
   }
   // hoisted prenet over the go-frame + all T targets (model.py:407-413)
   for (int s = 0; s < c.n_streams; ++s) {
