@@ -124,3 +124,54 @@ def test_backward_unsupported_shape_raises():
                inp["bert_lengths"].cuda())
     with pytest.raises(NotImplementedError):
         outs[0].sum().backward()
+
+
+def test_model_training_step_end_to_end():
+    """BERT_Tacotron2 drop-in: forward -> Tacotron2Loss-style loss (loss_function.py:12-66, L2 alignment variant) ->
+    backward -> optimizer step -> forward again (the engine must pick up the updated weights)."""
+    from tacotron2_subword_b200 import BERT_Tacotron2, create_hparams
+    torch.manual_seed(1234)
+    hp = create_hparams()
+    model = BERT_Tacotron2(hp).cuda().train()
+    model.decoder.weight_dtype = "fp16"
+    model.decoder.rng_seed = 11
+    B, T_in, T_sub, T = 16, 14, 6, 9
+    g = torch.Generator().manual_seed(3)
+    text = torch.randint(0, hp.n_symbols, (B, T_in), generator=g).cuda()
+    sub = torch.randint(0, hp.sub_n_symbols, (B, T_sub), generator=g).cuda()
+    in_len = torch.randint(T_in // 2, T_in + 1, (B,), generator=g); in_len[0] = T_in
+    sub_len = torch.randint(T_sub // 2, T_sub + 1, (B,), generator=g); sub_len[0] = T_sub
+    out_len = torch.randint(T // 2, T + 1, (B,), generator=g); out_len[0] = T
+    order = torch.argsort(in_len, descending=True)          # the encoder packs by length (data_utils.py:146-160)
+    in_len, sub_len, out_len = in_len[order].cuda(), sub_len[order].cuda(), out_len[order].cuda()
+    mels = torch.randn(B, 80, T, generator=g).cuda()
+    gate_t = torch.zeros(B, T).cuda()
+    align_t = torch.rand(B, T, T_in, generator=g).cuda()
+    pcls = torch.randn(B, T_in, hp.BERT_embedding_dim, generator=g).cuda()
+    bcls = torch.randn(B, T_sub, hp.BERT_embedding_dim, generator=g).cuda()
+    x = (text, in_len, sub_len, mels, (T_in, T), out_len, sub, pcls, bcls)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+
+    def loss_of(out):
+        mel, mel_post, gate, al, alb = out
+        F = torch.nn.functional
+        return (F.mse_loss(mel, mels) + F.mse_loss(mel_post, mels) +
+                F.binary_cross_entropy_with_logits(gate.reshape(-1, 1), gate_t.reshape(-1, 1)) + F.mse_loss(al, align_t))
+
+    loss0 = loss_of(model(x))
+    opt.zero_grad(set_to_none=True)
+    loss0.backward()
+    dead = 0
+    for n, p in model.named_parameters():
+        if "decoder_rnn_bert" in n:
+            assert p.grad is None
+            dead += 1
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert dead == 4
+    assert float(model.decoder.attention_rnn.weight_hh.grad.abs().max()) > 0
+    assert float(model.embedding.weight.grad.abs().max()) > 0          # gradient reaches the encoder through d memory
+    opt.step()
+    loss1 = loss_of(model(x))
+    assert torch.isfinite(loss1)
+    assert float(loss1.detach()) < float(loss0.detach())       # same dropout seed, small SGD step: the loss goes down
