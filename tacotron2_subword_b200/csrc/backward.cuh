@@ -255,8 +255,37 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
   float* de_s = dan_s + Ts + 4;       // Ts+4
   float* dm_s = de_s + Ts + 4;        // M+1
 
+  // ---- early requests: nothing below depends on the incoming gradients, so these loads overlap the d ctx chain ----
+  const float* mem_b = sp.mem + (size_t)b * Ts * E;
+  const float* pm_b = sp.pm + (size_t)b * Ts * A;
+  float* dpm_b = g.dpm[s] + (size_t)b * Ts * A;
+  float4 mrow[2][4];
+  float pmr[2][4], dpr[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int j = warp + kW * r;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      mrow[r][q] = j < Ts ? __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j * E) + lane + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pmr[r][q] = j < len ? __ldg(pm_b + (size_t)j * A + lane + 32 * q) : 0.f;
+      dpr[r][q] = j < len ? dpm_b[(size_t)j * A + lane + 32 * q] : 0.f;
+    }
+  }
   for (int r = tid; r <= M; r += kBwThreads)
     dm_s[r] = r < M ? g.d_mel[((size_t)b * p.T + t) * M + r] : g.d_gate[(size_t)b * p.T + t];
+  for (int a = tid; a < A; a += kBwThreads) {
+    q_s[a] = g.sv.q[(((size_t)t * p.S + s) * p.B + b) * A + a];
+    v_s[a] = sp.v[a];
+    dq_s[a] = 0.f;
+    dv_s[a] = 0.f;
+  }
+  for (int j = tid; j < Ts; j += kBwThreads) {
+    p_s[j] = g.p_saved[s][((size_t)t * p.B + b) * Ts + j];
+    ap_s[j] = t > 0 ? g.align[s][((size_t)b * p.T + (t - 1)) * Ts + j] : (j == 0 ? 1.f : 0.f);   // attention.py:324-328
+    float d = g.dalpha[s][(size_t)b * Ts + j];                      // carry from frame t+1
+    if (g.d_align[s]) d += g.d_align[s][((size_t)b * p.T + t) * Ts + j];   // external alignment gradient
+    dan_s[j] = d;
+  }
   __syncthreads();
   // d ctx[t] = next frame's attention-LSTM input gradient + this frame's decoder-LSTM input and projection gradients
   for (int d = tid; d < E; d += kBwThreads) {
@@ -268,34 +297,32 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
     dctx_s[d] = acc;
     g.dctx[(((size_t)s * p.T + t) * p.B + b) * E + d] = acc;
   }
-  for (int a = tid; a < A; a += kBwThreads) {
-    q_s[a] = g.sv.q[(((size_t)t * p.S + s) * p.B + b) * A + a];
-    v_s[a] = sp.v[a];
-    dq_s[a] = 0.f;
-    dv_s[a] = 0.f;
-  }
-  for (int j = tid; j < Ts; j += kBwThreads) {
-    p_s[j] = g.p_saved[s][((size_t)t * p.B + b) * Ts + j];
-    ap_s[j] = t > 0 ? g.align[s][((size_t)b * p.T + (t - 1)) * Ts + j] : (j == 0 ? 1.f : 0.f);   // attention.py:324-328
-  }
   __syncthreads();
 
-  // d alpha'_j = d ctx . memory_j + carry from frame t+1 (+ external alignment gradient)   (attention.py:395)
-  const float* mem_b = sp.mem + (size_t)b * Ts * E;
-  for (int j = warp; j < Ts; j += kW) {
-    const float4* m4 = reinterpret_cast<const float4*>(mem_b + (size_t)j * E);
-    float acc = 0.f;
+  // d alpha'_j += d ctx . memory_j   (attention.py:395); one warp per position, two positions in flight
+  {
+    const float4* dc4 = reinterpret_cast<const float4*>(dctx_s);
+    auto dot_row = [&](int j, const float4 (&m)[4]) {
+      float acc = 0.f;
 #pragma unroll
-    for (int q = 0; q < E / 128; ++q) {
-      const float4 mv = __ldg(m4 + lane + 32 * q);
-      const float4 dv = reinterpret_cast<const float4*>(dctx_s)[lane + 32 * q];
-      acc = fmaf(mv.x, dv.x, acc); acc = fmaf(mv.y, dv.y, acc); acc = fmaf(mv.z, dv.z, acc); acc = fmaf(mv.w, dv.w, acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float d = acc + g.dalpha[s][(size_t)b * Ts + j];
-      if (g.d_align[s]) d += g.d_align[s][((size_t)b * p.T + t) * Ts + j];
-      dan_s[j] = d;
+      for (int q = 0; q < 4; ++q) {
+        const float4 dv = dc4[lane + 32 * q];
+        acc = fmaf(m[q].x, dv.x, acc); acc = fmaf(m[q].y, dv.y, acc); acc = fmaf(m[q].z, dv.z, acc); acc = fmaf(m[q].w, dv.w, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) dan_s[j] += acc;
+    };
+    if (warp < Ts) dot_row(warp, mrow[0]);
+    if (warp + kW < Ts) dot_row(warp + kW, mrow[1]);
+    for (int j = warp + 2 * kW; j < Ts; j += 2 * kW) {
+      const int j1 = j + kW;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        mrow[0][q] = __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j * E) + lane + 32 * q);
+        mrow[1][q] = j1 < Ts ? __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j1 * E) + lane + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      dot_row(j, mrow[0]);
+      if (j1 < Ts) dot_row(j1, mrow[1]);
     }
   }
   __syncthreads();
@@ -308,20 +335,34 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
   __syncthreads();
   // e_j = v . tanh(q + pm_j)   (attention.py:340-345); positions >= len have p = 0, hence de = 0
   {
-    const float* pm_b = sp.pm + (size_t)b * Ts * A;
-    float* dpm_b = g.dpm[s] + (size_t)b * Ts * A;
     float dq_acc[4] = {0.f, 0.f, 0.f, 0.f}, dv_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = warp; j < len; j += kW) {
+    float qv[4], vv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { qv[q] = q_s[lane + 32 * q]; vv[q] = v_s[lane + 32 * q]; }
+    auto energy_bw = [&](int j, const float (&pm)[4], const float (&dp)[4]) {
       const float de = de_s[j];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int a = lane + 32 * q;
-        const float u = tanhf(q_s[a] + __ldg(pm_b + (size_t)j * A + a));
-        const float dz = de * v_s[a] * (1.0f - u * u);
+        const float u = lat::fast_tanh(qv[q] + pm[q]);
+        const float dz = de * vv[q] * (1.0f - u * u);
         dq_acc[q] += dz;
         dv_acc[q] = fmaf(de, u, dv_acc[q]);
-        dpm_b[(size_t)j * A + a] += dz;
+        dpm_b[(size_t)j * A + lane + 32 * q] = dp[q] + dz;
       }
+    };
+    if (warp < len) energy_bw(warp, pmr[0], dpr[0]);
+    if (warp + kW < len) energy_bw(warp + kW, pmr[1], dpr[1]);
+    for (int j = warp + 2 * kW; j < len; j += 2 * kW) {
+      const int j1 = j + kW;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        pmr[0][q] = __ldg(pm_b + (size_t)j * A + lane + 32 * q);
+        dpr[0][q] = dpm_b[(size_t)j * A + lane + 32 * q];
+        pmr[1][q] = j1 < len ? __ldg(pm_b + (size_t)j1 * A + lane + 32 * q) : 0.f;
+        dpr[1][q] = j1 < len ? dpm_b[(size_t)j1 * A + lane + 32 * q] : 0.f;
+      }
+      energy_bw(j, pmr[0], dpr[0]);
+      if (j1 < len) energy_bw(j1, pmr[1], dpr[1]);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

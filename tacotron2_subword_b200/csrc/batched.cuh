@@ -228,6 +228,151 @@ __global__ void __launch_bounds__(kThreads, 1) bt_attention(Params p, Bufs bf, c
   }
 }
 
+// Stepwise-monotonic attention specialised for this path (attention.py:330-398): same arithmetic as
+// attention_task<true>, restructured around memory latency -- one CTA sees only ~0.4 MB per frame, so the frame time
+// is the length of its dependent-load chain, not bandwidth.  The first 8 memory rows of every context thread and the
+// first two rounds of processed-memory rows of every energy warp are requested before anything else (neither depends
+// on the query), and the context loop keeps 8 independent 16-byte loads in flight per thread.
+constexpr int kCtxPF = 8;
+__host__ __device__ inline size_t sma_smem_floats(int Ts) { return 2 * (size_t)A + 3 * (size_t)(Ts + 4) + 4 * (size_t)E; }
+
+__global__ void __launch_bounds__(kThreads, 1) bt_attention_sma(Params p, Bufs bf, const int* t_ptr) {
+  extern __shared__ __align__(16) float att_smem[];
+  const int t = *t_ptr;
+  if (p.free_running && __ldcg(p.done_count) >= p.B) return;
+  const int s = blockIdx.x % p.S, b = blockIdx.x / p.S, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const StreamParams& sp = p.st[s];
+  const int Ts = sp.Ts;
+  const int len = sp.len ? (int)sp.len[b] : Ts;
+  float* red_s = att_smem;                 // 4*E context partials (16-byte aligned)
+  float* q_s = red_s + 4 * E;              // A
+  float* v_s = q_s + A;                    // A
+  float* e_s = v_s + A;                    // Ts+4: energies -> selection probabilities
+  float* ap_s = e_s + Ts + 4;              // Ts+4: ap_s[0] = 0, ap_s[1+j] = alpha_j entering the frame
+  float* an_s = ap_s + Ts + 4;             // Ts+4: alpha'_j
+
+  // ---- early requests: context rows (thread = position group jg, float4 column d4) ----
+  const int jg = tid >> 7, d4 = tid & 127;
+  const float4* mem4 = reinterpret_cast<const float4*>(sp.mem + (size_t)b * Ts * E) + d4;
+  float4 pf[kCtxPF];
+#pragma unroll
+  for (int i = 0; i < kCtxPF; ++i) {
+    const int j = jg + 4 * i;
+    pf[i] = j < Ts ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // ---- early requests: processed memory of the warp's first two rounds (4 positions x 4 columns per lane each) ----
+  const float* pm_b = sp.pm + (size_t)b * Ts * A;
+  float pmv[2][4][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      const float* row = pm_b + (size_t)min(warp * 4 + r * (kWarps * 4) + pp, Ts - 1) * A;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pmv[r][pp][c] = __ldg(row + lane + 32 * c);
+    }
+
+  if (tid < A) {
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPLITSQ; ++k) q += bf.gq[(((size_t)s * SPLITSQ + k) * 128 + tid) * bf.NPAD + b];
+    p.q[((size_t)s * p.B + b) * A + tid] = q;
+    if (bf.sv.q) bf.sv.q[(((size_t)t * p.S + s) * p.B + b) * A + tid] = q;
+    q_s[tid] = q;
+    v_s[tid] = sp.v[tid];
+  }
+  for (int j = tid; j < Ts; j += kThreads) ap_s[1 + j] = __ldcg(sp.a_prev + (size_t)b * Ts + j);
+  if (tid == 0) ap_s[0] = 0.f;
+  __syncthreads();
+
+  // ---- energies e_j = v . tanh(q + pm_j), masked (attention.py:340-345, 389) ----
+  {
+    const float q0 = q_s[lane], q1 = q_s[lane + 32], q2 = q_s[lane + 64], q3 = q_s[lane + 96];
+    const float v0 = v_s[lane], v1 = v_s[lane + 32], v2 = v_s[lane + 64], v3 = v_s[lane + 96];
+    auto round_of = [&](int j0, const float (&x)[4][4]) {
+      float e[4];
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp)
+        e[pp] = v0 * lat::fast_tanh(q0 + x[pp][0]) + v1 * lat::fast_tanh(q1 + x[pp][1]) +
+                v2 * lat::fast_tanh(q2 + x[pp][2]) + v3 * lat::fast_tanh(q3 + x[pp][3]);
+      const float ev = lat::butterfly4(e[0], e[1], e[2], e[3], lane);
+      const int j = j0 + (lane >> 3);
+      if ((lane & 7) == 0 && j < Ts) e_s[j] = (j >= len) ? -INFINITY : ev;
+    };
+    if (warp * 4 < Ts) round_of(warp * 4, pmv[0]);
+    if (warp * 4 + kWarps * 4 < Ts) round_of(warp * 4 + kWarps * 4, pmv[1]);
+    for (int j0 = warp * 4 + 2 * kWarps * 4; j0 < Ts; j0 += kWarps * 4) {
+      float x[4][4];
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        const float* row = pm_b + (size_t)min(j0 + pp, Ts - 1) * A;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[pp][c] = __ldg(row + lane + 32 * c);
+      }
+      round_of(j0, x);
+    }
+  }
+  __syncthreads();
+  // ---- p_j = sigmoid(e_j [+ 2 N(0,1)])  (attention.py:346-352) ----
+  for (int j = tid; j < Ts; j += kThreads) {
+    float e = e_s[j];
+    if (p.training) {
+      const size_t ni = ((size_t)t * p.B + b) * Ts + j;
+      const float nz = sp.noise ? sp.noise[ni] : philox_normal(p.seed, 10 + s, t, b * Ts + j);
+      e = e + nz * 2.0f;
+    }
+    const float pj = sigmoidf_(e);
+    e_s[j] = pj;
+    if (sp.p_save) sp.p_save[((size_t)t * p.B + b) * Ts + j] = pj;
+  }
+  __syncthreads();
+  // ---- alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1})  (attention.py:330-338) ----
+  {
+    float* align_out = sp.align + ((size_t)b * p.Tcap + t) * Ts;
+    for (int j = tid; j < Ts; j += kThreads) {
+      float a = ap_s[1 + j] * e_s[j];
+      if (j > 0) a += ap_s[j] * (1.0f - e_s[j - 1]);
+      if (p.free_running && j >= len) a = 0.0f;   // batched free-running: padded positions do not exist
+      an_s[j] = a;
+      sp.a_prev[(size_t)b * Ts + j] = a;
+      align_out[j] = a;
+    }
+  }
+  __syncthreads();
+  // ---- context = alpha' . memory  (attention.py:395) ----
+  {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kCtxPF; ++i) {
+      const int j = jg + 4 * i;
+      const float a = j < Ts ? an_s[j] : 0.f;
+      acc.x = fmaf(a, pf[i].x, acc.x); acc.y = fmaf(a, pf[i].y, acc.y); acc.z = fmaf(a, pf[i].z, acc.z); acc.w = fmaf(a, pf[i].w, acc.w);
+    }
+    for (int jb = jg + 4 * kCtxPF; jb < Ts; jb += 4 * kCtxPF) {
+#pragma unroll
+      for (int i = 0; i < kCtxPF; ++i) {
+        const int j = jb + 4 * i;
+        pf[i] = j < Ts ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < kCtxPF; ++i) {
+        const int j = jb + 4 * i;
+        const float a = j < Ts ? an_s[j] : 0.f;
+        acc.x = fmaf(a, pf[i].x, acc.x); acc.y = fmaf(a, pf[i].y, acc.y); acc.z = fmaf(a, pf[i].z, acc.z); acc.w = fmaf(a, pf[i].w, acc.w);
+      }
+    }
+    reinterpret_cast<float4*>(red_s)[jg * (E / 4) + d4] = acc;
+  }
+  __syncthreads();
+  for (int d = tid; d < E; d += kThreads) {
+    const float c = (red_s[d] + red_s[E + d]) + (red_s[2 * E + d] + red_s[3 * E + d]);
+    p.ctx[((size_t)s * p.B + b) * E + d] = c;
+    if (bf.sv.ctx) bf.sv.ctx[(((size_t)(t + 1) * p.S + s) * p.B + b) * E + d] = c;
+    x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, P + d, c);          // next frame's LSTM-1 input
+    x_store(bf.x2, bf.NPAD, b, s * (H + E) + H + d, c);                                     // this frame's LSTM-2 input
+  }
+}
+
 __global__ void bt_pointwise2(Params p, Bufs bf, const int* t_ptr) {
   const int t = *t_ptr;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -13,7 +13,7 @@
 //   shared-memory descriptor: SBO (next 8-row group) = 128 B, LBO (next 8 K-elements) = rows/8 * 128 B.
 //
 // Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31 -> registers -> global), warp 4 TMA
-// producer, warp 5 TMEM allocation + single-thread MMA issue.  4-stage mbarrier pipeline; every barrier is
+// producer, warp 5 TMEM allocation + single-thread MMA issue.  6/8-stage mbarrier pipeline; every barrier is
 // waited on by exactly one thread that observes every phase in order.
 #pragma once
 
@@ -25,7 +25,8 @@ namespace tc {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // fp16 elements per k-block (8 core matrices of 8)
-constexpr int kStages = 4;
+// pipeline depth: bytes in flight per CTA decide the achieved L2/HBM bandwidth of this bandwidth-bound GEMM
+__host__ __device__ constexpr int stages_for(int npad) { return npad <= 64 ? 8 : 6; }
 constexpr int kThreads = 192;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 
@@ -107,6 +108,7 @@ struct GemmParams {
 template <int NPAD>
 __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmParams p) {
   constexpr int kXTileBytes = NPAD * kBlockK * 2;
+  constexpr int kStages = stages_for(NPAD);
   constexpr int kTmemCols = NPAD < 32 ? 32 : NPAD;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* a_s = smem;                                   // [stages][16 KB]
@@ -215,13 +217,13 @@ __global__ void pack_tiles_kernel(const float* __restrict__ src, int n_rows, int
 
 template <int NPAD>
 inline cudaError_t prepare_gemm() {   // once per process / NPAD (not a stream operation)
-  const size_t smem = (size_t)kStages * (kATileBytes + NPAD * kBlockK * 2);
+  const size_t smem = (size_t)stages_for(NPAD) * (kATileBytes + NPAD * kBlockK * 2);
   return cudaFuncSetAttribute(gemm_f16_tn_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 template <int NPAD>
 inline cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)kStages * (kATileBytes + NPAD * kBlockK * 2);
+  const size_t smem = (size_t)stages_for(NPAD) * (kATileBytes + NPAD * kBlockK * 2);
   dim3 grid(p.M / kBlockM, p.splits, p.groups);
   gemm_f16_tn_kernel<NPAD><<<grid, kThreads, smem, st>>>(p);
   return cudaGetLastError();

@@ -1259,6 +1259,10 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   CUDA_TRY(cudaMemsetAsync(bf.x2, 0, (size_t)(bf.K2 / 64) * NPAD * 128, st));
   bt::bt_init_kernel<<<h->num_sms, 256, 0, st>>>(p, bf);
   CUDA_TRY(cudaFuncSetAttribute(bt::bt_attention<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  int max_ts = 0;
+  for (int s = 0; s < S; ++s) max_ts = std::max(max_ts, p.st[s].Ts);
+  const size_t sma_smem = bt::sma_smem_floats(max_ts) * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(bt::bt_attention_sma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma_smem));
   const int* done = p.free_running ? p.done_count : nullptr;
   tc::GemmParams g1{bf.a1, bf.x1, bf.g1, 4 * bt::H, bt::K1, bt::SPLITS1, S, (long long)(bt::K1 / 64) * NPAD * 128, 0, 0, done, B};
   tc::GemmParams gq{bf.aq, bf.x2, bf.gq, 128, bt::H, bt::SPLITSQ, S, 0, 0, (bt::H + bt::E) / 64, done, B};
@@ -1279,7 +1283,8 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   cudaError_t ce = tc::launch_gemm<NPAD>(g1, cs);
   bt::bt_pointwise1<<<(S * B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
   if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(gq, cs);
-  bt::bt_attention<true><<<S * B, kThreads, att_smem, cs>>>(p, bf, t_ptr);
+  if (p.attention == TACO2DEC_ATTN_SMA) bt::bt_attention_sma<<<S * B, kThreads, sma_smem, cs>>>(p, bf, t_ptr);
+  else bt::bt_attention<true><<<S * B, kThreads, att_smem, cs>>>(p, bf, t_ptr);
   if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(g2, cs);
   bt::bt_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
   if (!hoist_proj) bt::bt_proj<<<((bt::M + 1) * B * 32 + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);

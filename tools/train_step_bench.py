@@ -1,5 +1,7 @@
-"""BASELINE cfg 5: decoder training step (teacher-forced forward + backward) on one GPU, synthetic upstream gradients.
-usage: python tools/train_step_bench.py [B] [T] [--cpu]   (defaults 64 800; --cpu also times the CPU oracle on 16 frames)"""
+"""BASELINE cfg 5: decoder training step (teacher-forced forward + backward [+ gradient all-reduce]) with synthetic
+upstream gradients.  B is per GPU (weak scaling).
+usage: python tools/train_step_bench.py [B] [T] [--cpu]   (defaults 64 800; --cpu also times the CPU oracle on 16 frames)
+       python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/train_step_bench.py"""
 import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,10 +12,17 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 B = int(args[0]) if len(args) > 0 else 64
 T = int(args[1]) if len(args) > 1 else 800
 T_in, T_sub = 160, 53
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
 w = make_decoder_weights(SMA, seed=1234)
 dec = Decoder(create_hparams()); dec.load_state_dict(w); dec = dec.cuda().train()
 dec.decoder_path, dec.weight_dtype = "tensor", "fp16"
-inp = make_inputs(B, T_in, T_sub, T, seed=3, ragged=True)
+if world > 1:
+    import torch.distributed as dist
+    from tacotron2_subword_b200.distributed import apply_gradient_allreduce
+    dist.init_process_group("nccl", init_method="env://")
+    apply_gradient_allreduce(dec)          # broadcast + bucketed all-reduce hooks (distributed.py:132-179)
+inp = make_inputs(B, T_in, T_sub, T, seed=3 + rank, ragged=True)
 mem, emb, mels = inp["memory"].cuda().requires_grad_(True), inp["embeddings"].cuda().requires_grad_(True), inp["mels"].cuda()
 ml, bl = inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda()
 target = torch.randn(B, 80, T, device="cuda")
@@ -26,7 +35,7 @@ def step():
     mel, gate, al, alb = dec(mem, emb, mels, ml, bl)
     loss = torch.nn.functional.mse_loss(mel, target) + torch.nn.functional.binary_cross_entropy_with_logits(gate, torch.zeros_like(gate))
     ev[1].record()
-    loss.backward()
+    loss.backward()       # with world > 1 the bucketed all-reduce runs inside / right after this
     ev[2].record()
     ev[2].synchronize()
     return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), float(loss)
@@ -35,8 +44,20 @@ def step():
 step()
 res = [step() for _ in range(3)]
 fw = min(r[0] for r in res); bw = min(r[1] for r in res)
-out = dict(config=f"cfg5 train step B={B} T={T} {T_in}/{T_sub} SMA train-mode", forward_ms=round(fw, 2), backward_ms=round(bw, 2),
-           step_ms=round(fw + bw, 2), frames_per_s=round(B * T / ((fw + bw) * 1e-3)), us_per_frame_fwd=round(1e3 * fw / T, 1),
+if world > 1:
+    tmax = torch.tensor([fw, bw], device="cuda")
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)       # a step is as slow as its slowest rank
+    fw, bw = float(tmax[0]), float(tmax[1])
+    gsum = torch.stack([p.grad.abs().sum() for p in dec.parameters() if p.grad is not None]).sum()
+    glist = [torch.zeros_like(gsum) for _ in range(world)]
+    dist.all_gather(glist, gsum)
+    assert all(torch.equal(g_, glist[0]) for g_ in glist), "gradients differ across ranks after the all-reduce"
+if rank != 0:
+    dist.destroy_process_group()
+    sys.exit(0)
+out = dict(config=f"cfg5 train step B={B}/GPU T={T} {T_in}/{T_sub} SMA train-mode", n_gpus=world, forward_ms=round(fw, 2),
+           backward_ms=round(bw, 2), step_ms=round(fw + bw, 2), frames_per_s=round(world * B * T / ((fw + bw) * 1e-3)),
+           us_per_frame_fwd=round(1e3 * fw / T, 1),
            us_per_frame_bwd=round(1e3 * bw / T, 1), loss=res[-1][2], peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 2))
 print(json.dumps(out), flush=True)
 
@@ -56,4 +77,6 @@ if "--cpu" in sys.argv:
     print(json.dumps(cpu), flush=True)
     out.update(cpu)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/train_step.json", "w"), indent=1)
+json.dump(out, open(f"gpurun_out/train_step_{world}gpu.json", "w"), indent=1)
+if world > 1:
+    dist.destroy_process_group()
