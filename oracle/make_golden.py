@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 
 from oracle import ref_shim  # noqa: E402
 from oracle.synth import (LSA, SMA, DecoderDims, DropoutPlan, make_decoder_weights,  # noqa: E402
-                          make_dropout_plan, make_inputs, weights_checksum)
+                          make_dropout_plan, make_inputs, weights_checksum, seeded_loss, grad_digest)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
@@ -149,8 +149,55 @@ def run_reference(case: dict, seed: int = None):
     return res
 
 
+# ---------------------------------------------------------------------------------------------------
+# Gradient fixtures: the reference's own autograd (loss.backward() over model.py:392-428) on a seeded loss.
+# Full gradients are ~200 MB, so a fixture keeps per-tensor digests: max|g|, sum(g), a seeded random projection
+# <g, r> and the first 32 elements.  tests/ compare the oracle's autograd (and, on the GPU, the CUDA backward)
+# against the same digests.
+# ---------------------------------------------------------------------------------------------------
+GRAD_CASES = {
+    "grad_sma_train_B16": dict(mode="tf", attention=SMA, B=16, T_in=24, T_sub=8, T=5, ragged=True, training=True, seed=516),
+    "grad_sma_eval_B3": dict(mode="tf", attention=SMA, B=3, T_in=11, T_sub=4, T=4, ragged=True, training=False, seed=33),
+}
+
+
+def run_reference_grads(case: dict, loss_seed: int = 5):
+    """Reference Decoder.forward + autograd for one teacher-forced recipe -> digests of every gradient."""
+    seed = case["seed"]
+    attention = case["attention"]
+    dec, hp = ref_shim.build_reference_decoder(attention)
+    w = make_decoder_weights(attention, seed=seed)
+    dec.load_state_dict(w, strict=True)
+    B, T_in, T_sub, T = case["B"], case["T_in"], case["T_sub"], case["T"]
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=case["ragged"])
+    plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, case["training"], seed=seed + 1)
+    dec.train(case["training"])
+    mem = inp["memory"].clone().requires_grad_(True)
+    emb = inp["embeddings"].clone().requires_grad_(True)
+    with replay(plan, "tf", case["training"], T) as q:
+        outs = dec(mem, emb, inp["mels"], inp["memory_lengths"], inp["bert_lengths"])
+        assert not q, "dropout replay queue not drained"
+    seeded_loss(outs, loss_seed).backward()
+    res = {}
+    for n, p_ in dec.named_parameters():
+        if p_.grad is None:
+            res[n + "/none"] = np.array(1)
+        else:
+            res.update(grad_digest(n, p_.grad))
+    res.update(grad_digest("memory", mem.grad))
+    res.update(grad_digest("embeddings", emb.grad))
+    res["recipe"] = np.array(json.dumps(dict(case, loss_seed=loss_seed)))
+    res["weights_checksum"] = np.array(weights_checksum(w))
+    return res
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, case in GRAD_CASES.items():
+        res = run_reference_grads(case)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **res)
+        print(f"{name}: {sum(1 for k in res if k.endswith('/max'))} gradient digests -> {os.path.getsize(path)//1024} KiB")
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     for name, case in CASES.items():
         res = run_reference(case)

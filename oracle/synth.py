@@ -19,6 +19,7 @@ import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 
 SMA = "StepwiseMonotonicAttention"
@@ -184,3 +185,24 @@ def make_dropout_plan(B: int, T_p: int, T: int, T_in: int, T_sub: int, training:
         lstm_keep = (r >= p).to(torch.uint8)
         noise = [torch.randn(T, B, L, generator=g) for L in ((T_in, T_sub)[:dims.streams])]
     return DropoutPlan(prenet_keep=prenet_keep, lstm_keep=lstm_keep, sma_noise=noise)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Gradient parity plumbing shared by oracle/make_golden.py and tests/ (no reference import needed)
+# ---------------------------------------------------------------------------------------------------
+def seeded_loss(outs, seed: int):
+    """sum_o <o, N(0,1)> over (mel, gate, align, align_bert) with a CPU generator -- identical for every implementation."""
+    g = torch.Generator().manual_seed(seed)
+    total = 0.0
+    for o in outs:
+        if o is None:
+            continue
+        total = total + (o * torch.randn(o.shape, generator=g).to(o.device)).sum()
+    return total
+
+
+def grad_digest(name: str, g: torch.Tensor) -> dict:
+    g = g.detach().to("cpu", torch.float64).reshape(-1)
+    r = torch.randn(g.numel(), generator=torch.Generator().manual_seed(len(name) * 7919 + g.numel()), dtype=torch.float64)
+    return {name + "/max": np.array(float(g.abs().max())), name + "/sum": np.array(float(g.sum())),
+            name + "/proj": np.array(float((g * r).sum() / np.sqrt(g.numel()))), name + "/head": g[:32].numpy().copy()}

@@ -14,7 +14,42 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("grad_"))
+
+
+def grad_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("grad_"))
+
+
+def load_grad_golden(name: str):
+    """(recipe, {tensor name: digest dict or None for parameters the reference leaves without gradient})."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    recipe = json.loads(str(z["recipe"]))
+    digests = {}
+    for k in z.files:
+        if "/" not in k:
+            continue
+        n, field = k.rsplit("/", 1)
+        if field == "none":
+            digests[n] = None
+        else:
+            digests.setdefault(n, {})[field] = z[k]
+    return recipe, digests, str(z["weights_checksum"])
+
+
+def check_grad_digest(name: str, g: torch.Tensor, want: dict, rtol: float) -> float:
+    """Compare a gradient with a reference digest; every field is held to rtol * max|g_ref|.  Returns the worst ratio."""
+    from oracle.synth import grad_digest
+    got = grad_digest(name, g)
+    scale = float(want["max"])
+    n = g.numel()
+    errs = [abs(float(got[name + "/max"]) - scale) / scale,
+            abs(float(got[name + "/proj"]) - float(want["proj"])) / scale,            # projection is normalised by sqrt(n)
+            abs(float(got[name + "/sum"]) - float(want["sum"])) / (scale * max(1.0, n ** 0.5)),
+            float(np.abs(got[name + "/head"] - want["head"]).max()) / scale]
+    worst = max(errs)
+    assert worst <= rtol, f"{name}: gradient digest off by {worst:.2e} of max|g| (fields max/proj/sum/head: {errs})"
+    return worst
 
 
 def load_golden(name: str):

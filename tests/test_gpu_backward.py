@@ -175,3 +175,30 @@ def test_model_training_step_end_to_end():
     loss1 = loss_of(model(x))
     assert torch.isfinite(loss1)
     assert float(loss1.detach()) < float(loss0.detach())       # same dropout seed, small SGD step: the loss goes down
+
+
+def test_backward_vs_reference_gradient_digests():
+    """CUDA backward against digests of the REFERENCE's own autograd (tests/golden/grad_sma_train_B16.npz, made by
+    oracle/make_golden.py from the unmodified reference): max|g|, a seeded random projection, the sum and the first 32
+    elements of every gradient tensor, each within TOL_GRAD of max|g_ref|."""
+    from oracle.synth import seeded_loss
+    from tests.helpers import check_grad_digest, load_grad_golden, materialise
+    recipe, digests, _ = load_grad_golden("grad_sma_train_B16")
+    w, inp, plan = materialise(recipe)
+    dec = make_decoder(w, SMA)
+    dec.decoder_path, dec.weight_dtype = "tensor", "fp16"
+    dec.dropout_replay = replay_of(plan)
+    dec.train(recipe["training"])
+    mem = inp["memory"].cuda().requires_grad_(True)
+    emb = inp["embeddings"].cuda().requires_grad_(True)
+    outs = dec(mem, emb, inp["mels"].cuda(), inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+    seeded_loss(outs, recipe["loss_seed"]).backward()
+    grads = {n: p.grad for n, p in dec.named_parameters()}
+    grads["memory"], grads["embeddings"] = mem.grad, emb.grad
+    worst = {}
+    for n, want in digests.items():
+        if want is None:
+            assert grads[n] is None, n
+        else:
+            worst[n] = check_grad_digest(n, grads[n], want, rtol=TOL_GRAD)
+    print({k: f"{v:.1e}" for k, v in worst.items()})
