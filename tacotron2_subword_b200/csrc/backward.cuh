@@ -58,6 +58,8 @@ struct Grads {
   float* dpm[2];   // [B][Ts][A]     d processed_memory
   float* dalpha[2];// [B][Ts]        carry: d alignment state
   float *dc1, *dc2;// [S][B][H], [B][H] carry: d cell state
+  float* dyh;      // [T][H][B]      projection backwards, decoder-LSTM hidden columns   (bw_dy_all)
+  float* dyc;      // [T][B][S*E]    projection backwards, context columns
 };
 
 __device__ __forceinline__ void xb_store(unsigned char* xbase, int NPAD, int b, int k, float v) {
@@ -100,23 +102,58 @@ __device__ __forceinline__ void lstm_cell_backward(const float* sv, size_t gs, f
 // one 16-byte bf16 core-matrix row of the GEMM operand tile and 32 contiguous bytes of the fp32 gradient rows.
 constexpr int kPwB = 32, kPwJ = 8;
 
-// d(mel, gate) of the block's utterances at frame t -> shared memory [32][M+1] (odd stride: conflict-free per lane)
-__device__ __forceinline__ void stage_dout(const Params& p, const Grads& g, int t, int b0, float (*dm_s)[M + 1]) {
-  for (int i = threadIdx.x; i < kPwB * (M + 1); i += blockDim.x) {
-    const int bb = i / (M + 1), r = i - bb * (M + 1), b = b0 + bb;
+// Projection backwards for ALL frames before the loop (model.py:382-388):
+//   dY[(t,b)][k] = sum_row dmel[b][t][row] Wp[row][k] + dgate[b][t] wg[k]
+// K is only 81, so this is an output-bound pass: block = 64 (t,b) rows x 64 columns, thread = 8 rows x 2 columns.
+// The decoder-LSTM columns are written [t][unit][b] and the context columns [t][b][column]: the layouts in which the
+// frame loop's kernels read them coalesced.
+constexpr int kDyRows = 64, kDyCols = 64;
+__global__ void __launch_bounds__(256) bw_dy_all(Params p, Grads g) {
+  __shared__ float dm_s[kDyRows][M + 2];
+  __shared__ float w_s[M + 1][kDyCols];
+  const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
+  const int KD = H + p.S * E, R = p.T * p.B;
+  const int r0 = blockIdx.x * kDyRows, c0 = blockIdx.y * kDyCols;
+  for (int i = tid; i < kDyRows * (M + 1); i += 256) {
+    const int rl = i / (M + 1), k = i - rl * (M + 1), r = r0 + rl;
     float v = 0.f;
-    if (b < p.B) v = r < M ? g.d_mel[((size_t)b * p.T + t) * M + r] : g.d_gate[(size_t)b * p.T + t];
-    dm_s[bb][r] = v;
+    if (r < R) {
+      const int t = r / p.B, b = r - t * p.B;
+      v = k < M ? g.d_mel[((size_t)b * p.T + t) * M + k] : g.d_gate[(size_t)b * p.T + t];
+    }
+    dm_s[rl][k] = v;
+  }
+  for (int i = tid; i < (M + 1) * kDyCols; i += 256) {
+    const int k = i / kDyCols, c = i - k * kDyCols;
+    w_s[k][c] = k < M ? __ldg(p.proj_w + (size_t)k * KD + c0 + c) : __ldg(p.gate_w + c0 + c);
+  }
+  __syncthreads();
+  float acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = 0.f; }
+#pragma unroll 3
+  for (int k = 0; k <= M; ++k) {
+    const float w0 = w_s[k][lane], w1 = w_s[k][lane + 32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = dm_s[rg * 8 + i][k];
+      acc[i][0] = fmaf(d, w0, acc[i][0]); acc[i][1] = fmaf(d, w1, acc[i][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + rg * 8 + i;
+    if (r >= R) continue;
+    const int t = r / p.B, b = r - t * p.B;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = c0 + lane + 32 * q;
+      if (c < H) g.dyh[((size_t)t * H + c) * p.B + b] = acc[i][q];
+      else g.dyc[((size_t)t * p.B + b) * (p.S * E) + (c - H)] = acc[i][q];
+    }
   }
 }
-// projection backwards for input column k (model.py:382-388): sum_row dmel[row] Wp[row][k] + dgate wg[k]
-__device__ __forceinline__ float proj_backward_col(const Params& p, const float* dm_row, int k) {
-  const int KD = H + p.S * E;
-  float acc = dm_row[M] * __ldg(p.gate_w + k);
-#pragma unroll 8
-  for (int r = 0; r < M; ++r) acc = fmaf(dm_row[r], __ldg(p.proj_w + (size_t)r * KD + k), acc);
-  return acc;
-}
+
 // gate gradients of the block -> bf16 operand tile + fp32 rows [.., b, G]
 __device__ __forceinline__ void store_gate_grads(const float (*out_s)[kPwB][kPwJ + 1], int NPAD, int B, int b0, int j0,
                                                  unsigned char* tiles, float* rows /* + t*B*G */) {
@@ -140,21 +177,19 @@ __device__ __forceinline__ void store_gate_grads(const float (*out_s)[kPwB][kPwJ
 }
 
 __global__ void __launch_bounds__(256) bw_pointwise2(Params p, Bufs bb, Grads g, const int* t_ptr) {
-  __shared__ float dm_s[kPwB][M + 1];
   __shared__ float out_s[4][kPwB][kPwJ + 1];
   const int t = *t_ptr;
   const int nbt = (p.B + kPwB - 1) / kPwB;
   const int b0 = (blockIdx.x % nbt) * kPwB, j0 = (blockIdx.x / nbt) * kPwJ;
   const int bl = threadIdx.x & 31, jl = threadIdx.x >> 5, b = b0 + bl, j = j0 + jl;
-  stage_dout(p, g, t, b0, dm_s);
-  __syncthreads();
   if (b < p.B) {
     const size_t idx = (size_t)b * H + j;
-    float dh = proj_backward_col(p, dm_s[bl], j);
+    float dh = g.dyh[((size_t)t * H + j) * p.B + b];
 #pragma unroll
     for (int k = 0; k < SPLITSB2; ++k) dh += bb.dx2[((size_t)k * bb.K2 + p.S * (H + E) + j) * bb.NPAD + b];
     const size_t gs = (size_t)H * p.B;
     const float* sv = g.sv.gates2 + ((size_t)t * 5 * H + j) * p.B + b;
+    const float cn_prev = t > 0 ? (sv - 5 * gs)[4 * gs] : 0.f;
     float mh = 1.f, mc = 1.f, mc_prev = 1.f;
     if (p.training) {
       const float sc = 1.0f / (1.0f - p.p_dec);
@@ -167,9 +202,8 @@ __global__ void __launch_bounds__(256) bw_pointwise2(Params p, Bufs bb, Grads g,
         mc_prev = keep_mult(kcp, idx, p.seed, 9, t - 1, (int)idx, p.thresh_dec, sc);
       }
     }
-    const float c_prev = t > 0 ? mc_prev * (sv - 5 * gs)[4 * gs] : 0.f;
     float dgate[4];
-    lstm_cell_backward(sv, gs, c_prev, mh, mc, dh, g.dc2 + idx, dgate);
+    lstm_cell_backward(sv, gs, mc_prev * cn_prev, mh, mc, dh, g.dc2 + idx, dgate);
 #pragma unroll
     for (int q = 0; q < 4; ++q) out_s[q][bl][jl] = dgate[q];
   }
@@ -179,36 +213,42 @@ __global__ void __launch_bounds__(256) bw_pointwise2(Params p, Bufs bb, Grads g,
 
 __global__ void __launch_bounds__(256) bw_pointwise1(Params p, Bufs bb, Grads g, const int* t_ptr) {
   __shared__ float dq_s[A][kPwB + 1];
+  __shared__ float wq_s[A][kPwJ];
   __shared__ float out_s[4][kPwB][kPwJ + 1];
   const int t = *t_ptr;
   const int nbt = (p.B + kPwB - 1) / kPwB, njt = H / kPwJ;
   const int s = blockIdx.x / (nbt * njt), rem = blockIdx.x - s * nbt * njt;
   const int b0 = (rem % nbt) * kPwB, j0 = (rem / nbt) * kPwJ;
   const int bl = threadIdx.x & 31, jl = threadIdx.x >> 5, b = b0 + bl, j = j0 + jl;
+  // query layer operands of the block: dq of its 32 utterances, Wq columns of its 8 units (attention.py:56, 368)
   for (int i = threadIdx.x; i < kPwB * A; i += blockDim.x) {
     const int bb_ = i / A, a = i - bb_ * A;
     dq_s[a][bb_] = (b0 + bb_ < p.B) ? g.dq[(((size_t)s * p.T + t) * p.B + b0 + bb_) * A + a] : 0.f;
   }
-  __syncthreads();
+  for (int i = threadIdx.x; i < A * kPwJ; i += blockDim.x) {
+    const int a = i / kPwJ, jj = i - a * kPwJ;
+    wq_s[a][jj] = __ldg(p.st[s].wq + (size_t)a * H + j0 + jj);
+  }
+  float dh = 0.f, cn_prev = 0.f;
+  const size_t gs = (size_t)H * p.B;
+  const size_t idx = (size_t)min(b, p.B - 1) * H + j;
+  const float* sv = g.sv.gates1 + (((size_t)t * p.S + s) * 5 * H + j) * p.B + min(b, p.B - 1);
   if (b < p.B) {
-    const size_t idx = (size_t)b * H + j;
-    float dh = 0.f;
 #pragma unroll
     for (int k = 0; k < SPLITSB1; ++k) dh += bb.dx1[(((size_t)s * SPLITSB1 + k) * K1 + P + E + j) * bb.NPAD + b];
 #pragma unroll
     for (int k = 0; k < SPLITSB2; ++k) dh += bb.dx2[((size_t)k * bb.K2 + s * (H + E) + j) * bb.NPAD + b];
-    {  // query layer: dh1 += Wq^T dq  (attention.py:56, 368)
-      const float* wq = p.st[s].wq + j;
-      float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 8
-      for (int a = 0; a < A; a += 2) {
-        acc0 = fmaf(dq_s[a][bl], __ldg(wq + (size_t)a * H), acc0);
-        acc1 = fmaf(dq_s[a + 1][bl], __ldg(wq + (size_t)(a + 1) * H), acc1);
-      }
-      dh += acc0 + acc1;
+    if (t > 0) cn_prev = (sv - (size_t)p.S * 5 * gs)[4 * gs];
+  }
+  __syncthreads();
+  if (b < p.B) {
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 16
+    for (int a = 0; a < A; a += 2) {
+      acc0 = fmaf(dq_s[a][bl], wq_s[a][jl], acc0);
+      acc1 = fmaf(dq_s[a + 1][bl], wq_s[a + 1][jl], acc1);
     }
-    const size_t gs = (size_t)H * p.B;
-    const float* sv = g.sv.gates1 + (((size_t)t * p.S + s) * 5 * H + j) * p.B + b;
+    dh += acc0 + acc1;
     float mh = 1.f, mc = 1.f, mc_prev = 1.f;
     if (p.training) {
       const float sc = 1.0f / (1.0f - p.p_att);
@@ -221,9 +261,8 @@ __global__ void __launch_bounds__(256) bw_pointwise1(Params p, Bufs bb, Grads g,
         mc_prev = keep_mult(kcp, idx, p.seed, 5 + 2 * s, t - 1, (int)idx, p.thresh_att, sc);
       }
     }
-    const float c_prev = t > 0 ? mc_prev * (sv - (size_t)p.S * 5 * gs)[4 * gs] : 0.f;
     float dgate[4];
-    lstm_cell_backward(sv, gs, c_prev, mh, mc, dh, g.dc1 + (size_t)s * p.B * H + idx, dgate);
+    lstm_cell_backward(sv, gs, mc_prev * cn_prev, mh, mc, dh, g.dc1 + (size_t)s * p.B * H + idx, dgate);
 #pragma unroll
     for (int q = 0; q < 4; ++q) out_s[q][bl][jl] = dgate[q];
   }
@@ -253,7 +292,6 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
   float* ap_s = p_s + Ts + 4;         // Ts+4   alignment state entering frame t
   float* dan_s = ap_s + Ts + 4;       // Ts+4   d alpha'[t]
   float* de_s = dan_s + Ts + 4;       // Ts+4
-  float* dm_s = de_s + Ts + 4;        // M+1
 
   // ---- early requests: nothing below depends on the incoming gradients, so these loads overlap the d ctx chain ----
   const float* mem_b = sp.mem + (size_t)b * Ts * E;
@@ -271,8 +309,6 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
       dpr[r][q] = j < len ? dpm_b[(size_t)j * A + lane + 32 * q] : 0.f;
     }
   }
-  for (int r = tid; r <= M; r += kBwThreads)
-    dm_s[r] = r < M ? g.d_mel[((size_t)b * p.T + t) * M + r] : g.d_gate[(size_t)b * p.T + t];
   for (int a = tid; a < A; a += kBwThreads) {
     q_s[a] = g.sv.q[(((size_t)t * p.S + s) * p.B + b) * A + a];
     v_s[a] = sp.v[a];
@@ -289,7 +325,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
   __syncthreads();
   // d ctx[t] = next frame's attention-LSTM input gradient + this frame's decoder-LSTM input and projection gradients
   for (int d = tid; d < E; d += kBwThreads) {
-    float acc = proj_backward_col(p, dm_s, H + s * E + d);
+    float acc = g.dyc[((size_t)t * p.B + b) * (p.S * E) + s * E + d];
 #pragma unroll
     for (int k = 0; k < SPLITSB1; ++k) acc += bb.dx1[(((size_t)s * SPLITSB1 + k) * K1 + P + d) * bb.NPAD + b];
 #pragma unroll

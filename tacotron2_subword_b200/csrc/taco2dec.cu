@@ -1353,7 +1353,7 @@ taco2dec_saved_layout plan_saved(const taco2dec_config& c, int B, int T_in, int 
   return L;
 }
 
-struct GradScratch { size_t dalpha[2], dc1, dc2, zero_begin, zero_end; };
+struct GradScratch { size_t dalpha[2], dc1, dc2, zero_begin, zero_end, dyh, dyc; };
 
 taco2dec_grad_layout plan_grads(const taco2dec_config& c, int B, int T_in, int T_sub, int T, GradScratch* gs) {
   taco2dec_grad_layout L;
@@ -1378,6 +1378,8 @@ taco2dec_grad_layout plan_grads(const taco2dec_config& c, int B, int T_in, int T
   g.dc2 = take((size_t)B * D);
   g.zero_begin = zero_begin;
   g.zero_end = off;
+  g.dyh = take((size_t)T * D * B);
+  g.dyc = take((size_t)T * B * S * c.enc_dim);
   L.total = off;
   if (gs) *gs = g;
   return L;
@@ -1429,6 +1431,7 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
   CUDA_TRY(cudaMemsetAsync(bb.dx2, 0, (size_t)bw::SPLITSB2 * bb.K2 * NPAD * sizeof(float), st));
   int* t_ptr = h->bw_ctl;
   set_int_kernel<<<1, 1, 0, st>>>(t_ptr, p.T - 1);
+  bw::bw_dy_all<<<dim3((p.T * B + bw::kDyRows - 1) / bw::kDyRows, (bt::H + S * bt::E) / bw::kDyCols), 256, 0, st>>>(p, g);
   int max_ts = 0;
   for (int s = 0; s < S; ++s) max_ts = std::max(max_ts, p.st[s].Ts);
   const size_t att_smem = bw::bw_attention_smem_floats(max_ts) * sizeof(float);
@@ -1464,7 +1467,7 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
       return fail(TACO2DEC_E_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
     }
   }
-  h->launches += 7LL * p.T + 1;
+  h->launches += 7LL * p.T + 2;
   cudaGraphExecDestroy(exec);
   cudaGraphDestroy(graph);
   CUDA_TRY(cudaGetLastError());
@@ -1809,6 +1812,7 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
   g.dg1 = (float*)(gb + GL.dg1); g.dg2 = (float*)(gb + GL.dg2); g.dq = (float*)(gb + GL.dq);
   g.dctx = (float*)(gb + GL.dctx); g.dpre = (float*)(gb + GL.dpre); g.dv = (float*)(gb + GL.dv);
   g.dc1 = (float*)(gb + gs.dc1); g.dc2 = (float*)(gb + gs.dc2);
+  g.dyh = (float*)(gb + gs.dyh); g.dyc = (float*)(gb + gs.dyc);
   CUDA_TRY(cudaMemsetAsync(gb + gs.zero_begin, 0, gs.zero_end - gs.zero_begin, st));
   h->last_abort_flag = nullptr;
   if (int rc = bw_prepare(h, st)) return rc;
