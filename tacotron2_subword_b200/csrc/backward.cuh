@@ -11,7 +11,7 @@
 //                                                                                     (attention.py:330-398)
 //   bw_pointwise1   dh1[t] (frame t+1's GEMM + dX2 + Wq^T dq) -> attention-LSTM gate gradients dG1[t]
 //   GEMM            dX1 = [W_ih | W_hh]^T . dG1^T          tcgen05                           (model.py:337-346)
-//   bw_save_dpre    d prenet[t] out of dX1
+// (d prenet[t], rows of dX1, is saved by the next frame's first kernel; the frame counter is moved by bw_pointwise1.)
 //
 // Everything that is a plain sum over (frame, utterance) -- all weight gradients, d memory, the hoisted prenet -- is
 // left as saved per-frame gradient rows (dG1, dG2, dq, d ctx, d prenet) that the host wrapper contracts with the saved
@@ -176,12 +176,25 @@ __device__ __forceinline__ void store_gate_grads(const float (*out_s)[kPwB][kPwJ
   }
 }
 
-__global__ void __launch_bounds__(256) bw_pointwise2(Params p, Bufs bb, Grads g, const int* t_ptr) {
+// d prenet[t] = rows [0, P) of dX1[t] (sum of the split-K partials)
+__device__ __forceinline__ void save_dpre(const Params& p, const Bufs& bb, const Grads& g, int t, int s, int k, int b) {
+  float acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < SPLITSB1; ++q) acc += bb.dx1[(((size_t)s * SPLITSB1 + q) * K1 + k) * bb.NPAD + b];
+  g.dpre[(((size_t)s * p.T + t) * p.B + b) * P + k] = acc;
+}
+
+// First kernel of a backward frame.  Besides the decoder-LSTM cell it copies the frame index to t_ptr[1] (read by
+// bw_pointwise1, which then moves t_ptr[0] to t-1) and saves d prenet[t+1] out of the previous frame's dX1 before this
+// frame's GEMM overwrites it, so the frame needs no separate save / counter kernels.
+__global__ void __launch_bounds__(256) bw_pointwise2(Params p, Bufs bb, Grads g, int* t_ptr) {
   __shared__ float out_s[4][kPwB][kPwJ + 1];
   const int t = *t_ptr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) t_ptr[1] = t;
   const int nbt = (p.B + kPwB - 1) / kPwB;
   const int b0 = (blockIdx.x % nbt) * kPwB, j0 = (blockIdx.x / nbt) * kPwJ;
   const int bl = threadIdx.x & 31, jl = threadIdx.x >> 5, b = b0 + bl, j = j0 + jl;
+  if (b < p.B && j < p.S * P && t + 1 < p.T) save_dpre(p, bb, g, t + 1, j / P, j % P, b);
   if (b < p.B) {
     const size_t idx = (size_t)b * H + j;
     float dh = g.dyh[((size_t)t * H + j) * p.B + b];
@@ -211,11 +224,12 @@ __global__ void __launch_bounds__(256) bw_pointwise2(Params p, Bufs bb, Grads g,
   store_gate_grads(out_s, bb.NPAD, p.B, b0, j0, bb.dg2, g.dg2 + (size_t)t * p.B * G);
 }
 
-__global__ void __launch_bounds__(256) bw_pointwise1(Params p, Bufs bb, Grads g, const int* t_ptr) {
+__global__ void __launch_bounds__(256) bw_pointwise1(Params p, Bufs bb, Grads g, int* t_ptr) {
   __shared__ float dq_s[A][kPwB + 1];
   __shared__ float wq_s[A][kPwJ];
   __shared__ float out_s[4][kPwB][kPwJ + 1];
-  const int t = *t_ptr;
+  const int t = t_ptr[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) t_ptr[0] = t - 1;   // last t-dependent kernel of the frame; nobody reads t_ptr[0] until the next frame
   const int nbt = (p.B + kPwB - 1) / kPwB, njt = H / kPwJ;
   const int s = blockIdx.x / (nbt * njt), rem = blockIdx.x - s * nbt * njt;
   const int b0 = (rem % nbt) * kPwB, j0 = (rem / nbt) * kPwJ;
@@ -413,17 +427,12 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
   }
 }
 
-__global__ void bw_save_dpre(Params p, Bufs bb, Grads g, const int* t_ptr) {
-  const int t = *t_ptr;
+// after the loop: d prenet[0] is still in dX1
+__global__ void bw_save_dpre0(Params p, Bufs bb, Grads g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.S * p.B * P) return;
   const int s = i / (p.B * P), r = i - s * p.B * P, k = r / p.B, b = r - k * p.B;
-  float acc = 0.f;
-#pragma unroll
-  for (int q = 0; q < SPLITSB1; ++q) acc += bb.dx1[(((size_t)s * SPLITSB1 + q) * K1 + k) * bb.NPAD + b];
-  g.dpre[(((size_t)s * p.T + t) * p.B + b) * P + k] = acc;
+  save_dpre(p, bb, g, 0, s, k, b);
 }
-
-__global__ void bw_retreat(int* t_ptr) { *t_ptr -= 1; }
 
 }  // namespace bw

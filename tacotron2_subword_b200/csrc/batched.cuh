@@ -167,13 +167,19 @@ __global__ void __launch_bounds__(1024) bt_prenet_fr(Params p, Bufs bf, const in
 }
 
 // attention-LSTM pointwise: sums the split-K partials, gate order i,f,g,o (nn.LSTMCell), dropout on h and c
-__global__ void bt_pointwise1(Params p, Bufs bf, const int* t_ptr) {
+// tf_merge (teacher-forced frames): this kernel also (a) copies the frame index to t_ptr[1] for bt_pointwise2, which
+// then advances t_ptr[0] itself, and (b) moves the hoisted prenet output of frame t+1 into X1 -- GEMM 1 of frame t has
+// already consumed X1 -- so the frame needs neither a prenet-copy nor a counter kernel.
+__global__ void bt_pointwise1(Params p, Bufs bf, int* t_ptr, int tf_merge) {
   const int t = *t_ptr;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tf_merge && i == 0) t_ptr[1] = t;
   if (i >= p.S * p.B * H) return;
   if (p.free_running && __ldcg(p.done_count) >= p.B) return;
   const int s = i / (p.B * H), r = i - s * p.B * H, j = r / p.B, b = r - j * p.B;   // b fastest: coalesced partial reads
   const StreamParams& sp = p.st[s];
+  if (tf_merge && j < P && t + 1 < p.T)
+    x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, j, sp.pre[((size_t)(t + 1) * p.B + b) * P + j]);
   float pre[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -373,9 +379,10 @@ __global__ void __launch_bounds__(kThreads, 1) bt_attention_sma(Params p, Bufs b
   }
 }
 
-__global__ void bt_pointwise2(Params p, Bufs bf, const int* t_ptr) {
-  const int t = *t_ptr;
+__global__ void bt_pointwise2(Params p, Bufs bf, int* t_ptr, int tf_merge) {
+  const int t = tf_merge ? t_ptr[1] : t_ptr[0];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tf_merge && i == 0) t_ptr[0] = t + 1;     // last kernel of a teacher-forced frame; its other blocks read t_ptr[1]
   if (i >= p.B * H) return;
   if (p.free_running && __ldcg(p.done_count) >= p.B) return;
   const int j = i / p.B, b = i - j * p.B;

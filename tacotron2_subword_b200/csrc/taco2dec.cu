@@ -1278,17 +1278,24 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+  if (hoist_proj) {   // frame 0's prenet rows; later frames get theirs from bt_pointwise1 of the frame before
+    bt::bt_prenet_tf_to_x1<<<(S * B * bt::P + 255) / 256, 256, 0, st>>>(p, bf, t_ptr);
+    h->launches++;
+  }
+  // teacher-forced + hoisted projection: 6 kernels per frame (the LSTM pointwise kernels also move the prenet rows and
+  // the frame counter); otherwise 9
+  const int tf_merge = hoist_proj ? 1 : 0;
   if (p.free_running) bt::bt_prenet_fr<<<S * ((B + bt::kPreBT - 1) / bt::kPreBT), 1024, 0, cs>>>(p, bf, t_ptr);
-  else bt::bt_prenet_tf_to_x1<<<(S * B * bt::P + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
+  else if (!tf_merge) bt::bt_prenet_tf_to_x1<<<(S * B * bt::P + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
   cudaError_t ce = tc::launch_gemm<NPAD>(g1, cs);
-  bt::bt_pointwise1<<<(S * B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
+  bt::bt_pointwise1<<<(S * B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr, tf_merge);
   if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(gq, cs);
   if (p.attention == TACO2DEC_ATTN_SMA) bt::bt_attention_sma<<<S * B, kThreads, sma_smem, cs>>>(p, bf, t_ptr);
   else bt::bt_attention<true><<<S * B, kThreads, att_smem, cs>>>(p, bf, t_ptr);
   if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(g2, cs);
-  bt::bt_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
+  bt::bt_pointwise2<<<(B * bt::H + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr, tf_merge);
   if (!hoist_proj) bt::bt_proj<<<((bt::M + 1) * B * 32 + 255) / 256, 256, 0, cs>>>(p, bf, t_ptr);
-  bt::bt_advance<<<1, 1, 0, cs>>>(t_ptr);
+  if (!tf_merge) bt::bt_advance<<<1, 1, 0, cs>>>(t_ptr);
   const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
   if (ce != cudaSuccess || ee != cudaSuccess || graph == nullptr) {
     if (graph) cudaGraphDestroy(graph);
@@ -1303,7 +1310,7 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
       return fail(TACO2DEC_E_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
     }
   }
-  h->launches += (hoist_proj ? 8LL : 9LL) * n_steps;
+  h->launches += (hoist_proj ? 6LL : 9LL) * n_steps;
   // the executable graph may be destroyed once its launches are enqueued; CUDA keeps it alive until they finish
   cudaGraphExecDestroy(exec);
   cudaGraphDestroy(graph);
@@ -1451,8 +1458,6 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
   bw::bw_attention<<<S * B, bw::kBwThreads, att_smem, cs>>>(p, bb, g, t_ptr);
   bw::bw_pointwise1<<<S * pw_blocks, 256, 0, cs>>>(p, bb, g, t_ptr);
   if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(gb1, cs);
-  bw::bw_save_dpre<<<(S * B * bt::P + 255) / 256, 256, 0, cs>>>(p, bb, g, t_ptr);
-  bw::bw_retreat<<<1, 1, 0, cs>>>(t_ptr);
   const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
   if (ce != cudaSuccess || ee != cudaSuccess || graph == nullptr) {
     if (graph) cudaGraphDestroy(graph);
@@ -1467,9 +1472,10 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
       return fail(TACO2DEC_E_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
     }
   }
-  h->launches += 7LL * p.T + 2;
+  h->launches += 5LL * p.T + 3;
   cudaGraphExecDestroy(exec);
   cudaGraphDestroy(graph);
+  bw::bw_save_dpre0<<<(S * B * bt::P + 255) / 256, 256, 0, st>>>(p, bb, g);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
