@@ -103,22 +103,33 @@ struct GemmParams {
   const int* done;                // optional early-exit: skip when *done >= done_target (free-running decode)
   int done_target;
   uint32_t fmt;                   // operand formats OR-ed into the instruction descriptor (kFmtF16 / kFmtBF16)
+  int stages;                     // 0 = stages_for(NPAD); experiments may ask for fewer
+  unsigned long long* dbg;        // optional [CTAs][8] globaltimer stamps (ns): entry, setup done, first tile landed,
+                                  // accumulator complete, epilogue stored, exit
 };
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <int NPAD>
 __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmParams p) {
   constexpr int kXTileBytes = NPAD * kBlockK * 2;
-  constexpr int kStages = stages_for(NPAD);
+  constexpr int kMaxStages = stages_for(NPAD);
+  const int kStages = (p.stages > 0 && p.stages < kMaxStages) ? p.stages : kMaxStages;
   constexpr int kTmemCols = NPAD < 32 ? 32 : NPAD;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* a_s = smem;                                   // [stages][16 KB]
   unsigned char* x_s = smem + kStages * kATileBytes;           // [stages][NPAD*128]
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
 
   if (p.done != nullptr && __ldcg(p.done) >= p.done_target) return;   // uniform: nothing in this launch changes it
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, split = blockIdx.y, group = blockIdx.z;
+  unsigned long long* dbg = p.dbg ? p.dbg + ((size_t)(group * gridDim.y + split) * gridDim.x + mt) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
   const int m_tiles = p.M / kBlockM, kb_total = p.K / kBlockK, kb_per_split = kb_total / p.splits;
   const int kb0 = split * kb_per_split;
 
@@ -135,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
 
   if (warp == 4) {
     // ===== TMA producer =====
@@ -158,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
       for (int i = 0; i < kb_per_split; ++i) {
         const int s = i % kStages;
         mbar_wait(&full_bar[s], (uint32_t)((i / kStages) & 1));
+        if (dbg && i == 0) dbg[2] = gtime_ns();
         tc_fence_after();
         const uint32_t a_addr = smem_u32(a_s + (size_t)s * kATileBytes);
         const uint32_t x_addr = smem_u32(x_s + (size_t)s * kXTileBytes);
@@ -174,6 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
   } else {
     // ===== epilogue: warps 0-3 own TMEM lanes 32w .. 32w+31 (= output rows) =====
     mbar_wait(&tmem_full_bar, 0);
+    if (dbg && threadIdx.x == 0) dbg[3] = gtime_ns();
     tc_fence_after();
     const int row = mt * kBlockM + warp * 32 + lane;
     float* dst = p.out + (((size_t)group * p.splits + split) * p.M + row) * NPAD;
@@ -193,8 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
                                                               __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
     }
   }
+  if (dbg && threadIdx.x == 0) dbg[4] = gtime_ns();
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[5] = gtime_ns();
   if (warp == 5) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
@@ -223,7 +239,8 @@ inline cudaError_t prepare_gemm() {   // once per process / NPAD (not a stream o
 
 template <int NPAD>
 inline cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)stages_for(NPAD) * (kATileBytes + NPAD * kBlockK * 2);
+  const int stages = (p.stages > 0 && p.stages < stages_for(NPAD)) ? p.stages : stages_for(NPAD);
+  const size_t smem = (size_t)stages * (kATileBytes + NPAD * kBlockK * 2);
   dim3 grid(p.M / kBlockM, p.splits, p.groups);
   gemm_f16_tn_kernel<NPAD><<<grid, kThreads, smem, st>>>(p);
   return cudaGetLastError();

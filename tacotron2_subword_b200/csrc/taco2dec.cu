@@ -1545,7 +1545,37 @@ int run_test_gemm(int M, int N, int K, int splits, const float* A, const float* 
   tc::pack_tiles_kernel<<<1024, 256, 0, st>>>(A, M, K, tc::kBlockM, M / tc::kBlockM, a_t);
   tc::pack_tiles_kernel<<<256, 256, 0, st>>>(X, N, K, NPAD, 1, x_t);
   tc::GemmParams gp{a_t, x_t, part, M, K, splits, 1, 0, 0, 0, nullptr, 0};
+  unsigned long long* dbg = nullptr;
+  const int n_cta = (M / tc::kBlockM) * splits;
+  if (getenv("TACO2DEC_GEMM_STAMPS")) {
+    CUDA_TRY(cudaMalloc(&dbg, (size_t)n_cta * 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(dbg, 0, (size_t)n_cta * 8 * sizeof(unsigned long long)));
+    gp.dbg = dbg;
+  }
   CUDA_TRY(tc::prepare_gemm<NPAD>());
+  if (dbg) {   // warm launches, then a timed one whose stamps are printed (ns relative to the earliest CTA entry)
+    for (int i = 0; i < 3; ++i) CUDA_TRY(tc::launch_gemm<NPAD>(gp, st));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    CUDA_TRY(tc::launch_gemm<NPAD>(gp, st));
+    cudaEventRecord(e1, st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<unsigned long long> hst((size_t)n_cta * 8);
+    CUDA_TRY(cudaMemcpy(hst.data(), dbg, hst.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull, tend = 0;
+    for (int c = 0; c < n_cta; ++c) { t0 = std::min(t0, hst[c * 8]); tend = std::max(tend, hst[c * 8 + 5]); }
+    fprintf(stderr, "[gemm stamps] M=%d N=%d K=%d splits=%d ctas=%d event %.2f us, first entry -> last exit %.2f us\n", M, N, K,
+            splits, n_cta, ms * 1e3, (tend - t0) * 1e-3);
+    for (int c = 0; c < n_cta; c += std::max(1, n_cta / 4))
+      fprintf(stderr, "  cta %3d: entry +%.2f  setup %.2f  first tile %.2f  acc done %.2f  stored %.2f  exit %.2f us\n", c,
+              (hst[c * 8] - t0) * 1e-3, (hst[c * 8 + 1] - t0) * 1e-3, (hst[c * 8 + 2] - t0) * 1e-3, (hst[c * 8 + 3] - t0) * 1e-3,
+              (hst[c * 8 + 4] - t0) * 1e-3, (hst[c * 8 + 5] - t0) * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dbg);
+  }
   CUDA_TRY(tc::launch_gemm<NPAD>(gp, st));
   sum_splits_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(part, splits, M, NPAD, N, out);
   CUDA_TRY(cudaGetLastError());
