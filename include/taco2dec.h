@@ -49,7 +49,7 @@ extern "C" {
 #define TACO2DEC_PATH_AUTO 0
 #define TACO2DEC_PATH_GENERIC 1 /* grid-barrier persistent kernel, fp32 weights in PyTorch layout, any B / SMA+LSA */
 #define TACO2DEC_PATH_LATENCY 2 /* role-specialised persistent kernel, packed weights resident/streamed (batch 1) */
-#define TACO2DEC_PATH_TENSOR 3  /* batched (16 <= B <= 128): LSTM / query products on tcgen05, fp16 operands, fp32 accumulate */
+#define TACO2DEC_PATH_TENSOR 3  /* batched (2 <= B <= 128): LSTM / query products on tcgen05, fp16 operands, fp32 accumulate */
 #define TACO2DEC_W_FP32 0       /* packed LSTM weights stay fp32 (parity ~1e-6)                           */
 #define TACO2DEC_W_FP16 1       /* the three LSTM matrices stored fp16, fp32 accumulate (parity ~5e-5)   */
 
@@ -130,7 +130,7 @@ typedef struct taco2dec_tf_args {
   void* workspace;
   size_t workspace_bytes;
   void* saved;        /* NULL, or a buffer of taco2dec_saved_layout_query().total bytes: the call keeps the activations
-                         taco2dec_backward needs (tensor path only: 16 <= B <= 128, SMA, default dims) */
+                         taco2dec_backward needs (tensor path only: 2 <= B <= 128, SMA, default dims) */
   size_t saved_bytes;
 } taco2dec_tf_args;
 

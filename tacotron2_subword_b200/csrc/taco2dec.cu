@@ -936,7 +936,7 @@ WorkspaceLayout plan_workspace(const taco2dec_config& c, int B, int T_in, int T_
   L.q = take((size_t)c.n_streams * B * c.attn_dim);
   L.ctl = take(64);
   // tensor path, teacher-forced: h2 / context rows of every frame for the hoisted projection (bt_proj_all)
-  const bool rows = tf && B >= 16 && B <= 128;
+  const bool rows = tf && B >= 2 && B <= 128;
   L.h2_all = take(rows ? (size_t)(T + 1) * B * c.dec_rnn_dim : 0);
   L.ctx_all = take(rows ? (size_t)(T + 1) * c.n_streams * B * c.enc_dim : 0);
   L.total = off;
@@ -1193,7 +1193,7 @@ size_t attention_smem_bytes(const taco2dec_config& c, int T_in, int T_sub) {
 
 bool bt_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
   const taco2dec_config& c = h->cfg;
-  if (B < 16 || B > 128) return false;
+  if (B < 2 || B > 128) return false;   // B = 1 belongs to the latency path; columns up to the next multiple of 16 are padding
   if (c.attn_rnn_dim != bt::H || c.dec_rnn_dim != bt::H || c.enc_dim != bt::E || c.prenet_dim != bt::P ||
       c.attn_dim != bt::A || c.n_mel != bt::M)
     return false;
@@ -1496,7 +1496,7 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
   CUDA_TRY(cudaGetLastError());
   if (h->cur_sv.gates1) {   // activations are kept for backward: only the tensor path produces them
     if (!bw_shape_ok(h, p.B, T_in, T_sub) || (h->path_mode != TACO2DEC_PATH_AUTO && h->path_mode != TACO2DEC_PATH_TENSOR))
-      return fail(TACO2DEC_E_ARG, "saving activations for backward needs the tensor path: 16 <= B <= 128, SMA, default decoder dims");
+      return fail(TACO2DEC_E_ARG, "saving activations for backward needs the tensor path: 2 <= B <= 128, SMA, default decoder dims");
     return run_batched(h, p, T_in, T_sub, st);
   }
   const bool want_lat = (h->path_mode == TACO2DEC_PATH_AUTO || h->path_mode == TACO2DEC_PATH_LATENCY) &&
@@ -1506,7 +1506,7 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
   if (want_lat) return run_latency(h, p, st);
   const bool tensor_ok = bt_shape_ok(h, p.B, T_in, T_sub);
   if (h->path_mode == TACO2DEC_PATH_TENSOR && !tensor_ok)
-    return fail(TACO2DEC_E_ARG, "tensor path needs 16 <= B <= 128 and default decoder dims");
+    return fail(TACO2DEC_E_ARG, "tensor path needs 2 <= B <= 128 and default decoder dims");
   // AUTO takes the tensor-core path only when fp16 operands were asked for (it rounds weights AND x/h to fp16)
   if (tensor_ok && (h->path_mode == TACO2DEC_PATH_TENSOR ||
                     (h->path_mode == TACO2DEC_PATH_AUTO && h->weight_dtype == TACO2DEC_W_FP16)))
@@ -1764,7 +1764,7 @@ int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* 
       p.st[s].pre = (float*)(sb + SL.pre[s]);
       pre0_save[s] = (float*)(sb + SL.pre0[s]);
     }
-  } else if (a->B >= 16 && a->B <= 128) {
+  } else if (a->B >= 2 && a->B <= 128) {
     h->cur_sv.h2 = (float*)(ws + L.h2_all);
     h->cur_sv.ctx = (float*)(ws + L.ctx_all);
   }
@@ -1809,7 +1809,7 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
   if (c.n_streams == 2 && (!a->embeddings || !a->align_bert)) return fail(TACO2DEC_E_ARG, "sub-word stream tensors missing");
   const int T_sub = std::max(a->T_sub, 1);
   if (!bw_shape_ok(h, a->B, a->T_in, T_sub))
-    return fail(TACO2DEC_E_ARG, "backward needs the tensor path: 16 <= B <= 128, SMA, default decoder dims");
+    return fail(TACO2DEC_E_ARG, "backward needs the tensor path: 2 <= B <= 128, SMA, default decoder dims");
   if ((reinterpret_cast<uintptr_t>(a->saved) & 255u) || (reinterpret_cast<uintptr_t>(a->grads) & 255u))
     return fail(TACO2DEC_E_ARG, "saved / grads buffers must be 256-byte aligned");
   const taco2dec_saved_layout SL = plan_saved(c, a->B, a->T_in, T_sub, a->T);

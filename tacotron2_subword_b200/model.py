@@ -119,7 +119,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class _NoBackward(torch.autograd.Function):
     """Marks decoder outputs as differentiable so training code fails LOUDLY at backward()
     instead of silently skipping the decoder when the shape has no backward kernel (the BPTT
-    kernels cover the tensor path: 16 <= B <= 128, SMA, default dims)."""
+    kernels cover the tensor path: 2 <= B <= 128, SMA, default dims)."""
 
     @staticmethod
     def forward(ctx, anchor, *outs):
@@ -129,7 +129,7 @@ class _NoBackward(torch.autograd.Function):
     def backward(ctx, *grads):
         raise NotImplementedError(
             "tacotron2_subword_b200: decoder backward is implemented for the tensor path only "
-            "(16 <= batch <= 128, StepwiseMonotonicAttention, default decoder dims)")
+            "(2 <= batch <= 128, StepwiseMonotonicAttention, default decoder dims)")
 
 
 def _fview(buf: torch.Tensor, off: int, *shape) -> torch.Tensor:
@@ -410,7 +410,7 @@ class Decoder(nn.Module):
         -> mel [B,n_mel,T], gate [B,T], alignments [B,T,T_in], alignments_bert [B,T,T_sub].
 
         With autograd enabled the outputs carry a hand-written backward (``_DecoderTF``) when the shape is
-        covered by the tensor path (16 <= B <= 128, SMA, default dims); other shapes raise at backward()."""
+        covered by the tensor path (2 <= B <= 128, SMA, default dims); other shapes raise at backward()."""
         wants_grad = torch.is_grad_enabled() and (
             any(p.requires_grad for p in self.parameters()) or memory.requires_grad or
             (embeddings is not None and embeddings.requires_grad))
@@ -431,7 +431,7 @@ class Decoder(nn.Module):
         return outs
 
     def _backward_supported(self, memory) -> bool:
-        return (self.attention_kind == SMA and 16 <= memory.shape[0] <= 128 and self.decoder_path in ("auto", "tensor")
+        return (self.attention_kind == SMA and 2 <= memory.shape[0] <= 128 and self.decoder_path in ("auto", "tensor")
                 and (self.attention_rnn_dim, self.decoder_rnn_dim, self.encoder_embedding_dim, self.prenet_dim,
                      self.attention_dim, self.n_mel_channels) == (1024, 1024, 512, 256, 128, 80))
 

@@ -41,7 +41,7 @@ def _oracle_grads(w, inp, plan, training, dims=DecoderDims()):
     return grads, mem.grad, (emb.grad if emb is not None else None), outs
 
 
-@pytest.mark.parametrize("B,T,training,tf32", [(16, 5, False, False), (24, 7, True, False), (64, 4, True, True)])
+@pytest.mark.parametrize("B,T,training,tf32", [(3, 6, True, False), (16, 5, False, False), (24, 7, True, False), (64, 4, True, True)])
 def test_backward_vs_oracle_autograd(B, T, training, tf32):
     T_in, T_sub, seed = 24, 8, 500 + B
     w = make_decoder_weights(SMA, seed=seed)
@@ -116,14 +116,17 @@ def test_backward_philox_masks_match_forward():
 
 
 def test_backward_unsupported_shape_raises():
-    B, T, T_in, T_sub, seed = 2, 3, 12, 4, 7
-    w = make_decoder_weights(SMA, seed=seed)
-    inp = make_inputs(B, T_in, T_sub, T, seed=seed)
-    dec = make_decoder(w, SMA).train()
-    outs = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(), inp["memory_lengths"].cuda(),
-               inp["bert_lengths"].cuda())
-    with pytest.raises(NotImplementedError):
-        outs[0].sum().backward()
+    """Batch 1 (latency path) and LSA have no backward kernel: the forward output must refuse backward() loudly."""
+    from oracle.synth import LSA
+    for attention, B in ((SMA, 1), (LSA, 4)):
+        T, T_in, T_sub, seed = 3, 12, 4, 7
+        w = make_decoder_weights(attention, seed=seed)
+        inp = make_inputs(B, T_in, T_sub, T, seed=seed)
+        dec = make_decoder(w, attention).train()
+        outs = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(), inp["memory_lengths"].cuda(),
+                   inp["bert_lengths"].cuda())
+        with pytest.raises(NotImplementedError):
+            outs[0].sum().backward()
 
 
 def test_model_training_step_end_to_end():

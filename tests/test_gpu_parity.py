@@ -290,7 +290,7 @@ def test_model_wrapper_forward_and_inference_shapes():
 # that on the reference itself); integer outputs exact.
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("attention", [SMA, LSA])
-@pytest.mark.parametrize("B,training", [(16, False), (24, True), (64, False)])
+@pytest.mark.parametrize("B,training", [(2, True), (16, False), (24, True), (64, False)])
 def test_tensor_path_teacher_forced_vs_oracle(attention, B, training):
     T_in, T_sub, T, seed = 40, 13, 6, 300 + B
     w = make_decoder_weights(attention, seed=seed)

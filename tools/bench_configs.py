@@ -45,7 +45,8 @@ run("cfg1 TF B=1 80/26 T=400", "tf", 1, 80, 26, 400, "auto", "fp32")
 run("cfg1 TF B=1 80/26 T=400", "tf", 1, 80, 26, 400, "auto", "fp16")
 run("cfg3 FR B=64 120/40", "fr", 64, 120, 40, Tq or 1000, "tensor", "fp16")
 run("cfg3 FR B=64 120/40", "fr", 64, 120, 40, 50, "generic", "fp32")
-run("cfg3-strong FR B=8 120/40 (8 GPUs x 8)", "fr", 8, 120, 40, Tq or 1000, "generic", "fp32")
+run("cfg3-strong FR B=8 120/40 (8 GPUs x 8)", "fr", 8, 120, 40, Tq or 1000, "tensor", "fp16")
+run("cfg3-strong FR B=8 120/40 generic fp32", "fr", 8, 120, 40, 200, "generic", "fp32")
 run("cfg3-strong FR B=16 (4 GPUs x 16)", "fr", 16, 120, 40, Tq or 1000, "tensor", "fp16")
 run("cfg3-strong FR B=32 (2 GPUs x 32)", "fr", 32, 120, 40, Tq or 1000, "tensor", "fp16")
 run("cfg4 GTA TF B=16/GPU 160/53 T=800", "tf", 16, 160, 53, Tq or 800, "tensor", "fp16")
