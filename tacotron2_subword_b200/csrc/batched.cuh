@@ -40,8 +40,8 @@ struct Bufs {
   unsigned char* a1;    // [S][32 m-tiles][28 kb] attention LSTM weights [W_ih | W_hh]
   unsigned char* a2;    // [32][K2/64]            decoder LSTM weights   [W_ih | W_hh]
   unsigned char* aq;    // [S][1][16]             query weights
-  unsigned char* x1;    // [2 parities][S][28 kb][NPAD x 64]
-  unsigned char* x2;    // [2 parities][K2/64][NPAD x 64]     [h1_0 | ctx_0 | h1_1 | ctx_1 | h2]
+  unsigned char* x1;    // [S][28 kb][NPAD x 64]
+  unsigned char* x2;    // [K2/64][NPAD x 64]     [h1_0 | ctx_0 | h1_1 | ctx_1 | h2]
   // GEMM partial outputs (fp32)
   float* g1;            // [S][SPLITS1][4096][NPAD]
   float* g2;            // [SPLITS2][4096][NPAD]
@@ -53,20 +53,6 @@ struct Bufs {
   Saved sv;
 };
 
-// The operand buffers are double-buffered by frame parity: frame t's GEMMs read X1[t&1] / X2[t&1] while the same
-// frame's producers already write frame t+1's operands into the other half (required once the LSTM pointwise step runs
-// inside the GEMM: a tile's epilogue must not overwrite activations that other CTAs of the same GEMM still read).
-//   X1[t&1] = [prenet[t] | ctx[t-1] | h1[t-1]]       X2[t&1] = [h1_0[t] | ctx_0[t] | h1_1[t] | ctx_1[t] | h2[t-1]]
-__device__ __forceinline__ unsigned char* x1_of(const Bufs& bf, int S, int s, int parity) {
-  return bf.x1 + ((size_t)parity * S + s) * (K1 / 64) * bf.NPAD * 128;
-}
-__device__ __forceinline__ unsigned char* x2_of(const Bufs& bf, int parity) {
-  return bf.x2 + (size_t)parity * (bf.K2 / 64) * bf.NPAD * 128;
-}
-// row of gate g (i,f,g,o), hidden unit j inside a gate-interleaved GEMM output: a 128-row tile holds 32 units x 4 gates,
-// so that one CTA owns everything the LSTM cell update of its units needs
-__host__ __device__ __forceinline__ int gate_row(int g, int j) { return (j >> 5) * 128 + g * 32 + (j & 31); }
-
 __device__ __forceinline__ void x_store(unsigned char* xbase, int NPAD, int b, int k, float v) {
   const size_t off = (size_t)(k >> 6) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63);
   *reinterpret_cast<__half*>(xbase + off) = __float2half(v);
@@ -74,7 +60,7 @@ __device__ __forceinline__ void x_store(unsigned char* xbase, int NPAD, int b, i
 
 // weights: rows x (K0 + K1c) from two row-major fp32 sources -> [row tiles of 128][kb] fp16 tiles
 __global__ void pack_concat_tiles_kernel(const float* __restrict__ src0, int K0, const float* __restrict__ src1, int K1c,
-                                         int rows, unsigned char* __restrict__ dst, int interleave_gates) {
+                                         int rows, unsigned char* __restrict__ dst) {
   const int K = K0 + K1c, kb_total = K / tc::kBlockK;
   const int rows_pad = (rows + 127) / 128 * 128;
   const size_t total = (size_t)rows_pad * K;
@@ -82,9 +68,8 @@ __global__ void pack_concat_tiles_kernel(const float* __restrict__ src0, int K0,
     const int k = (int)(i % K), r = (int)(i / K);
     float v = 0.f;
     if (r < rows) v = k < K0 ? src0[(size_t)r * K0 + k] : src1[(size_t)r * K1c + (k - K0)];
-    const int ro = interleave_gates ? gate_row(r / (rows / 4), r % (rows / 4)) : r;   // source rows are [gate][unit]
-    const size_t tile = ((size_t)(ro / 128) * kb_total + (k / tc::kBlockK)) * tc::kATileBytes;
-    *reinterpret_cast<__half*>(dst + tile + tc::tile_offset_bytes(128, ro % 128, k % tc::kBlockK)) = __float2half(v);
+    const size_t tile = ((size_t)(r / 128) * kb_total + (k / tc::kBlockK)) * tc::kATileBytes;
+    *reinterpret_cast<__half*>(dst + tile + tc::tile_offset_bytes(128, r % 128, k % tc::kBlockK)) = __float2half(v);
   }
 }
 
@@ -113,7 +98,7 @@ __global__ void bt_prenet_tf_to_x1(Params p, Bufs bf, const int* t_ptr) {
   if (i >= p.S * p.B * P) return;
   const int s = i / (p.B * P), r = i - s * p.B * P, b = r / P, k = r - b * P;
   const float v = p.st[s].pre[((size_t)t * p.B + b) * P + k];
-  x_store(x1_of(bf, p.S, s, t & 1), bf.NPAD, b, k, v);
+  x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, k, v);
 }
 
 __global__ void transpose_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
@@ -176,7 +161,7 @@ __global__ void __launch_bounds__(1024) bt_prenet_fr(Params p, Bufs bf, const in
     if (b < p.B) {
       const float v = (part_s[0][bb][o] + part_s[1][bb][o]) + (part_s[2][bb][o] + part_s[3][bb][o]);
       const float mult = keep_mult(sp.keep1, ((size_t)t * p.B + b) * P + o, p.seed, s * 2 + 1, t, b * P + o, p.thresh_pre, 2.0f);
-      x_store(x1_of(bf, p.S, s, t & 1), bf.NPAD, b, o, fmaxf(v, 0.f) * mult);
+      x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, o, fmaxf(v, 0.f) * mult);
     }
   }
 }
@@ -194,13 +179,13 @@ __global__ void bt_pointwise1(Params p, Bufs bf, int* t_ptr, int tf_merge) {
   const int s = i / (p.B * H), r = i - s * p.B * H, j = r / p.B, b = r - j * p.B;   // b fastest: coalesced partial reads
   const StreamParams& sp = p.st[s];
   if (tf_merge && j < P && t + 1 < p.T)
-    x_store(x1_of(bf, p.S, s, (t + 1) & 1), bf.NPAD, b, j, sp.pre[((size_t)(t + 1) * p.B + b) * P + j]);
+    x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, j, sp.pre[((size_t)(t + 1) * p.B + b) * P + j]);
   float pre[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float a = sp.b_ih[g * H + j] + sp.b_hh[g * H + j];
 #pragma unroll
-    for (int k = 0; k < SPLITS1; ++k) a += bf.g1[(((size_t)s * SPLITS1 + k) * 4 * H + gate_row(g, j)) * bf.NPAD + b];
+    for (int k = 0; k < SPLITS1; ++k) a += bf.g1[(((size_t)s * SPLITS1 + k) * 4 * H + g * H + j) * bf.NPAD + b];
     pre[g] = a;
   }
   const size_t idx = (size_t)b * H + j;
@@ -221,8 +206,8 @@ __global__ void bt_pointwise1(Params p, Bufs bf, int* t_ptr, int tf_merge) {
   }
   bf.c1[(size_t)s * p.B * H + idx] = cn;
   if (bf.sv.h1) bf.sv.h1[(((size_t)(t + 1) * p.S + s) * p.B) * H + idx] = hn;
-  x_store(x1_of(bf, p.S, s, (t + 1) & 1), bf.NPAD, b, P + E + j, hn);     // next frame's LSTM-1 input
-  x_store(x2_of(bf, t & 1), bf.NPAD, b, s * (H + E) + j, hn);             // this frame's LSTM-2 / query input
+  x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, P + E + j, hn);     // next frame's LSTM-1 input
+  x_store(bf.x2, bf.NPAD, b, s * (H + E) + j, hn);                                        // this frame's LSTM-2 / query input
 }
 
 // attention: q = sum of the query-GEMM partials, then the generic attention task; context -> fp32 + tiles
@@ -244,8 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) bt_attention(Params p, Bufs bf, c
   for (int d = tid; d < E; d += kThreads) {
     const float c = __ldcg(p.ctx + ((size_t)s * p.B + b) * E + d);
     if (bf.sv.ctx) bf.sv.ctx[(((size_t)(t + 1) * p.S + s) * p.B + b) * E + d] = c;
-    x_store(x1_of(bf, p.S, s, (t + 1) & 1), bf.NPAD, b, P + d, c);          // next frame's LSTM-1 input
-    x_store(x2_of(bf, t & 1), bf.NPAD, b, s * (H + E) + H + d, c);          // this frame's LSTM-2 input
+    x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, P + d, c);          // next frame's LSTM-1 input
+    x_store(bf.x2, bf.NPAD, b, s * (H + E) + H + d, c);                                     // this frame's LSTM-2 input
   }
 }
 
@@ -389,8 +374,8 @@ __global__ void __launch_bounds__(kThreads, 1) bt_attention_sma(Params p, Bufs b
     const float c = (red_s[d] + red_s[E + d]) + (red_s[2 * E + d] + red_s[3 * E + d]);
     p.ctx[((size_t)s * p.B + b) * E + d] = c;
     if (bf.sv.ctx) bf.sv.ctx[(((size_t)(t + 1) * p.S + s) * p.B + b) * E + d] = c;
-    x_store(x1_of(bf, p.S, s, (t + 1) & 1), bf.NPAD, b, P + d, c);          // next frame's LSTM-1 input
-    x_store(x2_of(bf, t & 1), bf.NPAD, b, s * (H + E) + H + d, c);          // this frame's LSTM-2 input
+    x_store(bf.x1 + (size_t)s * (K1 / 64) * bf.NPAD * 128, bf.NPAD, b, P + d, c);          // next frame's LSTM-1 input
+    x_store(bf.x2, bf.NPAD, b, s * (H + E) + H + d, c);                                     // this frame's LSTM-2 input
   }
 }
 
@@ -406,7 +391,7 @@ __global__ void bt_pointwise2(Params p, Bufs bf, int* t_ptr, int tf_merge) {
   for (int g = 0; g < 4; ++g) {
     float a = p.d_b_ih[g * H + j] + p.d_b_hh[g * H + j];
 #pragma unroll
-    for (int k = 0; k < SPLITS2; ++k) a += bf.g2[((size_t)k * 4 * H + gate_row(g, j)) * bf.NPAD + b];
+    for (int k = 0; k < SPLITS2; ++k) a += bf.g2[((size_t)k * 4 * H + g * H + j) * bf.NPAD + b];
     pre[g] = a;
   }
   const size_t idx = (size_t)b * H + j;
@@ -428,7 +413,7 @@ __global__ void bt_pointwise2(Params p, Bufs bf, int* t_ptr, int tf_merge) {
   bf.c2[idx] = cn;
   bf.h2f[idx] = hn;
   if (bf.sv.h2) bf.sv.h2[(size_t)(t + 1) * p.B * H + idx] = hn;
-  x_store(x2_of(bf, (t + 1) & 1), bf.NPAD, b, p.S * (H + E) + j, hn);     // next frame's recurrent input
+  x_store(bf.x2, bf.NPAD, b, p.S * (H + E) + j, hn);     // next frame's recurrent input
 }
 
 // mel / gate projection (one warp per (row, batch)) + stop test

@@ -104,8 +104,6 @@ struct GemmParams {
   int done_target;
   uint32_t fmt;                   // operand formats OR-ed into the instruction descriptor (kFmtF16 / kFmtBF16)
   int stages;                     // 0 = stages_for(NPAD); experiments may ask for fewer
-  const int* parity_ptr;          // optional: X is double-buffered, this launch reads half (*parity_ptr & 1)
-  long long x_parity_stride;      // bytes between the two halves
   unsigned long long* dbg;        // optional [CTAs][8] globaltimer stamps (ns): entry, setup done, first tile landed,
                                   // accumulator complete, epilogue stored, exit
 };
@@ -155,7 +153,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
     if (lane == 0) {
       const unsigned char* a_src = p.a_tiles + ((size_t)group * m_tiles + mt) * kb_total * kATileBytes;
       const unsigned char* x_src = p.x_tiles + (size_t)group * p.x_group_stride +
-                                   (p.parity_ptr ? (size_t)(__ldcg(p.parity_ptr) & 1) * p.x_parity_stride : 0) +
                                    (size_t)(p.x_kb_base + group * p.x_kb_group_step) * kXTileBytes;
       for (int i = 0; i < kb_per_split; ++i) {
         const int s = i % kStages;

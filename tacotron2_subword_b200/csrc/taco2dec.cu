@@ -1209,8 +1209,8 @@ int bt_prepare(taco2dec_handle* h, cudaStream_t st) {
     CUDA_TRY(cudaMalloc(&b.a1, (size_t)S * 32 * (bt::K1 / 64) * tc::kATileBytes));
     CUDA_TRY(cudaMalloc(&b.a2, (size_t)32 * (K2 / 64) * tc::kATileBytes));
     CUDA_TRY(cudaMalloc(&b.aq, (size_t)S * (bt::H / 64) * tc::kATileBytes));
-    CUDA_TRY(cudaMalloc(&b.x1, (size_t)2 * S * (bt::K1 / 64) * NP * 128));
-    CUDA_TRY(cudaMalloc(&b.x2, (size_t)2 * (K2 / 64) * NP * 128));
+    CUDA_TRY(cudaMalloc(&b.x1, (size_t)S * (bt::K1 / 64) * NP * 128));
+    CUDA_TRY(cudaMalloc(&b.x2, (size_t)(K2 / 64) * NP * 128));
     CUDA_TRY(cudaMalloc(&b.g1, (size_t)S * bt::SPLITS1 * 4 * bt::H * NP * sizeof(float)));
     CUDA_TRY(cudaMalloc(&b.g2, (size_t)bt::SPLITS2 * 4 * bt::H * NP * sizeof(float)));
     CUDA_TRY(cudaMalloc(&b.gq, (size_t)S * bt::SPLITSQ * 128 * NP * sizeof(float)));
@@ -1227,15 +1227,15 @@ int bt_prepare(taco2dec_handle* h, cudaStream_t st) {
   if (!h->bt_tiles_valid) {
     for (int s = 0; s < S; ++s) {
       bt::pack_concat_tiles_kernel<<<2048, 256, 0, st>>>(h->w.stream[s].arnn_w_ih, bt::P + bt::E, h->w.stream[s].arnn_w_hh, bt::H,
-                                                         4 * bt::H, b.a1 + (size_t)s * 32 * (bt::K1 / 64) * tc::kATileBytes, 1);
+                                                         4 * bt::H, b.a1 + (size_t)s * 32 * (bt::K1 / 64) * tc::kATileBytes);
       bt::pack_concat_tiles_kernel<<<256, 256, 0, st>>>(h->w.stream[s].query_w, bt::H, nullptr, 0, bt::A,
-                                                        b.aq + (size_t)s * (bt::H / 64) * tc::kATileBytes, 0);
+                                                        b.aq + (size_t)s * (bt::H / 64) * tc::kATileBytes);
     }
     for (int s = 0; s < S; ++s) {
       bt::transpose_kernel<<<(bt::P * bt::M + 255) / 256, 256, 0, st>>>(h->w.stream[s].prenet_w0, bt::P, bt::M, b.w0t[s]);
       bt::transpose_kernel<<<(bt::P * bt::P + 255) / 256, 256, 0, st>>>(h->w.stream[s].prenet_w1, bt::P, bt::P, b.w1t[s]);
     }
-    bt::pack_concat_tiles_kernel<<<4096, 256, 0, st>>>(h->w.drnn_w_ih, S * (bt::H + bt::E), h->w.drnn_w_hh, bt::H, 4 * bt::H, b.a2, 1);
+    bt::pack_concat_tiles_kernel<<<4096, 256, 0, st>>>(h->w.drnn_w_ih, S * (bt::H + bt::E), h->w.drnn_w_hh, bt::H, 4 * bt::H, b.a2);
     CUDA_TRY(cudaGetLastError());
     h->launches += 2 * S + 1;
     h->bt_tiles_valid = true;
@@ -1255,9 +1255,8 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   if (bf.sv.ctx) CUDA_TRY(cudaMemsetAsync(bf.sv.ctx, 0, (size_t)S * B * bt::E * sizeof(float), st));
   if (bf.sv.h2) CUDA_TRY(cudaMemsetAsync(bf.sv.h2, 0, (size_t)B * bt::H * sizeof(float), st));
   const bool hoist_proj = !p.free_running && bf.sv.h2 && bf.sv.ctx && !getenv("TACO2DEC_NO_HOIST");
-  const long long x1_half = (long long)S * (bt::K1 / 64) * NPAD * 128, x2_half = (long long)(bf.K2 / 64) * NPAD * 128;
-  CUDA_TRY(cudaMemsetAsync(bf.x1, 0, (size_t)2 * x1_half, st));
-  CUDA_TRY(cudaMemsetAsync(bf.x2, 0, (size_t)2 * x2_half, st));
+  CUDA_TRY(cudaMemsetAsync(bf.x1, 0, (size_t)S * (bt::K1 / 64) * NPAD * 128, st));
+  CUDA_TRY(cudaMemsetAsync(bf.x2, 0, (size_t)(bf.K2 / 64) * NPAD * 128, st));
   bt::bt_init_kernel<<<h->num_sms, 256, 0, st>>>(p, bf);
   CUDA_TRY(cudaFuncSetAttribute(bt::bt_attention<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
   int max_ts = 0;
@@ -1265,18 +1264,15 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   const size_t sma_smem = bt::sma_smem_floats(max_ts) * sizeof(float);
   CUDA_TRY(cudaFuncSetAttribute(bt::bt_attention_sma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma_smem));
   const int* done = p.free_running ? p.done_count : nullptr;
-  int* t_ptr = p.done_count + 1;                      // control block word, zeroed by run_common
   tc::GemmParams g1{bf.a1, bf.x1, bf.g1, 4 * bt::H, bt::K1, bt::SPLITS1, S, (long long)(bt::K1 / 64) * NPAD * 128, 0, 0, done, B};
   tc::GemmParams gq{bf.aq, bf.x2, bf.gq, 128, bt::H, bt::SPLITSQ, S, 0, 0, (bt::H + bt::E) / 64, done, B};
   tc::GemmParams g2{bf.a2, bf.x2, bf.g2, 4 * bt::H, bf.K2, bt::SPLITS2, 1, 0, 0, 0, done, B};
-  g1.parity_ptr = gq.parity_ptr = g2.parity_ptr = t_ptr;          // frame t reads operand half t & 1
-  g1.x_parity_stride = x1_half;
-  gq.x_parity_stride = g2.x_parity_stride = x2_half;
   CUDA_TRY(tc::prepare_gemm<NPAD>());
   // One frame = 9 kernels; the frame index is read from device memory, so the sequence is captured ONCE into
   // a CUDA graph and replayed n_steps times (one graph launch per frame instead of nine kernel launches).
   // Capture happens on a private stream (the caller's stream may be the legacy default stream, which cannot
   // be captured); the instantiated graph is launched on the caller's stream.
+  int* t_ptr = p.done_count + 1;                      // control block word, zeroed by run_common
   if (!h->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   cudaStream_t cs = h->cap_stream;
   cudaGraph_t graph = nullptr;
