@@ -13,8 +13,11 @@ dec.decoder_path, dec.weight_dtype = "tensor", "fp16"
 inp = make_inputs(B, 120, 40, T, seed=3, ragged=True)
 a = [inp[k].cuda() for k in ("memory", "embeddings", "mels", "memory_lengths", "bert_lengths")]
 with torch.no_grad():
-    for _ in range(2):
+    for it in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         if mode == "tf": dec(a[0], a[1], a[2], a[3], a[4])
         else: dec.inference_batched(a[0], a[1], a[3], a[4], max_decoder_steps=T)
-torch.cuda.synchronize()
-print("ok")
+        e1.record(); e1.synchronize()
+        ms = e0.elapsed_time(e1)
+print(f"ok B={B} T={T} {mode}: {ms:.2f} ms, {1e3 * ms / T:.1f} us per frame-step, {B * T / (ms * 1e-3):.0f} frames/s")
