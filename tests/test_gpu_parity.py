@@ -356,3 +356,89 @@ def test_latency_path_single_stream_vs_oracle(wdtype, tol_mel, tol_align):
         got = dec(inp["memory"].cuda(), None, inp["mels"].cuda(), inp["memory_lengths"].cuda(), None)
         _cmp_tol(got, want, tol_mel, tol_align, "S=1 teacher-forced")
     assert dec._engine(torch.device("cuda", 0)).last_path() == "latency"
+
+
+# ---------------------------------------------------------------------------------------------------
+# Batched free-running with utterances that stop at DIFFERENT frames (and some that never stop): the stop
+# bookkeeping (n_frames, reached_max, done counter, early exit of the frame kernels) on both batched paths.
+# ---------------------------------------------------------------------------------------------------
+def _mixed_stop_bias(attention, seed, B, T_in, T_sub, steps, margin):
+    """A gate bias for which some utterances stop mid-way at different frames and others run into max_decoder_steps,
+    with every gate logit at least `margin` away from the threshold (so fp16 rounding cannot flip a decision)."""
+    import math
+    w = make_decoder_weights(attention, seed=seed, gate_bias=0.0)
+    inp = make_inputs(B, T_in, T_sub, 1, seed=seed, ragged=True)
+    plan = make_dropout_plan(B, steps, steps, T_in, T_sub, False, seed=seed + 1)
+    w_never = dict(w); w_never["gate_layer.linear_layer.bias"] = torch.full_like(w["gate_layer.linear_layer.bias"], -20.0)
+    outs = DecoderOracle(w_never, attention).inference_batched(inp["memory"], inp["embeddings"], inp["memory_lengths"],
+                                                               inp["bert_lengths"], plan, max_decoder_steps=steps)
+    G = torch.stack([o[1].reshape(-1) + 20.0 for o in outs])          # zero-bias gate logits [B, steps]
+    vals = torch.sort(G.reshape(-1)).values
+    best = None
+    for lo, hi in zip(vals[:-1].tolist(), vals[1:].tolist()):
+        if hi - lo < 2 * margin:
+            continue
+        c = 0.5 * (lo + hi)
+        stops = [(int((G[b] > c).nonzero()[0]) + 1) if bool((G[b] > c).any()) else None for b in range(B)]
+        n_stop = sum(s is not None for s in stops)
+        if 0.25 * B <= n_stop <= 0.75 * B and len({s for s in stops if s is not None}) >= 2:
+            best = c
+            break
+    assert best is not None, "no separating threshold found; change the seed"
+    return math.log(0.001 / 0.999) - best, inp, plan
+
+
+@pytest.mark.parametrize("path,wdtype,B,tol_mel,tol_align", [("generic", "fp32", 5, TOL_MEL, TOL_ALIGN),
+                                                             ("tensor", "fp16", 16, 1e-3, 2e-4)])
+def test_batched_free_running_mixed_stop_frames(path, wdtype, B, tol_mel, tol_align):
+    T_in, T_sub, steps, seed = 21, 8, 14, 88
+    bias, inp, plan = _mixed_stop_bias(SMA, seed, B, T_in, T_sub, steps, margin=5e-3)
+    w = make_decoder_weights(SMA, seed=seed, gate_bias=bias)
+    outs = DecoderOracle(w, SMA).inference_batched(inp["memory"], inp["embeddings"], inp["memory_lengths"],
+                                                   inp["bert_lengths"], plan, max_decoder_steps=steps)
+    want_n = [o[0].shape[2] for o in outs]
+    assert len(set(want_n)) >= 3 and steps in want_n, want_n            # several stop frames + at least one max-steps
+    dec = make_decoder(w, SMA).eval()
+    dec.decoder_path, dec.weight_dtype = path, wdtype
+    dec.dropout_replay = replay_of(plan)
+    with torch.no_grad():
+        mel, gate, al, alb, nf, reached = dec.inference_batched(inp["memory"].cuda(), inp["embeddings"].cuda(),
+                                                                inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda(),
+                                                                max_decoder_steps=steps)
+    assert dec._engine(torch.device("cuda", 0)).last_path() == path
+    assert [int(x) for x in nf] == want_n
+    for b, (omel, ogate, oal, oalb, oflag) in enumerate(outs):
+        n = want_n[b]
+        assert bool(reached[b]) == (not oflag)
+        Lm, Lb = int(inp["memory_lengths"][b]), int(inp["bert_lengths"][b])
+        _cmp_tol((mel[b:b + 1, :, :n], gate[b:b + 1, :n], al[b:b + 1, :n, :Lm], alb[b:b + 1, :n, :Lb]),
+                 (omel, ogate, oal, oalb), tol_mel, tol_align, f"{path} mixed-stop utt {b}")
+
+
+def test_tensor_path_single_stream_forward_and_backward():
+    """Tacotron2 compat decoder (1 stream, SMA) on the tensor path: K2 = 2560, one GEMM group; forward vs the oracle and
+    gradients vs autograd through the oracle."""
+    from oracle.synth import DecoderDims
+    from tests.test_gpu_backward import TOL_GRAD, _loss, _oracle_grads
+    dims = DecoderDims(streams=1)
+    B, T_in, T, seed = 16, 26, 5, 61
+    w = make_decoder_weights(SMA, seed=seed, dims=dims)
+    inp = make_inputs(B, T_in, 1, T, seed=seed, ragged=True, dims=dims)
+    plan = make_dropout_plan(B, T + 1, T, T_in, 1, True, seed=seed + 1, dims=dims)
+    want, want_dmem, _, want_outs = _oracle_grads(w, inp, plan, True, dims=dims)
+    dec = make_decoder(w, SMA, n_streams=1).train()
+    dec.decoder_path, dec.weight_dtype = "tensor", "fp16"
+    dec.dropout_replay = replay_of(plan)
+    mem = inp["memory"].cuda().requires_grad_(True)
+    outs = dec(mem, None, inp["mels"].cuda(), inp["memory_lengths"].cuda(), None)
+    assert dec._engine(torch.device("cuda", 0)).last_path() == "tensor"
+    _cmp_tol(tuple(o.detach() if o is not None else None for o in outs),
+             tuple(o.detach() if o is not None else None for o in want_outs), 1e-3, 2e-4, "tensor single-stream")
+    _loss(outs, 5).backward()
+    sd = dict(dec.named_parameters())
+    for name, gw in want.items():
+        if gw is None:
+            continue
+        err = float((sd[name].grad.cpu() - gw).abs().max() / gw.abs().max())
+        assert err < TOL_GRAD, (name, err)
+    assert float((mem.grad.cpu() - want_dmem).abs().max() / want_dmem.abs().max()) < TOL_GRAD
