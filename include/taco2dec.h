@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TACO2DEC_ABI_VERSION 2
+#define TACO2DEC_ABI_VERSION 3
 
 #define TACO2DEC_ATTN_SMA 0 /* StepwiseMonotonicAttention   (attention.py:291-398, hparams default) */
 #define TACO2DEC_ATTN_LSA 1 /* LocationSensitiveAttention   (attention.py:7-85)                      */
@@ -129,6 +129,10 @@ typedef struct taco2dec_tf_args {
   float* align_bert; /* [B, T, T_sub]   (NULL when n_streams==1) */
   void* workspace;
   size_t workspace_bytes;
+  int independent;    /* 0 = the reference's batched semantics (Decoder.forward under training: SMA lets alignment mass
+                         leak onto padded memory positions, model.py:414 + attention.py:330-338).  1 = every utterance is
+                         its own sequence, exactly as if it had been run alone at batch 1 on its un-padded memory (what
+                         GTA.py:35-61 does one utterance at a time): positions >= length do not exist */
   void* saved;        /* NULL, or a buffer of taco2dec_saved_layout_query().total bytes: the call keeps the activations
                          taco2dec_backward needs (tensor path only: 2 <= B <= 128, SMA, default dims) */
   size_t saved_bytes;
@@ -186,6 +190,7 @@ typedef struct taco2dec_bwd_args {
   const float* d_gate;           /* [B, T] */
   const float* d_align;          /* [B, T, T_in]  or NULL */
   const float* d_align_bert;     /* [B, T, T_sub] or NULL */
+  int independent;               /* as in the forward call */
   const void* saved;
   size_t saved_bytes;
   void* grads;

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtac
 ATTN_SMA, ATTN_LSA = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR = 0, 1, 2, 3
 W_FP32, W_FP16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTED_SYMBOLS = (
     "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
@@ -57,7 +57,7 @@ class TFArgs(C.Structure):
                 ("memory_lengths", _fp), ("bert_lengths", _fp), ("training", C.c_int), ("rng", Rng),
                 ("mel", _fp), ("gate", _fp), ("align", _fp), ("align_bert", _fp),
                 ("workspace", _fp), ("workspace_bytes", C.c_size_t),
-                ("saved", _fp), ("saved_bytes", C.c_size_t)]
+                ("independent", C.c_int), ("saved", _fp), ("saved_bytes", C.c_size_t)]
 
 
 class SavedLayout(C.Structure):
@@ -77,7 +77,7 @@ class BwdArgs(C.Structure):
                 ("memory", _fp), ("embeddings", _fp), ("memory_lengths", _fp), ("bert_lengths", _fp),
                 ("training", C.c_int), ("rng", Rng),
                 ("align", _fp), ("align_bert", _fp), ("d_mel", _fp), ("d_gate", _fp),
-                ("d_align", _fp), ("d_align_bert", _fp),
+                ("d_align", _fp), ("d_align_bert", _fp), ("independent", C.c_int),
                 ("saved", _fp), ("saved_bytes", C.c_size_t), ("grads", _fp), ("grads_bytes", C.c_size_t)]
 
 

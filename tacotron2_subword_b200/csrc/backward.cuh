@@ -377,6 +377,10 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
   }
   __syncthreads();
   // alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1})   (attention.py:330-338), p = sigmoid(e)
+  if (p.independent) {   // alpha'_j was forced to 0 beyond the utterance's length: no gradient flows through it
+    for (int j = len + tid; j < Ts; j += kBwThreads) dan_s[j] = 0.f;
+    __syncthreads();
+  }
   for (int j = tid; j < Ts; j += kBwThreads) {
     const float dn = dan_s[j], dn1 = j + 1 < Ts ? dan_s[j + 1] : 0.f, pj = p_s[j];
     g.dalpha[s][(size_t)b * Ts + j] = dn * pj + dn1 * (1.0f - pj);

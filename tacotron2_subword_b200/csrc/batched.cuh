@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) bt_attention_sma(Params p, Bufs b
     for (int j = tid; j < Ts; j += kThreads) {
       float a = ap_s[1 + j] * e_s[j];
       if (j > 0) a += ap_s[j] * (1.0f - e_s[j - 1]);
-      if (p.free_running && j >= len) a = 0.0f;   // batched free-running: padded positions do not exist
+      if ((p.free_running || p.independent) && j >= len) a = 0.0f;   // independent utterances: padded positions do not exist
       an_s[j] = a;
       sp.a_prev[(size_t)b * Ts + j] = a;
       align_out[j] = a;

@@ -65,6 +65,7 @@ struct StreamParams {
 struct Params {
   int B, T, S, H, D, E, P, A, M, LF, LK;
   int attention, free_running, training, max_steps, Tcap;
+  int independent;           // utterances are independent sequences: positions >= length do not exist (always so when free-running)
   float gate_thr, p_att, p_dec;
   unsigned thresh_pre, thresh_att, thresh_dec;  // Philox keep thresholds (u32 >= thresh -> keep)
   unsigned long long seed;
@@ -424,7 +425,7 @@ __device__ void attention_task(const Params& p, int s, int b, int t, float* sm) 
     for (int j = tid; j < Ts; j += kThreads) {
       float a = ap_s[pad + j] * e_s[j];
       if (j > 0) a += ap_s[pad + j - 1] * (1.0f - e_s[j - 1]);
-      if (p.free_running && j >= len) a = 0.0f;  // batched free-running: padded positions do not exist
+      if ((p.free_running || p.independent) && j >= len) a = 0.0f;  // independent utterances: padded positions do not exist
       an_s[j] = a;
       sp.a_prev[(size_t)b * Ts + j] = a;
       align_out[j] = a;
@@ -1744,6 +1745,7 @@ int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* 
   char* ws = (char*)a->workspace;
   fill_common(h, p, a->B, a->T_in, a->T_sub, a->memory, a->embeddings, a->memory_lengths, a->bert_lengths, a->rng, ws, L);
   p.T = a->T; p.Tcap = a->T; p.free_running = 0; p.training = a->training ? 1 : 0; p.max_steps = a->T;
+  p.independent = a->independent ? 1 : 0;
   p.dec_in = a->decoder_inputs;
   p.mel = a->mel; p.gate = a->gate;
   p.st[0].align = a->align;
@@ -1826,6 +1828,7 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
   p.h1 = p.c1 = p.h2 = p.c2 = p.ctx = p.q = nullptr;
   p.sync_ctr = nullptr; p.abort_flag = nullptr; p.done_count = nullptr; p.phase_clocks = nullptr;
   p.T = a->T; p.Tcap = a->T; p.free_running = 0; p.training = a->training ? 1 : 0; p.max_steps = a->T;
+  p.independent = a->independent ? 1 : 0;
   char* sb = (char*)const_cast<void*>(a->saved);
   char* gb = (char*)a->grads;
   bw::Grads g;

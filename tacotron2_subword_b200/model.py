@@ -146,9 +146,9 @@ class _DecoderTF(torch.autograd.Function):
     hoisted prenet -- are plain GEMMs over the rows it leaves behind (see ``taco2dec_grad_layout``)."""
 
     @staticmethod
-    def forward(ctx, dec, memory, embeddings, dec_in, mlen, blen, *params):
+    def forward(ctx, dec, independent, memory, embeddings, dec_in, mlen, blen, *params):
         ctx.set_materialize_grads(False)
-        outs, state = dec._run_tf(memory, embeddings, dec_in, mlen, blen, save=True)
+        outs, state = dec._run_tf(memory, embeddings, dec_in, mlen, blen, save=True, independent=independent)
         ctx.dec, ctx.state = dec, state
         ctx.n_params = len(params)
         mel, gate, align, align_b = outs
@@ -174,6 +174,7 @@ class _DecoderTF(torch.autograd.Function):
         a.memory, a.embeddings = _ptr(st["mem"]), _ptr(st["emb"])
         a.memory_lengths, a.bert_lengths = _ptr(st["mlen"]), _ptr(st["blen"])
         a.training = st["training"]
+        a.independent = st["independent"]
         a.rng = st["rng"]
         a.align, a.align_bert = _ptr(st["align"]), _ptr(st["align_b"])
         a.d_mel, a.d_gate, a.d_align, a.d_align_bert = _ptr(d_mel), _ptr(d_gate), _ptr(d_align), _ptr(d_align_b)
@@ -244,7 +245,7 @@ class _DecoderTF(torch.autograd.Function):
             torch.backends.cuda.matmul.allow_tf32 = old_tf32
         param_grads = tuple(grads.get(p_) if p_.requires_grad else None for p_ in st["params"])
         need = ctx.needs_input_grad
-        return (None, d_mems[0] if need[1] else None, d_mems[1] if (S == 2 and need[2]) else None, None, None, None) \
+        return (None, None, d_mems[0] if need[2] else None, d_mems[1] if (S == 2 and need[3]) else None, None, None, None) \
             + param_grads
 
 
@@ -403,11 +404,16 @@ class Decoder(nn.Module):
         return t
 
     # ------------------------------------------------------------------------------------
-    def forward(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths=None):
+    def forward(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths=None, independent: bool = False):
         """Teacher-forced pass (model.py:392-428).
 
         memory [B,T_in,E], embeddings [B,T_sub,E], decoder_inputs [B,n_mel,T], lengths int64 [B]
         -> mel [B,n_mel,T], gate [B,T], alignments [B,T,T_in], alignments_bert [B,T,T_sub].
+
+        ``independent=False`` is the reference's batched behaviour (with SMA, alignment mass leaks onto padded memory
+        positions).  ``independent=True`` (extension, used by ``gta.py``) treats every utterance as its own sequence:
+        row b equals the batch-1 run on ``memory[b, :memory_lengths[b]]``, which is what the reference's GTA.py computes
+        one utterance at a time.
 
         With autograd enabled the outputs carry a hand-written backward (``_DecoderTF``) when the shape is
         covered by the tensor path (2 <= B <= 128, SMA, default dims); other shapes raise at backward()."""
@@ -416,12 +422,13 @@ class Decoder(nn.Module):
             (embeddings is not None and embeddings.requires_grad))
         if wants_grad and self._backward_supported(memory):
             params = self._weight_tensors()
-            outs = _DecoderTF.apply(self, memory, embeddings if self.n_streams == 2 else None, decoder_inputs,
+            outs = _DecoderTF.apply(self, bool(independent), memory, embeddings if self.n_streams == 2 else None, decoder_inputs,
                                     memory_lengths, bert_lengths if self.n_streams == 2 else None, *params)
             mel, gate, align = outs[0], outs[1], outs[2]
             align_b = outs[3] if self.n_streams == 2 else None
             return mel.transpose(1, 2), gate, align, align_b
-        outs, _ = self._run_tf(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save=False)
+        outs, _ = self._run_tf(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save=False,
+                               independent=independent)
         mel, gate, align, align_b = outs
         outs = (mel.transpose(1, 2), gate, align, align_b)
         if wants_grad:
@@ -435,7 +442,7 @@ class Decoder(nn.Module):
                 and (self.attention_rnn_dim, self.decoder_rnn_dim, self.encoder_embedding_dim, self.prenet_dim,
                      self.attention_dim, self.n_mel_channels) == (1024, 1024, 512, 256, 128, 80))
 
-    def _run_tf(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save: bool):
+    def _run_tf(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save: bool, independent: bool = False):
         """One ``taco2dec_forward_teacher_forced`` call; mel is returned in its storage layout [B,T,n_mel]."""
         dev = self.gate_layer.linear_layer.weight.device
         eng = self._engine(dev)
@@ -465,6 +472,7 @@ class Decoder(nn.Module):
         a.memory, a.embeddings, a.decoder_inputs = _ptr(mem), _ptr(emb), _ptr(dec_in)
         a.memory_lengths, a.bert_lengths = _ptr(mlen), _ptr(blen)
         a.training = int(self.training)
+        a.independent = int(bool(independent))
         a.rng = self._rng(dev, keep)
         a.mel, a.gate, a.align, a.align_bert = _ptr(mel), _ptr(gate), _ptr(align), _ptr(align_b)
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
@@ -475,7 +483,7 @@ class Decoder(nn.Module):
             saved = torch.empty(int(SL.total), dtype=torch.uint8, device=dev)
             a.saved, a.saved_bytes = _ptr(saved), saved.numel()
             state = dict(eng=eng, dev=dev, B=B, T=T, T_in=T_in, T_sub=T_sub, mem=mem, emb=emb, dec_in=dec_in, mlen=mlen,
-                         blen=blen, training=int(self.training), rng=a.rng, keep=keep, align=align, align_b=align_b,
+                         blen=blen, training=int(self.training), independent=int(bool(independent)), rng=a.rng, keep=keep, align=align, align_b=align_b,
                          saved=saved, SL=SL, params=self._weight_tensors())
         with torch.cuda.device(dev):
             self._bind_weights(eng)

@@ -3,6 +3,8 @@ against (1) the committed reference goldens and (2) the CPU oracle on seeded inp
 
 Tolerances (north_star: teacher-forced mel max-abs <= 1e-3, alignments <= 1e-5, integer
 outputs exact).  The fp32 path is held to a much tighter bound so regressions show."""
+import os
+
 import pytest
 import torch
 
@@ -442,3 +444,77 @@ def test_tensor_path_single_stream_forward_and_backward():
         err = float((sd[name].grad.cpu() - gw).abs().max() / gw.abs().max())
         assert err < TOL_GRAD, (name, err)
     assert float((mem.grad.cpu() - want_dmem).abs().max() / want_dmem.abs().max()) < TOL_GRAD
+
+
+# ---------------------------------------------------------------------------------------------------
+# Independent-utterance teacher forcing (the batched form of the reference's GTA.py) and the GTA driver
+# ---------------------------------------------------------------------------------------------------
+def _sub_plan(plan, b, T_b):
+    from oracle.synth import DropoutPlan
+    pk = [[m[: T_b + 1, b:b + 1] for m in row] for row in plan.prenet_keep]
+    lk = None if plan.lstm_keep is None else plan.lstm_keep[:T_b, :, b:b + 1]
+    nz = None if plan.sma_noise is None else [n[:T_b, b:b + 1] for n in plan.sma_noise]
+    return DropoutPlan(prenet_keep=pk, lstm_keep=lk, sma_noise=nz)
+
+
+@pytest.mark.parametrize("path,wdtype,B,tol_mel,tol_align", [("generic", "fp32", 5, TOL_MEL, TOL_ALIGN),
+                                                             ("tensor", "fp16", 16, 1e-3, 2e-4)])
+def test_independent_teacher_forced_equals_per_utterance_batch1(path, wdtype, B, tol_mel, tol_align):
+    """Decoder.forward(..., independent=True): row b == the batch-1 oracle run on memory[b, :len_b] for its own T_b frames
+    (what GTA.py computes one utterance at a time), for ragged memory AND ragged output lengths."""
+    T_in, T_sub, T, seed = 23, 9, 11, 73
+    w = make_decoder_weights(SMA, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=True)
+    plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, False, seed=seed + 1)
+    g = torch.Generator().manual_seed(seed)
+    out_len = torch.randint(T // 2, T + 1, (B,), generator=g)
+    out_len[0] = T
+    dec = make_decoder(w, SMA).eval()
+    dec.decoder_path, dec.weight_dtype = path, wdtype
+    dec.dropout_replay = replay_of(plan)
+    with torch.no_grad():
+        mel, gate, al, alb = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(),
+                                 inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda(), independent=True)
+    assert dec._engine(torch.device("cuda", 0)).last_path() == path
+    orc = DecoderOracle(w, SMA)
+    differs_from_batched = False
+    for b in range(B):
+        Lm, Lb, Tb = int(inp["memory_lengths"][b]), int(inp["bert_lengths"][b]), int(out_len[b])
+        want = orc.forward(inp["memory"][b:b + 1, :Lm], inp["embeddings"][b:b + 1, :Lb], inp["mels"][b:b + 1, :, :Tb],
+                           torch.tensor([Lm]), torch.tensor([Lb]), _sub_plan(plan, b, Tb), training=False)
+        _cmp_tol((mel[b:b + 1, :, :Tb], gate[b:b + 1, :Tb], al[b:b + 1, :Tb, :Lm], alb[b:b + 1, :Tb, :Lb]), want,
+                 tol_mel, tol_align, f"{path} independent utt {b}")
+        if Lm < T_in:
+            assert float(al[b, :Tb, Lm:].abs().max()) == 0.0        # padded positions do not exist
+    # and it is a different function from the reference's batched semantics whenever something is padded
+    with torch.no_grad():
+        mel_batched = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(),
+                          inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())[0]
+    assert float((mel_batched - mel).abs().max()) > 1e-4
+
+
+def test_gta_driver_writes_reference_format(tmp_path):
+    """gta_extract: length-bucketed batches through the decoder, one float32 [1, 80, T] .npy per utterance (GTA.py:61),
+    identical to decoding that utterance's batch directly."""
+    import numpy as np
+    from tacotron2_subword_b200.gta import GtaItem, gta_extract
+    seed, n = 31, 37
+    w = make_decoder_weights(SMA, seed=seed)
+    dec = make_decoder(w, SMA).eval()
+    dec.weight_dtype, dec.rng_seed = "fp16", 99
+    g = torch.Generator().manual_seed(seed)
+    items = []
+    for i in range(n):
+        T_in, T = int(torch.randint(8, 30, (1,), generator=g)), int(torch.randint(5, 40, (1,), generator=g))
+        items.append(GtaItem(name=f"utt_{i:03d}", memory=0.5 * torch.randn(T_in, 512, generator=g),
+                             mel=torch.randn(80, T, generator=g), embeddings=0.5 * torch.randn(max(2, T_in // 3), 512, generator=g)))
+    files = gta_extract(dec, items, str(tmp_path), max_batch=16)
+    assert len(files) == n
+    for it in items:
+        a = np.load(tmp_path / (it.name + ".npy"))
+        assert a.dtype == np.float32 and a.shape == (1, 80, it.mel.shape[1]) and np.isfinite(a).all()
+    # two ranks write disjoint halves that together cover everything
+    f0 = gta_extract(dec, items, str(tmp_path / "r0"), max_batch=16, rank=0, world_size=2)
+    f1 = gta_extract(dec, items, str(tmp_path / "r1"), max_batch=16, rank=1, world_size=2)
+    names = sorted(os.path.basename(f) for f in f0 + f1)
+    assert names == sorted(it.name + ".npy" for it in items) and abs(len(f0) - len(f1)) <= 1
