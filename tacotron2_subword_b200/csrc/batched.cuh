@@ -3,16 +3,17 @@
 // Once batch x hidden makes the LSTM gate products genuine dense contractions they run on tcgen05
 // (gemm_tc.cuh): gates[4096, B] = [W_ih | W_hh][4096, K] x [x | h][B, K]^T with fp16 operands and fp32
 // accumulation in TMEM, 128 CTAs per GEMM (32 row tiles x split-K).  A frame is a short sequence of
-// kernels on one stream (no host synchronisation inside the loop):
+// kernels on one stream, captured once as a CUDA graph (no host synchronisation inside the loop):
 //
-//   x1 <- prenet[t]            bt_prenet_tf_to_x1 / bt_prenet_fr          (model.py:412-413 / 470-471)
+//   x1 <- prenet[t]            bt_prenet_fr (free-running); teacher-forced: copied by bt_pointwise1 of frame t-1
 //   G1  = A1 . X1^T            tcgen05 GEMM, 2 streams x split-K 2        (model.py:337-344)
 //   pointwise LSTM 1           -> c1, h1 (fp32) + fp16 tiles of X1', X2   (model.py:340-346)
 //   Q   = Wq . h1^T            tcgen05 GEMM (128 rows), split-K 4         (attention.py:56, 368)
-//   attention                  generic attention_task (fast energies) per (batch, stream) CTA
+//   attention                  bt_attention_sma (SMA) / generic attention_task (LSA), one CTA per (utterance, stream)
 //   G2  = A2 . X2^T            tcgen05 GEMM, split-K 4                    (model.py:362-371)
-//   pointwise LSTM 2           -> c2, h2                                  (model.py:371-373)
-//   projection + stop test     mel, gate                                  (model.py:382-388, 480-485)
+//   pointwise LSTM 2           -> c2, h2; teacher-forced: also advances the frame counter   (model.py:371-373)
+//   projection + stop test     free-running only; teacher-forced frames defer it to bt_proj_all after the loop
+//   frame counter              free-running only
 //
 // Every producer writes its fp16 output straight into the pre-tiled operand buffers of the GEMMs that
 // consume it (core-matrix layout of gemm_tc.cuh), so no separate packing pass exists.

@@ -1269,8 +1269,8 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   tc::GemmParams gq{bf.aq, bf.x2, bf.gq, 128, bt::H, bt::SPLITSQ, S, 0, 0, (bt::H + bt::E) / 64, done, B};
   tc::GemmParams g2{bf.a2, bf.x2, bf.g2, 4 * bt::H, bf.K2, bt::SPLITS2, 1, 0, 0, 0, done, B};
   CUDA_TRY(tc::prepare_gemm<NPAD>());
-  // One frame = 9 kernels; the frame index is read from device memory, so the sequence is captured ONCE into
-  // a CUDA graph and replayed n_steps times (one graph launch per frame instead of nine kernel launches).
+  // One frame = 9 kernels free-running, 6 teacher-forced; the frame index is read from device memory, so the sequence
+  // is captured ONCE into a CUDA graph and replayed n_steps times (one graph launch per frame).
   // Capture happens on a private stream (the caller's stream may be the legacy default stream, which cannot
   // be captured); the instantiated graph is launched on the caller's stream.
   int* t_ptr = p.done_count + 1;                      // control block word, zeroed by run_common
