@@ -17,6 +17,7 @@
 // waited on by exactly one thread that observes every phase in order.
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
 
 // fp32 row-major [rows][K] -> fp16 tiles ([row_tiles][K/64] tiles of rows_per_tile x 64), rows >= n_rows are zero
 __global__ void pack_tiles_kernel(const float* __restrict__ src, int n_rows, int K, int rows_per_tile, int n_row_tiles,
-                                  unsigned char* __restrict__ dst) {
+                                  unsigned char* __restrict__ dst, int as_bf16 = 0) {
   const size_t total = (size_t)n_row_tiles * rows_per_tile * K;
   const int kb_total = K / kBlockK;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -227,7 +228,9 @@ __global__ void pack_tiles_kernel(const float* __restrict__ src, int n_rows, int
     const int rt = r / rows_per_tile, rr = r - rt * rows_per_tile;
     const float v = r < n_rows ? src[(size_t)r * K + k] : 0.f;
     const size_t tile = ((size_t)rt * kb_total + (k / kBlockK)) * ((size_t)rows_per_tile * kBlockK * 2);
-    *reinterpret_cast<__half*>(dst + tile + tile_offset_bytes(rows_per_tile, rr, k % kBlockK)) = __float2half(v);
+    unsigned char* at = dst + tile + tile_offset_bytes(rows_per_tile, rr, k % kBlockK);
+    if (as_bf16) *reinterpret_cast<__nv_bfloat16*>(at) = __float2bfloat16(v);
+    else *reinterpret_cast<__half*>(at) = __float2half(v);
   }
 }
 

@@ -1543,9 +1543,14 @@ int run_test_gemm(int M, int N, int K, int splits, const float* A, const float* 
   CUDA_TRY(cudaMalloc(&a_t, (size_t)M * K * 2));
   CUDA_TRY(cudaMalloc(&x_t, (size_t)NPAD * K * 2));
   CUDA_TRY(cudaMalloc(&part, (size_t)splits * M * NPAD * sizeof(float)));
-  tc::pack_tiles_kernel<<<1024, 256, 0, st>>>(A, M, K, tc::kBlockM, M / tc::kBlockM, a_t);
-  tc::pack_tiles_kernel<<<256, 256, 0, st>>>(X, N, K, NPAD, 1, x_t);
+  // operand formats: default fp16 x fp16; TACO2DEC_GEMM_FMT = "bf16" (both) or "mixed" (fp16 weights x bf16 activations)
+  const char* fmt_env = getenv("TACO2DEC_GEMM_FMT");
+  const std::string fmt = fmt_env ? fmt_env : "";
+  const int a_bf16 = fmt == "bf16", x_bf16 = (fmt == "bf16" || fmt == "mixed");
+  tc::pack_tiles_kernel<<<1024, 256, 0, st>>>(A, M, K, tc::kBlockM, M / tc::kBlockM, a_t, a_bf16);
+  tc::pack_tiles_kernel<<<256, 256, 0, st>>>(X, N, K, NPAD, 1, x_t, x_bf16);
   tc::GemmParams gp{a_t, x_t, part, M, K, splits, 1, 0, 0, 0, nullptr, 0};
+  gp.fmt = ((unsigned)a_bf16 << 7) | ((unsigned)x_bf16 << 10);
   unsigned long long* dbg = nullptr;
   const int n_cta = (M / tc::kBlockM) * splits;
   if (getenv("TACO2DEC_GEMM_STAMPS")) {
