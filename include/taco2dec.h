@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TACO2DEC_ABI_VERSION 3
+#define TACO2DEC_ABI_VERSION 4
 
 #define TACO2DEC_ATTN_SMA 0 /* StepwiseMonotonicAttention   (attention.py:291-398, hparams default) */
 #define TACO2DEC_ATTN_LSA 1 /* LocationSensitiveAttention   (attention.py:7-85)                      */
@@ -134,7 +134,7 @@ typedef struct taco2dec_tf_args {
                          its own sequence, exactly as if it had been run alone at batch 1 on its un-padded memory (what
                          GTA.py:35-61 does one utterance at a time): positions >= length do not exist */
   void* saved;        /* NULL, or a buffer of taco2dec_saved_layout_query().total bytes: the call keeps the activations
-                         taco2dec_backward needs (tensor path only: 2 <= B <= 128, SMA, default dims) */
+                         taco2dec_backward needs (tensor path only: 2 <= B <= 128, default dims) */
   size_t saved_bytes;
 } taco2dec_tf_args;
 
@@ -169,6 +169,8 @@ typedef struct taco2dec_grad_layout {
   size_t dpre;     /* [S][T][B][prenet] gradient of the prenet output fed to frame t */
   size_t dv;       /* [S][B][A]       */
   size_t dpm[2];   /* [B][T_s][A]     gradient of the processed memory             */
+  size_t dloc_dense; /* LSA: [S][B][A][F]     per-utterance sums, location_dense weight gradient (attention.py:16-17) */
+  size_t dloc_conv;  /* LSA: [S][B][F][2][K]  per-utterance sums, location_conv weight gradient  (attention.py:12-15) */
   size_t scratch;  /* internal carries (d alignment state, d cell states) */
   size_t total;
 } taco2dec_grad_layout;

@@ -158,6 +158,7 @@ def run_reference(case: dict, seed: int = None):
 GRAD_CASES = {
     "grad_sma_train_B16": dict(mode="tf", attention=SMA, B=16, T_in=24, T_sub=8, T=5, ragged=True, training=True, seed=516),
     "grad_sma_eval_B3": dict(mode="tf", attention=SMA, B=3, T_in=11, T_sub=4, T=4, ragged=True, training=False, seed=33),
+    "grad_lsa_train_B4": dict(mode="tf", attention=LSA, B=4, T_in=19, T_sub=7, T=5, ragged=True, training=True, seed=44),
 }
 
 

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtac
 ATTN_SMA, ATTN_LSA = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR = 0, 1, 2, 3
 W_FP32, W_FP16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTED_SYMBOLS = (
     "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
@@ -68,7 +68,8 @@ class SavedLayout(C.Structure):
 
 class GradLayout(C.Structure):
     _fields_ = [("dg1", C.c_size_t), ("dg2", C.c_size_t), ("dq", C.c_size_t), ("dctx", C.c_size_t),
-                ("dpre", C.c_size_t), ("dv", C.c_size_t), ("dpm", C.c_size_t * 2), ("scratch", C.c_size_t),
+                ("dpre", C.c_size_t), ("dv", C.c_size_t), ("dpm", C.c_size_t * 2), ("dloc_dense", C.c_size_t),
+                ("dloc_conv", C.c_size_t), ("scratch", C.c_size_t),
                 ("total", C.c_size_t)]
 
 

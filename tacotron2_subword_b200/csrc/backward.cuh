@@ -60,6 +60,11 @@ struct Grads {
   float *dc1, *dc2;// [S][B][H], [B][H] carry: d cell state
   float* dyh;      // [T][H][B]      projection backwards, decoder-LSTM hidden columns   (bw_dy_all)
   float* dyc;      // [T][B][S*E]    projection backwards, context columns
+  // location-sensitive attention only
+  float* dcum[2];  // [B][Ts]        carry: d cumulative attention weights
+  float* dz[2];    // [B][Ts][A]     scratch: d tanh-argument of the current frame
+  float* dwd;      // [S][B][A*LF]   per-utterance partial sums, location_dense weight gradient [a][f]
+  float* dwc;      // [S][B][LF*2*LK] per-utterance partial sums, location_conv weight gradient [f][c][k]
 };
 
 __device__ __forceinline__ void xb_store(unsigned char* xbase, int NPAD, int b, int k, float v) {
@@ -428,6 +433,194 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_attention(Params p, Bufs bb,
   for (int a = tid; a < A; a += kBwThreads) {
     g.dq[(((size_t)s * p.T + t) * p.B + b) * A + a] = dq_s[a];
     g.dv[((size_t)s * p.B + b) * A + a] += dv_s[a];
+  }
+}
+
+// location-sensitive attention backwards (attention.py:7-85), one CTA per (utterance, stream):
+//   feat = conv1d(cat(alpha[t-1], cum[t-1]))  ->  loc = dense(feat)  ->  e = v . tanh(q + pm + loc)  ->  alpha = softmax(e)
+//   ctx = alpha . memory,  cum[t] = cum[t-1] + alpha[t]                                            (model.py:358-359)
+// alpha[t] receives gradient from the context, from frame t+1's convolution input (carry dalpha) and, through the
+// cumulative weights, from the convolution inputs of every later frame (carry dcum, a running sum).
+constexpr int kLF = 32, kLK = 31, kLPad = 15;
+__host__ __device__ inline size_t bw_lsa_smem_floats(int Ts) {
+  return (size_t)E + 4 * A + (size_t)kLF * A + 2 * kLK * kLF + 4 * (size_t)(Ts + 4) + 2 * (size_t)(Ts + 2 * kLPad + 2) +
+         2 * (size_t)Ts * kLF + (kBwThreads / 32) * A + 64;
+}
+__global__ void __launch_bounds__(kBwThreads, 1) bw_attention_lsa(Params p, Bufs bb, Grads g, const int* t_ptr) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = *t_ptr;
+  const int s = blockIdx.x % p.S, b = blockIdx.x / p.S, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kW = kBwThreads / 32;
+  const StreamParams& sp = p.st[s];
+  const int Ts = sp.Ts, Tp = Ts + 2 * kLPad;
+  const int len = sp.len ? (int)sp.len[b] : Ts;
+  float* dctx_s = sm;                       // E
+  float* q_s = dctx_s + E;                  // A
+  float* v_s = q_s + A;                     // A
+  float* dq_s = v_s + A;                    // A
+  float* dv_s = dq_s + A;                   // A
+  float* wd_s = dv_s + A;                   // LF*A  location_dense^T [f][a]
+  float* wc_s = wd_s + kLF * A;             // 2*LK*LF  location_conv [c][k][f]
+  float* al_s = wc_s + 2 * kLK * kLF;       // Ts+4  alpha[t]
+  float* dan_s = al_s + Ts + 4;             // Ts+4  d alpha[t]
+  float* de_s = dan_s + Ts + 4;             // Ts+4
+  float* red_s = de_s + Ts + 4;             // Ts+4 (only 32 used)
+  float* in0_s = red_s + Ts + 4;            // Tp+2  padded alpha[t-1]
+  float* in1_s = in0_s + Tp + 2;            // Tp+2  padded cum[t-1]
+  float* feat_s = in1_s + Tp + 2;           // Ts*LF
+  float* dfeat_s = feat_s + (size_t)Ts * kLF;   // Ts*LF
+  float* dzw_s = dfeat_s + (size_t)Ts * kLF;    // kW*A per-warp staging of dz
+
+  for (int d = tid; d < E; d += kBwThreads) {
+    float acc = g.dyc[((size_t)t * p.B + b) * (p.S * E) + s * E + d];
+#pragma unroll
+    for (int k = 0; k < SPLITSB1; ++k) acc += bb.dx1[(((size_t)s * SPLITSB1 + k) * K1 + P + d) * bb.NPAD + b];
+#pragma unroll
+    for (int k = 0; k < SPLITSB2; ++k) acc += bb.dx2[((size_t)k * bb.K2 + s * (H + E) + H + d) * bb.NPAD + b];
+    dctx_s[d] = acc;
+    g.dctx[(((size_t)s * p.T + t) * p.B + b) * E + d] = acc;
+  }
+  for (int a = tid; a < A; a += kBwThreads) {
+    q_s[a] = g.sv.q[(((size_t)t * p.S + s) * p.B + b) * A + a];
+    v_s[a] = sp.v[a];
+    dq_s[a] = 0.f;
+    dv_s[a] = 0.f;
+  }
+  for (int i = tid; i < kLF * A; i += kBwThreads) { const int f = i / A, a = i - f * A; wd_s[i] = sp.loc_dense[(size_t)a * kLF + f]; }
+  for (int i = tid; i < 2 * kLK * kLF; i += kBwThreads) { const int f = i % kLF, ck = i / kLF; wc_s[i] = sp.loc_conv[(size_t)f * 2 * kLK + ck]; }
+  for (int i = tid; i < Tp; i += kBwThreads) {
+    const int j = i - kLPad;
+    const bool in = j >= 0 && j < Ts;
+    in0_s[i] = (in && t > 0) ? g.align[s][((size_t)b * p.T + (t - 1)) * Ts + j] : 0.f;
+    in1_s[i] = in ? g.p_saved[s][((size_t)t * p.B + b) * Ts + j] : 0.f;
+  }
+  for (int j = tid; j < Ts; j += kBwThreads) {
+    al_s[j] = g.align[s][((size_t)b * p.T + t) * Ts + j];
+    float d = g.dalpha[s][(size_t)b * Ts + j] + g.dcum[s][(size_t)b * Ts + j];
+    if (g.d_align[s]) d += g.d_align[s][((size_t)b * p.T + t) * Ts + j];
+    dan_s[j] = d;
+  }
+  __syncthreads();
+  // d alpha_j += d ctx . memory_j
+  {
+    const float* mem_b = sp.mem + (size_t)b * Ts * E;
+    const float4* dc4 = reinterpret_cast<const float4*>(dctx_s);
+    for (int j = warp; j < Ts; j += kW) {
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j * E) + lane + 32 * q);
+        const float4 dv = dc4[lane + 32 * q];
+        acc = fmaf(m.x, dv.x, acc); acc = fmaf(m.y, dv.y, acc); acc = fmaf(m.z, dv.z, acc); acc = fmaf(m.w, dv.w, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) dan_s[j] += acc;
+    }
+  }
+  // location features of this frame (recomputed): feat[j][f] = sum_k Wc[f][0][k] a_prev[j+k-15] + Wc[f][1][k] cum[j+k-15]
+  for (int i = tid; i < Ts * kLF; i += kBwThreads) {
+    const int j = i / kLF, f = i - j * kLF;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLK; ++k) {
+      acc = fmaf(wc_s[k * kLF + f], in0_s[j + k], acc);
+      acc = fmaf(wc_s[(kLK + k) * kLF + f], in1_s[j + k], acc);
+    }
+    feat_s[i] = acc;
+    dfeat_s[i] = 0.f;
+  }
+  __syncthreads();
+  // softmax backwards: de_j = alpha_j (d alpha_j - sum_k alpha_k d alpha_k)
+  {
+    float part = 0.f;
+    for (int j = tid; j < Ts; j += kBwThreads) part = fmaf(al_s[j], dan_s[j], part);
+    part = warp_sum(part);
+    if (lane == 0) red_s[warp] = part;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < kW; ++w) tot += red_s[w];
+    for (int j = tid; j < Ts; j += kBwThreads) de_s[j] = al_s[j] * (dan_s[j] - tot);
+  }
+  __syncthreads();
+  // energies backwards, one warp per position
+  {
+    const float* pm_b = sp.pm + (size_t)b * Ts * A;
+    float* dpm_b = g.dpm[s] + (size_t)b * Ts * A;
+    float* dz_b = g.dz[s] + (size_t)b * Ts * A;
+    float* dzw = dzw_s + warp * A;
+    float dq_acc[4] = {0.f, 0.f, 0.f, 0.f}, dv_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = warp; j < len; j += kW) {
+      const float de = de_s[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int a = lane + 32 * q;
+        float loc = 0.f;
+#pragma unroll 8
+        for (int f = 0; f < kLF; ++f) loc = fmaf(wd_s[f * A + a], feat_s[j * kLF + f], loc);
+        const float u = tanhf(q_s[a] + __ldg(pm_b + (size_t)j * A + a) + loc);
+        const float dz = de * v_s[a] * (1.0f - u * u);
+        dq_acc[q] += dz;
+        dv_acc[q] = fmaf(de, u, dv_acc[q]);
+        dpm_b[(size_t)j * A + a] += dz;
+        dz_b[(size_t)j * A + a] = dz;
+        dzw[a] = dz;
+      }
+      __syncwarp();
+      {  // d feat[j][f] = sum_a dz[a] Wd[a][f]   (lane = f)
+        float acc = 0.f;
+#pragma unroll 8
+        for (int a = 0; a < A; ++a) acc = fmaf(dzw[a], wd_s[lane * A + a], acc);
+        dfeat_s[j * kLF + lane] = acc;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      atomicAdd(&dq_s[lane + 32 * q], dq_acc[q]);
+      atomicAdd(&dv_s[lane + 32 * q], dv_acc[q]);
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  for (int a = tid; a < A; a += kBwThreads) {
+    g.dq[(((size_t)s * p.T + t) * p.B + b) * A + a] = dq_s[a];
+    g.dv[((size_t)s * p.B + b) * A + a] += dv_s[a];
+  }
+  // location_dense weight gradient: dWd[a][f] += sum_j dz[j][a] feat[j][f]   (thread = a, 8 filters)
+  {
+    const int a = tid & (A - 1), f0 = (tid / A) * 8;
+    const float* dz_b = g.dz[s] + (size_t)b * Ts * A;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < len; ++j) {
+      const float dz = dz_b[(size_t)j * A + a];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) acc[f] = fmaf(dz, feat_s[j * kLF + f0 + f], acc[f]);
+    }
+    float* dst = g.dwd + ((size_t)s * p.B + b) * (A * kLF) + (size_t)a * kLF + f0;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) dst[f] += acc[f];
+  }
+  // convolution backwards: inputs (-> carries for frame t-1) and weights
+  for (int i = tid; i < 2 * Ts; i += kBwThreads) {
+    const int c = i / Ts, pos = i - c * Ts;
+    float acc = 0.f;
+    for (int k = 0; k < kLK; ++k) {
+      const int j = pos - k + kLPad;                 // output position that read input `pos` through tap k
+      if (j < 0 || j >= Ts) continue;
+      const float* df = dfeat_s + j * kLF;
+      const float* w = wc_s + (c * kLK + k) * kLF;
+#pragma unroll 8
+      for (int f = 0; f < kLF; ++f) acc = fmaf(df[f], w[f], acc);
+    }
+    if (c == 0) g.dalpha[s][(size_t)b * Ts + pos] = acc;            // d alpha[t-1] through the "previous weights" channel
+    else g.dcum[s][(size_t)b * Ts + pos] += acc;                    // running sum over all later frames
+  }
+  for (int i = tid; i < kLF * 2 * kLK; i += kBwThreads) {
+    const int f = i / (2 * kLK), ck = i - f * 2 * kLK, c = ck / kLK, k = ck - c * kLK;
+    const float* in = c == 0 ? in0_s : in1_s;
+    float acc = 0.f;
+    for (int j = 0; j < len; ++j) acc = fmaf(dfeat_s[j * kLF + f], in[j + k], acc);
+    g.dwc[((size_t)s * p.B + b) * (kLF * 2 * kLK) + i] += acc;
   }
 }
 

@@ -58,7 +58,8 @@ struct StreamParams {
   float* a_prev;            // [B, Ts]  SMA: alignment state; LSA: previous attention weights
   float* a_cum;             // [B, Ts]  LSA cumulative weights
   float* align;             // [B, Tcap, Ts] output
-  float* p_save;            // [T, B, Ts] SMA selection probabilities kept for the backward pass, or null
+  float* p_save;            // [T, B, Ts] kept for the backward pass, or null: SMA selection probabilities /
+                            // LSA cumulative weights entering the frame
   int Ts;
 };
 
@@ -461,6 +462,7 @@ __device__ void attention_task(const Params& p, int s, int b, int t, float* sm) 
       an_s[j] = a;
       sp.a_prev[(size_t)b * Ts + j] = a;
       sp.a_cum[(size_t)b * Ts + j] = ac_s[pad + j] + a;  // model.py:358-359
+      if (sp.p_save) sp.p_save[((size_t)t * p.B + b) * Ts + j] = ac_s[pad + j];   // cumulative weights entering the frame
       align_out[j] = a;
     }
   }
@@ -1361,7 +1363,7 @@ taco2dec_saved_layout plan_saved(const taco2dec_config& c, int B, int T_in, int 
   return L;
 }
 
-struct GradScratch { size_t dalpha[2], dc1, dc2, zero_begin, zero_end, dyh, dyc; };
+struct GradScratch { size_t dalpha[2], dcum[2], dz[2], dc1, dc2, zero_begin, zero_end, dyh, dyc; };
 
 taco2dec_grad_layout plan_grads(const taco2dec_config& c, int B, int T_in, int T_sub, int T, GradScratch* gs) {
   taco2dec_grad_layout L;
@@ -1379,22 +1381,31 @@ taco2dec_grad_layout plan_grads(const taco2dec_config& c, int B, int T_in, int T
   const size_t zero_begin = off;
   L.dv = take((size_t)S * B * c.attn_dim);
   for (int s = 0; s < 2; ++s) L.dpm[s] = take(s < S ? (size_t)B * Ts[s] * c.attn_dim : 0);
+  const bool lsa = c.attention == TACO2DEC_ATTN_LSA;
+  L.dloc_dense = take(lsa ? (size_t)S * B * c.attn_dim * c.loc_filters : 0);
+  L.dloc_conv = take(lsa ? (size_t)S * B * c.loc_filters * 2 * c.loc_kernel : 0);
   L.scratch = off;
   GradScratch g;
   for (int s = 0; s < 2; ++s) g.dalpha[s] = take(s < S ? (size_t)B * Ts[s] : 0);
+  for (int s = 0; s < 2; ++s) g.dcum[s] = take((lsa && s < S) ? (size_t)B * Ts[s] : 0);
   g.dc1 = take((size_t)S * B * H);
   g.dc2 = take((size_t)B * D);
   g.zero_begin = zero_begin;
   g.zero_end = off;
   g.dyh = take((size_t)T * D * B);
   g.dyc = take((size_t)T * B * S * c.enc_dim);
+  for (int s = 0; s < 2; ++s) g.dz[s] = take((lsa && s < S) ? (size_t)B * Ts[s] * c.attn_dim : 0);
   L.total = off;
   if (gs) *gs = g;
   return L;
 }
 
 bool bw_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
-  return h->cfg.attention == TACO2DEC_ATTN_SMA && bt_shape_ok(h, B, T_in, T_sub);
+  if (!bt_shape_ok(h, B, T_in, T_sub)) return false;
+  if (h->cfg.attention == TACO2DEC_ATTN_SMA) return true;
+  // LSA backward: compiled for the default location layer; its shared-memory plan grows with the memory length
+  return h->cfg.loc_filters == bw::kLF && h->cfg.loc_kernel == bw::kLK &&
+         bw::bw_lsa_smem_floats(std::max(T_in, T_sub)) * sizeof(float) <= (size_t)h->max_smem_optin;
 }
 
 int bw_prepare(taco2dec_handle* h, cudaStream_t st) {
@@ -1442,8 +1453,10 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
   bw::bw_dy_all<<<dim3((p.T * B + bw::kDyRows - 1) / bw::kDyRows, (bt::H + S * bt::E) / bw::kDyCols), 256, 0, st>>>(p, g);
   int max_ts = 0;
   for (int s = 0; s < S; ++s) max_ts = std::max(max_ts, p.st[s].Ts);
-  const size_t att_smem = bw::bw_attention_smem_floats(max_ts) * sizeof(float);
-  CUDA_TRY(cudaFuncSetAttribute(bw::bw_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  const bool lsa = p.attention == TACO2DEC_ATTN_LSA;
+  const size_t att_smem = (lsa ? bw::bw_lsa_smem_floats(max_ts) : bw::bw_attention_smem_floats(max_ts)) * sizeof(float);
+  if (lsa) CUDA_TRY(cudaFuncSetAttribute(bw::bw_attention_lsa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  else CUDA_TRY(cudaFuncSetAttribute(bw::bw_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
   tc::GemmParams gb2{bb.a2t, bb.dg2, bb.dx2, bb.K2, bw::G, bw::SPLITSB2, 1, 0, 0, 0, nullptr, 0, tc::kFmtBF16};
   tc::GemmParams gb1{bb.a1t, bb.dg1, bb.dx1, bt::K1, bw::G, bw::SPLITSB1, S, (long long)(bw::G / 64) * NPAD * 128, 0, 0,
                      nullptr, 0, tc::kFmtBF16};
@@ -1456,7 +1469,8 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
   const int pw_blocks = ((B + bw::kPwB - 1) / bw::kPwB) * (bt::H / bw::kPwJ);
   bw::bw_pointwise2<<<pw_blocks, 256, 0, cs>>>(p, bb, g, t_ptr);
   cudaError_t ce = tc::launch_gemm<NPAD>(gb2, cs);
-  bw::bw_attention<<<S * B, bw::kBwThreads, att_smem, cs>>>(p, bb, g, t_ptr);
+  if (lsa) bw::bw_attention_lsa<<<S * B, bw::kBwThreads, att_smem, cs>>>(p, bb, g, t_ptr);
+  else bw::bw_attention<<<S * B, bw::kBwThreads, att_smem, cs>>>(p, bb, g, t_ptr);
   bw::bw_pointwise1<<<S * pw_blocks, 256, 0, cs>>>(p, bb, g, t_ptr);
   if (ce == cudaSuccess) ce = tc::launch_gemm<NPAD>(gb1, cs);
   const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
@@ -1497,7 +1511,7 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
   CUDA_TRY(cudaGetLastError());
   if (h->cur_sv.gates1) {   // activations are kept for backward: only the tensor path produces them
     if (!bw_shape_ok(h, p.B, T_in, T_sub) || (h->path_mode != TACO2DEC_PATH_AUTO && h->path_mode != TACO2DEC_PATH_TENSOR))
-      return fail(TACO2DEC_E_ARG, "saving activations for backward needs the tensor path: 2 <= B <= 128, SMA, default decoder dims");
+      return fail(TACO2DEC_E_ARG, "saving activations for backward needs the tensor path: 2 <= B <= 128, default decoder dims");
     return run_batched(h, p, T_in, T_sub, st);
   }
   const bool want_lat = (h->path_mode == TACO2DEC_PATH_AUTO || h->path_mode == TACO2DEC_PATH_LATENCY) &&
@@ -1816,7 +1830,7 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
   if (c.n_streams == 2 && (!a->embeddings || !a->align_bert)) return fail(TACO2DEC_E_ARG, "sub-word stream tensors missing");
   const int T_sub = std::max(a->T_sub, 1);
   if (!bw_shape_ok(h, a->B, a->T_in, T_sub))
-    return fail(TACO2DEC_E_ARG, "backward needs the tensor path: 2 <= B <= 128, SMA, default decoder dims");
+    return fail(TACO2DEC_E_ARG, "backward needs the tensor path: 2 <= B <= 128, default decoder dims");
   if ((reinterpret_cast<uintptr_t>(a->saved) & 255u) || (reinterpret_cast<uintptr_t>(a->grads) & 255u))
     return fail(TACO2DEC_E_ARG, "saved / grads buffers must be 256-byte aligned");
   const taco2dec_saved_layout SL = plan_saved(c, a->B, a->T_in, T_sub, a->T);
@@ -1851,7 +1865,10 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
     g.d_align[s] = d_aligns[s];
     g.dpm[s] = (float*)(gb + GL.dpm[s]);
     g.dalpha[s] = (float*)(gb + gs.dalpha[s]);
+    g.dcum[s] = (float*)(gb + gs.dcum[s]);
+    g.dz[s] = (float*)(gb + gs.dz[s]);
   }
+  g.dwd = (float*)(gb + GL.dloc_dense); g.dwc = (float*)(gb + GL.dloc_conv);
   g.d_mel = a->d_mel; g.d_gate = a->d_gate;
   g.dg1 = (float*)(gb + GL.dg1); g.dg2 = (float*)(gb + GL.dg2); g.dq = (float*)(gb + GL.dq);
   g.dctx = (float*)(gb + GL.dctx); g.dpre = (float*)(gb + GL.dpre); g.dv = (float*)(gb + GL.dv);

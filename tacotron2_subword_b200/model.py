@@ -119,7 +119,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class _NoBackward(torch.autograd.Function):
     """Marks decoder outputs as differentiable so training code fails LOUDLY at backward()
     instead of silently skipping the decoder when the shape has no backward kernel (the BPTT
-    kernels cover the tensor path: 2 <= B <= 128, SMA, default dims)."""
+    kernels cover the tensor path: 2 <= B <= 128, default dims)."""
 
     @staticmethod
     def forward(ctx, anchor, *outs):
@@ -129,7 +129,7 @@ class _NoBackward(torch.autograd.Function):
     def backward(ctx, *grads):
         raise NotImplementedError(
             "tacotron2_subword_b200: decoder backward is implemented for the tensor path only "
-            "(2 <= batch <= 128, StepwiseMonotonicAttention, default decoder dims)")
+            "(2 <= batch <= 128, default decoder dims)")
 
 
 def _fview(buf: torch.Tensor, off: int, *shape) -> torch.Tensor:
@@ -218,6 +218,12 @@ class _DecoderTF(torch.autograd.Function):
                 grads[rnn.bias_ih], grads[rnn.bias_hh] = db, db.clone()
                 grads[att.query_layer.linear_layer.weight] = dq[s].t() @ h1[1:, s].reshape(T * B, H)
                 grads[att.v_weight()] = dv[s].sum(0).view(1, A)
+                if dec.attention_kind == LSA:
+                    LF, LK = dec.loc_filters, dec.loc_kernel
+                    grads[att.location_layer.location_dense.linear_layer.weight] = \
+                        _fview(gbuf, GL.dloc_dense, S, B, A, LF)[s].sum(0)
+                    grads[att.location_layer.location_conv.conv.weight] = \
+                        _fview(gbuf, GL.dloc_conv, S, B, LF, 2, LK)[s].sum(0)
                 dpm = _fview(gbuf, GL.dpm[s], B, Ts[s], A)
                 wm = att.memory_layer.linear_layer.weight
                 grads[wm] = dpm.reshape(-1, A).t() @ mems[s].reshape(-1, E)
@@ -416,7 +422,7 @@ class Decoder(nn.Module):
         one utterance at a time.
 
         With autograd enabled the outputs carry a hand-written backward (``_DecoderTF``) when the shape is
-        covered by the tensor path (2 <= B <= 128, SMA, default dims); other shapes raise at backward()."""
+        covered by the tensor path (2 <= B <= 128, default dims); other shapes raise at backward()."""
         wants_grad = torch.is_grad_enabled() and (
             any(p.requires_grad for p in self.parameters()) or memory.requires_grad or
             (embeddings is not None and embeddings.requires_grad))
@@ -438,7 +444,9 @@ class Decoder(nn.Module):
         return outs
 
     def _backward_supported(self, memory) -> bool:
-        return (self.attention_kind == SMA and 2 <= memory.shape[0] <= 128 and self.decoder_path in ("auto", "tensor")
+        if self.attention_kind == LSA and (self.loc_filters, self.loc_kernel) != (32, 31):
+            return False
+        return (2 <= memory.shape[0] <= 128 and self.decoder_path in ("auto", "tensor")
                 and (self.attention_rnn_dim, self.decoder_rnn_dim, self.encoder_embedding_dim, self.prenet_dim,
                      self.attention_dim, self.n_mel_channels) == (1024, 1024, 512, 256, 128, 80))
 

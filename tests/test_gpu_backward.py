@@ -29,8 +29,8 @@ def _loss(outs, seed):
     return total
 
 
-def _oracle_grads(w, inp, plan, training, dims=DecoderDims()):
-    orc = DecoderOracle(w, SMA, dims=dims)
+def _oracle_grads(w, inp, plan, training, dims=DecoderDims(), attention=SMA):
+    orc = DecoderOracle(w, attention, dims=dims)
     orc.w = {k: v.clone().requires_grad_(True) for k, v in orc.w.items()}
     mem = inp["memory"].clone().requires_grad_(True)
     emb = inp["embeddings"].clone().requires_grad_(True) if dims.streams == 2 else None
@@ -122,17 +122,57 @@ def test_backward_philox_masks_match_forward():
 
 
 def test_backward_unsupported_shape_raises():
-    """Batch 1 (latency path) and LSA have no backward kernel: the forward output must refuse backward() loudly."""
-    from oracle.synth import LSA
-    for attention, B in ((SMA, 1), (LSA, 4)):
+    """Batch 1 (latency path) and a forced generic path have no backward kernel: the output must refuse backward() loudly."""
+    for B, path in ((1, "auto"), (4, "generic")):
         T, T_in, T_sub, seed = 3, 12, 4, 7
-        w = make_decoder_weights(attention, seed=seed)
+        w = make_decoder_weights(SMA, seed=seed)
         inp = make_inputs(B, T_in, T_sub, T, seed=seed)
-        dec = make_decoder(w, attention).train()
+        dec = make_decoder(w, SMA).train()
+        dec.decoder_path = path
         outs = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(), inp["memory_lengths"].cuda(),
                    inp["bert_lengths"].cuda())
         with pytest.raises(NotImplementedError):
             outs[0].sum().backward()
+
+
+@pytest.mark.parametrize("B,T,training,T_in,T_sub", [(4, 5, False, 24, 8), (16, 4, True, 40, 13), (33, 3, True, 70, 20)])
+def test_lsa_backward_vs_oracle_autograd(B, T, training, T_in, T_sub):
+    """Location-sensitive attention (attention.py:7-85): softmax, the location conv/dense layers and the cumulative
+    weights are differentiated by bw_attention_lsa; all 30 live parameter gradients + d memory / d embeddings vs autograd
+    through the oracle."""
+    from oracle.synth import LSA
+    seed = 700 + B
+    w = make_decoder_weights(LSA, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=True)
+    plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, training, seed=seed + 1)
+    want, want_dmem, want_demb, want_outs = _oracle_grads(w, inp, plan, training, attention=LSA)
+    dec = make_decoder(w, LSA)
+    dec.decoder_path, dec.weight_dtype = "tensor", "fp16"
+    dec.dropout_replay = replay_of(plan)
+    dec.train(training)
+    mem = inp["memory"].cuda().requires_grad_(True)
+    emb = inp["embeddings"].cuda().requires_grad_(True)
+    outs = dec(mem, emb, inp["mels"].cuda(), inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+    for o, wo in zip(outs, want_outs):
+        assert (o.detach().cpu() - wo.detach()).abs().max() < 1e-3
+    _loss(outs, 5).backward()
+    sd = dict(dec.named_parameters())
+    worst = {}
+    n_live = 0
+    for name, gw in want.items():
+        got = sd[name].grad
+        if gw is None:
+            assert got is None, name
+            continue
+        n_live += 1
+        assert got is not None, f"{name}: no gradient"
+        worst[name] = float((got.cpu() - gw).abs().max() / gw.abs().max())
+    for name, gw, got in (("memory", want_dmem, mem.grad), ("embeddings", want_demb, emb.grad)):
+        worst[name] = float((got.cpu() - gw).abs().max() / gw.abs().max())
+    print({k: f"{v:.1e}" for k, v in worst.items() if "location" in k or "attention_layer" in k})
+    assert n_live == 30
+    bad = {k: v for k, v in worst.items() if not v < TOL_GRAD}
+    assert not bad, f"relative gradient error above {TOL_GRAD}: {bad}"
 
 
 def test_model_training_step_end_to_end():
@@ -186,15 +226,16 @@ def test_model_training_step_end_to_end():
     assert float(loss1.detach()) < float(loss0.detach())       # same dropout seed, small SGD step: the loss goes down
 
 
-def test_backward_vs_reference_gradient_digests():
-    """CUDA backward against digests of the REFERENCE's own autograd (tests/golden/grad_sma_train_B16.npz, made by
+@pytest.mark.parametrize("name", ["grad_sma_train_B16", "grad_sma_eval_B3", "grad_lsa_train_B4"])
+def test_backward_vs_reference_gradient_digests(name):
+    """CUDA backward against digests of the REFERENCE's own autograd (tests/golden/grad_*.npz, made by
     oracle/make_golden.py from the unmodified reference): max|g|, a seeded random projection, the sum and the first 32
     elements of every gradient tensor, each within TOL_GRAD of max|g_ref|."""
     from oracle.synth import seeded_loss
     from tests.helpers import check_grad_digest, load_grad_golden, materialise
-    recipe, digests, _ = load_grad_golden("grad_sma_train_B16")
+    recipe, digests, _ = load_grad_golden(name)
     w, inp, plan = materialise(recipe)
-    dec = make_decoder(w, SMA)
+    dec = make_decoder(w, recipe["attention"])
     dec.decoder_path, dec.weight_dtype = "tensor", "fp16"
     dec.dropout_replay = replay_of(plan)
     dec.train(recipe["training"])
