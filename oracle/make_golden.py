@@ -192,8 +192,30 @@ def run_reference_grads(case: dict, loss_seed: int = 5):
     return res
 
 
+def run_reference_postnet(seed: int = 21, B: int = 3, T: int = 37):
+    """Unmodified reference Postnet (model.py:27-70) in eval mode on seeded weights / BatchNorm statistics."""
+    from oracle.postnet_oracle import make_postnet_weights
+    ref_model, _, ref_hparams = ref_shim.import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        hp = ref_hparams.create_hparams()
+    net = ref_model.Postnet(hp).eval()
+    w = make_postnet_weights(seed)
+    sd = net.state_dict()
+    for k in sd:
+        if k in w:
+            sd[k] = w[k]
+    net.load_state_dict(sd, strict=True)
+    x = torch.randn(B, hp.n_mel_channels, T, generator=torch.Generator().manual_seed(seed + 1))
+    with torch.no_grad():
+        y = net(x)
+    return {"x": x.numpy(), "y": y.numpy(), "seed": np.array(seed)}
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    res = run_reference_postnet()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "postnet_eval.npz"), **res)
+    print(f"postnet_eval: y{res['y'].shape}")
     for name, case in GRAD_CASES.items():
         res = run_reference_grads(case)
         path = os.path.join(GOLDEN_DIR, name + ".npz")
