@@ -278,6 +278,41 @@ int taco2dec_read_phase_clocks(taco2dec_handle* h, void* cuda_stream, long long*
 /* Persistent-kernel launch geometry actually used (for DESIGN.md / bench bookkeeping). */
 int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* block, int* smem_bytes);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Postnet, eval mode: replaces Postnet.forward (model.py:27-70) + the residual add
+ * (model.py:557-558) + the output mask (model.py:531-541) when the module is not training.  Five Conv1d(k=5) +
+ * BatchNorm1d (running statistics, folded into the weights at set_weights) + tanh; fp16 operands on tcgen05, fp32
+ * accumulation.  Training mode (batch statistics, dropout, backward) stays with the reference's PyTorch modules.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct taco2dec_postnet taco2dec_postnet;
+
+typedef struct taco2dec_postnet_layer {
+  const float* conv_w;   /* postnet.convolutions.<i>.0.conv.weight  [C_out, C_in, 5] */
+  const float* conv_b;   /* postnet.convolutions.<i>.0.conv.bias    [C_out] */
+  const float* bn_weight;/* postnet.convolutions.<i>.1.weight       [C_out] */
+  const float* bn_bias;  /* postnet.convolutions.<i>.1.bias         [C_out] */
+  const float* bn_mean;  /* postnet.convolutions.<i>.1.running_mean [C_out] */
+  const float* bn_var;   /* postnet.convolutions.<i>.1.running_var  [C_out] */
+} taco2dec_postnet_layer;
+
+typedef struct taco2dec_postnet_weights {
+  int n_layers;                        /* hparams.postnet_n_convolutions (5) */
+  float bn_eps;                        /* nn.BatchNorm1d eps (1e-5) */
+  taco2dec_postnet_layer layer[8];
+} taco2dec_postnet_weights;
+
+/* n_mel <= 128, embed_dim a multiple of 128, kernel_size must be 5 (hparams.py:49), 2 <= n_layers <= 8. */
+int taco2dec_postnet_create(int n_mel, int embed_dim, int kernel_size, int n_layers, int device, taco2dec_postnet** out);
+int taco2dec_postnet_destroy(taco2dec_postnet* h);
+/* Folds BatchNorm and packs the GEMM tiles (library-owned copies): call again when the module's tensors change. */
+int taco2dec_postnet_set_weights(taco2dec_postnet* h, const taco2dec_postnet_weights* w, void* cuda_stream);
+size_t taco2dec_postnet_workspace_bytes(const taco2dec_postnet* h, int B, int T);
+/* mel: element (b, c, t) at mel[b*stride_b + c*stride_c + t*stride_t] (the decoder's storage is [B, T, n_mel]);
+ * mel_postnet: contiguous [B, n_mel, T] = mel + postnet(mel), zero where t >= output_lengths[b] (NULL = no mask). */
+int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stride_b, int64_t stride_c, int64_t stride_t,
+                             int B, int T, const int64_t* output_lengths, float* mel_postnet, void* workspace,
+                             size_t workspace_bytes, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = (
     "taco2dec_launch_geometry", "taco2dec_set_profiling", "taco2dec_last_kernel_ms",
     "taco2dec_read_phase_clocks", "taco2dec_set_mode", "taco2dec_last_path",
     "taco2dec_test_gemm", "taco2dec_saved_layout_query", "taco2dec_grad_layout_query", "taco2dec_backward",
+    "taco2dec_postnet_create", "taco2dec_postnet_destroy", "taco2dec_postnet_set_weights",
+    "taco2dec_postnet_workspace_bytes", "taco2dec_postnet_forward",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -82,6 +84,14 @@ class BwdArgs(C.Structure):
                 ("saved", _fp), ("saved_bytes", C.c_size_t), ("grads", _fp), ("grads_bytes", C.c_size_t)]
 
 
+class PostnetLayer(C.Structure):
+    _fields_ = [(n, _fp) for n in ("conv_w", "conv_b", "bn_weight", "bn_bias", "bn_mean", "bn_var")]
+
+
+class PostnetWeights(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("bn_eps", C.c_float), ("layer", PostnetLayer * 8)]
+
+
 class InferArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("T_in", C.c_int), ("T_sub", C.c_int), ("max_decoder_steps", C.c_int),
                 ("gate_threshold", C.c_float), ("memory", _fp), ("embeddings", _fp),
@@ -130,6 +140,17 @@ def load_library() -> C.CDLL:
     lib.taco2dec_grad_layout_query.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GradLayout)]
     lib.taco2dec_backward.restype = C.c_int
     lib.taco2dec_backward.argtypes = [H, C.POINTER(BwdArgs), C.c_void_p]
+    lib.taco2dec_postnet_create.restype = C.c_int
+    lib.taco2dec_postnet_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    lib.taco2dec_postnet_destroy.restype = C.c_int
+    lib.taco2dec_postnet_destroy.argtypes = [H]
+    lib.taco2dec_postnet_set_weights.restype = C.c_int
+    lib.taco2dec_postnet_set_weights.argtypes = [H, C.POINTER(PostnetWeights), C.c_void_p]
+    lib.taco2dec_postnet_workspace_bytes.restype = C.c_size_t
+    lib.taco2dec_postnet_workspace_bytes.argtypes = [H, C.c_int, C.c_int]
+    lib.taco2dec_postnet_forward.restype = C.c_int
+    lib.taco2dec_postnet_forward.argtypes = [H, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.taco2dec_check.restype = C.c_int
     lib.taco2dec_check.argtypes = [H, C.c_void_p]
     lib.taco2dec_launch_count.restype = C.c_int64

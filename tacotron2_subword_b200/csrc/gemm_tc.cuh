@@ -105,6 +105,7 @@ struct GemmParams {
   int done_target;
   uint32_t fmt;                   // operand formats OR-ed into the instruction descriptor (kFmtF16 / kFmtBF16)
   int stages;                     // 0 = stages_for(NPAD); experiments may ask for fewer
+  int a_shared;                   // 1 = every group multiplies the same A tiles (e.g. a convolution's weights)
   unsigned long long* dbg;        // optional [CTAs][8] globaltimer stamps (ns): entry, setup done, first tile landed,
                                   // accumulator complete, epilogue stored, exit
 };
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_f16_tn_kernel(const GemmPara
   if (warp == 4) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const unsigned char* a_src = p.a_tiles + ((size_t)group * m_tiles + mt) * kb_total * kATileBytes;
+      const unsigned char* a_src = p.a_tiles + ((size_t)(p.a_shared ? 0 : group) * m_tiles + mt) * kb_total * kATileBytes;
       const unsigned char* x_src = p.x_tiles + (size_t)group * p.x_group_stride +
                                    (size_t)(p.x_kb_base + group * p.x_kb_group_step) * kXTileBytes;
       for (int i = 0; i < kb_per_split; ++i) {

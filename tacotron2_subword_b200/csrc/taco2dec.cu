@@ -779,6 +779,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
 
 #include "batched.cuh"
 #include "backward.cuh"
+#include "postnet.cuh"
 
 // ------------------------------------------------------------------------------------------
 // One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
@@ -1936,6 +1937,140 @@ int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* bl
   if (grid) *grid = h->num_sms;
   if (block) *block = kThreads;
   if (smem_bytes) *smem_bytes = (int)persistent_smem_bytes(h->cfg, pick_bt(B), 256, 128);
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Postnet (postnet.cuh)
+// ------------------------------------------------------------------------------------------
+struct taco2dec_postnet {
+  int device, num_sms, n_mel, dim, n_layers;
+  bool have_weights;
+  pn::Layer layer[pn::kMaxLayers];
+  int64_t launches;
+};
+
+namespace {
+struct PnPlan { int groups; size_t x_bytes, part_bytes, total; };
+PnPlan pn_plan(const taco2dec_postnet* h, int B, int T) {
+  PnPlan pl;
+  pl.groups = (B * T + pn::kNP - 1) / pn::kNP;
+  int kmax = 0, cmax = 0;
+  for (int l = 0; l < h->n_layers; ++l) { kmax = std::max(kmax, h->layer[l].K); cmax = std::max(cmax, h->layer[l].cout_pad); }
+  pl.x_bytes = align_up((size_t)pl.groups * (kmax / tc::kBlockK) * pn::kNP * 128, 256);
+  pl.part_bytes = align_up((size_t)pl.groups * 4 * cmax * pn::kNP * sizeof(float), 256);     // up to 4 K-splits
+  pl.total = 2 * pl.x_bytes + pl.part_bytes;
+  return pl;
+}
+int pn_splits(int ctas_per_split, int kb_total, int num_sms) {
+  const int want = std::max(1, num_sms / std::max(1, ctas_per_split));
+  int best = 1;
+  for (int s : {2, 4}) if (s <= want && kb_total % s == 0) best = s;
+  return best;
+}
+}  // namespace
+
+extern "C" {
+
+int taco2dec_postnet_create(int n_mel, int embed_dim, int kernel_size, int n_layers, int device, taco2dec_postnet** out) {
+  if (!out) return fail(TACO2DEC_E_ARG, "null argument");
+  if (kernel_size != pn::kTaps) return fail(TACO2DEC_E_ARG, "postnet_kernel_size must be 5");
+  if (n_mel < 1 || n_mel > 128 || embed_dim < 128 || embed_dim % 128 || n_layers < 2 || n_layers > pn::kMaxLayers)
+    return fail(TACO2DEC_E_ARG, "postnet needs n_mel <= 128, embed_dim a multiple of 128, 2..8 layers");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(TACO2DEC_E_ARCH, "this library is built for sm_100a (B200) only and has no fallback");
+  taco2dec_postnet* h = new (std::nothrow) taco2dec_postnet();
+  if (!h) return fail(TACO2DEC_E_STATE, "out of host memory");
+  h->device = device; h->num_sms = prop.multiProcessorCount; h->n_mel = n_mel; h->dim = embed_dim; h->n_layers = n_layers;
+  h->have_weights = false; h->launches = 0;
+  CUDA_TRY(cudaSetDevice(device));
+  for (int l = 0; l < n_layers; ++l) {
+    pn::Layer& L = h->layer[l];
+    L.cin = l == 0 ? n_mel : embed_dim;
+    L.cout = l == n_layers - 1 ? n_mel : embed_dim;
+    L.cin_pad = (L.cin + 63) / 64 * 64;
+    L.cout_pad = (L.cout + 127) / 128 * 128;
+    L.K = pn::kTaps * L.cin_pad;
+    CUDA_TRY(cudaMalloc(&L.a_tiles, (size_t)L.cout_pad * L.K * 2));
+    CUDA_TRY(cudaMalloc(&L.bias, (size_t)L.cout_pad * sizeof(float)));
+  }
+  *out = h;
+  return 0;
+}
+
+int taco2dec_postnet_destroy(taco2dec_postnet* h) {
+  if (h) for (int l = 0; l < h->n_layers; ++l) { cudaFree(h->layer[l].a_tiles); cudaFree(h->layer[l].bias); }
+  delete h;
+  return 0;
+}
+
+int taco2dec_postnet_set_weights(taco2dec_postnet* h, const taco2dec_postnet_weights* w, void* cuda_stream) {
+  if (!h || !w) return fail(TACO2DEC_E_ARG, "null argument");
+  if (w->n_layers != h->n_layers) return fail(TACO2DEC_E_ARG, "layer count differs from create()");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (int l = 0; l < h->n_layers; ++l) {
+    const taco2dec_postnet_layer& s = w->layer[l];
+    if (!s.conv_w || !s.conv_b || !s.bn_weight || !s.bn_bias || !s.bn_mean || !s.bn_var)
+      return fail(TACO2DEC_E_ARG, "null postnet weight pointer");
+    const pn::Layer& L = h->layer[l];
+    pn::pn_pack_kernel<<<1024, 256, 0, st>>>(s.conv_w, s.conv_b, s.bn_weight, s.bn_bias, s.bn_mean, s.bn_var, w->bn_eps, L.cout,
+                                             L.cin, L.cout_pad, L.cin_pad, L.a_tiles, L.bias);
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->launches += h->n_layers;
+  h->have_weights = true;
+  return 0;
+}
+
+size_t taco2dec_postnet_workspace_bytes(const taco2dec_postnet* h, int B, int T) {
+  if (!h || B < 1 || T < 1) return 0;
+  return pn_plan(h, B, T).total;
+}
+
+int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stride_b, int64_t stride_c, int64_t stride_t,
+                             int B, int T, const int64_t* output_lengths, float* mel_postnet, void* workspace,
+                             size_t workspace_bytes, void* cuda_stream) {
+  if (!h || !mel || !mel_postnet || !workspace) return fail(TACO2DEC_E_ARG, "null argument");
+  if (!h->have_weights) return fail(TACO2DEC_E_STATE, "weights not set");
+  if (B < 1 || T < 1) return fail(TACO2DEC_E_ARG, "B and T must be >= 1");
+  const PnPlan pl = pn_plan(h, B, T);
+  if (workspace_bytes < pl.total) return fail(TACO2DEC_E_STATE, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(TACO2DEC_E_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  unsigned char* X[2] = {(unsigned char*)workspace, (unsigned char*)workspace + pl.x_bytes};
+  float* part = (float*)((char*)workspace + 2 * pl.x_bytes);
+  const int n_pad = pl.groups * pn::kNP;
+  CUDA_TRY(tc::prepare_gemm<pn::kNP>());
+  {
+    const pn::Layer& L0 = h->layer[0];
+    const size_t total = (size_t)n_pad * pn::kTaps * (L0.cin_pad / 8);
+    pn::pn_input_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 65535), 256, 0, st>>>(mel, stride_b, stride_c, stride_t, B, T,
+                                                                                               L0.cin, L0.cin_pad, n_pad, X[0]);
+  }
+  for (int l = 0; l < h->n_layers; ++l) {
+    const pn::Layer& L = h->layer[l];
+    const int m_tiles = L.cout_pad / tc::kBlockM, kb_total = L.K / tc::kBlockK;
+    const int splits = pn_splits(m_tiles * pl.groups, kb_total, h->num_sms);
+    tc::GemmParams gp{L.a_tiles, X[l & 1], part, L.cout_pad, L.K, splits, pl.groups, (long long)kb_total * pn::kNP * 128, 0, 0, nullptr, 0};
+    gp.a_shared = 1;
+    CUDA_TRY(tc::launch_gemm<pn::kNP>(gp, st));
+    if (l + 1 < h->n_layers) {
+      const pn::Layer& Ln = h->layer[l + 1];
+      pn::pn_pointwise_kernel<<<dim3(pl.groups, L.cout_pad / 8), 256, 0, st>>>(part, splits, L.cout_pad, L.bias, B, T, pl.groups,
+                                                                             X[(l + 1) & 1], Ln.K);
+    } else {
+      const size_t total = (size_t)B * L.cout * T;
+      pn::pn_output_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 65535), 256, 0, st>>>(
+          part, splits, L.cout_pad, L.bias, mel, stride_b, stride_c, stride_t, B, T, L.cout, (const long long*)output_lengths, mel_postnet);
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1 + 2 * h->n_layers;
   return 0;
 }
 

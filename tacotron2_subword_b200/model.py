@@ -565,7 +565,11 @@ class Decoder(nn.Module):
 
 
 class Postnet(nn.Module):
-    """model.py:27-70: five conv1d(k=5)+BatchNorm, tanh on all but the last, dropout 0.5 in training."""
+    """model.py:27-70: five conv1d(k=5)+BatchNorm, tanh on all but the last, dropout 0.5 in training.
+
+    ``forward`` is the reference module (PyTorch ops; used for training).  ``mel_postnet`` is what the model classes
+    call: mel + postnet(mel) with the output mask, which in eval mode on a B200 runs as five tcgen05 GEMMs with the
+    BatchNorm folded in (``taco2dec_postnet_*``, csrc/postnet.cuh) instead of ten cuDNN/elementwise launches."""
 
     def __init__(self, hparams):
         super().__init__()
@@ -577,6 +581,9 @@ class Postnet(nn.Module):
                                    w_init_gain="tanh" if i < n - 1 else "linear"),
                           nn.BatchNorm1d(chans[i + 1]))
             for i in range(n))
+        self.n_mel, self.dim, self.kernel, self.n_layers = hp.n_mel_channels, c, k, n
+        self.fused_eval = True          # extension: use the CUDA postnet when the module is in eval mode
+        self._fused = {}                # device index -> (handle, weights key, workspace)
 
     def forward(self, x):
         last = len(self.convolutions) - 1
@@ -584,6 +591,64 @@ class Postnet(nn.Module):
             x = conv(x)
             x = F.dropout(torch.tanh(x) if i < last else x, 0.5, self.training)
         return x
+
+    def _fusable(self, mel: torch.Tensor) -> bool:
+        return (self.fused_eval and not self.training and mel.is_cuda and mel.dtype == torch.float32 and self.kernel == 5
+                and self.n_mel <= 128 and self.dim % 128 == 0 and 2 <= self.n_layers <= 8
+                and not (torch.is_grad_enabled() and (mel.requires_grad or any(p.requires_grad for p in self.parameters()))))
+
+    def mel_postnet(self, mel: torch.Tensor, output_lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """mel [B, n_mel, T] (any strides) -> mel + postnet(mel) (model.py:557-558); with ``output_lengths`` the frames
+        beyond each utterance's length are zero (model.py:531-541)."""
+        if not self._fusable(mel):
+            out = mel + self.forward(mel)
+            if output_lengths is not None:
+                invalid = torch.arange(mel.shape[2], device=mel.device)[None, :] >= output_lengths.to(mel.device)[:, None]
+                out = out.masked_fill(invalid[:, None, :], 0.0)
+            return out
+        lib = _cabi.load_library()
+        dev = mel.device
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        ent = self._fused.get(key)
+        if ent is None:
+            h = C.c_void_p()
+            _cabi.check(lib.taco2dec_postnet_create(self.n_mel, self.dim, self.kernel, self.n_layers, key, C.byref(h)))
+            ent = self._fused[key] = {"h": h, "key": None, "ws": None}
+        tensors = []
+        for seq in self.convolutions:
+            conv, bn = seq[0].conv, seq[1]
+            tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        wkey = tuple((t.data_ptr(), t._version) for t in tensors)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            if wkey != ent["key"]:
+                w = _cabi.PostnetWeights()
+                w.n_layers, w.bn_eps = self.n_layers, float(self.convolutions[0][1].eps)
+                for i in range(self.n_layers):
+                    for name, t in zip(("conv_w", "conv_b", "bn_weight", "bn_bias", "bn_mean", "bn_var"), tensors[6 * i: 6 * i + 6]):
+                        if t.dtype != torch.float32 or not t.is_contiguous():
+                            raise _cabi.Taco2DecError("postnet parameters must be contiguous fp32")
+                        setattr(w.layer[i], name, t.data_ptr())
+                _cabi.check(lib.taco2dec_postnet_set_weights(ent["h"], C.byref(w), stream))
+                ent["key"] = wkey
+            B, _, T = mel.shape
+            need = int(lib.taco2dec_postnet_workspace_bytes(ent["h"], B, T))
+            if ent["ws"] is None or ent["ws"].numel() < need:
+                ent["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+            out = torch.empty(B, self.n_mel, T, device=dev)
+            lens = None if output_lengths is None else output_lengths.to(device=dev, dtype=torch.int64).contiguous()
+            sb, sc, st = mel.stride()
+            _cabi.check(lib.taco2dec_postnet_forward(ent["h"], _ptr(mel.detach()), sb, sc, st, B, T, _ptr(lens), _ptr(out),
+                                                     _ptr(ent["ws"]), ent["ws"].numel(), stream))
+        return out
+
+    def __del__(self):
+        try:
+            lib = _cabi.load_library()
+            for ent in self._fused.values():
+                lib.taco2dec_postnet_destroy(ent["h"])
+        except Exception:
+            pass
 
 
 class Encoder(nn.Module):
@@ -694,13 +759,13 @@ class BERT_Tacotron2(nn.Module):
         mem, mem_s = self._memories(text_inputs, embeddings, phoneme_embeddings_cls, bert_embeddings_cls,
                                     text_lengths, bert_lengths)
         mel, gate, align, align_b = self.decoder(mem, mem_s, mels, text_lengths, bert_lengths)   # model.py:556
-        mel_post = mel + self.postnet(mel)
+        mel_post = self.postnet.mel_postnet(mel)
         return self.parse_output([mel, mel_post, gate, align, align_b], output_lengths)
 
     def inference(self, inputs, embeddings, phoneme_embeddings_cls, bert_embeddings_cls):
         mem, mem_s = self._memories(inputs, embeddings, phoneme_embeddings_cls, bert_embeddings_cls)
         mel, gate, align, align_b, flag = self.decoder.inference(mem, mem_s)                      # model.py:574-575
-        mel_post = mel + self.postnet(mel)
+        mel_post = self.postnet.mel_postnet(mel)
         return self.parse_output([mel, mel_post, gate, align, align_b, flag])
 
 
@@ -726,12 +791,12 @@ class Tacotron2(nn.Module):
         input_lengths, output_lengths = input_lengths.data, output_lengths.data
         mem = self.encoder(self.embedding(text).transpose(1, 2), input_lengths)
         mel, gate, align, _ = self.decoder(mem, None, mels, input_lengths, None)
-        mel_post = mel + self.postnet(mel)
+        mel_post = self.postnet.mel_postnet(mel)
         out = _mask_outputs([mel, mel_post, gate, align], output_lengths, self.n_mel_channels, self.mask_padding)
         return tuple(out)
 
     def inference(self, sequence):
         mem = self.encoder.inference(self.embedding(sequence).transpose(1, 2))
         mel, gate, align, _, _flag = self.decoder.inference(mem, None)
-        mel_post = mel + self.postnet(mel)
+        mel_post = self.postnet.mel_postnet(mel)
         return mel, mel_post, gate, align

@@ -1,0 +1,108 @@
+"""-m gpu: eval-mode Postnet on tcgen05 (csrc/postnet.cuh) vs the reference golden, the CPU oracle and the PyTorch module.
+
+fp16 operands (activations and BatchNorm-folded weights), fp32 accumulation, five layers deep, and the last layer is
+linear (its outputs are not squashed by tanh): stated bound max|delta| <= 3e-3 * max(1, max|postnet output|)
+(measured ~1.4e-3 of the output scale)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.postnet_oracle import make_postnet_weights, mel_postnet, postnet_eval
+from tacotron2_subword_b200 import create_hparams
+from tacotron2_subword_b200.model import Postnet
+from tests.helpers import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-3
+
+
+def _close(got, want, residual=None):
+    """|got - want| within TOL of the scale of the postnet's own output (want - residual)."""
+    y = want if residual is None else want - residual
+    scale = max(1.0, float(y.abs().max()))
+    err = float((got - want).abs().max())
+    assert err <= TOL * scale, (err, scale)
+
+
+def _module(w):
+    net = Postnet(create_hparams())
+    sd = net.state_dict()
+    for k in sd:
+        if k in w:
+            sd[k] = w[k]
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval()
+
+
+def test_postnet_matches_reference_golden():
+    z = np.load(os.path.join(GOLDEN_DIR, "postnet_eval.npz"))
+    net = _module(make_postnet_weights(int(z["seed"])))
+    x = torch.from_numpy(z["x"]).cuda()
+    with torch.no_grad():
+        got = net.mel_postnet(x) - x
+    _close(got.cpu(), torch.from_numpy(z["y"]))
+
+
+@pytest.mark.parametrize("B,T", [(1, 1000), (1, 5), (3, 129), (16, 257), (64, 40)])
+def test_postnet_vs_oracle_shapes_strides_and_mask(B, T):
+    """Tile boundaries (T not a multiple of 128, utterances sharing a 128-position tile), the decoder's transposed storage
+    as input, and the output-length mask."""
+    seed = 5 + B
+    w = make_postnet_weights(seed)
+    net = _module(w)
+    g = torch.Generator().manual_seed(seed)
+    storage = torch.randn(B, T, 80, generator=g)                 # the decoder writes [B, T, n_mel]
+    mel = storage.transpose(1, 2)                                # ... and hands out this view
+    lens = torch.randint(max(1, T // 2), T + 1, (B,), generator=g)
+    lens[0] = T
+    want = mel_postnet(w, mel.contiguous(), lens)
+    with torch.no_grad():
+        got = net.mel_postnet(storage.cuda().transpose(1, 2), lens.cuda())
+    assert got.shape == (B, 80, T) and got.is_contiguous()
+    _close(got.cpu(), want, (mel.contiguous() * (torch.arange(T)[None, None, :] < lens[:, None, None])))
+    for b in range(B):
+        assert float(got[b, :, int(lens[b]):].abs().max() if int(lens[b]) < T else 0.0) == 0.0
+    # the unfused module path (PyTorch ops) agrees as well, and is what training mode uses
+    net.fused_eval = False
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # cuDNN's default TF32 convolutions are off by ~8e-3 here
+    try:
+        with torch.no_grad():
+            ref = net.mel_postnet(mel.cuda(), lens.cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert float((ref.cpu() - want).abs().max()) <= 2e-4
+
+
+def test_postnet_weights_are_repacked_after_an_update():
+    w = make_postnet_weights(9)
+    net = _module(w)
+    x = torch.randn(2, 80, 50, generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        a = net.mel_postnet(x)
+        net.convolutions[2][0].conv.weight.mul_(0.5)             # in-place update bumps the tensor version
+        b = net.mel_postnet(x)
+        want = x + net.forward(x)
+    assert float((a - b).abs().max()) > 1e-3
+    _close(b, want, x)
+
+
+def test_model_inference_uses_fused_postnet():
+    from tacotron2_subword_b200 import BERT_Tacotron2
+    torch.manual_seed(3)
+    hp = create_hparams()
+    model = BERT_Tacotron2(hp).cuda().eval()
+    model.decoder.max_decoder_steps = 9
+    model.decoder.rng_seed = 4
+    text = torch.randint(0, hp.n_symbols, (1, 11)).cuda()
+    sub = torch.randint(0, hp.sub_n_symbols, (1, 4)).cuda()
+    pcls = torch.randn(1, 11, hp.BERT_embedding_dim).cuda()
+    bcls = torch.randn(1, 4, hp.BERT_embedding_dim).cuda()
+    with torch.no_grad():
+        fused = model.inference(text, sub, pcls, bcls)
+        model.postnet.fused_eval = False
+        plain = model.inference(text, sub, pcls, bcls)
+    assert torch.equal(fused[0], plain[0])                        # same decoder output (same seed)
+    _close(fused[1], plain[1], plain[0])

@@ -50,6 +50,8 @@ def test_ctypes_structs_match_header_field_order():
     assert fields("taco2dec_saved_layout") == [f[0] for f in _cabi.SavedLayout._fields_]
     assert fields("taco2dec_grad_layout") == [f[0] for f in _cabi.GradLayout._fields_]
     assert fields("taco2dec_bwd_args") == [f[0] for f in _cabi.BwdArgs._fields_]
+    assert fields("taco2dec_postnet_layer") == [f[0] for f in _cabi.PostnetLayer._fields_]
+    assert fields("taco2dec_postnet_weights") == [f[0] for f in _cabi.PostnetWeights._fields_]
 
 
 def test_create_refuses_without_gpu():
