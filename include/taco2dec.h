@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TACO2DEC_ABI_VERSION 4
+#define TACO2DEC_ABI_VERSION 5
 
 #define TACO2DEC_ATTN_SMA 0 /* StepwiseMonotonicAttention   (attention.py:291-398, hparams default) */
 #define TACO2DEC_ATTN_LSA 1 /* LocationSensitiveAttention   (attention.py:7-85)                      */
@@ -308,10 +308,13 @@ int taco2dec_postnet_destroy(taco2dec_postnet* h);
 int taco2dec_postnet_set_weights(taco2dec_postnet* h, const taco2dec_postnet_weights* w, void* cuda_stream);
 size_t taco2dec_postnet_workspace_bytes(const taco2dec_postnet* h, int B, int T);
 /* mel: element (b, c, t) at mel[b*stride_b + c*stride_c + t*stride_t] (the decoder's storage is [B, T, n_mel]);
- * mel_postnet: contiguous [B, n_mel, T] = mel + postnet(mel), zero where t >= output_lengths[b] (NULL = no mask). */
+ * mel_postnet: contiguous [B, n_mel, T] = mel + postnet(mel), zero where t >= output_lengths[b] (NULL = no mask).
+ * independent = 0: the reference's batched behaviour (the convolutions run over the padded frames, model.py:557);
+ * independent = 1: frames >= output_lengths[b] do not exist (they are the convolutions' zero padding in every layer), so
+ * row b equals the batch-1 result on its first output_lengths[b] frames -- for batched free-running synthesis. */
 int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stride_b, int64_t stride_c, int64_t stride_t,
-                             int B, int T, const int64_t* output_lengths, float* mel_postnet, void* workspace,
-                             size_t workspace_bytes, void* cuda_stream);
+                             int B, int T, const int64_t* output_lengths, int independent, float* mel_postnet,
+                             void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtac
 ATTN_SMA, ATTN_LSA = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR = 0, 1, 2, 3
 W_FP32, W_FP16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EXPORTED_SYMBOLS = (
     "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
@@ -150,7 +150,7 @@ def load_library() -> C.CDLL:
     lib.taco2dec_postnet_workspace_bytes.argtypes = [H, C.c_int, C.c_int]
     lib.taco2dec_postnet_forward.restype = C.c_int
     lib.taco2dec_postnet_forward.argtypes = [H, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p,
-                                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.taco2dec_check.restype = C.c_int
     lib.taco2dec_check.argtypes = [H, C.c_void_p]
     lib.taco2dec_launch_count.restype = C.c_int64

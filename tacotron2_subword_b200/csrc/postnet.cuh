@@ -61,8 +61,11 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 
 // layer-0 operand from the mel input (arbitrary strides: the decoder's storage is [B, T, n_mel]).  One thread per
 // destination chunk (position n', tap kk, 8 channels): source frame t = t' + kk - 2 of the same utterance, else zeros.
+// `seq_len` (independent utterances): frames >= seq_len[b] do not exist -- they read as the convolution's zero padding in
+// every layer, so row b equals the batch-1 result on its first seq_len[b] frames.
 __global__ void pn_input_kernel(const float* __restrict__ mel, long long sb, long long sc, long long st, int B, int T,
-                                int cin, int cin_pad, int n_pad /* groups * 128 */, unsigned char* __restrict__ X) {
+                                int cin, int cin_pad, int n_pad /* groups * 128 */, const long long* __restrict__ seq_len,
+                                unsigned char* __restrict__ X) {
   const int chunks = cin_pad / 8, K = kTaps * cin_pad;
   const size_t total = (size_t)n_pad * kTaps * chunks;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -70,7 +73,8 @@ __global__ void pn_input_kernel(const float* __restrict__ mel, long long sb, lon
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (n < B * T) {
       const int b = n / T, t = n - b * T + kk - kHalo;
-      if (t >= 0 && t < T) {
+      const int Tb = seq_len ? min((int)seq_len[b], T) : T;
+      if (t >= 0 && t < Tb) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) { const int c = c8 * 8 + q; if (c < cin) v[q] = mel[b * sb + c * sc + t * st]; }
       }
@@ -84,6 +88,7 @@ __global__ void pn_input_kernel(const float* __restrict__ mel, long long sb, lon
 // memory, then every (position, tap) destination gets its 8 channels as one 16-byte store).
 __global__ void __launch_bounds__(256) pn_pointwise_kernel(const float* __restrict__ part, int splits, int cout_pad,
                                                            const float* __restrict__ bias, int B, int T, int groups,
+                                                           const long long* __restrict__ seq_len,
                                                            unsigned char* __restrict__ Xn, int Kn /* 5 * cout_pad */) {
   __shared__ float act_s[8][kNP + 2 * kHalo + 1];
   const int g = blockIdx.x, c0 = blockIdx.y * 8, tid = threadIdx.x;
@@ -92,7 +97,9 @@ __global__ void __launch_bounds__(256) pn_pointwise_kernel(const float* __restri
     const int cl = i / (kNP + 2 * kHalo), pl = i - cl * (kNP + 2 * kHalo);
     const int n = n0 - kHalo + pl;
     float a = 0.f;
-    if (n >= 0 && n < NT) {
+    bool exists = n >= 0 && n < NT;
+    if (exists && seq_len) { const int b = n / T; exists = (n - b * T) < (int)seq_len[b]; }
+    if (exists) {
       const int gg = n / kNP, nl = n - gg * kNP;
       float acc = bias[c0 + cl];
       for (int k = 0; k < splits; ++k) acc += part[(((size_t)gg * splits + k) * cout_pad + c0 + cl) * kNP + nl];

@@ -2032,11 +2032,13 @@ size_t taco2dec_postnet_workspace_bytes(const taco2dec_postnet* h, int B, int T)
 }
 
 int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stride_b, int64_t stride_c, int64_t stride_t,
-                             int B, int T, const int64_t* output_lengths, float* mel_postnet, void* workspace,
-                             size_t workspace_bytes, void* cuda_stream) {
+                             int B, int T, const int64_t* output_lengths, int independent, float* mel_postnet,
+                             void* workspace, size_t workspace_bytes, void* cuda_stream) {
   if (!h || !mel || !mel_postnet || !workspace) return fail(TACO2DEC_E_ARG, "null argument");
   if (!h->have_weights) return fail(TACO2DEC_E_STATE, "weights not set");
   if (B < 1 || T < 1) return fail(TACO2DEC_E_ARG, "B and T must be >= 1");
+  if (independent && !output_lengths) return fail(TACO2DEC_E_ARG, "independent utterances need output_lengths");
+  const long long* seq_len = independent ? (const long long*)output_lengths : nullptr;
   const PnPlan pl = pn_plan(h, B, T);
   if (workspace_bytes < pl.total) return fail(TACO2DEC_E_STATE, "workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(TACO2DEC_E_ARG, "workspace must be 256-byte aligned");
@@ -2050,7 +2052,7 @@ int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stri
     const pn::Layer& L0 = h->layer[0];
     const size_t total = (size_t)n_pad * pn::kTaps * (L0.cin_pad / 8);
     pn::pn_input_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 65535), 256, 0, st>>>(mel, stride_b, stride_c, stride_t, B, T,
-                                                                                               L0.cin, L0.cin_pad, n_pad, X[0]);
+                                                                                               L0.cin, L0.cin_pad, n_pad, seq_len, X[0]);
   }
   for (int l = 0; l < h->n_layers; ++l) {
     const pn::Layer& L = h->layer[l];
@@ -2062,7 +2064,7 @@ int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stri
     if (l + 1 < h->n_layers) {
       const pn::Layer& Ln = h->layer[l + 1];
       pn::pn_pointwise_kernel<<<dim3(pl.groups, L.cout_pad / 8), 256, 0, st>>>(part, splits, L.cout_pad, L.bias, B, T, pl.groups,
-                                                                             X[(l + 1) & 1], Ln.K);
+                                                                             seq_len, X[(l + 1) & 1], Ln.K);
     } else {
       const size_t total = (size_t)B * L.cout * T;
       pn::pn_output_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 65535), 256, 0, st>>>(

@@ -597,10 +597,20 @@ class Postnet(nn.Module):
                 and self.n_mel <= 128 and self.dim % 128 == 0 and 2 <= self.n_layers <= 8
                 and not (torch.is_grad_enabled() and (mel.requires_grad or any(p.requires_grad for p in self.parameters()))))
 
-    def mel_postnet(self, mel: torch.Tensor, output_lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def mel_postnet(self, mel: torch.Tensor, output_lengths: Optional[torch.Tensor] = None,
+                    independent: bool = False) -> torch.Tensor:
         """mel [B, n_mel, T] (any strides) -> mel + postnet(mel) (model.py:557-558); with ``output_lengths`` the frames
-        beyond each utterance's length are zero (model.py:531-541)."""
+        beyond each utterance's length are zero (model.py:531-541).  ``independent=True`` (extension, batched synthesis):
+        frames beyond the length do not exist at all, so row b equals the batch-1 result on its own frames."""
+        if independent and output_lengths is None:
+            raise ValueError("independent=True needs output_lengths")
         if not self._fusable(mel):
+            if independent:
+                out = torch.zeros_like(mel)
+                for b in range(mel.shape[0]):
+                    n = int(output_lengths[b])
+                    out[b:b + 1, :, :n] = mel[b:b + 1, :, :n] + self.forward(mel[b:b + 1, :, :n])
+                return out
             out = mel + self.forward(mel)
             if output_lengths is not None:
                 invalid = torch.arange(mel.shape[2], device=mel.device)[None, :] >= output_lengths.to(mel.device)[:, None]
@@ -638,8 +648,8 @@ class Postnet(nn.Module):
             out = torch.empty(B, self.n_mel, T, device=dev)
             lens = None if output_lengths is None else output_lengths.to(device=dev, dtype=torch.int64).contiguous()
             sb, sc, st = mel.stride()
-            _cabi.check(lib.taco2dec_postnet_forward(ent["h"], _ptr(mel.detach()), sb, sc, st, B, T, _ptr(lens), _ptr(out),
-                                                     _ptr(ent["ws"]), ent["ws"].numel(), stream))
+            _cabi.check(lib.taco2dec_postnet_forward(ent["h"], _ptr(mel.detach()), sb, sc, st, B, T, _ptr(lens), int(independent),
+                                                     _ptr(out), _ptr(ent["ws"]), ent["ws"].numel(), stream))
         return out
 
     def __del__(self):
@@ -767,6 +777,37 @@ class BERT_Tacotron2(nn.Module):
         mel, gate, align, align_b, flag = self.decoder.inference(mem, mem_s)                      # model.py:574-575
         mel_post = self.postnet.mel_postnet(mel)
         return self.parse_output([mel, mel_post, gate, align, align_b, flag])
+
+
+    @torch.no_grad()
+    def inference_batch(self, inputs, embeddings, phoneme_embeddings_cls, bert_embeddings_cls,
+                        max_decoder_steps: Optional[int] = None):
+        """Batched form of ``inference`` (extension; the reference synthesises one utterance per call, inference.py:361-375).
+
+        Every argument is a list with one entry per utterance, each entry exactly what ``inference`` takes ([1, T_in] ids,
+        [1, T_sub] ids, [1, T_in, 768] and [1, T_sub, 768] BERT embeddings).  Utterances are encoded one by one (the
+        reference encoder is not batch-invariant), decoded together (``Decoder.inference_batched``: every row is its own
+        batch-1 run, stop frames per utterance) and post-processed together (``Postnet.mel_postnet(independent=True)``).
+        Returns one ``inference``-shaped list [mel, mel_postnet, gate, align, align_bert, INFER_FLAG] per utterance."""
+        n = len(inputs)
+        mems = [self._memories(inputs[i], embeddings[i], phoneme_embeddings_cls[i], bert_embeddings_cls[i]) for i in range(n)]
+        dev = mems[0][0].device
+        mlen = torch.tensor([m.shape[1] for m, _ in mems], dtype=torch.int64, device=dev)
+        blen = torch.tensor([ms.shape[1] for _, ms in mems], dtype=torch.int64, device=dev)
+        mem = torch.zeros(n, int(mlen.max()), mems[0][0].shape[2], device=dev)
+        mem_s = torch.zeros(n, int(blen.max()), mems[0][1].shape[2], device=dev)
+        for i, (m, ms) in enumerate(mems):
+            mem[i, : m.shape[1]] = m[0]
+            mem_s[i, : ms.shape[1]] = ms[0]
+        mel, gate, align, align_b, n_frames, reached = self.decoder.inference_batched(mem, mem_s, mlen, blen, max_decoder_steps)
+        mel_post = self.postnet.mel_postnet(mel, n_frames.to(torch.int64), independent=True)
+        nf, rm = n_frames.tolist(), reached.tolist()
+        outs = []
+        for i in range(n):
+            t, li, lb = int(nf[i]), int(mlen[i]), int(blen[i])
+            outs.append([mel[i:i + 1, :, :t], mel_post[i:i + 1, :, :t], gate[i:i + 1, :t], align[i:i + 1, :t, :li],
+                         align_b[i:i + 1, :t, :lb], not bool(rm[i])])
+        return outs
 
 
 class Tacotron2(nn.Module):

@@ -106,3 +106,63 @@ def test_model_inference_uses_fused_postnet():
         plain = model.inference(text, sub, pcls, bcls)
     assert torch.equal(fused[0], plain[0])                        # same decoder output (same seed)
     _close(fused[1], plain[1], plain[0])
+
+
+def test_postnet_independent_rows_equal_batch1_on_truncated_input():
+    """independent=True: frames beyond an utterance's length do not exist in ANY layer, so row b equals the oracle on
+    mel[b, :, :len_b] alone -- whatever the padded frames contain (a free-running batch keeps decoding after a stop)."""
+    seed, B, T = 17, 6, 150
+    w = make_postnet_weights(seed)
+    net = _module(w)
+    g = torch.Generator().manual_seed(seed)
+    mel = torch.randn(B, 80, T, generator=g)
+    lens = torch.tensor([150, 149, 131, 128, 64, 3])
+    with torch.no_grad():
+        got = net.mel_postnet(mel.cuda(), lens.cuda(), independent=True).cpu()
+        garbage = mel.clone()
+        for b in range(B):
+            garbage[b, :, int(lens[b]):] = 100.0 * torch.randn(80, T - int(lens[b]), generator=g)
+        got2 = net.mel_postnet(garbage.cuda(), lens.cuda(), independent=True).cpu()
+    assert torch.equal(got, got2)                                   # padded frames are never read
+    for b in range(B):
+        n = int(lens[b])
+        want = mel_postnet(w, mel[b:b + 1, :, :n])
+        _close(got[b:b + 1, :, :n], want, mel[b:b + 1, :, :n])
+        assert float(got[b, :, n:].abs().max() if n < T else 0.0) == 0.0
+
+
+def test_model_inference_batch_equals_per_utterance_inference():
+    """BERT_Tacotron2.inference_batch vs one inference() call per utterance with the same replayed prenet masks:
+    stop frames identical, mel / mel_postnet within the 16-bit-path bounds."""
+    from tacotron2_subword_b200 import BERT_Tacotron2, DropoutReplay
+    torch.manual_seed(7)
+    hp = create_hparams()
+    model = BERT_Tacotron2(hp).cuda().eval()
+    steps, n = 12, 5
+    with torch.no_grad():
+        model.decoder.gate_layer.linear_layer.bias.fill_(-7.3)       # random-init gate logits straddle the stop threshold
+    model.decoder.max_decoder_steps = steps
+    model.decoder.weight_dtype = "fp16"
+    g = torch.Generator().manual_seed(2)
+    T_ins = [17, 9, 13, 17, 6]
+    seqs = [torch.randint(0, hp.n_symbols, (1, t), generator=g).cuda() for t in T_ins]
+    subs = [torch.randint(0, hp.sub_n_symbols, (1, max(2, t // 3)), generator=g).cuda() for t in T_ins]
+    pcls = [torch.randn(1, t, hp.BERT_embedding_dim, generator=g).cuda() for t in T_ins]
+    bcls = [torch.randn(1, s.shape[1], hp.BERT_embedding_dim, generator=g).cuda() for s in subs]
+    keep = [[(torch.rand(steps, n, 256, generator=g) < 0.5).to(torch.uint8) for _ in range(2)] for _ in range(2)]
+    model.decoder.dropout_replay = DropoutReplay(prenet_keep=keep)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        batch = model.inference_batch(seqs, subs, pcls, bcls)
+        assert model.decoder._engine(torch.device("cuda", 0)).last_path() == "tensor"
+        for i in range(n):
+            model.decoder.dropout_replay = DropoutReplay(prenet_keep=[[m[:, i:i + 1] for m in row] for row in keep])
+            with torch.no_grad():
+                one = model.inference(seqs[i], subs[i], pcls[i], bcls[i])
+            assert batch[i][0].shape == one[0].shape and batch[i][5] == one[5]
+            assert float((batch[i][0] - one[0]).abs().max()) <= 1e-3
+            _close(batch[i][1], one[1], one[0])
+            assert float((batch[i][3] - one[3]).abs().max()) <= 2e-4 and float((batch[i][4] - one[4]).abs().max()) <= 2e-4
+            assert batch[i][2].shape == one[2].shape
+        lengths = [b_[0].shape[2] for b_ in batch]
+        print("frames per utterance:", lengths)
