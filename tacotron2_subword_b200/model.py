@@ -694,6 +694,21 @@ class Encoder(nn.Module):
         out, _ = self.lstm(x)
         return out
 
+    def inference_independent(self, x, input_lengths):
+        """Eval-mode batch in which every row equals ``inference`` on that utterance alone (extension).  The reference's
+        batched ``forward`` lets the convolutions see the padding symbols' embeddings; here positions beyond a row's
+        length are held at zero before every convolution -- exactly the zero padding a batch-1 call sees -- and the
+        BiLSTM runs on the packed sequences."""
+        valid = (torch.arange(x.shape[2], device=x.device)[None, :] < input_lengths.to(x.device)[:, None]).unsqueeze(1)
+        x = x * valid
+        for conv in self.convolutions:
+            x = F.relu(conv(x)) * valid
+        packed = nn.utils.rnn.pack_padded_sequence(x.transpose(1, 2), input_lengths.cpu(), batch_first=True, enforce_sorted=False)
+        self.lstm.flatten_parameters()
+        out, _ = self.lstm(packed)
+        out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=x.shape[2])
+        return out
+
 
 def _uniform_embedding(n, dim, n_symbols_for_std):
     emb = nn.Embedding(n, dim)
@@ -785,20 +800,27 @@ class BERT_Tacotron2(nn.Module):
         """Batched form of ``inference`` (extension; the reference synthesises one utterance per call, inference.py:361-375).
 
         Every argument is a list with one entry per utterance, each entry exactly what ``inference`` takes ([1, T_in] ids,
-        [1, T_sub] ids, [1, T_in, 768] and [1, T_sub, 768] BERT embeddings).  Utterances are encoded one by one (the
-        reference encoder is not batch-invariant), decoded together (``Decoder.inference_batched``: every row is its own
+        [1, T_sub] ids, [1, T_in, 768] and [1, T_sub, 768] BERT embeddings).  Utterances are encoded together with
+        ``Encoder.inference_independent`` (rows equal batch-1 encoding), decoded together (``Decoder.inference_batched``: every row is its own
         batch-1 run, stop frames per utterance) and post-processed together (``Postnet.mel_postnet(independent=True)``).
         Returns one ``inference``-shaped list [mel, mel_postnet, gate, align, align_bert, INFER_FLAG] per utterance."""
         n = len(inputs)
-        mems = [self._memories(inputs[i], embeddings[i], phoneme_embeddings_cls[i], bert_embeddings_cls[i]) for i in range(n)]
-        dev = mems[0][0].device
-        mlen = torch.tensor([m.shape[1] for m, _ in mems], dtype=torch.int64, device=dev)
-        blen = torch.tensor([ms.shape[1] for _, ms in mems], dtype=torch.int64, device=dev)
-        mem = torch.zeros(n, int(mlen.max()), mems[0][0].shape[2], device=dev)
-        mem_s = torch.zeros(n, int(blen.max()), mems[0][1].shape[2], device=dev)
-        for i, (m, ms) in enumerate(mems):
-            mem[i, : m.shape[1]] = m[0]
-            mem_s[i, : ms.shape[1]] = ms[0]
+        dev = self.embedding.weight.device
+
+        def pad(items, dtype=None):
+            L = max(int(t.shape[1]) for t in items)
+            out = torch.zeros((n, L) + tuple(items[0].shape[2:]), dtype=dtype or items[0].dtype, device=dev)
+            for i, t in enumerate(items):
+                out[i, : t.shape[1]] = t[0].to(dev)
+            return out
+
+        mlen = torch.tensor([int(t.shape[1]) for t in inputs], dtype=torch.int64, device=dev)
+        blen = torch.tensor([int(t.shape[1]) for t in embeddings], dtype=torch.int64, device=dev)
+        text, sub = pad(inputs, torch.int64), pad(embeddings, torch.int64)
+        enc = self.encoder.inference_independent(self.embedding(text).transpose(1, 2), mlen)
+        enc_s = self.encoder_sub.inference_independent(self.embedding_sub(sub).transpose(1, 2), blen)
+        mem = self.linear_converter(torch.cat([enc, pad(phoneme_embeddings_cls)], 2))          # model.py:548-549
+        mem_s = self.linear_converter_sub(torch.cat([enc_s, pad(bert_embeddings_cls)], 2))     # model.py:553-554
         mel, gate, align, align_b, n_frames, reached = self.decoder.inference_batched(mem, mem_s, mlen, blen, max_decoder_steps)
         mel_post = self.postnet.mel_postnet(mel, n_frames.to(torch.int64), independent=True)
         nf, rm = n_frames.tolist(), reached.tolist()
