@@ -109,7 +109,7 @@ __global__ void transpose_kernel(const float* __restrict__ src, int rows, int co
 
 // free-running: prenet(mel[t-1]) for both streams.  Block = (stream, tile of kPreBT utterances), 1024 threads =
 // 4 k-quarters x 256 outputs; weights are read transposed (coalesced across outputs) and shared by the tile.
-constexpr int kPreBT = 4;
+constexpr int kPreBT = 1;
 __global__ void __launch_bounds__(1024) bt_prenet_fr(Params p, Bufs bf, const int* t_ptr) {
   __shared__ float x_s[kPreBT][M], h_s[kPreBT][P], part_s[4][kPreBT][P];
   const int t = *t_ptr;
@@ -124,9 +124,9 @@ __global__ void __launch_bounds__(1024) bt_prenet_fr(Params p, Bufs bf, const in
   }
   __syncthreads();
   {
-    float acc[kPreBT] = {0.f, 0.f, 0.f, 0.f};
+    float acc[kPreBT] = {};
     const float* w = bf.w0t[s] + o;
-#pragma unroll 5
+#pragma unroll 10
     for (int k = kq * (M / 4); k < (kq + 1) * (M / 4); ++k) {
       const float wv = __ldg(w + (size_t)k * P);
 #pragma unroll
@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(1024) bt_prenet_fr(Params p, Bufs bf, const in
   }
   __syncthreads();
   {
-    float acc[kPreBT] = {0.f, 0.f, 0.f, 0.f};
+    float acc[kPreBT] = {};
     const float* w = bf.w1t[s] + o;
-#pragma unroll 8
+#pragma unroll 16
     for (int k = kq * (P / 4); k < (kq + 1) * (P / 4); ++k) {
       const float wv = __ldg(w + (size_t)k * P);
 #pragma unroll
