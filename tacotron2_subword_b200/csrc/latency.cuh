@@ -76,6 +76,7 @@ struct LatParams {
   const unsigned long long* packed_off;  // [NL+1] byte offsets
   int res_budget;                // shared-memory bytes available for the resident prefix
   int l2_keep_mask;              // bit s set: step s's streamed weights use L2 evict_last, else evict_first
+  int use_tmem;                  // 0: off; 1: weight segments e0/e1 are held in tensor memory; 2: segments b/c (fp32 storage only)
   LatStream st[2];
   const float *d_b_ih, *d_b_hh;  // decoder LSTM biases [4H]
   const float *proj_w, *proj_b, *gate_w, *gate_b;
@@ -257,6 +258,8 @@ struct StepPlan {
   int res_off;       // byte offset of the step's resident chunks inside the resident region
   long long src_off; // byte offset of the step's first chunk inside this CTA's packed stream
   unsigned long long policy;  // L2 eviction policy of the step's streamed loads
+  int tmem_col;      // >= 0: the step's weights live in tensor memory (one item per warp), column offset inside the
+                     // warp's 128-column slice; -1: shared memory / global stream
 };
 
 // 16-byte unit -> multiply-accumulate against the activation registers
@@ -298,7 +301,69 @@ struct LstmShared {
   uint64_t* res_bar;                        // mbarrier of the one-off resident TMA load
   StepPlan* plan;                           // [kSteps]
   volatile int* exit_flag;
+  uint32_t tmem_base;                       // tensor-memory allocation of this CTA (all 512 columns)
 };
+
+// ---- tensor memory as weight storage --------------------------------------------------------------------------
+// The latency kernel issues no MMAs, so the SM's 256 KB of tensor memory would sit idle.  It is exactly the size of the
+// two weight segments that otherwise stream from HBM every frame (b: 16 units x 8 KB, c: 8 units x 16 KB per CTA in
+// fp32): they are copied in once (tcgen05.st) and read back every frame with tcgen05.ld.  A warp can address only its
+// lane quarter (32 * (warp & 3)), so warp w owns columns [128 * (w >> 2), +128) of that quarter: 64 columns for its
+// item of step b, 64 for its item of step c; lane l's column (chunk * 4 + gate) * 4 + e holds the e-th float of the
+// 16-byte unit that lane would otherwise load (same order as dot4).
+__device__ __forceinline__ uint32_t tmem_addr_of(uint32_t base, int warp, int col) {
+  return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128 + col);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// one item (4 gate rows x 512 fp32 columns) out of tensor memory: 4 chunks of 16 columns = [gate][4 floats]
+__device__ __forceinline__ void dot4_tmem(uint32_t taddr, const float* xs, int lane, float (&s)[4]) {
+  uint32_t w[4][16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tmem_ld16(taddr + 16 * c, w[c]);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  float a[4][2];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) a[g][0] = a[g][1] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)(lane + 32 * c) * 4);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 u = make_uint4(w[c][g * 4], w[c][g * 4 + 1], w[c][g * 4 + 2], w[c][g * 4 + 3]);
+      Mac<4>::run(u, x, a[g][0], a[g][1]);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) s[g] = a[g][0] + a[g][1];
+}
+// one-off: copy this warp's item of a step from the packed global stream into its tensor-memory columns
+__device__ __noinline__ void tmem_fill_item(uint32_t taddr, const unsigned char* base, int row_bytes, int lane) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t w[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)g * row_bytes + (size_t)(lane + 32 * c) * 16);
+      w[g * 4] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+    }
+    tmem_st16(taddr + 16 * c, w);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // One item = one hidden unit (4 gate rows) x one column range of KLEN columns, done by one warp.
 // All 4 * PU sixteen-byte weight loads of a pass are issued before the first is used (memory-level
@@ -370,11 +435,23 @@ __device__ __noinline__ void consume_items(const LstmShared& sh, const StepPlan&
   }
 }
 
+// a step whose weights live in tensor memory: exactly one 4 x 512 fp32 item per warp.  Kept out of consume_items so
+// that the register allocation of the streamed / shared-memory paths is unaffected.
+__device__ __noinline__ void consume_tmem_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
+                                               int max_units, int warp, int lane) {
+  const int unit = warp / sp.ksplit, kh = warp - unit * sp.ksplit;
+  float s[4];
+  dot4_tmem(tmem_addr_of(sh.tmem_base, warp, sp.tmem_col), xs + (size_t)kh * 512, lane, s);
+  const float c = butterfly4(s[0], s[1], s[2], s[3], lane);
+  if ((lane & 7) == 0) acc[((size_t)kh * max_units + unit) * 4 + (lane >> 3)] += c;
+}
+
 // runtime column-length dispatch (K / ksplit is one of 1024, 512, 256)
 template <int WB>
 __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
                                              int max_units, int warp, int lane) {
   if (sp.n_units == 0) return;
+  if (sp.tmem_col >= 0) { consume_tmem_step(sh, sp, xs, acc, max_units, warp, lane); return; }
   const int klen = sp.K / sp.ksplit;
   if (klen == 1024) consume_items<WB, 1024>(sh, sp, xs, acc, max_units, warp, lane);
   else if (klen == 512) consume_items<WB, 512>(sh, sp, xs, acc, max_units, warp, lane);
@@ -452,12 +529,19 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       sp.policy = ((p.l2_keep_mask >> s) & 1) ? l2_policy_evict_last() : l2_policy_evict_first();
       sp.src_off = src;
       src += (long long)nun[s] * sp.chunk_bytes;
+      // steps b and c (the ones that would stream from HBM) move into tensor memory when they are exactly one
+      // 4 x 512 fp32 item per warp
+      sp.tmem_col = -1;
+      const int t0 = p.use_tmem == 2 ? 1 : 4;      // first of the two steps that live in tensor memory
+      if (WB == 4 && p.use_tmem && (s == t0 || s == t0 + 1) && nun[s] * sp.ksplit == kWarps && ks[s] / sp.ksplit == 512)
+        sp.tmem_col = s == t0 ? 0 : 64;
     }
     // residency: critical-path steps first (d, f), then e1, e0, c, b, a
     const int prio[kSteps] = {3, 6, 5, 4, 2, 1, 0};
     int left = p.res_budget, roff = 0;
     for (int k = 0; k < kSteps; ++k) {
       StepPlan& sp = sh.plan[prio[k]];
+      if (sp.tmem_col >= 0) { sp.n_res = 0; sp.res_off = roff; continue; }
       int n = sp.chunk_bytes > 0 ? left / sp.chunk_bytes : 0;
       if (n > sp.n_units) n = sp.n_units;
       sp.n_res = n; sp.res_off = roff;
@@ -503,6 +587,32 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   }
   __syncthreads();
 
+  // ---- tensor memory: allocate all 512 columns, copy this warp's items of steps b / c in once ----------------------
+  __shared__ uint32_t tmem_base_s;
+  bool any_tmem = false;
+  for (int s = 0; s < kSteps; ++s) any_tmem = any_tmem || sh.plan[s].tmem_col >= 0;
+  sh.tmem_base = 0;
+  if (any_tmem) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    sh.tmem_base = tmem_base_s;
+    for (int s = 0; s < kSteps; ++s) {
+      const StepPlan& sp = sh.plan[s];
+      if (sp.tmem_col < 0) continue;
+      const int unit = warp / sp.ksplit, kh = warp - unit * sp.ksplit;
+      tmem_fill_item(tmem_addr_of(sh.tmem_base, warp, sp.tmem_col),
+                     sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + (size_t)kh * 512 * WB, sp.K * WB, lane);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+
   Watch wd{p.abort_flag, 0, 0};
   bool ok = true;
   const int rep = lc % kRep;
@@ -513,10 +623,11 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   }
   const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
   const int n_steps = p.n_steps;
+  // phase accounting of CTA 0 (diagnostics): accumulators in shared memory so that they cost no registers
+  __shared__ long long ph[16];
+  if (tid < 16) ph[tid] = 0;
+  __syncthreads();
   long long ph_t = clock64();
-  long long ph[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) ph[i] = 0;
 #define LPH(slot)                                         \
   if (lc == 0 && tid == 0) {                              \
     const long long n_ = clock64();                       \
@@ -641,6 +752,11 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   if (lc == 0 && tid == 0)
     for (int i = 0; i < 16; ++i) p.phase_clocks[i] = ph[i];
 #undef LPH
+  if (any_tmem) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(sh.tmem_base) : "memory");
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1143,7 +1143,12 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   // fp32: 98 MB are streamed per frame; keep a, e0, e1 (65 MB; they sit on the critical path) and let b, c
   // (33 MB; they run while the aux CTAs compute the next prenet) stream through from HBM.  Measured:
   // 29.3 us/frame with no hint, 26.4 keep-all, 25.4 keep a/b/c, 22.2 keep a/e0/e1.
-  p.l2_keep_mask = g.wbytes == 2 ? 0x7f : 0x31;
+  // fp32 storage: segments e0/e1 (on the critical path right after the h1 exchange) live in tensor memory, a and c are
+  // kept in L2 (evict_last), b streams from HBM (evict_first).  Measured sweep on one box, us/frame: TMEM off + keep
+  // a/e0/e1 21.6; TMEM(e) + keep a,c 18.5; keep a,b 19.1; keep a 19.5; keep a,b,c 20.6; keep c 23.0; TMEM(b,c) 22.7.
+  p.use_tmem = 1;
+  { const char* e = getenv("TACO2DEC_TMEM"); if (e) p.use_tmem = atoi(e); }
+  p.l2_keep_mask = g.wbytes == 2 ? 0x7f : (p.use_tmem == 1 ? 0x05 : 0x31);
   { const char* e = getenv("TACO2DEC_L2_KEEP_MASK"); if (e) p.l2_keep_mask = (int)strtol(e, nullptr, 0); }
   for (int s = 0; s < c.n_streams; ++s) {
     const StreamParams& sp = gp.st[s];
