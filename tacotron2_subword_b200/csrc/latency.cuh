@@ -76,7 +76,7 @@ struct LatParams {
   const unsigned long long* packed_off;  // [NL+1] byte offsets
   int res_budget;                // shared-memory bytes available for the resident prefix
   int l2_keep_mask;              // bit s set: step s's streamed weights use L2 evict_last, else evict_first
-  int use_tmem;                  // 0: off; 1: weight segments e0/e1 are held in tensor memory; 2: segments b/c (fp32 storage only)
+  int use_tmem;                  // 0: off; 1: weight segments e0, e1 (and a when it fits: 16-bit storage) live in tensor memory; 2: b, c
   LatStream st[2];
   const float *d_b_ih, *d_b_hh;  // decoder LSTM biases [4H]
   const float *proj_w, *proj_b, *gate_w, *gate_b;
@@ -328,32 +328,37 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
-// one item (4 gate rows x 512 fp32 columns) out of tensor memory: 4 chunks of 16 columns = [gate][4 floats]
+// one item (4 gate rows x NUC * 32 sixteen-byte units) out of tensor memory: NUC chunks of 16 columns = [gate][4 words]
+template <int WB, int NUC>
 __device__ __forceinline__ void dot4_tmem(uint32_t taddr, const float* xs, int lane, float (&s)[4]) {
-  uint32_t w[4][16];
+  constexpr int EPU = Mac<WB>::kElems;
+  uint32_t w[NUC][16];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) tmem_ld16(taddr + 16 * c, w[c]);
+  for (int c = 0; c < NUC; ++c) tmem_ld16(taddr + 16 * c, w[c]);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   float a[4][2];
 #pragma unroll
   for (int g = 0; g < 4; ++g) a[g][0] = a[g][1] = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)(lane + 32 * c) * 4);
-    const float x[4] = {v.x, v.y, v.z, v.w};
+  for (int c = 0; c < NUC; ++c) {
+    float x[EPU];
+#pragma unroll
+    for (int e = 0; e < EPU; e += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)(lane + 32 * c) * EPU + e);
+      x[e + 0] = v.x; x[e + 1] = v.y; x[e + 2] = v.z; x[e + 3] = v.w;
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const uint4 u = make_uint4(w[c][g * 4], w[c][g * 4 + 1], w[c][g * 4 + 2], w[c][g * 4 + 3]);
-      Mac<4>::run(u, x, a[g][0], a[g][1]);
+      Mac<WB>::run(u, x, a[g][0], a[g][1]);
     }
   }
 #pragma unroll
   for (int g = 0; g < 4; ++g) s[g] = a[g][0] + a[g][1];
 }
 // one-off: copy this warp's item of a step from the packed global stream into its tensor-memory columns
-__device__ __noinline__ void tmem_fill_item(uint32_t taddr, const unsigned char* base, int row_bytes, int lane) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
+__device__ __noinline__ void tmem_fill_item(uint32_t taddr, const unsigned char* base, int row_bytes, int lane, int nuc) {
+  for (int c = 0; c < nuc; ++c) {
     uint32_t w[16];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -435,13 +440,17 @@ __device__ __noinline__ void consume_items(const LstmShared& sh, const StepPlan&
   }
 }
 
-// a step whose weights live in tensor memory: exactly one 4 x 512 fp32 item per warp.  Kept out of consume_items so
-// that the register allocation of the streamed / shared-memory paths is unaffected.
+// a step whose weights live in tensor memory: exactly one item per warp.  Kept out of consume_items so that the
+// register allocation of the streamed / shared-memory paths is unaffected.
+template <int WB>
 __device__ __noinline__ void consume_tmem_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
                                                int max_units, int warp, int lane) {
   const int unit = warp / sp.ksplit, kh = warp - unit * sp.ksplit;
+  const int klen = sp.K / sp.ksplit;
+  const uint32_t taddr = tmem_addr_of(sh.tmem_base, warp, sp.tmem_col);
   float s[4];
-  dot4_tmem(tmem_addr_of(sh.tmem_base, warp, sp.tmem_col), xs + (size_t)kh * 512, lane, s);
+  if (klen * WB == 2048) dot4_tmem<WB, 4>(taddr, xs + (size_t)kh * klen, lane, s);     // 64 columns
+  else dot4_tmem<WB, 2>(taddr, xs + (size_t)kh * klen, lane, s);                        // 32 columns
   const float c = butterfly4(s[0], s[1], s[2], s[3], lane);
   if ((lane & 7) == 0) acc[((size_t)kh * max_units + unit) * 4 + (lane >> 3)] += c;
 }
@@ -451,7 +460,7 @@ template <int WB>
 __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
                                              int max_units, int warp, int lane) {
   if (sp.n_units == 0) return;
-  if (sp.tmem_col >= 0) { consume_tmem_step(sh, sp, xs, acc, max_units, warp, lane); return; }
+  if (sp.tmem_col >= 0) { consume_tmem_step<WB>(sh, sp, xs, acc, max_units, warp, lane); return; }
   const int klen = sp.K / sp.ksplit;
   if (klen == 1024) consume_items<WB, 1024>(sh, sp, xs, acc, max_units, warp, lane);
   else if (klen == 512) consume_items<WB, 512>(sh, sp, xs, acc, max_units, warp, lane);
@@ -529,12 +538,24 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       sp.policy = ((p.l2_keep_mask >> s) & 1) ? l2_policy_evict_last() : l2_policy_evict_first();
       sp.src_off = src;
       src += (long long)nun[s] * sp.chunk_bytes;
-      // steps b and c (the ones that would stream from HBM) move into tensor memory when they are exactly one
-      // 4 x 512 fp32 item per warp
       sp.tmem_col = -1;
-      const int t0 = p.use_tmem == 2 ? 1 : 4;      // first of the two steps that live in tensor memory
-      if (WB == 4 && p.use_tmem && (s == t0 || s == t0 + 1) && nun[s] * sp.ksplit == kWarps && ks[s] / sp.ksplit == 512)
-        sp.tmem_col = s == t0 ? 0 : 64;
+    }
+    // tensor memory (one item per warp, 128 columns per warp): the critical-path segments e0, e1 first, then a
+    // (use_tmem == 2: b, c instead -- kept for the record, slower)
+    if (p.use_tmem) {
+      const int cand1[3] = {4, 5, 0}, cand2[3] = {1, 2, -1};
+      const int* cand = p.use_tmem == 2 ? cand2 : cand1;
+      int col = 0;
+      for (int k = 0; k < 3; ++k) {
+        const int s = cand[k];
+        if (s < 0) continue;
+        StepPlan& sp = sh.plan[s];
+        const int item_bytes = sp.ksplit > 0 ? sp.chunk_bytes / sp.ksplit : 0;      // 4 rows x klen x WB
+        const int cols = item_bytes / 128;                                          // 32 lanes x 4 bytes per column
+        if (sp.n_units * sp.ksplit != kWarps || (cols != 32 && cols != 64) || col + cols > 128) continue;
+        sp.tmem_col = col;
+        col += cols;
+      }
     }
     // residency: critical-path steps first (d, f), then e1, e0, c, b, a
     const int prio[kSteps] = {3, 6, 5, 4, 2, 1, 0};
@@ -605,8 +626,10 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       const StepPlan& sp = sh.plan[s];
       if (sp.tmem_col < 0) continue;
       const int unit = warp / sp.ksplit, kh = warp - unit * sp.ksplit;
+      const int klen = sp.K / sp.ksplit;
       tmem_fill_item(tmem_addr_of(sh.tmem_base, warp, sp.tmem_col),
-                     sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + (size_t)kh * 512 * WB, sp.K * WB, lane);
+                     sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + (size_t)kh * klen * WB, sp.K * WB, lane,
+                     klen * WB / 512);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
