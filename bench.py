@@ -38,6 +38,29 @@ REF_SAMPLE_FRAMES = 250   # frames per step for the CPU reference arm (bounded s
 W_ACT = 32_082_257        # weights touched per frame, dual-stream SMA
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+# NCCL_DEBUG is set on the box, the reference-style decoder prints a warning at max_decoder_steps), so the process's
+# stdout is pointed at stderr for the whole run and the result line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _claim_stdout() -> None:
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line: dict) -> None:
+    payload = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(payload.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, payload)
+
+
 def algorithmic_bytes_per_frame(B, T_in, T_sub, bytes_per_weight=4):
     """W_act*s_w + B*[(T_in+T_sub)*(512+128)*4 + (T_in+T_sub)*12 + 57,988]."""
     tt = T_in + T_sub
@@ -144,7 +167,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config():
@@ -156,6 +179,7 @@ def workload_config():
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -343,7 +367,7 @@ def main():
                                     "sample": f"{len(t)} full {frames}-frame utterances of the same workload "
                                               f"(oracle/decoder_oracle.py = CPU restatement of model.Decoder.inference, "
                                               f"torch CPU fp32, {threads} threads)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
