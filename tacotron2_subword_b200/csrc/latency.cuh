@@ -1030,6 +1030,10 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
       bool good = true;
       float sum = 0.f;
       if (tid < S * P) {
+        // dropout bit first: it does not depend on the partials, so it is off the chain
+        const int s = tid / P, o = tid - s * P;
+        const uint8_t* keep = p.st[s].keep0;
+        const bool kp = keep ? keep[(size_t)(t + 1) * P + o] != 0 : philox_keep_l(p.seed, s * 2 + 0, t + 1, o, p.thresh_pre);
         unsigned pending = (1u << kAux) - 1u;
         float val[kAux];
         wd.arm();
@@ -1048,9 +1052,6 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
         }
 #pragma unroll
         for (int k = 0; k < kAux; ++k) sum += val[k];
-        const int s = tid / P, o = tid - s * P;
-        const uint8_t* keep = p.st[s].keep0;
-        const bool kp = keep ? keep[(size_t)(t + 1) * P + o] != 0 : philox_keep_l(p.seed, s * 2 + 0, t + 1, o, p.thresh_pre);
         l0_s[tid] = kp ? fmaxf(sum, 0.f) * 2.0f : 0.f;
       }
       if (tid == 0) {
@@ -1073,24 +1074,30 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
       }
       break;
     }
-    // ---- prenet layer 1 rows of this CTA ------------------------------------------------------------------
-    for (int it = warp; it < S * PR; it += kWarps) {
-      const int s = it / PR, r = it - s * PR, row = x * PR + r;
-      const float* w = w1_s + ((size_t)s * PR + r) * P;
-      const float* in = l0_s + (size_t)s * P;
-      float acc = 0.f;
-      for (int k = lane * 4; k < P; k += 128) {
-        const float4 a = *reinterpret_cast<const float4*>(w + k);
-        const float4 b = *reinterpret_cast<const float4*>(in + k);
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    // ---- prenet layer 1 rows of this CTA: a warp does 4 rows at once, the butterfly leaves row g's sum in lane group g
+    //      (8 lanes), and those 8 lanes publish it to the 8 replicas in parallel ---------------------------------------
+    static_assert(kRep == 8, "one lane of a butterfly group per replica");
+    for (int it0 = warp * 4; it0 < S * PR; it0 += kWarps * 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int it = min(it0 + q, S * PR - 1), s = it / PR, r = it - s * PR;
+        const float* w = w1_s + ((size_t)s * PR + r) * P;
+        const float* in = l0_s + (size_t)s * P;
+#pragma unroll
+        for (int k = lane * 4; k < P; k += 128) {
+          const float4 a = *reinterpret_cast<const float4*>(w + k);
+          const float4 b = *reinterpret_cast<const float4*>(in + k);
+          acc[q] = fmaf(a.x, b.x, acc[q]); acc[q] = fmaf(a.y, b.y, acc[q]); acc[q] = fmaf(a.z, b.z, acc[q]); acc[q] = fmaf(a.w, b.w, acc[q]);
+        }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) {
+      const float v = butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
+      const int it = it0 + (lane >> 3), rr = lane & 7;
+      if (it < S * PR) {
+        const int s = it / PR, r = it - s * PR, row = x * PR + r;
         const uint8_t* keep = p.st[s].keep1;
         const bool kp = keep ? keep[(size_t)(t + 1) * P + row] != 0 : philox_keep_l(p.seed, s * 2 + 1, t + 1, row, p.thresh_pre);
-        const float pv = kp ? fmaxf(acc, 0.f) * 2.0f : 0.f;
-#pragma unroll
-        for (int rr = 0; rr < kRep; ++rr) ll_store(rep_pre(p, rr) + ((size_t)rbn * 2 + s) * (P + 8) + row, pv, tag + 1u);
+        ll_store(rep_pre(p, rr) + ((size_t)rbn * 2 + s) * (P + 8) + row, kp ? fmaxf(v, 0.f) * 2.0f : 0.f, tag + 1u);
       }
     }
     __syncthreads();
