@@ -9,6 +9,7 @@
 //   GEMM            dX2 = [Wd_ih | Wd_hh]^T . dG2^T        tcgen05, bf16 operands, fp32 accumulate  (model.py:362-371)
 //   bw_attention    d ctx[t] -> d alpha' -> stepwise-monotonic recurrence -> d energies -> dq, dv, d processed_memory
 //                                                                                     (attention.py:330-398)
+//   (bw_attention_lsa for location-sensitive attention, attention.py:7-85)
 //   bw_pointwise1   dh1[t] (frame t+1's GEMM + dX2 + Wq^T dq) -> attention-LSTM gate gradients dG1[t]
 //   GEMM            dX1 = [W_ih | W_hh]^T . dG1^T          tcgen05                           (model.py:337-346)
 // (d prenet[t], rows of dX1, is saved by the next frame's first kernel; the frame counter is moved by bw_pointwise1.)
@@ -66,11 +67,6 @@ struct Grads {
   float* dwd;      // [S][B][A*LF]   per-utterance partial sums, location_dense weight gradient [a][f]
   float* dwc;      // [S][B][LF*2*LK] per-utterance partial sums, location_conv weight gradient [f][c][k]
 };
-
-__device__ __forceinline__ void xb_store(unsigned char* xbase, int NPAD, int b, int k, float v) {
-  const size_t off = (size_t)(k >> 6) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63);
-  *reinterpret_cast<__nv_bfloat16*>(xbase + off) = __float2bfloat16(v);
-}
 
 // transposed weights: dst rows r = feature of the concatenation [src0 cols | src1 cols], K = source row (gate)
 __global__ void pack_concat_tiles_T_kernel(const float* __restrict__ src0, int K0, const float* __restrict__ src1, int K1c,
