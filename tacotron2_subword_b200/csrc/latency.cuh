@@ -664,6 +664,24 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     const unsigned tag_cur = (unsigned)t + 1u;    // values produced during frame t
     const int rb = t % kLLDepth, rb_prev = (t + kLLDepth - 1) % kLLDepth;
 
+    // teacher-forced frames: request this frame's hoisted prenet row and check the LL flow control now, so that neither
+    // L2 round trip sits between two dependent steps later in the frame
+    float pre_tf_val = 0.f;
+    if (!p.free_running) {
+      if (tid < P) pre_tf_val = __ldg(p.st[s1].pre_tf + (size_t)t * P + tid);
+      // flow control: the aux CTAs are not in the dependency loop, so do not overwrite LL slot t % depth (first written
+      // by this frame's h1) before they have consumed frame t - depth
+      if (t >= kLLDepth && tid == 0) {
+        const unsigned need = (unsigned)kAux * (unsigned)(t - kLLDepth + 1);
+        wd.arm();
+        for (;;) {
+          unsigned v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.aux_done) : "memory");
+          if (v >= need) break;
+          if (wd.expired()) { ok = false; break; }
+        }
+      }
+    }
     // b: W_ih[:, P:] . ctx[t-1]      (a: W_hh . h1[t-1] already ran during the previous frame's attention wait)
     consume_step<WB>(sh, pl[1], sh.xctx + s1 * E, sh.acc1, kMaxU1, warp, lane);
     LPH(0)
@@ -679,7 +697,7 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       ok = poll_vector<1>(rep_pre(p, rep) + ((size_t)rb * 2 + s1) * (P + 8), P + 1, tag_cur, sh.xpre, tid, wd) && ok;
       if (!ok) *sh.exit_flag = 1;
     } else {
-      for (int i = tid; i < P; i += kThreads) sh.xpre[i] = __ldg(p.st[s1].pre_tf + (size_t)t * P + i);
+      if (tid < P) sh.xpre[tid] = pre_tf_val;
       if (tid == 0) sh.xpre[P] = 0.f;
     }
     __syncthreads();
@@ -736,18 +754,6 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     LPH(10)
     __syncthreads();
     LPH(11)
-    // flow control (teacher-forced only): the aux CTAs are not in the dependency loop, so do not
-    // overwrite LL slot t % depth before they have consumed frame t - depth
-    if (!p.free_running && t >= kLLDepth && tid == 0) {
-      const unsigned need = (unsigned)kAux * (unsigned)(t - kLLDepth + 1);
-      wd.arm();
-      for (;;) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.aux_done) : "memory");
-        if (v >= need) break;
-        if (wd.expired()) { ok = false; break; }
-      }
-    }
     {
       int u = 0; float hn = 0.f, cn = 0.f;
       if (lstm_pointwise(sh.acc2, kMaxU2, sh.bias2, sh.c2, nu2, tid, u, hn, cn)) {
