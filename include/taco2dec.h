@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TACO2DEC_ABI_VERSION 5
+#define TACO2DEC_ABI_VERSION 6
 
 #define TACO2DEC_ATTN_SMA 0 /* StepwiseMonotonicAttention   (attention.py:291-398, hparams default) */
 #define TACO2DEC_ATTN_LSA 1 /* LocationSensitiveAttention   (attention.py:7-85)                      */
@@ -44,12 +44,16 @@ extern "C" {
 #define TACO2DEC_E_STATE (-4)   /* weights not set, workspace too small, ... */
 #define TACO2DEC_E_ABORTED (-5) /* in-kernel watchdog fired (grid barrier timeout) */
 
-/* Kernel family selection (taco2dec_set_mode).  AUTO = latency path when eligible (B == 1, SMA,
- * default decoder dims), else the generic any-shape path. */
+/* Kernel family selection (taco2dec_set_mode).  AUTO = latency path when eligible (B == 1, SMA, default decoder
+ * dims); tensor path for 2 <= B <= 128 with default dims unless taco2dec_set_batched_precision(h, 1) asked for
+ * fp32-exact batched arithmetic; else the generic any-shape path. */
 #define TACO2DEC_PATH_AUTO 0
 #define TACO2DEC_PATH_GENERIC 1 /* grid-barrier persistent kernel, fp32 weights in PyTorch layout, any B / SMA+LSA */
 #define TACO2DEC_PATH_LATENCY 2 /* role-specialised persistent kernel, packed weights resident/streamed (batch 1) */
-#define TACO2DEC_PATH_TENSOR 3  /* batched (2 <= B <= 128): LSTM / query products on tcgen05, fp16 operands, fp32 accumulate */
+#define TACO2DEC_PATH_TENSOR 3  /* batched (2 <= B <= 128): LSTM / query products on tcgen05, fp16 operands, fp32 accumulate;
+                                   one persistent launch for all frames when the shape allows, else the per-frame graph */
+#define TACO2DEC_PATH_TENSOR_GRAPH 4 /* the same arithmetic as a CUDA graph of 6-9 kernels replayed per frame (round-1
+                                        implementation; kept for A/B measurements and as the shape fallback) */
 #define TACO2DEC_W_FP32 0       /* packed LSTM weights stay fp32 (parity ~1e-6)                           */
 #define TACO2DEC_W_FP16 1       /* the three LSTM matrices stored fp16, fp32 accumulate (parity ~5e-5)   */
 
@@ -243,8 +247,12 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
 int taco2dec_infer(taco2dec_handle* h, const taco2dec_infer_args* a, void* cuda_stream);
 
 /* Synchronises the stream and reports TACO2DEC_E_ABORTED if the in-kernel watchdog fired
- * during any call since the last check (asynchronous CUDA faults surface here too). */
+ * during any call since the last check (asynchronous CUDA faults surface here too).  The abort word is sticky:
+ * once set every later kernel of the handle bails out at once, until a check has reported and cleared it. */
 int taco2dec_check(taco2dec_handle* h, void* cuda_stream);
+/* The same test without waiting for the caller's stream (reads the sticky abort word on a private stream): for
+ * pipelined callers that already know the call of interest has finished (e.g. after an event wait). */
+int taco2dec_poll_abort(taco2dec_handle* h);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t taco2dec_launch_count(const taco2dec_handle* h);
@@ -261,7 +269,11 @@ int taco2dec_test_gemm(int M, int N, int K, int splits, const float* A, const fl
 
 /* Select the kernel family and the storage type of the packed LSTM weights (latency path). */
 int taco2dec_set_mode(taco2dec_handle* h, int path, int weight_dtype);
-/* TACO2DEC_PATH_GENERIC / _LATENCY / _TENSOR: the path the most recent call actually took. */
+/* fp32_exact = 0 (default): AUTO sends 2 <= B <= 128 to the tensor path (fp16 operands, fp32 accumulation; stated
+ * bound vs the fp32 reference: mel / gate <= 1e-3, alignments <= 2e-4).  fp32_exact = 1: AUTO keeps batched calls on
+ * the generic fp32 kernel; saving activations for backward is then refused (there is no fp32 BPTT). */
+int taco2dec_set_batched_precision(taco2dec_handle* h, int fp32_exact);
+/* TACO2DEC_PATH_GENERIC / _LATENCY / _TENSOR / _TENSOR_GRAPH: the path the most recent call actually took. */
 int taco2dec_last_path(const taco2dec_handle* h);
 
 /* Optional: record CUDA events on the launching stream around the persistent decoder kernel

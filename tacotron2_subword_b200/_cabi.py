@@ -14,9 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtaco2dec.so")  # env override: A/B builds
 
 ATTN_SMA, ATTN_LSA = 0, 1
-PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR, PATH_TENSOR_GRAPH = 0, 1, 2, 3, 4
 W_FP32, W_FP16 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 EXPORTED_SYMBOLS = (
     "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "taco2dec_test_gemm", "taco2dec_saved_layout_query", "taco2dec_grad_layout_query", "taco2dec_backward",
     "taco2dec_postnet_create", "taco2dec_postnet_destroy", "taco2dec_postnet_set_weights",
     "taco2dec_postnet_workspace_bytes", "taco2dec_postnet_forward",
+    "taco2dec_set_batched_precision", "taco2dec_poll_abort",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -165,6 +166,10 @@ def load_library() -> C.CDLL:
     lib.taco2dec_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.taco2dec_set_mode.restype = C.c_int
     lib.taco2dec_set_mode.argtypes = [H, C.c_int, C.c_int]
+    lib.taco2dec_set_batched_precision.restype = C.c_int
+    lib.taco2dec_set_batched_precision.argtypes = [H, C.c_int]
+    lib.taco2dec_poll_abort.restype = C.c_int
+    lib.taco2dec_poll_abort.argtypes = [H]
     lib.taco2dec_last_path.restype = C.c_int
     lib.taco2dec_last_path.argtypes = [H]
     lib.taco2dec_test_gemm.restype = C.c_int

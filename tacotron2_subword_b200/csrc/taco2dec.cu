@@ -894,7 +894,9 @@ struct taco2dec_handle {
   bool have_weights;
   taco2dec_weights w;
   int64_t launches;
-  int* last_abort_flag;  // device address of the watchdog flag of the most recent call
+  int* abort_dev;        // sticky watchdog word (library-owned); every kernel of the handle polls / sets it
+  cudaStream_t aux_stream;  // private non-blocking stream: reads of abort_dev that must not wait for the caller's stream
+  int batched_fp32;      // 1 = AUTO keeps 2 <= B <= 128 on the generic fp32 kernel
   long long* last_phase_clocks;
   int path_mode;         // TACO2DEC_PATH_*
   int weight_dtype;      // TACO2DEC_W_*
@@ -1032,7 +1034,7 @@ int fill_common(taco2dec_handle* h, Params& p, int B, int T_in, int T_sub, const
   p.h1 = (float*)(ws + L.h1); p.c1 = (float*)(ws + L.c1); p.h2 = (float*)(ws + L.h2); p.c2 = (float*)(ws + L.c2);
   p.ctx = (float*)(ws + L.ctx); p.q = (float*)(ws + L.q);
   p.sync_ctr = (unsigned*)(ws + L.ctl);
-  p.abort_flag = (int*)(ws + L.ctl) + 1;
+  p.abort_flag = h->abort_dev;
   p.done_count = (int*)(ws + L.ctl) + 2;
   p.phase_clocks = (long long*)(ws + L.ctl + 64);
   return 0;
@@ -1505,7 +1507,6 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
   const taco2dec_config& c = h->cfg;
   // control words: barrier counter, watchdog flag, done counter
   CUDA_TRY(cudaMemsetAsync(ws + L.ctl, 0, 64 * sizeof(float), st));
-  h->last_abort_flag = p.abort_flag;
   h->last_phase_clocks = p.phase_clocks;
   // processed memory, once per call (model.py:258-261)
   for (int s = 0; s < c.n_streams; ++s) {
@@ -1515,9 +1516,13 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  const bool tensor_ok = bt_shape_ok(h, p.B, T_in, T_sub);
+  const bool tensor_mode = h->path_mode == TACO2DEC_PATH_TENSOR || h->path_mode == TACO2DEC_PATH_TENSOR_GRAPH;
   if (h->cur_sv.gates1) {   // activations are kept for backward: only the tensor path produces them
-    if (!bw_shape_ok(h, p.B, T_in, T_sub) || (h->path_mode != TACO2DEC_PATH_AUTO && h->path_mode != TACO2DEC_PATH_TENSOR))
-      return fail(TACO2DEC_E_ARG, "saving activations for backward needs the tensor path: 2 <= B <= 128, default decoder dims");
+    if (!bw_shape_ok(h, p.B, T_in, T_sub) || (h->path_mode != TACO2DEC_PATH_AUTO && !tensor_mode) ||
+        (h->path_mode == TACO2DEC_PATH_AUTO && h->batched_fp32))
+      return fail(TACO2DEC_E_ARG, "saving activations for backward needs the tensor path: 2 <= B <= 128, default decoder "
+                                  "dims, batched precision fp16");
     return run_batched(h, p, T_in, T_sub, st);
   }
   const bool want_lat = (h->path_mode == TACO2DEC_PATH_AUTO || h->path_mode == TACO2DEC_PATH_LATENCY) &&
@@ -1525,12 +1530,11 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
   if (h->path_mode == TACO2DEC_PATH_LATENCY && !want_lat)
     return fail(TACO2DEC_E_ARG, "latency path needs B=1, SMA, default decoder dims and a short enough memory");
   if (want_lat) return run_latency(h, p, st);
-  const bool tensor_ok = bt_shape_ok(h, p.B, T_in, T_sub);
-  if (h->path_mode == TACO2DEC_PATH_TENSOR && !tensor_ok)
+  if (tensor_mode && !tensor_ok)
     return fail(TACO2DEC_E_ARG, "tensor path needs 2 <= B <= 128 and default decoder dims");
-  // AUTO takes the tensor-core path only when fp16 operands were asked for (it rounds weights AND x/h to fp16)
-  if (tensor_ok && (h->path_mode == TACO2DEC_PATH_TENSOR ||
-                    (h->path_mode == TACO2DEC_PATH_AUTO && h->weight_dtype == TACO2DEC_W_FP16)))
+  // AUTO: batched calls take the tensor-core path (weights AND x/h operands rounded to fp16, fp32 accumulation)
+  // unless the caller asked for fp32-exact batched arithmetic (taco2dec_set_batched_precision)
+  if (tensor_ok && (tensor_mode || (h->path_mode == TACO2DEC_PATH_AUTO && !h->batched_fp32)))
     return run_batched(h, p, T_in, T_sub, st);
   h->last_path = TACO2DEC_PATH_GENERIC;
   const int BT = pick_bt(p.B);
@@ -1636,7 +1640,7 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   h->have_weights = false;
   h->launches = 0;
-  h->last_abort_flag = nullptr;
+  h->abort_dev = nullptr; h->aux_stream = nullptr; h->batched_fp32 = 0;
   h->last_phase_clocks = nullptr;
   h->path_mode = TACO2DEC_PATH_AUTO;
   h->weight_dtype = TACO2DEC_W_FP32;
@@ -1650,6 +1654,9 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
+  CUDA_TRY(cudaMalloc(&h->abort_dev, 64));
+  CUDA_TRY(cudaMemset(h->abort_dev, 0, 64));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
   *out = h;
   return 0;
 }
@@ -1658,6 +1665,8 @@ int taco2dec_destroy(taco2dec_handle* h) {
   if (h) {
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
+    if (h->abort_dev) cudaFree(h->abort_dev);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->packed) cudaFree(h->packed);
     if (h->packed_off) cudaFree(h->packed_off);
     if (h->ll_buf) cudaFree(h->ll_buf);
@@ -1699,7 +1708,7 @@ int taco2dec_test_gemm(int M, int N, int K, int splits, const float* A, const fl
 
 int taco2dec_set_mode(taco2dec_handle* h, int path, int weight_dtype) {
   if (!h) return fail(TACO2DEC_E_ARG, "null handle");
-  if (path < TACO2DEC_PATH_AUTO || path > TACO2DEC_PATH_TENSOR) return fail(TACO2DEC_E_ARG, "bad path");
+  if (path < TACO2DEC_PATH_AUTO || path > TACO2DEC_PATH_TENSOR_GRAPH) return fail(TACO2DEC_E_ARG, "bad path");
   if (weight_dtype != TACO2DEC_W_FP32 && weight_dtype != TACO2DEC_W_FP16) return fail(TACO2DEC_E_ARG, "bad weight dtype");
   h->path_mode = path;
   h->weight_dtype = weight_dtype;
@@ -1881,7 +1890,6 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
   g.dc1 = (float*)(gb + gs.dc1); g.dc2 = (float*)(gb + gs.dc2);
   g.dyh = (float*)(gb + gs.dyh); g.dyc = (float*)(gb + gs.dyc);
   CUDA_TRY(cudaMemsetAsync(gb + gs.zero_begin, 0, gs.zero_end - gs.zero_begin, st));
-  h->last_abort_flag = nullptr;
   if (int rc = bw_prepare(h, st)) return rc;
   if (a->B <= 16) return bw_run_frames<16>(h, p, g, st);
   if (a->B <= 32) return bw_run_frames<32>(h, p, g, st);
@@ -1920,11 +1928,26 @@ int taco2dec_check(taco2dec_handle* h, void* cuda_stream) {
   if (!h) return fail(TACO2DEC_E_ARG, "null handle");
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
   CUDA_TRY(cudaGetLastError());
-  if (h->last_abort_flag) {
-    int flag = 0;
-    CUDA_TRY(cudaMemcpy(&flag, h->last_abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(TACO2DEC_E_ABORTED, "persistent decoder kernel aborted: grid barrier watchdog fired");
+  return taco2dec_poll_abort(h);
+}
+
+int taco2dec_poll_abort(taco2dec_handle* h) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null handle");
+  int flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flag, h->abort_dev, sizeof(int), cudaMemcpyDeviceToHost, h->aux_stream));
+  CUDA_TRY(cudaStreamSynchronize(h->aux_stream));
+  if (flag) {
+    CUDA_TRY(cudaMemsetAsync(h->abort_dev, 0, sizeof(int), h->aux_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->aux_stream));
+    return fail(TACO2DEC_E_ABORTED, "persistent decoder kernel aborted: an in-kernel watchdog fired (outputs of the calls "
+                                    "since the last check are invalid)");
   }
+  return 0;
+}
+
+int taco2dec_set_batched_precision(taco2dec_handle* h, int fp32_exact) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null handle");
+  h->batched_fp32 = fp32_exact ? 1 : 0;
   return 0;
 }
 

@@ -156,19 +156,23 @@ def gta_extract(decoder, items: Sequence[GtaItem], out_dir: str, max_batch: int 
             mel_out.record_stream(copy_stream)
             pending.append((done, host, [items[i].name for i in idx], tlen))
             while len(pending) > 1:                      # hand the previous batch to the writer
-                _flush(pending.pop(0), writer)
+                _flush(pending.pop(0), writer, decoder)
             if on_batch is not None:
                 on_batch(bi, len(batches))
         while pending:
-            _flush(pending.pop(0), writer)
+            _flush(pending.pop(0), writer, decoder)
     finally:
         files = writer.close()
     return files
 
 
-def _flush(entry, writer: AsyncNpyWriter) -> None:
+def _flush(entry, writer: AsyncNpyWriter, decoder=None) -> None:
     done, host, names, tlen = entry
     done.synchronize()
+    if decoder is not None:
+        # the batch has finished: if an in-kernel watchdog aborted it, its outputs are garbage -- raise instead of writing
+        # them (reads the sticky abort word on a private stream, so the next batch keeps running meanwhile)
+        decoder.check(sync=False)
     arr = host.numpy()
     for r, (name, t) in enumerate(zip(names, tlen)):
         writer.put(name, np.ascontiguousarray(arr[r: r + 1, :, :t]))     # [1, n_mel, T], GTA.py:61

@@ -78,17 +78,20 @@ class _Engine:
     def launch_count(self) -> int:
         return int(self.lib.taco2dec_launch_count(self.handle))
 
-    def set_mode(self, path: str, weight_dtype: str) -> None:
+    def set_mode(self, path: str, weight_dtype: str, batched_precision: str = "fp16") -> None:
         paths = {"auto": _cabi.PATH_AUTO, "generic": _cabi.PATH_GENERIC, "latency": _cabi.PATH_LATENCY,
-                 "tensor": _cabi.PATH_TENSOR}
+                 "tensor": _cabi.PATH_TENSOR, "tensor_graph": _cabi.PATH_TENSOR_GRAPH}
         dts = {"fp32": _cabi.W_FP32, "fp16": _cabi.W_FP16}
-        if (path, weight_dtype) != self.mode:
+        bps = {"fp16": 0, "fp32": 1}
+        if (path, weight_dtype, batched_precision) != self.mode:
             _cabi.check(self.lib.taco2dec_set_mode(self.handle, paths[path], dts[weight_dtype]))
-            self.mode = (path, weight_dtype)
+            _cabi.check(self.lib.taco2dec_set_batched_precision(self.handle, bps[batched_precision]))
+            self.mode = (path, weight_dtype, batched_precision)
             self.weights_key = None   # packed streams depend on the storage type
 
     def last_path(self) -> str:
-        return {0: "none", 1: "generic", 2: "latency", 3: "tensor"}[int(self.lib.taco2dec_last_path(self.handle))]
+        return {0: "none", 1: "generic", 2: "latency", 3: "tensor", 4: "tensor_graph"}[
+            int(self.lib.taco2dec_last_path(self.handle))]
 
     def set_profiling(self, on: bool) -> None:
         _cabi.check(self.lib.taco2dec_set_profiling(self.handle, int(on)))
@@ -149,15 +152,24 @@ class _DecoderTF(torch.autograd.Function):
     def forward(ctx, dec, independent, memory, embeddings, dec_in, mlen, blen, *params):
         ctx.set_materialize_grads(False)
         outs, state = dec._run_tf(memory, embeddings, dec_in, mlen, blen, save=True, independent=independent)
+        mel, gate, align, align_b = outs
+        # The Function's own outputs must not be reachable from ctx (output -> grad_fn -> ctx -> output is a cycle the
+        # reference counter cannot free, and it would pin the multi-GB `saved` buffer): keep detached aliases instead.
+        state["align"] = align.detach()
+        state["align_b"] = None if align_b is None else align_b.detach()
         ctx.dec, ctx.state = dec, state
         ctx.n_params = len(params)
-        mel, gate, align, align_b = outs
         return (mel, gate, align) + ((align_b,) if align_b is not None else ())
 
     @staticmethod
     def backward(ctx, d_mel, d_gate, d_align=None, d_align_b=None):
         dec, st = ctx.dec, ctx.state
+        if st is None:
+            raise RuntimeError("decoder backward called twice: the saved activations are released after the first pass "
+                               "(retain_graph is not supported by the hand-written BPTT)")
+        ctx.state = None          # release the saved-activation buffer as soon as this pass is done
         eng, dev = st["eng"], st["dev"]
+        dec.check(dev)            # a watchdog abort in the forward pass must not turn into silent garbage gradients
         B, T, T_in, T_sub = st["B"], st["T"], st["T_in"], st["T_sub"]
         S, H, E, P, A, M = dec.n_streams, dec.attention_rnn_dim, dec.encoder_embedding_dim, dec.prenet_dim, \
             dec.attention_dim, dec.n_mel_channels
@@ -304,8 +316,13 @@ class Decoder(nn.Module):
         self.linear_projection = LinearNorm(proj_in, mel_in)
         self.gate_layer = LinearNorm(proj_in, 1, bias=True, w_init_gain="sigmoid")
         # -- extensions (not in the reference) --------------------------------------------
-        self.decoder_path = "auto"      # "auto" | "generic" | "latency" | "tensor"  (see include/taco2dec.h)
-        self.weight_dtype = "fp32"      # storage of the packed LSTM matrices on the latency path: "fp32" | "fp16"
+        # "auto": batch 1 -> latency path; 2 <= B <= 128 -> tensor path unless batched_precision == "fp32"; else generic
+        self.decoder_path = "auto"      # "auto" | "generic" | "latency" | "tensor" | "tensor_graph"  (include/taco2dec.h)
+        self.weight_dtype = "fp32"      # storage of the packed LSTM matrices on the LATENCY path (batch 1): "fp32" | "fp16"
+        # Batched calls (2 <= B <= 128): "fp16" = tcgen05 path, LSTM / query operands (weights AND x, h) rounded to fp16,
+        # fp32 accumulation, stated bound mel/gate <= 1e-3, alignments <= 2e-4 vs the fp32 reference; "fp32" = the generic
+        # fp32-exact kernel (~15x slower at B = 64; no backward: training with it raises).
+        self.batched_precision = "fp16"
         self.dropout_replay: Optional[DropoutReplay] = None  # parity runs: externally drawn masks
         self.rng_seed: Optional[int] = None                  # fixed Philox seed; None = fresh per call
         self.validate_lengths = True
@@ -351,10 +368,33 @@ class Decoder(nn.Module):
                self.gate_layer.linear_layer.weight, self.gate_layer.linear_layer.bias]
         return ts
 
+    def invalidate_weights(self) -> None:
+        """Force the library-owned weight re-layouts (latency-path streams, fp16 / bf16 tiles) to be rebuilt on the next
+        call.  Needed after in-place updates that autograd does not see (``p.data.add_()``, ``p.data.copy_()`` -- used by
+        some optimizers and EMA swaps -- do not bump ``_version``).  In training mode every call re-packs anyway."""
+        for eng in self._engines.values():
+            eng.weights_key = None
+
+    def check(self, device=None, sync: bool = True) -> None:
+        """Synchronise and raise ``Taco2DecError`` (TACO2DEC_E_ABORTED) if an in-kernel watchdog fired in any decoder
+        call since the last check -- the teacher-forced entry points return without synchronising, so callers that are
+        about to consume the outputs on the host (GTA writer, backward) call this first.  ``sync=False`` does not wait
+        for the current stream (for pipelined callers that have already waited on an event)."""
+        dev = device if device is not None else self.gate_layer.linear_layer.weight.device
+        eng = self._engine(torch.device(dev))
+        with torch.cuda.device(eng.device):
+            if not sync:     # caller already knows the call of interest has finished (event wait)
+                _cabi.check(eng.lib.taco2dec_poll_abort(eng.handle))
+                return
+            stream = torch.cuda.current_stream(eng.device).cuda_stream
+            _cabi.check(eng.lib.taco2dec_check(eng.handle, C.c_void_p(stream)))
+
     def _bind_weights(self, eng: _Engine) -> None:
-        eng.set_mode(self.decoder_path, self.weight_dtype)
+        eng.set_mode(self.decoder_path, self.weight_dtype, self.batched_precision)
         key = tuple((t.data_ptr(), t._version) for t in self._weight_tensors())
-        if key == eng.weights_key:
+        # training mode: optimizers may write through .data (no version bump), and a re-pack (<0.5 ms) is noise next
+        # to a training step -- always rebuild; eval mode: rebuild on pointer / version change or invalidate_weights()
+        if key == eng.weights_key and not self.training:
             return
         eng.weights_key = key
         w = _cabi.Weights()
@@ -426,6 +466,10 @@ class Decoder(nn.Module):
         wants_grad = torch.is_grad_enabled() and (
             any(p.requires_grad for p in self.parameters()) or memory.requires_grad or
             (embeddings is not None and embeddings.requires_grad))
+        if wants_grad and self.decoder_path == "auto" and self.batched_precision == "fp32" and memory.shape[0] >= 2:
+            raise NotImplementedError(
+                "tacotron2_subword_b200: batched_precision='fp32' has no backward (the BPTT kernels use fp16 forward / "
+                "bf16 backward operands); train with batched_precision='fp16' or evaluate under torch.no_grad()")
         if wants_grad and self._backward_supported(memory):
             params = self._weight_tensors()
             outs = _DecoderTF.apply(self, bool(independent), memory, embeddings if self.n_streams == 2 else None, decoder_inputs,
@@ -446,7 +490,7 @@ class Decoder(nn.Module):
     def _backward_supported(self, memory) -> bool:
         if self.attention_kind == LSA and (self.loc_filters, self.loc_kernel) != (32, 31):
             return False
-        return (2 <= memory.shape[0] <= 128 and self.decoder_path in ("auto", "tensor")
+        return (2 <= memory.shape[0] <= 128 and self.decoder_path in ("auto", "tensor", "tensor_graph")
                 and (self.attention_rnn_dim, self.decoder_rnn_dim, self.encoder_embedding_dim, self.prenet_dim,
                      self.attention_dim, self.n_mel_channels) == (1024, 1024, 512, 256, 128, 80))
 

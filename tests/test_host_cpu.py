@@ -140,3 +140,61 @@ def test_oracle_vs_live_reference():
                                         inp["bert_lengths"], plan, training=True)
     for k, v in zip(("mel", "gate", "align", "align_bert"), out):
         assert maxabs(v, torch.from_numpy(ref[k])) <= 2e-6, k
+
+
+def test_decoder_tf_function_does_not_pin_saved_activations():
+    """_DecoderTF must not keep its own outputs reachable from ctx -- output -> grad_fn -> ctx -> output
+    is a cycle that pins the multi-GB saved-activation buffer.  With the C call mocked out, dropping the outputs must free
+    the buffer by reference counting alone (no gc.collect())."""
+    import gc
+    import weakref
+    from tacotron2_subword_b200.model import _DecoderTF
+    dec = Decoder(create_hparams())
+    refs = []
+
+    def fake_run_tf(memory, embeddings, dec_in, mlen, blen, save, independent=False):
+        B, T = memory.shape[0], dec_in.shape[2]
+        outs = (torch.zeros(B, T, 80), torch.zeros(B, T), torch.zeros(B, T, memory.shape[1]), torch.zeros(B, T, embeddings.shape[1]))
+        saved = torch.zeros(1 << 16, dtype=torch.uint8)
+        refs.append(weakref.ref(saved))
+        return outs, dict(saved=saved, align=outs[2], align_b=outs[3], params=dec._weight_tensors())
+
+    dec._run_tf = fake_run_tf
+    gc.disable()
+    try:
+        for _ in range(3):
+            outs = _DecoderTF.apply(dec, False, torch.zeros(2, 5, 512, requires_grad=True), torch.zeros(2, 3, 512), torch.zeros(2, 80, 4),
+                                    None, None, *dec._weight_tensors())
+            assert outs[0].grad_fn is not None
+            del outs
+        assert all(r() is None for r in refs), "saved-activation buffers are still alive after their outputs were dropped"
+    finally:
+        gc.enable()
+
+
+def test_invalidate_weights_and_training_mode_force_a_rebind():
+    """`.data` updates do not bump ``_version``; invalidate_weights() drops the cached key, and in
+    training mode the key is never trusted."""
+    dec = Decoder(create_hparams())
+
+    class FakeEng:
+        weights_key = None
+        device = torch.device("cpu")
+
+        def set_mode(self, *a):
+            pass
+
+    eng = FakeEng()
+    dec._engines[0] = eng
+    key = tuple((t.data_ptr(), t._version) for t in dec._weight_tensors())
+    eng.weights_key = key
+    dec.decoder_rnn.weight_hh.data.add_(1.0)
+    assert tuple((t.data_ptr(), t._version) for t in dec._weight_tensors()) == key     # the blind spot itself
+    dec.invalidate_weights()
+    assert eng.weights_key is None
+    eng.weights_key = key
+    dec.train()
+    with pytest.raises(Exception):      # training mode goes on to re-pack (and fails here only because there is no library handle)
+        dec._bind_weights(eng)
+    dec.eval()
+    dec._bind_weights(eng)              # eval + unchanged key: early return, nothing touched
