@@ -1,0 +1,907 @@
+// persist.cuh -- persistent batched decoder (2 <= B <= 128, SMA): ONE cooperative launch runs every frame.
+//
+// Same arithmetic as the per-frame graph of batched.cuh (fp16 operands on tcgen05, fp32 accumulation in TMEM, fp32
+// pointwise / attention / projection) but without kernel boundaries: 128 CTAs stay resident, each owns one
+// (128-row tile, K split) of BOTH LSTM gate products for the whole utterance and keeps its cell states in shared memory.
+//
+//   warp 16 (one thread)   TMA producer: walks the frame's tile program -- 14 k-blocks of the attention-LSTM product, 16 of
+//                          the decoder-LSTM product -- ordered by when their inputs become available (h[t-1] first, then
+//                          context, then the prenet / this frame's h1 and context), polls the producers' counters, and stages
+//                          weight tile + activation tile per k-block with cp.async.bulk into an mbarrier ring
+//   warp 17 (one thread)   issues tcgen05.mma (M = 128 gate rows, N = padded batch, K = 16) into two TMEM accumulators
+//   warps 0-15             epilogue + everything pointwise: TMEM -> split-K partials -> (partner CTAs) -> LSTM cell update for
+//                          a column share of the tile -> fp16 operand tiles of the consumers + query partials; then one
+//                          attention task (utterance, stream) per CTA; free-running: projection partials, mel sum + stop
+//                          test, and the two prenet layers, each spread over all 128 CTAs
+//
+// CTAs exchange through L2: data with plain stores, then ONE release-increment of a counter per CTA and phase; consumers
+// acquire-poll the counter (no grid-wide barrier: a consumer only waits for the counters it depends on, and the producer
+// warp prefetches the weight tiles of the next product while the compute warps are still in the previous phase).
+//
+// Reference arithmetic: model.py:322-390 (decode), attention.py:330-398 (SMA), model.py:13-24 (prenet), :480-485 (stop).
+#pragma once
+
+namespace pb {
+
+using bt::A;
+using bt::E;
+using bt::H;
+using bt::M;
+using bt::P;
+
+constexpr int kCtas = 128;                    // LSTM CTAs = 32 row tiles x 4 splits (decoder) = 2 x 32 x 2 (attention LSTMs)
+constexpr int kCT = 512;                      // compute threads (warps 0-15)
+constexpr int kThreads = kCT + 64;            // + producer warp + MMA warp
+constexpr int kTiles1 = 14;                   // k-blocks per CTA and frame, attention-LSTM product (K1 = 1792, split 2)
+constexpr int kMaxTiles = 30;                 // + 16 of the decoder-LSTM product (K2 = 4096, split 4)
+constexpr int kMelPad = 96;                   // 80 mel rows + gate, padded
+constexpr int kSlices = 16;                   // context slices of the projection (64 features each)
+constexpr long long kTimeoutClocks = 6000000000LL;
+
+// counters (one 128-byte line each)
+enum { F_P1 = 0, F_P2 = 64, F_H1 = 96, F_CTX = 98, F_H2 = 100, F_MEL = 101, F_L0 = 102, F_PRE = 104, F_DONE = 106, F_COUNT = 108 };
+constexpr int kFlagStride = 32;               // words
+
+struct PbParams {
+  const unsigned char* wt;      // [kCtas][kMaxTiles] fp16 weight tiles (16 KB) in consumption order
+  unsigned char* x1;            // [2 parities][S][28 kb][NPAD x 64] fp16   [prenet | ctx | h1]
+  unsigned char* x2;            // [2 parities][K2/64 kb][NPAD x 64] fp16   [h1_0 | ctx_0 | (h1_1 | ctx_1) | h2]
+  const unsigned char* xpre;    // teacher-forced: [T][S][4 kb][NPAD x 64] hoisted prenet tiles
+  float* part1;                 // [S][32][2][128][NPAD]
+  float* part2;                 // [32][4][128][NPAD]
+  float* qpart;                 // [S][32][NPAD][A]
+  float* melp;                  // [32][NPAD][kMelPad]   projection partials over the CTA's 32 h2 units
+  float* ctxp;                  // [kSlices][NPAD][kMelPad] projection partials over a 64-feature context slice
+  float* melx;                  // [NPAD][M]             mel frame fed back to the prenet
+  float* l0x;                   // [S][NPAD][P]          prenet layer-0 activations
+  unsigned* flags;              // [F_COUNT][kFlagStride]
+  bt::Saved sv;
+  int stages;                   // ring depth
+  int n_res;                    // weight tiles resident in shared memory (first n_res of the CTA's program)
+};
+
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(tc::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+struct Ctl {
+  int* abort_flag;
+  volatile int* s_exit;
+};
+// every wait in the kernel goes through one of these two: a protocol bug or a dead peer becomes an abort word all CTAs see
+__device__ __noinline__ bool poll_ge(const unsigned* f, unsigned target, const Ctl& c) {
+  if (target == 0u) return true;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while ((int)(ld_acquire_u32(f) - target) < 0) {
+    if ((++spins & 63u) == 0u) {
+      if (*c.s_exit) return false;
+      if (*((volatile int*)c.abort_flag) != 0) { *c.s_exit = 1; return false; }
+      if ((spins & 4095u) == 0u && clock64() - t0 > kTimeoutClocks) { atomicExch(c.abort_flag, 1); *c.s_exit = 1; return false; }
+    }
+  }
+  return true;
+}
+__device__ __noinline__ bool mbar_wait_ab(uint64_t* bar, uint32_t parity, const Ctl& c) {
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 63u) == 0u) {
+      if (*c.s_exit) return false;
+      if (*((volatile int*)c.abort_flag) != 0) { *c.s_exit = 1; return false; }
+      if ((spins & 1023u) == 0u && clock64() - t0 > kTimeoutClocks) { atomicExch(c.abort_flag, 1); *c.s_exit = 1; return false; }
+    }
+  }
+  return true;
+}
+// one thread, after a compute-warp barrier: publish this CTA's stores of the phase
+__device__ __forceinline__ void signal(unsigned* f) {
+  __threadfence();
+  red_release_add(f, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The frame's tile program.  Logical k-block numbering follows the operand buffers:
+//   X1[s]: pre 0-3 | ctx 4-11 | h1 12-27            X2 (S=2): h1_0 0-15 | ctx_0 16-23 | h1_1 24-39 | ctx_1 40-47 | h2 48-63
+//                                                   X2 (S=1): h1_0 0-15 | ctx_0 16-23 | h2 24-39
+// ------------------------------------------------------------------------------------------------------------------
+enum Dep { DEP_NONE = 0, DEP_H1_PREV, DEP_CTX_PREV, DEP_PRE, DEP_H2_PREV, DEP_H1_0, DEP_H1_1, DEP_CTX_0, DEP_CTX_1 };
+struct TileInfo {
+  int gemm;    // 0 = attention LSTM, 1 = decoder LSTM
+  int kb;      // logical k-block inside the operand buffer
+  int dep;
+  int first, last;   // first / last tile of its product
+};
+__host__ __device__ inline int tiles2_of(int S) { return S == 2 ? 16 : 10; }
+__host__ __device__ inline TileInfo tile_info(int i, bool has_g1, int S, int sig1, int sig2) {
+  TileInfo ti;
+  if (has_g1 && i < kTiles1) {
+    ti.gemm = 0; ti.first = i == 0; ti.last = i == kTiles1 - 1;
+    if (i < 8) { ti.kb = 12 + 8 * sig1 + i; ti.dep = DEP_H1_PREV; }
+    else if (i < 12) { ti.kb = 4 + 4 * sig1 + (i - 8); ti.dep = DEP_CTX_PREV; }
+    else { ti.kb = 2 * sig1 + (i - 12); ti.dep = DEP_PRE; }
+    return ti;
+  }
+  const int j = has_g1 ? i - kTiles1 : i;
+  const int n2 = tiles2_of(S);
+  ti.gemm = 1; ti.first = j == 0; ti.last = j == n2 - 1;
+  const int kb_h2 = S == 2 ? 48 : 24;
+  if (j < 4) { ti.kb = kb_h2 + 4 * sig2 + j; ti.dep = DEP_H2_PREV; }
+  else if (j < 8) { ti.kb = 4 * sig2 + (j - 4); ti.dep = DEP_H1_0; }
+  else if (S == 2 && j < 12) { ti.kb = 24 + 4 * sig2 + (j - 8); ti.dep = DEP_H1_1; }
+  else if (S == 2 && j < 14) { ti.kb = 16 + 2 * sig2 + (j - 12); ti.dep = DEP_CTX_0; }
+  else if (S == 2) { ti.kb = 40 + 2 * sig2 + (j - 14); ti.dep = DEP_CTX_1; }
+  else { ti.kb = 16 + 2 * sig2 + (j - 8); ti.dep = DEP_CTX_0; }
+  return ti;
+}
+
+// weights -> per-CTA fp16 tiles in consumption order; tile rows = [gate g][unit u] of the CTA's 32 hidden units
+struct PackSrc {
+  const float* w_ih[2];
+  const float* w_hh[2];
+  const float* d_w_ih;
+  const float* d_w_hh;
+};
+__global__ void pb_pack_weights(PackSrc src, int S, unsigned char* __restrict__ wt) {
+  const int c = blockIdx.x;
+  const bool has_g1 = c < S * 64;
+  const int s1 = c / 64, mt1 = (c % 64) / 2, sig1 = c % 2, mt2 = c / 4, sig2 = c % 4;
+  const int n_tiles = (has_g1 ? kTiles1 : 0) + tiles2_of(S);
+  const int K2x = S * (H + E);
+  for (int i = 0; i < n_tiles; ++i) {
+    const TileInfo ti = tile_info(i, has_g1, S, sig1, sig2);
+    unsigned char* tile = wt + ((size_t)c * kMaxTiles + i) * tc::kATileBytes;
+    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
+      const int kk = e & 63, r = e >> 6, g = r >> 5, u = r & 31;
+      const int k = ti.kb * 64 + kk;
+      float v;
+      if (ti.gemm == 0) {
+        const size_t row = (size_t)g * H + mt1 * 32 + u;
+        v = k < P + E ? src.w_ih[s1][row * (P + E) + k] : src.w_hh[s1][row * H + (k - (P + E))];
+      } else {
+        const size_t row = (size_t)g * H + mt2 * 32 + u;
+        v = k < K2x ? src.d_w_ih[row * K2x + k] : src.d_w_hh[row * H + (k - K2x)];
+      }
+      *reinterpret_cast<__half*>(tile + tc::tile_offset_bytes(128, r, kk)) = __float2half(v);
+    }
+  }
+}
+
+// teacher-forced: hoisted prenet output [T+1][B][P] fp32 -> per-frame operand tiles [T][4 kb][NPAD x 64] fp16 of one stream
+__global__ void pb_prenet_tiles(const float* __restrict__ pre, int T, int B, int NPAD, int S, int s, unsigned char* __restrict__ xpre) {
+  const size_t total = (size_t)T * B * (P / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % (P / 8)), b = (int)((i / (P / 8)) % B), t = (int)(i / ((size_t)(P / 8) * B));
+    const float* src = pre + ((size_t)t * B + b) * P + c8 * 8;
+    const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const int k = c8 * 8;
+    unsigned char* dst = xpre + (((size_t)t * S + s) * 4 + (k >> 6)) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63);
+    *reinterpret_cast<uint4*>(dst) = pn::pack8(v);
+  }
+}
+
+__device__ __forceinline__ unsigned char* x_chunk_ptr(unsigned char* xbase, int NPAD, int b, int k) {   // k % 8 == 0
+  return xbase + (size_t)(k >> 6) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63);
+}
+
+// shared-memory plan (bytes); everything after the ring is fixed-size except the attention scratch
+struct Smem {
+  size_t ring, res, c1, c2, hs, wq, wph, wpc, w0, w1, bias, att, red, total;
+};
+__host__ __device__ inline Smem smem_plan(int NPAD, int stages, int n_res, int max_ts, int fr) {
+  Smem s;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~(size_t)127; return o; };
+  s.ring = take((size_t)stages * (tc::kATileBytes + (size_t)NPAD * 128));
+  s.res = take((size_t)n_res * tc::kATileBytes);
+  s.c1 = take((size_t)32 * (NPAD / 2) * 4);
+  s.c2 = take((size_t)32 * (NPAD / 4) * 4);
+  s.hs = take((size_t)(NPAD / 2) * 33 * 4);
+  s.wq = take((size_t)A * 33 * 4);
+  s.wph = take(fr ? (size_t)(M + 1) * 33 * 4 : 0);
+  s.wpc = take(fr ? (size_t)(M + 1) * 65 * 4 : 0);
+  s.w0 = take(fr ? (size_t)4 * M * 4 : 0);
+  s.w1 = take(fr ? (size_t)4 * P * 4 : 0);
+  s.bias = take((size_t)2 * 128 * 4);
+  s.att = take(bt::sma_smem_floats(max_ts) * 4);
+  s.red = take((size_t)8 * kMelPad * 4 + 16 * 64 * 4);
+  s.total = off;
+  return s;
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const __grid_constant__ Params p,
+                                                                           const __grid_constant__ PbParams q) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int s_exit;
+  __shared__ volatile int s_ok[2];
+  __shared__ long long s_ph[16];
+
+  constexpr int kXTileBytes = NPAD * 128;
+  constexpr int kStageBytes = tc::kATileBytes + kXTileBytes;
+  constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.x;
+  const int S = p.S, B = p.B, fr = p.free_running;
+  const bool has_g1 = c < S * 64;
+  const int s1 = c / 64, mt1 = (c % 64) / 2, sig1 = c % 2, mt2 = c / 4, sig2 = c % 4;
+  const int n_tiles = (has_g1 ? kTiles1 : 0) + tiles2_of(S);
+  const int NS = q.stages;
+  const int n_steps = fr ? p.max_steps : p.T;
+  const int per_stream = kCtas / S;            // CTAs publishing h1 / prenet rows of one stream
+  const size_t x1_stream = (size_t)28 * kXTileBytes, x1_par = (size_t)S * x1_stream;
+  const size_t x2_par = (size_t)(S == 2 ? 64 : 40) * kXTileBytes;
+  unsigned* const F = q.flags;
+  auto flag = [&](int id) { return F + (size_t)id * kFlagStride; };
+
+  int max_ts = 0;
+  for (int s = 0; s < S; ++s) max_ts = max(max_ts, p.st[s].Ts);
+  const Smem sp = smem_plan(NPAD, NS, q.n_res, max_ts, fr);
+  unsigned char* ring = smem + sp.ring;
+  unsigned char* res_s = smem + sp.res;
+  float* c1_s = (float*)(smem + sp.c1);
+  float* c2_s = (float*)(smem + sp.c2);
+  float* hs_s = (float*)(smem + sp.hs);
+  float* wq_s = (float*)(smem + sp.wq);
+  float* wph_s = (float*)(smem + sp.wph);
+  float* wpc_s = (float*)(smem + sp.wpc);
+  float* w0_s = (float*)(smem + sp.w0);
+  float* w1_s = (float*)(smem + sp.w1);
+  float* bias_s = (float*)(smem + sp.bias);     // [0,128): attention LSTM [g*32+u], [128,256): decoder LSTM
+  float* att_s = (float*)(smem + sp.att);
+  float* red_s = (float*)(smem + sp.red);
+
+  // ---- one-off setup ---------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_exit = 0; s_ok[0] = 1; s_ok[1] = 1;
+  }
+  if (tid < 16) s_ph[tid] = 0;
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_base_s)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < kCT) {
+    for (int i = tid; i < 32 * (NPAD / 2); i += kCT) c1_s[i] = 0.f;
+    for (int i = tid; i < 32 * (NPAD / 4); i += kCT) c2_s[i] = 0.f;
+    for (int i = tid; i < 256; i += kCT) {
+      const int which = i >> 7, r = i & 127, g = r >> 5, u = r & 31;
+      float v = 0.f;
+      if (which == 0) { if (has_g1) v = p.st[s1].b_ih[g * H + mt1 * 32 + u] + p.st[s1].b_hh[g * H + mt1 * 32 + u]; }
+      else v = p.d_b_ih[g * H + mt2 * 32 + u] + p.d_b_hh[g * H + mt2 * 32 + u];
+      bias_s[i] = v;
+    }
+    if (has_g1)
+      for (int i = tid; i < A * 32; i += kCT) { const int a = i >> 5, u = i & 31; wq_s[a * 33 + u] = p.st[s1].wq[(size_t)a * H + mt1 * 32 + u]; }
+    if (fr) {
+      const int KD = H + S * E;
+      for (int i = tid; i < (M + 1) * 32; i += kCT) {
+        const int r = i >> 5, u = i & 31;
+        wph_s[r * 33 + u] = r < M ? p.proj_w[(size_t)r * KD + mt2 * 32 + u] : p.gate_w[mt2 * 32 + u];
+      }
+      const int x = c & 15;
+      if (x < S * 8)
+        for (int i = tid; i < (M + 1) * 64; i += kCT) {
+          const int r = i >> 6, k = i & 63;
+          wpc_s[r * 65 + k] = r < M ? p.proj_w[(size_t)r * KD + H + x * 64 + k] : p.gate_w[H + x * 64 + k];
+        }
+      const int rp = 2 * S, sP = c / per_stream, o0 = (c % per_stream) * rp;
+      for (int i = tid; i < rp * M; i += kCT) w0_s[i] = p.st[sP].pre_w0[(size_t)(o0 + i / M) * M + i % M];
+      for (int i = tid; i < rp * P; i += kCT) w1_s[i] = p.st[sP].pre_w1[(size_t)(o0 + i / P) * P + i % P];
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t acc_addr[2] = {tmem_base, tmem_base + (uint32_t)NPAD};
+  Ctl ctl{p.abort_flag, &s_exit};
+  const unsigned char* my_wt = q.wt + (size_t)c * kMaxTiles * tc::kATileBytes;
+
+  // free-running: every role takes the same decision at the top of frame t: the utterances were all finished by the end
+  // of frame t-2 (that fact is published before the prenet rows every role has -- transitively -- waited for)
+  auto frame_runs = [&](int t) -> bool {
+    if (!fr || t < 2) return true;
+    const unsigned d = ld_relaxed_u32(flag(F_DONE));
+    return !(d != 0u && (int)d <= t - 1);
+  };
+
+  if (warp == 16) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      // resident weight tiles: loaded once, behind the first ring phase of stage 0 .. (they are simply the first n_res
+      // tiles of every frame's program); one-off copy with plain loads would need all threads -- use TMA on full_bar of a
+      // private barrier instead
+      unsigned it = 0;
+      unsigned have[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // highest counter value already observed per dependency kind
+      bool ok = true;
+      for (int t = 0; t < n_steps && ok; ++t) {
+        if (!frame_runs(t)) break;
+        for (int i = 0; i < n_tiles && ok; ++i) {
+          const TileInfo ti = tile_info(i, has_g1, S, sig1, sig2);
+          const unsigned char* xsrc;
+          const unsigned* f = nullptr;
+          unsigned target = 0;
+          switch (ti.dep) {
+            case DEP_H1_PREV: f = flag(F_H1 + s1); target = (unsigned)per_stream * t; break;
+            case DEP_CTX_PREV: f = flag(F_CTX + s1); target = (unsigned)B * t; break;
+            case DEP_PRE: if (fr) { f = flag(F_PRE + s1); target = (unsigned)per_stream * t; } break;
+            case DEP_H2_PREV: f = flag(F_H2); target = (unsigned)kCtas * t; break;
+            case DEP_H1_0: f = flag(F_H1 + 0); target = (unsigned)per_stream * (t + 1); break;
+            case DEP_H1_1: f = flag(F_H1 + 1); target = (unsigned)per_stream * (t + 1); break;
+            case DEP_CTX_0: f = flag(F_CTX + 0); target = (unsigned)B * (t + 1); break;
+            default: f = flag(F_CTX + 1); target = (unsigned)B * (t + 1); break;
+          }
+          if (ti.gemm == 0) {
+            if (ti.dep == DEP_PRE && !fr) xsrc = q.xpre + (((size_t)t * S + s1) * 4 + ti.kb) * kXTileBytes;
+            else xsrc = q.x1 + (size_t)(t & 1) * x1_par + (size_t)s1 * x1_stream + (size_t)ti.kb * kXTileBytes;
+          } else {
+            xsrc = q.x2 + (size_t)(t & 1) * x2_par + (size_t)ti.kb * kXTileBytes;
+          }
+          const int stage = (int)(it % (unsigned)NS);
+          if (it >= (unsigned)NS) ok = mbar_wait_ab(&empty_bar[stage], ((it / (unsigned)NS) & 1u) ^ 1u, ctl);
+          if (!ok) break;
+          const bool resident = i < q.n_res && t > 0;      // frame 0 fills the resident copy as it streams by
+          unsigned char* a_dst = i < q.n_res ? res_s + (size_t)i * tc::kATileBytes : ring + (size_t)stage * kStageBytes;
+          unsigned char* x_dst = ring + (size_t)stage * kStageBytes + tc::kATileBytes;
+          tc::mbar_expect_tx(&full_bar[stage], (resident ? 0u : (unsigned)tc::kATileBytes) + (unsigned)kXTileBytes);
+          if (!resident) tc::tma_load_1d(a_dst, my_wt + (size_t)i * tc::kATileBytes, tc::kATileBytes, &full_bar[stage]);
+          if (f != nullptr && (int)(have[ti.dep] - target) < 0) {
+            ok = poll_ge(f, target, ctl);
+            have[ti.dep] = target;
+            fence_proxy_async();         // the tiles were written through the generic proxy by other SMs
+          }
+          if (!ok) break;
+          tc::tma_load_1d(x_dst, xsrc, kXTileBytes, &full_bar[stage]);
+          ++it;
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_f16(128, NPAD);
+      constexpr uint32_t lbo_a = (128 / 8) * 128, lbo_x = (NPAD / 8) * 128, sbo = 128;
+      unsigned it = 0;
+      bool ok = true;
+      for (int t = 0; t < n_steps && ok; ++t) {
+        if (!frame_runs(t)) break;
+        for (int i = 0; i < n_tiles && ok; ++i) {
+          const TileInfo ti = tile_info(i, has_g1, S, sig1, sig2);
+          if (ti.first && t > 0) {     // the epilogue of the previous frame must have drained this accumulator
+            ok = mbar_wait_ab(&acc_empty[ti.gemm], (uint32_t)((t - 1) & 1), ctl);
+            if (!ok) break;
+          }
+          const int stage = (int)(it % (unsigned)NS);
+          ok = mbar_wait_ab(&full_bar[stage], (it / (unsigned)NS) & 1u, ctl);
+          if (!ok) break;
+          tc::tc_fence_after();
+          const uint32_t a_addr = tc::smem_u32(i < q.n_res ? res_s + (size_t)i * tc::kATileBytes : ring + (size_t)stage * kStageBytes);
+          const uint32_t x_addr = tc::smem_u32(ring + (size_t)stage * kStageBytes + tc::kATileBytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t da = tc::make_smem_desc(a_addr + j * 2 * lbo_a, lbo_a, sbo);
+            const uint64_t dx = tc::make_smem_desc(x_addr + j * 2 * lbo_x, lbo_x, sbo);
+            tc::umma_f16(acc_addr[ti.gemm], da, dx, idesc, (ti.first && j == 0) ? 0u : 1u);
+          }
+          tc::umma_commit(&empty_bar[stage]);
+          if (ti.last) tc::umma_commit(&acc_full[ti.gemm]);
+          ++it;
+        }
+      }
+    }
+  } else {
+    // =========================== compute warps ===========================
+    long long ph_t = clock64();
+#define PB_PH(slot)                                       \
+    if (c == 0 && tid == 0) {                             \
+      const long long n_ = clock64();                     \
+      s_ph[slot] += n_ - ph_t;                            \
+      ph_t = n_;                                          \
+    }
+    int wn = 0;      // wait counter: alternates the broadcast slot
+    // thread 0 waits, everybody learns the outcome
+#define PB_WAIT_FLAG(fptr, target)                                            \
+    {                                                                         \
+      if (tid == 0) s_ok[wn & 1] = poll_ge((fptr), (target), ctl) ? 1 : 0;    \
+      bar_compute();                                                          \
+      const int ok_ = s_ok[wn & 1];                                           \
+      ++wn;                                                                   \
+      if (!ok_) goto pb_done;                                                 \
+    }
+#define PB_WAIT_MBAR(bar, parity)                                             \
+    {                                                                         \
+      if (tid == 0) s_ok[wn & 1] = mbar_wait_ab((bar), (parity), ctl) ? 1 : 0;\
+      bar_compute();                                                          \
+      const int ok_ = s_ok[wn & 1];                                           \
+      ++wn;                                                                   \
+      if (!ok_) goto pb_done;                                                 \
+    }
+    const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
+    const int row_ep = (warp & 3) * 32 + lane;
+
+    for (int t = 0; t < n_steps; ++t) {
+      if (!frame_runs(t)) break;
+      unsigned char* x1_next = q.x1 + (size_t)((t + 1) & 1) * x1_par;
+      unsigned char* x2_cur = q.x2 + (size_t)(t & 1) * x2_par;
+      unsigned char* x2_next = q.x2 + (size_t)((t + 1) & 1) * x2_par;
+
+      // ---------------- attention LSTM: epilogue -> partials -> cell update for NPAD/2 columns ----------------
+      if (has_g1) {
+        PB_WAIT_MBAR(&acc_full[0], (uint32_t)(t & 1))
+        PB_PH(0)
+        tc::tc_fence_after();
+        float* part_mine = q.part1 + (((size_t)(s1 * 32 + mt1) * 2 + sig1) * 128) * NPAD;
+        for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
+          uint32_t v[16];
+          const uint32_t taddr = acc_addr[0] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
+          lat::tmem_ld16(taddr, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
+                                  __uint_as_float(v[4 * k4 + 3]));
+        }
+        tc::tc_fence_before();
+        bar_compute();
+        unsigned* fp1 = flag(F_P1 + s1 * 32 + mt1);
+        if (tid == 0) { mbar_arrive(&acc_empty[0]); signal(fp1); }
+        PB_PH(1)
+        PB_WAIT_FLAG(fp1, 2u * (unsigned)(t + 1))
+        PB_PH(2)
+        constexpr int NC = NPAD / 2;
+        const int col0 = sig1 * NC;
+        const float* part_tile = q.part1 + ((size_t)(s1 * 32 + mt1) * 2 * 128) * NPAD;
+        const StreamParams& st1 = p.st[s1];
+        for (int e = tid; e < 32 * NC; e += kCT) {
+          const int bl = e % NC, u = e / NC, b = col0 + bl;
+          float hn = 0.f;
+          if (b < B) {
+            const int j = mt1 * 32 + u;
+            float pre[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              pre[g] = bias_s[g * 32 + u] + (__ldcg(part_tile + (size_t)(g * 32 + u) * NPAD + b) +
+                                             __ldcg(part_tile + (size_t)(128 + g * 32 + u) * NPAD + b));
+            const float gi = sigmoidf_(pre[0]), gf = sigmoidf_(pre[1]), gg = tanhf(pre[2]), go = sigmoidf_(pre[3]);
+            float cn = gf * c1_s[u * NC + bl] + gi * gg;
+            hn = go * tanhf(cn);
+            if (q.sv.gates1) {
+              float* sv = q.sv.gates1 + (((size_t)t * S + s1) * 5 * H + j) * B + b;
+              const size_t gs = (size_t)H * B;
+              sv[0] = gi; sv[gs] = gf; sv[2 * gs] = gg; sv[3 * gs] = go; sv[4 * gs] = cn;
+            }
+            if (p.training) {
+              const size_t idx = (size_t)b * H + j;
+              const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s1) * B * H : nullptr;
+              const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * s1 + 1) * B * H : nullptr;
+              hn *= keep_mult(kh, idx, p.seed, 4 + 2 * s1, t, (int)idx, p.thresh_att, sc_att);
+              cn *= keep_mult(kc, idx, p.seed, 5 + 2 * s1, t, (int)idx, p.thresh_att, sc_att);
+            }
+            c1_s[u * NC + bl] = cn;
+          }
+          hs_s[bl * 33 + u] = hn;
+        }
+        bar_compute();
+        // fp16 operand chunks (8 units = 16 bytes): next frame's attention-LSTM input, this frame's decoder-LSTM input
+        for (int e = tid; e < NC * 4; e += kCT) {
+          const int bl = e >> 2, k8 = e & 3, b = col0 + bl;
+          if (b >= B) continue;
+          const float* hv = hs_s + bl * 33 + k8 * 8;
+          const float v[8] = {hv[0], hv[1], hv[2], hv[3], hv[4], hv[5], hv[6], hv[7]};
+          const uint4 pk = pn::pack8(v);
+          const int j = mt1 * 32 + k8 * 8;
+          *reinterpret_cast<uint4*>(x_chunk_ptr(x1_next + (size_t)s1 * x1_stream, NPAD, b, P + E + j)) = pk;
+          *reinterpret_cast<uint4*>(x_chunk_ptr(x2_cur, NPAD, b, s1 * (H + E) + j)) = pk;
+          if (q.sv.h1) {
+            float* d = q.sv.h1 + (((size_t)(t + 1) * S + s1) * B + b) * H + j;
+            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+        // query partials over the CTA's 32 units: q_part[b][a] = sum_u Wq[a][u] h1[u][b]   (attention.py:56, 368)
+        {
+          const int a = tid & (A - 1), grp = tid >> 7;
+          const float* wrow = wq_s + a * 33;
+          float wr[32];
+#pragma unroll
+          for (int u = 0; u < 32; ++u) wr[u] = wrow[u];
+          float* qdst = q.qpart + ((size_t)(s1 * 32 + mt1) * NPAD) * A + a;
+          for (int bl = grp; bl < NC; bl += 4) {
+            const int b = col0 + bl;
+            if (b >= B) continue;
+            const float* hv = hs_s + bl * 33;
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) acc = fmaf(wr[u], hv[u], acc);
+            qdst[(size_t)b * A] = acc;
+          }
+        }
+        bar_compute();
+        if (tid == 0) signal(flag(F_H1 + s1));
+        PB_PH(3)
+      }
+
+      // ---------------- attention: one (utterance, stream) task per CTA and round (attention.py:330-398) ----------------
+      for (int tau = c; tau < S * B; tau += kCtas) {
+        const int s = tau / B, b = tau - s * B;
+        PB_WAIT_FLAG(flag(F_H1 + s), (unsigned)per_stream * (unsigned)(t + 1))
+        PB_PH(4)
+        const StreamParams& sa = p.st[s];
+        const int Ts = sa.Ts;
+        const int len = sa.len ? (int)sa.len[b] : Ts;
+        float* ctxr_s = att_s;                   // 4*E context partials
+        float* q_s = ctxr_s + 4 * E;             // A
+        float* v_s = q_s + A;                    // A
+        float* e_s = v_s + A;                    // Ts+4
+        float* ap_s = e_s + Ts + 4;              // Ts+4
+        float* an_s = ap_s + Ts + 4;             // Ts+4
+        const int jg = tid >> 7, d4 = tid & 127;
+        const float4* mem4 = reinterpret_cast<const float4*>(sa.mem + (size_t)b * Ts * E) + d4;
+        float4 pf[bt::kCtxPF];
+#pragma unroll
+        for (int i = 0; i < bt::kCtxPF; ++i) {
+          const int j = jg + 4 * i;
+          pf[i] = j < Ts ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float* pm_b = sa.pm + (size_t)b * Ts * A;
+        if (tid < A) {
+          const float* qs = q.qpart + ((size_t)(s * 32) * NPAD + b) * A + tid;
+          float qa[32];
+#pragma unroll
+          for (int m = 0; m < 32; ++m) qa[m] = __ldcg(qs + (size_t)m * NPAD * A);
+          float qv = 0.f;
+#pragma unroll
+          for (int m = 0; m < 32; ++m) qv += qa[m];
+          if (q.sv.q) q.sv.q[(((size_t)t * S + s) * B + b) * A + tid] = qv;
+          q_s[tid] = qv;
+          v_s[tid] = sa.v[tid];
+        }
+        for (int j = tid; j < Ts; j += kCT) ap_s[1 + j] = sa.a_prev[(size_t)b * Ts + j];
+        if (tid == 0) ap_s[0] = 0.f;
+        bar_compute();
+        {
+          const float q0 = q_s[lane], q1 = q_s[lane + 32], q2 = q_s[lane + 64], q3 = q_s[lane + 96];
+          const float v0 = v_s[lane], v1 = v_s[lane + 32], v2 = v_s[lane + 64], v3 = v_s[lane + 96];
+          for (int j0 = warp * 4; j0 < Ts; j0 += 16 * 4) {
+            float x[4][4];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              const float* row = pm_b + (size_t)min(j0 + pp, Ts - 1) * A;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) x[pp][cc] = __ldg(row + lane + 32 * cc);
+            }
+            float e[4];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp)
+              e[pp] = v0 * lat::fast_tanh(q0 + x[pp][0]) + v1 * lat::fast_tanh(q1 + x[pp][1]) +
+                      v2 * lat::fast_tanh(q2 + x[pp][2]) + v3 * lat::fast_tanh(q3 + x[pp][3]);
+            const float ev = lat::butterfly4(e[0], e[1], e[2], e[3], lane);
+            const int j = j0 + (lane >> 3);
+            if ((lane & 7) == 0 && j < Ts) e_s[j] = (j >= len) ? -INFINITY : ev;
+          }
+        }
+        bar_compute();
+        for (int j = tid; j < Ts; j += kCT) {
+          float e = e_s[j];
+          if (p.training) {
+            const size_t ni = ((size_t)t * B + b) * Ts + j;
+            const float nz = sa.noise ? sa.noise[ni] : philox_normal(p.seed, 10 + s, t, b * Ts + j);
+            e = e + nz * 2.0f;
+          }
+          const float pj = sigmoidf_(e);
+          e_s[j] = pj;
+          if (sa.p_save) sa.p_save[((size_t)t * B + b) * Ts + j] = pj;
+        }
+        bar_compute();
+        {
+          float* align_out = sa.align + ((size_t)b * p.Tcap + t) * Ts;
+          for (int j = tid; j < Ts; j += kCT) {
+            float a = ap_s[1 + j] * e_s[j];
+            if (j > 0) a += ap_s[j] * (1.0f - e_s[j - 1]);
+            if ((fr || p.independent) && j >= len) a = 0.0f;
+            an_s[j] = a;
+            sa.a_prev[(size_t)b * Ts + j] = a;
+            align_out[j] = a;
+          }
+        }
+        bar_compute();
+        {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < bt::kCtxPF; ++i) {
+            const int j = jg + 4 * i;
+            const float a = j < Ts ? an_s[j] : 0.f;
+            acc.x = fmaf(a, pf[i].x, acc.x); acc.y = fmaf(a, pf[i].y, acc.y); acc.z = fmaf(a, pf[i].z, acc.z); acc.w = fmaf(a, pf[i].w, acc.w);
+          }
+          for (int jb = jg + 4 * bt::kCtxPF; jb < Ts; jb += 4 * bt::kCtxPF) {
+#pragma unroll
+            for (int i = 0; i < bt::kCtxPF; ++i) {
+              const int j = jb + 4 * i;
+              pf[i] = j < Ts ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < bt::kCtxPF; ++i) {
+              const int j = jb + 4 * i;
+              const float a = j < Ts ? an_s[j] : 0.f;
+              acc.x = fmaf(a, pf[i].x, acc.x); acc.y = fmaf(a, pf[i].y, acc.y); acc.z = fmaf(a, pf[i].z, acc.z); acc.w = fmaf(a, pf[i].w, acc.w);
+            }
+          }
+          reinterpret_cast<float4*>(ctxr_s)[jg * (E / 4) + d4] = acc;
+        }
+        bar_compute();
+        if (tid < E / 8) {
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int d = tid * 8 + k;
+            v[k] = (ctxr_s[d] + ctxr_s[E + d]) + (ctxr_s[2 * E + d] + ctxr_s[3 * E + d]);
+          }
+          const int d0 = tid * 8;
+          float* cdst = p.ctx + ((size_t)s * B + b) * E + d0;
+          *reinterpret_cast<float4*>(cdst) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(cdst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          if (q.sv.ctx) {
+            float* d = q.sv.ctx + (((size_t)(t + 1) * S + s) * B + b) * E + d0;
+            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          const uint4 pk = pn::pack8(v);
+          *reinterpret_cast<uint4*>(x_chunk_ptr(x1_next + (size_t)s * x1_stream, NPAD, b, P + d0)) = pk;
+          *reinterpret_cast<uint4*>(x_chunk_ptr(x2_cur, NPAD, b, s * (H + E) + H + d0)) = pk;
+        }
+        bar_compute();
+        if (tid == 0) signal(flag(F_CTX + s));
+        PB_PH(5)
+      }
+
+      // ---------------- free-running: projection partial over a 64-feature context slice (model.py:382-388) ----------------
+      if (fr) {
+        const int x = c & 15;
+        if (x < S * 8) {
+          const int sx = x >> 3, dx0 = (x & 7) * 64, grp = c >> 4;
+          const int NB = (B + 7) / 8, b0 = grp * NB;
+          PB_WAIT_FLAG(flag(F_CTX + sx), (unsigned)B * (unsigned)(t + 1))
+          float* cs = red_s + 8 * kMelPad;        // [16][64]
+          for (int e = tid; e < NB * 64; e += kCT) {
+            const int bl = e >> 6, k = e & 63, b = b0 + bl;
+            cs[e] = b < B ? __ldcg(p.ctx + ((size_t)sx * B + b) * E + dx0 + k) : 0.f;
+          }
+          bar_compute();
+          for (int e = tid; e < NB * (M + 1); e += kCT) {
+            const int r = e % (M + 1), bl = e / (M + 1), b = b0 + bl;
+            if (b >= B) continue;
+            const float* w = wpc_s + r * 65;
+            const float* xv = cs + bl * 64;
+            float acc = 0.f;
+#pragma unroll 16
+            for (int k = 0; k < 64; ++k) acc = fmaf(w[k], xv[k], acc);
+            q.ctxp[((size_t)x * NPAD + b) * kMelPad + r] = acc;
+          }
+        }
+        PB_PH(6)
+      }
+
+      // ---------------- decoder LSTM: epilogue -> partials -> cell update for NPAD/4 columns ----------------
+      {
+        PB_WAIT_MBAR(&acc_full[1], (uint32_t)(t & 1))
+        PB_PH(7)
+        tc::tc_fence_after();
+        float* part_mine = q.part2 + (((size_t)mt2 * 4 + sig2) * 128) * NPAD;
+        for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
+          uint32_t v[16];
+          const uint32_t taddr = acc_addr[1] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
+          lat::tmem_ld16(taddr, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
+                                  __uint_as_float(v[4 * k4 + 3]));
+        }
+        tc::tc_fence_before();
+        bar_compute();
+        unsigned* fp2 = flag(F_P2 + mt2);
+        if (tid == 0) { mbar_arrive(&acc_empty[1]); signal(fp2); }
+        PB_PH(8)
+        PB_WAIT_FLAG(fp2, 4u * (unsigned)(t + 1))
+        PB_PH(9)
+        constexpr int NC = NPAD / 4;
+        const int col0 = sig2 * NC;
+        const float* part_tile = q.part2 + ((size_t)mt2 * 4 * 128) * NPAD;
+        for (int e = tid; e < 32 * NC; e += kCT) {
+          const int bl = e % NC, u = e / NC, b = col0 + bl;
+          float hn = 0.f;
+          if (b < B) {
+            const int j = mt2 * 32 + u;
+            float pre[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float* pr = part_tile + (size_t)(g * 32 + u) * NPAD + b;
+              pre[g] = bias_s[128 + g * 32 + u] + ((__ldcg(pr) + __ldcg(pr + (size_t)128 * NPAD)) +
+                                                   (__ldcg(pr + (size_t)256 * NPAD) + __ldcg(pr + (size_t)384 * NPAD)));
+            }
+            const float gi = sigmoidf_(pre[0]), gf = sigmoidf_(pre[1]), gg = tanhf(pre[2]), go = sigmoidf_(pre[3]);
+            float cn = gf * c2_s[u * NC + bl] + gi * gg;
+            hn = go * tanhf(cn);
+            if (q.sv.gates2) {
+              float* sv = q.sv.gates2 + ((size_t)t * 5 * H + j) * B + b;
+              const size_t gs = (size_t)H * B;
+              sv[0] = gi; sv[gs] = gf; sv[2 * gs] = gg; sv[3 * gs] = go; sv[4 * gs] = cn;
+            }
+            if (p.training) {
+              const size_t idx = (size_t)b * H + j;
+              const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * B * H : nullptr;
+              const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * B * H : nullptr;
+              hn *= keep_mult(kh, idx, p.seed, 8, t, (int)idx, p.thresh_dec, sc_dec);
+              cn *= keep_mult(kc, idx, p.seed, 9, t, (int)idx, p.thresh_dec, sc_dec);
+            }
+            c2_s[u * NC + bl] = cn;
+          }
+          hs_s[bl * 33 + u] = hn;
+        }
+        bar_compute();
+        for (int e = tid; e < NC * 4; e += kCT) {
+          const int bl = e >> 2, k8 = e & 3, b = col0 + bl;
+          if (b >= B) continue;
+          const float* hv = hs_s + bl * 33 + k8 * 8;
+          const float v[8] = {hv[0], hv[1], hv[2], hv[3], hv[4], hv[5], hv[6], hv[7]};
+          const int j = mt2 * 32 + k8 * 8;
+          *reinterpret_cast<uint4*>(x_chunk_ptr(x2_next, NPAD, b, S * (H + E) + j)) = pn::pack8(v);
+          if (q.sv.h2) {
+            float* d = q.sv.h2 + ((size_t)(t + 1) * B + b) * H + j;
+            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+        if (fr) {   // projection partial over the CTA's 32 h2 units (model.py:382-388)
+          for (int e = tid; e < NC * (M + 1); e += kCT) {
+            const int r = e % (M + 1), bl = e / (M + 1), b = col0 + bl;
+            if (b >= B) continue;
+            const float* w = wph_s + r * 33;
+            const float* hv = hs_s + bl * 33;
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) acc = fmaf(w[u], hv[u], acc);
+            q.melp[((size_t)mt2 * NPAD + b) * kMelPad + r] = acc;
+          }
+        }
+        bar_compute();
+        if (tid == 0) signal(flag(F_H2));
+        PB_PH(10)
+      }
+
+      if (fr) {
+        // ---------------- mel / gate of utterance b = c: sum of the projection partials, stop test (model.py:480-485) ----
+        if (c < B) {
+          const int b = c;
+          PB_WAIT_FLAG(flag(F_H2), (unsigned)kCtas * (unsigned)(t + 1))
+          PB_PH(11)
+          const int n_part = 32 + S * 8;
+          if (tid < (M + 1) * 6) {
+            const int r = tid % (M + 1), grp = tid / (M + 1);
+            float acc = 0.f;
+            for (int pi = grp; pi < n_part; pi += 6)
+              acc += pi < 32 ? __ldcg(q.melp + ((size_t)pi * NPAD + b) * kMelPad + r)
+                             : __ldcg(q.ctxp + ((size_t)(pi - 32) * NPAD + b) * kMelPad + r);
+            red_s[grp * kMelPad + r] = acc;
+          }
+          bar_compute();
+          if (tid <= M) {
+            float v = 0.f;
+#pragma unroll
+            for (int g6 = 0; g6 < 6; ++g6) v += red_s[g6 * kMelPad + tid];
+            if (tid < M) {
+              v += p.proj_b[tid];
+              p.mel[((size_t)b * p.Tcap + t) * M + tid] = v;
+              q.melx[(size_t)b * M + tid] = v;
+            } else {
+              const float g = v + p.gate_b[0];
+              p.gate[(size_t)b * p.Tcap + t] = g;
+              if (p.n_frames[b] == 0) {
+                bool fin = false;
+                if (sigmoidf_(g) > p.gate_thr) { p.n_frames[b] = t + 1; fin = true; }
+                else if (t + 1 == p.max_steps) { p.n_frames[b] = t + 1; p.reached_max[b] = 1; fin = true; }
+                if (fin && atomicAdd(p.done_count, 1) + 1 == B) atomicExch(flag(F_DONE), (unsigned)(t + 1));
+              }
+            }
+          }
+          bar_compute();
+          if (tid == 0) signal(flag(F_MEL));
+        }
+        PB_PH(12)
+        // ---------------- prenet of frame t+1, 2S rows of each layer per CTA (model.py:13-24, 470-471) ----------------
+        {
+          const int rp = 2 * S, sP = c / per_stream, o0 = (c % per_stream) * rp;
+          const StreamParams& sq = p.st[sP];
+          const int tt = t + 1;
+          PB_WAIT_FLAG(flag(F_MEL), (unsigned)B * (unsigned)(t + 1))
+          for (int b = warp; b < B; b += 16) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (lane < M / 4) {
+              const float4 xv = __ldcg(reinterpret_cast<const float4*>(q.melx + (size_t)b * M) + lane);
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+                if (r < rp) {
+                  const float4 wv = *reinterpret_cast<const float4*>(w0_s + r * M + lane * 4);
+                  acc[r] = wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+                }
+            }
+            const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
+            const int r = lane >> 3;
+            if ((lane & 7) == 0 && r < rp) {
+              const int o = o0 + r;
+              const float mult = keep_mult(sq.keep0, ((size_t)tt * B + b) * P + o, p.seed, sP * 2 + 0, tt, b * P + o, p.thresh_pre, 2.0f);
+              q.l0x[((size_t)sP * NPAD + b) * P + o] = fmaxf(v, 0.f) * mult;
+            }
+          }
+          bar_compute();
+          if (tid == 0) signal(flag(F_L0 + sP));
+          PB_PH(13)
+          PB_WAIT_FLAG(flag(F_L0 + sP), (unsigned)per_stream * (unsigned)(t + 1))
+          for (int b = warp; b < B; b += 16) {
+            const float4* xs = reinterpret_cast<const float4*>(q.l0x + ((size_t)sP * NPAD + b) * P) + lane * 2;
+            const float4 xa = __ldcg(xs), xb = __ldcg(xs + 1);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (r < rp) {
+                const float4 wa = *reinterpret_cast<const float4*>(w1_s + r * P + lane * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(w1_s + r * P + lane * 8 + 4);
+                acc[r] = (wa.x * xa.x + wa.y * xa.y + wa.z * xa.z + wa.w * xa.w) + (wb.x * xb.x + wb.y * xb.y + wb.z * xb.z + wb.w * xb.w);
+              }
+            const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
+            const int r = lane >> 3;
+            if ((lane & 7) == 0 && r < rp) {
+              const int o = o0 + r;
+              const float mult = keep_mult(sq.keep1, ((size_t)tt * B + b) * P + o, p.seed, sP * 2 + 1, tt, b * P + o, p.thresh_pre, 2.0f);
+              bt::x_store(x1_next + (size_t)sP * x1_stream, NPAD, b, o, fmaxf(v, 0.f) * mult);
+            }
+          }
+          bar_compute();
+          if (tid == 0) signal(flag(F_PRE + sP));
+          PB_PH(14)
+        }
+      }
+    }
+  pb_done:;
+#undef PB_WAIT_FLAG
+#undef PB_WAIT_MBAR
+#undef PB_PH
+    if (c == 0 && tid == 0 && p.phase_clocks)
+      for (int i = 0; i < 16; ++i) p.phase_clocks[i] = s_ph[i];
+  }
+
+  // ---- teardown: every thread of every role ends up here (normally, or through the abort word) ----
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace pb

@@ -8,8 +8,9 @@
 Stated bounds: fp32 kernels mel / gate <= 1e-4, alignments <= 1e-5; 16-bit modes mel / gate <= 1e-3, alignments <= 2e-4
 (north_star: mel <= 1e-3); stop frames / flags exact whenever the oracle's gate logits are at least 2e-3 away from the
 threshold ("safe" utterances), and the fraction of ALL utterances with a matching stop frame is reported (>= 90 %).  Gradients:
-max|got - want| <= GRAD_BOUND(T) * max|want| per tensor, GRAD_BOUND(T) = 1e-2 * max(1, sqrt(T / 50)) -- bf16 rounding of
-the gate gradients is re-drawn every frame, so the accumulated error of a sum over T frames grows like sqrt(T).
+max|got - want| <= GRAD_BOUND(T) * max|want| per tensor, GRAD_BOUND(T) = 1e-2 for T <= 200 (measured on a B200: 3.0e-3 at
+B=16/T=50, 3.5e-3 at B=16/T=200, 5.3e-3 at B=64/T=200 -- the error does NOT grow with the horizon: the bf16 rounding of the gate
+gradients is re-drawn every frame and averages out in the sums over frames), 1e-2 * sqrt(T / 200) beyond that.
 
 The oracle for the batched free-running case is a batched loop over ``DecoderOracle._decode(..., truncate=True)`` (the
 per-utterance definition costs 64 x 400 batch-1 frames); it is checked against the per-utterance definition on two
@@ -30,7 +31,7 @@ LOGIT_THR = math.log(0.001 / 0.999)        # sigmoid(g) > 0.001  <=>  g > LOGIT_
 
 
 def grad_bound(T: int) -> float:
-    return 1e-2 * max(1.0, math.sqrt(T / 50.0))
+    return 1e-2 * max(1.0, math.sqrt(T / 200.0))
 
 
 def _cmp(got, want, tol_mel, tol_align, tag):
