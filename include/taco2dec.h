@@ -287,6 +287,11 @@ int taco2dec_last_kernel_ms(taco2dec_handle* h, float* ms);
  * [15] = state init + first barrier.  Synchronises the stream. */
 int taco2dec_read_phase_clocks(taco2dec_handle* h, void* cuda_stream, long long* out16_host);
 
+/* Diagnostics of the persistent batched kernel (enabled by the environment variable TACO2DEC_PB_DEBUG=<frame>,
+ * TACO2DEC_PB_DEBUG_CTA=<cta>): 256 SM-clock stamps of that CTA during that frame -- [0,32) activation tile requested,
+ * [32,64) operands landed, [64,96) MMAs issued, [96,128) weight tile requested, [128,144) compute-warp phase marks. */
+int taco2dec_read_debug_stamps(taco2dec_handle* h, void* cuda_stream, long long* out256_host);
+
 /* Persistent-kernel launch geometry actually used (for DESIGN.md / bench bookkeeping). */
 int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* block, int* smem_bytes);
 

@@ -31,7 +31,7 @@ using bt::P;
 
 constexpr int kCtas = 128;                    // LSTM CTAs = 32 row tiles x 4 splits (decoder) = 2 x 32 x 2 (attention LSTMs)
 constexpr int kCT = 512;                      // compute threads (warps 0-15)
-constexpr int kThreads = kCT + 64;            // + producer warp + MMA warp
+constexpr int kThreads = kCT + 96;            // + producer warp + one MMA-issuing warp per gate product
 constexpr int kTiles1 = 14;                   // k-blocks per CTA and frame, attention-LSTM product (K1 = 1792, split 2)
 constexpr int kMaxTiles = 30;                 // + 16 of the decoder-LSTM product (K2 = 4096, split 4)
 constexpr int kMelPad = 96;                   // 80 mel rows + gate, padded
@@ -56,9 +56,12 @@ struct PbParams {
   float* l0x;                   // [S][NPAD][P]          prenet layer-0 activations
   unsigned* flags;              // [F_COUNT][kFlagStride]
   bt::Saved sv;
-  int stages;                   // ring depth
-  int n_res;                    // weight tiles resident in shared memory (first n_res of the CTA's program)
-};
+  int stages_a, stages_x;       // ring depths: streamed weight tiles / activation tiles
+  int n_res;                    // weight tiles resident in shared memory
+  int n_tm;                     // weight tiles resident in tensor memory (A operand read from TMEM)
+  long long* dbg;               // optional [256] SM-clock stamps of CTA dbg_cta during frame dbg_frame (diagnostics):
+  int dbg_frame, dbg_cta;       //   [0,32) activation tile requested, [32,64) operands landed (MMA thread), [64,96) MMAs issued,
+};                              //   [96,128) weight tile requested, [128,160) compute-warp phase marks
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -72,6 +75,36 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(tc::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// TMA bulk copy with an explicit L2 eviction policy: the 63 MB of weight tiles are re-read every frame and must stay in
+// L2 (evict_last); per-frame teacher-forced prenet tiles are read exactly once (evict_first)
+__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                 unsigned long long policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(tc::smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(tc::smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+// tcgen05.mma with the A operand in tensor memory (128 lanes = rows, 8 columns = 16 fp16 K elements per instruction)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// non-blocking probe (try_wait may suspend the thread for a hardware time-out when the phase is not complete: fatal inside
+// the producer's event loop, where a full ring on one cursor must not delay the other)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(tc::smem_u32(bar)), "r"(parity)
@@ -112,10 +145,12 @@ __device__ __noinline__ bool mbar_wait_ab(uint64_t* bar, uint32_t parity, const 
   }
   return true;
 }
+// LSTM gate activations with ex2-based forms (abs error ~1e-6, far below the fp16 operand rounding of this path)
+__device__ __forceinline__ float fsig(float x) { return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float ftanh(float x) { return lat::fast_tanh(x); }
 // one thread, after a compute-warp barrier: publish this CTA's stores of the phase
 __device__ __forceinline__ void signal(unsigned* f) {
-  __threadfence();
-  red_release_add(f, 1u);
+  red_release_add(f, 1u);      // release at gpu scope: cumulative over the stores the barrier before it ordered
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -152,6 +187,28 @@ __host__ __device__ inline TileInfo tile_info(int i, bool has_g1, int S, int sig
   else { ti.kb = 16 + 2 * sig2 + (j - 8); ti.dep = DEP_CTX_0; }
   return ti;
 }
+
+// Where a weight tile of the CTA's program lives: the later its activations arrive inside a frame, the more it pays to have
+// it on-chip (its product sits on the critical path).  rank 0 = most critical.
+__host__ __device__ inline int dep_rank(int dep) {
+  switch (dep) {
+    case DEP_PRE: return 0;
+    case DEP_CTX_PREV: return 1;
+    case DEP_CTX_0: case DEP_CTX_1: return 2;
+    case DEP_H1_0: case DEP_H1_1: return 3;
+    case DEP_H1_PREV: return 4;
+    default: return 5;
+  }
+}
+// per-tile record of the frame program, built once per CTA in shared memory (the producer / MMA threads are single
+// threads on the critical path: their per-tile work has to be a table lookup)
+struct TileRec {
+  int kb, gemm, first, last, loc;
+  int flag;        // counter the activation tile depends on (index into the flag block), -1 = none
+  int mul, add;    // it is ready when counter >= mul * (frame + add)
+  int xkind;       // 0: X1 of stream s1, 1: X2, 2: hoisted prenet tiles (teacher-forced)
+};
+constexpr int LOC_STREAM = -1, LOC_SMEM = 64;     // loc < 0: streamed; 0..63: tensor-memory slot; >= 64: shared-memory slot + 64
 
 // weights -> per-CTA fp16 tiles in consumption order; tile rows = [gate g][unit u] of the CTA's 32 hidden units
 struct PackSrc {
@@ -205,17 +262,18 @@ __device__ __forceinline__ unsigned char* x_chunk_ptr(unsigned char* xbase, int 
 
 // shared-memory plan (bytes); everything after the ring is fixed-size except the attention scratch
 struct Smem {
-  size_t ring, res, c1, c2, hs, wq, wph, wpc, w0, w1, bias, att, red, total;
+  size_t aring, xring, res, c1, c2, hs, wq, wph, wpc, w0, w1, bias, att, red, total;
 };
-__host__ __device__ inline Smem smem_plan(int NPAD, int stages, int n_res, int max_ts, int fr) {
+__host__ __device__ inline Smem smem_plan(int NPAD, int stages_a, int stages_x, int n_res, int max_ts, int fr) {
   Smem s;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~(size_t)127; return o; };
-  s.ring = take((size_t)stages * (tc::kATileBytes + (size_t)NPAD * 128));
+  s.aring = take((size_t)stages_a * tc::kATileBytes);
+  s.xring = take((size_t)stages_x * (size_t)NPAD * 128);
   s.res = take((size_t)n_res * tc::kATileBytes);
   s.c1 = take((size_t)32 * (NPAD / 2) * 4);
   s.c2 = take((size_t)32 * (NPAD / 4) * 4);
-  s.hs = take((size_t)(NPAD / 2) * 33 * 4);
+  s.hs = take((size_t)(NPAD / 2) * 36 * 4);
   s.wq = take((size_t)A * 33 * 4);
   s.wph = take(fr ? (size_t)(M + 1) * 33 * 4 : 0);
   s.wpc = take(fr ? (size_t)(M + 1) * 65 * 4 : 0);
@@ -232,24 +290,30 @@ template <int NPAD>
 __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const __grid_constant__ Params p,
                                                                            const __grid_constant__ PbParams q) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t full_a[8], empty_a[8], full_x[8], empty_x[8], acc_full[2], acc_empty[2], res_bar;
+  __shared__ int s_loc[32];
+  __shared__ TileRec s_tile[32];
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int s_exit;
+  // rounds filled so far per ring slot: lanes / issuers may be several rounds away from a slot, and an mbarrier parity test
+  // only distinguishes neighbouring phases -- nobody tests a slot's barrier before the round before its own has been filled
+  __shared__ volatile unsigned s_xfill[8], s_afill[8];
+  __shared__ volatile int s_go, s_stop_at;      // frames the compute warps have decided to run / first frame that does not run
   __shared__ volatile int s_ok[2];
   __shared__ long long s_ph[16];
 
   constexpr int kXTileBytes = NPAD * 128;
-  constexpr int kStageBytes = tc::kATileBytes + kXTileBytes;
-  constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
+  constexpr int kTmemCols = 512;               // accumulators in columns [0, 2 NPAD), resident weight tiles above
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.x;
   const int S = p.S, B = p.B, fr = p.free_running;
   const bool has_g1 = c < S * 64;
   const int s1 = c / 64, mt1 = (c % 64) / 2, sig1 = c % 2, mt2 = c / 4, sig2 = c % 4;
   const int n_tiles = (has_g1 ? kTiles1 : 0) + tiles2_of(S);
-  const int NS = q.stages;
+  const int NSA = q.stages_a, NSX = q.stages_x;
   const int n_steps = fr ? p.max_steps : p.T;
-  const int per_stream = kCtas / S;            // CTAs publishing h1 / prenet rows of one stream
+  const int per_stream = kCtas / S;            // CTAs computing prenet rows of one stream (free-running)
+  constexpr int n_h1 = 64;                     // CTAs publishing h1 of one stream (32 row tiles x 2 splits)
   const size_t x1_stream = (size_t)28 * kXTileBytes, x1_par = (size_t)S * x1_stream;
   const size_t x2_par = (size_t)(S == 2 ? 64 : 40) * kXTileBytes;
   unsigned* const F = q.flags;
@@ -257,8 +321,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
 
   int max_ts = 0;
   for (int s = 0; s < S; ++s) max_ts = max(max_ts, p.st[s].Ts);
-  const Smem sp = smem_plan(NPAD, NS, q.n_res, max_ts, fr);
-  unsigned char* ring = smem + sp.ring;
+  const Smem sp = smem_plan(NPAD, NSA, NSX, q.n_res, max_ts, fr);
+  unsigned char* aring = smem + sp.aring;
+  unsigned char* xring = smem + sp.xring;
   unsigned char* res_s = smem + sp.res;
   float* c1_s = (float*)(smem + sp.c1);
   float* c2_s = (float*)(smem + sp.c2);
@@ -274,10 +339,41 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
 
   // ---- one-off setup ---------------------------------------------------------------------------------------------
   if (tid == 0) {
-    for (int i = 0; i < 8; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 8; ++i) {
+      tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); tc::mbar_init(&full_x[i], 1); tc::mbar_init(&empty_x[i], 1);
+    }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 1); }
+    tc::mbar_init(&res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_exit = 0; s_ok[0] = 1; s_ok[1] = 1;
+    s_go = fr ? 2 : n_steps; s_stop_at = 0x7fffffff;
+    for (int i = 0; i < 8; ++i) { s_xfill[i] = 0; s_afill[i] = 0; }
+    // placement of the program's weight tiles: tensor memory first, then shared memory, in order of criticality
+    int n_tm = q.n_tm, n_sm = q.n_res, tm = 0, sm = 0;
+    for (int i = 0; i < 32; ++i) s_loc[i] = LOC_STREAM;
+    for (int rank = 0; rank < 6; ++rank)
+      for (int i = 0; i < n_tiles; ++i) {
+        if (dep_rank(tile_info(i, has_g1, S, sig1, sig2).dep) != rank) continue;
+        if (tm < n_tm) s_loc[i] = tm++;
+        else if (sm < n_sm) s_loc[i] = LOC_SMEM + sm++;
+      }
+    for (int i = 0; i < n_tiles; ++i) {
+      const TileInfo ti = tile_info(i, has_g1, S, sig1, sig2);
+      TileRec r;
+      r.kb = ti.kb; r.gemm = ti.gemm; r.first = ti.first; r.last = ti.last; r.loc = s_loc[i];
+      r.xkind = ti.gemm == 0 ? ((ti.dep == DEP_PRE && !fr) ? 2 : 0) : 1;
+      switch (ti.dep) {
+        case DEP_H1_PREV: r.flag = F_H1 + s1; r.mul = n_h1; r.add = 0; break;
+        case DEP_CTX_PREV: r.flag = F_CTX + s1; r.mul = B; r.add = 0; break;
+        case DEP_PRE: r.flag = fr ? F_PRE + s1 : -1; r.mul = per_stream; r.add = 0; break;
+        case DEP_H2_PREV: r.flag = F_H2; r.mul = kCtas; r.add = 0; break;
+        case DEP_H1_0: r.flag = F_H1 + 0; r.mul = n_h1; r.add = 1; break;
+        case DEP_H1_1: r.flag = F_H1 + 1; r.mul = n_h1; r.add = 1; break;
+        case DEP_CTX_0: r.flag = F_CTX + 0; r.mul = B; r.add = 1; break;
+        default: r.flag = F_CTX + 1; r.mul = B; r.add = 1; break;
+      }
+      s_tile[i] = r;
+    }
   }
   if (tid < 16) s_ph[tid] = 0;
   if (warp == 17) {
@@ -318,8 +414,34 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t acc_addr[2] = {tmem_base, tmem_base + (uint32_t)NPAD};
+  const uint32_t tm_w_col = (uint32_t)(2 * NPAD);      // first tensor-memory column of the resident weight tiles (32 per tile)
   Ctl ctl{p.abort_flag, &s_exit};
   const unsigned char* my_wt = q.wt + (size_t)c * kMaxTiles * tc::kATileBytes;
+
+  // ---- weight tiles resident in tensor memory: copied in once (tcgen05.st), read by tcgen05.mma as its A operand for the
+  //      whole utterance.  A [128 x 64] fp16 tile = 128 lanes x 32 columns (two K elements per 32-bit column); warp w fills
+  //      lane quarter w & 3 of the slots w >> 2, w >> 2 + 4, ...; a thread owns one row: its eight 16-byte K groups. ----
+  if (tid < kCT && q.n_tm > 0) {
+    const int quarter = warp & 3, r = quarter * 32 + lane;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int loc = s_loc[i];
+      if (loc < 0 || loc >= LOC_SMEM || (loc & 3) != (warp >> 2)) continue;
+      const unsigned char* src = my_wt + (size_t)i * tc::kATileBytes + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16;
+      uint32_t wv[32];
+#pragma unroll
+      for (int kg = 0; kg < 8; ++kg) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + (size_t)kg * 16 * 128);
+        wv[4 * kg] = u.x; wv[4 * kg + 1] = u.y; wv[4 * kg + 2] = u.z; wv[4 * kg + 3] = u.w;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tm_w_col + (uint32_t)(loc * 32);
+      lat::tmem_st16(taddr, wv);
+      lat::tmem_st16(taddr + 16, wv + 16);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
 
   // free-running: every role takes the same decision at the top of frame t: the utterances were all finished by the end
   // of frame t-2 (that fact is published before the prenet rows every role has -- transitively -- waited for)
@@ -329,87 +451,169 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
     return !(d != 0u && (int)d <= t - 1);
   };
 
+  // free-running: the compute warps decide at the top of every frame whether it runs (frame_runs) and publish the decision
+  // in shared memory; the producer lanes and the MMA threads never work on a frame that has not been released
+  auto wait_frame = [&](int t) -> bool {
+    if (t < s_go) return true;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    for (;;) {
+      if (t < s_go) return true;
+      if (s_stop_at <= t || s_exit) return false;
+      if ((++spins & 255u) == 0u) {
+        if (*((volatile int*)p.abort_flag) != 0) { s_exit = 1; return false; }
+        if ((spins & 4095u) == 0u && clock64() - t0 > kTimeoutClocks) { atomicExch(p.abort_flag, 1); s_exit = 1; return false; }
+      }
+    }
+  };
+
+  auto wait_fill = [&](volatile unsigned* f, unsigned want) -> bool {     // the ring slot has been handed to round want-1
+    if ((int)(*f - want) >= 0) return true;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while ((int)(*f - want) < 0) {
+      if ((++spins & 255u) == 0u) {
+        if (s_exit) return false;
+        if (*((volatile int*)p.abort_flag) != 0) { s_exit = 1; return false; }
+        if ((spins & 4095u) == 0u && clock64() - t0 > kTimeoutClocks) { atomicExch(p.abort_flag, 1); s_exit = 1; return false; }
+      }
+    }
+    return true;
+  };
+
   if (warp == 16) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      // resident weight tiles: loaded once, behind the first ring phase of stage 0 .. (they are simply the first n_res
-      // tiles of every frame's program); one-off copy with plain loads would need all threads -- use TMA on full_bar of a
-      // private barrier instead
-      unsigned it = 0;
-      unsigned have[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // highest counter value already observed per dependency kind
+    // =========================== TMA producer: one lane per tile of the frame program ===========================
+    // Lane i owns tile i of every frame: it requests the weight tile as soon as its ring slot is free (weights depend on
+    // nothing) and the activation tile as soon as the counter it depends on has reached the frame's target.  Lanes are
+    // independent, so a dependency that is not ready yet never delays the tiles behind it.
+    const unsigned long long pol_keep = lat::l2_policy_evict_last(), pol_once = lat::l2_policy_evict_first();
+    if (lane == 0) {      // shared-memory resident tiles: one-off bulk copies
+      unsigned bytes = 0;
+      for (int i = 0; i < n_tiles; ++i) if (s_loc[i] >= LOC_SMEM) bytes += (unsigned)tc::kATileBytes;
+      if (bytes) {
+        tc::mbar_expect_tx(&res_bar, bytes);
+        for (int i = 0; i < n_tiles; ++i)
+          if (s_loc[i] >= LOC_SMEM)
+            tma_load_1d_hint(res_s + (size_t)(s_loc[i] - LOC_SMEM) * tc::kATileBytes, my_wt + (size_t)i * tc::kATileBytes,
+                             tc::kATileBytes, &res_bar, pol_once);
+      } else {
+        mbar_arrive(&res_bar);
+      }
+    }
+    if (lane < n_tiles) {
+      const int i = lane;
+      const TileRec tr = s_tile[i];
+      const bool streamed = tr.loc == LOC_STREAM;
+      int arank = 0, n_streamed = 0;
+      for (int j = 0; j < n_tiles; ++j) { const int st_ = s_loc[j] == LOC_STREAM; n_streamed += st_; if (j < i) arank += st_; }
+      const unsigned* fptr = tr.flag >= 0 ? flag(tr.flag) : nullptr;
+      unsigned seen = 0;
       bool ok = true;
       for (int t = 0; t < n_steps && ok; ++t) {
-        if (!frame_runs(t)) break;
-        for (int i = 0; i < n_tiles && ok; ++i) {
-          const TileInfo ti = tile_info(i, has_g1, S, sig1, sig2);
-          const unsigned char* xsrc;
-          const unsigned* f = nullptr;
-          unsigned target = 0;
-          switch (ti.dep) {
-            case DEP_H1_PREV: f = flag(F_H1 + s1); target = (unsigned)per_stream * t; break;
-            case DEP_CTX_PREV: f = flag(F_CTX + s1); target = (unsigned)B * t; break;
-            case DEP_PRE: if (fr) { f = flag(F_PRE + s1); target = (unsigned)per_stream * t; } break;
-            case DEP_H2_PREV: f = flag(F_H2); target = (unsigned)kCtas * t; break;
-            case DEP_H1_0: f = flag(F_H1 + 0); target = (unsigned)per_stream * (t + 1); break;
-            case DEP_H1_1: f = flag(F_H1 + 1); target = (unsigned)per_stream * (t + 1); break;
-            case DEP_CTX_0: f = flag(F_CTX + 0); target = (unsigned)B * (t + 1); break;
-            default: f = flag(F_CTX + 1); target = (unsigned)B * (t + 1); break;
+        if (fr && !wait_frame(t)) break;
+        bool need_a = streamed, need_x = true;
+        const unsigned ga = (unsigned)t * (unsigned)n_streamed + (unsigned)arank, gx = (unsigned)t * (unsigned)n_tiles + (unsigned)i;
+        const unsigned target = fptr ? (unsigned)tr.mul * (unsigned)(t + tr.add) : 0u;
+        const unsigned char* xsrc = tr.xkind == 2 ? q.xpre + (((size_t)t * S + s1) * 4 + tr.kb) * kXTileBytes
+                                    : tr.xkind == 0 ? q.x1 + (size_t)(t & 1) * x1_par + (size_t)s1 * x1_stream + (size_t)tr.kb * kXTileBytes
+                                                    : q.x2 + (size_t)(t & 1) * x2_par + (size_t)tr.kb * kXTileBytes;
+        unsigned spins = 0;
+        long long t0 = 0;
+        for (;;) {
+          if (need_a) {
+            const int slot = (int)(ga % (unsigned)NSA);
+            const unsigned round = ga / (unsigned)NSA;
+            if (s_afill[slot] == round && (round == 0u || mbar_test(&empty_a[slot], (round & 1u) ^ 1u))) {
+              tc::mbar_expect_tx(&full_a[slot], (unsigned)tc::kATileBytes);
+              tma_load_1d_hint(aring + (size_t)slot * tc::kATileBytes, my_wt + (size_t)i * tc::kATileBytes, tc::kATileBytes,
+                               &full_a[slot], pol_keep);
+              s_afill[slot] = round + 1u;
+              if (q.dbg && c == q.dbg_cta && t == q.dbg_frame) q.dbg[96 + i] = clock64();
+              need_a = false;
+            }
           }
-          if (ti.gemm == 0) {
-            if (ti.dep == DEP_PRE && !fr) xsrc = q.xpre + (((size_t)t * S + s1) * 4 + ti.kb) * kXTileBytes;
-            else xsrc = q.x1 + (size_t)(t & 1) * x1_par + (size_t)s1 * x1_stream + (size_t)ti.kb * kXTileBytes;
-          } else {
-            xsrc = q.x2 + (size_t)(t & 1) * x2_par + (size_t)ti.kb * kXTileBytes;
+          if (need_x) {
+            bool ready = fptr == nullptr || (int)(seen - target) >= 0;
+            if (!ready) {
+              seen = ld_acquire_u32(fptr);
+              ready = (int)(seen - target) >= 0;
+              if (ready) fence_proxy_async();      // the tiles were written through the generic proxy by other SMs
+            }
+            if (ready) {
+              const int slot = (int)(gx % (unsigned)NSX);
+              const unsigned round = gx / (unsigned)NSX;
+              if (s_xfill[slot] == round && (round == 0u || mbar_test(&empty_x[slot], (round & 1u) ^ 1u))) {
+                tc::mbar_expect_tx(&full_x[slot], (unsigned)kXTileBytes);
+                if (tr.xkind == 2) tma_load_1d_hint(xring + (size_t)slot * kXTileBytes, xsrc, kXTileBytes, &full_x[slot], pol_once);
+                else tc::tma_load_1d(xring + (size_t)slot * kXTileBytes, xsrc, kXTileBytes, &full_x[slot]);
+                s_xfill[slot] = round + 1u;
+                if (q.dbg && c == q.dbg_cta && t == q.dbg_frame) q.dbg[i] = clock64();
+                need_x = false;
+              }
+            }
           }
-          const int stage = (int)(it % (unsigned)NS);
-          if (it >= (unsigned)NS) ok = mbar_wait_ab(&empty_bar[stage], ((it / (unsigned)NS) & 1u) ^ 1u, ctl);
-          if (!ok) break;
-          const bool resident = i < q.n_res && t > 0;      // frame 0 fills the resident copy as it streams by
-          unsigned char* a_dst = i < q.n_res ? res_s + (size_t)i * tc::kATileBytes : ring + (size_t)stage * kStageBytes;
-          unsigned char* x_dst = ring + (size_t)stage * kStageBytes + tc::kATileBytes;
-          tc::mbar_expect_tx(&full_bar[stage], (resident ? 0u : (unsigned)tc::kATileBytes) + (unsigned)kXTileBytes);
-          if (!resident) tc::tma_load_1d(a_dst, my_wt + (size_t)i * tc::kATileBytes, tc::kATileBytes, &full_bar[stage]);
-          if (f != nullptr && (int)(have[ti.dep] - target) < 0) {
-            ok = poll_ge(f, target, ctl);
-            have[ti.dep] = target;
-            fence_proxy_async();         // the tiles were written through the generic proxy by other SMs
+          if (!need_a && !need_x) break;
+          if ((++spins & 63u) == 0u) {
+            if (s_exit) { ok = false; break; }
+            if (*((volatile int*)p.abort_flag) != 0) { s_exit = 1; ok = false; break; }
+            if (spins == 4096u) t0 = clock64();
+            else if ((spins & 4095u) == 0u && clock64() - t0 > kTimeoutClocks) { atomicExch(p.abort_flag, 1); s_exit = 1; ok = false; break; }
           }
-          if (!ok) break;
-          tc::tma_load_1d(x_dst, xsrc, kXTileBytes, &full_bar[stage]);
-          ++it;
         }
       }
     }
-  } else if (warp == 17) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+  } else if (warp == 17 || warp == 18) {
+    // =========================== MMA issuers: warp 17 = attention-LSTM product, warp 18 = decoder-LSTM product ==========
+    const int my_gemm = warp - 17;
+    if (lane == 0 && (my_gemm == 1 || has_g1)) {
       const uint32_t idesc = tc::make_idesc_f16(128, NPAD);
       constexpr uint32_t lbo_a = (128 / 8) * 128, lbo_x = (NPAD / 8) * 128, sbo = 128;
-      unsigned it = 0;
-      bool ok = true;
+      int n_streamed = 0;
+      for (int j = 0; j < n_tiles; ++j) n_streamed += s_loc[j] == LOC_STREAM;
+      const int i_lo = my_gemm == 0 ? 0 : (has_g1 ? kTiles1 : 0), i_hi = my_gemm == 0 ? kTiles1 : n_tiles;
+      int arank0 = 0;
+      for (int j = 0; j < i_lo; ++j) arank0 += s_loc[j] == LOC_STREAM;
+      bool ok = mbar_wait_ab(&res_bar, 0u, ctl);
       for (int t = 0; t < n_steps && ok; ++t) {
-        if (!frame_runs(t)) break;
-        for (int i = 0; i < n_tiles && ok; ++i) {
-          const TileInfo ti = tile_info(i, has_g1, S, sig1, sig2);
-          if (ti.first && t > 0) {     // the epilogue of the previous frame must have drained this accumulator
-            ok = mbar_wait_ab(&acc_empty[ti.gemm], (uint32_t)((t - 1) & 1), ctl);
-            if (!ok) break;
-          }
-          const int stage = (int)(it % (unsigned)NS);
-          ok = mbar_wait_ab(&full_bar[stage], (it / (unsigned)NS) & 1u, ctl);
+        if (fr && !wait_frame(t)) break;
+        if (t > 0) {     // the epilogue of the previous frame must have drained this accumulator
+          ok = mbar_wait_ab(&acc_empty[my_gemm], (uint32_t)((t - 1) & 1), ctl);
           if (!ok) break;
+        }
+        unsigned ga = (unsigned)t * (unsigned)n_streamed + (unsigned)arank0;
+        for (int i = i_lo; i < i_hi && ok; ++i) {
+          const int loc = s_loc[i];
+          const unsigned gx = (unsigned)t * (unsigned)n_tiles + (unsigned)i;
+          const int sx = (int)(gx % (unsigned)NSX), sa = (int)(ga % (unsigned)NSA);
+          ok = wait_fill(&s_xfill[sx], gx / (unsigned)NSX + 1u) && mbar_wait_ab(&full_x[sx], (gx / (unsigned)NSX) & 1u, ctl);
+          if (ok && loc == LOC_STREAM)
+            ok = wait_fill(&s_afill[sa], ga / (unsigned)NSA + 1u) && mbar_wait_ab(&full_a[sa], (ga / (unsigned)NSA) & 1u, ctl);
+          if (!ok) break;
+          if (q.dbg && c == q.dbg_cta && t == q.dbg_frame) q.dbg[32 + i] = clock64();
           tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(i < q.n_res ? res_s + (size_t)i * tc::kATileBytes : ring + (size_t)stage * kStageBytes);
-          const uint32_t x_addr = tc::smem_u32(ring + (size_t)stage * kStageBytes + tc::kATileBytes);
+          const uint32_t x_addr = tc::smem_u32(xring + (size_t)sx * kXTileBytes);
+          const uint32_t acc = acc_addr[my_gemm];
+          if (loc >= 0 && loc < LOC_SMEM) {
+            const uint32_t a_tm = tmem_base + tm_w_col + (uint32_t)(loc * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t da = tc::make_smem_desc(a_addr + j * 2 * lbo_a, lbo_a, sbo);
-            const uint64_t dx = tc::make_smem_desc(x_addr + j * 2 * lbo_x, lbo_x, sbo);
-            tc::umma_f16(acc_addr[ti.gemm], da, dx, idesc, (ti.first && j == 0) ? 0u : 1u);
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t dx = tc::make_smem_desc(x_addr + j * 2 * lbo_x, lbo_x, sbo);
+              umma_f16_ts(acc, a_tm + (uint32_t)(j * 8), dx, idesc, (i == i_lo && j == 0) ? 0u : 1u);
+            }
+          } else {
+            const uint32_t a_addr = tc::smem_u32(loc == LOC_STREAM ? aring + (size_t)sa * tc::kATileBytes
+                                                                   : res_s + (size_t)(loc - LOC_SMEM) * tc::kATileBytes);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t da = tc::make_smem_desc(a_addr + j * 2 * lbo_a, lbo_a, sbo);
+              const uint64_t dx = tc::make_smem_desc(x_addr + j * 2 * lbo_x, lbo_x, sbo);
+              tc::umma_f16(acc, da, dx, idesc, (i == i_lo && j == 0) ? 0u : 1u);
+            }
           }
-          tc::umma_commit(&empty_bar[stage]);
-          if (ti.last) tc::umma_commit(&acc_full[ti.gemm]);
-          ++it;
+          tc::umma_commit(&empty_x[sx]);
+          if (loc == LOC_STREAM) { tc::umma_commit(&empty_a[sa]); ++ga; }
+          if (i == i_hi - 1) tc::umma_commit(&acc_full[my_gemm]);
+          if (q.dbg && c == q.dbg_cta && t == q.dbg_frame) q.dbg[64 + i] = clock64();
         }
       }
     }
@@ -421,7 +625,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       const long long n_ = clock64();                     \
       s_ph[slot] += n_ - ph_t;                            \
       ph_t = n_;                                          \
-    }
+    }                                                     \
+    if (q.dbg && c == q.dbg_cta && tid == 0 && t == q.dbg_frame) q.dbg[128 + slot] = clock64();
     int wn = 0;      // wait counter: alternates the broadcast slot
     // thread 0 waits, everybody learns the outcome
 #define PB_WAIT_FLAG(fptr, target)                                            \
@@ -445,6 +650,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
 
     for (int t = 0; t < n_steps; ++t) {
       if (!frame_runs(t)) break;
+      // the fate of frame t+1 is already final here (every stop decision of frame t-1 was published before the prenet
+      // rows this CTA waited for at the end of frame t-1): release it to the producer lanes / MMA threads one frame ahead,
+      // so that their early tiles (h[t], context[t]) overlap the tail of this frame
+      if (fr && tid == 0) { if (frame_runs(t + 1)) s_go = t + 2; else s_stop_at = t + 1; }
       unsigned char* x1_next = q.x1 + (size_t)((t + 1) & 1) * x1_par;
       unsigned char* x2_cur = q.x2 + (size_t)(t & 1) * x2_par;
       unsigned char* x2_next = q.x2 + (size_t)((t + 1) & 1) * x2_par;
@@ -476,20 +685,35 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
         constexpr int NC = NPAD / 2;
         const int col0 = sig1 * NC;
         const float* part_tile = q.part1 + ((size_t)(s1 * 32 + mt1) * 2 * 128) * NPAD;
-        const StreamParams& st1 = p.st[s1];
-        for (int e = tid; e < 32 * NC; e += kCT) {
+#define PB_DBG_C(k) if (q.dbg && c == q.dbg_cta && tid == 0 && t == q.dbg_frame) q.dbg[176 + (k)] = clock64();
+        PB_DBG_C(0)
+        constexpr int CPT1 = (32 * NC + kCT - 1) / kCT;      // cells per thread: all partial loads are issued before any is used
+        float pr1[CPT1][4];
+#pragma unroll
+        for (int ci = 0; ci < CPT1; ++ci) {
+          const int e = tid + ci * kCT, bl = e % NC, u = (e / NC) & 31, b = col0 + bl;
+          const bool live = e < 32 * NC && b < B;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float* pa = part_tile + (size_t)(g * 32 + u) * NPAD + (live ? b : 0);
+            pr1[ci][g] = __ldcg(pa) + __ldcg(pa + (size_t)128 * NPAD);
+          }
+        }
+        if (q.dbg && c == q.dbg_cta && tid == 0 && t == q.dbg_frame) { volatile float sink = pr1[0][0] + pr1[CPT1 - 1][3]; (void)sink; q.dbg[177] = clock64(); }
+#pragma unroll
+        for (int ci = 0; ci < CPT1; ++ci) {
+          const int e = tid + ci * kCT;
+          if (e >= 32 * NC) break;
           const int bl = e % NC, u = e / NC, b = col0 + bl;
           float hn = 0.f;
           if (b < B) {
             const int j = mt1 * 32 + u;
             float pre[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              pre[g] = bias_s[g * 32 + u] + (__ldcg(part_tile + (size_t)(g * 32 + u) * NPAD + b) +
-                                             __ldcg(part_tile + (size_t)(128 + g * 32 + u) * NPAD + b));
-            const float gi = sigmoidf_(pre[0]), gf = sigmoidf_(pre[1]), gg = tanhf(pre[2]), go = sigmoidf_(pre[3]);
+            for (int g = 0; g < 4; ++g) pre[g] = bias_s[g * 32 + u] + pr1[ci][g];
+            const float gi = fsig(pre[0]), gf = fsig(pre[1]), gg = ftanh(pre[2]), go = fsig(pre[3]);
             float cn = gf * c1_s[u * NC + bl] + gi * gg;
-            hn = go * tanhf(cn);
+            hn = go * ftanh(cn);
             if (q.sv.gates1) {
               float* sv = q.sv.gates1 + (((size_t)t * S + s1) * 5 * H + j) * B + b;
               const size_t gs = (size_t)H * B;
@@ -504,14 +728,16 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             }
             c1_s[u * NC + bl] = cn;
           }
-          hs_s[bl * 33 + u] = hn;
+          hs_s[bl * 36 + u] = hn;
         }
+        PB_DBG_C(2)
         bar_compute();
+        PB_DBG_C(3)
         // fp16 operand chunks (8 units = 16 bytes): next frame's attention-LSTM input, this frame's decoder-LSTM input
         for (int e = tid; e < NC * 4; e += kCT) {
           const int bl = e >> 2, k8 = e & 3, b = col0 + bl;
           if (b >= B) continue;
-          const float* hv = hs_s + bl * 33 + k8 * 8;
+          const float* hv = hs_s + bl * 36 + k8 * 8;
           const float v[8] = {hv[0], hv[1], hv[2], hv[3], hv[4], hv[5], hv[6], hv[7]};
           const uint4 pk = pn::pack8(v);
           const int j = mt1 * 32 + k8 * 8;
@@ -523,6 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
+        PB_DBG_C(4)
         // query partials over the CTA's 32 units: q_part[b][a] = sum_u Wq[a][u] h1[u][b]   (attention.py:56, 368)
         {
           const int a = tid & (A - 1), grp = tid >> 7;
@@ -534,23 +761,28 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           for (int bl = grp; bl < NC; bl += 4) {
             const int b = col0 + bl;
             if (b >= B) continue;
-            const float* hv = hs_s + bl * 33;
-            float acc = 0.f;
+            const float4* hv4 = reinterpret_cast<const float4*>(hs_s + bl * 36);
+            float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-            for (int u = 0; u < 32; ++u) acc = fmaf(wr[u], hv[u], acc);
-            qdst[(size_t)b * A] = acc;
+            for (int u4 = 0; u4 < 8; ++u4) {
+              const float4 hq = hv4[u4];
+              acc0 = fmaf(wr[4 * u4], hq.x, acc0); acc1 = fmaf(wr[4 * u4 + 1], hq.y, acc1);
+              acc0 = fmaf(wr[4 * u4 + 2], hq.z, acc0); acc1 = fmaf(wr[4 * u4 + 3], hq.w, acc1);
+            }
+            qdst[(size_t)b * A] = acc0 + acc1;
           }
         }
+        PB_DBG_C(5)
         bar_compute();
+        PB_DBG_C(6)
         if (tid == 0) signal(flag(F_H1 + s1));
+        PB_DBG_C(7)
         PB_PH(3)
       }
 
       // ---------------- attention: one (utterance, stream) task per CTA and round (attention.py:330-398) ----------------
       for (int tau = c; tau < S * B; tau += kCtas) {
         const int s = tau / B, b = tau - s * B;
-        PB_WAIT_FLAG(flag(F_H1 + s), (unsigned)per_stream * (unsigned)(t + 1))
-        PB_PH(4)
         const StreamParams& sa = p.st[s];
         const int Ts = sa.Ts;
         const int len = sa.len ? (int)sa.len[b] : Ts;
@@ -560,6 +792,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
         float* e_s = v_s + A;                    // Ts+4
         float* ap_s = e_s + Ts + 4;              // Ts+4
         float* an_s = ap_s + Ts + 4;             // Ts+4
+        // requests that do not depend on the query go out BEFORE the wait for h1: the first 8 memory rows of every context
+        // thread and the processed-memory rows of the warp's first two energy rounds
         const int jg = tid >> 7, d4 = tid & 127;
         const float4* mem4 = reinterpret_cast<const float4*>(sa.mem + (size_t)b * Ts * E) + d4;
         float4 pf[bt::kCtxPF];
@@ -569,6 +803,20 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           pf[i] = j < Ts ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float* pm_b = sa.pm + (size_t)b * Ts * A;
+        float pmv[2][4][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const float* row = pm_b + (size_t)min(warp * 4 + r * 64 + pp, Ts - 1) * A;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) pmv[r][pp][cc] = __ldg(row + lane + 32 * cc);
+          }
+        for (int j = tid; j < Ts; j += kCT) ap_s[1 + j] = sa.a_prev[(size_t)b * Ts + j];
+        if (tid == 0) ap_s[0] = 0.f;
+        if (tid < A) v_s[tid] = sa.v[tid];
+        PB_WAIT_FLAG(flag(F_H1 + s), (unsigned)n_h1 * (unsigned)(t + 1))
+        PB_PH(4)
         if (tid < A) {
           const float* qs = q.qpart + ((size_t)(s * 32) * NPAD + b) * A + tid;
           float qa[32];
@@ -579,22 +827,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           for (int m = 0; m < 32; ++m) qv += qa[m];
           if (q.sv.q) q.sv.q[(((size_t)t * S + s) * B + b) * A + tid] = qv;
           q_s[tid] = qv;
-          v_s[tid] = sa.v[tid];
         }
-        for (int j = tid; j < Ts; j += kCT) ap_s[1 + j] = sa.a_prev[(size_t)b * Ts + j];
-        if (tid == 0) ap_s[0] = 0.f;
         bar_compute();
         {
           const float q0 = q_s[lane], q1 = q_s[lane + 32], q2 = q_s[lane + 64], q3 = q_s[lane + 96];
           const float v0 = v_s[lane], v1 = v_s[lane + 32], v2 = v_s[lane + 64], v3 = v_s[lane + 96];
-          for (int j0 = warp * 4; j0 < Ts; j0 += 16 * 4) {
-            float x[4][4];
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-              const float* row = pm_b + (size_t)min(j0 + pp, Ts - 1) * A;
-#pragma unroll
-              for (int cc = 0; cc < 4; ++cc) x[pp][cc] = __ldg(row + lane + 32 * cc);
-            }
+          auto round_of = [&](int j0, const float (&x)[4][4]) {
             float e[4];
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp)
@@ -603,6 +841,18 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             const float ev = lat::butterfly4(e[0], e[1], e[2], e[3], lane);
             const int j = j0 + (lane >> 3);
             if ((lane & 7) == 0 && j < Ts) e_s[j] = (j >= len) ? -INFINITY : ev;
+          };
+          if (warp * 4 < Ts) round_of(warp * 4, pmv[0]);
+          if (warp * 4 + 64 < Ts) round_of(warp * 4 + 64, pmv[1]);
+          for (int j0 = warp * 4 + 128; j0 < Ts; j0 += 64) {
+            float x[4][4];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              const float* row = pm_b + (size_t)min(j0 + pp, Ts - 1) * A;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) x[pp][cc] = __ldg(row + lane + 32 * cc);
+            }
+            round_of(j0, x);
           }
         }
         bar_compute();
@@ -692,15 +942,32 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             cs[e] = b < B ? __ldcg(p.ctx + ((size_t)sx * B + b) * E + dx0 + k) : 0.f;
           }
           bar_compute();
-          for (int e = tid; e < NB * (M + 1); e += kCT) {
-            const int r = e % (M + 1), bl = e / (M + 1), b = b0 + bl;
-            if (b >= B) continue;
-            const float* w = wpc_s + r * 65;
-            const float* xv = cs + bl * 64;
-            float acc = 0.f;
-#pragma unroll 16
-            for (int k = 0; k < 64; ++k) acc = fmaf(w[k], xv[k], acc);
-            q.ctxp[((size_t)x * NPAD + b) * kMelPad + r] = acc;
+          if (tid < (M + 1) * 6) {
+            const int r = tid % (M + 1), g6 = tid / (M + 1);
+            float acc[3] = {0.f, 0.f, 0.f};             // NB <= 16 utterances -> at most 3 per thread
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              float wr[32];
+#pragma unroll
+              for (int k = 0; k < 32; ++k) wr[k] = wpc_s[r * 65 + half * 32 + k];
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                const int bl = g6 + 6 * i;
+                if (bl >= NB) break;
+                const float4* xv4 = reinterpret_cast<const float4*>(cs + bl * 64 + half * 32);
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                  const float4 xq = xv4[k4];
+                  acc[i] = fmaf(wr[4 * k4], xq.x, acc[i]); acc[i] = fmaf(wr[4 * k4 + 1], xq.y, acc[i]);
+                  acc[i] = fmaf(wr[4 * k4 + 2], xq.z, acc[i]); acc[i] = fmaf(wr[4 * k4 + 3], xq.w, acc[i]);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int bl = g6 + 6 * i, b = b0 + bl;
+              if (bl < NB && b < B) q.ctxp[((size_t)x * NPAD + b) * kMelPad + r] = acc[i];
+            }
           }
         }
         PB_PH(6)
@@ -733,21 +1000,32 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
         constexpr int NC = NPAD / 4;
         const int col0 = sig2 * NC;
         const float* part_tile = q.part2 + ((size_t)mt2 * 4 * 128) * NPAD;
-        for (int e = tid; e < 32 * NC; e += kCT) {
+        constexpr int CPT2 = (32 * NC + kCT - 1) / kCT;
+        float pr2[CPT2][4];
+#pragma unroll
+        for (int ci = 0; ci < CPT2; ++ci) {
+          const int e = tid + ci * kCT, bl = e % NC, u = (e / NC) & 31, b = col0 + bl;
+          const bool live = e < 32 * NC && b < B;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float* pa = part_tile + (size_t)(g * 32 + u) * NPAD + (live ? b : 0);
+            pr2[ci][g] = (__ldcg(pa) + __ldcg(pa + (size_t)128 * NPAD)) + (__ldcg(pa + (size_t)256 * NPAD) + __ldcg(pa + (size_t)384 * NPAD));
+          }
+        }
+#pragma unroll
+        for (int ci = 0; ci < CPT2; ++ci) {
+          const int e = tid + ci * kCT;
+          if (e >= 32 * NC) break;
           const int bl = e % NC, u = e / NC, b = col0 + bl;
           float hn = 0.f;
           if (b < B) {
             const int j = mt2 * 32 + u;
             float pre[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float* pr = part_tile + (size_t)(g * 32 + u) * NPAD + b;
-              pre[g] = bias_s[128 + g * 32 + u] + ((__ldcg(pr) + __ldcg(pr + (size_t)128 * NPAD)) +
-                                                   (__ldcg(pr + (size_t)256 * NPAD) + __ldcg(pr + (size_t)384 * NPAD)));
-            }
-            const float gi = sigmoidf_(pre[0]), gf = sigmoidf_(pre[1]), gg = tanhf(pre[2]), go = sigmoidf_(pre[3]);
+            for (int g = 0; g < 4; ++g) pre[g] = bias_s[128 + g * 32 + u] + pr2[ci][g];
+            const float gi = fsig(pre[0]), gf = fsig(pre[1]), gg = ftanh(pre[2]), go = fsig(pre[3]);
             float cn = gf * c2_s[u * NC + bl] + gi * gg;
-            hn = go * tanhf(cn);
+            hn = go * ftanh(cn);
             if (q.sv.gates2) {
               float* sv = q.sv.gates2 + ((size_t)t * 5 * H + j) * B + b;
               const size_t gs = (size_t)H * B;
@@ -762,13 +1040,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             }
             c2_s[u * NC + bl] = cn;
           }
-          hs_s[bl * 33 + u] = hn;
+          hs_s[bl * 36 + u] = hn;
         }
         bar_compute();
         for (int e = tid; e < NC * 4; e += kCT) {
           const int bl = e >> 2, k8 = e & 3, b = col0 + bl;
           if (b >= B) continue;
-          const float* hv = hs_s + bl * 33 + k8 * 8;
+          const float* hv = hs_s + bl * 36 + k8 * 8;
           const float v[8] = {hv[0], hv[1], hv[2], hv[3], hv[4], hv[5], hv[6], hv[7]};
           const int j = mt2 * 32 + k8 * 8;
           *reinterpret_cast<uint4*>(x_chunk_ptr(x2_next, NPAD, b, S * (H + E) + j)) = pn::pack8(v);
@@ -779,15 +1057,24 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           }
         }
         if (fr) {   // projection partial over the CTA's 32 h2 units (model.py:382-388)
-          for (int e = tid; e < NC * (M + 1); e += kCT) {
-            const int r = e % (M + 1), bl = e / (M + 1), b = col0 + bl;
-            if (b >= B) continue;
-            const float* w = wph_s + r * 33;
-            const float* hv = hs_s + bl * 33;
-            float acc = 0.f;
+          if (tid < (M + 1) * 6) {
+            const int r = tid % (M + 1), g6 = tid / (M + 1);
+            float wr[32];
 #pragma unroll
-            for (int u = 0; u < 32; ++u) acc = fmaf(w[u], hv[u], acc);
-            q.melp[((size_t)mt2 * NPAD + b) * kMelPad + r] = acc;
+            for (int u = 0; u < 32; ++u) wr[u] = wph_s[r * 33 + u];
+            for (int bl = g6; bl < NC; bl += 6) {
+              const int b = col0 + bl;
+              if (b >= B) continue;
+              const float4* hv4 = reinterpret_cast<const float4*>(hs_s + bl * 36);
+              float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+              for (int u4 = 0; u4 < 8; ++u4) {
+                const float4 hq = hv4[u4];
+                acc0 = fmaf(wr[4 * u4], hq.x, acc0); acc1 = fmaf(wr[4 * u4 + 1], hq.y, acc1);
+                acc0 = fmaf(wr[4 * u4 + 2], hq.z, acc0); acc1 = fmaf(wr[4 * u4 + 3], hq.w, acc1);
+              }
+              q.melp[((size_t)mt2 * NPAD + b) * kMelPad + r] = acc0 + acc1;
+            }
           }
         }
         bar_compute();
@@ -796,18 +1083,37 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       }
 
       if (fr) {
+        // prenet dropout of frame t+1 (model.py:23: always on) does not depend on the data: one multiplier per lane now --
+        // lane = (layer, utterance i of the pass, row r) -- fetched with a shuffle where the rows are finished
+        const int rp = 2 * S, sP = c / per_stream, o0 = (c % per_stream) * rp, tt = t + 1;
+        const StreamParams& sq = p.st[sP];
+        float pmult[2];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const int lyr = lane >> 4, r = lane & 3, b = warp + 16 * ((lane >> 2) & 3) + 64 * pass, o = o0 + r;
+          pmult[pass] = (r < rp && b < B)
+                            ? keep_mult(lyr ? sq.keep1 : sq.keep0, ((size_t)tt * B + b) * P + o, p.seed, sP * 2 + lyr, tt, b * P + o, p.thresh_pre, 2.0f)
+                            : 0.f;
+        }
         // ---------------- mel / gate of utterance b = c: sum of the projection partials, stop test (model.py:480-485) ----
         if (c < B) {
           const int b = c;
           PB_WAIT_FLAG(flag(F_H2), (unsigned)kCtas * (unsigned)(t + 1))
           PB_PH(11)
           const int n_part = 32 + S * 8;
-          if (tid < (M + 1) * 6) {
+          if (tid < (M + 1) * 6) {     // 6 groups x 8 partials, all requested before the first is used
             const int r = tid % (M + 1), grp = tid / (M + 1);
+            float pv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int pi = grp + 6 * k;
+              pv[k] = pi >= n_part ? 0.f
+                      : pi < 32 ? __ldcg(q.melp + ((size_t)pi * NPAD + b) * kMelPad + r)
+                                : __ldcg(q.ctxp + ((size_t)(pi - 32) * NPAD + b) * kMelPad + r);
+            }
             float acc = 0.f;
-            for (int pi = grp; pi < n_part; pi += 6)
-              acc += pi < 32 ? __ldcg(q.melp + ((size_t)pi * NPAD + b) * kMelPad + r)
-                             : __ldcg(q.ctxp + ((size_t)(pi - 32) * NPAD + b) * kMelPad + r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc += pv[k];
             red_s[grp * kMelPad + r] = acc;
           }
           bar_compute();
@@ -836,50 +1142,65 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
         PB_PH(12)
         // ---------------- prenet of frame t+1, 2S rows of each layer per CTA (model.py:13-24, 470-471) ----------------
         {
-          const int rp = 2 * S, sP = c / per_stream, o0 = (c % per_stream) * rp;
-          const StreamParams& sq = p.st[sP];
-          const int tt = t + 1;
           PB_WAIT_FLAG(flag(F_MEL), (unsigned)B * (unsigned)(t + 1))
-          for (int b = warp; b < B; b += 16) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (lane < M / 4) {
-              const float4 xv = __ldcg(reinterpret_cast<const float4*>(q.melx + (size_t)b * M) + lane);
+          for (int pass = 0; pass * 64 < B; ++pass) {       // 4 utterances per warp and pass: their mel rows are requested together
+            const int bb = warp + 64 * pass;
+            float4 xv[4];
 #pragma unroll
-              for (int r = 0; r < 4; ++r)
-                if (r < rp) {
-                  const float4 wv = *reinterpret_cast<const float4*>(w0_s + r * M + lane * 4);
-                  acc[r] = wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
-                }
+            for (int i = 0; i < 4; ++i) {
+              const int b = bb + 16 * i;
+              xv[i] = (lane < M / 4 && b < B) ? __ldcg(reinterpret_cast<const float4*>(q.melx + (size_t)b * M) + lane)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
-            const int r = lane >> 3;
-            if ((lane & 7) == 0 && r < rp) {
-              const int o = o0 + r;
-              const float mult = keep_mult(sq.keep0, ((size_t)tt * B + b) * P + o, p.seed, sP * 2 + 0, tt, b * P + o, p.thresh_pre, 2.0f);
-              q.l0x[((size_t)sP * NPAD + b) * P + o] = fmaxf(v, 0.f) * mult;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int b = bb + 16 * i;
+              if (b >= B) break;
+              float acc[4] = {0.f, 0.f, 0.f, 0.f};
+              if (lane < M / 4) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                  if (r < rp) {
+                    const float4 wv = *reinterpret_cast<const float4*>(w0_s + r * M + lane * 4);
+                    acc[r] = wv.x * xv[i].x + wv.y * xv[i].y + wv.z * xv[i].z + wv.w * xv[i].w;
+                  }
+              }
+              const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
+              const float mult = __shfl_sync(0xffffffffu, pmult[pass], (i << 2) | (lane >> 3));
+              const int r = lane >> 3;
+              if ((lane & 7) == 0 && r < rp) q.l0x[((size_t)sP * NPAD + b) * P + o0 + r] = fmaxf(v, 0.f) * mult;
             }
           }
           bar_compute();
           if (tid == 0) signal(flag(F_L0 + sP));
           PB_PH(13)
           PB_WAIT_FLAG(flag(F_L0 + sP), (unsigned)per_stream * (unsigned)(t + 1))
-          for (int b = warp; b < B; b += 16) {
-            const float4* xs = reinterpret_cast<const float4*>(q.l0x + ((size_t)sP * NPAD + b) * P) + lane * 2;
-            const float4 xa = __ldcg(xs), xb = __ldcg(xs + 1);
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int pass = 0; pass * 64 < B; ++pass) {
+            const int bb = warp + 64 * pass;
+            float4 xa[4], xb[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-              if (r < rp) {
-                const float4 wa = *reinterpret_cast<const float4*>(w1_s + r * P + lane * 8);
-                const float4 wb = *reinterpret_cast<const float4*>(w1_s + r * P + lane * 8 + 4);
-                acc[r] = (wa.x * xa.x + wa.y * xa.y + wa.z * xa.z + wa.w * xa.w) + (wb.x * xb.x + wb.y * xb.y + wb.z * xb.z + wb.w * xb.w);
-              }
-            const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
-            const int r = lane >> 3;
-            if ((lane & 7) == 0 && r < rp) {
-              const int o = o0 + r;
-              const float mult = keep_mult(sq.keep1, ((size_t)tt * B + b) * P + o, p.seed, sP * 2 + 1, tt, b * P + o, p.thresh_pre, 2.0f);
-              bt::x_store(x1_next + (size_t)sP * x1_stream, NPAD, b, o, fmaxf(v, 0.f) * mult);
+            for (int i = 0; i < 4; ++i) {
+              const int b = bb + 16 * i;
+              const float4* xs = reinterpret_cast<const float4*>(q.l0x + ((size_t)sP * NPAD + (b < B ? b : 0)) * P) + lane * 2;
+              xa[i] = __ldcg(xs); xb[i] = __ldcg(xs + 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int b = bb + 16 * i;
+              if (b >= B) break;
+              float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+                if (r < rp) {
+                  const float4 wa = *reinterpret_cast<const float4*>(w1_s + r * P + lane * 8);
+                  const float4 wb = *reinterpret_cast<const float4*>(w1_s + r * P + lane * 8 + 4);
+                  acc[r] = (wa.x * xa[i].x + wa.y * xa[i].y + wa.z * xa[i].z + wa.w * xa[i].w) +
+                           (wb.x * xb[i].x + wb.y * xb[i].y + wb.z * xb[i].z + wb.w * xb[i].w);
+                }
+              const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
+              const float mult = __shfl_sync(0xffffffffu, pmult[pass], 16 | (i << 2) | (lane >> 3));
+              const int r = lane >> 3;
+              if ((lane & 7) == 0 && r < rp) bt::x_store(x1_next + (size_t)sP * x1_stream, NPAD, b, o0 + r, fmaxf(v, 0.f) * mult);
             }
           }
           bar_compute();

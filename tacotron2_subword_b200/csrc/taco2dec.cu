@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
 #include "batched.cuh"
 #include "backward.cuh"
 #include "postnet.cuh"
+#include "persist.cuh"
 
 // ------------------------------------------------------------------------------------------
 // One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
@@ -910,6 +911,10 @@ struct taco2dec_handle {
   bt::Bufs bt_bufs;      // batched tensor path: library-owned tiled operands / partials / state
   bool bt_alloc, bt_tiles_valid;
   bt::Saved cur_sv;      // where the current teacher-forced call keeps activations for backward (null = nowhere)
+  pb::PbParams pb;       // persistent batched kernel: library-owned weight tiles, operand buffers, partials, counters
+  bool pb_alloc, pb_tiles_valid;
+  unsigned char* pb_xpre; size_t pb_xpre_bytes;
+  long long* pb_dbg;
   bw::Bufs bw_bufs;      // backward pass: transposed bf16 weight tiles, gate-gradient tiles, GEMM partials
   bool bw_alloc, bw_tiles_valid;
   int* bw_ctl;           // device word: frame counter of the backward graph
@@ -1331,11 +1336,166 @@ int bt_run_frames(taco2dec_handle* h, const Params& p, size_t att_smem, cudaStre
   }
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
+  h->last_path = TACO2DEC_PATH_TENSOR_GRAPH;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent batched kernel (persist.cuh): eligibility, buffers, launch
+// ------------------------------------------------------------------------------------------
+struct PbGeometry { int npad, stages_a, stages_x, n_res, n_tm; size_t smem; };
+
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+bool pb_geometry(const taco2dec_handle* h, int B, int T_in, int T_sub, int fr, PbGeometry* out) {
+  const int npad = B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : 128;
+  const int max_ts = std::max(T_in, h->cfg.n_streams == 2 ? T_sub : 0);
+  const size_t budget = (size_t)h->max_smem_optin - 2048;          // static shared: barriers, phase stamps, placement table
+  const size_t fixed = pb::smem_plan(npad, 0, 0, 0, max_ts, fr).total;
+  const size_t xt = (size_t)npad * 128, at = tc::kATileBytes;
+  // tensor memory: 512 columns, 2 * npad of them accumulators, 32 per resident weight tile
+  int n_tm = std::min(env_int("TACO2DEC_PB_TMEM", 64), (512 - 2 * npad) / 32);
+  n_tm = std::max(0, std::min(n_tm, pb::kMaxTiles));
+  int stages_x = std::max(2, std::min(8, env_int("TACO2DEC_PB_STAGES_X", 6)));
+  int stages_a = std::max(2, std::min(8, env_int("TACO2DEC_PB_STAGES_A", 4)));
+  while (fixed + stages_x * xt + stages_a * at + 1024 > budget && stages_a > 2) --stages_a;
+  while (fixed + stages_x * xt + stages_a * at + 1024 > budget && stages_x > 2) --stages_x;
+  if (fixed + stages_x * xt + stages_a * at + 1024 > budget) return false;
+  int n_res = (int)((budget - fixed - stages_x * xt - stages_a * at - 1024) / at);
+  n_res = std::max(0, std::min(std::min(n_res, env_int("TACO2DEC_PB_RES", 64)), pb::kMaxTiles - n_tm));
+  out->npad = npad; out->stages_a = stages_a; out->stages_x = stages_x; out->n_res = n_res; out->n_tm = n_tm;
+  out->smem = pb::smem_plan(npad, stages_a, stages_x, n_res, max_ts, fr).total;
+  return out->smem <= budget;
+}
+
+bool pb_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub, int fr) {
+  if (!bt_shape_ok(h, B, T_in, T_sub)) return false;
+  if (h->cfg.attention != TACO2DEC_ATTN_SMA || h->num_sms < pb::kCtas) return false;
+  if (getenv("TACO2DEC_NO_PERSIST")) return false;
+  PbGeometry g;
+  return pb_geometry(h, B, T_in, T_sub, fr, &g);
+}
+
+int pb_prepare(taco2dec_handle* h, cudaStream_t st) {
+  const int S = h->cfg.n_streams;
+  pb::PbParams& b = h->pb;
+  if (!h->pb_alloc) {
+    const size_t NP = 128;
+    unsigned char* wt = nullptr;
+    CUDA_TRY(cudaMalloc(&wt, (size_t)pb::kCtas * pb::kMaxTiles * tc::kATileBytes));
+    b.wt = wt;
+    CUDA_TRY(cudaMalloc(&b.x1, (size_t)2 * 2 * 28 * NP * 128));
+    CUDA_TRY(cudaMalloc(&b.x2, (size_t)2 * 64 * NP * 128));
+    CUDA_TRY(cudaMalloc(&b.part1, (size_t)2 * 32 * 2 * 128 * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.part2, (size_t)32 * 4 * 128 * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.qpart, (size_t)2 * 32 * NP * pb::A * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.melp, (size_t)32 * NP * pb::kMelPad * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.ctxp, (size_t)pb::kSlices * NP * pb::kMelPad * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.melx, (size_t)NP * pb::M * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.l0x, (size_t)2 * NP * pb::P * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.flags, (size_t)pb::F_COUNT * pb::kFlagStride * sizeof(unsigned)));
+    h->pb_alloc = true;
+  }
+  if (!h->pb_tiles_valid) {
+    pb::PackSrc src;
+    for (int s = 0; s < 2; ++s) { src.w_ih[s] = h->w.stream[s].arnn_w_ih; src.w_hh[s] = h->w.stream[s].arnn_w_hh; }
+    src.d_w_ih = h->w.drnn_w_ih; src.d_w_hh = h->w.drnn_w_hh;
+    pb::pb_pack_weights<<<pb::kCtas, 512, 0, st>>>(src, S, const_cast<unsigned char*>(b.wt));
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    h->pb_tiles_valid = true;
+  }
+  return 0;
+}
+
+__global__ void pb_init_kernel(Params p) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
+  for (int i = gtid; i < p.S * p.B * p.E; i += n) p.ctx[i] = 0.f;
+  for (int s = 0; s < p.S; ++s) {
+    const int Ts = p.st[s].Ts;
+    for (int i = gtid; i < p.B * Ts; i += n) p.st[s].a_prev[i] = (i % Ts) == 0 ? 1.0f : 0.0f;    // attention.py:324-328
+  }
+  if (p.free_running) {
+    for (int i = gtid; i < p.B; i += n) { p.n_frames[i] = 0; p.reached_max[i] = 0; }
+    if (gtid == 0) *p.done_count = 0;
+  }
+}
+
+template <int NPAD>
+int pb_launch(taco2dec_handle* h, const Params& p, const PbGeometry& g, cudaStream_t st) {
+  const int S = p.S, B = p.B;
+  pb::PbParams q = h->pb;
+  q.sv = h->cur_sv;
+  q.stages_a = g.stages_a; q.stages_x = g.stages_x; q.n_res = g.n_res; q.n_tm = g.n_tm;
+  q.dbg = nullptr;
+  if (getenv("TACO2DEC_PB_DEBUG")) {     // diagnostics: clock stamps of one CTA during one frame (tools/pb_timeline.py)
+    if (!h->pb_dbg) CUDA_TRY(cudaMalloc(&h->pb_dbg, 256 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(h->pb_dbg, 0, 256 * sizeof(long long), st));
+    q.dbg = h->pb_dbg; q.dbg_frame = env_int("TACO2DEC_PB_DEBUG", 20); q.dbg_cta = env_int("TACO2DEC_PB_DEBUG_CTA", 0);
+  }
+  const size_t xt = (size_t)NPAD * 128;
+  CUDA_TRY(cudaMemsetAsync(q.flags, 0, (size_t)pb::F_COUNT * pb::kFlagStride * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(q.x1, 0, (size_t)2 * S * 28 * xt, st));
+  CUDA_TRY(cudaMemsetAsync(q.x2, 0, (size_t)2 * (S == 2 ? 64 : 40) * xt, st));
+  if (q.sv.h1) CUDA_TRY(cudaMemsetAsync(q.sv.h1, 0, (size_t)S * B * bt::H * sizeof(float), st));
+  if (q.sv.ctx) CUDA_TRY(cudaMemsetAsync(q.sv.ctx, 0, (size_t)S * B * bt::E * sizeof(float), st));
+  if (q.sv.h2) CUDA_TRY(cudaMemsetAsync(q.sv.h2, 0, (size_t)B * bt::H * sizeof(float), st));
+  pb_init_kernel<<<h->num_sms, 256, 0, st>>>(p);
+  h->launches++;
+  if (!p.free_running) {      // hoisted prenet rows -> per-frame fp16 operand tiles
+    const size_t need = (size_t)p.T * S * 4 * xt;
+    if (h->pb_xpre_bytes < need) {
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (h->pb_xpre) CUDA_TRY(cudaFree(h->pb_xpre));
+      h->pb_xpre = nullptr; h->pb_xpre_bytes = 0;
+      CUDA_TRY(cudaMalloc(&h->pb_xpre, need));
+      h->pb_xpre_bytes = need;
+    }
+    if (B < NPAD) CUDA_TRY(cudaMemsetAsync(h->pb_xpre, 0, need, st));
+    for (int s = 0; s < S; ++s) {
+      const size_t total = (size_t)p.T * B * (bt::P / 8);
+      pb::pb_prenet_tiles<<<(unsigned)std::min<size_t>((total + 255) / 256, 4096), 256, 0, st>>>(p.st[s].pre, p.T, B, NPAD, S, s, h->pb_xpre);
+      h->launches++;
+    }
+    q.xpre = h->pb_xpre;
+  }
+  auto kern = pb::decoder_batched_persistent<NPAD>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pb::kThreads, g.smem));
+  if (per_sm < 1) return fail(TACO2DEC_E_STATE, "persistent batched kernel does not fit on an SM");
+  void* args[] = {(void*)&p, (void*)&q};
+  if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(pb::kCtas), dim3(pb::kThreads), args, g.smem, st));
+  if (h->profiling) { CUDA_TRY(cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
+  h->launches++;
+  if (!p.free_running) {      // mel / gate of all frames in one pass over the stored h2 / context rows (model.py:382-388)
+    bt::Bufs bf;
+    memset(&bf, 0, sizeof(bf));
+    bf.sv = h->cur_sv;
+    bt::bt_proj_all<<<(p.T * B + bt::kPaRows - 1) / bt::kPaRows, 256, 0, st>>>(p, bf);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
   h->last_path = TACO2DEC_PATH_TENSOR;
   return 0;
 }
 
+int run_persistent_batched(taco2dec_handle* h, const Params& p, int T_in, int T_sub, cudaStream_t st) {
+  PbGeometry g;
+  if (!pb_geometry(h, p.B, T_in, T_sub, p.free_running, &g)) return fail(TACO2DEC_E_STATE, "persistent batched kernel: shared-memory plan does not fit");
+  if (int rc = pb_prepare(h, st)) return rc;
+  switch (g.npad) {
+    case 16: return pb_launch<16>(h, p, g, st);
+    case 32: return pb_launch<32>(h, p, g, st);
+    case 64: return pb_launch<64>(h, p, g, st);
+    default: return pb_launch<128>(h, p, g, st);
+  }
+}
+
 int run_batched(taco2dec_handle* h, const Params& p, int T_in, int T_sub, cudaStream_t st) {
+  if (h->path_mode != TACO2DEC_PATH_TENSOR_GRAPH && pb_shape_ok(h, p.B, T_in, T_sub, p.free_running))
+    return run_persistent_batched(h, p, T_in, T_sub, st);
   if (int rc = bt_prepare(h, st)) return rc;
   const size_t att = attention_smem_bytes(h->cfg, T_in, T_sub);
   if (p.B <= 16) return bt_run_frames<16>(h, p, att, st);
@@ -1648,6 +1808,7 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   h->ll_buf = nullptr; h->ll_bytes = 0; h->last_path = 0;
   memset(&h->bt_bufs, 0, sizeof(h->bt_bufs)); h->bt_alloc = false; h->bt_tiles_valid = false; h->cap_stream = nullptr;
   memset(&h->cur_sv, 0, sizeof(h->cur_sv));
+  memset(&h->pb, 0, sizeof(h->pb)); h->pb_alloc = false; h->pb_tiles_valid = false; h->pb_xpre = nullptr; h->pb_xpre_bytes = 0; h->pb_dbg = nullptr;
   memset(&h->bw_bufs, 0, sizeof(h->bw_bufs)); h->bw_alloc = false; h->bw_tiles_valid = false; h->bw_ctl = nullptr;
   h->profiling = false;
   h->ev_valid = false;
@@ -1676,6 +1837,11 @@ int taco2dec_destroy(taco2dec_handle* h) {
       void* ptrs[] = {b.a1, b.a2, b.aq, b.x1, b.x2, b.g1, b.g2, b.gq, b.c1, b.c2, b.h2f, b.w0t[0], b.w0t[1], b.w1t[0], b.w1t[1]};
       for (void* q : ptrs) if (q) cudaFree(q);
     }
+    if (h->pb_alloc) {
+      pb::PbParams& b = h->pb;
+      void* ptrs[] = {(void*)b.wt, b.x1, b.x2, b.part1, b.part2, b.qpart, b.melp, b.ctxp, b.melx, b.l0x, b.flags, h->pb_xpre};
+      for (void* q : ptrs) if (q) cudaFree(q);
+    }
     if (h->bw_alloc) {
       bw::Bufs& b = h->bw_bufs;
       void* ptrs[] = {b.a1t, b.a2t, b.dg1, b.dg2, b.dx1, b.dx2, h->bw_ctl};
@@ -1683,6 +1849,14 @@ int taco2dec_destroy(taco2dec_handle* h) {
     }
   }
   delete h;
+  return 0;
+}
+
+int taco2dec_read_debug_stamps(taco2dec_handle* h, void* cuda_stream, long long* out256_host) {
+  if (!h || !out256_host) return fail(TACO2DEC_E_ARG, "null argument");
+  if (!h->pb_dbg) return fail(TACO2DEC_E_STATE, "no debug stamps recorded (set TACO2DEC_PB_DEBUG=<frame>)");
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  CUDA_TRY(cudaMemcpy(out256_host, h->pb_dbg, 256 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1752,6 +1926,7 @@ int taco2dec_set_weights(taco2dec_handle* h, const taco2dec_weights* w, void* /*
   h->packed_wbytes = 0;  // latency-path weight streams are re-packed on next use
   h->bt_tiles_valid = false;
   h->bw_tiles_valid = false;
+  h->pb_tiles_valid = false;
   return 0;
 }
 

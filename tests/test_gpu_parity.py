@@ -307,7 +307,7 @@ def test_tensor_path_teacher_forced_vs_oracle(attention, B, training):
     with torch.no_grad():
         got = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(),
                   inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
-    assert dec._engine(torch.device("cuda", 0)).last_path() == "tensor"
+    assert dec._engine(torch.device("cuda", 0)).last_path() in ("tensor", "tensor_graph")
     _cmp_tol(got, want, 1e-3, 2e-4, f"tensor {attention} B={B}")
 
 
@@ -325,7 +325,7 @@ def test_tensor_path_batched_free_running_vs_oracle():
         mel, gate, al, alb, nf, reached = dec.inference_batched(inp["memory"].cuda(), inp["embeddings"].cuda(),
                                                                 inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda(),
                                                                 max_decoder_steps=steps)
-    assert dec._engine(torch.device("cuda", 0)).last_path() == "tensor"
+    assert dec._engine(torch.device("cuda", 0)).last_path() in ("tensor", "tensor_graph")
     for b, (omel, ogate, oal, oalb, oflag) in enumerate(outs):
         n = omel.shape[2]
         assert int(nf[b]) == n and bool(reached[b]) == (not oflag)
@@ -433,7 +433,7 @@ def test_tensor_path_single_stream_forward_and_backward():
     dec.dropout_replay = replay_of(plan)
     mem = inp["memory"].cuda().requires_grad_(True)
     outs = dec(mem, None, inp["mels"].cuda(), inp["memory_lengths"].cuda(), None)
-    assert dec._engine(torch.device("cuda", 0)).last_path() == "tensor"
+    assert dec._engine(torch.device("cuda", 0)).last_path() in ("tensor", "tensor_graph")
     _cmp_tol(tuple(o.detach() if o is not None else None for o in outs),
              tuple(o.detach() if o is not None else None for o in want_outs), 1e-3, 2e-4, "tensor single-stream")
     _loss(outs, 5).backward()
