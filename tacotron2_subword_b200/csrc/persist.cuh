@@ -268,8 +268,8 @@ __host__ __device__ inline Smem smem_plan(int NPAD, int stages_a, int stages_x, 
   Smem s;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~(size_t)127; return o; };
-  s.aring = take((size_t)stages_a * tc::kATileBytes);
-  s.xring = take((size_t)stages_x * (size_t)NPAD * 128);
+  s.aring = take((size_t)2 * stages_a * tc::kATileBytes);
+  s.xring = take((size_t)2 * stages_x * (size_t)NPAD * 128);
   s.res = take((size_t)n_res * tc::kATileBytes);
   s.c1 = take((size_t)32 * (NPAD / 2) * 4);
   s.c2 = take((size_t)32 * (NPAD / 4) * 4);
@@ -290,14 +290,16 @@ template <int NPAD>
 __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const __grid_constant__ Params p,
                                                                            const __grid_constant__ PbParams q) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full_a[8], empty_a[8], full_x[8], empty_x[8], acc_full[2], acc_empty[2], res_bar;
+  // one weight ring and one activation ring PER gate product: the early tiles of the next frame's attention-LSTM product
+  // must not queue behind the decoder-LSTM tiles that are still waiting for this frame's context
+  __shared__ __align__(8) uint64_t full_a[2][8], empty_a[2][8], full_x[2][8], empty_x[2][8], acc_full[2], acc_empty[2], res_bar;
   __shared__ int s_loc[32];
   __shared__ TileRec s_tile[32];
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int s_exit;
   // rounds filled so far per ring slot: lanes / issuers may be several rounds away from a slot, and an mbarrier parity test
   // only distinguishes neighbouring phases -- nobody tests a slot's barrier before the round before its own has been filled
-  __shared__ volatile unsigned s_xfill[8], s_afill[8];
+  __shared__ volatile unsigned s_xfill[2][8], s_afill[2][8];
   __shared__ volatile int s_go, s_stop_at;      // frames the compute warps have decided to run / first frame that does not run
   __shared__ volatile int s_ok[2];
   __shared__ long long s_ph[16];
@@ -339,15 +341,16 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
 
   // ---- one-off setup ---------------------------------------------------------------------------------------------
   if (tid == 0) {
-    for (int i = 0; i < 8; ++i) {
-      tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); tc::mbar_init(&full_x[i], 1); tc::mbar_init(&empty_x[i], 1);
-    }
+    for (int g = 0; g < 2; ++g)
+      for (int i = 0; i < 8; ++i) {
+        tc::mbar_init(&full_a[g][i], 1); tc::mbar_init(&empty_a[g][i], 1); tc::mbar_init(&full_x[g][i], 1); tc::mbar_init(&empty_x[g][i], 1);
+      }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 1); }
     tc::mbar_init(&res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_exit = 0; s_ok[0] = 1; s_ok[1] = 1;
     s_go = fr ? 2 : n_steps; s_stop_at = 0x7fffffff;
-    for (int i = 0; i < 8; ++i) { s_xfill[i] = 0; s_afill[i] = 0; }
+    for (int g = 0; g < 2; ++g) for (int i = 0; i < 8; ++i) { s_xfill[g][i] = 0; s_afill[g][i] = 0; }
     // placement of the program's weight tiles: tensor memory first, then shared memory, in order of criticality
     int n_tm = q.n_tm, n_sm = q.n_res, tm = 0, sm = 0;
     for (int i = 0; i < 32; ++i) s_loc[i] = LOC_STREAM;
@@ -504,15 +507,19 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       const int i = lane;
       const TileRec tr = s_tile[i];
       const bool streamed = tr.loc == LOC_STREAM;
-      int arank = 0, n_streamed = 0;
-      for (int j = 0; j < n_tiles; ++j) { const int st_ = s_loc[j] == LOC_STREAM; n_streamed += st_; if (j < i) arank += st_; }
+      const int g = tr.gemm;
+      const int g_lo = g == 0 ? 0 : (has_g1 ? kTiles1 : 0), g_hi = g == 0 ? kTiles1 : n_tiles, n_g = g_hi - g_lo;
+      int arank = 0, n_streamed = 0;       // streamed weight tiles of this product: before this tile / per frame
+      for (int j = g_lo; j < g_hi; ++j) { const int st_ = s_loc[j] == LOC_STREAM; n_streamed += st_; if (j < i) arank += st_; }
+      unsigned char* const my_aring = aring + (size_t)g * NSA * tc::kATileBytes;
+      unsigned char* const my_xring = xring + (size_t)g * NSX * kXTileBytes;
       const unsigned* fptr = tr.flag >= 0 ? flag(tr.flag) : nullptr;
       unsigned seen = 0;
       bool ok = true;
       for (int t = 0; t < n_steps && ok; ++t) {
         if (fr && !wait_frame(t)) break;
         bool need_a = streamed, need_x = true;
-        const unsigned ga = (unsigned)t * (unsigned)n_streamed + (unsigned)arank, gx = (unsigned)t * (unsigned)n_tiles + (unsigned)i;
+        const unsigned ga = (unsigned)t * (unsigned)n_streamed + (unsigned)arank, gx = (unsigned)t * (unsigned)n_g + (unsigned)(i - g_lo);
         const unsigned target = fptr ? (unsigned)tr.mul * (unsigned)(t + tr.add) : 0u;
         const unsigned char* xsrc = tr.xkind == 2 ? q.xpre + (((size_t)t * S + s1) * 4 + tr.kb) * kXTileBytes
                                     : tr.xkind == 0 ? q.x1 + (size_t)(t & 1) * x1_par + (size_t)s1 * x1_stream + (size_t)tr.kb * kXTileBytes
@@ -523,11 +530,11 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           if (need_a) {
             const int slot = (int)(ga % (unsigned)NSA);
             const unsigned round = ga / (unsigned)NSA;
-            if (s_afill[slot] == round && (round == 0u || mbar_test(&empty_a[slot], (round & 1u) ^ 1u))) {
-              tc::mbar_expect_tx(&full_a[slot], (unsigned)tc::kATileBytes);
-              tma_load_1d_hint(aring + (size_t)slot * tc::kATileBytes, my_wt + (size_t)i * tc::kATileBytes, tc::kATileBytes,
-                               &full_a[slot], pol_keep);
-              s_afill[slot] = round + 1u;
+            if (s_afill[g][slot] == round && (round == 0u || mbar_test(&empty_a[g][slot], (round & 1u) ^ 1u))) {
+              tc::mbar_expect_tx(&full_a[g][slot], (unsigned)tc::kATileBytes);
+              tma_load_1d_hint(my_aring + (size_t)slot * tc::kATileBytes, my_wt + (size_t)i * tc::kATileBytes, tc::kATileBytes,
+                               &full_a[g][slot], pol_keep);
+              s_afill[g][slot] = round + 1u;
               if (q.dbg && c == q.dbg_cta && t == q.dbg_frame) q.dbg[96 + i] = clock64();
               need_a = false;
             }
@@ -542,11 +549,11 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             if (ready) {
               const int slot = (int)(gx % (unsigned)NSX);
               const unsigned round = gx / (unsigned)NSX;
-              if (s_xfill[slot] == round && (round == 0u || mbar_test(&empty_x[slot], (round & 1u) ^ 1u))) {
-                tc::mbar_expect_tx(&full_x[slot], (unsigned)kXTileBytes);
-                if (tr.xkind == 2) tma_load_1d_hint(xring + (size_t)slot * kXTileBytes, xsrc, kXTileBytes, &full_x[slot], pol_once);
-                else tc::tma_load_1d(xring + (size_t)slot * kXTileBytes, xsrc, kXTileBytes, &full_x[slot]);
-                s_xfill[slot] = round + 1u;
+              if (s_xfill[g][slot] == round && (round == 0u || mbar_test(&empty_x[g][slot], (round & 1u) ^ 1u))) {
+                tc::mbar_expect_tx(&full_x[g][slot], (unsigned)kXTileBytes);
+                if (tr.xkind == 2) tma_load_1d_hint(my_xring + (size_t)slot * kXTileBytes, xsrc, kXTileBytes, &full_x[g][slot], pol_once);
+                else tc::tma_load_1d(my_xring + (size_t)slot * kXTileBytes, xsrc, kXTileBytes, &full_x[g][slot]);
+                s_xfill[g][slot] = round + 1u;
                 if (q.dbg && c == q.dbg_cta && t == q.dbg_frame) q.dbg[i] = clock64();
                 need_x = false;
               }
@@ -568,11 +575,16 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
     if (lane == 0 && (my_gemm == 1 || has_g1)) {
       const uint32_t idesc = tc::make_idesc_f16(128, NPAD);
       constexpr uint32_t lbo_a = (128 / 8) * 128, lbo_x = (NPAD / 8) * 128, sbo = 128;
+      const int i_lo = my_gemm == 0 ? 0 : (has_g1 ? kTiles1 : 0), i_hi = my_gemm == 0 ? kTiles1 : n_tiles, n_g = i_hi - i_lo;
       int n_streamed = 0;
-      for (int j = 0; j < n_tiles; ++j) n_streamed += s_loc[j] == LOC_STREAM;
-      const int i_lo = my_gemm == 0 ? 0 : (has_g1 ? kTiles1 : 0), i_hi = my_gemm == 0 ? kTiles1 : n_tiles;
-      int arank0 = 0;
-      for (int j = 0; j < i_lo; ++j) arank0 += s_loc[j] == LOC_STREAM;
+      for (int j = i_lo; j < i_hi; ++j) n_streamed += s_loc[j] == LOC_STREAM;
+      const int g = my_gemm;
+      unsigned char* const my_aring = aring + (size_t)g * NSA * tc::kATileBytes;
+      unsigned char* const my_xring = xring + (size_t)g * NSX * kXTileBytes;
+      // descriptor templates (K-major, no swizzle): everything but the 14-bit start-address field is constant
+      const uint64_t desc_hi_a = tc::make_smem_desc(0u, lbo_a, sbo), desc_hi_x = tc::make_smem_desc(0u, lbo_x, sbo);
+      const uint32_t a_ring_addr = tc::smem_u32(my_aring), x_ring_addr = tc::smem_u32(my_xring), res_addr = tc::smem_u32(res_s);
+      const uint32_t acc = acc_addr[my_gemm];
       bool ok = mbar_wait_ab(&res_bar, 0u, ctl);
       for (int t = 0; t < n_steps && ok; ++t) {
         if (fr && !wait_frame(t)) break;
@@ -580,40 +592,41 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           ok = mbar_wait_ab(&acc_empty[my_gemm], (uint32_t)((t - 1) & 1), ctl);
           if (!ok) break;
         }
-        unsigned ga = (unsigned)t * (unsigned)n_streamed + (unsigned)arank0;
-        for (int i = i_lo; i < i_hi && ok; ++i) {
+        unsigned ga = (unsigned)t * (unsigned)n_streamed;
+        unsigned gx = (unsigned)t * (unsigned)n_g;
+        const bool dbg_on = q.dbg && c == q.dbg_cta && t == q.dbg_frame;
+        for (int i = i_lo; i < i_hi; ++i, ++gx) {
+          // this thread is the critical path of the product: per tile a couple of barrier probes, eight descriptor adds,
+          // four MMAs and the commits -- nothing else
           const int loc = s_loc[i];
-          const unsigned gx = (unsigned)t * (unsigned)n_tiles + (unsigned)i;
           const int sx = (int)(gx % (unsigned)NSX), sa = (int)(ga % (unsigned)NSA);
-          ok = wait_fill(&s_xfill[sx], gx / (unsigned)NSX + 1u) && mbar_wait_ab(&full_x[sx], (gx / (unsigned)NSX) & 1u, ctl);
-          if (ok && loc == LOC_STREAM)
-            ok = wait_fill(&s_afill[sa], ga / (unsigned)NSA + 1u) && mbar_wait_ab(&full_a[sa], (ga / (unsigned)NSA) & 1u, ctl);
+          if (!mbar_try(&full_x[g][sx], (gx / (unsigned)NSX) & 1u)) ok = mbar_wait_ab(&full_x[g][sx], (gx / (unsigned)NSX) & 1u, ctl);
+          if (ok && loc == LOC_STREAM && !mbar_try(&full_a[g][sa], (ga / (unsigned)NSA) & 1u))
+            ok = mbar_wait_ab(&full_a[g][sa], (ga / (unsigned)NSA) & 1u, ctl);
           if (!ok) break;
-          if (q.dbg && c == q.dbg_cta && t == q.dbg_frame) q.dbg[32 + i] = clock64();
+          if (dbg_on) q.dbg[32 + i] = clock64();
           tc::tc_fence_after();
-          const uint32_t x_addr = tc::smem_u32(xring + (size_t)sx * kXTileBytes);
-          const uint32_t acc = acc_addr[my_gemm];
+          const uint64_t dx0 = desc_hi_x | (uint64_t)(((x_ring_addr + (uint32_t)sx * (uint32_t)kXTileBytes) >> 4) & 0x3fffu);
+          const uint32_t first = (i == i_lo) ? 0u : 1u;
           if (loc >= 0 && loc < LOC_SMEM) {
             const uint32_t a_tm = tmem_base + tm_w_col + (uint32_t)(loc * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t dx = tc::make_smem_desc(x_addr + j * 2 * lbo_x, lbo_x, sbo);
-              umma_f16_ts(acc, a_tm + (uint32_t)(j * 8), dx, idesc, (i == i_lo && j == 0) ? 0u : 1u);
-            }
+            umma_f16_ts(acc, a_tm, dx0, idesc, first);
+            umma_f16_ts(acc, a_tm + 8u, dx0 + (uint64_t)((2 * lbo_x) >> 4), idesc, 1u);
+            umma_f16_ts(acc, a_tm + 16u, dx0 + (uint64_t)((4 * lbo_x) >> 4), idesc, 1u);
+            umma_f16_ts(acc, a_tm + 24u, dx0 + (uint64_t)((6 * lbo_x) >> 4), idesc, 1u);
           } else {
-            const uint32_t a_addr = tc::smem_u32(loc == LOC_STREAM ? aring + (size_t)sa * tc::kATileBytes
-                                                                   : res_s + (size_t)(loc - LOC_SMEM) * tc::kATileBytes);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t da = tc::make_smem_desc(a_addr + j * 2 * lbo_a, lbo_a, sbo);
-              const uint64_t dx = tc::make_smem_desc(x_addr + j * 2 * lbo_x, lbo_x, sbo);
-              tc::umma_f16(acc, da, dx, idesc, (i == i_lo && j == 0) ? 0u : 1u);
-            }
+            const uint32_t a_addr = loc == LOC_STREAM ? a_ring_addr + (uint32_t)sa * (uint32_t)tc::kATileBytes
+                                                      : res_addr + (uint32_t)(loc - LOC_SMEM) * (uint32_t)tc::kATileBytes;
+            const uint64_t da0 = desc_hi_a | (uint64_t)((a_addr >> 4) & 0x3fffu);
+            tc::umma_f16(acc, da0, dx0, idesc, first);
+            tc::umma_f16(acc, da0 + (uint64_t)((2 * lbo_a) >> 4), dx0 + (uint64_t)((2 * lbo_x) >> 4), idesc, 1u);
+            tc::umma_f16(acc, da0 + (uint64_t)((4 * lbo_a) >> 4), dx0 + (uint64_t)((4 * lbo_x) >> 4), idesc, 1u);
+            tc::umma_f16(acc, da0 + (uint64_t)((6 * lbo_a) >> 4), dx0 + (uint64_t)((6 * lbo_x) >> 4), idesc, 1u);
           }
-          tc::umma_commit(&empty_x[sx]);
-          if (loc == LOC_STREAM) { tc::umma_commit(&empty_a[sa]); ++ga; }
+          tc::umma_commit(&empty_x[g][sx]);
+          if (loc == LOC_STREAM) { tc::umma_commit(&empty_a[g][sa]); ++ga; }
           if (i == i_hi - 1) tc::umma_commit(&acc_full[my_gemm]);
-          if (q.dbg && c == q.dbg_cta && t == q.dbg_frame) q.dbg[64 + i] = clock64();
+          if (dbg_on) q.dbg[64 + i] = clock64();
         }
       }
     }

@@ -1356,12 +1356,12 @@ bool pb_geometry(const taco2dec_handle* h, int B, int T_in, int T_sub, int fr, P
   // tensor memory: 512 columns, 2 * npad of them accumulators, 32 per resident weight tile
   int n_tm = std::min(env_int("TACO2DEC_PB_TMEM", 64), (512 - 2 * npad) / 32);
   n_tm = std::max(0, std::min(n_tm, pb::kMaxTiles));
-  int stages_x = std::max(2, std::min(8, env_int("TACO2DEC_PB_STAGES_X", 6)));
-  int stages_a = std::max(2, std::min(8, env_int("TACO2DEC_PB_STAGES_A", 4)));
-  while (fixed + stages_x * xt + stages_a * at + 1024 > budget && stages_a > 2) --stages_a;
-  while (fixed + stages_x * xt + stages_a * at + 1024 > budget && stages_x > 2) --stages_x;
-  if (fixed + stages_x * xt + stages_a * at + 1024 > budget) return false;
-  int n_res = (int)((budget - fixed - stages_x * xt - stages_a * at - 1024) / at);
+  // ring depths are PER gate product (two weight rings, two activation rings)
+  int stages_x = std::max(2, std::min(8, env_int("TACO2DEC_PB_STAGES_X", npad <= 32 ? 8 : npad == 64 ? 4 : 3)));
+  int stages_a = std::max(2, std::min(8, env_int("TACO2DEC_PB_STAGES_A", 2)));
+  while (fixed + 2 * (stages_x * xt + stages_a * at) + 1024 > budget && stages_x > 2) --stages_x;
+  if (fixed + 2 * (stages_x * xt + stages_a * at) + 1024 > budget) return false;
+  int n_res = (int)((budget - fixed - 2 * (stages_x * xt + stages_a * at) - 1024) / at);
   n_res = std::max(0, std::min(std::min(n_res, env_int("TACO2DEC_PB_RES", 64)), pb::kMaxTiles - n_tm));
   out->npad = npad; out->stages_a = stages_a; out->stages_x = stages_x; out->n_res = n_res; out->n_tm = n_tm;
   out->smem = pb::smem_plan(npad, stages_a, stages_x, n_res, max_ts, fr).total;
