@@ -5,22 +5,34 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1], the configuration the metric is quoted on): free-running
-``Decoder.inference``, batch 1, 150-phone / 50-sub-word synthetic memory, max_decoder_steps=1000,
-default hparams (dual-stream, StepwiseMonotonicAttention), gate bias -20 so every utterance runs
-exactly 1000 frames.  One "step" = one utterance.  N GPUs = N independent utterances, one per rank
-(utterance sharding, no data-path collective; weak scaling).
+Headline workload (BASELINE.json configs[1], the configuration the metric is quoted on): free-running
+``Decoder.inference``, batch 1, 150-phone / 50-sub-word synthetic memory, max_decoder_steps=1000, default hparams
+(dual-stream, StepwiseMonotonicAttention), gate bias -20 so every utterance runs exactly 1000 frames.  One "step" = one
+utterance.  N GPUs = N independent utterances, one per rank (utterance sharding, no data-path collective; weak scaling).
 
-Printed JSON line (rank 0): value = frames/s with inputs resident in HBM (device-timed, CUDA
-events, max over ranks); e2e = the same metric through the Python drop-in API with pinned HOST
-inputs (H2D + D2H inside the timed region); roofline = algorithmic bytes of the persistent kernel /
-its event-timed duration vs the measured HBM peak; cpu_baseline = the CPU oracle port of the
-reference decoder timed on this box's host cores.
+The JSON line (rank 0):
+  value         frames/s, inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e           the same metric through ``Decoder.inference`` with pinned HOST inputs and ALL five outputs copied back
+  roofline      the binding roof of the latency kernel.  Its weights live in shared memory, tensor memory and L2 (DRAM pipe
+                ~3 % busy), so the HBM-algorithmic figure (kept as ``hbm_algorithmic``) is not a bound: the frame time is
+                a chain of cross-CTA exchanges through L2 plus one L2 pass over the non-resident weights.  Both are
+                measured on this device in this run (``taco2dec_measure_machine``): floor = hops x hop latency + L2 bytes /
+                L2 read rate; frac = floor / achieved.  ``traffic`` comes from the committed ncu capture and is only
+                reported when that capture was taken with the library that is loaded now (sha256 stamp).
+  cpu_baseline  the reference arm (below) run as a subprocess on the same host before any GPU work: same function, same
+                sample, same process conditions as ``--impl reference``
+  sub_records   the BASELINE configs that have a bottleneck when sharded: cfg 3 (64 utterances in total, strong scaling,
+                persistent tcgen05 kernel), cfg 4 (128 utterances in total, teacher-forced GTA shape), cfg 5 (decoder
+                forward + backward + NCCL gradient all-reduce, 64 utterances per GPU, weak scaling)
+
+``--impl reference``: the CPU oracle port of the reference decoder (the reference is Python and does not travel to the
+GPU box) on all host threads, full 1000-frame utterances.
 """
 from __future__ import annotations
 
 import argparse
 import contextlib
+import hashlib
 import json
 import os
 import statistics
@@ -34,17 +46,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CFG = dict(B=1, T_in=150, T_sub=50, max_steps=1000, attention="StepwiseMonotonicAttention", gate_bias=-20.0, seed=1234)
-REF_SAMPLE_FRAMES = 250   # frames per step for the CPU reference arm (bounded sample of the 1000-frame workload)
 W_ACT = 32_082_257        # weights touched per frame, dual-stream SMA
+LAT_HOPS_PER_FRAME = 7    # dependent cross-CTA exchanges of the latency kernel per free-running frame:
+                          # prenet -> h1 -> q partials -> context -> h2 -> projection/stop -> prenet L0 partials -> prenet
+LIB = os.path.join(ROOT, "tacotron2_subword_b200", "csrc", "libtaco2dec.so")
 
-
-# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
-# NCCL_DEBUG is set on the box, the reference-style decoder prints a warning at max_decoder_steps), so the process's
-# stdout is pointed at stderr for the whole run and the result line goes to the saved descriptor.
 _REAL_STDOUT = None
 
 
 def _claim_stdout() -> None:
+    """The contract is ONE JSON line on stdout; libraries print there too, so stdout is pointed at stderr."""
     global _REAL_STDOUT
     if _REAL_STDOUT is None:
         sys.stdout.flush()
@@ -68,12 +79,19 @@ def algorithmic_bytes_per_frame(B, T_in, T_sub, bytes_per_weight=4):
 
 
 def measured_peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def lib_stamp() -> str:
+    try:
+        with open(LIB, "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()[:16]
+    except Exception:
+        return "missing"
 
 
 class ClockSampler:
@@ -146,36 +164,145 @@ def time_cpu_port(w, inp, frames, repeats, threads):
     return times
 
 
+def workload_config():
+    return {"workload": "cfg2: free-running Decoder.inference, B=1/GPU, 150 phones + 50 sub-words, "
+                        "max_decoder_steps=1000 (gate bias -20 => exactly 1000 frames), dual-stream SMA, default hparams",
+            "frames_per_step": CFG["max_steps"], "utterances_per_gpu": 1,
+            "l2": "L2 flushed (256 MiB write) between timed steps; per-frame working set 128.9 MB > 126 MB L2",
+            "sharding": "one utterance per rank, no collective on the data path"}
+
+
 def run_reference_arm(args, rank):
-    """--impl reference: the reference's own CPU algorithm (oracle port; the reference is Python
-    and does not travel to the GPU box) on all host threads, same config/metric/unit."""
+    """--impl reference: the reference's own CPU algorithm (oracle port) on all host threads, full 1000-frame utterances,
+    same config / metric / unit as the b200 arm."""
     if rank != 0:
         return
     w, inp = make_problem()
     threads = os.cpu_count() or 1
-    time_cpu_port(w, inp, 20, max(1, args.warmup), threads)  # warm-up on a short utterance
-    times = time_cpu_port(w, inp, REF_SAMPLE_FRAMES, args.steps, threads)
+    frames = CFG["max_steps"]
+    time_cpu_port(w, inp, 50, max(1, min(args.warmup, 2)), threads)   # warm-up on a short utterance (thread pool, page-in)
+    times = time_cpu_port(w, inp, frames, args.steps, threads)
     total = sum(times)
-    value = REF_SAMPLE_FRAMES * args.steps / total
+    value = frames * args.steps / total
     line = {
         "impl": "reference", "metric": "mel_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} x {REF_SAMPLE_FRAMES}-frame prefix of the 1000-frame utterance "
-                                   f"(oracle/decoder_oracle.py, torch CPU fp32, {threads} threads)"},
+                         "sample": f"{args.steps} full {frames}-frame utterances of the workload "
+                                   f"(oracle/decoder_oracle.py = CPU restatement of model.Decoder.inference, torch CPU fp32, "
+                                   f"{threads} threads, own process)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
-def workload_config():
-    return {"workload": "cfg2: free-running Decoder.inference, B=1/GPU, 150 phones + 50 sub-words, "
-                        "max_decoder_steps=1000 (gate bias -20 => exactly 1000 frames), dual-stream SMA, default hparams",
-            "frames_per_step": CFG["max_steps"], "utterances_per_gpu": 1, "weights": "fp32 (reference layouts)",
-            "l2": "L2 flushed (256 MiB write) between timed steps; per-frame working set 128.9 MB > 126 MB L2",
-            "sharding": "one utterance per rank, no collective on the data path"}
+def cpu_baseline_subprocess(steps=3):
+    """The reference arm in its own process BEFORE this process touches the GPU: identical code and conditions, so
+    cpu_baseline and the driver's --impl reference run cannot disagree by construction."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "1"],
+                             capture_output=True, text=True, timeout=600)
+        for ln in out.stdout.splitlines()[::-1]:
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+    except Exception as e:      # noqa: BLE001
+        return {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    return {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "no output"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sub-records: the configurations whose scaling has a bottleneck
+# ------------------------------------------------------------------------------------------------------------------
+def sub_records(torch, dist, dev, rank, world, w_never_stop):
+    from oracle.synth import SMA, make_decoder_weights, make_inputs
+    from tacotron2_subword_b200 import Decoder, create_hparams
+    recs = []
+
+    def timed(fn, reps=2):
+        fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([min(ts)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dec = Decoder(create_hparams()); dec.load_state_dict(w_never_stop, strict=True); dec = dec.to(dev).eval()
+    dec.rng_seed = 7 + rank
+    eng = dec._engine(dev)
+    # cfg 3: 64 utterances in total, free-running 1000 frames, sharded over the ranks (strong scaling)
+    total, T = 64, 1000
+    Bp = total // world
+    inp = make_inputs(total, 120, 40, 1, seed=3, ragged=True)
+    sl = slice(rank * Bp, (rank + 1) * Bp)
+    mem, emb = inp["memory"][sl].to(dev), inp["embeddings"][sl].to(dev)
+    ml, bl = inp["memory_lengths"][sl].to(dev), inp["bert_lengths"][sl].to(dev)
+    T_in, T_sub = int(ml.max()), int(bl.max())
+    mem, emb = mem[:, :T_in].contiguous(), emb[:, :T_sub].contiguous()
+    with torch.no_grad():
+        ms = timed(lambda: dec.inference_batched(mem, emb, ml, bl, max_decoder_steps=T))
+    recs.append({"config": "cfg3: batched free-running inference, 64 utterances in total, 120 phones / 40 sub-words, 1000 frames",
+                 "scaling": "strong", "utterances_per_gpu": Bp, "path": eng.last_path(), "ms": ms, "us_per_frame_step": 1e3 * ms / T,
+                 "value": total * T / (ms * 1e-3), "unit": "frames/s", "collective": "none (utterance sharding)"})
+    # cfg 4: GTA shape, 128 utterances in total, teacher-forced 800 frames
+    total, T = 128, 800
+    Bp = total // world
+    inp = make_inputs(total, 160, 53, T, seed=4, ragged=True)
+    sl = slice(rank * Bp, (rank + 1) * Bp)
+    ml, bl = inp["memory_lengths"][sl].to(dev), inp["bert_lengths"][sl].to(dev)
+    T_in, T_sub = int(ml.max()), int(bl.max())
+    mem, emb = inp["memory"][sl, :T_in].contiguous().to(dev), inp["embeddings"][sl, :T_sub].contiguous().to(dev)
+    mels = inp["mels"][sl].to(dev)
+    with torch.no_grad():
+        ms = timed(lambda: dec(mem, emb, mels, ml, bl, independent=True))
+    recs.append({"config": "cfg4: GTA extraction shape, teacher-forced, 128 utterances in total, 160 / 53, 800 frames",
+                 "scaling": "strong", "utterances_per_gpu": Bp, "path": eng.last_path(), "ms": ms, "us_per_frame_step": 1e3 * ms / T,
+                 "value": total * T / (ms * 1e-3), "unit": "frames/s", "collective": "none (utterance sharding)"})
+    del dec
+    # cfg 5: decoder training step, 64 utterances per GPU (weak), forward + backward + gradient all-reduce over NCCL
+    B, T = 64, 800
+    dect = Decoder(create_hparams()); dect.load_state_dict(make_decoder_weights(SMA, seed=1234), strict=True)
+    dect = dect.to(dev).train()
+    dect.rng_seed = 11
+    n_coll = 0
+    if world > 1:
+        from tacotron2_subword_b200.distributed import apply_gradient_allreduce
+        apply_gradient_allreduce(dect)
+    inp = make_inputs(B, 160, 53, T, seed=5 + rank, ragged=True)
+    mem, emb = inp["memory"].to(dev).requires_grad_(True), inp["embeddings"].to(dev).requires_grad_(True)
+    mels, ml, bl = inp["mels"].to(dev), inp["memory_lengths"].to(dev), inp["bert_lengths"].to(dev)
+    target = torch.randn(B, 80, T, device=dev)
+
+    def step():
+        dect.zero_grad(set_to_none=True)
+        mel, gate, al, alb = dect(mem, emb, mels, ml, bl)
+        loss = torch.nn.functional.mse_loss(mel, target) + \
+            torch.nn.functional.binary_cross_entropy_with_logits(gate, torch.zeros_like(gate))
+        loss.backward()
+
+    ms = timed(step)
+    if world > 1:
+        n_coll = dect._grad_bucketer.n_collectives
+        gsum = torch.stack([p.grad.double().abs().sum() for p in dect.parameters() if p.grad is not None]).sum()
+        glist = [torch.zeros_like(gsum) for _ in range(world)]
+        dist.all_gather(glist, gsum)
+        assert all(torch.equal(g_, glist[0]) for g_ in glist), "gradients differ across ranks after the all-reduce"
+    grad_bytes = sum(p.grad.numel() * 4 for p in dect.parameters() if p.grad is not None)
+    recs.append({"config": "cfg5: decoder training step (teacher-forced forward + BPTT backward + NCCL gradient all-reduce), "
+                           "64 utterances per GPU, 160 / 53, 800 frames, train mode",
+                 "scaling": "weak", "utterances_per_gpu": B, "path": dect._engine(dev).last_path(), "ms": ms,
+                 "us_per_frame_step": 1e3 * ms / T, "value": world * B * T / (ms * 1e-3), "unit": "frames/s",
+                 "collective": f"all-reduce of {grad_bytes / 1e6:.0f} MB of decoder gradients per step over NCCL" if world > 1 else "none (1 GPU)",
+                 "nccl_calls_total": n_coll})
+    return recs
 
 
 def main():
@@ -186,6 +313,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true")
     ap.add_argument("--weights", default="fp32", choices=["fp32", "fp16"],
                     help="storage of the packed LSTM matrices on the latency path (headline = fp32, the reference's dtype)")
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "latency"])
@@ -199,6 +327,11 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
+
+    # CPU baseline first, in its own process, before this process creates a CUDA context
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_subprocess()
 
     import torch
     import torch.distributed as dist
@@ -245,7 +378,7 @@ def main():
             e = emb_host.to(dev, non_blocking=True)
             with contextlib.redirect_stdout(sys.stderr):      # the API prints "Warning! Reached max decoder steps"
                 mel, gate, al, alb, flag = dec.inference(m, e)
-            return mel.cpu(), gate.cpu(), flag
+            return mel.cpu(), gate.cpu(), al.cpu(), alb.cpu(), flag      # everything Decoder.inference returns
 
     for _ in range(args.warmup):
         out = resident_step()
@@ -287,7 +420,7 @@ def main():
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         e0.record()
-        mel_h, gate_h, flag = e2e_step()
+        outs_h = e2e_step()
         e1.record()
         e1.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
@@ -298,9 +431,9 @@ def main():
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     e2e_value = n_gpus * frames * args.steps / (float(e2e_total.item()) / 1e3)
     h2d = mem_host.numel() * 4 + emb_host.numel() * 4
-    d2h = mel_h.numel() * 4 + gate_h.numel() * 4
+    d2h = sum(t.numel() * 4 for t in outs_h[:4])
 
-    # ---------------- p50 latency without the L2 flush (a server decoding back-to-back utterances; SURVEY.md 8d asks for both) ----
+    # ---------------- p50 latency without the L2 flush (a server decoding back-to-back utterances) ----------------
     warm_ms = []
     for _ in range(args.steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -327,46 +460,72 @@ def main():
         variant = {"weights": "fp16 LSTM matrices (fp32 accumulate, everything else fp32)", "kernel_ms": statistics.mean(v_ms),
                    "us_per_frame": 1e3 * statistics.mean(v_ms) / frames, "frames_per_sec_1gpu": frames / (statistics.mean(v_ms) * 1e-3),
                    "mel_max_abs_vs_fp32_over_1000_free_running_frames": err}
+
+    l2_gbs, hop_ns = eng.measure_machine()
+    subs = None
+    if not args.no_sub_records:
+        subs = sub_records(torch, dist, dev, rank, world, w)
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         wb = 4 if args.weights == "fp32" else 2
         bpf = (algorithmic_bytes_per_frame(1, CFG["T_in"], CFG["T_sub"], 4) if wb == 4
                else 31_457_280 * 2 + 624_977 * 4 + (algorithmic_bytes_per_frame(1, CFG["T_in"], CFG["T_sub"], 4) - W_ACT * 4))
         k_ms = statistics.mean(kern_ms)
-        achieved = bpf * frames / (k_ms * 1e-3) / 1e9
-        traffic = None
+        us_frame = 1e3 * k_ms / frames
+        hbm_alg = bpf * frames / (k_ms * 1e-3) / 1e9
+        # committed ncu capture of this kernel: only valid for the library it was taken with
+        traffic = l2_traffic = None
+        traffic_note = "no capture"
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("lib_sha256_16") == lib_stamp():
+                traffic, l2_traffic = tj.get("dram_bytes_per_launch"), tj.get("l2_bytes_per_launch")
+                traffic_note = f"ncu capture {tj.get('source')} (library {tj.get('lib_sha256_16')})"
+            else:
+                traffic_note = f"stale: capture was taken with library {tj.get('lib_sha256_16')}, loaded library is {lib_stamp()}"
         except Exception:
             pass
+        # bytes the latency kernel pulls through L2 per frame: everything that is not resident in shared / tensor memory
+        l2_bpf = (l2_traffic / frames) if l2_traffic else (bpf - (24.5e6 + 33.5e6 if wb == 4 else 52.0e6))
+        floor_us = LAT_HOPS_PER_FRAME * hop_ns * 1e-3 + l2_bpf / (l2_gbs * 1e9) * 1e6
+        is_lat = path_taken == "latency"
         line = {
             "metric": "mel_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": statistics.mean(step_ms), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.weights == "fp32" else "f16-weights/f32-accumulate",
             "data": "synthetic", "config": dict(workload_config(), kernel_path=path_taken, weights=args.weights),
             "latency_ms_p50": statistics.median(step_ms), "latency_ms_p50_no_l2_flush": statistics.median(warm_ms),
-            "us_per_frame": 1e3 * k_ms / frames,
+            "us_per_frame": us_frame,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "latency_ms_p50": statistics.median(e2e_ms)},
+                    "latency_ms_p50": statistics.median(e2e_ms),
+                    "outputs_copied_back": "mel, gate, alignments, alignments_bert (everything Decoder.inference returns)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic if (args.weights == "fp32" and path_taken == "latency") else None,
-                         "kernel": ("lat::decoder_latency<%d>" % wb) if path_taken == "latency" else "decoder_persistent<1>",
-                         "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": bpf * frames, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)"},
+            "roofline": {
+                "bound": "l2+latency" if is_lat else "hbm",
+                "achieved": (l2_bpf * frames / (k_ms * 1e-3) / 1e9) if is_lat else hbm_alg,
+                "peak": l2_gbs if is_lat else peak, "unit": "GB/s",
+                "frac": (floor_us / us_frame) if is_lat else hbm_alg / peak,
+                "traffic": traffic, "traffic_source": traffic_note,
+                "kernel": ("lat::decoder_latency<%d>" % wb) if is_lat else "decoder_persistent<1>", "kernel_ms": k_ms,
+                "model": {"what": "per-frame floor = hops x measured cross-CTA exchange latency + L2 bytes / measured L2 read rate; "
+                                  "frac = floor / achieved frame time (achieved / peak are the L2 byte rate and the measured L2 read rate)",
+                          "hops_per_frame": LAT_HOPS_PER_FRAME, "hop_ns_measured": hop_ns, "l2_read_gbs_measured": l2_gbs,
+                          "l2_bytes_per_frame": l2_bpf, "floor_us_per_frame": floor_us, "achieved_us_per_frame": us_frame},
+                "hbm_algorithmic": {"achieved_gbs": hbm_alg, "peak_gbs": peak, "frac": hbm_alg / peak,
+                                    "algorithmic_bytes_per_launch": bpf * frames,
+                                    "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+                                    "note": "not a bound: > 90 % of these bytes are served from shared memory, tensor memory and L2"},
+            },
         }
         if variant is not None:
             line["variants"] = [variant]
-        if n_gpus == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            time_cpu_port(w, inp, 20, 1, threads)
-            t = time_cpu_port(w, inp, frames, 2, threads)
-            line["cpu_baseline"] = {"value": frames * len(t) / sum(t), "unit": "frames/s", "cores": threads, "kind": "port",
-                                    "sample": f"{len(t)} full {frames}-frame utterances of the same workload "
-                                              f"(oracle/decoder_oracle.py = CPU restatement of model.Decoder.inference, "
-                                              f"torch CPU fp32, {threads} threads)"}
+        if subs is not None:
+            line["sub_records"] = subs
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -292,6 +292,11 @@ int taco2dec_read_phase_clocks(taco2dec_handle* h, void* cuda_stream, long long*
  * [32,64) operands landed, [64,96) MMAs issued, [96,128) weight tile requested, [128,144) compute-warp phase marks. */
 int taco2dec_read_debug_stamps(taco2dec_handle* h, void* cuda_stream, long long* out256_host);
 
+/* Machine probes behind bench.py's roofline for kernels whose weights live on-chip / in L2: the L2 -> SM read rate of
+ * this device (GB/s, 32 MiB resident buffer read by every SM) and the latency of one cross-CTA exchange through L2 (ns:
+ * one 8-byte {value, tag} store by one CTA until a polling CTA on another SM has seen it).  Synchronises the stream. */
+int taco2dec_measure_machine(taco2dec_handle* h, void* cuda_stream, double* l2_read_gbs, double* hop_ns);
+
 /* Persistent-kernel launch geometry actually used (for DESIGN.md / bench bookkeeping). */
 int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* block, int* smem_bytes);
 

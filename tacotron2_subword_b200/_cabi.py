@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "taco2dec_test_gemm", "taco2dec_saved_layout_query", "taco2dec_grad_layout_query", "taco2dec_backward",
     "taco2dec_postnet_create", "taco2dec_postnet_destroy", "taco2dec_postnet_set_weights",
     "taco2dec_postnet_workspace_bytes", "taco2dec_postnet_forward",
-    "taco2dec_set_batched_precision", "taco2dec_poll_abort", "taco2dec_read_debug_stamps",
+    "taco2dec_set_batched_precision", "taco2dec_poll_abort", "taco2dec_read_debug_stamps", "taco2dec_measure_machine",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -170,6 +170,8 @@ def load_library() -> C.CDLL:
     lib.taco2dec_set_batched_precision.argtypes = [H, C.c_int]
     lib.taco2dec_read_debug_stamps.restype = C.c_int
     lib.taco2dec_read_debug_stamps.argtypes = [H, C.c_void_p, C.POINTER(C.c_longlong)]
+    lib.taco2dec_measure_machine.restype = C.c_int
+    lib.taco2dec_measure_machine.argtypes = [H, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.taco2dec_poll_abort.restype = C.c_int
     lib.taco2dec_poll_abort.argtypes = [H]
     lib.taco2dec_last_path.restype = C.c_int

@@ -799,6 +799,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
         const StreamParams& sa = p.st[s];
         const int Ts = sa.Ts;
         const int len = sa.len ? (int)sa.len[b] : Ts;
+        // independent utterances (free-running, GTA): positions >= len do not exist -- their alignment is exactly zero, so
+        // neither their energies nor their memory rows are touched
+        const int Tc = (fr || p.independent) ? min(len, Ts) : Ts;
         float* ctxr_s = att_s;                   // 4*E context partials
         float* q_s = ctxr_s + 4 * E;             // A
         float* v_s = q_s + A;                    // A
@@ -813,7 +816,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
 #pragma unroll
         for (int i = 0; i < bt::kCtxPF; ++i) {
           const int j = jg + 4 * i;
-          pf[i] = j < Ts ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          pf[i] = j < Tc ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float* pm_b = sa.pm + (size_t)b * Ts * A;
         float pmv[2][4][4];
@@ -821,7 +824,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
         for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int pp = 0; pp < 4; ++pp) {
-            const float* row = pm_b + (size_t)min(warp * 4 + r * 64 + pp, Ts - 1) * A;
+            const float* row = pm_b + (size_t)min(warp * 4 + r * 64 + pp, Tc - 1) * A;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) pmv[r][pp][cc] = __ldg(row + lane + 32 * cc);
           }
@@ -853,15 +856,16 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
                       v2 * lat::fast_tanh(q2 + x[pp][2]) + v3 * lat::fast_tanh(q3 + x[pp][3]);
             const float ev = lat::butterfly4(e[0], e[1], e[2], e[3], lane);
             const int j = j0 + (lane >> 3);
-            if ((lane & 7) == 0 && j < Ts) e_s[j] = (j >= len) ? -INFINITY : ev;
+            if ((lane & 7) == 0 && j < Tc) e_s[j] = (j >= len) ? -INFINITY : ev;
           };
-          if (warp * 4 < Ts) round_of(warp * 4, pmv[0]);
-          if (warp * 4 + 64 < Ts) round_of(warp * 4 + 64, pmv[1]);
-          for (int j0 = warp * 4 + 128; j0 < Ts; j0 += 64) {
+          for (int j = Tc + tid; j < Ts; j += kCT) e_s[j] = -INFINITY;
+          if (warp * 4 < Tc) round_of(warp * 4, pmv[0]);
+          if (warp * 4 + 64 < Tc) round_of(warp * 4 + 64, pmv[1]);
+          for (int j0 = warp * 4 + 128; j0 < Tc; j0 += 64) {
             float x[4][4];
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp) {
-              const float* row = pm_b + (size_t)min(j0 + pp, Ts - 1) * A;
+              const float* row = pm_b + (size_t)min(j0 + pp, Tc - 1) * A;
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) x[pp][cc] = __ldg(row + lane + 32 * cc);
             }
@@ -898,19 +902,19 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
 #pragma unroll
           for (int i = 0; i < bt::kCtxPF; ++i) {
             const int j = jg + 4 * i;
-            const float a = j < Ts ? an_s[j] : 0.f;
+            const float a = j < Tc ? an_s[j] : 0.f;
             acc.x = fmaf(a, pf[i].x, acc.x); acc.y = fmaf(a, pf[i].y, acc.y); acc.z = fmaf(a, pf[i].z, acc.z); acc.w = fmaf(a, pf[i].w, acc.w);
           }
-          for (int jb = jg + 4 * bt::kCtxPF; jb < Ts; jb += 4 * bt::kCtxPF) {
+          for (int jb = jg + 4 * bt::kCtxPF; jb < Tc; jb += 4 * bt::kCtxPF) {
 #pragma unroll
             for (int i = 0; i < bt::kCtxPF; ++i) {
               const int j = jb + 4 * i;
-              pf[i] = j < Ts ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              pf[i] = j < Tc ? __ldg(mem4 + (size_t)j * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < bt::kCtxPF; ++i) {
               const int j = jb + 4 * i;
-              const float a = j < Ts ? an_s[j] : 0.f;
+              const float a = j < Tc ? an_s[j] : 0.f;
               acc.x = fmaf(a, pf[i].x, acc.x); acc.y = fmaf(a, pf[i].y, acc.y); acc.z = fmaf(a, pf[i].z, acc.z); acc.w = fmaf(a, pf[i].w, acc.w);
             }
           }

@@ -2145,6 +2145,88 @@ int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* bl
 
 }  // extern "C"
 
+
+// ------------------------------------------------------------------------------------------
+// Machine probes for bench.py's roofline: what the decoder kernels are actually bound by once the weights are on-chip /
+// L2-resident is (a) the L2 -> SM read rate and (b) the latency of one cross-CTA exchange through L2
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(512) l2_read_kernel(const float4* __restrict__ buf, size_t n_vec, int iters, float* sink) {
+  float acc = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; ++it)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += stride * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (i + k * stride < n_vec) ? __ldcg(buf + i + k * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  if (acc == 1.2345e-30f) *sink = acc;
+}
+// two CTAs bounce one 64-bit {value, tag} word: one round trip = two exchanges
+__global__ void hop_pingpong_kernel(unsigned long long* words, int rounds, int* abort_flag) {
+  if (threadIdx.x != 0) return;
+  lat::Watch wd{abort_flag, 0, 0};
+  float v;
+  for (int k = 1; k <= rounds; ++k) {
+    if (blockIdx.x == 0) {
+      lat::ll_store(words, (float)k, (unsigned)k);
+      if (!lat::ll_wait(words + 16, (unsigned)k, v, wd)) return;
+    } else {
+      if (!lat::ll_wait(words, (unsigned)k, v, wd)) return;
+      lat::ll_store(words + 16, v, (unsigned)k);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int taco2dec_measure_machine(taco2dec_handle* h, void* cuda_stream, double* l2_read_gbs, double* hop_ns) {
+  if (!h || !l2_read_gbs || !hop_ns) return fail(TACO2DEC_E_ARG, "null argument");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)32 << 20;      // 32 MiB: resident in either half of the L2
+  float4* buf = nullptr;
+  float* sink = nullptr;
+  unsigned long long* words = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, bytes));
+  CUDA_TRY(cudaMalloc(&sink, 256));
+  CUDA_TRY(cudaMalloc(&words, 256));
+  CUDA_TRY(cudaMemsetAsync(buf, 0, bytes, st));
+  CUDA_TRY(cudaMemsetAsync(words, 0, 256, st));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int iters = 40;
+  l2_read_kernel<<<h->num_sms * 4, 512, 0, st>>>(buf, bytes / 16, 2, sink);          // warm: pull the buffer into L2
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    l2_read_kernel<<<h->num_sms * 4, 512, 0, st>>>(buf, bytes / 16, iters, sink);
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  *l2_read_gbs = (double)bytes * iters / (best * 1e-3) / 1e9;
+  const int rounds = 2000;
+  hop_pingpong_kernel<<<2, 32, 0, st>>>(words, 50, h->abort_dev);
+  CUDA_TRY(cudaMemsetAsync(words, 0, 256, st));
+  CUDA_TRY(cudaEventRecord(e0, st));
+  hop_pingpong_kernel<<<2, 32, 0, st>>>(words, rounds, h->abort_dev);
+  CUDA_TRY(cudaEventRecord(e1, st));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  *hop_ns = (double)ms * 1e6 / (2.0 * rounds);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf); cudaFree(sink); cudaFree(words);
+  h->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Postnet (postnet.cuh)
 // ------------------------------------------------------------------------------------------

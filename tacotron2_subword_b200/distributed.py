@@ -96,10 +96,33 @@ class GradientBucketer:
         self._bucket_of: Dict[int, _Bucket] = {id(p): b for b in self.buckets for p in b.params}
         self._callback_queued = False
         self.n_collectives = 0
+        self._early: List = []                 # (work handle) of gradients reduced before autograd saw them
+        self._prereduced = set()               # ids of parameters whose gradient of this pass is already the mean
+        self.early_min_bytes = 1 << 20
         for b in self.buckets:
             b.reset()
         for p in params:
             p.register_post_accumulate_grad_hook(self._on_grad)
+        # modules that produce several gradients in one autograd node (the decoder's hand-written BPTT) publish them one by
+        # one through these two attributes; see model._DecoderTF.backward
+        for m in module.modules():
+            if hasattr(m, "_weight_tensors") and hasattr(m, "decoder_rnn"):
+                m._grad_ready = self.early_reduce
+                m._grad_ready_finish = self.early_finish
+
+    # -- early path: reduce a finished gradient in place while its producer keeps computing the others ------------------
+    def early_reduce(self, p: torch.nn.Parameter, g: torch.Tensor) -> None:
+        if id(p) not in self._bucket_of or g.numel() * g.element_size() < self.early_min_bytes or p.grad is not None:
+            return                              # small tensors ride in their bucket; accumulating passes take the normal path
+        g.mul_(1.0 / self.world)
+        self._early.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._prereduced.add(id(p))
+        self.n_collectives += 1
+
+    def early_finish(self) -> None:
+        for wk in self._early:
+            wk.wait()
+        self._early = []
 
     # -- hooks ------------------------------------------------------------------------------
     def _on_grad(self, p: torch.nn.Parameter) -> None:
@@ -107,7 +130,10 @@ class GradientBucketer:
             self._callback_queued = True
             Variable._execution_engine.queue_callback(self._finish)   # end of this backward pass
         b = self._bucket_of[id(p)]
-        b.ready.append(p)
+        if id(p) in self._prereduced:           # already averaged in place by early_reduce
+            self._prereduced.discard(id(p))
+        else:
+            b.ready.append(p)
         b.pending -= 1
         if b.pending == 0:
             self._launch(b)

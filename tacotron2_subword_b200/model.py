@@ -102,6 +102,13 @@ class _Engine:
         _cabi.check(self.lib.taco2dec_read_phase_clocks(self.handle, C.c_void_p(stream), buf))
         return list(buf)
 
+    def measure_machine(self):
+        """(L2 -> SM read rate in GB/s, latency of one cross-CTA exchange through L2 in ns) measured on this device."""
+        bw, hop = C.c_double(), C.c_double()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _cabi.check(self.lib.taco2dec_measure_machine(self.handle, C.c_void_p(stream), C.byref(bw), C.byref(hop)))
+        return float(bw.value), float(hop.value)
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         _cabi.check(self.lib.taco2dec_last_kernel_ms(self.handle, C.byref(ms)))
@@ -213,10 +220,27 @@ class _DecoderTF(torch.autograd.Function):
         x_frames = F.pad(st["dec_in"].permute(2, 0, 1), (0, 0, 0, 0, 1, 0))[:T].reshape(T * B, M)   # go frame + targets
         grads = {}
         d_mems = [None, None]
-        tf32 = dec.grad_gemm_tf32 if dec.grad_gemm_tf32 is not None else dec.weight_dtype == "fp16"
+        # ``dec._grad_ready`` (set by distributed.GradientBucketer): called with (parameter, gradient) the moment a weight
+        # gradient exists, largest tensors first, so that its all-reduce over NCCL runs while the remaining contractions
+        # are still being computed (the reference reduces everything after the whole backward, distributed.py:160-167)
+        publish = getattr(dec, "_grad_ready", None)
+
+        def put(param, g):
+            grads[param] = g
+            if publish is not None and param.requires_grad:
+                publish(param, g)
+
+        tf32 = dec.grad_gemm_tf32 if dec.grad_gemm_tf32 is not None else True
         old_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
         try:
+            g2t = dg2.t()
+            x2 = torch.cat([t_ for s in range(S) for t_ in (h1[1:, s].reshape(T * B, H), cx[1:, s].reshape(T * B, E))], dim=1)
+            put(dec.decoder_rnn.weight_ih, g2t @ x2)
+            put(dec.decoder_rnn.weight_hh, g2t @ h2[:T].reshape(T * B, H))
+            db = dg2.sum(0)
+            put(dec.decoder_rnn.bias_ih, db)
+            put(dec.decoder_rnn.bias_hh, db.clone())
             for s, sfx in enumerate(dec._sfx()):
                 pre_m, rnn, att = getattr(dec, "prenet" + sfx), getattr(dec, "attention_rnn" + sfx), \
                     getattr(dec, "attention_layer" + sfx)
@@ -224,43 +248,39 @@ class _DecoderTF(torch.autograd.Function):
                 pre0 = _fview(sv, SL.pre0[s], T + 1, B, P)[:T].reshape(T * B, P)
                 g1t = dg1[s].t()
                 x1 = torch.cat([pre, cx[:T, s].reshape(T * B, E)], dim=1)
-                grads[rnn.weight_ih] = g1t @ x1
-                grads[rnn.weight_hh] = g1t @ h1[:T, s].reshape(T * B, H)
+                put(rnn.weight_hh, g1t @ h1[:T, s].reshape(T * B, H))
+                put(rnn.weight_ih, g1t @ x1)
                 db = dg1[s].sum(0)
-                grads[rnn.bias_ih], grads[rnn.bias_hh] = db, db.clone()
-                grads[att.query_layer.linear_layer.weight] = dq[s].t() @ h1[1:, s].reshape(T * B, H)
-                grads[att.v_weight()] = dv[s].sum(0).view(1, A)
+                put(rnn.bias_ih, db)
+                put(rnn.bias_hh, db.clone())
+                put(att.query_layer.linear_layer.weight, dq[s].t() @ h1[1:, s].reshape(T * B, H))
+                put(att.v_weight(), dv[s].sum(0).view(1, A))
                 if dec.attention_kind == LSA:
                     LF, LK = dec.loc_filters, dec.loc_kernel
-                    grads[att.location_layer.location_dense.linear_layer.weight] = \
-                        _fview(gbuf, GL.dloc_dense, S, B, A, LF)[s].sum(0)
-                    grads[att.location_layer.location_conv.conv.weight] = \
-                        _fview(gbuf, GL.dloc_conv, S, B, LF, 2, LK)[s].sum(0)
+                    put(att.location_layer.location_dense.linear_layer.weight, _fview(gbuf, GL.dloc_dense, S, B, A, LF)[s].sum(0))
+                    put(att.location_layer.location_conv.conv.weight, _fview(gbuf, GL.dloc_conv, S, B, LF, 2, LK)[s].sum(0))
                 dpm = _fview(gbuf, GL.dpm[s], B, Ts[s], A)
                 wm = att.memory_layer.linear_layer.weight
-                grads[wm] = dpm.reshape(-1, A).t() @ mems[s].reshape(-1, E)
+                put(wm, dpm.reshape(-1, A).t() @ mems[s].reshape(-1, E))
                 d_mems[s] = torch.bmm(aligns[s].transpose(1, 2), dctx[s].transpose(0, 1)) + dpm @ wm.detach()
                 # prenet: two bias-free linear + ReLU + always-on dropout layers (model.py:13-24); kept <=> output > 0
                 w0, w1 = pre_m.layers[0].linear_layer.weight, pre_m.layers[1].linear_layer.weight
                 dz1 = dpre[s].reshape(T * B, P) * 2.0 * (pre > 0)
-                grads[w1] = dz1.t() @ pre0
+                put(w1, dz1.t() @ pre0)
                 dz0 = (dz1 @ w1.detach()) * 2.0 * (pre0 > 0)
-                grads[w0] = dz0.t() @ x_frames
-            g2t = dg2.t()
-            x2 = torch.cat([t_ for s in range(S) for t_ in (h1[1:, s].reshape(T * B, H), cx[1:, s].reshape(T * B, E))], dim=1)
-            grads[dec.decoder_rnn.weight_ih] = g2t @ x2
-            grads[dec.decoder_rnn.weight_hh] = g2t @ h2[:T].reshape(T * B, H)
-            db = dg2.sum(0)
-            grads[dec.decoder_rnn.bias_ih], grads[dec.decoder_rnn.bias_hh] = db, db.clone()
+                put(w0, dz0.t() @ x_frames)
             y = torch.cat([h2[1:].reshape(T * B, H)] + [cx[1:, s].reshape(T * B, E) for s in range(S)], dim=1)
             dm = d_mel.transpose(0, 1).reshape(T * B, M)
             dgt = d_gate.t().reshape(T * B, 1)
-            grads[dec.linear_projection.linear_layer.weight] = dm.t() @ y
-            grads[dec.linear_projection.linear_layer.bias] = dm.sum(0)
-            grads[dec.gate_layer.linear_layer.weight] = dgt.t() @ y
-            grads[dec.gate_layer.linear_layer.bias] = dgt.sum(0)
+            put(dec.linear_projection.linear_layer.weight, dm.t() @ y)
+            put(dec.linear_projection.linear_layer.bias, dm.sum(0))
+            put(dec.gate_layer.linear_layer.weight, dgt.t() @ y)
+            put(dec.gate_layer.linear_layer.bias, dgt.sum(0))
         finally:
             torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        finish = getattr(dec, "_grad_ready_finish", None)
+        if finish is not None:
+            finish()          # the early all-reduces must have landed before autograd hands these tensors on
         param_grads = tuple(grads.get(p_) if p_.requires_grad else None for p_ in st["params"])
         need = ctx.needs_input_grad
         return (None, None, d_mems[0] if need[2] else None, d_mems[1] if (S == 2 and need[3]) else None, None, None, None) \

@@ -107,3 +107,93 @@ def test_shard_by_length_is_balanced_and_complete():
         assert {len(s) for s in shards} == {64 // w}
         loads = [sum(lengths[i] for i in s) for s in shards]
         assert (max(loads) - min(loads)) / max(loads) < 0.03
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# early path: a module that produces several gradients inside ONE autograd node (the decoder's hand-written BPTT)
+# publishes them one by one; large ones are averaged in place while the node is still computing the others
+# ---------------------------------------------------------------------------------------------------------------
+class _TwoGrads(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, big, small):
+        ctx.mod = mod
+        ctx.save_for_backward(x)
+        return x @ big + small.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        mod = ctx.mod
+        d_big = x.t() @ g
+        if getattr(mod, "_grad_ready", None) is not None:
+            mod._grad_ready(mod.big, d_big)           # published before the node returns
+        d_small = g.sum() * torch.ones_like(mod.small)
+        if getattr(mod, "_grad_ready", None) is not None:
+            mod._grad_ready(mod.small, d_small)       # below the size threshold: stays on the bucket path
+        if getattr(mod, "_grad_ready_finish", None) is not None:
+            mod._grad_ready_finish()
+        return None, None, d_big, d_small
+
+
+class _FakeDecoder(torch.nn.Module):
+    """Looks like the decoder to GradientBucketer (it keys on _weight_tensors / decoder_rnn)."""
+
+    def __init__(self):
+        super().__init__()
+        self.big = torch.nn.Parameter(torch.randn(16, 8))
+        self.small = torch.nn.Parameter(torch.randn(3))
+        self.decoder_rnn = torch.nn.Identity()
+
+    def _weight_tensors(self):
+        return [self.big, self.small]
+
+    def forward(self, x):
+        return _TwoGrads.apply(self, x, self.big, self.small)
+
+
+def _early_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(5)
+        net = _FakeDecoder()
+        apply_gradient_allreduce(net)
+        net._grad_bucketer.early_min_bytes = 256      # `big` (512 B) takes the early path, `small` (12 B) does not
+        out = []
+        for step in range(2):
+            torch.manual_seed(50 + step * 10 + rank)
+            x = torch.randn(4, 16)
+            net.zero_grad(set_to_none=True)
+            net(x).pow(2).sum().backward()
+            out.append((net.big.grad.numpy().copy(), net.small.grad.numpy().copy()))
+        q.put((rank, out, net._grad_bucketer.n_collectives))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_early_published_gradients_are_averaged_once():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_early_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(5)
+    ref = _FakeDecoder()
+    for step in range(2):
+        local = []
+        for rank in range(world):
+            torch.manual_seed(50 + step * 10 + rank)
+            x = torch.randn(4, 16)
+            ref.zero_grad(set_to_none=True)
+            ref(x).pow(2).sum().backward()
+            local.append((ref.big.grad.clone(), ref.small.grad.clone()))
+        for k in range(2):
+            want = (local[0][k] + local[1][k]) / 2
+            for rank in range(world):
+                assert torch.allclose(torch.from_numpy(out[rank][1][step][k]), want, atol=1e-5), (step, k, rank)
+    assert out[0][2] == 4       # per step: one early all-reduce (big) + one bucket (small)
