@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TACO2DEC_ABI_VERSION 6
+#define TACO2DEC_ABI_VERSION 7
 
 #define TACO2DEC_ATTN_SMA 0 /* StepwiseMonotonicAttention   (attention.py:291-398, hparams default) */
 #define TACO2DEC_ATTN_LSA 1 /* LocationSensitiveAttention   (attention.py:7-85)                      */
@@ -140,6 +140,8 @@ typedef struct taco2dec_tf_args {
   void* saved;        /* NULL, or a buffer of taco2dec_saved_layout_query().total bytes: the call keeps the activations
                          taco2dec_backward needs (tensor path only: 2 <= B <= 128, default dims) */
   size_t saved_bytes;
+  const float* processed_memory[2]; /* NULL, or [B, T_s, attn_dim] = memory_layer(memory) of stream s already computed by
+                         taco2dec_memprep_forward (model.py:258-261); NULL = computed inside the call */
 } taco2dec_tf_args;
 
 /* Byte offsets of the arrays inside the `saved` buffer (fp32).  State arrays have T+1 slots: slot 0 = the zero
@@ -223,6 +225,7 @@ typedef struct taco2dec_infer_args {
   int32_t* reached_max; /* [B] 1 = hit max_decoder_steps without the gate firing (INFER_FLAG = False, model.py:482-485) */
   void* workspace;
   size_t workspace_bytes;
+  const float* processed_memory[2]; /* as in taco2dec_tf_args */
 } taco2dec_infer_args;
 
 int taco2dec_abi_version(void);
@@ -337,6 +340,58 @@ size_t taco2dec_postnet_workspace_bytes(const taco2dec_postnet* h, int B, int T)
 int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stride_b, int64_t stride_c, int64_t stride_t,
                              int B, int T, const int64_t* output_lengths, int independent, float* mel_postnet,
                              void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Decoder inputs: memory = linear_converter(cat(encoder_outputs, cls_embeddings)) (model.py:548-549,
+ * 553-554) and processed_memory = memory_layer(memory) (model.py:258-261), one handle per stream.  Two chained tcgen05
+ * GEMMs over all (utterance, position) rows; every fp32 operand is split into two fp16 terms (hi + lo) and the product is
+ * evaluated as hi.hi + hi.lo + lo.hi with fp32 accumulation, so the results agree with the fp32 reference to ~1e-6
+ * relative (they feed the whole recurrence).  Inference / no-grad only.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct taco2dec_memprep taco2dec_memprep;
+/* enc_dim (512) and attn_dim (128) multiples of 128; enc_dim + cls_dim (1280) a multiple of 64. */
+int taco2dec_memprep_create(int enc_dim, int cls_dim, int attn_dim, int device, taco2dec_memprep** out);
+int taco2dec_memprep_destroy(taco2dec_memprep* h);
+/* converter_w [enc_dim, enc_dim + cls_dim], converter_b [enc_dim] (linear_converter{,_sub}.linear_layer.*),
+ * memory_w [attn_dim, enc_dim] (decoder.attention_layer{,_bert}.memory_layer.linear_layer.weight).  converter_w may be
+ * NULL: the handle then only projects an existing memory (taco2dec_memprep_project). */
+int taco2dec_memprep_set_weights(taco2dec_memprep* h, const float* converter_w, const float* converter_b, const float* memory_w,
+                                 void* cuda_stream);
+size_t taco2dec_memprep_workspace_bytes(const taco2dec_memprep* h, int n_rows);
+/* encoder_outputs [n_rows, enc_dim], cls_embeddings [n_rows, cls_dim] -> memory [n_rows, enc_dim], processed_memory
+ * [n_rows, attn_dim]; n_rows = B * T (rows of padded positions are computed like any other, as in the reference). */
+int taco2dec_memprep_forward(taco2dec_memprep* h, const float* encoder_outputs, const float* cls_embeddings, int n_rows,
+                             float* memory, float* processed_memory, void* workspace, size_t workspace_bytes, void* cuda_stream);
+/* memory [n_rows, enc_dim] -> processed_memory [n_rows, attn_dim] only. */
+int taco2dec_memprep_project(taco2dec_memprep* h, const float* memory, int n_rows, float* processed_memory, void* workspace,
+                             size_t workspace_bytes, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Tacotron2Loss + the output gradients that seed the backward pass, one sweep (reference
+ * loss_function.py:12-66): mel_loss = MSE(mel, target) + MSE(mel_postnet, target), gate_loss = BCEWithLogits(gate, target),
+ * optional alignment L2 terms (alignloss == "L2").  d_mel is written in [B, T, n_mel] order = taco2dec_bwd_args.d_mel.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct taco2dec_loss_args {
+  int B, n_mel, T;
+  const float* mel;                       /* decoder mel: element (b, c, t) at mel[b*stride_b + c*stride_c + t*stride_t] */
+  int64_t mel_stride_b, mel_stride_c, mel_stride_t;
+  const float* mel_postnet;               /* [B, n_mel, T] */
+  const float* gate;                      /* [B, T] logits */
+  const float* mel_target;                /* [B, n_mel, T] */
+  const float* gate_target;               /* [B, T] */
+  const float* align[2];                  /* NULL, or [B, T, T_align[s]] (char / sub-word stream) */
+  const float* align_target[2];
+  int T_align[2];
+  float* d_mel;                           /* [B, T, n_mel]   d loss / d mel (the direct MSE term only) */
+  float* d_mel_postnet;                   /* [B, n_mel, T] */
+  float* d_gate;                          /* [B, T] */
+  float* d_align[2];                      /* [B, T, T_align[s]] when align[s] is given */
+  float* losses;                          /* device [5]: total, mel_loss, gate_loss, align_loss, align_bert_loss */
+  void* workspace;
+  size_t workspace_bytes;
+} taco2dec_loss_args;
+size_t taco2dec_loss_workspace_bytes(int B, int n_mel, int T);
+int taco2dec_loss_forward(const taco2dec_loss_args* a, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -211,8 +211,62 @@ def run_reference_postnet(seed: int = 21, B: int = 3, T: int = 37):
     return {"x": x.numpy(), "y": y.numpy(), "seed": np.array(seed)}
 
 
+def run_reference_memprep(seed: int = 31, B: int = 2, T: int = 9):
+    """The reference's own modules for the decoder-input step: layers.LinearNorm wired as model.py:548-549 (linear_converter
+    over cat(encoder_outputs, cls)) and as model.py:258-261 (the attention layer's memory_layer), on seeded weights."""
+    from oracle.memprep_oracle import make_memprep_inputs, make_memprep_weights
+    ref_shim.import_reference()
+    import layers as ref_layers
+    w = make_memprep_weights(seed)
+    conv = ref_layers.LinearNorm(512 + 768, 512)
+    meml = ref_layers.LinearNorm(512, 128, bias=False, w_init_gain="tanh")
+    conv.load_state_dict({"linear_layer.weight": w["linear_converter.linear_layer.weight"],
+                          "linear_layer.bias": w["linear_converter.linear_layer.bias"]}, strict=True)
+    meml.load_state_dict({"linear_layer.weight": w["memory_layer.linear_layer.weight"]}, strict=True)
+    enc, cls = make_memprep_inputs(B, T, seed + 1)
+    with torch.no_grad():
+        memory = conv(torch.cat([enc, cls], 2))
+        pm = meml(memory)
+    return {"memory": memory.numpy(), "processed_memory": pm.numpy(), "seed": np.array(seed), "B": np.array(B), "T": np.array(T)}
+
+
+def run_reference_loss(alignloss: str, seed: int = 61, B: int = 3, T: int = 21, T_in: int = 13):
+    """Unmodified reference Tacotron2Loss (loss_function.py:7-66) + torch.autograd on a seeded case: loss terms and, per
+    output, max|g|, sum(g) and the first 16 elements of d total / d output."""
+    from oracle.loss_oracle import make_loss_case
+    ref_shim.import_reference()
+    sys.path.insert(0, ref_shim.REFERENCE_ROOT)
+    try:
+        import loss_function as ref_loss
+    finally:
+        sys.path.remove(ref_shim.REFERENCE_ROOT)
+    c = make_loss_case(B, T, T_in, seed)
+    outs = [c[k].clone().requires_grad_(True) for k in ("mel", "mel_postnet", "gate", "align", "align_bert")]
+    targets = (c["mel_target"].clone(), c["gate_target"].clone(), c["align_target"].clone())
+    total, mel_loss, gate_loss, al, alb = ref_loss.Tacotron2Loss(alignloss)(outs, targets, None, 0)
+    total.backward()
+    res = {"total": total.detach().numpy(), "mel_loss": mel_loss.detach().numpy(), "gate_loss": gate_loss.detach().numpy(),
+           "align_loss": np.array(float("nan") if al is None else float(al)), "align_bert_loss": np.array(float("nan") if alb is None else float(alb)),
+           "alignloss": np.array(alignloss), "seed": np.array(seed), "B": np.array(B), "T": np.array(T), "T_in": np.array(T_in)}
+    for k, o in zip(("mel", "mel_postnet", "gate", "align", "align_bert"), outs):
+        if o.grad is None:
+            continue
+        g = o.grad
+        res[f"g_{k}/max"] = g.abs().max().numpy()
+        res[f"g_{k}/sum"] = g.double().sum().numpy()
+        res[f"g_{k}/head"] = g.reshape(-1)[:16].numpy()
+    return res
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for al in ("", "L2"):
+        res = run_reference_loss(al)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"loss_{al or 'default'}.npz"), **res)
+        print(f"loss_{al or 'default'}: total {float(res['total']):.6f}")
+    res = run_reference_memprep()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "memprep.npz"), **res)
+    print(f"memprep: memory{res['memory'].shape}")
     res = run_reference_postnet()
     np.savez_compressed(os.path.join(GOLDEN_DIR, "postnet_eval.npz"), **res)
     print(f"postnet_eval: y{res['y'].shape}")

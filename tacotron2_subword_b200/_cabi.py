@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtac
 ATTN_SMA, ATTN_LSA = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR, PATH_TENSOR_GRAPH = 0, 1, 2, 3, 4
 W_FP32, W_FP16 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 EXPORTED_SYMBOLS = (
     "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = (
     "taco2dec_postnet_create", "taco2dec_postnet_destroy", "taco2dec_postnet_set_weights",
     "taco2dec_postnet_workspace_bytes", "taco2dec_postnet_forward",
     "taco2dec_set_batched_precision", "taco2dec_poll_abort", "taco2dec_read_debug_stamps", "taco2dec_measure_machine",
+    "taco2dec_memprep_create", "taco2dec_memprep_destroy", "taco2dec_memprep_set_weights", "taco2dec_memprep_workspace_bytes",
+    "taco2dec_memprep_forward", "taco2dec_memprep_project", "taco2dec_loss_workspace_bytes", "taco2dec_loss_forward",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -60,7 +62,7 @@ class TFArgs(C.Structure):
                 ("memory_lengths", _fp), ("bert_lengths", _fp), ("training", C.c_int), ("rng", Rng),
                 ("mel", _fp), ("gate", _fp), ("align", _fp), ("align_bert", _fp),
                 ("workspace", _fp), ("workspace_bytes", C.c_size_t),
-                ("independent", C.c_int), ("saved", _fp), ("saved_bytes", C.c_size_t)]
+                ("independent", C.c_int), ("saved", _fp), ("saved_bytes", C.c_size_t), ("processed_memory", _fp * 2)]
 
 
 class SavedLayout(C.Structure):
@@ -98,7 +100,16 @@ class InferArgs(C.Structure):
                 ("gate_threshold", C.c_float), ("memory", _fp), ("embeddings", _fp),
                 ("memory_lengths", _fp), ("bert_lengths", _fp), ("rng", Rng),
                 ("mel", _fp), ("gate", _fp), ("align", _fp), ("align_bert", _fp),
-                ("n_frames", _fp), ("reached_max", _fp), ("workspace", _fp), ("workspace_bytes", C.c_size_t)]
+                ("n_frames", _fp), ("reached_max", _fp), ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+                ("processed_memory", _fp * 2)]
+
+
+class LossArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("n_mel", C.c_int), ("T", C.c_int), ("mel", _fp), ("mel_stride_b", C.c_int64),
+                ("mel_stride_c", C.c_int64), ("mel_stride_t", C.c_int64), ("mel_postnet", _fp), ("gate", _fp),
+                ("mel_target", _fp), ("gate_target", _fp), ("align", _fp * 2), ("align_target", _fp * 2), ("T_align", C.c_int * 2),
+                ("d_mel", _fp), ("d_mel_postnet", _fp), ("d_gate", _fp), ("d_align", _fp * 2), ("losses", _fp),
+                ("workspace", _fp), ("workspace_bytes", C.c_size_t)]
 
 
 class Taco2DecError(RuntimeError):
@@ -172,6 +183,22 @@ def load_library() -> C.CDLL:
     lib.taco2dec_read_debug_stamps.argtypes = [H, C.c_void_p, C.POINTER(C.c_longlong)]
     lib.taco2dec_measure_machine.restype = C.c_int
     lib.taco2dec_measure_machine.argtypes = [H, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.taco2dec_memprep_create.restype = C.c_int
+    lib.taco2dec_memprep_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    lib.taco2dec_memprep_destroy.restype = C.c_int
+    lib.taco2dec_memprep_destroy.argtypes = [H]
+    lib.taco2dec_memprep_set_weights.restype = C.c_int
+    lib.taco2dec_memprep_set_weights.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.taco2dec_memprep_workspace_bytes.restype = C.c_size_t
+    lib.taco2dec_memprep_workspace_bytes.argtypes = [H, C.c_int]
+    lib.taco2dec_memprep_forward.restype = C.c_int
+    lib.taco2dec_memprep_forward.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.taco2dec_memprep_project.restype = C.c_int
+    lib.taco2dec_memprep_project.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.taco2dec_loss_workspace_bytes.restype = C.c_size_t
+    lib.taco2dec_loss_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.taco2dec_loss_forward.restype = C.c_int
+    lib.taco2dec_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p]
     lib.taco2dec_poll_abort.restype = C.c_int
     lib.taco2dec_poll_abort.argtypes = [H]
     lib.taco2dec_last_path.restype = C.c_int

@@ -781,6 +781,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
 #include "backward.cuh"
 #include "postnet.cuh"
 #include "persist.cuh"
+#include "memprep.cuh"
+#include "loss.cuh"
 
 // ------------------------------------------------------------------------------------------
 // One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
@@ -915,6 +917,7 @@ struct taco2dec_handle {
   bool pb_alloc, pb_tiles_valid;
   unsigned char* pb_xpre; size_t pb_xpre_bytes;
   long long* pb_dbg;
+  const float* pm_given[2];   // processed memory supplied by the caller for the current call (else null)
   bw::Bufs bw_bufs;      // backward pass: transposed bf16 weight tiles, gate-gradient tiles, GEMM partials
   bool bw_alloc, bw_tiles_valid;
   int* bw_ctl;           // device word: frame counter of the backward graph
@@ -1671,6 +1674,10 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
   // processed memory, once per call (model.py:258-261)
   for (int s = 0; s < c.n_streams; ++s) {
     const int n_rows = p.B * p.st[s].Ts;
+    if (h->pm_given[s]) {      // already computed upstream (taco2dec_memprep_forward): one copy into the call's layout
+      CUDA_TRY(cudaMemcpyAsync(p.st[s].pm, h->pm_given[s], (size_t)n_rows * c.attn_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
     const int blocks = std::min((n_rows + 7) / 8, h->num_sms * 8);
     processed_memory_kernel<<<blocks, 256, 0, st>>>(p.st[s].mem, p.st[s].wm, p.st[s].pm, n_rows, c.enc_dim, c.attn_dim);
     h->launches++;
@@ -1808,7 +1815,7 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   h->ll_buf = nullptr; h->ll_bytes = 0; h->last_path = 0;
   memset(&h->bt_bufs, 0, sizeof(h->bt_bufs)); h->bt_alloc = false; h->bt_tiles_valid = false; h->cap_stream = nullptr;
   memset(&h->cur_sv, 0, sizeof(h->cur_sv));
-  memset(&h->pb, 0, sizeof(h->pb)); h->pb_alloc = false; h->pb_tiles_valid = false; h->pb_xpre = nullptr; h->pb_xpre_bytes = 0; h->pb_dbg = nullptr;
+  memset(&h->pb, 0, sizeof(h->pb)); h->pb_alloc = false; h->pb_tiles_valid = false; h->pb_xpre = nullptr; h->pb_xpre_bytes = 0; h->pb_dbg = nullptr; h->pm_given[0] = h->pm_given[1] = nullptr;
   memset(&h->bw_bufs, 0, sizeof(h->bw_bufs)); h->bw_alloc = false; h->bw_tiles_valid = false; h->bw_ctl = nullptr;
   h->profiling = false;
   h->ev_valid = false;
@@ -1992,7 +1999,9 @@ int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* 
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  h->pm_given[0] = a->processed_memory[0]; h->pm_given[1] = c.n_streams == 2 ? a->processed_memory[1] : nullptr;
   const int rc = run_common(h, p, a->T_in, std::max(a->T_sub, 1), ws, L, st);
+  h->pm_given[0] = h->pm_given[1] = nullptr;
   memset(&h->cur_sv, 0, sizeof(h->cur_sv));
   return rc;
 }
@@ -2096,7 +2105,10 @@ int taco2dec_infer(taco2dec_handle* h, const taco2dec_infer_args* a, void* cuda_
   p.st[0].align = a->align;
   if (c.n_streams == 2) p.st[1].align = a->align_bert;
   p.n_frames = a->n_frames; p.reached_max = a->reached_max;
-  return run_common(h, p, a->T_in, std::max(a->T_sub, 1), ws, L, st);
+  h->pm_given[0] = a->processed_memory[0]; h->pm_given[1] = c.n_streams == 2 ? a->processed_memory[1] : nullptr;
+  const int rc = run_common(h, p, a->T_in, std::max(a->T_sub, 1), ws, L, st);
+  h->pm_given[0] = h->pm_given[1] = nullptr;
+  return rc;
 }
 
 int taco2dec_check(taco2dec_handle* h, void* cuda_stream) {
@@ -2223,6 +2235,209 @@ extern "C" int taco2dec_measure_machine(taco2dec_handle* h, void* cuda_stream, d
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(buf); cudaFree(sink); cudaFree(words);
   h->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Decoder inputs (memprep.cuh)
+// ------------------------------------------------------------------------------------------
+struct taco2dec_memprep {
+  int device, num_sms, enc, cls, attn;
+  bool have_conv, have_mem;
+  unsigned char *a1, *a2;     // split-fp16 weight tiles: converter [enc/128][3 (enc+cls)/64], memory layer [attn/128][3 enc/64]
+  float* bias;                // [enc]
+  int64_t launches;
+};
+
+namespace {
+struct MpPlan { int groups, n_pad, sp1, sp2; size_t x1, part1, x2, part2, total; };
+MpPlan mp_plan(const taco2dec_memprep* h, int n_rows) {
+  MpPlan pl;
+  pl.groups = (n_rows + mp::kNP - 1) / mp::kNP;
+  pl.n_pad = pl.groups * mp::kNP;
+  const size_t k1 = 3 * (size_t)(h->enc + h->cls), k2 = 3 * (size_t)h->enc;
+  // split K only as far as it takes to give every SM a CTA (small inputs: one utterance is 2 groups)
+  pl.sp1 = mp::pick_splits(h->enc / tc::kBlockM * pl.groups, (int)(k1 / tc::kBlockK), h->num_sms);
+  pl.sp2 = mp::pick_splits(h->attn / tc::kBlockM * pl.groups, (int)(k2 / tc::kBlockK), h->num_sms);
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+  pl.x1 = take((size_t)pl.n_pad * k1 * 2);
+  pl.part1 = take((size_t)pl.groups * pl.sp1 * h->enc * mp::kNP * sizeof(float));
+  pl.x2 = take((size_t)pl.n_pad * k2 * 2);
+  pl.part2 = take((size_t)pl.groups * pl.sp2 * h->attn * mp::kNP * sizeof(float));
+  pl.total = off;
+  return pl;
+}
+int mp_project_impl(taco2dec_memprep* h, const MpPlan& pl, int n_rows, float* pm, char* ws, cudaStream_t st) {
+  const int kb2 = 3 * h->enc / tc::kBlockK;
+  const int sp2 = pl.sp2;
+  float* part2 = (float*)(ws + pl.part2);
+  tc::GemmParams g2{h->a2, (unsigned char*)(ws + pl.x2), part2, h->attn, 3 * h->enc, sp2, pl.groups, (long long)kb2 * mp::kNP * 128, 0, 0, nullptr, 0};
+  g2.a_shared = 1;
+  CUDA_TRY(tc::launch_gemm<mp::kNP>(g2, st));
+  mp::mp_finish_kernel<<<dim3(pl.groups, h->attn / 32), 256, 0, st>>>(part2, sp2, h->attn, nullptr, n_rows, pm, nullptr);
+  h->launches += 2;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int taco2dec_memprep_create(int enc_dim, int cls_dim, int attn_dim, int device, taco2dec_memprep** out) {
+  if (!out) return fail(TACO2DEC_E_ARG, "null argument");
+  if (enc_dim < 128 || enc_dim % 128 || attn_dim < 128 || attn_dim % 128 || cls_dim < 0 || (enc_dim + cls_dim) % 64)
+    return fail(TACO2DEC_E_ARG, "memprep needs enc_dim and attn_dim multiples of 128 and enc_dim + cls_dim a multiple of 64");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(TACO2DEC_E_ARCH, "this library is built for sm_100a (B200) only and has no fallback");
+  taco2dec_memprep* h = new (std::nothrow) taco2dec_memprep();
+  if (!h) return fail(TACO2DEC_E_STATE, "out of host memory");
+  h->device = device; h->num_sms = prop.multiProcessorCount; h->enc = enc_dim; h->cls = cls_dim; h->attn = attn_dim;
+  h->have_conv = h->have_mem = false; h->launches = 0;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMalloc(&h->a1, (size_t)enc_dim * 3 * (enc_dim + cls_dim) * 2));
+  CUDA_TRY(cudaMalloc(&h->a2, (size_t)attn_dim * 3 * enc_dim * 2));
+  CUDA_TRY(cudaMalloc(&h->bias, (size_t)enc_dim * sizeof(float)));
+  *out = h;
+  return 0;
+}
+
+int taco2dec_memprep_destroy(taco2dec_memprep* h) {
+  if (h) { cudaFree(h->a1); cudaFree(h->a2); cudaFree(h->bias); }
+  delete h;
+  return 0;
+}
+
+int taco2dec_memprep_set_weights(taco2dec_memprep* h, const float* converter_w, const float* converter_b, const float* memory_w,
+                                 void* cuda_stream) {
+  if (!h || !memory_w) return fail(TACO2DEC_E_ARG, "null argument");
+  if ((converter_w == nullptr) != (converter_b == nullptr)) return fail(TACO2DEC_E_ARG, "converter weight and bias go together");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (converter_w) {
+    mp::mp_pack_weights<<<1024, 256, 0, st>>>(converter_w, h->enc, h->enc + h->cls, h->enc, h->a1);
+    CUDA_TRY(cudaMemcpyAsync(h->bias, converter_b, (size_t)h->enc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    h->launches++;
+  }
+  mp::mp_pack_weights<<<256, 256, 0, st>>>(memory_w, h->attn, h->enc, h->attn, h->a2);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  h->have_conv = converter_w != nullptr;
+  h->have_mem = true;
+  return 0;
+}
+
+size_t taco2dec_memprep_workspace_bytes(const taco2dec_memprep* h, int n_rows) {
+  if (!h || n_rows < 1) return 0;
+  return mp_plan(h, n_rows).total;
+}
+
+int taco2dec_memprep_forward(taco2dec_memprep* h, const float* encoder_outputs, const float* cls_embeddings, int n_rows,
+                             float* memory, float* processed_memory, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!h || !encoder_outputs || !memory || !processed_memory || !workspace) return fail(TACO2DEC_E_ARG, "null argument");
+  if (h->cls > 0 && !cls_embeddings) return fail(TACO2DEC_E_ARG, "cls_embeddings missing");
+  if (!h->have_conv || !h->have_mem) return fail(TACO2DEC_E_STATE, "weights not set");
+  if (n_rows < 1) return fail(TACO2DEC_E_ARG, "n_rows must be >= 1");
+  if ((reinterpret_cast<uintptr_t>(encoder_outputs) | reinterpret_cast<uintptr_t>(cls_embeddings) | reinterpret_cast<uintptr_t>(memory) |
+       reinterpret_cast<uintptr_t>(processed_memory)) & 15u)
+    return fail(TACO2DEC_E_ARG, "tensors must be 16-byte aligned");
+  const MpPlan pl = mp_plan(h, n_rows);
+  if (workspace_bytes < pl.total) return fail(TACO2DEC_E_STATE, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(TACO2DEC_E_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  char* ws = (char*)workspace;
+  CUDA_TRY(tc::prepare_gemm<mp::kNP>());
+  const int K1 = h->enc + h->cls, kb1 = 3 * K1 / tc::kBlockK;
+  {
+    const size_t total = (size_t)pl.n_pad * (K1 / 8);
+    mp::mp_input_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 65535), 256, 0, st>>>(encoder_outputs, h->enc, cls_embeddings, h->cls,
+                                                                                               n_rows, pl.n_pad, (unsigned char*)(ws + pl.x1));
+  }
+  const int sp1 = pl.sp1;
+  float* part1 = (float*)(ws + pl.part1);
+  tc::GemmParams g1{h->a1, (unsigned char*)(ws + pl.x1), part1, h->enc, 3 * K1, sp1, pl.groups, (long long)kb1 * mp::kNP * 128, 0, 0, nullptr, 0};
+  g1.a_shared = 1;
+  CUDA_TRY(tc::launch_gemm<mp::kNP>(g1, st));
+  mp::mp_finish_kernel<<<dim3(pl.groups, h->enc / 32), 256, 0, st>>>(part1, sp1, h->enc, h->bias, n_rows, memory, (unsigned char*)(ws + pl.x2));
+  h->launches += 3;
+  if (int rc = mp_project_impl(h, pl, n_rows, processed_memory, ws, st)) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int taco2dec_memprep_project(taco2dec_memprep* h, const float* memory, int n_rows, float* processed_memory, void* workspace,
+                             size_t workspace_bytes, void* cuda_stream) {
+  if (!h || !memory || !processed_memory || !workspace) return fail(TACO2DEC_E_ARG, "null argument");
+  if (!h->have_mem) return fail(TACO2DEC_E_STATE, "weights not set");
+  if (n_rows < 1) return fail(TACO2DEC_E_ARG, "n_rows must be >= 1");
+  const MpPlan pl = mp_plan(h, n_rows);
+  if (workspace_bytes < pl.total) return fail(TACO2DEC_E_STATE, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(TACO2DEC_E_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  char* ws = (char*)workspace;
+  CUDA_TRY(tc::prepare_gemm<mp::kNP>());
+  const size_t total = (size_t)pl.n_pad * (h->enc / 8);
+  mp::mp_memory_operand_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 65535), 256, 0, st>>>(memory, h->enc, n_rows, pl.n_pad,
+                                                                                                      (unsigned char*)(ws + pl.x2));
+  h->launches++;
+  if (int rc = mp_project_impl(h, pl, n_rows, processed_memory, ws, st)) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------
+// Loss + gradient seeding (loss.cuh)
+// ------------------------------------------------------------------------------------------
+extern "C" size_t taco2dec_loss_workspace_bytes(int B, int n_mel, int T) {
+  if (B < 1 || n_mel < 1 || T < 1) return 0;
+  const size_t mel_blocks = (size_t)B * ((T + ls::kTT - 1) / ls::kTT);
+  return align_up((2 * mel_blocks + 3 * 1024) * sizeof(float), 256);
+}
+
+extern "C" int taco2dec_loss_forward(const taco2dec_loss_args* a, void* cuda_stream) {
+  if (!a) return fail(TACO2DEC_E_ARG, "null argument");
+  if (a->B < 1 || a->n_mel < 1 || a->T < 1) return fail(TACO2DEC_E_ARG, "B, n_mel, T must be >= 1");
+  if (!a->mel || !a->mel_postnet || !a->gate || !a->mel_target || !a->gate_target || !a->d_mel || !a->d_mel_postnet || !a->d_gate ||
+      !a->losses || !a->workspace)
+    return fail(TACO2DEC_E_ARG, "null tensor pointer");
+  for (int s = 0; s < 2; ++s)
+    if (a->align[s] && (!a->align_target[s] || !a->d_align[s] || a->T_align[s] < 1))
+      return fail(TACO2DEC_E_ARG, "alignment loss needs a target, a gradient buffer and its width");
+  if (a->workspace_bytes < taco2dec_loss_workspace_bytes(a->B, a->n_mel, a->T)) return fail(TACO2DEC_E_STATE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int mel_blocks = a->B * ((a->T + ls::kTT - 1) / ls::kTT);
+  float* part_mel = (float*)a->workspace;
+  float* part_gate = part_mel + 2 * (size_t)mel_blocks;
+  float* part_al[2] = {part_gate + 1024, part_gate + 2048};
+  const double n_mel_el = (double)a->B * a->n_mel * a->T, n_gate_el = (double)a->B * a->T;
+  const size_t smem = (size_t)a->n_mel * (ls::kTT + 1) * sizeof(float);
+  ls::ls_mel_kernel<<<mel_blocks, 256, smem, st>>>(a->mel, a->mel_stride_b, a->mel_stride_c, a->mel_stride_t, a->mel_postnet, a->mel_target,
+                                                   a->B, a->n_mel, a->T, (float)(1.0 / n_mel_el), a->d_mel, a->d_mel_postnet, part_mel);
+  const int gate_blocks = (int)std::min<size_t>(1024, ((size_t)a->B * a->T + 255) / 256);
+  ls::ls_gate_kernel<<<gate_blocks, 256, 0, st>>>(a->gate, a->gate_target, a->B * a->T, (float)(1.0 / n_gate_el), a->d_gate, part_gate);
+  ls::ReduceArgs r;
+  memset(&r, 0, sizeof(r));
+  int al_blocks[2] = {0, 0};
+  double inv_al[2] = {0, 0};
+  for (int s = 0; s < 2; ++s) {
+    if (!a->align[s]) continue;
+    const size_t n = (size_t)a->B * a->T * a->T_align[s];
+    al_blocks[s] = (int)std::min<size_t>(1024, (n + 255) / 256);
+    inv_al[s] = 1.0 / (double)n;
+    ls::ls_mse_kernel<<<al_blocks[s], 256, 0, st>>>(a->align[s], a->align_target[s], n, (float)inv_al[s], a->d_align[s], part_al[s]);
+  }
+  r.mel_part = part_mel; r.gate_part = part_gate; r.al_part = part_al[0]; r.alb_part = part_al[1];
+  r.n_mel_blocks = mel_blocks; r.n_gate_blocks = gate_blocks; r.n_al_blocks = al_blocks[0]; r.n_alb_blocks = al_blocks[1];
+  r.inv_mel = 1.0 / n_mel_el; r.inv_gate = 1.0 / n_gate_el; r.inv_al = inv_al[0]; r.inv_alb = inv_al[1];
+  r.losses = a->losses;
+  ls::ls_reduce_kernel<<<1, 256, 0, st>>>(r);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

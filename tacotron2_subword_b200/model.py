@@ -346,6 +346,7 @@ class Decoder(nn.Module):
         self.dropout_replay: Optional[DropoutReplay] = None  # parity runs: externally drawn masks
         self.rng_seed: Optional[int] = None                  # fixed Philox seed; None = fresh per call
         self.validate_lengths = True
+        self._pm_hint = None            # (memory ptr, processed memory) pairs from MemoryPrep, consumed by the next call
         self.grad_gemm_tf32: Optional[bool] = None   # weight-gradient GEMMs in TF32; None = only with weight_dtype "fp16"
         self._engines = {}
 
@@ -387,6 +388,23 @@ class Decoder(nn.Module):
                self.linear_projection.linear_layer.weight, self.linear_projection.linear_layer.bias,
                self.gate_layer.linear_layer.weight, self.gate_layer.linear_layer.bias]
         return ts
+
+    def set_processed_memory(self, memory, pm, embeddings=None, pm_bert=None) -> None:
+        """Hand the next decoder call the processed memory that ``MemoryPrep`` already computed for exactly these tensors
+        (``memory_layer(memory)``, model.py:258-261); ignored unless the call receives the same storage."""
+        self._pm_hint = [(memory.data_ptr(), tuple(memory.shape[:2]), pm),
+                         None if embeddings is None else (embeddings.data_ptr(), tuple(embeddings.shape[:2]), pm_bert)]
+
+    def _take_pm_hint(self, mem, emb):
+        hint, self._pm_hint = self._pm_hint, None
+        out = [None, None]
+        if hint is None:
+            return out
+        for i, t in enumerate((mem, emb)):
+            h = hint[i] if i < len(hint) else None
+            if t is not None and h is not None and h[0] == t.data_ptr() and h[1] == tuple(t.shape[:2]) and h[2].is_contiguous():
+                out[i] = h[2]
+        return out
 
     def invalidate_weights(self) -> None:
         """Force the library-owned weight re-layouts (latency-path streams, fp16 / bf16 tiles) to be rebuilt on the next
@@ -548,6 +566,10 @@ class Decoder(nn.Module):
         a.rng = self._rng(dev, keep)
         a.mel, a.gate, a.align, a.align_bert = _ptr(mel), _ptr(gate), _ptr(align), _ptr(align_b)
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        pm_given = self._take_pm_hint(mem, emb)
+        for i in range(2):
+            a.processed_memory[i] = None if pm_given[i] is None else pm_given[i].data_ptr()
+        keep.append(pm_given)
         state = None
         if save:
             SL = _cabi.SavedLayout()
@@ -598,6 +620,9 @@ class Decoder(nn.Module):
         a.mel, a.gate, a.align, a.align_bert = _ptr(mel), _ptr(gate), _ptr(align), _ptr(align_b)
         a.n_frames, a.reached_max = _ptr(n_frames), _ptr(reached)
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        pm_given = self._take_pm_hint(mem, emb)
+        for i in range(2):
+            a.processed_memory[i] = None if pm_given[i] is None else pm_given[i].data_ptr()
         with torch.cuda.device(dev):
             self._bind_weights(eng)
             stream = torch.cuda.current_stream(dev)
@@ -725,6 +750,64 @@ class Postnet(nn.Module):
             pass
 
 
+class MemoryPrep:
+    """Decoder inputs on the GPU path: ``memory = linear_converter(cat(encoder_outputs, cls))``
+    (model.py:548-549 / 553-554) and ``processed_memory = memory_layer(memory)`` (model.py:258-261) as two chained tcgen05
+    GEMMs with split-fp16 operands (fp32-grade results, ``taco2dec_memprep_*``).  Inference / no-grad only; one instance
+    per stream.  The modules keep owning the parameters (state_dict layout unchanged)."""
+
+    def __init__(self, converter: LinearNorm, memory_layer: LinearNorm):
+        self.converter, self.memory_layer = converter, memory_layer
+        self._h = {}           # device index -> {"h": handle, "key": weights key, "ws": workspace}
+
+    def usable(self, enc: torch.Tensor, cls: torch.Tensor) -> bool:
+        w = self.converter.linear_layer.weight
+        e, c, a = enc.shape[-1], cls.shape[-1], self.memory_layer.linear_layer.weight.shape[0]
+        return (enc.is_cuda and enc.dtype == torch.float32 and cls.dtype == torch.float32 and e % 128 == 0 and a % 128 == 0
+                and (e + c) % 64 == 0 and w.shape == (e, e + c) and self.converter.linear_layer.bias is not None
+                and not (torch.is_grad_enabled() and (enc.requires_grad or cls.requires_grad or w.requires_grad)))
+
+    def __call__(self, enc: torch.Tensor, cls: torch.Tensor):
+        """enc [B,T,enc_dim], cls [B,T,cls_dim] -> (memory [B,T,enc_dim], processed_memory [B,T,attn_dim])."""
+        lib = _cabi.load_library()
+        dev = enc.device
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        wc, bc, wm = self.converter.linear_layer.weight, self.converter.linear_layer.bias, self.memory_layer.linear_layer.weight
+        B, T, E = enc.shape
+        ent = self._h.get(key)
+        if ent is None:
+            h = C.c_void_p()
+            _cabi.check(lib.taco2dec_memprep_create(E, cls.shape[-1], wm.shape[0], key, C.byref(h)))
+            ent = self._h[key] = {"h": h, "key": None, "ws": None}
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            wkey = tuple((t.data_ptr(), t._version) for t in (wc, bc, wm))
+            if wkey != ent["key"]:
+                for t in (wc, bc, wm):
+                    if t.dtype != torch.float32 or not t.is_contiguous():
+                        raise _cabi.Taco2DecError("converter / memory-layer parameters must be contiguous fp32")
+                _cabi.check(lib.taco2dec_memprep_set_weights(ent["h"], _ptr(wc.detach()), _ptr(bc.detach()), _ptr(wm.detach()), stream))
+                ent["key"] = wkey
+            n = B * T
+            need = int(lib.taco2dec_memprep_workspace_bytes(ent["h"], n))
+            if ent["ws"] is None or ent["ws"].numel() < need:
+                ent["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+            enc_c, cls_c = enc.detach().contiguous(), cls.detach().contiguous()
+            memory = torch.empty(B, T, E, device=dev)
+            pm = torch.empty(B, T, wm.shape[0], device=dev)
+            _cabi.check(lib.taco2dec_memprep_forward(ent["h"], _ptr(enc_c), _ptr(cls_c), n, _ptr(memory), _ptr(pm), _ptr(ent["ws"]),
+                                                     ent["ws"].numel(), stream))
+        return memory, pm
+
+    def __del__(self):
+        try:
+            lib = _cabi.load_library()
+            for ent in self._h.values():
+                lib.taco2dec_memprep_destroy(ent["h"])
+        except Exception:
+            pass
+
+
 class Encoder(nn.Module):
     """model.py:73-125: 3x (conv1d k=5 + BatchNorm + ReLU + dropout) then a BiLSTM."""
 
@@ -810,6 +893,24 @@ class BERT_Tacotron2(nn.Module):
                                                hp.encoder_embedding_dim)
         self.decoder = Decoder(hp)
         self.postnet = Postnet(hp)
+        # extension: decoder inputs through the CUDA path when no gradient is needed (plain attributes, not sub-modules)
+        self.fused_memory = True
+        object.__setattr__(self, "_memprep", None)
+
+    def _convert(self, enc, pcls, enc_s, bcls):
+        """(memory, memory_sub) = the two linear converters (model.py:548-549, 553-554).  Without autograd on a CUDA device the
+        converter and the attention layers' memory_layer run as chained tcgen05 GEMMs and the processed memories are handed
+        to the decoder's next call; otherwise the reference's PyTorch modules run."""
+        if self._memprep is None:
+            object.__setattr__(self, "_memprep", (MemoryPrep(self.linear_converter, self.decoder.attention_layer.memory_layer),
+                                                  MemoryPrep(self.linear_converter_sub, self.decoder.attention_layer_bert.memory_layer)))
+        mp0, mp1 = self._memprep
+        if self.fused_memory and mp0.usable(enc, pcls) and mp1.usable(enc_s, bcls):
+            mem, pm = mp0(enc, pcls)
+            mem_s, pm_s = mp1(enc_s, bcls)
+            self.decoder.set_processed_memory(mem, pm, mem_s, pm_s)
+            return mem, mem_s
+        return self.linear_converter(torch.cat([enc, pcls], 2)), self.linear_converter_sub(torch.cat([enc_s, bcls], 2))
 
     def parse_batch(self, batch):
         (text_padded, input_lengths, input_lengths_bert, mel_padded, gate_padded, output_lengths, embeddings,
@@ -837,9 +938,7 @@ class BERT_Tacotron2(nn.Module):
             enc, enc_s = self.encoder.inference(e), self.encoder_sub.inference(es)
         else:
             enc, enc_s = self.encoder(e, text_lengths), self.encoder_sub(es, bert_lengths)
-        mem = self.linear_converter(torch.cat([enc, pcls], 2))          # model.py:548-549
-        mem_s = self.linear_converter_sub(torch.cat([enc_s, bcls], 2))  # model.py:553-554
-        return mem, mem_s
+        return self._convert(enc, pcls, enc_s, bcls)                    # model.py:548-549, 553-554
 
     def forward(self, inputs):
         (text_inputs, text_lengths, bert_lengths, mels, _max_lens, output_lengths, embeddings,
@@ -883,8 +982,7 @@ class BERT_Tacotron2(nn.Module):
         text, sub = pad(inputs, torch.int64), pad(embeddings, torch.int64)
         enc = self.encoder.inference_independent(self.embedding(text).transpose(1, 2), mlen)
         enc_s = self.encoder_sub.inference_independent(self.embedding_sub(sub).transpose(1, 2), blen)
-        mem = self.linear_converter(torch.cat([enc, pad(phoneme_embeddings_cls)], 2))          # model.py:548-549
-        mem_s = self.linear_converter_sub(torch.cat([enc_s, pad(bert_embeddings_cls)], 2))     # model.py:553-554
+        mem, mem_s = self._convert(enc, pad(phoneme_embeddings_cls), enc_s, pad(bert_embeddings_cls))   # model.py:548-549, 553-554
         mel, gate, align, align_b, n_frames, reached = self.decoder.inference_batched(mem, mem_s, mlen, blen, max_decoder_steps)
         mel_post = self.postnet.mel_postnet(mel, n_frames.to(torch.int64), independent=True)
         nf, rm = n_frames.tolist(), reached.tolist()

@@ -15,7 +15,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith(".npz") and not f.startswith(("grad_", "postnet_")))
+                  if f.endswith(".npz") and not f.startswith(("grad_", "postnet_", "memprep", "loss_")))
 
 
 def grad_golden_names():
