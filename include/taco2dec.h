@@ -306,8 +306,8 @@ int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* bl
 /* ---------------------------------------------------------------------------------------------------------
  * Postnet, eval mode: replaces Postnet.forward (model.py:27-70) + the residual add
  * (model.py:557-558) + the output mask (model.py:531-541) when the module is not training.  Five Conv1d(k=5) +
- * BatchNorm1d (running statistics, folded into the weights at set_weights) + tanh; fp16 operands on tcgen05, fp32
- * accumulation.  Training mode (batch statistics, dropout, backward) stays with the reference's PyTorch modules.
+ * BatchNorm1d (running statistics, folded into the weights at set_weights) + tanh on tcgen05, fp32 accumulation, operands
+ * as split fp16 pairs by default (see taco2dec_postnet_set_precision).  Training mode (batch statistics, dropout, backward) stays with the reference's PyTorch modules.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct taco2dec_postnet taco2dec_postnet;
 
@@ -329,6 +329,10 @@ typedef struct taco2dec_postnet_weights {
 /* n_mel <= 128, embed_dim a multiple of 128, kernel_size must be 5 (hparams.py:49), 2 <= n_layers <= 8. */
 int taco2dec_postnet_create(int n_mel, int embed_dim, int kernel_size, int n_layers, int device, taco2dec_postnet** out);
 int taco2dec_postnet_destroy(taco2dec_postnet* h);
+/* fp16_only = 0 (default): every operand is split into two fp16 terms and the convolutions are evaluated as
+ * hi.hi + hi.lo + lo.hi (fp32-grade mel_postnet, ~2.5x the tensor work); fp16_only = 1: plain fp16 operands (relative error
+ * ~8e-4 of the output scale).  Takes effect at the next taco2dec_postnet_set_weights. */
+int taco2dec_postnet_set_precision(taco2dec_postnet* h, int fp16_only);
 /* Folds BatchNorm and packs the GEMM tiles (library-owned copies): call again when the module's tensors change. */
 int taco2dec_postnet_set_weights(taco2dec_postnet* h, const taco2dec_postnet_weights* w, void* cuda_stream);
 size_t taco2dec_postnet_workspace_bytes(const taco2dec_postnet* h, int B, int T);

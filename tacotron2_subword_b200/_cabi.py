@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "taco2dec_set_batched_precision", "taco2dec_poll_abort", "taco2dec_read_debug_stamps", "taco2dec_measure_machine",
     "taco2dec_memprep_create", "taco2dec_memprep_destroy", "taco2dec_memprep_set_weights", "taco2dec_memprep_workspace_bytes",
     "taco2dec_memprep_forward", "taco2dec_memprep_project", "taco2dec_loss_workspace_bytes", "taco2dec_loss_forward",
+    "taco2dec_postnet_set_precision",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -154,6 +155,8 @@ def load_library() -> C.CDLL:
     lib.taco2dec_backward.argtypes = [H, C.POINTER(BwdArgs), C.c_void_p]
     lib.taco2dec_postnet_create.restype = C.c_int
     lib.taco2dec_postnet_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    lib.taco2dec_postnet_set_precision.restype = C.c_int
+    lib.taco2dec_postnet_set_precision.argtypes = [H, C.c_int]
     lib.taco2dec_postnet_destroy.restype = C.c_int
     lib.taco2dec_postnet_destroy.argtypes = [H]
     lib.taco2dec_postnet_set_weights.restype = C.c_int

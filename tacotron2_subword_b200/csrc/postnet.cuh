@@ -22,20 +22,34 @@ struct Layer {
   float* bias;                                   // [cout_pad] folded bias
 };
 
+// Precision: segs = 1 -- plain fp16 operands (relative error ~8e-4 of the output scale after five layers); segs = 3 -- every
+// fp32 operand is split into two fp16 terms (hi + lo) and the product is evaluated as hi.hi + hi.lo + lo.hi: K segments
+// [W_hi | W_hi | W_lo] x [X_hi | X_lo | X_hi], fp32 accumulation -> fp32-grade mel_postnet (the default; the tensor the
+// vocoder consumes is held to the same 1e-3 bar as the decoder mel).
+__device__ __forceinline__ void pn_split(float v, __half& hi, __half& lo) {
+  hi = __float2half(v);
+  lo = __float2half(v - __half2float(hi));
+}
+
 // conv weight [cout][cin][taps] + BatchNorm (eval) -> fp16 GEMM tiles with K = tap * cin_pad + ci, folded bias
 __global__ void pn_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var,
                                float eps, int cout, int cin, int cout_pad, int cin_pad, unsigned char* __restrict__ tiles,
-                               float* __restrict__ bias_out) {
-  const int K = kTaps * cin_pad, kb_total = K / tc::kBlockK;
+                               float* __restrict__ bias_out, int segs) {
+  const int K = kTaps * cin_pad, kb_total = segs * K / tc::kBlockK;
   const size_t total = (size_t)cout_pad * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % K), ro = (int)(i / K);
     const int kk = k / cin_pad, ci = k - kk * cin_pad;
     float v = 0.f;
     if (ro < cout && ci < cin) v = w[((size_t)ro * cin + ci) * kTaps + kk] * (gamma[ro] * rsqrtf(var[ro] + eps));
-    const size_t tile = ((size_t)(ro / 128) * kb_total + (k / tc::kBlockK)) * tc::kATileBytes;
-    *reinterpret_cast<__half*>(tiles + tile + tc::tile_offset_bytes(128, ro % 128, k % tc::kBlockK)) = __float2half(v);
+    __half hi, lo;
+    pn_split(v, hi, lo);
+    for (int seg = 0; seg < segs; ++seg) {
+      const int kk = seg * K + k;
+      const size_t tile = ((size_t)(ro / 128) * kb_total + (kk / tc::kBlockK)) * tc::kATileBytes;
+      *reinterpret_cast<__half*>(tiles + tile + tc::tile_offset_bytes(128, ro % 128, kk % tc::kBlockK)) = seg == 2 ? lo : hi;
+    }
     if (k == 0) {
       float bo = 0.f;
       if (ro < cout) { const float sc = gamma[ro] * rsqrtf(var[ro] + eps); bo = (b[ro] - mean[ro]) * sc + beta[ro]; }
@@ -45,10 +59,16 @@ __global__ void pn_pack_kernel(const float* __restrict__ w, const float* __restr
 }
 
 // 16 bytes = 8 consecutive channels of tap kk at position n of the operand (group = n / 128)
-__device__ __forceinline__ void x_chunk_store(unsigned char* X, int K, int n, int k8, uint4 v) {
+__device__ __forceinline__ void x_chunk_store(unsigned char* X, int K, int n, int k8, const float* v, int segs) {
   const int g = n / kNP, nl = n - g * kNP, k = k8 * 8;
-  unsigned char* tile = X + ((size_t)g * (K / tc::kBlockK) + (k >> 6)) * ((size_t)kNP * 128);
-  *reinterpret_cast<uint4*>(tile + tc::tile_offset_bytes(kNP, nl, k & 63)) = v;
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) pn_split(v[q], hi[q], lo[q]);
+  for (int seg = 0; seg < segs; ++seg) {      // operand segments [hi | lo | hi]
+    const int kk = seg * K + k;
+    unsigned char* tile = X + ((size_t)g * (segs * K / tc::kBlockK) + (kk >> 6)) * ((size_t)kNP * 128);
+    *reinterpret_cast<uint4*>(tile + tc::tile_offset_bytes(kNP, nl, kk & 63)) = *reinterpret_cast<const uint4*>(seg == 1 ? lo : hi);
+  }
 }
 __device__ __forceinline__ uint4 pack8(const float* v) {
   __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
@@ -65,7 +85,7 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 // every layer, so row b equals the batch-1 result on its first seq_len[b] frames.
 __global__ void pn_input_kernel(const float* __restrict__ mel, long long sb, long long sc, long long st, int B, int T,
                                 int cin, int cin_pad, int n_pad /* groups * 128 */, const long long* __restrict__ seq_len,
-                                unsigned char* __restrict__ X) {
+                                unsigned char* __restrict__ X, int segs) {
   const int chunks = cin_pad / 8, K = kTaps * cin_pad;
   const size_t total = (size_t)n_pad * kTaps * chunks;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -79,7 +99,7 @@ __global__ void pn_input_kernel(const float* __restrict__ mel, long long sb, lon
         for (int q = 0; q < 8; ++q) { const int c = c8 * 8 + q; if (c < cin) v[q] = mel[b * sb + c * sc + t * st]; }
       }
     }
-    x_chunk_store(X, K, n, kk * chunks + c8, pack8(v));
+    x_chunk_store(X, K, n, kk * chunks + c8, v, segs);
   }
 }
 
@@ -89,7 +109,7 @@ __global__ void pn_input_kernel(const float* __restrict__ mel, long long sb, lon
 __global__ void __launch_bounds__(256) pn_pointwise_kernel(const float* __restrict__ part, int splits, int cout_pad,
                                                            const float* __restrict__ bias, int B, int T, int groups,
                                                            const long long* __restrict__ seq_len,
-                                                           unsigned char* __restrict__ Xn, int Kn /* 5 * cout_pad */) {
+                                                           unsigned char* __restrict__ Xn, int Kn /* 5 * cout_pad */, int segs) {
   __shared__ float act_s[8][kNP + 2 * kHalo + 1];
   const int g = blockIdx.x, c0 = blockIdx.y * 8, tid = threadIdx.x;
   const int NT = B * T, n0 = g * kNP;
@@ -118,7 +138,7 @@ __global__ void __launch_bounds__(256) pn_pointwise_kernel(const float* __restri
         for (int q = 0; q < 8; ++q) v[q] = act_s[q][nl + kk];
       }
     }
-    x_chunk_store(Xn, Kn, n, kk * (cout_pad / 8) + blockIdx.y, pack8(v));
+    x_chunk_store(Xn, Kn, n, kk * (cout_pad / 8) + blockIdx.y, v, segs);
   }
   (void)groups;
 }

@@ -2447,6 +2447,7 @@ extern "C" int taco2dec_loss_forward(const taco2dec_loss_args* a, void* cuda_str
 // ------------------------------------------------------------------------------------------
 struct taco2dec_postnet {
   int device, num_sms, n_mel, dim, n_layers;
+  int segs;              // 3 = split-fp16 operands (fp32-grade, default), 1 = plain fp16 operands
   bool have_weights;
   pn::Layer layer[pn::kMaxLayers];
   int64_t launches;
@@ -2459,7 +2460,7 @@ PnPlan pn_plan(const taco2dec_postnet* h, int B, int T) {
   pl.groups = (B * T + pn::kNP - 1) / pn::kNP;
   int kmax = 0, cmax = 0;
   for (int l = 0; l < h->n_layers; ++l) { kmax = std::max(kmax, h->layer[l].K); cmax = std::max(cmax, h->layer[l].cout_pad); }
-  pl.x_bytes = align_up((size_t)pl.groups * (kmax / tc::kBlockK) * pn::kNP * 128, 256);
+  pl.x_bytes = align_up((size_t)pl.groups * (h->segs * kmax / tc::kBlockK) * pn::kNP * 128, 256);
   pl.part_bytes = align_up((size_t)pl.groups * 4 * cmax * pn::kNP * sizeof(float), 256);     // up to 4 K-splits
   pl.total = 2 * pl.x_bytes + pl.part_bytes;
   return pl;
@@ -2485,7 +2486,7 @@ int taco2dec_postnet_create(int n_mel, int embed_dim, int kernel_size, int n_lay
   taco2dec_postnet* h = new (std::nothrow) taco2dec_postnet();
   if (!h) return fail(TACO2DEC_E_STATE, "out of host memory");
   h->device = device; h->num_sms = prop.multiProcessorCount; h->n_mel = n_mel; h->dim = embed_dim; h->n_layers = n_layers;
-  h->have_weights = false; h->launches = 0;
+  h->have_weights = false; h->launches = 0; h->segs = 3;
   CUDA_TRY(cudaSetDevice(device));
   for (int l = 0; l < n_layers; ++l) {
     pn::Layer& L = h->layer[l];
@@ -2494,10 +2495,17 @@ int taco2dec_postnet_create(int n_mel, int embed_dim, int kernel_size, int n_lay
     L.cin_pad = (L.cin + 63) / 64 * 64;
     L.cout_pad = (L.cout + 127) / 128 * 128;
     L.K = pn::kTaps * L.cin_pad;
-    CUDA_TRY(cudaMalloc(&L.a_tiles, (size_t)L.cout_pad * L.K * 2));
+    CUDA_TRY(cudaMalloc(&L.a_tiles, (size_t)L.cout_pad * 3 * L.K * 2));
     CUDA_TRY(cudaMalloc(&L.bias, (size_t)L.cout_pad * sizeof(float)));
   }
   *out = h;
+  return 0;
+}
+
+int taco2dec_postnet_set_precision(taco2dec_postnet* h, int fp16_only) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null handle");
+  const int segs = fp16_only ? 1 : 3;
+  if (segs != h->segs) { h->segs = segs; h->have_weights = false; }      // the weight tiles depend on it: set_weights again
   return 0;
 }
 
@@ -2518,7 +2526,7 @@ int taco2dec_postnet_set_weights(taco2dec_postnet* h, const taco2dec_postnet_wei
       return fail(TACO2DEC_E_ARG, "null postnet weight pointer");
     const pn::Layer& L = h->layer[l];
     pn::pn_pack_kernel<<<1024, 256, 0, st>>>(s.conv_w, s.conv_b, s.bn_weight, s.bn_bias, s.bn_mean, s.bn_var, w->bn_eps, L.cout,
-                                             L.cin, L.cout_pad, L.cin_pad, L.a_tiles, L.bias);
+                                             L.cin, L.cout_pad, L.cin_pad, L.a_tiles, L.bias, h->segs);
   }
   CUDA_TRY(cudaGetLastError());
   h->launches += h->n_layers;
@@ -2552,19 +2560,19 @@ int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stri
     const pn::Layer& L0 = h->layer[0];
     const size_t total = (size_t)n_pad * pn::kTaps * (L0.cin_pad / 8);
     pn::pn_input_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 65535), 256, 0, st>>>(mel, stride_b, stride_c, stride_t, B, T,
-                                                                                               L0.cin, L0.cin_pad, n_pad, seq_len, X[0]);
+                                                                                               L0.cin, L0.cin_pad, n_pad, seq_len, X[0], h->segs);
   }
   for (int l = 0; l < h->n_layers; ++l) {
     const pn::Layer& L = h->layer[l];
-    const int m_tiles = L.cout_pad / tc::kBlockM, kb_total = L.K / tc::kBlockK;
+    const int m_tiles = L.cout_pad / tc::kBlockM, kb_total = h->segs * L.K / tc::kBlockK;
     const int splits = pn_splits(m_tiles * pl.groups, kb_total, h->num_sms);
-    tc::GemmParams gp{L.a_tiles, X[l & 1], part, L.cout_pad, L.K, splits, pl.groups, (long long)kb_total * pn::kNP * 128, 0, 0, nullptr, 0};
+    tc::GemmParams gp{L.a_tiles, X[l & 1], part, L.cout_pad, h->segs * L.K, splits, pl.groups, (long long)kb_total * pn::kNP * 128, 0, 0, nullptr, 0};
     gp.a_shared = 1;
     CUDA_TRY(tc::launch_gemm<pn::kNP>(gp, st));
     if (l + 1 < h->n_layers) {
       const pn::Layer& Ln = h->layer[l + 1];
       pn::pn_pointwise_kernel<<<dim3(pl.groups, L.cout_pad / 8), 256, 0, st>>>(part, splits, L.cout_pad, L.bias, B, T, pl.groups,
-                                                                             seq_len, X[(l + 1) & 1], Ln.K);
+                                                                             seq_len, X[(l + 1) & 1], Ln.K, h->segs);
     } else {
       const size_t total = (size_t)B * L.cout * T;
       pn::pn_output_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 65535), 256, 0, st>>>(
