@@ -249,6 +249,24 @@ int taco2dec_grad_layout_query(const taco2dec_handle* h, int B, int T_in, int T_
 int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda_stream);
 int taco2dec_infer(taco2dec_handle* h, const taco2dec_infer_args* a, void* cuda_stream);
 
+/* Weight-gradient contraction after taco2dec_backward: C[m][n] (+)= sum over rows k = (t, b) of
+ * Y[k][m] * X[k][n], K = T*B.  Row (t, b) of Y starts at Y + t*y_stride_t + b*y_stride_b (elements), likewise X: the per-frame
+ * gradient rows of taco2dec_grad_layout and the saved activations of taco2dec_saved_layout are addressed in place.  Runs
+ * on the tcgen05 GEMM (fp16 operands, Y pre-scaled by a power of two from its absolute maximum, fp32 accumulation).
+ * reuse_y = 1: the previous call on this workspace had the same Y, M, T, B -- its packed operand is used again. */
+size_t taco2dec_wgrad_workspace_bytes(const taco2dec_handle* h, int M, int N, int T, int B);
+int taco2dec_wgrad_gemm(taco2dec_handle* h, const float* Y, int64_t y_stride_t, int64_t y_stride_b, int M, const float* X,
+                        int64_t x_stride_t, int64_t x_stride_b, int N, int T, int B, float* C, int64_t ldc, int accumulate,
+                        int reuse_y, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* The two small backward contractions that are not sums over (frame, utterance) rows, fp32 on the CUDA cores:
+ * sgemm_nn: C[r][n] (+)= sum_k A[r][k] B[k][n], optionally gated by the prenet's ReLU/dropout mask (x2 where mask > 0, else 0;
+ * model.py:23); bmm_tn: C[b][m][n] = sum_t A[b][t][m] B[t][b][n] (d memory = alignments^T . d context, attention.py:395). */
+int taco2dec_sgemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int R, int N, int K,
+                      const float* mask, int64_t ldm, int accumulate, void* cuda_stream);
+int taco2dec_bmm_tn(const float* A, int64_t a_stride_b, int64_t a_stride_t, const float* B, int64_t b_stride_t, int64_t b_stride_b,
+                    float* C, int64_t c_stride_b, int64_t ldc, int batch, int M, int N, int T, void* cuda_stream);
+
 /* Synchronises the stream and reports TACO2DEC_E_ABORTED if the in-kernel watchdog fired
  * during any call since the last check (asynchronous CUDA faults surface here too).  The abort word is sticky:
  * once set every later kernel of the handle bails out at once, until a check has reported and cleared it. */

@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = (
     "taco2dec_set_batched_precision", "taco2dec_poll_abort", "taco2dec_read_debug_stamps", "taco2dec_measure_machine",
     "taco2dec_memprep_create", "taco2dec_memprep_destroy", "taco2dec_memprep_set_weights", "taco2dec_memprep_workspace_bytes",
     "taco2dec_memprep_forward", "taco2dec_memprep_project", "taco2dec_loss_workspace_bytes", "taco2dec_loss_forward",
-    "taco2dec_postnet_set_precision",
+    "taco2dec_postnet_set_precision", "taco2dec_wgrad_workspace_bytes", "taco2dec_wgrad_gemm",
+    "taco2dec_sgemm_nn", "taco2dec_bmm_tn",
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -202,6 +203,17 @@ def load_library() -> C.CDLL:
     lib.taco2dec_loss_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.taco2dec_loss_forward.restype = C.c_int
     lib.taco2dec_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p]
+    lib.taco2dec_wgrad_workspace_bytes.restype = C.c_size_t
+    lib.taco2dec_wgrad_workspace_bytes.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.taco2dec_wgrad_gemm.restype = C.c_int
+    lib.taco2dec_wgrad_gemm.argtypes = [H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.taco2dec_sgemm_nn.restype = C.c_int
+    lib.taco2dec_sgemm_nn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    lib.taco2dec_bmm_tn.restype = C.c_int
+    lib.taco2dec_bmm_tn.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.taco2dec_poll_abort.restype = C.c_int
     lib.taco2dec_poll_abort.argtypes = [H]
     lib.taco2dec_last_path.restype = C.c_int

@@ -783,6 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
 #include "persist.cuh"
 #include "memprep.cuh"
 #include "loss.cuh"
+#include "wgrad.cuh"
 
 // ------------------------------------------------------------------------------------------
 // One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
@@ -850,6 +851,90 @@ __global__ void __launch_bounds__(256) prenet_tf_kernel(const float* __restrict_
         }
       }
       __syncwarp();
+    }
+  }
+}
+
+// Same computation for the full-size prenet (P = 256), tiled: one block = 64 frame rows x all 256 features, both layers, the
+// weights streamed through shared memory once per block instead of once per row (the per-row kernel above moves
+// rows x 344 KB through L2: 2.6 ms per stream at 51k rows; this one is bound by its fp32 FMAs).  fp32 throughout.
+constexpr int kPtRows = 64, kPtKC = 16, kPtP = 256;
+constexpr size_t kPtSmem = ((size_t)kPtP * (kPtRows + 4) + (size_t)kPtKC * (kPtP + 4)) * sizeof(float);
+__global__ void __launch_bounds__(256, 2) prenet_tf_tiled_kernel(const float* __restrict__ dec_in, const float* __restrict__ w0,
+                                                                 const float* __restrict__ w1, const uint8_t* keep0, const uint8_t* keep1,
+                                                                 float* __restrict__ out, float* __restrict__ out0, int B, int T, int M,
+                                                                 unsigned long long seed, int stream_id, unsigned thresh) {
+  extern __shared__ __align__(16) float sm[];
+  float (*in_s)[kPtRows + 4] = reinterpret_cast<float (*)[kPtRows + 4]>(sm);                       // [k][row]: x, then layer-0 output
+  float (*w_s)[kPtP + 4] = reinterpret_cast<float (*)[kPtP + 4]>(sm + (size_t)kPtP * (kPtRows + 4));   // [k in chunk][feature]
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int n_rows = (T + 1) * B, n0 = blockIdx.x * kPtRows;
+  const int Mp = (M + kPtKC - 1) / kPtKC * kPtKC;
+  // teacher-forced input rows, transposed: row n = (frame r, utterance b); r = 0 is the go-frame
+  for (int i = tid; i < Mp * kPtRows; i += 256) {
+    const int m = i / kPtRows, row = i - m * kPtRows, n = n0 + row;
+    float v = 0.f;
+    if (n < n_rows && m < M) {
+      const int r = n / B, b = n - r * B;
+      if (r > 0) v = dec_in[((size_t)b * M + m) * T + (r - 1)];
+    }
+    in_s[m][row] = v;
+  }
+  for (int layer = 0; layer < 2; ++layer) {
+    const float* W = layer == 0 ? w0 : w1;
+    const int K = layer == 0 ? M : kPtP, Kp = layer == 0 ? Mp : kPtP;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < Kp; k0 += kPtKC) {
+      __syncthreads();                                   // previous chunk consumed (first pass: in_s complete)
+      for (int i = tid; i < kPtKC * kPtP; i += 256) {   // W[feature][k0 .. k0+16) -> w_s[k][feature]
+        const int f = i >> 4, kl = i & 15;
+        w_s[kl][f] = (k0 + kl < K) ? W[(size_t)f * K + k0 + kl] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kl = 0; kl < kPtKC; ++kl) {
+        const float4 xa = *reinterpret_cast<const float4*>(&in_s[k0 + kl][ty * 8]);
+        const float4 xb = *reinterpret_cast<const float4*>(&in_s[k0 + kl][ty * 8 + 4]);
+        const float4 wa = *reinterpret_cast<const float4*>(&w_s[kl][tx * 4]);
+        const float4 wb = *reinterpret_cast<const float4*>(&w_s[kl][128 + tx * 4]);
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();                                     // every thread is done reading in_s before layer 0 overwrites it
+    const uint8_t* keep = layer == 0 ? keep0 : keep1;
+    float* dst = layer == 0 ? out0 : out;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = ty * 8 + i, n = n0 + row;
+      if (n >= n_rows) {
+        if (layer == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) in_s[(j < 4 ? 0 : 128) + tx * 4 + (j & 3)][row] = 0.f;
+        }
+        continue;
+      }
+      const int r = n / B, b = n - r * B;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = (j < 4 ? 0 : 128) + tx * 4 + (j & 3);
+        const float mult = keep_mult(keep, (size_t)n * kPtP + col, seed, stream_id * 2 + layer, r, b * kPtP + col, thresh, 2.0f);
+        v[j] = fmaxf(acc[i][j], 0.0f) * mult;
+        if (layer == 0) in_s[col][row] = v[j];
+      }
+      if (dst) {
+        *reinterpret_cast<float4*>(dst + (size_t)n * kPtP + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + (size_t)n * kPtP + 128 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
     }
   }
 }
@@ -1992,10 +2077,17 @@ int taco2dec_forward_teacher_forced(taco2dec_handle* h, const taco2dec_tf_args* 
     const int wpb = 8;
     const int blocks = std::min((n_rows + wpb - 1) / wpb, h->num_sms * 8);
     const size_t sm = (size_t)wpb * (((c.n_mel + 3) & ~3) + c.prenet_dim) * sizeof(float);
-    prenet_tf_kernel<<<blocks, wpb * 32, sm, st>>>(a->decoder_inputs, h->w.stream[s].prenet_w0, h->w.stream[s].prenet_w1,
-                                                   a->rng.prenet_keep[s][0], a->rng.prenet_keep[s][1], p.st[s].pre,
-                                                   pre0_save[s], a->B, a->T, c.n_mel, c.prenet_dim, a->rng.seed, s,
-                                                   p.thresh_pre);
+    if (c.prenet_dim == kPtP && c.n_mel <= kPtP && n_rows >= 4 * kPtRows) {
+      CUDA_TRY(cudaFuncSetAttribute(prenet_tf_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPtSmem));
+      prenet_tf_tiled_kernel<<<(n_rows + kPtRows - 1) / kPtRows, 256, kPtSmem, st>>>(
+          a->decoder_inputs, h->w.stream[s].prenet_w0, h->w.stream[s].prenet_w1, a->rng.prenet_keep[s][0], a->rng.prenet_keep[s][1],
+          p.st[s].pre, pre0_save[s], a->B, a->T, c.n_mel, a->rng.seed, s, p.thresh_pre);
+    } else {
+      prenet_tf_kernel<<<blocks, wpb * 32, sm, st>>>(a->decoder_inputs, h->w.stream[s].prenet_w0, h->w.stream[s].prenet_w1,
+                                                     a->rng.prenet_keep[s][0], a->rng.prenet_keep[s][1], p.st[s].pre,
+                                                     pre0_save[s], a->B, a->T, c.n_mel, c.prenet_dim, a->rng.seed, s,
+                                                     p.thresh_pre);
+    }
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -2438,6 +2530,69 @@ extern "C" int taco2dec_loss_forward(const taco2dec_loss_args* a, void* cuda_str
   r.inv_mel = 1.0 / n_mel_el; r.inv_gate = 1.0 / n_gate_el; r.inv_al = inv_al[0]; r.inv_alb = inv_al[1];
   r.losses = a->losses;
   ls::ls_reduce_kernel<<<1, 256, 0, st>>>(r);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Weight-gradient contractions (wgrad.cuh)
+// ------------------------------------------------------------------------------------------
+extern "C" size_t taco2dec_wgrad_workspace_bytes(const taco2dec_handle* h, int M, int N, int T, int B) {
+  if (!h || M < 1 || N < 1 || T < 1 || B < 1) return 0;
+  return wg::plan(M, N, T * B, h->num_sms).total;
+}
+
+extern "C" int taco2dec_wgrad_gemm(taco2dec_handle* h, const float* Y, int64_t y_stride_t, int64_t y_stride_b, int M, const float* X,
+                                   int64_t x_stride_t, int64_t x_stride_b, int N, int T, int B, float* Cout, int64_t ldc, int accumulate,
+                                   int reuse_y, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!h || !Y || !X || !Cout || !workspace) return fail(TACO2DEC_E_ARG, "null argument");
+  if (M < 1 || N < 1 || T < 1 || B < 1 || ldc < N) return fail(TACO2DEC_E_ARG, "bad shape");
+  const wg::Plan pl = wg::plan(M, N, T * B, h->num_sms);
+  if (workspace_bytes < pl.total) return fail(TACO2DEC_E_STATE, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(TACO2DEC_E_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  char* ws = (char*)workspace;
+  unsigned* amax = (unsigned*)ws;
+  float* scale2 = (float*)(ws + 64);
+  unsigned char* a_t = (unsigned char*)(ws + pl.a_off);
+  unsigned char* x_t = (unsigned char*)(ws + pl.x_off);
+  float* part = (float*)(ws + pl.part_off);
+  const int kbs = pl.Kpad / 64;
+  if (!reuse_y) {       // the packed, scaled image of Y at the head of the workspace is still valid otherwise
+    CUDA_TRY(cudaMemsetAsync(amax, 0, 64, st));
+    wg::wg_absmax_kernel<<<h->num_sms * 4, 256, 0, st>>>(Y, y_stride_t, y_stride_b, T, B, M, amax);
+    wg::wg_scale_kernel<<<1, 1, 0, st>>>(amax, scale2);
+    wg::wg_pack_T_kernel<<<dim3(kbs, pl.Mpad / 128), 256, 0, st>>>(Y, y_stride_t, y_stride_b, T, B, M, pl.Kpad, scale2, a_t);
+    h->launches += 3;
+  }
+  wg::wg_pack_T_kernel<<<dim3(kbs, pl.groups), 256, 0, st>>>(X, x_stride_t, x_stride_b, T, B, N, pl.Kpad, nullptr, x_t);
+  CUDA_TRY(tc::prepare_gemm<wg::kNP>());
+  tc::GemmParams gp{a_t, x_t, part, pl.Mpad, pl.Kpad, pl.splits, pl.groups, (long long)kbs * wg::kNP * 128, 0, 0, nullptr, 0};
+  gp.a_shared = 1;
+  CUDA_TRY(tc::launch_gemm<wg::kNP>(gp, st));
+  wg::wg_finish_kernel<<<dim3(std::min(64, (M * wg::kNP + 255) / 256), pl.groups), 256, 0, st>>>(part, pl.splits, pl.Mpad, M, N, scale2, Cout, ldc,
+                                                                                                accumulate);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 3;
+  return 0;
+}
+
+extern "C" int taco2dec_sgemm_nn(const float* A, int64_t lda, const float* Bm, int64_t ldb, float* Cout, int64_t ldc, int R, int N, int K,
+                                 const float* mask, int64_t ldm, int accumulate, void* cuda_stream) {
+  if (!A || !Bm || !Cout || R < 1 || N < 1 || K < 1) return fail(TACO2DEC_E_ARG, "bad argument");
+  wg::sgemm_nn_kernel<<<dim3((N + 63) / 64, (R + 63) / 64), 256, 0, (cudaStream_t)cuda_stream>>>(A, lda, Bm, ldb, Cout, ldc, R, N, K, mask, ldm,
+                                                                                                accumulate);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int taco2dec_bmm_tn(const float* A, int64_t a_stride_b, int64_t a_stride_t, const float* Bm, int64_t b_stride_t, int64_t b_stride_b,
+                               float* Cout, int64_t c_stride_b, int64_t ldc, int batch, int M, int N, int T, void* cuda_stream) {
+  if (!A || !Bm || !Cout || batch < 1 || M < 1 || N < 1 || T < 1) return fail(TACO2DEC_E_ARG, "bad argument");
+  wg::bmm_tn_kernel<<<dim3((N + 63) / 64, (M + 63) / 64, batch), 256, 0, (cudaStream_t)cuda_stream>>>(A, a_stride_b, a_stride_t, Bm, b_stride_t,
+                                                                                                     b_stride_b, Cout, c_stride_b, ldc, M, N, T);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

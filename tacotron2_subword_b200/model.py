@@ -203,57 +203,85 @@ class _DecoderTF(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev)
             _cabi.check(eng.lib.taco2dec_backward(eng.handle, C.byref(a), C.c_void_p(stream.cuda_stream)))
 
-        # ---- contractions over (frame, utterance): library GEMMs on the rows the kernels left behind ----
+        # ---- contractions over (frame, utterance) on the repo's own tcgen05 GEMM (taco2dec_wgrad_gemm): Y^T . X with K = T*B;
+        #      the per-frame gradient rows and the saved activations are addressed in place through (frame, utterance) strides ----
         SL, sv = st["SL"], st["saved"]
         h1 = _fview(sv, SL.h1, T + 1, S, B, H)
         cx = _fview(sv, SL.ctx, T + 1, S, B, E)
         h2 = _fview(sv, SL.h2, T + 1, B, H)
-        dg1 = _fview(gbuf, GL.dg1, S, T * B, G)
-        dg2 = _fview(gbuf, GL.dg2, T * B, G)
-        dq = _fview(gbuf, GL.dq, S, T * B, A)
+        dg1 = _fview(gbuf, GL.dg1, S, T, B, G)
+        dg2 = _fview(gbuf, GL.dg2, T, B, G)
+        dq = _fview(gbuf, GL.dq, S, T, B, A)
         dctx = _fview(gbuf, GL.dctx, S, T, B, E)
         dpre = _fview(gbuf, GL.dpre, S, T, B, P)
         dv = _fview(gbuf, GL.dv, S, B, A)
         Ts = [T_in, T_sub]
         mems = [st["mem"], st["emb"]]
         aligns = [st["align"], st["align_b"]]
-        x_frames = F.pad(st["dec_in"].permute(2, 0, 1), (0, 0, 0, 0, 1, 0))[:T].reshape(T * B, M)   # go frame + targets
+        x_frames = F.pad(st["dec_in"].permute(2, 0, 1), (0, 0, 0, 0, 1, 0))[:T].contiguous()     # go frame + targets [T, B, M]
         grads = {}
         d_mems = [None, None]
         # ``dec._grad_ready`` (set by distributed.GradientBucketer): called with (parameter, gradient) the moment a weight
         # gradient exists, largest tensors first, so that its all-reduce over NCCL runs while the remaining contractions
         # are still being computed (the reference reduces everything after the whole backward, distributed.py:160-167)
         publish = getattr(dec, "_grad_ready", None)
+        lib, hnd, cstream = eng.lib, eng.handle, C.c_void_p(stream.cuda_stream)
+        ws_box = [None, None]       # workspace, key of the Y operand whose packed image it holds
+
+        def wgrad(Y3, X3, out, accumulate=False):
+            """out[M, N] (a 2-D view, unit column stride) (+)= sum over (t, b) of Y3[t, b, :]^T X3[t, b, :]."""
+            Tn, Bn, Mn = Y3.shape
+            Nn = X3.shape[2]
+            assert X3.shape[:2] == (Tn, Bn) and Y3.stride(2) == 1 and X3.stride(2) == 1 and out.stride(1) == 1
+            need = int(lib.taco2dec_wgrad_workspace_bytes(hnd, Mn, Nn, Tn, Bn))
+            if ws_box[0] is None or ws_box[0].numel() < need:
+                ws_box[0], ws_box[1] = torch.empty(max(need, ws_need), dtype=torch.uint8, device=dev), None
+            ykey = (Y3.data_ptr(), tuple(Y3.shape), tuple(Y3.stride()))
+            reuse = ws_box[1] == ykey          # same gradient rows as the previous product: its packed operand is still there
+            ws_box[1] = ykey
+            _cabi.check(lib.taco2dec_wgrad_gemm(hnd, _ptr(Y3), Y3.stride(0), Y3.stride(1), Mn, _ptr(X3), X3.stride(0), X3.stride(1), Nn,
+                                                Tn, Bn, _ptr(out), out.stride(0), int(accumulate), int(reuse), _ptr(ws_box[0]),
+                                                ws_box[0].numel(), cstream))
 
         def put(param, g):
             grads[param] = g
             if publish is not None and param.requires_grad:
                 publish(param, g)
 
-        tf32 = dec.grad_gemm_tf32 if dec.grad_gemm_tf32 is not None else True
-        old_tf32 = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
-        try:
-            g2t = dg2.t()
-            x2 = torch.cat([t_ for s in range(S) for t_ in (h1[1:, s].reshape(T * B, H), cx[1:, s].reshape(T * B, E))], dim=1)
-            put(dec.decoder_rnn.weight_ih, g2t @ x2)
-            put(dec.decoder_rnn.weight_hh, g2t @ h2[:T].reshape(T * B, H))
-            db = dg2.sum(0)
+        # one workspace for every product: sized for the largest (gate rows x the widest activation block)
+        ws_need = int(lib.taco2dec_wgrad_workspace_bytes(hnd, G, H, T, B))
+        with torch.cuda.device(dev):
+            # decoder LSTM: dWd_ih = dg2^T [h1_0 | ctx_0 | h1_1 | ctx_1](t), dWd_hh = dg2^T h2(t-1)
+            g_ih = torch.empty(G, S * (H + E), device=dev)
+            for s in range(S):
+                wgrad(dg2, h1[1:, s], g_ih[:, s * (H + E): s * (H + E) + H])
+                wgrad(dg2, cx[1:, s], g_ih[:, s * (H + E) + H: (s + 1) * (H + E)])
+            put(dec.decoder_rnn.weight_ih, g_ih)
+            g_hh = torch.empty(G, H, device=dev)
+            wgrad(dg2, h2[:T], g_hh)
+            put(dec.decoder_rnn.weight_hh, g_hh)
+            db = dg2.sum((0, 1))
             put(dec.decoder_rnn.bias_ih, db)
             put(dec.decoder_rnn.bias_hh, db.clone())
             for s, sfx in enumerate(dec._sfx()):
                 pre_m, rnn, att = getattr(dec, "prenet" + sfx), getattr(dec, "attention_rnn" + sfx), \
                     getattr(dec, "attention_layer" + sfx)
-                pre = _fview(sv, SL.pre[s], T + 1, B, P)[:T].reshape(T * B, P)
-                pre0 = _fview(sv, SL.pre0[s], T + 1, B, P)[:T].reshape(T * B, P)
-                g1t = dg1[s].t()
-                x1 = torch.cat([pre, cx[:T, s].reshape(T * B, E)], dim=1)
-                put(rnn.weight_hh, g1t @ h1[:T, s].reshape(T * B, H))
-                put(rnn.weight_ih, g1t @ x1)
-                db = dg1[s].sum(0)
+                pre = _fview(sv, SL.pre[s], T + 1, B, P)[:T]
+                pre0 = _fview(sv, SL.pre0[s], T + 1, B, P)[:T]
+                # attention LSTM: dW_hh = dg1^T h1(t-1), dW_ih = dg1^T [prenet(t) | ctx(t-1)]
+                g_hh = torch.empty(G, H, device=dev)
+                wgrad(dg1[s], h1[:T, s], g_hh)
+                put(rnn.weight_hh, g_hh)
+                g_ih = torch.empty(G, P + E, device=dev)
+                wgrad(dg1[s], pre, g_ih[:, :P])
+                wgrad(dg1[s], cx[:T, s], g_ih[:, P:])
+                put(rnn.weight_ih, g_ih)
+                db = dg1[s].sum((0, 1))
                 put(rnn.bias_ih, db)
                 put(rnn.bias_hh, db.clone())
-                put(att.query_layer.linear_layer.weight, dq[s].t() @ h1[1:, s].reshape(T * B, H))
+                g_q = torch.empty(A, H, device=dev)
+                wgrad(dq[s], h1[1:, s], g_q)
+                put(att.query_layer.linear_layer.weight, g_q)
                 put(att.v_weight(), dv[s].sum(0).view(1, A))
                 if dec.attention_kind == LSA:
                     LF, LK = dec.loc_filters, dec.loc_kernel
@@ -261,23 +289,43 @@ class _DecoderTF(torch.autograd.Function):
                     put(att.location_layer.location_conv.conv.weight, _fview(gbuf, GL.dloc_conv, S, B, LF, 2, LK)[s].sum(0))
                 dpm = _fview(gbuf, GL.dpm[s], B, Ts[s], A)
                 wm = att.memory_layer.linear_layer.weight
-                put(wm, dpm.reshape(-1, A).t() @ mems[s].reshape(-1, E))
-                d_mems[s] = torch.bmm(aligns[s].transpose(1, 2), dctx[s].transpose(0, 1)) + dpm @ wm.detach()
+                g_m = torch.empty(A, E, device=dev)
+                wgrad(dpm.reshape(B * Ts[s], 1, A), mems[s].reshape(B * Ts[s], 1, E), g_m)       # rows = (utterance, position)
+                put(wm, g_m)
+                # d memory[b] = alignments[b]^T . d ctx[:, b] + d processed_memory[b] . Wm      (attention.py:395, model.py:258-261)
+                dm_s = torch.empty(B, Ts[s], E, device=dev)
+                al = aligns[s]
+                _cabi.check(lib.taco2dec_bmm_tn(_ptr(al), al.stride(0), al.stride(1), _ptr(dctx[s]), dctx[s].stride(0), dctx[s].stride(1),
+                                                _ptr(dm_s), dm_s.stride(0), dm_s.stride(1), B, Ts[s], E, T, cstream))
+                wmd = wm.detach()
+                _cabi.check(lib.taco2dec_sgemm_nn(_ptr(dpm), A, _ptr(wmd), wmd.stride(0), _ptr(dm_s), E, B * Ts[s], E, A, None, 0, 1, cstream))
+                d_mems[s] = dm_s
                 # prenet: two bias-free linear + ReLU + always-on dropout layers (model.py:13-24); kept <=> output > 0
                 w0, w1 = pre_m.layers[0].linear_layer.weight, pre_m.layers[1].linear_layer.weight
-                dz1 = dpre[s].reshape(T * B, P) * 2.0 * (pre > 0)
-                put(w1, dz1.t() @ pre0)
-                dz0 = (dz1 @ w1.detach()) * 2.0 * (pre0 > 0)
-                put(w0, dz0.t() @ x_frames)
-            y = torch.cat([h2[1:].reshape(T * B, H)] + [cx[1:, s].reshape(T * B, E) for s in range(S)], dim=1)
-            dm = d_mel.transpose(0, 1).reshape(T * B, M)
-            dgt = d_gate.t().reshape(T * B, 1)
-            put(dec.linear_projection.linear_layer.weight, dm.t() @ y)
-            put(dec.linear_projection.linear_layer.bias, dm.sum(0))
-            put(dec.gate_layer.linear_layer.weight, dgt.t() @ y)
-            put(dec.gate_layer.linear_layer.bias, dgt.sum(0))
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = old_tf32
+                dz1 = dpre[s] * 2.0 * (pre > 0)
+                g_w1 = torch.empty(P, P, device=dev)
+                wgrad(dz1, pre0, g_w1)
+                put(w1, g_w1)
+                dz0 = torch.empty(T, B, P, device=dev)
+                w1d = w1.detach()
+                _cabi.check(lib.taco2dec_sgemm_nn(_ptr(dz1), P, _ptr(w1d), w1d.stride(0), _ptr(dz0), P, T * B, P, P, _ptr(pre0), P, 0, cstream))
+                g_w0 = torch.empty(P, M, device=dev)
+                wgrad(dz0, x_frames, g_w0)
+                put(w0, g_w0)
+            # projection / gate: d[Wp ; wg] = [d mel | d gate]^T [h2(t) | ctx_0(t) | ctx_1(t)]
+            KD = H + S * E
+            g_p = torch.empty(M, KD, device=dev)
+            g_g = torch.empty(1, KD, device=dev)
+            dm3 = d_mel.transpose(0, 1)                      # [T, B, M] view of the [B, T, M] gradient
+            dg3 = d_gate.t().unsqueeze(2)                    # [T, B, 1]
+            for Y3, out in ((dm3, g_p), (dg3, g_g)):
+                wgrad(Y3, h2[1:], out[:, :H])
+                for s in range(S):
+                    wgrad(Y3, cx[1:, s], out[:, H + s * E: H + (s + 1) * E])
+            put(dec.linear_projection.linear_layer.weight, g_p)
+            put(dec.linear_projection.linear_layer.bias, d_mel.sum((0, 1)))
+            put(dec.gate_layer.linear_layer.weight, g_g)
+            put(dec.gate_layer.linear_layer.bias, d_gate.sum().view(1))
         finish = getattr(dec, "_grad_ready_finish", None)
         if finish is not None:
             finish()          # the early all-reduces must have landed before autograd hands these tensors on

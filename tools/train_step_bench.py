@@ -61,6 +61,16 @@ out = dict(config=f"cfg5 train step B={B}/GPU T={T} {T_in}/{T_sub} SMA train-mod
            us_per_frame_bwd=round(1e3 * bw / T, 1), loss=res[-1][2], peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 2))
 print(json.dumps(out), flush=True)
 
+if "--profile" in sys.argv:          # kernel-time table of one step (CUPTI through torch.profiler; not a bench number)
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+    rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:28]
+    tot = sum(e.device_time_total for e in prof.key_averages())
+    print(f"kernel time of one step: {tot / 1e3:.2f} ms")
+    for e in rows:
+        print(f"{e.device_time_total / 1e3:9.3f} ms {e.count:6d} x {e.device_time_total / max(1, e.count):9.1f} us  {e.key[:90]}")
+
 if "--cpu" in sys.argv:
     from oracle.decoder_oracle import DecoderOracle
     Tc = 16
