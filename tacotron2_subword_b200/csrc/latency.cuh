@@ -85,9 +85,13 @@ struct LatParams {
   int *n_frames, *reached_max;
   // LL exchange buffers (64-bit {value, tag}); zeroed by the host before launch
   unsigned long long *ll_h1, *ll_h2, *ll_ctx, *ll_q, *ll_pre, *ll_mel, *ll_l0;
+  unsigned long long *ll_e;      // partial energies [depth][2 streams][8 slices][kLatTsCap]
   unsigned* aux_done;
   int* abort_flag;
   long long* phase_clocks;       // [16] diagnostics (LSTM CTA 0)
+  long long* dbg;                // optional [256] cycle sums (TACO2DEC_LAT_DEBUG=1): [0,64) per-step detail of LSTM CTA 0
+                                 // (step*4 + {dot, reduce, calls}), [64,80) attention CTA (0,0), [80,96) attention CTA (1,0),
+                                 // [96,112) aux CTA 0
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -302,6 +306,7 @@ struct LstmShared {
   StepPlan* plan;                           // [kSteps]
   volatile int* exit_flag;
   uint32_t tmem_base;                       // tensor-memory allocation of this CTA (all 512 columns)
+  long long* dbg_s;                         // diagnostics of LSTM CTA 0 (shared memory [64]) or null
 };
 
 // ---- tensor memory as weight storage --------------------------------------------------------------------------
@@ -423,7 +428,14 @@ __device__ __noinline__ void consume_items(const LstmShared& sh, const StepPlan&
   constexpr int PU = NU >= 4 ? 4 : NU;                                  // resident (shared memory) pass width
   constexpr int PUG = NU >= TACO2DEC_STREAM_PU ? TACO2DEC_STREAM_PU : NU;   // streamed (L2/HBM) pass width
   const int n_items = sp.n_units * sp.ksplit;
+#ifdef TACO2DEC_LAT_STAMPS
+  const bool dbg_on = sh.dbg_s && warp == 0 && lane == 0;
+#else
+  constexpr bool dbg_on = false;
+#endif
+  long long d_dot = 0, d_red = 0;
   for (int it = warp; it < n_items; it += kWarps) {
+    const long long d0 = dbg_on ? clock64() : 0;
     const int unit = it / sp.ksplit, kh = it - unit * sp.ksplit;
     const float* xk = xs + (size_t)kh * KLEN;
     float s[4];
@@ -435,8 +447,15 @@ __device__ __noinline__ void consume_items(const LstmShared& sh, const StepPlan&
       dot4<WB, KLEN, PUG, true>(sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + col_off, row_bytes, xk, lane, s,
                                  sp.policy);
     }
+    long long d1 = 0;
+    if (dbg_on) { volatile float sink = s[0] + s[1] + s[2] + s[3]; (void)sink; d1 = clock64(); d_dot += d1 - d0; }
     const float c = butterfly4(s[0], s[1], s[2], s[3], lane);
     if ((lane & 7) == 0) acc[((size_t)kh * max_units + unit) * 4 + (lane >> 3)] += c;
+    if (dbg_on) d_red += clock64() - d1;
+  }
+  if (dbg_on) {
+    const int si = (int)(&sp - sh.plan);
+    sh.dbg_s[si * 4 + 0] += d_dot; sh.dbg_s[si * 4 + 1] += d_red; sh.dbg_s[si * 4 + 2] += 1;
   }
 }
 
@@ -448,11 +467,23 @@ __device__ __noinline__ void consume_tmem_step(const LstmShared& sh, const StepP
   const int unit = warp / sp.ksplit, kh = warp - unit * sp.ksplit;
   const int klen = sp.K / sp.ksplit;
   const uint32_t taddr = tmem_addr_of(sh.tmem_base, warp, sp.tmem_col);
+#ifdef TACO2DEC_LAT_STAMPS
+  const bool dbg_on = sh.dbg_s && warp == 0 && lane == 0;
+#else
+  constexpr bool dbg_on = false;
+#endif
+  const long long d0 = dbg_on ? clock64() : 0;
   float s[4];
   if (klen * WB == 2048) dot4_tmem<WB, 4>(taddr, xs + (size_t)kh * klen, lane, s);     // 64 columns
   else dot4_tmem<WB, 2>(taddr, xs + (size_t)kh * klen, lane, s);                        // 32 columns
+  long long d1 = 0;
+  if (dbg_on) { volatile float sink = s[0] + s[1] + s[2] + s[3]; (void)sink; d1 = clock64(); }
   const float c = butterfly4(s[0], s[1], s[2], s[3], lane);
   if ((lane & 7) == 0) acc[((size_t)kh * max_units + unit) * 4 + (lane >> 3)] += c;
+  if (dbg_on) {
+    const int si = (int)(&sp - sh.plan);
+    sh.dbg_s[si * 4 + 0] += d1 - d0; sh.dbg_s[si * 4 + 1] += clock64() - d1; sh.dbg_s[si * 4 + 2] += 1;
+  }
 }
 
 // runtime column-length dispatch (K / ksplit is one of 1024, 512, 256)
@@ -648,7 +679,10 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   const int n_steps = p.n_steps;
   // phase accounting of CTA 0 (diagnostics): accumulators in shared memory so that they cost no registers
   __shared__ long long ph[16];
+  __shared__ long long dbg_sm[64];
   if (tid < 16) ph[tid] = 0;
+  if (tid < 64) dbg_sm[tid] = 0;
+  sh.dbg_s = (p.dbg && lc == 0) ? dbg_sm : nullptr;
   __syncthreads();
   long long ph_t = clock64();
 #define LPH(slot)                                         \
@@ -705,6 +739,9 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     LPH(3)
     consume_step<WB>(sh, pl[3], sh.xpre, sh.acc1, kMaxU1, warp, lane);
     LPH(13)
+#ifdef TACO2DEC_LAT_EXPERIMENT_DOUBLE_D
+    consume_step<WB>(sh, pl[3], sh.xpre, sh.acc1, kMaxU1, warp, lane);   // timing experiment only (results are wrong)
+#endif
     __syncthreads();
     LPH(14)
     // attention-LSTM pointwise (gate order i,f,g,o), dropout on h and c when training
@@ -780,6 +817,8 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   }
   if (lc == 0 && tid == 0)
     for (int i = 0; i < 16; ++i) p.phase_clocks[i] = ph[i];
+  if (sh.dbg_s && tid == 0)
+    for (int i = 0; i < 64; ++i) p.dbg[i] = dbg_sm[i];
 #undef LPH
   if (any_tmem) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -789,38 +828,62 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// attention CTA: stream s, context feature slice g  (attention.py:330-398)
+// attention CTA: stream s, slice g of na  (attention.py:330-398)
+//
+// The na CTAs of a stream split the work twice:
+//   * energies by ATTENTION DIMENSION: CTA g owns a in [g*AS, (g+1)*AS), AS = A / na.  It gathers only that slice of the query
+//     partials (NL1 * AS words instead of NL1 * A), evaluates  e~_j = sum_{a in slice} v_a tanh(q_a + pm_ja)  for every position
+//     (A * Ts / na tanh instead of A * Ts: the energies were SFU-bound) and publishes the partial energies; every CTA then sums
+//     the na partials of each position in a fixed order (one more LL exchange, ~1 L2 round trip, for 4x-8x less work on the chain);
+//   * the context by ENCODER FEATURE as before: CTA g owns features [g*FS, (g+1)*FS).
 // ---------------------------------------------------------------------------------------------
+constexpr int kLatTsCap = 512;          // positions per stream the partial-energy exchange is sized for
 __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* smem_raw) {
   const LatStream& sp = p.st[s];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Ts = sp.Ts;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int Ts = sp.Ts, na = sp.na;
   const int Teff = sp.len ? min((int)sp.len[0], Ts) : Ts;
-  const int FS = E / sp.na;                 // context features owned by this CTA (64 or 128)
+  const int FS = E / na;                    // context features owned by this CTA (64 or 128)
+  const int AS = A / na;                    // attention dimensions owned by this CTA (16 or 32)
   const int NJ = kThreads / FS;             // position groups in the context reduction
+  const int NL1 = p.NL1;
+  const int nq = NL1 * AS;                  // query-partial words this CTA gathers
   float* sm = reinterpret_cast<float*>(smem_raw);
-  float* pm_s = sm;                         // [Ts][A]
-  float* mem_s = pm_s + (size_t)Ts * A;     // [Ts][FS]
-  float* q_s = mem_s + (size_t)Ts * FS;     // [4][A] partial sums, then q in row 0
-  float* v_s = q_s + 4 * A;                 // [A]
-  float* red_s = v_s + A;                   // [NJ][FS] = kThreads
+  float* pm_s = sm;                         // [Ts][AS]   own slice of the processed memory
+  float* mem_s = pm_s + (size_t)Ts * AS;    // [Ts][FS]
+  float* qp_s = mem_s + (size_t)Ts * FS;    // [NL1][AS] gathered partials
+  float* q8_s = qp_s + (size_t)kThreads * 4;   // [8][AS]
+  float* q_s = q8_s + 8 * 32;               // [AS]
+  float* v_s = q_s + 32;                    // [AS]
+  float* red_s = v_s + 32;                  // [NJ][FS] = kThreads
   float* al_s = red_s + kThreads;           // [Ts] alignment state
   float* pr_s = al_s + Ts;                  // [Ts + 4] probabilities
   float* an_s = pr_s + Ts + 4;              // [Ts] new alignment
   __shared__ int s_stop;
 
-  for (int i = tid; i < Ts * A; i += kThreads) pm_s[i] = sp.pm[i];
+  for (int i = tid; i < Ts * AS; i += kThreads) {
+    const int j = i / AS, a = i - j * AS;
+    pm_s[i] = sp.pm[(size_t)j * A + g * AS + a];
+  }
   for (int i = tid; i < Ts * FS; i += kThreads) {
     const int j = i / FS, f = i - j * FS;
     mem_s[i] = sp.mem[(size_t)j * E + g * FS + f];
   }
-  for (int i = tid; i < A; i += kThreads) v_s[i] = sp.v[i];
+  for (int i = tid; i < AS; i += kThreads) v_s[i] = sp.v[g * AS + i];
   for (int i = tid; i < Ts; i += kThreads) al_s[i] = i == 0 ? 1.0f : 0.0f;   // attention.py:324-328
   if (tid == 0) s_stop = 0;
   __syncthreads();
 
   Watch wd{p.abort_flag, 0, 0};
-  const int NL1 = p.NL1;
+  __shared__ long long aph[16];
+  if (tid < 16) aph[tid] = 0;
+  __syncthreads();
+  const bool adbg = p.dbg && g == 0 && tid == 0;
+  long long aph_t = clock64();
+#define APH(slot) if (adbg) { const long long n_ = clock64(); aph[slot] += n_ - aph_t; aph_t = n_; }
+  // energies: 4 lanes per position, APL attention dimensions per lane
+  const int APL = AS / 4;
+  const int el = tid & 3;
   for (int t = 0; t < p.n_steps; ++t) {
     const unsigned tag = (unsigned)t + 1u;
     const int rb = t % kLLDepth;
@@ -833,71 +896,114 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
       __syncthreads();
       if (s_stop) break;
     }
-    // ---- q = sum over LSTM CTAs of their partials: thread (part, a) owns CTAs part, part+4, ... ----
+    APH(0)
+    // ---- own slice of the query partials: word i = (LSTM CTA c, a') with a' fastest; <= 4 words per thread ----
     {
-      const int part = tid >> 7, a = tid & (A - 1);
-      const unsigned long long* src = p.ll_q + ((size_t)rb * 2 + s) * NL1 * A + a;
-      constexpr int KQ = 16;                       // words in flight per thread per round
-      float acc = 0.f;
+      const unsigned long long* src = p.ll_q + ((size_t)rb * 2 + s) * NL1 * A + g * AS;
+      unsigned pending = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (tid + k * kThreads < nq) pending |= 1u << k;
       bool good = true;
-      for (int c0 = part; c0 < NL1 && good; c0 += 4 * KQ) {
-        unsigned pending = 0;
-        float val[KQ];
+      wd.arm();
+      while (pending) {
+        unsigned long long w[4];
 #pragma unroll
-        for (int k = 0; k < KQ; ++k) {
-          val[k] = 0.f;
-          if (c0 + 4 * k < NL1) pending |= 1u << k;
-        }
-        wd.arm();
-        while (pending) {
-          unsigned long long w[KQ];
+        for (int k = 0; k < 4; ++k)
+          if (pending & (1u << k)) {
+            const int i = tid + k * kThreads, c = i / AS, a = i - c * AS;
+            w[k] = ll_load(src + (size_t)c * A + a);
+          }
 #pragma unroll
-          for (int k = 0; k < KQ; ++k)
-            if (pending & (1u << k)) w[k] = ll_load(src + (size_t)(c0 + 4 * k) * A);
-#pragma unroll
-          for (int k = 0; k < KQ; ++k)
-            if ((pending & (1u << k)) && (unsigned)(w[k] >> 32) == tag) {
-              val[k] = __uint_as_float((unsigned)w[k]);
-              pending &= ~(1u << k);
-            }
-          if (pending && wd.expired()) { good = false; break; }
-        }
-#pragma unroll
-        for (int k = 0; k < KQ; ++k) acc += val[k];      // fixed order: deterministic
+        for (int k = 0; k < 4; ++k)
+          if ((pending & (1u << k)) && (unsigned)(w[k] >> 32) == tag) {
+            qp_s[tid + k * kThreads] = __uint_as_float((unsigned)w[k]);
+            pending &= ~(1u << k);
+          }
+        if (pending && wd.expired()) { good = false; break; }
       }
       if (!good) s_stop = 1;
-      q_s[part * A + a] = acc;
+    }
+    APH(1)
+    __syncthreads();
+    APH(2)
+    if (s_stop) break;
+    if (tid < 8 * AS) {                      // fixed-order tree: 8 groups of LSTM CTAs, then the 8 group sums
+      const int part = tid / AS, a = tid - part * AS;
+      float acc = 0.f;
+      for (int c = part; c < NL1; c += 8) acc += qp_s[c * AS + a];
+      q8_s[part * 32 + a] = acc;
     }
     __syncthreads();
-    if (s_stop) break;
-    if (tid < A) q_s[tid] = (q_s[tid] + q_s[A + tid]) + (q_s[2 * A + tid] + q_s[3 * A + tid]);
-    __syncthreads();
-    // ---- energies e_j = v . tanh(q + pm_j), p_j = sigmoid(e_j [+ 2 N(0,1)]); a warp does 4 positions ----
-    {
-      const float q0 = q_s[lane], q1 = q_s[lane + 32], q2 = q_s[lane + 64], q3 = q_s[lane + 96];
-      const float v0 = v_s[lane], v1 = v_s[lane + 32], v2 = v_s[lane + 64], v3 = v_s[lane + 96];
-      for (int j0 = warp * 4; j0 < Teff; j0 += kWarps * 4) {
-        float e[4];
+    if (tid < AS) {
+      float acc = 0.f;
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) {
-          const int j = min(j0 + pp, Teff - 1);
-          const float* r = pm_s + (size_t)j * A;
-          e[pp] = v0 * fast_tanh(q0 + r[lane]) + v1 * fast_tanh(q1 + r[lane + 32]) +
-                  v2 * fast_tanh(q2 + r[lane + 64]) + v3 * fast_tanh(q3 + r[lane + 96]);
-        }
-        float ev = butterfly4(e[0], e[1], e[2], e[3], lane);
-        const int j = j0 + (lane >> 3);
-        if ((lane & 7) == 0 && j < Teff) {
+      for (int k = 0; k < 8; ++k) acc += q8_s[k * 32 + tid];
+      q_s[tid] = acc;
+    }
+    __syncthreads();
+    APH(3)
+    // ---- partial energies of every position over the own attention dimensions ----
+    {
+      unsigned long long* dst = p.ll_e + (((size_t)rb * 2 + s) * 8 + g) * kLatTsCap;
+      float qv[8], vv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        qv[i] = i < APL ? q_s[el * APL + i] : 0.f;
+        vv[i] = i < APL ? v_s[el * APL + i] : 0.f;
+      }
+      for (int j0 = 0; j0 < Teff; j0 += kThreads / 4) {
+        const int j = j0 + (tid >> 2), jc = min(j, Teff - 1);
+        const float* r = pm_s + (size_t)jc * AS + el * APL;
+        float e = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < APL) e = fmaf(vv[i], fast_tanh(qv[i] + r[i]), e);
+        e += __shfl_xor_sync(0xffffffffu, e, 1);
+        e += __shfl_xor_sync(0xffffffffu, e, 2);
+        if (el == 0 && j < Teff) ll_store(dst + j, e, tag);
+      }
+    }
+    // ---- e_j = sum of the na partials (fixed order), p_j = sigmoid(e_j [+ 2 N(0,1)]) ----
+    {
+      const unsigned long long* src = p.ll_e + ((size_t)rb * 2 + s) * 8 * kLatTsCap;
+      bool good = true;
+      for (int j = tid; j < Ts; j += kThreads) {
+        float pr = 0.f;                                           // sigmoid(-inf) beyond the length, attention.py:388-391
+        if (j < Teff) {
+          unsigned pending = (1u << na) - 1u;
+          float val[8];
+          wd.arm();
+          while (pending) {
+            unsigned long long w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (pending & (1u << k)) w[k] = ll_load(src + (size_t)k * kLatTsCap + j);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if ((pending & (1u << k)) && (unsigned)(w[k] >> 32) == tag) {
+                val[k] = __uint_as_float((unsigned)w[k]);
+                pending &= ~(1u << k);
+              }
+            if (pending && wd.expired()) { good = false; break; }
+          }
+          float ev = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < na) ev += val[k];
           if (p.training) {
             const float nz = sp.noise ? sp.noise[(size_t)t * Ts + j] : philox_normal(p.seed, 10 + s, t, j);
             ev += 2.0f * nz;
           }
-          pr_s[j] = sigmoid_acc(ev);
+          pr = sigmoid_acc(ev);
         }
+        pr_s[j] = pr;
       }
-      for (int j = Teff + tid; j < Ts; j += kThreads) pr_s[j] = 0.f;   // sigmoid(-inf), attention.py:388-391
+      if (!good) s_stop = 1;
     }
     __syncthreads();
+    APH(4)
+    if (s_stop) break;
     // ---- alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1}) -------------------------------
     for (int j = tid; j < Ts; j += kThreads) {
       float a = al_s[j] * pr_s[j];
@@ -907,23 +1013,38 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
       if (g == 0) sp.align[(size_t)t * Ts + j] = a;
     }
     __syncthreads();
-    // ---- context slice: NJ position groups x FS features ----------------------------------
+    APH(5)
+    // ---- context slice: NJ position groups x FS features, 4 independent chains per thread ----
     {
       const int f = tid % FS, jg = tid / FS;
-      float acc = 0.f;
-      for (int j = jg; j < Ts; j += NJ) acc = fmaf(an_s[j], mem_s[(size_t)j * FS + f], acc);
-      red_s[jg * FS + f] = acc;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int j = jg;
+      for (; j + 3 * NJ < Ts; j += 4 * NJ) {
+        a0 = fmaf(an_s[j], mem_s[(size_t)j * FS + f], a0);
+        a1 = fmaf(an_s[j + NJ], mem_s[(size_t)(j + NJ) * FS + f], a1);
+        a2 = fmaf(an_s[j + 2 * NJ], mem_s[(size_t)(j + 2 * NJ) * FS + f], a2);
+        a3 = fmaf(an_s[j + 3 * NJ], mem_s[(size_t)(j + 3 * NJ) * FS + f], a3);
+      }
+      for (; j < Ts; j += NJ) a0 = fmaf(an_s[j], mem_s[(size_t)j * FS + f], a0);
+      red_s[jg * FS + f] = (a0 + a1) + (a2 + a3);
     }
     for (int j = tid; j < Ts; j += kThreads) al_s[j] = an_s[j];
     __syncthreads();
+    APH(6)
     if (tid < FS) {
       float c = 0.f;
       for (int k = 0; k < NJ; ++k) c += red_s[k * FS + tid];
 #pragma unroll
       for (int r = 0; r < kRep; ++r) ll_store(rep_ctx(p, r) + ((size_t)rb * 2 + s) * E + g * FS + tid, c, tag);
     }
+    APH(7)
     __syncthreads();
+    APH(8)
   }
+#undef APH
+  if (adbg)
+    for (int i = 0; i < 16; ++i) p.dbg[64 + 16 * s + i] = aph[i];
+  (void)lane;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -963,9 +1084,17 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
   }
   if (tid == 0) { s_stop = 0; s_stopval = 0; }
   if (tid < 16) own_s[tid] = 0.f;
+  const float row_bias = warp < nr ? (r0 + warp < M ? p.proj_b[r0 + warp] : p.gate_b[0]) : 0.f;
+  static_assert(2 * PR <= kWarps * 4, "prenet layer 1: one pass of 4 rows per warp");
   __syncthreads();
 
   Watch wd{p.abort_flag, 0, 0};
+  __shared__ long long xph[16];
+  if (tid < 16) xph[tid] = 0;
+  __syncthreads();
+  const bool xdbg = p.dbg && x == 0 && tid == 0;
+  long long xph_t = clock64();
+#define XPH(slot) if (xdbg) { const long long n_ = clock64(); xph[slot] += n_ - xph_t; xph_t = n_; }
   // prenet of frame 0 = prenet(go-frame of zeros) = zeros (model.py:444-450); stop word = 0
   if (p.free_running) {
     for (int i = tid; i < S * PR * kRep; i += kThreads) {
@@ -978,41 +1107,75 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
   for (int t = 0; t < p.n_steps; ++t) {
     const unsigned tag = (unsigned)t + 1u;
     const int rb = t % kLLDepth, rbn = (t + 1) % kLLDepth;
-    // ---- y = [h2_t | ctx_t | ctx_bert_t]; the context is published long before h2, poll it first ----
+    // ---- y = [h2_t | ctx_t | ctx_bert_t].  The context is published long before h2: its share of the projection rows and
+    //      the dropout bits of the next prenet are finished while the decoder LSTM is still running, so that only the
+    //      h2 half of each row (fully unrolled, every load in flight at once) sits between h2 and the prenet ----------
+    XPH(0)
     bool ok = poll_vector<2>(rep_ctx(p, x % kRep) + (size_t)rb * 2 * E, S * E, tag, y_s + H, tid, wd);
+    __syncthreads();
+    float pc = 0.f;                     // context part of this warp's row (all lanes)
+    if (warp < nr) {
+      const float* w = wp_s + (size_t)warp * KD + H;
+      float a0 = 0.f, a1 = 0.f;
+      for (int k = lane * 4; k < S * E; k += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(w + k);
+        const float4 b = *reinterpret_cast<const float4*>(y_s + H + k);
+        a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a0 = fmaf(a.z, b.z, a0); a1 = fmaf(a.w, b.w, a1);
+      }
+      pc = warp_sum(a0 + a1) + row_bias;
+    }
+    // dropout bits of the layer-1 rows this lane will publish (independent of the data)
+    bool kp1 = false;
+    {
+      const int it = warp * 4 + (lane >> 3);
+      if (p.free_running && it < S * PR) {
+        const int s = it / PR, r = it - s * PR, row = x * PR + r;
+        const uint8_t* keep = p.st[s].keep1;
+        kp1 = keep ? keep[(size_t)(t + 1) * P + row] != 0 : philox_keep_l(p.seed, s * 2 + 1, t + 1, row, p.thresh_pre);
+      }
+    }
+    XPH(1)
     ok = poll_vector<2>(rep_h2(p, x % kRep) + (size_t)rb * H, H, tag, y_s, tid, wd) && ok;
     if (!ok) s_stop = 1;
+    XPH(2)
     __syncthreads();
+    XPH(3)
     if (s_stop) break;
-    // ---- projection rows (one warp per row) ------------------------------------------------
+    // ---- projection rows (one warp per row), h2 half -----------------------------------------
     if (warp < nr) {
       const float* w = wp_s + (size_t)warp * KD;
-      float acc0 = 0.f, acc1 = 0.f;
-      for (int k = lane * 4; k < KD; k += 128) {
-        const float4 a = *reinterpret_cast<const float4*>(w + k);
-        const float4 b = *reinterpret_cast<const float4*>(y_s + k);
-        acc0 = fmaf(a.x, b.x, acc0); acc1 = fmaf(a.y, b.y, acc1); acc0 = fmaf(a.z, b.z, acc0); acc1 = fmaf(a.w, b.w, acc1);
+      float4 wa[H / 128], ya[H / 128];
+#pragma unroll
+      for (int i = 0; i < H / 128; ++i) {
+        wa[i] = *reinterpret_cast<const float4*>(w + lane * 4 + 128 * i);
+        ya[i] = *reinterpret_cast<const float4*>(y_s + lane * 4 + 128 * i);
       }
-      const float acc = warp_sum(acc0 + acc1);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < H / 128; ++i) {
+        a0 = fmaf(wa[i].x, ya[i].x, a0); a1 = fmaf(wa[i].y, ya[i].y, a1);
+        a2 = fmaf(wa[i].z, ya[i].z, a2); a3 = fmaf(wa[i].w, ya[i].w, a3);
+      }
+      const float acc = warp_sum((a0 + a1) + (a2 + a3)) + pc;
       if (lane == 0) {
         const int row = r0 + warp;
         if (row < M) {
-          const float v = acc + p.proj_b[row];
-          p.mel[(size_t)t * M + row] = v;
-          own_s[warp] = v;
+          p.mel[(size_t)t * M + row] = acc;
+          own_s[warp] = acc;
         } else {
-          const float gv = acc + p.gate_b[0];
-          p.gate[t] = gv;
+          p.gate[t] = acc;
           if (p.free_running) {
             int stop = 0;
-            if (sigmoid_acc(gv) > p.gate_thr) { stop = 1; p.n_frames[0] = t + 1; }            // model.py:480-481
+            if (sigmoid_acc(acc) > p.gate_thr) { stop = 1; p.n_frames[0] = t + 1; }            // model.py:480-481
             else if (t + 1 == p.n_steps) { stop = 1; p.n_frames[0] = t + 1; p.reached_max[0] = 1; }  // :482-485
             s_stopval = stop;
           }
         }
       }
     }
+    XPH(4)
     __syncthreads();
+    XPH(5)
     if (!p.free_running) {
       // nobody waits for the projection when teacher forcing: report progress for LL flow control
       if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.aux_done), "r"(1u) : "memory");
@@ -1030,6 +1193,7 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
       }
       if (tid == 0) ll_store(blk + 2 * P, s_stopval ? 1.f : 0.f, tag + 1u);   // meaningful in the gate owner's block
     }
+    XPH(6)
     // ---- gather the kAux partials (fixed order), relu + dropout(0.5) -> layer-0 activations -------------
     {
       const unsigned long long* base = p.ll_l0 + (size_t)rbn * kAux * LW;
@@ -1067,7 +1231,9 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
       }
       if (!good) s_stop = 1;
     }
+    XPH(7)
     __syncthreads();
+    XPH(8)
     if (s_stop) break;
     const bool stop = s_stopval != 0;
     if (x == 0 && tid < S * kRep)   // the stop word rides in every replica / stream block of the next frame's prenet
@@ -1083,31 +1249,43 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
     // ---- prenet layer 1 rows of this CTA: a warp does 4 rows at once, the butterfly leaves row g's sum in lane group g
     //      (8 lanes), and those 8 lanes publish it to the 8 replicas in parallel ---------------------------------------
     static_assert(kRep == 8, "one lane of a butterfly group per replica");
-    for (int it0 = warp * 4; it0 < S * PR; it0 += kWarps * 4) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const int it0 = warp * 4;
+      if (it0 < S * PR) {
+        const int s0 = it0 / PR;                         // the 4 rows of a warp belong to one stream (PR % 4 == 0)
+        const float* in = l0_s + (size_t)s0 * P;
+        const float* w = w1_s + ((size_t)s0 * PR + (it0 - s0 * PR)) * P;
+        float4 xv[P / 128], wv[4][P / 128];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int it = min(it0 + q, S * PR - 1), s = it / PR, r = it - s * PR;
-        const float* w = w1_s + ((size_t)s * PR + r) * P;
-        const float* in = l0_s + (size_t)s * P;
+        for (int i = 0; i < P / 128; ++i) {
+          xv[i] = *reinterpret_cast<const float4*>(in + lane * 4 + 128 * i);
 #pragma unroll
-        for (int k = lane * 4; k < P; k += 128) {
-          const float4 a = *reinterpret_cast<const float4*>(w + k);
-          const float4 b = *reinterpret_cast<const float4*>(in + k);
-          acc[q] = fmaf(a.x, b.x, acc[q]); acc[q] = fmaf(a.y, b.y, acc[q]); acc[q] = fmaf(a.z, b.z, acc[q]); acc[q] = fmaf(a.w, b.w, acc[q]);
+          for (int q = 0; q < 4; ++q) wv[q][i] = *reinterpret_cast<const float4*>(w + (size_t)q * P + lane * 4 + 128 * i);
         }
-      }
-      const float v = butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
-      const int it = it0 + (lane >> 3), rr = lane & 7;
-      if (it < S * PR) {
-        const int s = it / PR, r = it - s * PR, row = x * PR + r;
-        const uint8_t* keep = p.st[s].keep1;
-        const bool kp = keep ? keep[(size_t)(t + 1) * P + row] != 0 : philox_keep_l(p.seed, s * 2 + 1, t + 1, row, p.thresh_pre);
-        ll_store(rep_pre(p, rr) + ((size_t)rbn * 2 + s) * (P + 8) + row, kp ? fmaxf(v, 0.f) * 2.0f : 0.f, tag + 1u);
+        float acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < P / 128; ++i) {
+            e0 = fmaf(wv[q][i].x, xv[i].x, e0); e1 = fmaf(wv[q][i].y, xv[i].y, e1);
+            e0 = fmaf(wv[q][i].z, xv[i].z, e0); e1 = fmaf(wv[q][i].w, xv[i].w, e1);
+          }
+          acc[q] = e0 + e1;
+        }
+        const float v = butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
+        const int it = it0 + (lane >> 3), rr = lane & 7;
+        const int r = it - s0 * PR, row = x * PR + r;
+        ll_store(rep_pre(p, rr) + ((size_t)rbn * 2 + s0) * (P + 8) + row, kp1 ? fmaxf(v, 0.f) * 2.0f : 0.f, tag + 1u);
       }
     }
+    XPH(9)
     __syncthreads();
+    XPH(10)
   }
+#undef XPH
+  if (xdbg)
+    for (int i = 0; i < 16; ++i) p.dbg[96 + i] = xph[i];
 }
 
 template <int WB>

@@ -952,6 +952,7 @@ __global__ void philox_mask_kernel(unsigned long long seed, int mask_id, int row
 // ------------------------------------------------------------------------------------------
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int env_int(const char* name, int dflt);
 #define CUDA_TRY(x)                                                                              \
   do {                                                                                           \
     cudaError_t e_ = (x);                                                                        \
@@ -1168,9 +1169,9 @@ bool lat_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
   const LatGeometry g = lat_geometry(h, 4);
   const int Ts[2] = {T_in, T_sub};
   for (int s = 0; s < c.n_streams; ++s) {
-    const size_t fs = lat::E / g.na[s];
-    const size_t att = ((size_t)Ts[s] * (lat::A + fs) + 5 * lat::A + lat::kThreads + 3 * (size_t)Ts[s] + 8) * sizeof(float);
-    if (att > kLatDynSmem) return false;
+    const size_t fs = lat::E / g.na[s], as = lat::A / g.na[s];
+    const size_t att = ((size_t)Ts[s] * (as + fs) + 4 * lat::kThreads + 8 * 32 + 64 + lat::kThreads + 3 * (size_t)Ts[s] + 8) * sizeof(float);
+    if (att > kLatDynSmem || Ts[s] > lat::kLatTsCap) return false;
   }
   return true;
 }
@@ -1178,7 +1179,7 @@ bool lat_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
 size_t lat_ll_words(const taco2dec_handle* h) {
   const size_t d = lat::kLLDepth, r = lat::kRep;
   return r * (d * 2 * lat::H + d * lat::H + d * 2 * lat::E + d * 2 * (lat::P + 8)) + d * 2 * (size_t)h->num_sms * lat::A +
-         d * (lat::M + 16) + d * lat::kAux * (2 * lat::P + 8) + 64;
+         d * (lat::M + 16) + d * lat::kAux * (2 * lat::P + 8) + d * 2 * 8 * (size_t)lat::kLatTsCap + 64;
 }
 
 int lat_pack_weights(taco2dec_handle* h, const LatGeometry& g, cudaStream_t st) {
@@ -1265,9 +1266,16 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   p.ll_pre = w; w += r * d * 2 * (lat::P + 8);
   p.ll_mel = w; w += d * (lat::M + 16);
   p.ll_l0 = w; w += d * lat::kAux * (2 * lat::P + 8);
+  p.ll_e = w; w += d * 2 * 8 * (size_t)lat::kLatTsCap;
   p.aux_done = (unsigned*)w;
   p.abort_flag = gp.abort_flag;
   p.phase_clocks = gp.phase_clocks;
+  p.dbg = nullptr;
+  if (env_int("TACO2DEC_LAT_DEBUG", 0)) {        // diagnostics: per-role cycle sums, read with taco2dec_read_debug_stamps
+    if (!h->pb_dbg) CUDA_TRY(cudaMalloc(&h->pb_dbg, 256 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(h->pb_dbg, 0, 256 * sizeof(long long), st));
+    p.dbg = h->pb_dbg;
+  }
   void* args[] = {(void*)&p};
   void* kern = g.wbytes == 4 ? (void*)lat::decoder_latency<4> : (void*)lat::decoder_latency<2>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));

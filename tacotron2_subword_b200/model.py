@@ -391,6 +391,7 @@ class Decoder(nn.Module):
         # fp32 accumulation, stated bound mel/gate <= 1e-3, alignments <= 2e-4 vs the fp32 reference; "fp32" = the generic
         # fp32-exact kernel (~15x slower at B = 64; no backward: training with it raises).
         self.batched_precision = "fp16"
+        self.max_backward_rows = 128       # rows one BPTT call takes (tcgen05 N limit); larger batches run as sub-batches
         self.dropout_replay: Optional[DropoutReplay] = None  # parity runs: externally drawn masks
         self.rng_seed: Optional[int] = None                  # fixed Philox seed; None = fresh per call
         self.validate_lengths = True
@@ -547,22 +548,21 @@ class Decoder(nn.Module):
         row b equals the batch-1 run on ``memory[b, :memory_lengths[b]]``, which is what the reference's GTA.py computes
         one utterance at a time.
 
-        With autograd enabled the outputs carry a hand-written backward (``_DecoderTF``) when the shape is
-        covered by the tensor path (2 <= B <= 128, default dims); other shapes raise at backward()."""
+        With autograd enabled the outputs carry a hand-written backward (``_DecoderTF``, tensor path, default dims):
+        2 <= B <= 128 in one BPTT call, B == 1 and B > 128 through ``_tf_autograd_resized``; other layer sizes raise at
+        backward()."""
         wants_grad = torch.is_grad_enabled() and (
             any(p.requires_grad for p in self.parameters()) or memory.requires_grad or
             (embeddings is not None and embeddings.requires_grad))
-        if wants_grad and self.decoder_path == "auto" and self.batched_precision == "fp32" and memory.shape[0] >= 2:
+        if wants_grad and self.decoder_path == "auto" and self.batched_precision == "fp32":
             raise NotImplementedError(
                 "tacotron2_subword_b200: batched_precision='fp32' has no backward (the BPTT kernels use fp16 forward / "
                 "bf16 backward operands); train with batched_precision='fp16' or evaluate under torch.no_grad()")
         if wants_grad and self._backward_supported(memory):
-            params = self._weight_tensors()
-            outs = _DecoderTF.apply(self, bool(independent), memory, embeddings if self.n_streams == 2 else None, decoder_inputs,
-                                    memory_lengths, bert_lengths if self.n_streams == 2 else None, *params)
-            mel, gate, align = outs[0], outs[1], outs[2]
-            align_b = outs[3] if self.n_streams == 2 else None
-            return mel.transpose(1, 2), gate, align, align_b
+            B = memory.shape[0]
+            if B == 1 or B > self.max_backward_rows:
+                return self._tf_autograd_resized(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent)
+            return self._tf_autograd(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent)
         outs, _ = self._run_tf(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save=False,
                                independent=independent)
         mel, gate, align, align_b = outs
@@ -576,9 +576,75 @@ class Decoder(nn.Module):
     def _backward_supported(self, memory) -> bool:
         if self.attention_kind == LSA and (self.loc_filters, self.loc_kernel) != (32, 31):
             return False
-        return (2 <= memory.shape[0] <= 128 and self.decoder_path in ("auto", "tensor", "tensor_graph")
+        return (memory.shape[0] >= 1 and self.decoder_path in ("auto", "tensor", "tensor_graph")
                 and (self.attention_rnn_dim, self.decoder_rnn_dim, self.encoder_embedding_dim, self.prenet_dim,
                      self.attention_dim, self.n_mel_channels) == (1024, 1024, 512, 256, 128, 80))
+
+    def _tf_autograd(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent):
+        """One differentiable teacher-forced pass on the tensor path (2 <= B <= max_backward_rows)."""
+        two = self.n_streams == 2
+        params = self._weight_tensors()
+        outs = _DecoderTF.apply(self, bool(independent), memory, embeddings if two else None, decoder_inputs,
+                                memory_lengths, bert_lengths if two else None, *params)
+        return outs[0].transpose(1, 2), outs[1], outs[2], (outs[3] if two else None)
+
+    def _tf_autograd_resized(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent):
+        """Batches the BPTT kernels do not take directly (train.py:330 trains whatever ``collate_fn`` emits, including
+        size-1 remainders, data_utils.py:146-160).  Utterances never interact inside the decoder, so
+
+        * B == 1 runs as a batch of two whose second row is a detached copy of the first: its upstream gradients are
+          exactly zero, hence so is everything it adds to the weight gradients;
+        * B > max_backward_rows (128, the tcgen05 N limit) runs as consecutive sub-batches over the SAME padded memory
+          (so the SMA leakage onto padded positions is what the full batch would give); autograd sums their weight
+          gradients.  Each sub-batch draws from its own Philox stream; replayed masks are sliced along the batch."""
+        B = memory.shape[0]
+        two = self.n_streams == 2
+        saved = (self.dropout_replay, self.rng_seed, self.validate_lengths)
+        rp = saved[0]
+
+        def rows(t, dim, sl, dup):
+            if t is None:
+                return None
+            if dup:
+                return torch.cat([t, t], dim)
+            idx = [slice(None)] * t.dim()
+            idx[dim] = sl
+            return t[tuple(idx)]
+
+        def replay_for(sl, dup):
+            if rp is None:
+                return None
+            pk = None if rp.prenet_keep is None else [[rows(m, 1, sl, dup) for m in row] for row in rp.prenet_keep]
+            nz = None if rp.sma_noise is None else [rows(n, 1, sl, dup) for n in rp.sma_noise]
+            return DropoutReplay(pk, rows(rp.lstm_keep, 2, sl, dup), nz)
+
+        if self.validate_lengths:            # once, on the whole batch (a sub-batch need not contain the longest utterance)
+            if memory_lengths is not None and int(memory_lengths.max()) != memory.shape[1]:
+                raise ValueError("memory.size(1) must equal max(memory_lengths) (utils.py:11, model.py:414)")
+            if two and bert_lengths is not None and int(bert_lengths.max()) != embeddings.shape[1]:
+                raise ValueError("embeddings.size(1) must equal max(bert_lengths)")
+        try:
+            self.validate_lengths = False
+            if B == 1:
+                dd = lambda t: None if t is None else torch.cat([t, t.detach()], 0)
+                self.dropout_replay = replay_for(None, True)
+                outs = self._tf_autograd(dd(memory), dd(embeddings) if two else None, dd(decoder_inputs), dd(memory_lengths),
+                                         dd(bert_lengths) if two else None, independent)
+                return tuple(None if o is None else o[:1] for o in outs)
+            n_sub = -(-B // self.max_backward_rows)           # balanced sub-batches: sizes differ by at most one, none is 1
+            bounds = [B * k // n_sub for k in range(n_sub + 1)]
+            parts = []
+            for k in range(n_sub):
+                sl = slice(bounds[k], bounds[k + 1])
+                cut = lambda t: None if t is None else t[sl]
+                self.dropout_replay = replay_for(sl, False)
+                if saved[1] is not None:
+                    self.rng_seed = (int(saved[1]) + 0x9E3779B97F4A7C15 * k) % (1 << 62)
+                parts.append(self._tf_autograd(cut(memory), cut(embeddings) if two else None, cut(decoder_inputs),
+                                               cut(memory_lengths), cut(bert_lengths) if two else None, independent))
+            return tuple(None if parts[0][i] is None else torch.cat([p_[i] for p_ in parts], 0) for i in range(4))
+        finally:
+            self.dropout_replay, self.rng_seed, self.validate_lengths = saved
 
     def _run_tf(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save: bool, independent: bool = False):
         """One ``taco2dec_forward_teacher_forced`` call; mel is returned in its storage layout [B,T,n_mel]."""

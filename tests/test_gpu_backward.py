@@ -83,6 +83,44 @@ def test_backward_vs_oracle_autograd(B, T, training, tf32, T_in, T_sub):
     print({k: f"{v:.2e}" for k, v in worst.items()})
     assert not bad, f"relative gradient error above {TOL_GRAD}: {bad}"
 
+@pytest.mark.parametrize("B,rows,training", [(1, 128, True), (1, 128, False), (11, 4, True), (130, 128, False)])
+def test_backward_batch1_and_sub_batches(B, rows, training):
+    """Batches outside one BPTT call (train.py:330 trains whatever collate_fn emits, data_utils.py:146-160): B = 1 runs as a
+    padded pair, B > max_backward_rows as balanced sub-batches over the same padded memory; outputs and every gradient must
+    equal autograd through the oracle on the whole batch (replayed masks sliced along the batch)."""
+    T, T_in, T_sub, seed = 4, 22, 7, 700 + B
+    w = make_decoder_weights(SMA, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=B > 1)
+    plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, training, seed=seed + 1)
+    want, want_dmem, want_demb, want_outs = _oracle_grads(w, inp, plan, training)
+    dec = make_decoder(w, SMA, exact=False)
+    dec.max_backward_rows = rows
+    dec.dropout_replay = replay_of(plan)
+    dec.train(training)
+    mem = inp["memory"].cuda().requires_grad_(True)
+    emb = inp["embeddings"].cuda().requires_grad_(True)
+    outs = dec(mem, emb, inp["mels"].cuda(), inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+    for o, wo in zip(outs, want_outs):
+        assert o.shape == wo.shape
+        assert (o.detach().cpu() - wo.detach()).abs().max() < 1e-3
+    _loss(outs, 5).backward()
+    torch.cuda.synchronize()
+    sd = dict(dec.named_parameters())
+    worst = {}
+    for name, gw in want.items():
+        got = sd[name].grad
+        if gw is None:
+            assert got is None, name
+            continue
+        assert got is not None, f"{name}: no gradient"
+        worst[name] = float((got.cpu() - gw).abs().max()) / float(gw.abs().max())
+    for name, gw, got in (("memory", want_dmem, mem.grad), ("embeddings", want_demb, emb.grad)):
+        assert got.shape == gw.shape
+        worst[name] = float((got.cpu() - gw).abs().max() / gw.abs().max())
+    bad = {k: v for k, v in worst.items() if not v < TOL_GRAD}
+    assert not bad, f"relative gradient error above {TOL_GRAD}: {bad}"
+    assert dec.dropout_replay is not None and dec.validate_lengths and dec.max_backward_rows == rows     # state restored
+
 
 def test_backward_philox_masks_match_forward():
     """Production mode (no replay): backward re-draws the LSTM-state dropout masks from Philox.  Materialising the
@@ -122,8 +160,8 @@ def test_backward_philox_masks_match_forward():
 
 
 def test_backward_unsupported_shape_raises():
-    """Batch 1 (latency path) and a forced generic path have no backward kernel: the output must refuse backward() loudly."""
-    for B, path in ((1, "auto"), (4, "generic")):
+    """A forced latency / generic path has no backward kernel: the output must refuse backward() loudly."""
+    for B, path in ((1, "latency"), (4, "generic")):
         T, T_in, T_sub, seed = 3, 12, 4, 7
         w = make_decoder_weights(SMA, seed=seed)
         inp = make_inputs(B, T_in, T_sub, T, seed=seed)
