@@ -53,6 +53,7 @@ struct LatStream {
   const float *b_ih, *b_hh;      // attention LSTM biases [4H]
   const float *wq;               // [A, H]
   const float *v;                // [A]
+  const float *loc_conv, *loc_dense;   // location-sensitive attention: conv [LF, 2, LK], dense [A, LF] (else null)
   const float *pre_w0, *pre_w1;  // [P, M], [P, P]
   const float *mem;              // [T_s, E]   (batch 1)
   const float *pm;               // [T_s, A]   processed memory (precomputed)
@@ -68,6 +69,7 @@ struct LatStream {
 struct LatParams {
   int S, NL, NL1;                // streams, LSTM CTAs, LSTM CTAs per stream (attention LSTM split)
   int free_running, training, n_steps, Tcap;
+  int lsa, LF, LK;               // location-sensitive attention (attention.py:25-85) instead of stepwise-monotonic; its conv shape
   float gate_thr, p_att, p_dec;
   unsigned thresh_pre, thresh_att, thresh_dec;
   unsigned long long seed;
@@ -836,6 +838,12 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
 //     (A * Ts / na tanh instead of A * Ts: the energies were SFU-bound) and publishes the partial energies; every CTA then sums
 //     the na partials of each position in a fixed order (one more LL exchange, ~1 L2 round trip, for 4x-8x less work on the chain);
 //   * the context by ENCODER FEATURE as before: CTA g owns features [g*FS, (g+1)*FS).
+//
+// Location-sensitive attention (attention.py:25-85, model.py:355-359) uses the same split.  Its location term
+//   loc_j[a] = sum_f Wd[a][f] . conv1d([alpha[t-1]; cum[t-1]])_j[f]
+// depends only on the PREVIOUS frame's weights, so every CTA computes it for its own attention dimensions right after it has
+// published the context of frame t-1 -- off the critical path, while the LSTM CTAs are busy -- and the chain from the query
+// to the context only gains the softmax (two block reductions) over the stepwise-monotonic variant.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLatTsCap = 512;          // positions per stream the partial-energy exchange is sized for
 __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* smem_raw) {
@@ -856,10 +864,18 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
   float* q_s = q8_s + 8 * 32;               // [AS]
   float* v_s = q_s + 32;                    // [AS]
   float* red_s = v_s + 32;                  // [NJ][FS] = kThreads
-  float* al_s = red_s + kThreads;           // [Ts] alignment state
+  // location-sensitive attention only (16-byte aligned blocks before the T-dependent scalar arrays)
+  const bool lsa = p.lsa != 0;
+  const int LF = p.LF, LK = p.LK, pad = (LK - 1) / 2, Tp = (Ts + 2 * pad + 2 + 3) & ~3;
+  float* loc_s = red_s + kThreads;          // [Ts][AS]  location term of the coming frame, own attention dimensions
+  float* wf_s = loc_s + (lsa ? (size_t)Ts * AS : 0);   // [2][LK][AS]  location conv and dense folded into one map (both bias-free linear)
+  float* ap_s = wf_s + (lsa ? 2 * LK * AS : 0);        // [Tp] zero-padded previous weights
+  float* ac_s = ap_s + (lsa ? Tp : 0);      // [Tp] zero-padded cumulative weights
+  float* al_s = ac_s + (lsa ? Tp : 0);      // [Ts] alignment state
   float* pr_s = al_s + Ts;                  // [Ts + 4] probabilities
   float* an_s = pr_s + Ts + 4;              // [Ts] new alignment
   __shared__ int s_stop;
+  __shared__ float s_red[kWarps];
 
   for (int i = tid; i < Ts * AS; i += kThreads) {
     const int j = i / AS, a = i - j * AS;
@@ -871,6 +887,17 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
   }
   for (int i = tid; i < AS; i += kThreads) v_s[i] = sp.v[g * AS + i];
   for (int i = tid; i < Ts; i += kThreads) al_s[i] = i == 0 ? 1.0f : 0.0f;   // attention.py:324-328
+  if (lsa) {
+    // loc_j[a] = sum_f Wd[a][f] sum_{c,k} Wc[f][c][k] x_c[j+k-pad]  =  sum_{c,k} Wf[c][k][a] x_c[j+k-pad]   (attention.py:12-23)
+    for (int i = tid; i < 2 * LK * AS; i += kThreads) {
+      const int a = i % AS, ck = i / AS;
+      float acc = 0.f;
+      for (int f = 0; f < LF; ++f) acc = fmaf(sp.loc_dense[(size_t)(g * AS + a) * LF + f], sp.loc_conv[(size_t)f * 2 * LK + ck], acc);
+      wf_s[i] = acc;
+    }
+    for (int i = tid; i < Tp; i += kThreads) { ap_s[i] = 0.f; ac_s[i] = 0.f; }      // model.py:277-280: both start at zero
+    for (int i = tid; i < Ts * AS; i += kThreads) loc_s[i] = 0.f;                   // hence so does the location term
+  }
   if (tid == 0) s_stop = 0;
   __syncthreads();
 
@@ -955,10 +982,11 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
       for (int j0 = 0; j0 < Teff; j0 += kThreads / 4) {
         const int j = j0 + (tid >> 2), jc = min(j, Teff - 1);
         const float* r = pm_s + (size_t)jc * AS + el * APL;
+        const float* lc = loc_s + (size_t)jc * AS + el * APL;
         float e = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (i < APL) e = fmaf(vv[i], fast_tanh(qv[i] + r[i]), e);
+          if (i < APL) e = fmaf(vv[i], fast_tanh(qv[i] + r[i] + (lsa ? lc[i] : 0.f)), e);
         e += __shfl_xor_sync(0xffffffffu, e, 1);
         e += __shfl_xor_sync(0xffffffffu, e, 2);
         if (el == 0 && j < Teff) ll_store(dst + j, e, tag);
@@ -991,11 +1019,17 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             if (k < na) ev += val[k];
-          if (p.training) {
-            const float nz = sp.noise ? sp.noise[(size_t)t * Ts + j] : philox_normal(p.seed, 10 + s, t, j);
-            ev += 2.0f * nz;
+          if (lsa) {
+            pr = ev;
+          } else {
+            if (p.training) {
+              const float nz = sp.noise ? sp.noise[(size_t)t * Ts + j] : philox_normal(p.seed, 10 + s, t, j);
+              ev += 2.0f * nz;
+            }
+            pr = sigmoid_acc(ev);
           }
-          pr = sigmoid_acc(ev);
+        } else if (lsa) {
+          pr = -INFINITY;                                         // masked_fill_(mask, -inf), attention.py:79
         }
         pr_s[j] = pr;
       }
@@ -1004,13 +1038,43 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
     __syncthreads();
     APH(4)
     if (s_stop) break;
-    // ---- alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1}) -------------------------------
-    for (int j = tid; j < Ts; j += kThreads) {
-      float a = al_s[j] * pr_s[j];
-      if (j > 0) a += al_s[j - 1] * (1.0f - pr_s[j - 1]);
-      if (p.free_running && j >= Teff) a = 0.f;
-      an_s[j] = a;
-      if (g == 0) sp.align[(size_t)t * Ts + j] = a;
+    if (lsa) {
+      // ---- alpha = softmax(e) over the positions (attention.py:81); every thread owns at most one position ----
+      static_assert(kLatTsCap <= kThreads, "one position per thread in the softmax");
+      const int warp = tid >> 5;
+      const float ev = tid < Ts ? pr_s[tid] : -INFINITY;
+      float m = ev;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) s_red[warp] = m;
+      __syncthreads();
+      m = s_red[0];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) m = fmaxf(m, s_red[w]);
+      __syncthreads();
+      const float ex = tid < Ts ? expf(ev - m) : 0.f;
+      float sum = warp_sum(ex);
+      if (lane == 0) s_red[warp] = sum;
+      __syncthreads();
+      sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) sum += s_red[w];
+      if (tid < Ts) {
+        const float a = ex / sum;
+        an_s[tid] = a;
+        ap_s[pad + tid] = a;
+        ac_s[pad + tid] += a;                                     // model.py:358-359
+        if (g == 0) sp.align[(size_t)t * Ts + tid] = a;
+      }
+    } else {
+      // ---- alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1}) -------------------------------
+      for (int j = tid; j < Ts; j += kThreads) {
+        float a = al_s[j] * pr_s[j];
+        if (j > 0) a += al_s[j - 1] * (1.0f - pr_s[j - 1]);
+        if (p.free_running && j >= Teff) a = 0.f;
+        an_s[j] = a;
+        if (g == 0) sp.align[(size_t)t * Ts + j] = a;
+      }
     }
     __syncthreads();
     APH(5)
@@ -1038,6 +1102,33 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
       for (int r = 0; r < kRep; ++r) ll_store(rep_ctx(p, r) + ((size_t)rb * 2 + s) * E + g * FS + tid, c, tag);
     }
     APH(7)
+    if (lsa) {
+      // ---- off the critical path: location term of frame t+1 for the own attention dimensions from the weights just
+      //      computed; a thread does 2 consecutive positions x 4 dimensions, the windows slide through registers ----
+      const int A4 = AS / 4, n_items = A4 * ((Teff + 1) / 2);
+      for (int it = tid; it < n_items; it += kThreads) {
+        const int a4 = it % A4, j0 = 2 * (it / A4);
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float x0 = ap_s[j0], c0 = ac_s[j0];
+        for (int k = 0; k < LK; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wf_s + (size_t)k * AS + 4 * a4);
+          const float4 w1 = *reinterpret_cast<const float4*>(wf_s + (size_t)(LK + k) * AS + 4 * a4);
+          const float x1 = ap_s[j0 + k + 1], c1 = ac_s[j0 + k + 1];
+          acc[0][0] = fmaf(w0.x, x0, acc[0][0]); acc[0][1] = fmaf(w0.y, x0, acc[0][1]);
+          acc[0][2] = fmaf(w0.z, x0, acc[0][2]); acc[0][3] = fmaf(w0.w, x0, acc[0][3]);
+          acc[1][0] = fmaf(w0.x, x1, acc[1][0]); acc[1][1] = fmaf(w0.y, x1, acc[1][1]);
+          acc[1][2] = fmaf(w0.z, x1, acc[1][2]); acc[1][3] = fmaf(w0.w, x1, acc[1][3]);
+          acc[0][0] = fmaf(w1.x, c0, acc[0][0]); acc[0][1] = fmaf(w1.y, c0, acc[0][1]);
+          acc[0][2] = fmaf(w1.z, c0, acc[0][2]); acc[0][3] = fmaf(w1.w, c0, acc[0][3]);
+          acc[1][0] = fmaf(w1.x, c1, acc[1][0]); acc[1][1] = fmaf(w1.y, c1, acc[1][1]);
+          acc[1][2] = fmaf(w1.z, c1, acc[1][2]); acc[1][3] = fmaf(w1.w, c1, acc[1][3]);
+          x0 = x1; c0 = c1;
+        }
+        *reinterpret_cast<float4*>(loc_s + (size_t)j0 * AS + 4 * a4) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+        if (j0 + 1 < Ts)
+          *reinterpret_cast<float4*>(loc_s + (size_t)(j0 + 1) * AS + 4 * a4) = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
+      }
+    }
     __syncthreads();
     APH(8)
   }

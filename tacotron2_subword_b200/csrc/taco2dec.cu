@@ -1161,7 +1161,9 @@ LatGeometry lat_geometry(const taco2dec_handle* h, int wbytes) {
 
 bool lat_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
   const taco2dec_config& c = h->cfg;
-  if (B != 1 || c.attention != TACO2DEC_ATTN_SMA) return false;
+  if (B != 1) return false;
+  const bool lsa = c.attention == TACO2DEC_ATTN_LSA;
+  if (lsa && (c.loc_filters < 1 || c.loc_filters > 32 || c.loc_kernel % 2 == 0 || c.loc_kernel > 63)) return false;
   if (c.attn_rnn_dim != lat::H || c.dec_rnn_dim != lat::H || c.enc_dim != lat::E || c.prenet_dim != lat::P ||
       c.attn_dim != lat::A || c.n_mel != lat::M)
     return false;
@@ -1170,8 +1172,10 @@ bool lat_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
   const int Ts[2] = {T_in, T_sub};
   for (int s = 0; s < c.n_streams; ++s) {
     const size_t fs = lat::E / g.na[s], as = lat::A / g.na[s];
-    const size_t att = ((size_t)Ts[s] * (as + fs) + 4 * lat::kThreads + 8 * 32 + 64 + lat::kThreads + 3 * (size_t)Ts[s] + 8) * sizeof(float);
-    if (att > kLatDynSmem || Ts[s] > lat::kLatTsCap) return false;
+    size_t att = (size_t)Ts[s] * (as + fs) + 4 * lat::kThreads + 8 * 32 + 64 + lat::kThreads + 3 * (size_t)Ts[s] + 8;
+    if (lsa)    // location term, folded conv . dense weights, zero-padded previous and cumulative weights
+      att += (size_t)Ts[s] * as + 2 * (size_t)c.loc_kernel * as + 2 * ((size_t)Ts[s] + c.loc_kernel + 5);
+    if (att * sizeof(float) > kLatDynSmem || Ts[s] > lat::kLatTsCap) return false;
   }
   return true;
 }
@@ -1232,6 +1236,7 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   p.S = c.n_streams; p.NL = g.NL; p.NL1 = g.NL1;
   p.free_running = gp.free_running; p.training = gp.training; p.n_steps = gp.free_running ? gp.max_steps : gp.T;
   p.Tcap = gp.Tcap; p.gate_thr = gp.gate_thr; p.p_att = gp.p_att; p.p_dec = gp.p_dec;
+  p.lsa = c.attention == TACO2DEC_ATTN_LSA ? 1 : 0; p.LF = p.lsa ? c.loc_filters : 0; p.LK = p.lsa ? c.loc_kernel : 1;
   p.thresh_pre = gp.thresh_pre; p.thresh_att = gp.thresh_att; p.thresh_dec = gp.thresh_dec; p.seed = gp.seed;
   p.wbytes = g.wbytes; p.packed = h->packed; p.packed_off = h->packed_off;
   p.res_budget = g.res_budget;
@@ -1250,6 +1255,7 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
     const StreamParams& sp = gp.st[s];
     lat::LatStream& ls = p.st[s];
     ls.b_ih = sp.b_ih; ls.b_hh = sp.b_hh; ls.wq = sp.wq; ls.v = sp.v; ls.pre_w0 = sp.pre_w0; ls.pre_w1 = sp.pre_w1;
+    ls.loc_conv = sp.loc_conv; ls.loc_dense = sp.loc_dense;
     ls.mem = sp.mem; ls.pm = sp.pm; ls.pre_tf = sp.pre; ls.noise = sp.noise; ls.keep0 = sp.keep0; ls.keep1 = sp.keep1;
     ls.align = sp.align; ls.Ts = sp.Ts; ls.len = sp.len; ls.na = g.na[s];
   }
@@ -1788,7 +1794,7 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
   const bool want_lat = (h->path_mode == TACO2DEC_PATH_AUTO || h->path_mode == TACO2DEC_PATH_LATENCY) &&
                         lat_shape_ok(h, p.B, T_in, T_sub);
   if (h->path_mode == TACO2DEC_PATH_LATENCY && !want_lat)
-    return fail(TACO2DEC_E_ARG, "latency path needs B=1, SMA, default decoder dims and a short enough memory");
+    return fail(TACO2DEC_E_ARG, "latency path needs B=1, default decoder dims and a short enough memory");
   if (want_lat) return run_latency(h, p, st);
   if (tensor_mode && !tensor_ok)
     return fail(TACO2DEC_E_ARG, "tensor path needs 2 <= B <= 128 and default decoder dims");

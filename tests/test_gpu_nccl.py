@@ -87,6 +87,6 @@ def test_decoder_gradients_allreduced_over_nccl_match_mean_of_local_gradients():
     for rank, worst, n_coll, n_early, n_grads in out:
         assert n_grads == 26                                   # every live decoder parameter (decoder_rnn_bert is dead)
         # early (per-tensor, in place) reductions for the large tensors + at least one bucket for the small ones
-        assert n_early >= 8 and n_coll >= n_early + 1, (n_coll, n_early)
+        assert n_early >= 6 and n_coll >= n_early + 1, (n_coll, n_early)
         # same Philox seed, same kernels: the only difference is the order of the fp32 atomics inside the contractions
         assert worst < 5e-3, f"rank {rank}: all-reduced gradient off by {worst:.2e} of its scale"

@@ -10,6 +10,7 @@ import torch
 
 from oracle.decoder_oracle import DecoderOracle
 from oracle.synth import LSA, SMA, make_decoder_weights, make_dropout_plan, make_inputs
+from tacotron2_subword_b200 import DropoutReplay
 from tests.gpu_util import make_decoder, replay_of
 from tests.helpers import golden_names, load_golden, materialise, maxabs
 
@@ -52,9 +53,9 @@ def _cmp_tol(got, want, tol_mel, tol_align, tag=""):
 
 
 @pytest.mark.parametrize("path,wdtype,tol_mel,tol_align", PATHS)
-@pytest.mark.parametrize("name", [n for n in golden_names() if "lsa" not in n])
+@pytest.mark.parametrize("name", golden_names())
 def test_latency_path_matches_reference_golden(name, path, wdtype, tol_mel, tol_align):
-    """Batch-1 SMA goldens through the role-specialised latency kernel (fp32 and fp16 weight storage)
+    """Batch-1 goldens (SMA and LSA) through the role-specialised latency kernel (fp32 and fp16 weight storage)
     and, for comparison, the generic kernel.  Stop frames / INFER_FLAG exact in every mode."""
     recipe, gold, _ = load_golden(name)
     if recipe["B"] != 1:
@@ -80,22 +81,46 @@ def test_latency_path_matches_reference_golden(name, path, wdtype, tol_mel, tol_
     _cmp_tol(got, want, tol_mel, tol_align, f"{name} {path}/{wdtype}")
 
 
+@pytest.mark.parametrize("attention", [SMA, LSA])
 @pytest.mark.parametrize("path,wdtype,tol_mel,tol_align", PATHS[1:])
-def test_latency_path_training_mode_vs_oracle(path, wdtype, tol_mel, tol_align):
+def test_latency_path_training_mode_vs_oracle(path, wdtype, tol_mel, tol_align, attention):
     """B=1 teacher-forced train() (LSTM-state dropout on h and c + SMA noise, replayed) on the latency path."""
     T_in, T_sub, T, seed = 37, 12, 24, 9
-    w = make_decoder_weights(SMA, seed=seed)
+    w = make_decoder_weights(attention, seed=seed)
     inp = make_inputs(1, T_in, T_sub, T, seed=seed)
     plan = make_dropout_plan(1, T + 1, T, T_in, T_sub, True, seed=seed + 1)
-    want = DecoderOracle(w, SMA).forward(inp["memory"], inp["embeddings"], inp["mels"], inp["memory_lengths"],
-                                         inp["bert_lengths"], plan, training=True)
-    dec = make_decoder(w, SMA).train()
+    want = DecoderOracle(w, attention).forward(inp["memory"], inp["embeddings"], inp["mels"], inp["memory_lengths"],
+                                               inp["bert_lengths"], plan, training=True)
+    dec = make_decoder(w, attention).train()
     dec.decoder_path, dec.weight_dtype = path, wdtype
     dec.dropout_replay = replay_of(plan)
     with torch.no_grad():
         got = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(),
                   inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+    assert dec._engine(torch.device("cuda", 0)).last_path() == "latency"
     _cmp_tol(got, want, tol_mel, tol_align, f"train {path}/{wdtype}")
+
+
+@pytest.mark.parametrize("path,wdtype,tol_mel,tol_align", PATHS[1:])
+@pytest.mark.parametrize("T_in,T_sub,steps", [(150, 50, 300), (31, 9, 40), (333, 111, 25)])
+def test_latency_path_lsa_free_running_vs_oracle(path, wdtype, tol_mel, tol_align, T_in, T_sub, steps):
+    """Location-sensitive attention (attention.py:25-85) on the batch-1 latency kernel, free-running: location conv + dense
+    of the previous / cumulative weights, masked softmax, cumulative update (model.py:355-359); rows of alpha sum to 1."""
+    seed = 21
+    w = make_decoder_weights(LSA, seed=seed, gate_bias=-20.0)
+    inp = make_inputs(1, T_in, T_sub, 1, seed=seed)
+    plan = make_dropout_plan(1, steps + 1, steps, T_in, T_sub, False, seed=seed + 1)
+    omel, ogate, oal, oalb, oflag = DecoderOracle(w, LSA).inference(inp["memory"], inp["embeddings"], plan, max_decoder_steps=steps)
+    dec = make_decoder(w, LSA).eval()
+    dec.decoder_path, dec.weight_dtype = path, wdtype
+    dec.max_decoder_steps = steps
+    dec.dropout_replay = DropoutReplay(prenet_keep=[[m[:, :1].contiguous() for m in row] for row in plan.prenet_keep])
+    with torch.no_grad():
+        mel, gate, al, alb, flag = dec.inference(inp["memory"].cuda(), inp["embeddings"].cuda())
+    assert dec._engine(torch.device("cuda", 0)).last_path() == "latency"
+    assert mel.shape[2] == omel.shape[2] and int(flag) == int(oflag)
+    _cmp_tol((mel, gate, al, alb), (omel, ogate, oal, oalb), tol_mel, tol_align, f"lsa fr {path}/{wdtype}")
+    assert float((al.sum(-1) - 1).abs().max()) <= 1e-5 and float((alb.sum(-1) - 1).abs().max()) <= 1e-5
 
 
 @pytest.mark.parametrize("name", golden_names())
