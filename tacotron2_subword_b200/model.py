@@ -549,7 +549,7 @@ class Decoder(nn.Module):
         one utterance at a time.
 
         With autograd enabled the outputs carry a hand-written backward (``_DecoderTF``, tensor path, default dims):
-        2 <= B <= 128 in one BPTT call, B == 1 and B > 128 through ``_tf_autograd_resized``; other layer sizes raise at
+        2 <= B <= 128 in one BPTT call, B == 1 and B > 128 through ``_tf_resized``; other layer sizes raise at
         backward()."""
         wants_grad = torch.is_grad_enabled() and (
             any(p.requires_grad for p in self.parameters()) or memory.requires_grad or
@@ -561,12 +561,13 @@ class Decoder(nn.Module):
         if wants_grad and self._backward_supported(memory):
             B = memory.shape[0]
             if B == 1 or B > self.max_backward_rows:
-                return self._tf_autograd_resized(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent)
+                return self._tf_resized(self._tf_autograd, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent)
             return self._tf_autograd(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent)
-        outs, _ = self._run_tf(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save=False,
-                               independent=independent)
-        mel, gate, align, align_b = outs
-        outs = (mel.transpose(1, 2), gate, align, align_b)
+        if self._wants_sub_batches(memory):
+            # more utterances than one tensor-path launch takes (tcgen05 N limit): balanced sub-batches instead of the ~15x slower
+            # generic kernel
+            return self._tf_resized(self._tf_plain, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent)
+        outs = self._tf_plain(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent)
         if wants_grad:
             live = [o for o in outs if o is not None]
             marked = list(_NoBackward.apply(self.gate_layer.linear_layer.weight, *live))
@@ -580,6 +581,16 @@ class Decoder(nn.Module):
                 and (self.attention_rnn_dim, self.decoder_rnn_dim, self.encoder_embedding_dim, self.prenet_dim,
                      self.attention_dim, self.n_mel_channels) == (1024, 1024, 512, 256, 128, 80))
 
+    def _wants_sub_batches(self, memory) -> bool:
+        return (memory.shape[0] > self.max_backward_rows and self._backward_supported(memory) and
+                (self.decoder_path != "auto" or self.batched_precision == "fp16"))
+
+    def _tf_plain(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent):
+        outs, _ = self._run_tf(memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, save=False,
+                               independent=independent)
+        mel, gate, align, align_b = outs
+        return mel.transpose(1, 2), gate, align, align_b
+
     def _tf_autograd(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent):
         """One differentiable teacher-forced pass on the tensor path (2 <= B <= max_backward_rows)."""
         two = self.n_streams == 2
@@ -588,8 +599,8 @@ class Decoder(nn.Module):
                                 memory_lengths, bert_lengths if two else None, *params)
         return outs[0].transpose(1, 2), outs[1], outs[2], (outs[3] if two else None)
 
-    def _tf_autograd_resized(self, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent):
-        """Batches the BPTT kernels do not take directly (train.py:330 trains whatever ``collate_fn`` emits, including
+    def _tf_resized(self, run, memory, embeddings, decoder_inputs, memory_lengths, bert_lengths, independent):
+        """Batches one tensor-path call does not take directly (train.py:330 trains whatever ``collate_fn`` emits, including
         size-1 remainders, data_utils.py:146-160).  Utterances never interact inside the decoder, so
 
         * B == 1 runs as a batch of two whose second row is a detached copy of the first: its upstream gradients are
@@ -628,8 +639,8 @@ class Decoder(nn.Module):
             if B == 1:
                 dd = lambda t: None if t is None else torch.cat([t, t.detach()], 0)
                 self.dropout_replay = replay_for(None, True)
-                outs = self._tf_autograd(dd(memory), dd(embeddings) if two else None, dd(decoder_inputs), dd(memory_lengths),
-                                         dd(bert_lengths) if two else None, independent)
+                outs = run(dd(memory), dd(embeddings) if two else None, dd(decoder_inputs), dd(memory_lengths),
+                           dd(bert_lengths) if two else None, independent)
                 return tuple(None if o is None else o[:1] for o in outs)
             n_sub = -(-B // self.max_backward_rows)           # balanced sub-batches: sizes differ by at most one, none is 1
             bounds = [B * k // n_sub for k in range(n_sub + 1)]
@@ -640,8 +651,8 @@ class Decoder(nn.Module):
                 self.dropout_replay = replay_for(sl, False)
                 if saved[1] is not None:
                     self.rng_seed = (int(saved[1]) + 0x9E3779B97F4A7C15 * k) % (1 << 62)
-                parts.append(self._tf_autograd(cut(memory), cut(embeddings) if two else None, cut(decoder_inputs),
-                                               cut(memory_lengths), cut(bert_lengths) if two else None, independent))
+                parts.append(run(cut(memory), cut(embeddings) if two else None, cut(decoder_inputs),
+                                 cut(memory_lengths), cut(bert_lengths) if two else None, independent))
             return tuple(None if parts[0][i] is None else torch.cat([p_[i] for p_ in parts], 0) for i in range(4))
         finally:
             self.dropout_replay, self.rng_seed, self.validate_lengths = saved
@@ -707,6 +718,8 @@ class Decoder(nn.Module):
 
         Returns mel [B,n_mel,Tmax], gate [B,Tmax,1], align [B,Tmax,T_in], align_bert, n_frames [B] (int32),
         reached_max [B] (int32); frames >= n_frames[b] are zeroed (gate there = 1e3 as in parse_output)."""
+        if self._wants_sub_batches(memory):
+            return self._inference_sub_batches(memory, embeddings, memory_lengths, bert_lengths, max_decoder_steps)
         dev = self.gate_layer.linear_layer.weight.device
         eng = self._engine(dev)
         two = self.n_streams == 2
@@ -753,6 +766,36 @@ class Decoder(nn.Module):
         if two:
             align_b = align_b[:, :Tmax].masked_fill(dead.unsqueeze(2), 0.0)
         return mel, gate, align, align_b, n_frames, reached
+
+    def _inference_sub_batches(self, memory, embeddings, memory_lengths, bert_lengths, max_decoder_steps):
+        """More utterances than one persistent launch takes: balanced sub-batches (utterances are independent), outputs padded
+        to the longest utterance exactly as one call would (mel / alignments 0, gate 1e3 beyond an utterance's last frame)."""
+        B = memory.shape[0]
+        two = self.n_streams == 2
+        n_sub = -(-B // self.max_backward_rows)
+        bounds = [B * k // n_sub for k in range(n_sub + 1)]
+        saved = (self.dropout_replay, self.rng_seed)
+        rp = saved[0]
+        parts = []
+        try:
+            for k in range(n_sub):
+                sl = slice(bounds[k], bounds[k + 1])
+                cut = lambda t: None if t is None else t[sl]
+                if rp is not None:
+                    pk = None if rp.prenet_keep is None else [[m[:, sl] for m in row] for row in rp.prenet_keep]
+                    self.dropout_replay = DropoutReplay(pk, None, None)
+                if saved[1] is not None:
+                    self.rng_seed = (int(saved[1]) + 0x9E3779B97F4A7C15 * k) % (1 << 62)
+                parts.append(self.inference_batched(cut(memory), cut(embeddings) if two else None, cut(memory_lengths),
+                                                    cut(bert_lengths) if two else None, max_decoder_steps))
+        finally:
+            self.dropout_replay, self.rng_seed = saved
+        Tmax = max(p_[0].shape[2] for p_ in parts)
+        grow = lambda t, dim, val: t if t.shape[dim] == Tmax else F.pad(
+            t, [0, 0] * (t.dim() - 1 - dim) + [0, Tmax - t.shape[dim]], value=val)
+        cat = lambda i, dim, val: torch.cat([grow(p_[i], dim, val) for p_ in parts], 0)
+        return (cat(0, 2, 0.0), cat(1, 1, 1e3), cat(2, 1, 0.0), cat(3, 1, 0.0) if two else None,
+                torch.cat([p_[4] for p_ in parts]), torch.cat([p_[5] for p_ in parts]))
 
     def inference(self, memory, embeddings=None):
         """Free-running decode (model.py:430-492): mel [B,n_mel,T], gate [B,T,1], alignments,

@@ -415,9 +415,12 @@ def _mixed_stop_bias(attention, seed, B, T_in, T_sub, steps, margin):
     return math.log(0.001 / 0.999) - best, inp, plan
 
 
-@pytest.mark.parametrize("path,wdtype,B,tol_mel,tol_align", [("generic", "fp32", 5, TOL_MEL, TOL_ALIGN),
-                                                             ("tensor", "fp16", 16, 1e-3, 2e-4)])
-def test_batched_free_running_mixed_stop_frames(path, wdtype, B, tol_mel, tol_align):
+@pytest.mark.parametrize("path,wdtype,B,tol_mel,tol_align,rows", [("generic", "fp32", 5, TOL_MEL, TOL_ALIGN, 128),
+                                                                  ("tensor", "fp16", 16, 1e-3, 2e-4, 128),
+                                                                  ("tensor", "fp16", 16, 1e-3, 2e-4, 6)])   # 3 sub-batches
+def test_batched_free_running_mixed_stop_frames(path, wdtype, B, tol_mel, tol_align, rows):
+    """``rows`` < B: the batch runs as balanced sub-batches (what a call with more than 128 utterances does) whose outputs are
+    padded to the longest utterance of the whole batch."""
     T_in, T_sub, steps, seed = 21, 8, 14, 88
     bias, inp, plan = _mixed_stop_bias(SMA, seed, B, T_in, T_sub, steps, margin=5e-3)
     w = make_decoder_weights(SMA, seed=seed, gate_bias=bias)
@@ -427,6 +430,7 @@ def test_batched_free_running_mixed_stop_frames(path, wdtype, B, tol_mel, tol_al
     assert len(set(want_n)) >= 3 and steps in want_n, want_n            # several stop frames + at least one max-steps
     dec = make_decoder(w, SMA).eval()
     dec.decoder_path, dec.weight_dtype = path, wdtype
+    dec.max_backward_rows = rows
     dec.dropout_replay = replay_of(plan)
     with torch.no_grad():
         mel, gate, al, alb, nf, reached = dec.inference_batched(inp["memory"].cuda(), inp["embeddings"].cuda(),
@@ -434,12 +438,33 @@ def test_batched_free_running_mixed_stop_frames(path, wdtype, B, tol_mel, tol_al
                                                                 max_decoder_steps=steps)
     assert dec._engine(torch.device("cuda", 0)).last_path() == path
     assert [int(x) for x in nf] == want_n
+    assert mel.shape == (B, 80, max(want_n)) and gate.shape == (B, max(want_n), 1) and al.shape == (B, max(want_n), T_in)
+    for b in range(B):      # beyond an utterance's last frame: mel / alignments 0, gate 1e3 (parse_output convention)
+        assert float(mel[b, :, want_n[b]:].abs().sum()) == 0.0 and bool((gate[b, want_n[b]:] == 1e3).all())
     for b, (omel, ogate, oal, oalb, oflag) in enumerate(outs):
         n = want_n[b]
         assert bool(reached[b]) == (not oflag)
         Lm, Lb = int(inp["memory_lengths"][b]), int(inp["bert_lengths"][b])
         _cmp_tol((mel[b:b + 1, :, :n], gate[b:b + 1, :n], al[b:b + 1, :n, :Lm], alb[b:b + 1, :n, :Lb]),
                  (omel, ogate, oal, oalb), tol_mel, tol_align, f"{path} mixed-stop utt {b}")
+
+
+def test_teacher_forced_sub_batches_without_grad():
+    """More rows than one tensor-path launch takes (here 4 instead of 128): balanced sub-batches over the same padded memory."""
+    B, T_in, T_sub, T, seed = 11, 24, 8, 5, 47
+    w = make_decoder_weights(SMA, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=True)
+    plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, True, seed=seed + 1)
+    want = DecoderOracle(w, SMA).forward(inp["memory"], inp["embeddings"], inp["mels"], inp["memory_lengths"],
+                                         inp["bert_lengths"], plan, training=True)
+    dec = make_decoder(w, SMA, exact=False).train()
+    dec.max_backward_rows = 4
+    dec.dropout_replay = replay_of(plan)
+    with torch.no_grad():
+        got = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(), inp["memory_lengths"].cuda(),
+                  inp["bert_lengths"].cuda())
+    assert dec._engine(torch.device("cuda", 0)).last_path() in ("tensor", "tensor_graph")
+    _cmp_tol(got, want, 1e-3, 2e-4, "sub-batched teacher forcing")
 
 
 def test_tensor_path_single_stream_forward_and_backward():
