@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TACO2DEC_ABI_VERSION 7
+#define TACO2DEC_ABI_VERSION 8
 
 #define TACO2DEC_ATTN_SMA 0 /* StepwiseMonotonicAttention   (attention.py:291-398, hparams default) */
 #define TACO2DEC_ATTN_LSA 1 /* LocationSensitiveAttention   (attention.py:7-85)                      */
@@ -325,7 +325,7 @@ int taco2dec_launch_geometry(const taco2dec_handle* h, int B, int* grid, int* bl
  * Postnet, eval mode: replaces Postnet.forward (model.py:27-70) + the residual add
  * (model.py:557-558) + the output mask (model.py:531-541) when the module is not training.  Five Conv1d(k=5) +
  * BatchNorm1d (running statistics, folded into the weights at set_weights) + tanh on tcgen05, fp32 accumulation, operands
- * as split fp16 pairs by default (see taco2dec_postnet_set_precision).  Training mode (batch statistics, dropout, backward) stays with the reference's PyTorch modules.
+ * as split fp16 pairs by default (see taco2dec_postnet_set_precision).  Training mode: the building blocks further down.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct taco2dec_postnet taco2dec_postnet;
 
@@ -362,6 +362,48 @@ size_t taco2dec_postnet_workspace_bytes(const taco2dec_postnet* h, int B, int T)
 int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stride_b, int64_t stride_c, int64_t stride_t,
                              int B, int T, const int64_t* output_lengths, int independent, float* mel_postnet,
                              void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Postnet, training mode (model.py:27-70 under model.train(): BatchNorm1d with BATCH statistics, tanh, F.dropout(0.5) after
+ * every layer; the reference gets the backward pass from autograd).  Activations are kept channel-last with a two-frame
+ * zero halo per utterance, x_pad[b][t + 2][c]: the im2col row of frame (b, t) is then the contiguous run of 5*C floats at
+ * x_pad[b][t][0], and every contraction of a layer is a "rows x weights^T" product over overlapping rows on tcgen05
+ * (fp16 operands, fp32 accumulation).  The caller (tacotron2_subword_b200.model._PostnetTrain) chains these calls per layer:
+ *   forward : rows_gemm(x_pad, W'[co][(k,ci)], bias, stats) -> y[n][co] and the per-channel sums of y and y^2
+ *             bn_act_forward(y, mean, rstd, gamma, beta) -> next layer's x_pad interior (or the [B, C, T] output)
+ *   backward: bn_act_backward(d, y, ...) -> dz in place + per-channel sums of dz and dz.zhat
+ *             bn_backward_input(dz, y, ...) -> dy_pad interior;  postnet_wgrad per tap (dW);  rows_gemm(dy_pad, W''[ci][(k,co)],
+ *             scale_x = 1) -> gradient w.r.t. the layer input.
+ * Dropout masks come from Philox (seed, mask_id) or from a replayed uint8 array [n_rows][C] (parity tests).
+ * --------------------------------------------------------------------------------------------------------- */
+size_t taco2dec_postnet_rows_gemm_workspace_bytes(const taco2dec_postnet* h, int M, int K, int n_rows);
+/* out[n][m] = sum_k X_n[k] W[m][k] (+ bias[m]);  row n = (b, t) is the K contiguous floats at X + b*x_stride_b + t*x_stride_t
+ * (rows may overlap); W is row-major [M][K]; out has leading dimension ldo >= M.  scale_x = 1 scales the rows by a power
+ * of two taken from their absolute maximum before the fp16 conversion (gradient rows).  stats (optional, double[2*M], must be
+ * zeroed by the caller): += per-channel sums of out and out^2 over all rows. */
+int taco2dec_postnet_rows_gemm(taco2dec_postnet* h, const float* X, int64_t x_stride_b, int64_t x_stride_t, int B, int T, int K,
+                               const float* W, int M, const float* bias, int scale_x, float* out, int64_t ldo, double* stats,
+                               void* workspace, size_t workspace_bytes, void* cuda_stream);
+/* o = dropout(act(gamma (y - mean) rstd + beta)), act = tanh or identity; y is [B*T][C]; element (b, t, c) of the output goes to
+ * out[b*out_stride_b + t*out_stride_t + c*out_stride_c].  C % 4 == 0, C <= 1024. */
+int taco2dec_postnet_bn_act_forward(taco2dec_postnet* h, const float* y, int B, int T, int C, const float* mean, const float* rstd,
+                                    const float* gamma, const float* beta, int use_tanh, uint64_t seed, int mask_id, float p_drop,
+                                    const uint8_t* keep, float* out, int64_t out_stride_b, int64_t out_stride_t, int64_t out_stride_c,
+                                    void* cuda_stream);
+/* d [n_rows][C]: gradient w.r.t. the layer output, overwritten with dz (gradient w.r.t. the BatchNorm output);
+ * sums (double[2*C], zeroed by the caller) += sum_n dz, sum_n dz . zhat. */
+int taco2dec_postnet_bn_act_backward(taco2dec_postnet* h, float* d, const float* y, int n_rows, int C, const float* mean, const float* rstd,
+                                     const float* gamma, const float* beta, int use_tanh, uint64_t seed, int mask_id, float p_drop,
+                                     const uint8_t* keep, double* sums, void* cuda_stream);
+/* dy = gamma rstd (dz - mean_dz - zhat mean_dz_zhat) into the interior of dy_pad [B][T + 4][C] (halo rows stay untouched). */
+int taco2dec_postnet_bn_backward_input(taco2dec_postnet* h, const float* dz, const float* y, int B, int T, int C, const float* mean,
+                                       const float* rstd, const float* gamma, const float* mean_dz, const float* mean_dz_zhat,
+                                       float* dy_pad, void* cuda_stream);
+/* Same contract as taco2dec_wgrad_gemm / taco2dec_wgrad_workspace_bytes, on a postnet handle. */
+size_t taco2dec_postnet_wgrad_workspace_bytes(const taco2dec_postnet* h, int M, int N, int T, int B);
+int taco2dec_postnet_wgrad(taco2dec_postnet* h, const float* Y, int64_t y_stride_t, int64_t y_stride_b, int M, const float* X,
+                           int64_t x_stride_t, int64_t x_stride_b, int N, int T, int B, float* C, int64_t ldc, int accumulate,
+                           int reuse_y, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Decoder inputs: memory = linear_converter(cat(encoder_outputs, cls_embeddings)) (model.py:548-549,

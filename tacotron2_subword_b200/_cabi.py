@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("TACO2DEC_LIB") or os.path.join(_HERE, "csrc", "libtac
 ATTN_SMA, ATTN_LSA = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_LATENCY, PATH_TENSOR, PATH_TENSOR_GRAPH = 0, 1, 2, 3, 4
 W_FP32, W_FP16 = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 EXPORTED_SYMBOLS = (
     "taco2dec_abi_version", "taco2dec_last_error", "taco2dec_create", "taco2dec_destroy",
@@ -31,6 +31,9 @@ EXPORTED_SYMBOLS = (
     "taco2dec_memprep_create", "taco2dec_memprep_destroy", "taco2dec_memprep_set_weights", "taco2dec_memprep_workspace_bytes",
     "taco2dec_memprep_forward", "taco2dec_memprep_project", "taco2dec_loss_workspace_bytes", "taco2dec_loss_forward",
     "taco2dec_postnet_set_precision", "taco2dec_wgrad_workspace_bytes", "taco2dec_wgrad_gemm",
+    "taco2dec_postnet_rows_gemm_workspace_bytes", "taco2dec_postnet_rows_gemm", "taco2dec_postnet_bn_act_forward",
+    "taco2dec_postnet_bn_act_backward", "taco2dec_postnet_bn_backward_input", "taco2dec_postnet_wgrad_workspace_bytes",
+    "taco2dec_postnet_wgrad",
     "taco2dec_sgemm_nn", "taco2dec_bmm_tn",
 )
 
@@ -208,6 +211,25 @@ def load_library() -> C.CDLL:
     lib.taco2dec_wgrad_gemm.restype = C.c_int
     lib.taco2dec_wgrad_gemm.argtypes = [H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.taco2dec_postnet_wgrad_workspace_bytes.restype = C.c_size_t
+    lib.taco2dec_postnet_wgrad_workspace_bytes.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.taco2dec_postnet_wgrad.restype = C.c_int
+    lib.taco2dec_postnet_wgrad.argtypes = lib.taco2dec_wgrad_gemm.argtypes
+    lib.taco2dec_postnet_rows_gemm_workspace_bytes.restype = C.c_size_t
+    lib.taco2dec_postnet_rows_gemm_workspace_bytes.argtypes = [H, C.c_int, C.c_int, C.c_int]
+    lib.taco2dec_postnet_rows_gemm.restype = C.c_int
+    lib.taco2dec_postnet_rows_gemm.argtypes = [H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                               C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.taco2dec_postnet_bn_act_forward.restype = C.c_int
+    lib.taco2dec_postnet_bn_act_forward.argtypes = [H, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_int, C.c_uint64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                                    C.c_int64, C.c_void_p]
+    lib.taco2dec_postnet_bn_act_backward.restype = C.c_int
+    lib.taco2dec_postnet_bn_act_backward.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     C.c_int, C.c_uint64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.taco2dec_postnet_bn_backward_input.restype = C.c_int
+    lib.taco2dec_postnet_bn_backward_input.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.taco2dec_sgemm_nn.restype = C.c_int
     lib.taco2dec_sgemm_nn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_int64, C.c_int, C.c_void_p]

@@ -784,6 +784,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
 #include "memprep.cuh"
 #include "loss.cuh"
 #include "wgrad.cuh"
+#include "postnet_train.cuh"
 
 // ------------------------------------------------------------------------------------------
 // One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
@@ -2557,16 +2558,16 @@ extern "C" size_t taco2dec_wgrad_workspace_bytes(const taco2dec_handle* h, int M
   return wg::plan(M, N, T * B, h->num_sms).total;
 }
 
-extern "C" int taco2dec_wgrad_gemm(taco2dec_handle* h, const float* Y, int64_t y_stride_t, int64_t y_stride_b, int M, const float* X,
-                                   int64_t x_stride_t, int64_t x_stride_b, int N, int T, int B, float* Cout, int64_t ldc, int accumulate,
-                                   int reuse_y, void* workspace, size_t workspace_bytes, void* cuda_stream) {
-  if (!h || !Y || !X || !Cout || !workspace) return fail(TACO2DEC_E_ARG, "null argument");
+static int wgrad_impl(int device, int num_sms, int64_t* launches, const float* Y, int64_t y_stride_t, int64_t y_stride_b, int M,
+                      const float* X, int64_t x_stride_t, int64_t x_stride_b, int N, int T, int B, float* Cout, int64_t ldc,
+                      int accumulate, int reuse_y, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!Y || !X || !Cout || !workspace) return fail(TACO2DEC_E_ARG, "null argument");
   if (M < 1 || N < 1 || T < 1 || B < 1 || ldc < N) return fail(TACO2DEC_E_ARG, "bad shape");
-  const wg::Plan pl = wg::plan(M, N, T * B, h->num_sms);
+  const wg::Plan pl = wg::plan(M, N, T * B, num_sms);
   if (workspace_bytes < pl.total) return fail(TACO2DEC_E_STATE, "workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(TACO2DEC_E_ARG, "workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaSetDevice(device));
   char* ws = (char*)workspace;
   unsigned* amax = (unsigned*)ws;
   float* scale2 = (float*)(ws + 64);
@@ -2576,10 +2577,10 @@ extern "C" int taco2dec_wgrad_gemm(taco2dec_handle* h, const float* Y, int64_t y
   const int kbs = pl.Kpad / 64;
   if (!reuse_y) {       // the packed, scaled image of Y at the head of the workspace is still valid otherwise
     CUDA_TRY(cudaMemsetAsync(amax, 0, 64, st));
-    wg::wg_absmax_kernel<<<h->num_sms * 4, 256, 0, st>>>(Y, y_stride_t, y_stride_b, T, B, M, amax);
+    wg::wg_absmax_kernel<<<num_sms * 4, 256, 0, st>>>(Y, y_stride_t, y_stride_b, T, B, M, amax);
     wg::wg_scale_kernel<<<1, 1, 0, st>>>(amax, scale2);
     wg::wg_pack_T_kernel<<<dim3(kbs, pl.Mpad / 128), 256, 0, st>>>(Y, y_stride_t, y_stride_b, T, B, M, pl.Kpad, scale2, a_t);
-    h->launches += 3;
+    *launches += 3;
   }
   wg::wg_pack_T_kernel<<<dim3(kbs, pl.groups), 256, 0, st>>>(X, x_stride_t, x_stride_b, T, B, N, pl.Kpad, nullptr, x_t);
   CUDA_TRY(tc::prepare_gemm<wg::kNP>());
@@ -2589,8 +2590,16 @@ extern "C" int taco2dec_wgrad_gemm(taco2dec_handle* h, const float* Y, int64_t y
   wg::wg_finish_kernel<<<dim3(std::min(64, (M * wg::kNP + 255) / 256), pl.groups), 256, 0, st>>>(part, pl.splits, pl.Mpad, M, N, scale2, Cout, ldc,
                                                                                                 accumulate);
   CUDA_TRY(cudaGetLastError());
-  h->launches += 3;
+  *launches += 3;
   return 0;
+}
+
+extern "C" int taco2dec_wgrad_gemm(taco2dec_handle* h, const float* Y, int64_t y_stride_t, int64_t y_stride_b, int M, const float* X,
+                                   int64_t x_stride_t, int64_t x_stride_b, int N, int T, int B, float* Cout, int64_t ldc, int accumulate,
+                                   int reuse_y, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null argument");
+  return wgrad_impl(h->device, h->num_sms, &h->launches, Y, y_stride_t, y_stride_b, M, X, x_stride_t, x_stride_b, N, T, B, Cout, ldc,
+                    accumulate, reuse_y, workspace, workspace_bytes, cuda_stream);
 }
 
 extern "C" int taco2dec_sgemm_nn(const float* A, int64_t lda, const float* Bm, int64_t ldb, float* Cout, int64_t ldc, int R, int N, int K,
@@ -2751,6 +2760,114 @@ int taco2dec_postnet_forward(taco2dec_postnet* h, const float* mel, int64_t stri
   CUDA_TRY(cudaGetLastError());
   h->launches += 1 + 2 * h->n_layers;
   return 0;
+}
+
+// ---- training-mode Postnet (postnet_train.cuh): contraction + element-wise building blocks, orchestrated by the caller ----
+size_t taco2dec_postnet_rows_gemm_workspace_bytes(const taco2dec_postnet* h, int M, int K, int n_rows) {
+  if (!h || M < 1 || K < 1 || n_rows < 1) return 0;
+  return pt::rows_plan(M, K, n_rows, h->num_sms).total;
+}
+
+int taco2dec_postnet_rows_gemm(taco2dec_postnet* h, const float* X, int64_t x_stride_b, int64_t x_stride_t, int B, int T, int K,
+                               const float* W, int M, const float* bias, int scale_x, float* out, int64_t ldo, double* stats,
+                               void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!h || !X || !W || !out || !workspace) return fail(TACO2DEC_E_ARG, "null argument");
+  if (B < 1 || T < 1 || K < 1 || M < 1 || ldo < M) return fail(TACO2DEC_E_ARG, "bad shape");
+  const pt::RowsPlan pl = pt::rows_plan(M, K, B * T, h->num_sms);
+  if (workspace_bytes < pl.total) return fail(TACO2DEC_E_STATE, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(TACO2DEC_E_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaSetDevice(h->device));
+  char* ws = (char*)workspace;
+  unsigned* amax = (unsigned*)ws;
+  float* scale2 = (float*)(ws + 64);
+  unsigned char* a_t = (unsigned char*)(ws + pl.a_off);
+  unsigned char* x_t = (unsigned char*)(ws + pl.x_off);
+  float* part = (float*)(ws + pl.part_off);
+  const int kbs = pl.Kpad / 64;
+  if (scale_x) {        // gradient rows: power-of-two scale from the absolute maximum so that they survive fp16
+    CUDA_TRY(cudaMemsetAsync(amax, 0, 64, st));
+    wg::wg_absmax_kernel<<<h->num_sms * 4, 256, 0, st>>>(X, x_stride_t, x_stride_b, T, B, K, amax);
+    wg::wg_scale_kernel<<<1, 1, 0, st>>>(amax, scale2);
+  }
+  pt::pt_pack_w_kernel<<<(unsigned)std::min<size_t>(((size_t)pl.Mpad * (pl.Kpad / 8) + 255) / 256, 4096), 256, 0, st>>>(W, M, K, pl.Mpad, pl.Kpad, a_t);
+  pt::pt_pack_rows_kernel<<<dim3(kbs, pl.groups), 256, 0, st>>>(X, x_stride_b, x_stride_t, B, T, K, pl.Kpad, scale_x ? scale2 : nullptr, x_t);
+  CUDA_TRY(tc::prepare_gemm<pt::kNP>());
+  tc::GemmParams gp{a_t, x_t, part, pl.Mpad, pl.Kpad, pl.splits, pl.groups, (long long)kbs * pt::kNP * 128, 0, 0, nullptr, 0};
+  gp.a_shared = 1;
+  CUDA_TRY(tc::launch_gemm<pt::kNP>(gp, st));
+  pt::pt_finish_kernel<<<dim3(pl.groups, pl.Mpad / 32), 256, 0, st>>>(part, pl.splits, pl.Mpad, M, B * T, bias, scale_x ? scale2 : nullptr, out,
+                                                                      ldo, stats);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += scale_x ? 6 : 4;
+  return 0;
+}
+
+static int pt_bn_args(const float* mean, const float* rstd, const float* gamma, const float* beta, int use_tanh, uint64_t seed,
+                      int mask_id, float p_drop, const uint8_t* keep, int C, pt::BnArgs* a) {
+  if (!mean || !rstd || !gamma || !beta) return fail(TACO2DEC_E_ARG, "null argument");
+  if (C < 4 || (C & 3) || C > 1024) return fail(TACO2DEC_E_ARG, "channel count must be a multiple of 4, at most 1024");
+  if (!(p_drop >= 0.f && p_drop < 1.f)) return fail(TACO2DEC_E_ARG, "bad dropout probability");
+  a->mean = mean; a->rstd = rstd; a->gamma = gamma; a->beta = beta; a->use_tanh = use_tanh ? 1 : 0; a->seed = seed; a->mask_id = mask_id;
+  a->thresh = keep_threshold(p_drop); a->keep_scale = 1.0f / (1.0f - p_drop); a->keep = keep;
+  return 0;
+}
+
+int taco2dec_postnet_bn_act_forward(taco2dec_postnet* h, const float* y, int B, int T, int C, const float* mean, const float* rstd,
+                                    const float* gamma, const float* beta, int use_tanh, uint64_t seed, int mask_id, float p_drop,
+                                    const uint8_t* keep, float* out, int64_t out_stride_b, int64_t out_stride_t, int64_t out_stride_c,
+                                    void* cuda_stream) {
+  if (!h || !y || !out || B < 1 || T < 1) return fail(TACO2DEC_E_ARG, "bad argument");
+  pt::BnArgs a;
+  if (int rc = pt_bn_args(mean, rstd, gamma, beta, use_tanh, seed, mask_id, p_drop, keep, C, &a)) return rc;
+  if (out_stride_c == 1 && ((out_stride_b | out_stride_t) & 3)) return fail(TACO2DEC_E_ARG, "output strides must keep 16-byte alignment");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t total = (size_t)B * T * (C / 4);
+  pt::pt_bn_act_fwd_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16), 256, 0, (cudaStream_t)cuda_stream>>>(
+      y, B, T, C, a, out, out_stride_b, out_stride_t, out_stride_c);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int taco2dec_postnet_bn_act_backward(taco2dec_postnet* h, float* d, const float* y, int n_rows, int C, const float* mean, const float* rstd,
+                                     const float* gamma, const float* beta, int use_tanh, uint64_t seed, int mask_id, float p_drop,
+                                     const uint8_t* keep, double* sums, void* cuda_stream) {
+  if (!h || !d || !y || !sums || n_rows < 1) return fail(TACO2DEC_E_ARG, "bad argument");
+  pt::BnArgs a;
+  if (int rc = pt_bn_args(mean, rstd, gamma, beta, use_tanh, seed, mask_id, p_drop, keep, C, &a)) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  pt::pt_bn_act_bwd1_kernel<<<h->num_sms, 256, 0, (cudaStream_t)cuda_stream>>>(d, y, n_rows, C, a, sums);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int taco2dec_postnet_bn_backward_input(taco2dec_postnet* h, const float* dz, const float* y, int B, int T, int C, const float* mean,
+                                       const float* rstd, const float* gamma, const float* mean_dz, const float* mean_dz_zhat,
+                                       float* dy_pad, void* cuda_stream) {
+  if (!h || !dz || !y || !mean || !rstd || !gamma || !mean_dz || !mean_dz_zhat || !dy_pad || B < 1 || T < 1 || C < 4 || (C & 3))
+    return fail(TACO2DEC_E_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t total = (size_t)B * T * (C / 4);
+  pt::pt_bn_bwd2_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16), 256, 0, (cudaStream_t)cuda_stream>>>(
+      dz, y, B, T, C, mean, rstd, gamma, mean_dz, mean_dz_zhat, dy_pad);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+size_t taco2dec_postnet_wgrad_workspace_bytes(const taco2dec_postnet* h, int M, int N, int T, int B) {
+  if (!h || M < 1 || N < 1 || T < 1 || B < 1) return 0;
+  return wg::plan(M, N, T * B, h->num_sms).total;
+}
+
+int taco2dec_postnet_wgrad(taco2dec_postnet* h, const float* Y, int64_t y_stride_t, int64_t y_stride_b, int M, const float* X,
+                           int64_t x_stride_t, int64_t x_stride_b, int N, int T, int B, float* Cout, int64_t ldc, int accumulate,
+                           int reuse_y, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!h) return fail(TACO2DEC_E_ARG, "null argument");
+  return wgrad_impl(h->device, h->num_sms, &h->launches, Y, y_stride_t, y_stride_b, M, X, x_stride_t, x_stride_b, N, T, B, Cout, ldc,
+                    accumulate, reuse_y, workspace, workspace_bytes, cuda_stream);
 }
 
 }  // extern "C"

@@ -810,10 +810,124 @@ class Decoder(nn.Module):
         return mel, gate, align, align_b, flag
 
 
+class _PostnetTrain(torch.autograd.Function):
+    """Training-mode Postnet (model.py:27-70 under model.train()) with a hand-written backward on the repo's own kernels
+    (csrc/postnet_train.cuh): per layer one tcgen05 "rows x weights^T" contraction over the channel-last, halo-padded
+    activations + fused BatchNorm(batch statistics) / tanh / dropout; backward = the element-wise derivatives, one tcgen05
+    weight-gradient product per tap and the transposed-convolution contraction.  The reference relies on autograd."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        lib, dev = _cabi.load_library(), x.device
+        h = net._handle(dev)
+        B, C0, T = x.shape
+        N, L = B * T, net.n_layers
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        seed = net.rng_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        replay = net.dropout_replay
+        xpad = torch.zeros(B, T + 4, C0, device=dev)
+        xpad[:, 2:T + 2] = x.detach().transpose(1, 2)
+        saved, out = [], None
+        with torch.cuda.device(dev):
+            for l in range(L):
+                w, b, gamma, beta = (t.detach() for t in params[4 * l: 4 * l + 4])
+                bn = net.convolutions[l][1]
+                Cout, Cin, K = w.shape
+                wt = w.permute(0, 2, 1).reshape(Cout, K * Cin).contiguous()          # [co][(k, ci)]
+                y = torch.empty(N, Cout, device=dev)
+                stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+                ws = net._workspace(dev, int(lib.taco2dec_postnet_rows_gemm_workspace_bytes(h, Cout, K * Cin, N)))
+                _cabi.check(lib.taco2dec_postnet_rows_gemm(h, _ptr(xpad), (T + 4) * Cin, Cin, B, T, K * Cin, _ptr(wt), Cout, _ptr(b.contiguous()),
+                                                           0, _ptr(y), Cout, _ptr(stats), _ptr(ws), ws.numel(), stream))
+                mean64 = stats[:Cout] / N
+                var64 = (stats[Cout:] / N - mean64 * mean64).clamp_min(0.0)                  # biased, as BatchNorm normalises with
+                mean, rstd = mean64.float(), (var64 + bn.eps).rsqrt().float()
+                if bn.track_running_stats and bn.running_mean is not None:
+                    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+                    bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+                    bn.running_var.mul_(1 - mom).add_((var64 * (N / max(N - 1, 1))).float(), alpha=mom)
+                    bn.num_batches_tracked += 1
+                last = l == L - 1
+                keep = None if replay is None else replay[l].to(device=dev, dtype=torch.uint8).contiguous()
+                g32, b32 = gamma.contiguous(), beta.contiguous()
+                if last:
+                    out = torch.empty(B, Cout, T, device=dev)
+                    dst, osb, ost, osc = out, Cout * T, 1, T
+                    nxt = None
+                else:
+                    nxt = torch.zeros(B, T + 4, Cout, device=dev)
+                    dst, osb, ost, osc = nxt[:, 2:], (T + 4) * Cout, Cout, 1
+                _cabi.check(lib.taco2dec_postnet_bn_act_forward(h, _ptr(y), B, T, Cout, _ptr(mean), _ptr(rstd), _ptr(g32), _ptr(b32),
+                                                                int(not last), seed, l, net.p_dropout, _ptr(keep), _ptr(dst), osb, ost, osc,
+                                                                stream))
+                saved.append((xpad, y, mean, rstd, keep))
+                xpad = nxt
+        ctx.net, ctx.saved, ctx.seed, ctx.shape = net, saved, seed, (B, C0, T)
+        ctx.params = params
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        net, saved, seed = ctx.net, ctx.saved, ctx.seed
+        if saved is None:
+            raise RuntimeError("postnet backward called twice (the saved activations are released after the first pass)")
+        ctx.saved = None
+        B, C0, T = ctx.shape
+        N, L = B * T, net.n_layers
+        lib, dev = _cabi.load_library(), d_out.device
+        h = net._handle(dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        d = d_out.detach().to(torch.float32).transpose(1, 2).reshape(N, -1).contiguous()
+        if d.data_ptr() == d_out.data_ptr():
+            d = d.clone()                       # the element-wise backward works in place
+        grads = [None] * (4 * L)
+        need_dx = ctx.needs_input_grad[1]
+        with torch.cuda.device(dev):
+            for l in reversed(range(L)):
+                w, b, gamma, beta = (t.detach() for t in ctx.params[4 * l: 4 * l + 4])
+                xpad, y, mean, rstd, keep = saved[l]
+                saved[l] = None
+                Cout, Cin, K = w.shape
+                g32, b32 = gamma.contiguous(), beta.contiguous()
+                sums = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+                _cabi.check(lib.taco2dec_postnet_bn_act_backward(h, _ptr(d), _ptr(y), N, Cout, _ptr(mean), _ptr(rstd), _ptr(g32), _ptr(b32),
+                                                                 int(l != L - 1), seed, l, net.p_dropout, _ptr(keep), _ptr(sums), stream))
+                grads[4 * l + 3] = sums[:Cout].float()                                  # d beta  = sum dz
+                grads[4 * l + 2] = sums[Cout:].float()                                  # d gamma = sum dz . zhat
+                m_dz, m_dzz = (sums[:Cout] / N).float(), (sums[Cout:] / N).float()
+                dypad = torch.zeros(B, T + 4, Cout, device=dev)
+                _cabi.check(lib.taco2dec_postnet_bn_backward_input(h, _ptr(d), _ptr(y), B, T, Cout, _ptr(mean), _ptr(rstd), _ptr(g32),
+                                                                   _ptr(m_dz), _ptr(m_dzz), _ptr(dypad), stream))
+                # d W[co][ci][k] = sum_(b,t) dy[b][t][co] . x_pad[b][t + k][ci]: one tcgen05 product per tap, the packed dy is reused
+                dw = torch.empty(K, Cout, Cin, device=dev)
+                ws = net._workspace(dev, int(lib.taco2dec_postnet_wgrad_workspace_bytes(h, Cout, Cin, T, B)))
+                y3 = dypad[:, 2:T + 2]
+                for k in range(K):
+                    x3 = xpad[:, k:k + T]
+                    _cabi.check(lib.taco2dec_postnet_wgrad(h, _ptr(y3), Cout, (T + 4) * Cout, Cout, _ptr(x3), Cin, (T + 4) * Cin, Cin, T, B,
+                                                           _ptr(dw[k]), Cin, 0, int(k > 0), _ptr(ws), ws.numel(), stream))
+                grads[4 * l] = dw.permute(1, 2, 0).contiguous()
+                grads[4 * l + 1] = torch.zeros(Cout, device=dev)      # a bias in front of a batch-statistics BatchNorm has exactly zero gradient
+                if l > 0 or need_dx:
+                    # d x[n][ci] = sum_{k,co} dy_pad[n + k][co] . W[co][ci][K-1-k]   (transposed convolution as rows x weights^T)
+                    wd = w.flip(2).permute(1, 2, 0).reshape(Cin, K * Cout).contiguous()
+                    dn = torch.empty(N, Cin, device=dev)
+                    ws = net._workspace(dev, int(lib.taco2dec_postnet_rows_gemm_workspace_bytes(h, Cin, K * Cout, N)))
+                    _cabi.check(lib.taco2dec_postnet_rows_gemm(h, _ptr(dypad), (T + 4) * Cout, Cout, B, T, K * Cout, _ptr(wd), Cin, None, 1,
+                                                               _ptr(dn), Cin, None, _ptr(ws), ws.numel(), stream))
+                    d = dn
+        dx = d.view(B, T, C0).transpose(1, 2) if need_dx else None
+        pg = tuple(g if p_.requires_grad else None for g, p_ in zip(grads, ctx.params))
+        return (None, dx) + pg
+
+
 class Postnet(nn.Module):
     """model.py:27-70: five conv1d(k=5)+BatchNorm, tanh on all but the last, dropout 0.5 in training.
 
-    ``forward`` is the reference module (PyTorch ops; used for training).  ``mel_postnet`` is what the model classes
+    ``forward`` in training mode runs on the repo's own kernels with a hand-written backward (``_PostnetTrain``); in eval mode it
+    is the reference module (PyTorch ops).  ``mel_postnet`` is what the model classes
     call: mel + postnet(mel) with the output mask, which in eval mode on a B200 runs as five tcgen05 GEMMs with the
     BatchNorm folded in (``taco2dec_postnet_*``, csrc/postnet.cuh) instead of ten cuDNN/elementwise launches."""
 
@@ -833,8 +947,40 @@ class Postnet(nn.Module):
         # "fp16": plain fp16 operands (~8e-4 of the output scale, 2.5x less tensor work)
         self.fused_precision = "fp32"
         self._fused = {}                # device index -> (handle, weights key, workspace)
+        # training mode (batch statistics, dropout, backward) on the repo's own kernels (csrc/postnet_train.cuh, fp16 operands /
+        # fp32 accumulation: the grade of cuDNN's default TF32 convolutions); False = the reference's PyTorch ops
+        self.fused_train = True
+        self.p_dropout = 0.5            # model.py:60, 67
+        self.rng_seed: Optional[int] = None           # fixed Philox seed for the dropout masks; None = fresh per call
+        self.dropout_replay = None      # parity runs: one uint8 keep mask [B*T, C_out] per layer
+        self._train_ws = {}
+
+    def _handle(self, dev):
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        ent = self._fused.get(key)
+        if ent is None:
+            h = C.c_void_p()
+            _cabi.check(_cabi.load_library().taco2dec_postnet_create(self.n_mel, self.dim, self.kernel, self.n_layers, key, C.byref(h)))
+            ent = self._fused[key] = {"h": h, "key": None, "ws": None}
+        return ent["h"]
+
+    def _workspace(self, dev, need: int) -> torch.Tensor:
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        ws = self._train_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._train_ws[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+        return ws
+
+    def _train_fusable(self, x: torch.Tensor) -> bool:
+        return (self.fused_train and self.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and self.kernel == 5
+                and self.n_mel <= 128 and self.n_mel % 4 == 0 and self.dim % 128 == 0 and self.dim <= 1024 and 2 <= self.n_layers <= 8)
 
     def forward(self, x):
+        if self._train_fusable(x):
+            params = []
+            for seq in self.convolutions:
+                params += [seq[0].conv.weight, seq[0].conv.bias, seq[1].weight, seq[1].bias]
+            return _PostnetTrain.apply(self, x, *params)
         last = len(self.convolutions) - 1
         for i, conv in enumerate(self.convolutions):
             x = conv(x)
@@ -868,11 +1014,8 @@ class Postnet(nn.Module):
         lib = _cabi.load_library()
         dev = mel.device
         key = dev.index if dev.index is not None else torch.cuda.current_device()
-        ent = self._fused.get(key)
-        if ent is None:
-            h = C.c_void_p()
-            _cabi.check(lib.taco2dec_postnet_create(self.n_mel, self.dim, self.kernel, self.n_layers, key, C.byref(h)))
-            ent = self._fused[key] = {"h": h, "key": None, "ws": None}
+        self._handle(dev)
+        ent = self._fused[key]
         tensors = []
         for seq in self.convolutions:
             conv, bn = seq[0].conv, seq[1]
