@@ -8,7 +8,7 @@
 // x_pad[b][t][0], so every contraction of the layer is a plain "rows x weights^T" product over overlapping rows:
 //   forward   y[n][co]  = sum_{k,ci} x_pad[n + k][ci] . W[co][ci][k]                 (rows of x_pad,  W'  [co][(k, ci)])
 //   d input   dx[n][ci] = sum_{k,co} dy_pad[n + k][co] . W[co][ci][4 - k]            (rows of dy_pad, W'' [ci][(k, co)])
-//   d weight  dW[co][ci][k] = sum_n dy[n][co] . x_pad[n + k][ci]                     (wgrad.cuh, one product per tap)
+//   d weight  dW[co][(k,ci)] = sum_n dy[n][co] . x_pad[n + k][ci]                    (wgrad.cuh over the same overlapping rows)
 // The first two run through pt_pack_rows_kernel -> tc::gemm_f16_tn_kernel -> pt_finish_kernel (fp16 operands, fp32
 // accumulation in TMEM; gradient rows are scaled by a power of two taken from their absolute maximum so that they survive
 // fp16, exactly as in wgrad.cuh); the finishing kernel also accumulates the per-channel sums BatchNorm needs.  Everything
@@ -64,29 +64,30 @@ __global__ void pt_pack_w_kernel(const float* __restrict__ w, int M, int K, int 
 }
 
 // partials [group][split][Mpad][128] -> out[n][m] = (sum of the splits) / scale + bias[m]; optionally the per-channel sums of
-// out and out^2 over all rows (BatchNorm batch statistics), accumulated in double precision.  Block = 128 rows x 32 channels.
+// out and out^2 over all rows (BatchNorm batch statistics), accumulated in double precision.  Block = 128 rows x 64 channels.
 __global__ void __launch_bounds__(256) pt_finish_kernel(const float* __restrict__ part, int splits, int Mpad, int M, int n_rows,
                                                         const float* __restrict__ bias, const float* __restrict__ scale2,
                                                         float* __restrict__ out, long long ldo, double* __restrict__ stats) {
-  __shared__ float t_s[32][kNP + 1];
-  const int g = blockIdx.x, m0 = blockIdx.y * 32, tid = threadIdx.x;
+  constexpr int kMC = 64;
+  __shared__ float t_s[kMC][kNP + 1];
+  const int g = blockIdx.x, m0 = blockIdx.y * kMC, tid = threadIdx.x;
   const float inv = scale2 ? scale2[1] : 1.0f;
-  for (int i = tid; i < 32 * kNP; i += 256) {
+  for (int i = tid; i < kMC * kNP; i += 256) {
     const int ml = i >> 7, nl = i & 127, m = m0 + ml;
     float acc = 0.f;
     for (int k = 0; k < splits; ++k) acc += part[(((size_t)g * splits + k) * Mpad + m) * kNP + nl];
     t_s[ml][nl] = acc * inv + ((bias && m < M) ? bias[m] : 0.f);
   }
   __syncthreads();
-  for (int i = tid; i < kNP * 32; i += 256) {
-    const int nl = i >> 5, ml = i & 31, n = g * kNP + nl, m = m0 + ml;
+  for (int i = tid; i < kNP * kMC; i += 256) {
+    const int nl = i >> 6, ml = i & 63, n = g * kNP + nl, m = m0 + ml;
     if (n < n_rows && m < M) out[(size_t)n * ldo + m] = t_s[ml][nl];
   }
   if (stats) {
     const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ml = warp * 4 + q, m = m0 + ml;
+    for (int q = 0; q < 8; ++q) {
+      const int ml = warp * 8 + q, m = m0 + ml;
       float s1 = 0.f, s2 = 0.f;
       for (int nl = lane; nl < kNP; nl += 32)
         if (g * kNP + nl < n_rows) { const float v = t_s[ml][nl]; s1 += v; s2 = fmaf(v, v, s2); }

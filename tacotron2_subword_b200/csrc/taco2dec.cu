@@ -2796,7 +2796,7 @@ int taco2dec_postnet_rows_gemm(taco2dec_postnet* h, const float* X, int64_t x_st
   tc::GemmParams gp{a_t, x_t, part, pl.Mpad, pl.Kpad, pl.splits, pl.groups, (long long)kbs * pt::kNP * 128, 0, 0, nullptr, 0};
   gp.a_shared = 1;
   CUDA_TRY(tc::launch_gemm<pt::kNP>(gp, st));
-  pt::pt_finish_kernel<<<dim3(pl.groups, pl.Mpad / 32), 256, 0, st>>>(part, pl.splits, pl.Mpad, M, B * T, bias, scale_x ? scale2 : nullptr, out,
+  pt::pt_finish_kernel<<<dim3(pl.groups, pl.Mpad / 64), 256, 0, st>>>(part, pl.splits, pl.Mpad, M, B * T, bias, scale_x ? scale2 : nullptr, out,
                                                                       ldo, stats);
   CUDA_TRY(cudaGetLastError());
   h->launches += scale_x ? 6 : 4;
@@ -2837,7 +2837,7 @@ int taco2dec_postnet_bn_act_backward(taco2dec_postnet* h, float* d, const float*
   pt::BnArgs a;
   if (int rc = pt_bn_args(mean, rstd, gamma, beta, use_tanh, seed, mask_id, p_drop, keep, C, &a)) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
-  pt::pt_bn_act_bwd1_kernel<<<h->num_sms, 256, 0, (cudaStream_t)cuda_stream>>>(d, y, n_rows, C, a, sums);
+  pt::pt_bn_act_bwd1_kernel<<<h->num_sms * 4, 256, 0, (cudaStream_t)cuda_stream>>>(d, y, n_rows, C, a, sums);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return 0;

@@ -827,7 +827,13 @@ class _PostnetTrain(torch.autograd.Function):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
         replay = net.dropout_replay
-        xpad = torch.zeros(B, T + 4, C0, device=dev)
+        def padded(c):                      # [B][T + 4][c], only the two-frame halos need zeroing
+            t_ = torch.empty(B, T + 4, c, device=dev)
+            t_[:, :2].zero_()
+            t_[:, T + 2:].zero_()
+            return t_
+
+        xpad = padded(C0)
         xpad[:, 2:T + 2] = x.detach().transpose(1, 2)
         saved, out = [], None
         with torch.cuda.device(dev):
@@ -857,7 +863,7 @@ class _PostnetTrain(torch.autograd.Function):
                     dst, osb, ost, osc = out, Cout * T, 1, T
                     nxt = None
                 else:
-                    nxt = torch.zeros(B, T + 4, Cout, device=dev)
+                    nxt = padded(Cout)
                     dst, osb, ost, osc = nxt[:, 2:], (T + 4) * Cout, Cout, 1
                 _cabi.check(lib.taco2dec_postnet_bn_act_forward(h, _ptr(y), B, T, Cout, _ptr(mean), _ptr(rstd), _ptr(g32), _ptr(b32),
                                                                 int(not last), seed, l, net.p_dropout, _ptr(keep), _ptr(dst), osb, ost, osc,
@@ -897,18 +903,18 @@ class _PostnetTrain(torch.autograd.Function):
                 grads[4 * l + 3] = sums[:Cout].float()                                  # d beta  = sum dz
                 grads[4 * l + 2] = sums[Cout:].float()                                  # d gamma = sum dz . zhat
                 m_dz, m_dzz = (sums[:Cout] / N).float(), (sums[Cout:] / N).float()
-                dypad = torch.zeros(B, T + 4, Cout, device=dev)
+                dypad = torch.empty(B, T + 4, Cout, device=dev)
+                dypad[:, :2].zero_()
+                dypad[:, T + 2:].zero_()
                 _cabi.check(lib.taco2dec_postnet_bn_backward_input(h, _ptr(d), _ptr(y), B, T, Cout, _ptr(mean), _ptr(rstd), _ptr(g32),
                                                                    _ptr(m_dz), _ptr(m_dzz), _ptr(dypad), stream))
-                # d W[co][ci][k] = sum_(b,t) dy[b][t][co] . x_pad[b][t + k][ci]: one tcgen05 product per tap, the packed dy is reused
-                dw = torch.empty(K, Cout, Cin, device=dev)
-                ws = net._workspace(dev, int(lib.taco2dec_postnet_wgrad_workspace_bytes(h, Cout, Cin, T, B)))
+                # d W[co][(k, ci)] = sum_(b,t) dy[b][t][co] . x_pad[b][t + k][ci]: ONE tcgen05 product over the overlapping im2col rows
+                dw = torch.empty(Cout, K * Cin, device=dev)
+                ws = net._workspace(dev, int(lib.taco2dec_postnet_wgrad_workspace_bytes(h, Cout, K * Cin, T, B)))
                 y3 = dypad[:, 2:T + 2]
-                for k in range(K):
-                    x3 = xpad[:, k:k + T]
-                    _cabi.check(lib.taco2dec_postnet_wgrad(h, _ptr(y3), Cout, (T + 4) * Cout, Cout, _ptr(x3), Cin, (T + 4) * Cin, Cin, T, B,
-                                                           _ptr(dw[k]), Cin, 0, int(k > 0), _ptr(ws), ws.numel(), stream))
-                grads[4 * l] = dw.permute(1, 2, 0).contiguous()
+                _cabi.check(lib.taco2dec_postnet_wgrad(h, _ptr(y3), Cout, (T + 4) * Cout, Cout, _ptr(xpad), Cin, (T + 4) * Cin, K * Cin, T, B,
+                                                       _ptr(dw), K * Cin, 0, 0, _ptr(ws), ws.numel(), stream))
+                grads[4 * l] = dw.view(Cout, K, Cin).permute(0, 2, 1).contiguous()
                 grads[4 * l + 1] = torch.zeros(Cout, device=dev)      # a bias in front of a batch-statistics BatchNorm has exactly zero gradient
                 if l > 0 or need_dx:
                     # d x[n][ci] = sum_{k,co} dy_pad[n + k][co] . W[co][ci][K-1-k]   (transposed convolution as rows x weights^T)

@@ -1,18 +1,25 @@
-"""BASELINE cfg 5, whole model: one BERT_Tacotron2 training step (reference-code encoder / postnet / loss in PyTorch, CUDA
-decoder forward + backward, SGD update) on one GPU.  usage: python tools/train_step_full.py [B] [T]"""
+"""BASELINE cfg 5, whole model: one BERT_Tacotron2 training step on one GPU: reference-code encoder in PyTorch; decoder forward +
+backward, training-mode postnet forward + backward and the fused loss on the repo's kernels; SGD update.
+usage: python tools/train_step_full.py [B] [T] [--torch-postnet-loss]   (the flag puts postnet and loss back on PyTorch ops)"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
 from tacotron2_subword_b200 import BERT_Tacotron2, create_hparams
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-T = int(sys.argv[2]) if len(sys.argv) > 2 else 800
+from tacotron2_subword_b200.loss_function import Tacotron2Loss
+args_ = [a for a in sys.argv[1:] if not a.startswith("--")]
+B = int(args_[0]) if len(args_) > 0 else 64
+T = int(args_[1]) if len(args_) > 1 else 800
+torch_tail = "--torch-postnet-loss" in sys.argv
 T_in, T_sub = 160, 53
 torch.manual_seed(1234)
 hp = create_hparams()
 model = BERT_Tacotron2(hp).cuda().train()
 model.decoder.weight_dtype = "fp16"
+model.postnet.fused_train = not torch_tail
+criterion = Tacotron2Loss()
+criterion.fused = not torch_tail
 g = torch.Generator().manual_seed(0)
 in_len = torch.randint(T_in // 2, T_in + 1, (B,), generator=g); in_len[0] = T_in
 in_len, _ = torch.sort(in_len, descending=True)                      # collate order (data_utils.py:146-160)
@@ -32,8 +39,7 @@ def step():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     opt.zero_grad(set_to_none=True)
     ev[0].record()
-    mel, mel_post, gate, al, alb = model(x)
-    loss = F.mse_loss(mel, mels) + F.mse_loss(mel_post, mels) + F.binary_cross_entropy_with_logits(gate.reshape(-1, 1), gate_t.reshape(-1, 1))
+    loss = criterion(model(x), (mels, gate_t, None), x, 50000)[0]
     ev[1].record()
     loss.backward()
     ev[2].record()
@@ -45,9 +51,9 @@ def step():
 step()
 res = [step() for _ in range(3)]
 fw, bw, up = (min(r[i] for r in res) for i in range(3))
-out = dict(config=f"cfg5 whole-model training step B={B} T={T} {T_in}/{T_sub}", forward_ms=round(fw, 2), backward_ms=round(bw, 2),
+out = dict(config=f"cfg5 whole-model training step B={B} T={T} {T_in}/{T_sub}", postnet_and_loss="PyTorch ops" if torch_tail else "repo kernels", forward_ms=round(fw, 2), backward_ms=round(bw, 2),
            optimizer_ms=round(up, 2), step_ms=round(fw + bw + up, 2), frames_per_s=round(B * T / ((fw + bw + up) * 1e-3)),
            loss_first=res[0][3], loss_last=res[-1][3], peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 2))
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/train_step_full.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/train_step_full%s.json" % ("_torch_tail" if torch_tail else ""), "w"), indent=1)
