@@ -1,0 +1,679 @@
+// persist_bwd.cuh -- persistent back-propagation through time for the teacher-forced decoder (SMA, 2 <= B <= 128): ONE
+// cooperative launch runs every frame of the reverse-time loop that backward.cuh replays as a 5-kernel graph per frame.
+// Included by taco2dec.cu after persist.cuh and backward.cuh (same arithmetic, same buffers, same gradient rows).
+//
+// Per frame t (descending) the recurrence is                                              (model.py:322-390 backwards)
+//   dG2[t] = decoder-LSTM cell backward( dh2[t] = Wd_hh^T dG2[t+1] + projection gradient )
+//   dX2[t] = [Wd_ih | Wd_hh]^T dG2[t]                       tcgen05, bf16 operands, 32 row tiles x 4 K-splits = 128 CTAs
+//   attention backward per (utterance, stream): d ctx[t] -> d alpha' -> d energies -> dq[t], d processed_memory, dv
+//   dG1[t] = attention-LSTM cell backward( dh1[t] = rows of dX2[t] + rows of dX1[t+1] + Wq^T dq[t] )
+//   dX1[t] = [W_ih | W_hh]^T dG1[t]                         tcgen05, 14 row tiles x 4 K-splits per stream = 112 CTAs
+// The decoder-LSTM chain (dG2 -> dX2 -> dG2 of the frame before) does not depend on the attention side at all, so every CTA runs
+// it ONE FRAME AHEAD: its product and epilogue hide behind the attention chain, which is the critical path
+// (attention[t] -> dG1[t] -> dX1[t] -> attention[t-1]).
+//
+// Roles per CTA are those of persist.cuh: warp 16 = TMA producer (lane i owns tile i of the CTA's 16 + 16 k-blocks; weight tiles
+// are the transposed bf16 tiles backward.cuh packs, resident in tensor memory / shared memory first, streamed from L2 otherwise),
+// warps 17/18 = one MMA-issuing thread per product, warps 0-15 = epilogues, LSTM cell updates, attention tasks.  CTAs exchange
+// through L2 with one release-increment of a counter per CTA and phase; every wait has a watchdog.
+#pragma once
+
+namespace pbw {
+
+using bt::A;
+using bt::E;
+using bt::H;
+using bt::P;
+using bt::K1;
+using bw::G;
+
+constexpr int kCtas = 128;
+constexpr int kCT = 512;
+constexpr int kThreads = kCT + 96;
+constexpr int kKb = 16;                       // k-blocks per CTA and product (G / 64 / 4 K-splits)
+constexpr int kSplits = 4;
+constexpr int kRowTiles1 = K1 / 128;          // 14 per stream
+enum { F_DG2 = 0, F_X2 = 1, F_DQ = 2, F_DG1 = 4, F_X1 = 6, F_COUNT = 8 };
+constexpr int kFlagStride = 32;
+
+struct PbwParams {
+  const unsigned char* a1t;     // [S][14][64] transposed bf16 weight tiles (rows = [prenet | ctx | h1] features, K = gate rows)
+  const unsigned char* a2t;     // [K2/128][64]
+  unsigned char* dg1t;          // [S][64 kb][NPAD x 64] bf16 tiles of dG1[t]
+  unsigned char* dg2t;          // [64 kb][NPAD x 64]
+  float* dx1;                   // [2 parities][S][4][K1][NPAD]
+  float* dx2;                   // [2 parities][4][K2][NPAD]
+  unsigned* flags;              // [F_COUNT][kFlagStride]
+  int K2;
+  int stages_a, stages_x, n_res, n_tm;
+};
+
+struct Smem { size_t aring, xring, res, out, dq, wq, att, total; };
+__host__ __device__ inline size_t att_floats(int max_ts) { return (size_t)E + 4 * A + 4 * (size_t)(max_ts + 4) + 16; }
+__host__ __device__ inline Smem smem_plan(int NPAD, int stages_a, int stages_x, int n_res, int max_ts) {
+  Smem s;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~(size_t)127; return o; };
+  s.aring = take((size_t)2 * stages_a * tc::kATileBytes);
+  s.xring = take((size_t)2 * stages_x * (size_t)NPAD * 128);
+  s.res = take((size_t)n_res * tc::kATileBytes);
+  s.out = take((size_t)4 * NPAD * 9 * 4);             // staging of 8 units x 4 gates x NPAD utterances
+  s.dq = take((size_t)A * (NPAD + 1) * 4);            // dq of the CTA's stream, [a][b]
+  s.wq = take((size_t)A * 16 * 4);                    // Wq columns of the CTA's 16 attention-LSTM units, [a][unit]
+  s.att = take(att_floats(max_ts) * 4);
+  s.total = off;
+  return s;
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const __grid_constant__ Params p, const __grid_constant__ bw::Grads g,
+                                                                            const __grid_constant__ PbwParams q) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_a[2][8], empty_a[2][8], full_x[2][8], empty_x[2][8], acc_full[2], acc_empty[2], res_bar;
+  __shared__ int s_loc[32];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int s_exit;
+  __shared__ volatile unsigned s_xfill[2][8], s_afill[2][8];
+  __shared__ volatile int s_ok[2];
+
+  constexpr int kXTileBytes = NPAD * 128;
+  constexpr int kTmemCols = 512;
+  constexpr int LOC_STREAM = -1, LOC_SMEM = 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.x;
+  const int S = p.S, B = p.B, T = p.T, K2 = q.K2;
+  const int n_g2 = (K2 / 128) * kSplits;                 // CTAs with a share of the decoder-LSTM product (128 for two streams)
+  const int n_g1s = kRowTiles1 * kSplits;                // CTAs per stream with a share of the attention-LSTM product (56)
+  const bool has_g2 = c < n_g2, has_g1 = c < S * n_g1s;
+  const int m2 = c / kSplits, sig2 = c % kSplits;
+  const int s1 = c / n_g1s, m1 = (c % n_g1s) / kSplits, sig1 = c % kSplits;
+  const int n_tiles = (has_g1 ? kKb : 0) + (has_g2 ? kKb : 0);   // program: attention-LSTM tiles first, then decoder-LSTM tiles
+  const int NSA = q.stages_a, NSX = q.stages_x;
+  unsigned* const F = q.flags;
+  auto flag = [&](int id) { return F + (size_t)id * kFlagStride; };
+  // pointwise ownership: decoder LSTM units [8c, 8c+8); attention LSTM of stream sp, units [16 (c % per), +16)
+  const int per = kCtas / S;
+  const int sp = c / per, j1 = (c % per) * (H / per);    // H / per = 16 (two streams) or 8 (one stream)
+  const int nu1 = H / per;
+  const int j2 = c * (H / kCtas);                        // 8 units
+
+  int max_ts = 0;
+  for (int s = 0; s < S; ++s) max_ts = max(max_ts, p.st[s].Ts);
+  const Smem spl = smem_plan(NPAD, NSA, NSX, q.n_res, max_ts);
+  unsigned char* aring = smem + spl.aring;
+  unsigned char* xring = smem + spl.xring;
+  unsigned char* res_s = smem + spl.res;
+  float* out_s = (float*)(smem + spl.out);               // [4][NPAD][9]
+  float* dq_s = (float*)(smem + spl.dq);                 // [A][NPAD + 1]
+  float* wq_s = (float*)(smem + spl.wq);                 // [A][16]
+  float* att_s = (float*)(smem + spl.att);
+
+  if (tid == 0) {
+    for (int gg = 0; gg < 2; ++gg)
+      for (int i = 0; i < 8; ++i) {
+        tc::mbar_init(&full_a[gg][i], 1); tc::mbar_init(&empty_a[gg][i], 1); tc::mbar_init(&full_x[gg][i], 1); tc::mbar_init(&empty_x[gg][i], 1);
+        s_xfill[gg][i] = 0; s_afill[gg][i] = 0;
+      }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 1); }
+    tc::mbar_init(&res_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_exit = 0; s_ok[0] = 1; s_ok[1] = 1;
+    // placement: the attention-LSTM product sits on the critical chain -> its tiles go on-chip first
+    int tm = 0, sm = 0;
+    for (int i = 0; i < 32; ++i) s_loc[i] = LOC_STREAM;
+    for (int i = 0; i < n_tiles; ++i) {
+      if (tm < q.n_tm) s_loc[i] = tm++;
+      else if (sm < q.n_res) s_loc[i] = LOC_SMEM + sm++;
+    }
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_base_s)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < kCT) {
+    for (int i = tid; i < A * 16; i += kCT) {
+      const int a = i >> 4, u = i & 15;
+      wq_s[i] = u < nu1 ? p.st[sp].wq[(size_t)a * H + j1 + u] : 0.f;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t acc_addr[2] = {tmem_base, tmem_base + (uint32_t)NPAD};
+  const uint32_t tm_w_col = (uint32_t)(2 * NPAD);
+  pb::Ctl ctl{p.abort_flag, &s_exit};
+  // tile i of the program: product gg (0 = attention LSTM, 1 = decoder LSTM) and k-block index inside the CTA's K split
+  auto tile_gemm = [&](int i) { return (has_g1 && i < kKb) ? 0 : 1; };
+  auto tile_src = [&](int i) -> const unsigned char* {
+    if (has_g1 && i < kKb) return q.a1t + (((size_t)s1 * kRowTiles1 + m1) * (G / 64) + sig1 * kKb + i) * tc::kATileBytes;
+    const int j = has_g1 ? i - kKb : i;
+    return q.a2t + ((size_t)m2 * (G / 64) + sig2 * kKb + j) * tc::kATileBytes;
+  };
+
+  // ---- weight tiles resident in tensor memory (A operand of tcgen05.mma), copied in once ----
+  if (tid < kCT && q.n_tm > 0) {
+    const int quarter = warp & 3, r = quarter * 32 + lane;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int loc = s_loc[i];
+      if (loc < 0 || loc >= LOC_SMEM || (loc & 3) != (warp >> 2)) continue;
+      const unsigned char* src = tile_src(i) + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16;
+      uint32_t wv[32];
+#pragma unroll
+      for (int kg = 0; kg < 8; ++kg) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + (size_t)kg * 16 * 128);
+        wv[4 * kg] = u.x; wv[4 * kg + 1] = u.y; wv[4 * kg + 2] = u.z; wv[4 * kg + 3] = u.w;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tm_w_col + (uint32_t)(loc * 32);
+      lat::tmem_st16(taddr, wv);
+      lat::tmem_st16(taddr + 16, wv + 16);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  if (warp == 16) {
+    // =========================== TMA producer: lane i owns tile i of every frame ===========================
+    const unsigned long long pol_keep = lat::l2_policy_evict_last(), pol_once = lat::l2_policy_evict_first();
+    if (lane == 0) {
+      unsigned bytes = 0;
+      for (int i = 0; i < n_tiles; ++i) if (s_loc[i] >= LOC_SMEM) bytes += (unsigned)tc::kATileBytes;
+      if (bytes) {
+        tc::mbar_expect_tx(&res_bar, bytes);
+        for (int i = 0; i < n_tiles; ++i)
+          if (s_loc[i] >= LOC_SMEM)
+            pb::tma_load_1d_hint(res_s + (size_t)(s_loc[i] - LOC_SMEM) * tc::kATileBytes, tile_src(i), tc::kATileBytes, &res_bar, pol_once);
+      } else {
+        pb::mbar_arrive(&res_bar);
+      }
+    }
+    if (lane < n_tiles) {
+      const int i = lane, gg = tile_gemm(i);
+      const bool streamed = s_loc[i] == LOC_STREAM;
+      const int g_lo = gg == 0 ? 0 : (has_g1 ? kKb : 0), g_hi = g_lo + kKb;
+      int arank = 0, n_streamed = 0;
+      for (int j = g_lo; j < g_hi; ++j) { const int st_ = s_loc[j] == LOC_STREAM; n_streamed += st_; if (j < i) arank += st_; }
+      unsigned char* const my_aring = aring + (size_t)gg * NSA * tc::kATileBytes;
+      unsigned char* const my_xring = xring + (size_t)gg * NSX * kXTileBytes;
+      const unsigned char* const a_src = tile_src(i);
+      // activation tile = k-block (K split base + local index) of the gate-gradient tiles
+      const unsigned char* const x_src = gg == 0 ? q.dg1t + ((size_t)s1 * (G / 64) + sig1 * kKb + (i - g_lo)) * kXTileBytes
+                                                 : q.dg2t + ((size_t)sig2 * kKb + (i - g_lo)) * kXTileBytes;
+      const unsigned* fptr = gg == 0 ? flag(F_DG1 + s1) : flag(F_DG2);
+      const unsigned mul = gg == 0 ? (unsigned)per : (unsigned)kCtas;
+      unsigned seen = 0;
+      bool ok = true;
+      for (int step = 0; step < T && ok; ++step) {
+        bool need_a = streamed, need_x = true;
+        const unsigned ga = (unsigned)step * (unsigned)n_streamed + (unsigned)arank, gx = (unsigned)step * (unsigned)kKb + (unsigned)(i - g_lo);
+        const unsigned target = mul * (unsigned)(step + 1);
+        unsigned spins = 0;
+        long long t0 = 0;
+        for (;;) {
+          if (need_a) {
+            const int slot = (int)(ga % (unsigned)NSA);
+            const unsigned round = ga / (unsigned)NSA;
+            if (s_afill[gg][slot] == round && (round == 0u || pb::mbar_test(&empty_a[gg][slot], (round & 1u) ^ 1u))) {
+              tc::mbar_expect_tx(&full_a[gg][slot], (unsigned)tc::kATileBytes);
+              pb::tma_load_1d_hint(my_aring + (size_t)slot * tc::kATileBytes, a_src, tc::kATileBytes, &full_a[gg][slot], pol_keep);
+              s_afill[gg][slot] = round + 1u;
+              need_a = false;
+            }
+          }
+          if (need_x) {
+            bool ready = (int)(seen - target) >= 0;
+            if (!ready) {
+              seen = ld_acquire_u32(fptr);
+              ready = (int)(seen - target) >= 0;
+              if (ready) pb::fence_proxy_async();
+            }
+            if (ready) {
+              const int slot = (int)(gx % (unsigned)NSX);
+              const unsigned round = gx / (unsigned)NSX;
+              if (s_xfill[gg][slot] == round && (round == 0u || pb::mbar_test(&empty_x[gg][slot], (round & 1u) ^ 1u))) {
+                tc::mbar_expect_tx(&full_x[gg][slot], (unsigned)kXTileBytes);
+                tc::tma_load_1d(my_xring + (size_t)slot * kXTileBytes, x_src, kXTileBytes, &full_x[gg][slot]);
+                s_xfill[gg][slot] = round + 1u;
+                need_x = false;
+              }
+            }
+          }
+          if (!need_a && !need_x) break;
+          if ((++spins & 63u) == 0u) {
+            if (s_exit) { ok = false; break; }
+            if (*((volatile int*)p.abort_flag) != 0) { s_exit = 1; ok = false; break; }
+            if (spins == 4096u) t0 = clock64();
+            else if ((spins & 4095u) == 0u && clock64() - t0 > pb::kTimeoutClocks) { atomicExch(p.abort_flag, 1); s_exit = 1; ok = false; break; }
+          }
+        }
+      }
+    }
+  } else if (warp == 17 || warp == 18) {
+    // =========================== MMA issuers: warp 17 = attention-LSTM product, warp 18 = decoder-LSTM product ==========
+    const int gg = warp - 17;
+    if (lane == 0 && (gg == 0 ? has_g1 : has_g2)) {
+      const uint32_t idesc = tc::make_idesc_f16(128, NPAD) | tc::kFmtBF16;
+      constexpr uint32_t lbo_a = (128 / 8) * 128, lbo_x = (NPAD / 8) * 128, sbo = 128;
+      const int i_lo = gg == 0 ? 0 : (has_g1 ? kKb : 0), i_hi = i_lo + kKb;
+      int n_streamed = 0;
+      for (int j = i_lo; j < i_hi; ++j) n_streamed += s_loc[j] == LOC_STREAM;
+      unsigned char* const my_aring = aring + (size_t)gg * NSA * tc::kATileBytes;
+      unsigned char* const my_xring = xring + (size_t)gg * NSX * kXTileBytes;
+      const uint64_t desc_hi_a = tc::make_smem_desc(0u, lbo_a, sbo), desc_hi_x = tc::make_smem_desc(0u, lbo_x, sbo);
+      const uint32_t a_ring_addr = tc::smem_u32(my_aring), x_ring_addr = tc::smem_u32(my_xring), res_addr = tc::smem_u32(res_s);
+      const uint32_t acc = acc_addr[gg];
+      bool ok = pb::mbar_wait_ab(&res_bar, 0u, ctl);
+      for (int step = 0; step < T && ok; ++step) {
+        if (step > 0) {
+          ok = pb::mbar_wait_ab(&acc_empty[gg], (uint32_t)((step - 1) & 1), ctl);
+          if (!ok) break;
+        }
+        unsigned ga = (unsigned)step * (unsigned)n_streamed;
+        unsigned gx = (unsigned)step * (unsigned)kKb;
+        for (int i = i_lo; i < i_hi; ++i, ++gx) {
+          const int loc = s_loc[i];
+          const int sx = (int)(gx % (unsigned)NSX), sa = (int)(ga % (unsigned)NSA);
+          if (!pb::mbar_try(&full_x[gg][sx], (gx / (unsigned)NSX) & 1u)) ok = pb::mbar_wait_ab(&full_x[gg][sx], (gx / (unsigned)NSX) & 1u, ctl);
+          if (ok && loc == LOC_STREAM && !pb::mbar_try(&full_a[gg][sa], (ga / (unsigned)NSA) & 1u))
+            ok = pb::mbar_wait_ab(&full_a[gg][sa], (ga / (unsigned)NSA) & 1u, ctl);
+          if (!ok) break;
+          tc::tc_fence_after();
+          const uint64_t dx0 = desc_hi_x | (uint64_t)(((x_ring_addr + (uint32_t)sx * (uint32_t)kXTileBytes) >> 4) & 0x3fffu);
+          const uint32_t first = (i == i_lo) ? 0u : 1u;
+          if (loc >= 0 && loc < LOC_SMEM) {
+            const uint32_t a_tm = tmem_base + tm_w_col + (uint32_t)(loc * 32);
+            pb::umma_f16_ts(acc, a_tm, dx0, idesc, first);
+            pb::umma_f16_ts(acc, a_tm + 8u, dx0 + (uint64_t)((2 * lbo_x) >> 4), idesc, 1u);
+            pb::umma_f16_ts(acc, a_tm + 16u, dx0 + (uint64_t)((4 * lbo_x) >> 4), idesc, 1u);
+            pb::umma_f16_ts(acc, a_tm + 24u, dx0 + (uint64_t)((6 * lbo_x) >> 4), idesc, 1u);
+          } else {
+            const uint32_t a_addr = loc == LOC_STREAM ? a_ring_addr + (uint32_t)sa * (uint32_t)tc::kATileBytes
+                                                      : res_addr + (uint32_t)(loc - LOC_SMEM) * (uint32_t)tc::kATileBytes;
+            const uint64_t da0 = desc_hi_a | (uint64_t)((a_addr >> 4) & 0x3fffu);
+            tc::umma_f16(acc, da0, dx0, idesc, first);
+            tc::umma_f16(acc, da0 + (uint64_t)((2 * lbo_a) >> 4), dx0 + (uint64_t)((2 * lbo_x) >> 4), idesc, 1u);
+            tc::umma_f16(acc, da0 + (uint64_t)((4 * lbo_a) >> 4), dx0 + (uint64_t)((4 * lbo_x) >> 4), idesc, 1u);
+            tc::umma_f16(acc, da0 + (uint64_t)((6 * lbo_a) >> 4), dx0 + (uint64_t)((6 * lbo_x) >> 4), idesc, 1u);
+          }
+          tc::umma_commit(&empty_x[gg][sx]);
+          if (loc == LOC_STREAM) { tc::umma_commit(&empty_a[gg][sa]); ++ga; }
+          if (i == i_hi - 1) tc::umma_commit(&acc_full[gg]);
+        }
+      }
+    }
+  } else {
+    // =========================== compute warps ===========================
+    int wn = 0;
+#define PBW_WAIT_FLAG(fptr, target)                                               \
+    {                                                                             \
+      if (tid == 0) s_ok[wn & 1] = pb::poll_ge((fptr), (target), ctl) ? 1 : 0;    \
+      pb::bar_compute();                                                          \
+      const int ok_ = s_ok[wn & 1];                                               \
+      ++wn;                                                                       \
+      if (!ok_) goto pbw_done;                                                    \
+    }
+#define PBW_WAIT_MBAR(bar, parity)                                                \
+    {                                                                             \
+      if (tid == 0) s_ok[wn & 1] = pb::mbar_wait_ab((bar), (parity), ctl) ? 1 : 0;\
+      pb::bar_compute();                                                          \
+      const int ok_ = s_ok[wn & 1];                                               \
+      ++wn;                                                                       \
+      if (!ok_) goto pbw_done;                                                    \
+    }
+    const size_t dx1_par = (size_t)S * kSplits * K1 * NPAD, dx1_str = (size_t)kSplits * K1 * NPAD;
+    const size_t dx2_par = (size_t)kSplits * K2 * NPAD;
+    const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
+    const int row_ep = (warp & 3) * 32 + lane;
+    float dc2_r[2] = {0.f, 0.f};               // carries: d cell state of the CTA's cells (fixed cell -> thread mapping)
+    float dc1_r[4] = {0.f, 0.f, 0.f, 0.f};
+    const size_t gs = (size_t)H * B;
+
+    // gate gradients staged in out_s[q][b][jl] -> bf16 operand tile chunk + fp32 rows (8 consecutive units per (gate, utterance))
+    auto store_gates = [&](unsigned char* tiles, float* rows, int j0) {
+      if (tid < 4 * B) {
+        const int qg = tid / B, b = tid - qg * B;
+        const float* v = out_s + ((size_t)qg * NPAD + b) * 9;
+        const int k = qg * H + j0;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&h0); pk.y = *reinterpret_cast<unsigned*>(&h1);
+        pk.z = *reinterpret_cast<unsigned*>(&h2); pk.w = *reinterpret_cast<unsigned*>(&h3);
+        *reinterpret_cast<uint4*>(tiles + (size_t)(k >> 6) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63)) = pk;
+        float4* dst = reinterpret_cast<float4*>(rows + (size_t)b * G + k);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    };
+
+    // decoder-LSTM cell backward of frame t for units [j2, j2 + 8) x all utterances; dh2 = projection rows + (Wd_hh^T dG2[t+1])
+    auto pointwise2 = [&](int t, bool have_next) {
+      const float* dxn = q.dx2 + (size_t)((t + 1) & 1) * dx2_par;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int e = tid + ci * kCT;
+        if (e >= 8 * B) break;
+        const int jl = e / B, b = e - jl * B, j = j2 + jl;
+        const size_t idx = (size_t)b * H + j;
+        float dh = g.dyh[((size_t)t * H + j) * B + b];
+        if (have_next) {
+#pragma unroll
+          for (int k = 0; k < kSplits; ++k) dh += __ldcg(dxn + ((size_t)k * K2 + S * (H + E) + j) * NPAD + b);
+        }
+        const float* sv = g.sv.gates2 + ((size_t)t * 5 * H + j) * B + b;
+        const float cn_prev = t > 0 ? (sv - 5 * gs)[4 * gs] : 0.f;
+        float mh = 1.f, mc = 1.f, mc_prev = 1.f;
+        if (p.training) {
+          const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * B * H : nullptr;
+          const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * B * H : nullptr;
+          mh = keep_mult(kh, idx, p.seed, 8, t, (int)idx, p.thresh_dec, sc_dec);
+          mc = keep_mult(kc, idx, p.seed, 9, t, (int)idx, p.thresh_dec, sc_dec);
+          if (t > 0) {
+            const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 5) * B * H : nullptr;
+            mc_prev = keep_mult(kcp, idx, p.seed, 9, t - 1, (int)idx, p.thresh_dec, sc_dec);
+          }
+        }
+        float dgate[4];
+        bw::lstm_cell_backward(sv, gs, mc_prev * cn_prev, mh, mc, dh, &dc2_r[ci], dgate);
+#pragma unroll
+        for (int qg = 0; qg < 4; ++qg) out_s[((size_t)qg * NPAD + b) * 9 + jl] = dgate[qg];
+      }
+      pb::bar_compute();
+      store_gates(q.dg2t, g.dg2 + (size_t)t * B * G, j2);
+      pb::bar_compute();
+    };
+
+    for (int step = 0; step < T; ++step) {
+      const int t = T - 1 - step;
+      float* dx2_cur = q.dx2 + (size_t)(t & 1) * dx2_par;
+      const float* dx1_nxt = q.dx1 + (size_t)((t + 1) & 1) * dx1_par;      // written by frame t + 1
+      float* dx1_cur = q.dx1 + (size_t)(t & 1) * dx1_par;
+
+      if (step == 0) {
+        pointwise2(t, false);
+        if (tid == 0) pb::signal(flag(F_DG2));
+      }
+      // ---------------- epilogue of dX2[t]: TMEM -> split-K partials ----------------
+      if (has_g2) {
+        PBW_WAIT_MBAR(&acc_full[1], (uint32_t)(step & 1))
+        tc::tc_fence_after();
+        float* part_mine = dx2_cur + ((size_t)sig2 * K2 + (size_t)m2 * 128) * NPAD;
+        for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
+          uint32_t v[16];
+          const uint32_t taddr = acc_addr[1] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
+          lat::tmem_ld16(taddr, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
+                                  __uint_as_float(v[4 * k4 + 3]));
+        }
+        tc::tc_fence_before();
+        pb::bar_compute();
+        if (tid == 0) { pb::mbar_arrive(&acc_empty[1]); pb::signal(flag(F_X2)); }
+      }
+      PBW_WAIT_FLAG(flag(F_X2), (unsigned)n_g2 * (unsigned)(step + 1))
+      // ---------------- the decoder-LSTM chain runs one frame ahead: dG2[t-1] now, its product overlaps the attention chain ----
+      if (t > 0) {
+        pointwise2(t - 1, true);
+        if (tid == 0) pb::signal(flag(F_DG2));
+      }
+      // the attention side of frame t needs dX1[t+1] (context and hidden rows) of its stream
+      if (step > 0) {
+        PBW_WAIT_FLAG(flag(F_X1 + sp), (unsigned)n_g1s * (unsigned)step)
+        // d prenet[t+1] = prenet rows of dX1[t+1]: the CTA saves rows [4 (c % per) ...) of its stream (P / per each)
+        const int npk = P / per, k0 = (c % per) * npk;
+        for (int e = tid; e < npk * B; e += kCT) {
+          const int kl = e / B, b = e - kl * B, k = k0 + kl;
+          float acc = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < kSplits; ++qq) acc += __ldcg(dx1_nxt + (size_t)sp * dx1_str + ((size_t)qq * K1 + k) * NPAD + b);
+          g.dpre[(((size_t)sp * T + (t + 1)) * B + b) * P + k] = acc;
+        }
+      }
+
+      // ---------------- attention backward: one (utterance, stream) task per CTA and round (attention.py:330-398) ----------------
+      for (int tau = c; tau < S * B; tau += kCtas) {
+        const int s = tau / B, b = tau - s * B;
+        const StreamParams& sa = p.st[s];
+        const int Ts = sa.Ts;
+        const int len = sa.len ? (int)sa.len[b] : Ts;
+        constexpr int kW = kCT / 32;
+        float* dctx_s = att_s;              // E
+        float* q_s = dctx_s + E;            // A
+        float* v_s = q_s + A;               // A
+        float* dqa_s = v_s + A;             // A
+        float* dva_s = dqa_s + A;           // A
+        float* p_s = dva_s + A;             // Ts+4
+        float* ap_s = p_s + Ts + 4;         // Ts+4
+        float* dan_s = ap_s + Ts + 4;       // Ts+4
+        float* de_s = dan_s + Ts + 4;       // Ts+4
+        const float* mem_b = sa.mem + (size_t)b * Ts * E;
+        const float* pm_b = sa.pm + (size_t)b * Ts * A;
+        float* dpm_b = g.dpm[s] + (size_t)b * Ts * A;
+        // early requests (independent of the incoming gradients)
+        float4 mrow[2][4];
+        float pmr[2][4], dpr[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int j = warp + kW * r;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            mrow[r][qq] = j < Ts ? __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j * E) + lane + 32 * qq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pmr[r][qq] = j < len ? __ldg(pm_b + (size_t)j * A + lane + 32 * qq) : 0.f;
+            dpr[r][qq] = j < len ? dpm_b[(size_t)j * A + lane + 32 * qq] : 0.f;
+          }
+        }
+        for (int a = tid; a < A; a += kCT) {
+          q_s[a] = g.sv.q[(((size_t)t * S + s) * B + b) * A + a];
+          v_s[a] = sa.v[a];
+          dqa_s[a] = 0.f;
+          dva_s[a] = 0.f;
+        }
+        for (int j = tid; j < Ts; j += kCT) {
+          p_s[j] = g.p_saved[s][((size_t)t * B + b) * Ts + j];
+          ap_s[j] = t > 0 ? g.align[s][((size_t)b * T + (t - 1)) * Ts + j] : (j == 0 ? 1.f : 0.f);
+          float d = g.dalpha[s][(size_t)b * Ts + j];
+          if (g.d_align[s]) d += g.d_align[s][((size_t)b * T + t) * Ts + j];
+          dan_s[j] = d;
+        }
+        if (step > 0 && s != sp) PBW_WAIT_FLAG(flag(F_X1 + s), (unsigned)n_g1s * (unsigned)step)
+        pb::bar_compute();
+        for (int d = tid; d < E; d += kCT) {
+          float acc = g.dyc[((size_t)t * B + b) * (S * E) + s * E + d];
+          if (step > 0) {
+#pragma unroll
+            for (int k = 0; k < kSplits; ++k) acc += __ldcg(dx1_nxt + (size_t)s * dx1_str + ((size_t)k * K1 + P + d) * NPAD + b);
+          }
+#pragma unroll
+          for (int k = 0; k < kSplits; ++k) acc += __ldcg(dx2_cur + ((size_t)k * K2 + s * (H + E) + H + d) * NPAD + b);
+          dctx_s[d] = acc;
+          g.dctx[(((size_t)s * T + t) * B + b) * E + d] = acc;
+        }
+        pb::bar_compute();
+        {
+          const float4* dc4 = reinterpret_cast<const float4*>(dctx_s);
+          auto dot_row = [&](int j, const float4 (&m)[4]) {
+            float acc = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const float4 dv = dc4[lane + 32 * qq];
+              acc = fmaf(m[qq].x, dv.x, acc); acc = fmaf(m[qq].y, dv.y, acc); acc = fmaf(m[qq].z, dv.z, acc); acc = fmaf(m[qq].w, dv.w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) dan_s[j] += acc;
+          };
+          if (warp < Ts) dot_row(warp, mrow[0]);
+          if (warp + kW < Ts) dot_row(warp + kW, mrow[1]);
+          for (int j = warp + 2 * kW; j < Ts; j += 2 * kW) {
+            const int jb = j + kW;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              mrow[0][qq] = __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j * E) + lane + 32 * qq);
+              mrow[1][qq] = jb < Ts ? __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)jb * E) + lane + 32 * qq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            dot_row(j, mrow[0]);
+            if (jb < Ts) dot_row(jb, mrow[1]);
+          }
+        }
+        pb::bar_compute();
+        if (p.independent) {
+          for (int j = len + tid; j < Ts; j += kCT) dan_s[j] = 0.f;
+          pb::bar_compute();
+        }
+        for (int j = tid; j < Ts; j += kCT) {
+          const float dn = dan_s[j], dn1 = j + 1 < Ts ? dan_s[j + 1] : 0.f, pj = p_s[j];
+          g.dalpha[s][(size_t)b * Ts + j] = dn * pj + dn1 * (1.0f - pj);
+          de_s[j] = ap_s[j] * (dn - dn1) * pj * (1.0f - pj);
+        }
+        pb::bar_compute();
+        {
+          float dq_acc[4] = {0.f, 0.f, 0.f, 0.f}, dv_acc[4] = {0.f, 0.f, 0.f, 0.f};
+          float qv[4], vv[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) { qv[qq] = q_s[lane + 32 * qq]; vv[qq] = v_s[lane + 32 * qq]; }
+          auto energy_bw = [&](int j, const float (&pm)[4], const float (&dp)[4]) {
+            const float de = de_s[j];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const float u = lat::fast_tanh(qv[qq] + pm[qq]);
+              const float dz = de * vv[qq] * (1.0f - u * u);
+              dq_acc[qq] += dz;
+              dv_acc[qq] = fmaf(de, u, dv_acc[qq]);
+              dpm_b[(size_t)j * A + lane + 32 * qq] = dp[qq] + dz;
+            }
+          };
+          if (warp < len) energy_bw(warp, pmr[0], dpr[0]);
+          if (warp + kW < len) energy_bw(warp + kW, pmr[1], dpr[1]);
+          for (int j = warp + 2 * kW; j < len; j += 2 * kW) {
+            const int jb = j + kW;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              pmr[0][qq] = __ldg(pm_b + (size_t)j * A + lane + 32 * qq);
+              dpr[0][qq] = dpm_b[(size_t)j * A + lane + 32 * qq];
+              pmr[1][qq] = jb < len ? __ldg(pm_b + (size_t)jb * A + lane + 32 * qq) : 0.f;
+              dpr[1][qq] = jb < len ? dpm_b[(size_t)jb * A + lane + 32 * qq] : 0.f;
+            }
+            energy_bw(j, pmr[0], dpr[0]);
+            if (jb < len) energy_bw(jb, pmr[1], dpr[1]);
+          }
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            atomicAdd(&dqa_s[lane + 32 * qq], dq_acc[qq]);
+            atomicAdd(&dva_s[lane + 32 * qq], dv_acc[qq]);
+          }
+        }
+        pb::bar_compute();
+        for (int a = tid; a < A; a += kCT) {
+          g.dq[(((size_t)s * T + t) * B + b) * A + a] = dqa_s[a];
+          g.dv[((size_t)s * B + b) * A + a] += dva_s[a];
+        }
+        pb::bar_compute();
+        if (tid == 0) pb::signal(flag(F_DQ + s));
+      }
+
+      // ---------------- attention-LSTM cell backward: stream sp, units [j1, j1 + nu1) x all utterances ----------------
+      PBW_WAIT_FLAG(flag(F_DQ + sp), (unsigned)B * (unsigned)(step + 1))
+      for (int i = tid; i < A * B; i += kCT) {
+        const int b = i / A, a = i - b * A;
+        dq_s[a * (NPAD + 1) + b] = __ldcg(g.dq + (((size_t)sp * T + t) * B + b) * A + a);
+      }
+      pb::bar_compute();
+      for (int half = 0; half * 8 < nu1; ++half) {
+        const int n_cells = 8 * B;                              // cells of this half: e = jl * B + b, jl in [0, 8)
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int e = tid + ci * kCT;
+          if (e >= n_cells) break;
+          const int jl = e / B, b = e - jl * B, ju = half * 8 + jl, j = j1 + ju;
+          const size_t idx = (size_t)b * H + j;
+          float dh = 0.f;
+          if (step > 0) {
+#pragma unroll
+            for (int k = 0; k < kSplits; ++k) dh += __ldcg(dx1_nxt + (size_t)sp * dx1_str + ((size_t)k * K1 + P + E + j) * NPAD + b);
+          }
+#pragma unroll
+          for (int k = 0; k < kSplits; ++k) dh += __ldcg(dx2_cur + ((size_t)k * K2 + sp * (H + E) + j) * NPAD + b);
+          {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 16
+            for (int a = 0; a < A; a += 2) {
+              acc0 = fmaf(dq_s[a * (NPAD + 1) + b], wq_s[a * 16 + ju], acc0);
+              acc1 = fmaf(dq_s[(a + 1) * (NPAD + 1) + b], wq_s[(a + 1) * 16 + ju], acc1);
+            }
+            dh += acc0 + acc1;
+          }
+          const float* sv = g.sv.gates1 + (((size_t)t * S + sp) * 5 * H + j) * B + b;
+          const float cn_prev = t > 0 ? (sv - (size_t)S * 5 * gs)[4 * gs] : 0.f;
+          float mh = 1.f, mc = 1.f, mc_prev = 1.f;
+          if (p.training) {
+            const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * sp) * B * H : nullptr;
+            const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * sp + 1) * B * H : nullptr;
+            mh = keep_mult(kh, idx, p.seed, 4 + 2 * sp, t, (int)idx, p.thresh_att, sc_att);
+            mc = keep_mult(kc, idx, p.seed, 5 + 2 * sp, t, (int)idx, p.thresh_att, sc_att);
+            if (t > 0) {
+              const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 2 * sp + 1) * B * H : nullptr;
+              mc_prev = keep_mult(kcp, idx, p.seed, 5 + 2 * sp, t - 1, (int)idx, p.thresh_att, sc_att);
+            }
+          }
+          float dgate[4];
+          bw::lstm_cell_backward(sv, gs, mc_prev * cn_prev, mh, mc, dh, &dc1_r[half * 2 + ci], dgate);
+#pragma unroll
+          for (int qg = 0; qg < 4; ++qg) out_s[((size_t)qg * NPAD + b) * 9 + jl] = dgate[qg];
+        }
+        pb::bar_compute();
+        store_gates(q.dg1t + (size_t)sp * (G / 64) * NPAD * 128, g.dg1 + ((size_t)sp * T + t) * B * G, j1 + half * 8);
+        pb::bar_compute();
+      }
+      if (tid == 0) pb::signal(flag(F_DG1 + sp));
+
+      // ---------------- epilogue of dX1[t] ----------------
+      if (has_g1) {
+        PBW_WAIT_MBAR(&acc_full[0], (uint32_t)(step & 1))
+        tc::tc_fence_after();
+        float* part_mine = dx1_cur + (size_t)s1 * dx1_str + ((size_t)sig1 * K1 + (size_t)m1 * 128) * NPAD;
+        for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
+          uint32_t v[16];
+          const uint32_t taddr = acc_addr[0] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
+          lat::tmem_ld16(taddr, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
+                                  __uint_as_float(v[4 * k4 + 3]));
+        }
+        tc::tc_fence_before();
+        pb::bar_compute();
+        if (tid == 0) { pb::mbar_arrive(&acc_empty[0]); pb::signal(flag(F_X1 + s1)); }
+      }
+    }
+    // d prenet[0] = prenet rows of dX1[0]
+    {
+      PBW_WAIT_FLAG(flag(F_X1 + sp), (unsigned)n_g1s * (unsigned)T)
+      const float* dx1_0 = q.dx1;            // parity of frame 0
+      const int npk = P / per, k0 = (c % per) * npk;
+      for (int e = tid; e < npk * B; e += kCT) {
+        const int kl = e / B, b = e - kl * B, k = k0 + kl;
+        float acc = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < kSplits; ++qq) acc += __ldcg(dx1_0 + (size_t)sp * dx1_str + ((size_t)qq * K1 + k) * NPAD + b);
+        g.dpre[(((size_t)sp * T + 0) * B + b) * P + k] = acc;
+      }
+    }
+  pbw_done:;
+#undef PBW_WAIT_FLAG
+#undef PBW_WAIT_MBAR
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace pbw

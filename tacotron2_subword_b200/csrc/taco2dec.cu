@@ -781,6 +781,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
 #include "backward.cuh"
 #include "postnet.cuh"
 #include "persist.cuh"
+#include "persist_bwd.cuh"
 #include "memprep.cuh"
 #include "loss.cuh"
 #include "wgrad.cuh"
@@ -1008,6 +1009,8 @@ struct taco2dec_handle {
   bw::Bufs bw_bufs;      // backward pass: transposed bf16 weight tiles, gate-gradient tiles, GEMM partials
   bool bw_alloc, bw_tiles_valid;
   int* bw_ctl;           // device word: frame counter of the backward graph
+  pbw::PbwParams pbw;    // persistent backward kernel: parity-buffered split-K partials, counters
+  bool pbw_alloc;
   cudaStream_t cap_stream;   // private stream used only to capture the per-frame CUDA graph
   bool profiling;        // record CUDA events around the persistent launch
   cudaEvent_t ev0, ev1;
@@ -1766,6 +1769,69 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent backward kernel (persist_bwd.cuh): eligibility, buffers, launch
+// ------------------------------------------------------------------------------------------
+struct PbwGeometry { int npad, stages_a, stages_x, n_res, n_tm; size_t smem; };
+
+bool pbw_geometry(const taco2dec_handle* h, int B, int T_in, int T_sub, PbwGeometry* out) {
+  const int npad = B <= 16 ? 16 : B <= 32 ? 32 : 64;
+  const int max_ts = std::max(T_in, h->cfg.n_streams == 2 ? T_sub : 0);
+  const size_t budget = (size_t)h->max_smem_optin - 2048;
+  const size_t fixed = pbw::smem_plan(npad, 0, 0, 0, max_ts).total;
+  const size_t xt = (size_t)npad * 128, at = tc::kATileBytes;
+  int n_tm = std::min(env_int("TACO2DEC_PBW_TMEM", 64), (512 - 2 * npad) / 32);
+  n_tm = std::max(0, std::min(n_tm, 32));
+  int stages_x = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_X", npad <= 32 ? 8 : 4)));
+  int stages_a = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_A", 2)));
+  while (fixed + 2 * (stages_x * xt + stages_a * at) + 1024 > budget && stages_x > 2) --stages_x;
+  if (fixed + 2 * (stages_x * xt + stages_a * at) + 1024 > budget) return false;
+  int n_res = (int)((budget - fixed - 2 * (stages_x * xt + stages_a * at) - 1024) / at);
+  n_res = std::max(0, std::min(std::min(n_res, env_int("TACO2DEC_PBW_RES", 64)), 32 - n_tm));
+  out->npad = npad; out->stages_a = stages_a; out->stages_x = stages_x; out->n_res = n_res; out->n_tm = n_tm;
+  out->smem = pbw::smem_plan(npad, stages_a, stages_x, n_res, max_ts).total;
+  return out->smem <= budget;
+}
+
+bool pbw_shape_ok(const taco2dec_handle* h, int B, int T_in, int T_sub) {
+  if (h->cfg.attention != TACO2DEC_ATTN_SMA || h->num_sms < pbw::kCtas || B < 2 || B > 64) return false;
+  if (getenv("TACO2DEC_NO_PERSIST_BWD")) return false;
+  PbwGeometry g;
+  return pbw_geometry(h, B, T_in, T_sub, &g);
+}
+
+template <int NPAD>
+int pbw_run(taco2dec_handle* h, const Params& p, const bw::Grads& g, const PbwGeometry& geo, cudaStream_t st) {
+  const int S = p.S, B = p.B;
+  const bw::Bufs& bb = h->bw_bufs;
+  if (!h->pbw_alloc) {
+    const size_t NP = 128;
+    CUDA_TRY(cudaMalloc(&h->pbw.dx1, (size_t)2 * 2 * pbw::kSplits * bt::K1 * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->pbw.dx2, (size_t)2 * pbw::kSplits * (2 * (bt::H + bt::E) + bt::H) * NP * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->pbw.flags, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned)));
+    h->pbw_alloc = true;
+  }
+  pbw::PbwParams q = h->pbw;
+  q.a1t = bb.a1t; q.a2t = bb.a2t; q.dg1t = bb.dg1; q.dg2t = bb.dg2; q.K2 = bb.K2;
+  q.stages_a = geo.stages_a; q.stages_x = geo.stages_x; q.n_res = geo.n_res; q.n_tm = geo.n_tm;
+  CUDA_TRY(cudaMemsetAsync(q.flags, 0, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(bb.dg1, 0, (size_t)S * (bw::G / 64) * NPAD * 128, st));      // utterance columns >= B of the operand tiles
+  CUDA_TRY(cudaMemsetAsync(bb.dg2, 0, (size_t)(bw::G / 64) * NPAD * 128, st));
+  bw::bw_dy_all<<<dim3((p.T * B + bw::kDyRows - 1) / bw::kDyRows, (bt::H + S * bt::E) / bw::kDyCols), 256, 0, st>>>(p, g);
+  auto kern = pbw::decoder_backward_persistent<NPAD>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pbw::kThreads, geo.smem));
+  if (per_sm < 1) return fail(TACO2DEC_E_STATE, "persistent backward kernel does not fit on an SM");
+  void* args[] = {(void*)&p, (void*)&g, (void*)&q};
+  if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(pbw::kCtas), dim3(pbw::kThreads), args, geo.smem, st));
+  if (h->profiling) { CUDA_TRY(cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  return 0;
+}
+
 int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, const WorkspaceLayout& L, cudaStream_t st) {
   const taco2dec_config& c = h->cfg;
   // control words: barrier counter, watchdog flag, done counter
@@ -1917,6 +1983,7 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   memset(&h->cur_sv, 0, sizeof(h->cur_sv));
   memset(&h->pb, 0, sizeof(h->pb)); h->pb_alloc = false; h->pb_tiles_valid = false; h->pb_xpre = nullptr; h->pb_xpre_bytes = 0; h->pb_dbg = nullptr; h->pm_given[0] = h->pm_given[1] = nullptr;
   memset(&h->bw_bufs, 0, sizeof(h->bw_bufs)); h->bw_alloc = false; h->bw_tiles_valid = false; h->bw_ctl = nullptr;
+  memset(&h->pbw, 0, sizeof(h->pbw)); h->pbw_alloc = false;
   h->profiling = false;
   h->ev_valid = false;
   CUDA_TRY(cudaSetDevice(device));
@@ -1952,6 +2019,10 @@ int taco2dec_destroy(taco2dec_handle* h) {
     if (h->bw_alloc) {
       bw::Bufs& b = h->bw_bufs;
       void* ptrs[] = {b.a1t, b.a2t, b.dg1, b.dg2, b.dx1, b.dx2, h->bw_ctl};
+      for (void* q : ptrs) if (q) cudaFree(q);
+    }
+    if (h->pbw_alloc) {
+      void* ptrs[] = {h->pbw.dx1, h->pbw.dx2, h->pbw.flags};
       for (void* q : ptrs) if (q) cudaFree(q);
     }
   }
@@ -2182,6 +2253,16 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
   g.dyh = (float*)(gb + gs.dyh); g.dyc = (float*)(gb + gs.dyc);
   CUDA_TRY(cudaMemsetAsync(gb + gs.zero_begin, 0, gs.zero_end - gs.zero_begin, st));
   if (int rc = bw_prepare(h, st)) return rc;
+  if (pbw_shape_ok(h, a->B, a->T_in, T_sub)) {       // one persistent launch for the whole reverse-time loop
+    PbwGeometry geo;
+    pbw_geometry(h, a->B, a->T_in, T_sub, &geo);
+    p.abort_flag = h->abort_dev;
+    switch (geo.npad) {
+      case 16: return pbw_run<16>(h, p, g, geo, st);
+      case 32: return pbw_run<32>(h, p, g, geo, st);
+      default: return pbw_run<64>(h, p, g, geo, st);
+    }
+  }
   if (a->B <= 16) return bw_run_frames<16>(h, p, g, st);
   if (a->B <= 32) return bw_run_frames<32>(h, p, g, st);
   if (a->B <= 64) return bw_run_frames<64>(h, p, g, st);
