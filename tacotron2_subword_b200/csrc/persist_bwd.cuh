@@ -45,17 +45,20 @@ struct PbwParams {
   float* dx2;                   // [2 parities][4][K2][NPAD]
   unsigned* flags;              // [F_COUNT][kFlagStride]
   int K2;
-  int stages_a, stages_x, n_res, n_tm;
+  int stages_a, stages_x0, stages_x1, n_res, n_tm;      // ring depths: weight tiles (per product), activation tiles of product 0 / 1
 };
 
 struct Smem { size_t aring, xring, res, out, dq, wq, att, total; };
-__host__ __device__ inline size_t att_floats(int max_ts) { return (size_t)E + 4 * A + 4 * (size_t)(max_ts + 4) + 16; }
+__host__ __device__ inline size_t att_floats(int max_ts) {      // attention scratch; also holds u[16][NPAD + 1] (<= 16 * 129 floats)
+  const size_t a = (size_t)E + 4 * A + 4 * (size_t)(max_ts + 4) + 16;
+  return a > 16 * 129 ? a : 16 * 129;
+}
 __host__ __device__ inline Smem smem_plan(int NPAD, int stages_a, int stages_x, int n_res, int max_ts) {
   Smem s;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~(size_t)127; return o; };
   s.aring = take((size_t)2 * stages_a * tc::kATileBytes);
-  s.xring = take((size_t)2 * stages_x * (size_t)NPAD * 128);
+  s.xring = take((size_t)stages_x * (size_t)NPAD * 128);        // stages_x = slots of both products together
   s.res = take((size_t)n_res * tc::kATileBytes);
   s.out = take((size_t)4 * NPAD * 9 * 4);             // staging of 8 units x 4 gates x NPAD utterances
   s.dq = take((size_t)A * (NPAD + 1) * 4);            // dq of the CTA's stream, [a][b]
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
   __shared__ volatile int s_exit;
   __shared__ volatile unsigned s_xfill[2][8], s_afill[2][8];
   __shared__ volatile int s_ok[2];
+  __shared__ long long s_ph[16];
 
   constexpr int kXTileBytes = NPAD * 128;
   constexpr int kTmemCols = 512;
@@ -88,18 +92,22 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
   const int m2 = c / kSplits, sig2 = c % kSplits;
   const int s1 = c / n_g1s, m1 = (c % n_g1s) / kSplits, sig1 = c % kSplits;
   const int n_tiles = (has_g1 ? kKb : 0) + (has_g2 ? kKb : 0);   // program: attention-LSTM tiles first, then decoder-LSTM tiles
-  const int NSA = q.stages_a, NSX = q.stages_x;
+  const int NSA = q.stages_a;
+  const int NSXg[2] = {q.stages_x0, q.stages_x1};        // activation ring depth per product
   unsigned* const F = q.flags;
   auto flag = [&](int id) { return F + (size_t)id * kFlagStride; };
   // pointwise ownership: decoder LSTM units [8c, 8c+8); attention LSTM of stream sp, units [16 (c % per), +16)
   const int per = kCtas / S;
   const int sp = c / per, j1 = (c % per) * (H / per);    // H / per = 16 (two streams) or 8 (one stream)
   const int nu1 = H / per;
-  const int j2 = c * (H / kCtas);                        // 8 units
+  // decoder-LSTM cells: with two streams the CTAs of the sub-word stream (short memory: light attention tasks) take all of them
+  const bool own2 = S == 2 ? c >= per : true;
+  const int n_own2 = S == 2 ? per : kCtas, nu2 = H / n_own2;        // 16 or 8 units
+  const int j2 = (S == 2 ? c - per : c) * nu2;
 
   int max_ts = 0;
   for (int s = 0; s < S; ++s) max_ts = max(max_ts, p.st[s].Ts);
-  const Smem spl = smem_plan(NPAD, NSA, NSX, q.n_res, max_ts);
+  const Smem spl = smem_plan(NPAD, NSA, NSXg[0] + NSXg[1], q.n_res, max_ts);
   unsigned char* aring = smem + spl.aring;
   unsigned char* xring = smem + spl.xring;
   unsigned char* res_s = smem + spl.res;
@@ -118,6 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
     tc::mbar_init(&res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_exit = 0; s_ok[0] = 1; s_ok[1] = 1;
+    for (int i = 0; i < 16; ++i) s_ph[i] = 0;
     // placement: the attention-LSTM product sits on the critical chain -> its tiles go on-chip first
     int tm = 0, sm = 0;
     for (int i = 0; i < 32; ++i) s_loc[i] = LOC_STREAM;
@@ -196,13 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
       int arank = 0, n_streamed = 0;
       for (int j = g_lo; j < g_hi; ++j) { const int st_ = s_loc[j] == LOC_STREAM; n_streamed += st_; if (j < i) arank += st_; }
       unsigned char* const my_aring = aring + (size_t)gg * NSA * tc::kATileBytes;
-      unsigned char* const my_xring = xring + (size_t)gg * NSX * kXTileBytes;
+      unsigned char* const my_xring = xring + (size_t)gg * NSXg[0] * kXTileBytes;
+      const int NSX = NSXg[gg];
       const unsigned char* const a_src = tile_src(i);
       // activation tile = k-block (K split base + local index) of the gate-gradient tiles
       const unsigned char* const x_src = gg == 0 ? q.dg1t + ((size_t)s1 * (G / 64) + sig1 * kKb + (i - g_lo)) * kXTileBytes
                                                  : q.dg2t + ((size_t)sig2 * kKb + (i - g_lo)) * kXTileBytes;
       const unsigned* fptr = gg == 0 ? flag(F_DG1 + s1) : flag(F_DG2);
-      const unsigned mul = gg == 0 ? (unsigned)per : (unsigned)kCtas;
+      const unsigned mul = gg == 0 ? (unsigned)per : (unsigned)(S == 2 ? per : kCtas);
       unsigned seen = 0;
       bool ok = true;
       for (int step = 0; step < T && ok; ++step) {
@@ -260,7 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
       int n_streamed = 0;
       for (int j = i_lo; j < i_hi; ++j) n_streamed += s_loc[j] == LOC_STREAM;
       unsigned char* const my_aring = aring + (size_t)gg * NSA * tc::kATileBytes;
-      unsigned char* const my_xring = xring + (size_t)gg * NSX * kXTileBytes;
+      unsigned char* const my_xring = xring + (size_t)gg * NSXg[0] * kXTileBytes;
+      const int NSX = NSXg[gg];
       const uint64_t desc_hi_a = tc::make_smem_desc(0u, lbo_a, sbo), desc_hi_x = tc::make_smem_desc(0u, lbo_x, sbo);
       const uint32_t a_ring_addr = tc::smem_u32(my_aring), x_ring_addr = tc::smem_u32(my_xring), res_addr = tc::smem_u32(res_s);
       const uint32_t acc = acc_addr[gg];
@@ -306,6 +317,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
   } else {
     // =========================== compute warps ===========================
     int wn = 0;
+    long long ph_t = clock64();
+#define PBW_PH(slot)                                      \
+    if (c == 0 && tid == 0) {                             \
+      const long long n_ = clock64();                     \
+      s_ph[slot] += n_ - ph_t;                            \
+      ph_t = n_;                                          \
+    }
 #define PBW_WAIT_FLAG(fptr, target)                                               \
     {                                                                             \
       if (tid == 0) s_ok[wn & 1] = pb::poll_ge((fptr), (target), ctl) ? 1 : 0;    \
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
     const size_t dx2_par = (size_t)kSplits * K2 * NPAD;
     const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
     const int row_ep = (warp & 3) * 32 + lane;
-    float dc2_r[2] = {0.f, 0.f};               // carries: d cell state of the CTA's cells (fixed cell -> thread mapping)
+    float dc2_r[4] = {0.f, 0.f, 0.f, 0.f};     // carries: d cell state of the CTA's cells (fixed cell -> thread mapping)
     float dc1_r[4] = {0.f, 0.f, 0.f, 0.f};
     const size_t gs = (size_t)H * B;
 
@@ -351,79 +369,98 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
     // decoder-LSTM cell backward of frame t for units [j2, j2 + 8) x all utterances; dh2 = projection rows + (Wd_hh^T dG2[t+1])
     auto pointwise2 = [&](int t, bool have_next) {
       const float* dxn = q.dx2 + (size_t)((t + 1) & 1) * dx2_par;
+      for (int half = 0; half * 8 < nu2; ++half) {
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int e = tid + ci * kCT;
-        if (e >= 8 * B) break;
-        const int jl = e / B, b = e - jl * B, j = j2 + jl;
-        const size_t idx = (size_t)b * H + j;
-        float dh = g.dyh[((size_t)t * H + j) * B + b];
-        if (have_next) {
+        for (int ci = 0; ci < 2; ++ci) {
+          const int e = tid + ci * kCT;
+          if (e >= 8 * B) break;
+          const int jl = e / B, b = e - jl * B, j = j2 + half * 8 + jl;
+          const size_t idx = (size_t)b * H + j;
+          float dh = g.dyh[((size_t)t * H + j) * B + b];
+          if (have_next) {
 #pragma unroll
-          for (int k = 0; k < kSplits; ++k) dh += __ldcg(dxn + ((size_t)k * K2 + S * (H + E) + j) * NPAD + b);
-        }
-        const float* sv = g.sv.gates2 + ((size_t)t * 5 * H + j) * B + b;
-        const float cn_prev = t > 0 ? (sv - 5 * gs)[4 * gs] : 0.f;
-        float mh = 1.f, mc = 1.f, mc_prev = 1.f;
-        if (p.training) {
-          const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * B * H : nullptr;
-          const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * B * H : nullptr;
-          mh = keep_mult(kh, idx, p.seed, 8, t, (int)idx, p.thresh_dec, sc_dec);
-          mc = keep_mult(kc, idx, p.seed, 9, t, (int)idx, p.thresh_dec, sc_dec);
-          if (t > 0) {
-            const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 5) * B * H : nullptr;
-            mc_prev = keep_mult(kcp, idx, p.seed, 9, t - 1, (int)idx, p.thresh_dec, sc_dec);
+            for (int k = 0; k < kSplits; ++k) dh += __ldcg(dxn + ((size_t)k * K2 + S * (H + E) + j) * NPAD + b);
           }
-        }
-        float dgate[4];
-        bw::lstm_cell_backward(sv, gs, mc_prev * cn_prev, mh, mc, dh, &dc2_r[ci], dgate);
+          const float* sv = g.sv.gates2 + ((size_t)t * 5 * H + j) * B + b;
+          const float cn_prev = t > 0 ? (sv - 5 * gs)[4 * gs] : 0.f;
+          float mh = 1.f, mc = 1.f, mc_prev = 1.f;
+          if (p.training) {
+            const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 4) * B * H : nullptr;
+            const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 5) * B * H : nullptr;
+            mh = keep_mult(kh, idx, p.seed, 8, t, (int)idx, p.thresh_dec, sc_dec);
+            mc = keep_mult(kc, idx, p.seed, 9, t, (int)idx, p.thresh_dec, sc_dec);
+            if (t > 0) {
+              const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 5) * B * H : nullptr;
+              mc_prev = keep_mult(kcp, idx, p.seed, 9, t - 1, (int)idx, p.thresh_dec, sc_dec);
+            }
+          }
+          float dgate[4];
+          bw::lstm_cell_backward(sv, gs, mc_prev * cn_prev, mh, mc, dh, &dc2_r[half * 2 + ci], dgate);
 #pragma unroll
-        for (int qg = 0; qg < 4; ++qg) out_s[((size_t)qg * NPAD + b) * 9 + jl] = dgate[qg];
+          for (int qg = 0; qg < 4; ++qg) out_s[((size_t)qg * NPAD + b) * 9 + jl] = dgate[qg];
+        }
+        pb::bar_compute();
+        store_gates(q.dg2t, g.dg2 + (size_t)t * B * G, j2 + half * 8);
+        pb::bar_compute();
       }
-      pb::bar_compute();
-      store_gates(q.dg2t, g.dg2 + (size_t)t * B * G, j2);
-      pb::bar_compute();
     };
+
+    // epilogue of the e-th decoder-LSTM product (frame T-1-e): TMEM -> split-K partials of dX2, then the counter
+    auto epilogue2 = [&](int e) -> bool {
+      if (!has_g2) return true;
+      if (tid == 0) s_ok[wn & 1] = pb::mbar_wait_ab(&acc_full[1], (uint32_t)(e & 1), ctl) ? 1 : 0;
+      pb::bar_compute();
+      const int ok_ = s_ok[wn & 1];
+      ++wn;
+      if (!ok_) return false;
+      tc::tc_fence_after();
+      const int tt = T - 1 - e;
+      float* part_mine = q.dx2 + (size_t)(tt & 1) * dx2_par + ((size_t)sig2 * K2 + (size_t)m2 * 128) * NPAD;
+      for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
+        uint32_t v[16];
+        const uint32_t taddr = acc_addr[1] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
+        lat::tmem_ld16(taddr, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
+                                __uint_as_float(v[4 * k4 + 3]));
+      }
+      tc::tc_fence_before();
+      pb::bar_compute();
+      if (tid == 0) { pb::mbar_arrive(&acc_empty[1]); pb::signal(flag(F_X2)); }
+      return true;
+    };
+
+    // ---- prologue: the decoder-LSTM chain (dG2 -> dX2 -> dG2 of the frame before) does not depend on the attention side; it is
+    //      started two cell updates ahead and afterwards advanced inside the window in which the compute warps would otherwise
+    //      wait for the attention-LSTM product (see the end of the loop body) ----
+    if (own2) {
+      pointwise2(T - 1, false);
+      if (tid == 0) pb::signal(flag(F_DG2));
+    }
+    if (!epilogue2(0)) goto pbw_done;
+    if (own2 && T > 1) {
+      PBW_WAIT_FLAG(flag(F_X2), (unsigned)n_g2)
+      pointwise2(T - 2, true);
+      if (tid == 0) pb::signal(flag(F_DG2));
+    }
 
     for (int step = 0; step < T; ++step) {
       const int t = T - 1 - step;
-      float* dx2_cur = q.dx2 + (size_t)(t & 1) * dx2_par;
+      const float* dx2_cur = q.dx2 + (size_t)(t & 1) * dx2_par;
       const float* dx1_nxt = q.dx1 + (size_t)((t + 1) & 1) * dx1_par;      // written by frame t + 1
       float* dx1_cur = q.dx1 + (size_t)(t & 1) * dx1_par;
 
-      if (step == 0) {
-        pointwise2(t, false);
-        if (tid == 0) pb::signal(flag(F_DG2));
-      }
-      // ---------------- epilogue of dX2[t]: TMEM -> split-K partials ----------------
-      if (has_g2) {
-        PBW_WAIT_MBAR(&acc_full[1], (uint32_t)(step & 1))
-        tc::tc_fence_after();
-        float* part_mine = dx2_cur + ((size_t)sig2 * K2 + (size_t)m2 * 128) * NPAD;
-        for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
-          uint32_t v[16];
-          const uint32_t taddr = acc_addr[1] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
-          lat::tmem_ld16(taddr, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
-                                  __uint_as_float(v[4 * k4 + 3]));
-        }
-        tc::tc_fence_before();
-        pb::bar_compute();
-        if (tid == 0) { pb::mbar_arrive(&acc_empty[1]); pb::signal(flag(F_X2)); }
-      }
-      PBW_WAIT_FLAG(flag(F_X2), (unsigned)n_g2 * (unsigned)(step + 1))
-      // ---------------- the decoder-LSTM chain runs one frame ahead: dG2[t-1] now, its product overlaps the attention chain ----
-      if (t > 0) {
-        pointwise2(t - 1, true);
-        if (tid == 0) pb::signal(flag(F_DG2));
-      }
+      PBW_PH(0)
+      PBW_WAIT_FLAG(flag(F_X2), (unsigned)n_g2 * (unsigned)(step + 1))      // dX2[t] of every CTA (normally long since there)
+      PBW_PH(3)
+      PBW_PH(4)
       // the attention side of frame t needs dX1[t+1] (context and hidden rows) of its stream
       if (step > 0) {
         PBW_WAIT_FLAG(flag(F_X1 + sp), (unsigned)n_g1s * (unsigned)step)
+        PBW_PH(5)
         // d prenet[t+1] = prenet rows of dX1[t+1]: the CTA saves rows [4 (c % per) ...) of its stream (P / per each)
         const int npk = P / per, k0 = (c % per) * npk;
         for (int e = tid; e < npk * B; e += kCT) {
@@ -435,6 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         }
       }
 
+      PBW_PH(6)
       // ---------------- attention backward: one (utterance, stream) task per CTA and round (attention.py:330-398) ----------------
       for (int tau = c; tau < S * B; tau += kCtas) {
         const int s = tau / B, b = tau - s * B;
@@ -575,64 +613,108 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         if (tid == 0) pb::signal(flag(F_DQ + s));
       }
 
+      PBW_PH(7)
       // ---------------- attention-LSTM cell backward: stream sp, units [j1, j1 + nu1) x all utterances ----------------
+      // Everything but Wq^T dq is known before the last attention task of the stream has finished: the split-K partials, the saved
+      // gates and the dropout masks are fetched (and the cell's derivative reduced to one linear form in dh and the carry) while
+      // this CTA would otherwise wait for dq;  cell e = ju * B + b, two cells per thread at most (16 units x B <= 64 utterances)
+      float c_dh[2], c_mc[2], c_al[2], c_gf[2], c_b0[2], c_b1[2], c_b2[2], c_b3[2];
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int e = tid + ci * kCT;
+        c_dh[ci] = c_mc[ci] = c_al[ci] = c_gf[ci] = c_b0[ci] = c_b1[ci] = c_b2[ci] = c_b3[ci] = 0.f;
+        if (e >= nu1 * B) continue;
+        const int ju = e / B, b = e - ju * B, j = j1 + ju;
+        const size_t idx = (size_t)b * H + j;
+        float dh = 0.f;
+        if (step > 0) {
+#pragma unroll
+          for (int k = 0; k < kSplits; ++k) dh += __ldcg(dx1_nxt + (size_t)sp * dx1_str + ((size_t)k * K1 + P + E + j) * NPAD + b);
+        }
+#pragma unroll
+        for (int k = 0; k < kSplits; ++k) dh += __ldcg(dx2_cur + ((size_t)k * K2 + sp * (H + E) + j) * NPAD + b);
+        const float* sv = g.sv.gates1 + (((size_t)t * S + sp) * 5 * H + j) * B + b;
+        const float gi = sv[0], gf = sv[gs], gg = sv[2 * gs], go = sv[3 * gs], cn = sv[4 * gs];
+        const float cn_prev = t > 0 ? (sv - (size_t)S * 5 * gs)[4 * gs] : 0.f;
+        float mh = 1.f, mc = 1.f, mc_prev = 1.f;
+        if (p.training) {
+          const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * sp) * B * H : nullptr;
+          const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * sp + 1) * B * H : nullptr;
+          mh = keep_mult(kh, idx, p.seed, 4 + 2 * sp, t, (int)idx, p.thresh_att, sc_att);
+          mc = keep_mult(kc, idx, p.seed, 5 + 2 * sp, t, (int)idx, p.thresh_att, sc_att);
+          if (t > 0) {
+            const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 2 * sp + 1) * B * H : nullptr;
+            mc_prev = keep_mult(kcp, idx, p.seed, 5 + 2 * sp, t - 1, (int)idx, p.thresh_att, sc_att);
+          }
+        }
+        // bw::lstm_cell_backward as a linear form:  dcn = carry * mc + dh * al;  carry' = dcn * gf;  dgate = {dcn b0, dcn b1, dcn b2, dh b3}
+        const float tcn = tanhf(cn);
+        c_dh[ci] = dh; c_mc[ci] = mc; c_gf[ci] = gf;
+        c_al[ci] = mh * go * (1.0f - tcn * tcn);
+        c_b0[ci] = gg * gi * (1.0f - gi);
+        c_b1[ci] = (mc_prev * cn_prev) * gf * (1.0f - gf);
+        c_b2[ci] = gi * (1.0f - gg * gg);
+        c_b3[ci] = mh * tcn * go * (1.0f - go);
+      }
       PBW_WAIT_FLAG(flag(F_DQ + sp), (unsigned)B * (unsigned)(step + 1))
+      PBW_PH(8)
       for (int i = tid; i < A * B; i += kCT) {
         const int b = i / A, a = i - b * A;
         dq_s[a * (NPAD + 1) + b] = __ldcg(g.dq + (((size_t)sp * T + t) * B + b) * A + a);
       }
       pb::bar_compute();
+      // u[unit][b] = sum_a Wq[a][unit] dq[b][a]   (attention.py:56 backwards): thread = (utterance, 4 units), one dq word and
+      // one 16-byte weight word per 4 multiply-adds
+      float* u_s = att_s;                                     // [16][NPAD + 1], the attention scratch is free in this phase
+      if (tid < 4 * B) {
+        const int b = tid % B, uq = tid / B;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int a = 0; a < A; ++a) {
+          const float d = dq_s[a * (NPAD + 1) + b];
+          const float4 w = *reinterpret_cast<const float4*>(wq_s + a * 16 + 4 * uq);
+          a0 = fmaf(d, w.x, a0); a1 = fmaf(d, w.y, a1); a2 = fmaf(d, w.z, a2); a3 = fmaf(d, w.w, a3);
+        }
+        u_s[(4 * uq + 0) * (NPAD + 1) + b] = a0; u_s[(4 * uq + 1) * (NPAD + 1) + b] = a1;
+        u_s[(4 * uq + 2) * (NPAD + 1) + b] = a2; u_s[(4 * uq + 3) * (NPAD + 1) + b] = a3;
+      }
+      pb::bar_compute();
       for (int half = 0; half * 8 < nu1; ++half) {
-        const int n_cells = 8 * B;                              // cells of this half: e = jl * B + b, jl in [0, 8)
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int e = tid + ci * kCT;
-          if (e >= n_cells) break;
-          const int jl = e / B, b = e - jl * B, ju = half * 8 + jl, j = j1 + ju;
-          const size_t idx = (size_t)b * H + j;
-          float dh = 0.f;
-          if (step > 0) {
-#pragma unroll
-            for (int k = 0; k < kSplits; ++k) dh += __ldcg(dx1_nxt + (size_t)sp * dx1_str + ((size_t)k * K1 + P + E + j) * NPAD + b);
-          }
-#pragma unroll
-          for (int k = 0; k < kSplits; ++k) dh += __ldcg(dx2_cur + ((size_t)k * K2 + sp * (H + E) + j) * NPAD + b);
-          {
-            float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 16
-            for (int a = 0; a < A; a += 2) {
-              acc0 = fmaf(dq_s[a * (NPAD + 1) + b], wq_s[a * 16 + ju], acc0);
-              acc1 = fmaf(dq_s[(a + 1) * (NPAD + 1) + b], wq_s[(a + 1) * 16 + ju], acc1);
-            }
-            dh += acc0 + acc1;
-          }
-          const float* sv = g.sv.gates1 + (((size_t)t * S + sp) * 5 * H + j) * B + b;
-          const float cn_prev = t > 0 ? (sv - (size_t)S * 5 * gs)[4 * gs] : 0.f;
-          float mh = 1.f, mc = 1.f, mc_prev = 1.f;
-          if (p.training) {
-            const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * sp) * B * H : nullptr;
-            const uint8_t* kc = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * sp + 1) * B * H : nullptr;
-            mh = keep_mult(kh, idx, p.seed, 4 + 2 * sp, t, (int)idx, p.thresh_att, sc_att);
-            mc = keep_mult(kc, idx, p.seed, 5 + 2 * sp, t, (int)idx, p.thresh_att, sc_att);
-            if (t > 0) {
-              const uint8_t* kcp = p.lstm_keep ? p.lstm_keep + ((size_t)(t - 1) * 6 + 2 * sp + 1) * B * H : nullptr;
-              mc_prev = keep_mult(kcp, idx, p.seed, 5 + 2 * sp, t - 1, (int)idx, p.thresh_att, sc_att);
-            }
-          }
-          float dgate[4];
-          bw::lstm_cell_backward(sv, gs, mc_prev * cn_prev, mh, mc, dh, &dc1_r[half * 2 + ci], dgate);
-#pragma unroll
-          for (int qg = 0; qg < 4; ++qg) out_s[((size_t)qg * NPAD + b) * 9 + jl] = dgate[qg];
+          if (e >= nu1 * B) continue;
+          const int ju = e / B, b = e - ju * B;
+          if ((ju >> 3) != half) continue;
+          const float dh = c_dh[ci] + u_s[ju * (NPAD + 1) + b];
+          const float dcn = dc1_r[ci] * c_mc[ci] + dh * c_al[ci];
+          dc1_r[ci] = dcn * c_gf[ci];
+          float* o = out_s + (size_t)b * 9 + (ju & 7);
+          o[0] = dcn * c_b0[ci]; o[(size_t)NPAD * 9] = dcn * c_b1[ci]; o[(size_t)2 * NPAD * 9] = dcn * c_b2[ci]; o[(size_t)3 * NPAD * 9] = dh * c_b3[ci];
         }
         pb::bar_compute();
         store_gates(q.dg1t + (size_t)sp * (G / 64) * NPAD * 128, g.dg1 + ((size_t)sp * T + t) * B * G, j1 + half * 8);
         pb::bar_compute();
       }
       if (tid == 0) pb::signal(flag(F_DG1 + sp));
+      PBW_PH(9)
+      // ---------------- window: the attention-LSTM product of frame t is being issued now; advance the decoder-LSTM chain ----------------
+      if (t > 0) {
+        if (!epilogue2(step + 1)) goto pbw_done;                 // dX2[t-1]
+        PBW_PH(1)
+        if (own2 && t > 1) {
+          PBW_WAIT_FLAG(flag(F_X2), (unsigned)n_g2 * (unsigned)(step + 2))
+          PBW_PH(2)
+          pointwise2(t - 2, true);                               // dG2[t-2]: needs the hidden rows of dX2[t-1] from every K split
+          if (tid == 0) pb::signal(flag(F_DG2));
+        }
+      }
+      PBW_PH(4)
 
       // ---------------- epilogue of dX1[t] ----------------
       if (has_g1) {
         PBW_WAIT_MBAR(&acc_full[0], (uint32_t)(step & 1))
+        PBW_PH(10)
         tc::tc_fence_after();
         float* part_mine = dx1_cur + (size_t)s1 * dx1_str + ((size_t)sig1 * K1 + (size_t)m1 * 128) * NPAD;
         for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
@@ -650,6 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         pb::bar_compute();
         if (tid == 0) { pb::mbar_arrive(&acc_empty[0]); pb::signal(flag(F_X1 + s1)); }
       }
+      PBW_PH(11)
     }
     // d prenet[0] = prenet rows of dX1[0]
     {
@@ -665,6 +748,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
       }
     }
   pbw_done:;
+    if (c == 0 && tid == 0 && p.phase_clocks)
+      for (int i = 0; i < 16; ++i) p.phase_clocks[i] = s_ph[i];
+#undef PBW_PH
 #undef PBW_WAIT_FLAG
 #undef PBW_WAIT_MBAR
   }

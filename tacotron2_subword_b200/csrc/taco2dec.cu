@@ -1772,7 +1772,7 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
 // ------------------------------------------------------------------------------------------
 // Persistent backward kernel (persist_bwd.cuh): eligibility, buffers, launch
 // ------------------------------------------------------------------------------------------
-struct PbwGeometry { int npad, stages_a, stages_x, n_res, n_tm; size_t smem; };
+struct PbwGeometry { int npad, stages_a, stages_x0, stages_x1, n_res, n_tm; size_t smem; };
 
 bool pbw_geometry(const taco2dec_handle* h, int B, int T_in, int T_sub, PbwGeometry* out) {
   const int npad = B <= 16 ? 16 : B <= 32 ? 32 : 64;
@@ -1782,14 +1782,16 @@ bool pbw_geometry(const taco2dec_handle* h, int B, int T_in, int T_sub, PbwGeome
   const size_t xt = (size_t)npad * 128, at = tc::kATileBytes;
   int n_tm = std::min(env_int("TACO2DEC_PBW_TMEM", 64), (512 - 2 * npad) / 32);
   n_tm = std::max(0, std::min(n_tm, 32));
-  int stages_x = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_X", npad <= 32 ? 8 : 4)));
+  // activation rings: the attention-LSTM product (0) is on the critical chain and all of its 16 tiles become ready at once
+  int sx0 = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_X0", 8)));
+  int sx1 = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_X1", npad <= 32 ? 4 : 2)));
   int stages_a = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_A", 2)));
-  while (fixed + 2 * (stages_x * xt + stages_a * at) + 1024 > budget && stages_x > 2) --stages_x;
-  if (fixed + 2 * (stages_x * xt + stages_a * at) + 1024 > budget) return false;
-  int n_res = (int)((budget - fixed - 2 * (stages_x * xt + stages_a * at) - 1024) / at);
+  while (fixed + (sx0 + sx1) * xt + 2 * stages_a * at + 1024 > budget && sx0 > 2) --sx0;
+  if (fixed + (sx0 + sx1) * xt + 2 * stages_a * at + 1024 > budget) return false;
+  int n_res = (int)((budget - fixed - (sx0 + sx1) * xt - 2 * stages_a * at - 1024) / at);
   n_res = std::max(0, std::min(std::min(n_res, env_int("TACO2DEC_PBW_RES", 64)), 32 - n_tm));
-  out->npad = npad; out->stages_a = stages_a; out->stages_x = stages_x; out->n_res = n_res; out->n_tm = n_tm;
-  out->smem = pbw::smem_plan(npad, stages_a, stages_x, n_res, max_ts).total;
+  out->npad = npad; out->stages_a = stages_a; out->stages_x0 = sx0; out->stages_x1 = sx1; out->n_res = n_res; out->n_tm = n_tm;
+  out->smem = pbw::smem_plan(npad, stages_a, sx0 + sx1, n_res, max_ts).total;
   return out->smem <= budget;
 }
 
@@ -1808,12 +1810,12 @@ int pbw_run(taco2dec_handle* h, const Params& p, const bw::Grads& g, const PbwGe
     const size_t NP = 128;
     CUDA_TRY(cudaMalloc(&h->pbw.dx1, (size_t)2 * 2 * pbw::kSplits * bt::K1 * NP * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->pbw.dx2, (size_t)2 * pbw::kSplits * (2 * (bt::H + bt::E) + bt::H) * NP * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&h->pbw.flags, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&h->pbw.flags, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned) + 16 * sizeof(long long)));
     h->pbw_alloc = true;
   }
   pbw::PbwParams q = h->pbw;
   q.a1t = bb.a1t; q.a2t = bb.a2t; q.dg1t = bb.dg1; q.dg2t = bb.dg2; q.K2 = bb.K2;
-  q.stages_a = geo.stages_a; q.stages_x = geo.stages_x; q.n_res = geo.n_res; q.n_tm = geo.n_tm;
+  q.stages_a = geo.stages_a; q.stages_x0 = geo.stages_x0; q.stages_x1 = geo.stages_x1; q.n_res = geo.n_res; q.n_tm = geo.n_tm;
   CUDA_TRY(cudaMemsetAsync(q.flags, 0, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned), st));
   CUDA_TRY(cudaMemsetAsync(bb.dg1, 0, (size_t)S * (bw::G / 64) * NPAD * 128, st));      // utterance columns >= B of the operand tiles
   CUDA_TRY(cudaMemsetAsync(bb.dg2, 0, (size_t)(bw::G / 64) * NPAD * 128, st));
@@ -2257,6 +2259,15 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
     PbwGeometry geo;
     pbw_geometry(h, a->B, a->T_in, T_sub, &geo);
     p.abort_flag = h->abort_dev;
+    if (!h->pbw_alloc) {       // first call: pbw_run allocates; the phase clocks live behind the counters
+      const size_t NP = 128;
+      CUDA_TRY(cudaMalloc(&h->pbw.dx1, (size_t)2 * 2 * pbw::kSplits * bt::K1 * NP * sizeof(float)));
+      CUDA_TRY(cudaMalloc(&h->pbw.dx2, (size_t)2 * pbw::kSplits * (2 * (bt::H + bt::E) + bt::H) * NP * sizeof(float)));
+      CUDA_TRY(cudaMalloc(&h->pbw.flags, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned) + 16 * sizeof(long long)));
+      h->pbw_alloc = true;
+    }
+    p.phase_clocks = (long long*)(h->pbw.flags + (size_t)pbw::F_COUNT * pbw::kFlagStride);
+    h->last_phase_clocks = p.phase_clocks;
     switch (geo.npad) {
       case 16: return pbw_run<16>(h, p, g, geo, st);
       case 32: return pbw_run<32>(h, p, g, geo, st);

@@ -1,0 +1,28 @@
+"""Per-phase SM-clock shares of the persistent backward kernel (CTA 0).  usage: python tools/pbw_phases.py [B] [T]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from oracle.synth import SMA, make_decoder_weights, make_inputs
+from tacotron2_subword_b200 import Decoder, create_hparams
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+w = make_decoder_weights(SMA, seed=1234)
+dec = Decoder(create_hparams()); dec.load_state_dict(w); dec = dec.cuda().train()
+eng = dec._engine(torch.device("cuda", 0)); eng.set_profiling(True)
+inp = make_inputs(B, 160, 53, T, seed=3, ragged=True)
+mem, emb, mels = inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda()
+ml, bl = inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda()
+for _ in range(3):
+    dec.zero_grad(set_to_none=True)
+    outs = dec(mem, emb, mels, ml, bl)
+    loss = outs[0].square().mean() + outs[1].square().mean()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); loss.backward(); e1.record(); e1.synchronize()
+ms, kms, pc = e0.elapsed_time(e1), eng.last_kernel_ms(), eng.phase_clocks()
+names = ["pw2 (step 0) / loop top", "wait acc2", "epilogue 2 + signal", "wait X2 (all)", "pw2 (frame ahead) + signal", "wait X1 (stream)", "d prenet save",
+         "attention tasks", "wait dq (stream)", "pw1 (dq load, Wq^T dq, cells, stores) + signal", "wait acc1", "epilogue 1 + signal"]
+tot = sum(pc)
+print(f"B={B} T={T}: backward {ms:.2f} ms, persistent kernel {kms:.2f} ms = {1e3 * kms / T:.1f} us/frame; CTA 0: {tot / T / 1e3:.1f} kcyc/frame")
+for n, v in zip(names, pc):
+    print(f"  {n:50s} {v / T / 1e3:7.2f} kcyc/frame ({100 * v / max(tot, 1):5.1f}%)")
