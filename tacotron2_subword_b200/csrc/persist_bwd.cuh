@@ -45,8 +45,21 @@ struct PbwParams {
   float* dx2;                   // [2 parities][4][K2][NPAD]
   unsigned* flags;              // [F_COUNT][kFlagStride]
   int K2;
+  int att_chunk;                // positions per attention sub-task
   int stages_a, stages_x0, stages_x1, n_res, n_tm;      // ring depths: weight tiles (per product), activation tiles of product 0 / 1
 };
+
+// per-frame re-read operands of the attention tasks (memory, processed memory) must stay in L2 next to the 33 MB of streamed weight
+// tiles; everything that is touched once per call (saved activations, gradient rows) is read / written with streaming hints
+__device__ __forceinline__ float4 ld_keep_f4(const float* p, unsigned long long policy) {
+  const uint4 r = lat::ldg_stream(reinterpret_cast<const unsigned char*>(p), policy);
+  return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+}
+__device__ __forceinline__ float ld_keep_f(const float* p, unsigned long long policy) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+  return v;
+}
 
 struct Smem { size_t aring, xring, res, out, dq, wq, att, total; };
 __host__ __device__ inline size_t att_floats(int max_ts) {      // attention scratch; also holds u[16][NPAD + 1] (<= 16 * 129 floats)
@@ -347,6 +360,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
     float dc2_r[4] = {0.f, 0.f, 0.f, 0.f};     // carries: d cell state of the CTA's cells (fixed cell -> thread mapping)
     float dc1_r[4] = {0.f, 0.f, 0.f, 0.f};
     const size_t gs = (size_t)H * B;
+    const unsigned long long pol_keep = lat::l2_policy_evict_last();
+    const int parts0 = (p.st[0].Ts + q.att_chunk - 1) / q.att_chunk, parts1 = S == 2 ? (p.st[1].Ts + q.att_chunk - 1) / q.att_chunk : 0;
+    const int n_sub0 = B * parts0, n_sub = n_sub0 + B * parts1;
+    const int parts_sp = sp == 0 ? parts0 : parts1;
 
     // gate gradients staged in out_s[q][b][jl] -> bf16 operand tile chunk + fp32 rows (8 consecutive units per (gate, utterance))
     auto store_gates = [&](unsigned char* tiles, float* rows, int j0) {
@@ -361,8 +378,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         pk.z = *reinterpret_cast<unsigned*>(&h2); pk.w = *reinterpret_cast<unsigned*>(&h3);
         *reinterpret_cast<uint4*>(tiles + (size_t)(k >> 6) * ((size_t)NPAD * 128) + tc::tile_offset_bytes(NPAD, b, k & 63)) = pk;
         float4* dst = reinterpret_cast<float4*>(rows + (size_t)b * G + k);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        __stcs(dst, make_float4(v[0], v[1], v[2], v[3]));
+        __stcs(dst + 1, make_float4(v[4], v[5], v[6], v[7]));
       }
     };
 
@@ -468,60 +485,67 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
           float acc = 0.f;
 #pragma unroll
           for (int qq = 0; qq < kSplits; ++qq) acc += __ldcg(dx1_nxt + (size_t)sp * dx1_str + ((size_t)qq * K1 + k) * NPAD + b);
-          g.dpre[(((size_t)sp * T + (t + 1)) * B + b) * P + k] = acc;
+          __stcs(g.dpre + (((size_t)sp * T + (t + 1)) * B + b) * P + k, acc);
         }
       }
 
       PBW_PH(6)
-      // ---------------- attention backward: one (utterance, stream) task per CTA and round (attention.py:330-398) ----------------
-      for (int tau = c; tau < S * B; tau += kCtas) {
-        const int s = tau / B, b = tau - s * B;
+      // ---------------- attention backward (attention.py:330-398) ----------------
+      // A task (utterance, stream) is position-parallel except for one neighbour value, so it is cut into sub-tasks of `chunk`
+      // positions: the phoneme stream's long memories would otherwise make their CTAs the slowest of every frame.  Sub-task u ->
+      // (stream, utterance, part); its partial dq / dv sums are added into zero-initialised rows (at most a few addends).
+      for (int u = c; u < n_sub; u += kCtas) {
+        const int s = u < n_sub0 ? 0 : 1;
+        const int ul = s == 0 ? u : u - n_sub0;
+        const int b = ul % B, part = ul / B;
         const StreamParams& sa = p.st[s];
         const int Ts = sa.Ts;
         const int len = sa.len ? (int)sa.len[b] : Ts;
+        const int jlo = part * q.att_chunk, jhi = min(jlo + q.att_chunk, Ts);     // own positions [jlo, jhi)
+        const int jdn = min(jhi + 1, Ts);                                         // d alpha' is also needed at the right neighbour
         constexpr int kW = kCT / 32;
         float* dctx_s = att_s;              // E
-        float* q_s = dctx_s + E;            // A
-        float* v_s = q_s + A;               // A
-        float* dqa_s = v_s + A;             // A
+        float* dqa_s = dctx_s + E;          // A
         float* dva_s = dqa_s + A;           // A
-        float* p_s = dva_s + A;             // Ts+4
-        float* ap_s = p_s + Ts + 4;         // Ts+4
-        float* dan_s = ap_s + Ts + 4;       // Ts+4
-        float* de_s = dan_s + Ts + 4;       // Ts+4
         const float* mem_b = sa.mem + (size_t)b * Ts * E;
         const float* pm_b = sa.pm + (size_t)b * Ts * A;
         float* dpm_b = g.dpm[s] + (size_t)b * Ts * A;
-        // early requests (independent of the incoming gradients)
+        // Every warp owns a CONTIGUOUS block of R <= 31 positions [r0, r1) of the sub-task; lane i holds the per-position scalars of
+        // position r0 + i.  The only cross-position dependency -- d alpha'[j+1] -- stays inside the warp (a shuffle) except at the
+        // block's right edge, where the warp computes the neighbour's value itself (one more row).  No block barrier between the
+        // phases: the warps run them back to back on their own rows and hide each other's load latencies.
+        const int R = (jhi - jlo + kW - 1) / kW;
+        const int r0 = min(jlo + warp * R, jhi), r1 = min(r0 + R, jhi);
+        const int rd = min(r1 + 1, Ts);                         // rows whose d alpha' this warp needs (own + right neighbour)
+        const int jme = r0 + lane;                              // this lane's position
+        const bool own = jme < r1, need = jme < rd && r1 > r0;
+        float pj = 0.f, apj = 0.f, base = 0.f;
+        if (need) {
+          base = __ldcg(g.dalpha[s] + (size_t)b * Ts + jme);    // carry from frame t+1 (the neighbour's was written by another warp / CTA)
+          if (g.d_align[s]) base += g.d_align[s][((size_t)b * T + t) * Ts + jme];
+        }
+        if (own) {
+          pj = __ldcs(g.p_saved[s] + ((size_t)t * B + b) * Ts + jme);
+          apj = t > 0 ? __ldcs(g.align[s] + ((size_t)b * T + (t - 1)) * Ts + jme) : (jme == 0 ? 1.f : 0.f);
+        }
         float4 mrow[2][4];
-        float pmr[2][4], dpr[2][4];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const int j = warp + kW * r;
+          const int j = r0 + r;
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            mrow[r][qq] = j < Ts ? __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j * E) + lane + 32 * qq) : make_float4(0.f, 0.f, 0.f, 0.f);
-            pmr[r][qq] = j < len ? __ldg(pm_b + (size_t)j * A + lane + 32 * qq) : 0.f;
-            dpr[r][qq] = j < len ? dpm_b[(size_t)j * A + lane + 32 * qq] : 0.f;
-          }
+          for (int qq = 0; qq < 4; ++qq)
+            mrow[r][qq] = (j < rd && r1 > r0) ? ld_keep_f4(mem_b + (size_t)j * E + 4 * (lane + 32 * qq), pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int a = tid; a < A; a += kCT) {
-          q_s[a] = g.sv.q[(((size_t)t * S + s) * B + b) * A + a];
-          v_s[a] = sa.v[a];
-          dqa_s[a] = 0.f;
-          dva_s[a] = 0.f;
+        float qv[4], vv[4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          qv[qq] = g.sv.q[(((size_t)t * S + s) * B + b) * A + lane + 32 * qq];
+          vv[qq] = sa.v[lane + 32 * qq];
         }
-        for (int j = tid; j < Ts; j += kCT) {
-          p_s[j] = g.p_saved[s][((size_t)t * B + b) * Ts + j];
-          ap_s[j] = t > 0 ? g.align[s][((size_t)b * T + (t - 1)) * Ts + j] : (j == 0 ? 1.f : 0.f);
-          float d = g.dalpha[s][(size_t)b * Ts + j];
-          if (g.d_align[s]) d += g.d_align[s][((size_t)b * T + t) * Ts + j];
-          dan_s[j] = d;
-        }
+        for (int a = tid; a < 2 * A; a += kCT) dqa_s[a] = 0.f;          // dqa_s and dva_s are adjacent
         if (step > 0 && s != sp) PBW_WAIT_FLAG(flag(F_X1 + s), (unsigned)n_g1s * (unsigned)step)
-        pb::bar_compute();
         for (int d = tid; d < E; d += kCT) {
-          float acc = g.dyc[((size_t)t * B + b) * (S * E) + s * E + d];
+          float acc = __ldcs(g.dyc + ((size_t)t * B + b) * (S * E) + s * E + d);
           if (step > 0) {
 #pragma unroll
             for (int k = 0; k < kSplits; ++k) acc += __ldcg(dx1_nxt + (size_t)s * dx1_str + ((size_t)k * K1 + P + d) * NPAD + b);
@@ -529,85 +553,103 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
 #pragma unroll
           for (int k = 0; k < kSplits; ++k) acc += __ldcg(dx2_cur + ((size_t)k * K2 + s * (H + E) + H + d) * NPAD + b);
           dctx_s[d] = acc;
-          g.dctx[(((size_t)s * T + t) * B + b) * E + d] = acc;
+          if (part == 0) __stcs(g.dctx + (((size_t)s * T + t) * B + b) * E + d, acc);
         }
         pb::bar_compute();
-        {
+        // ---- d alpha'_j = carry_j + d ctx . memory_j   (attention.py:395): two rows in flight per warp ----
+        float dan = base;                                       // lane i: d alpha' of position r0 + i
+        if (r1 > r0) {
           const float4* dc4 = reinterpret_cast<const float4*>(dctx_s);
-          auto dot_row = [&](int j, const float4 (&m)[4]) {
+          float4 dcv[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) dcv[qq] = dc4[lane + 32 * qq];
+          auto dot_row = [&](const float4 (&m)[4]) {
             float acc = 0.f;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
-              const float4 dv = dc4[lane + 32 * qq];
-              acc = fmaf(m[qq].x, dv.x, acc); acc = fmaf(m[qq].y, dv.y, acc); acc = fmaf(m[qq].z, dv.z, acc); acc = fmaf(m[qq].w, dv.w, acc);
+              acc = fmaf(m[qq].x, dcv[qq].x, acc); acc = fmaf(m[qq].y, dcv[qq].y, acc);
+              acc = fmaf(m[qq].z, dcv[qq].z, acc); acc = fmaf(m[qq].w, dcv[qq].w, acc);
             }
-            acc = warp_sum(acc);
-            if (lane == 0) dan_s[j] += acc;
+            return warp_sum(acc);
           };
-          if (warp < Ts) dot_row(warp, mrow[0]);
-          if (warp + kW < Ts) dot_row(warp + kW, mrow[1]);
-          for (int j = warp + 2 * kW; j < Ts; j += 2 * kW) {
-            const int jb = j + kW;
+          for (int j = r0; j < rd; j += 2) {
+            const float d0 = dot_row(mrow[0]);
+            const float d1 = j + 1 < rd ? dot_row(mrow[1]) : 0.f;
+            // next pair of rows
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              mrow[0][qq] = __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)j * E) + lane + 32 * qq);
-              mrow[1][qq] = jb < Ts ? __ldg(reinterpret_cast<const float4*>(mem_b + (size_t)jb * E) + lane + 32 * qq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < 2; ++r) {
+              const int jn = j + 2 + r;
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq)
+                if (jn < rd) mrow[r][qq] = ld_keep_f4(mem_b + (size_t)jn * E + 4 * (lane + 32 * qq), pol_keep);
             }
-            dot_row(j, mrow[0]);
-            if (jb < Ts) dot_row(jb, mrow[1]);
+            if (lane == j - r0) dan += d0;
+            if (lane == j + 1 - r0) dan += d1;
           }
         }
-        pb::bar_compute();
-        if (p.independent) {
-          for (int j = len + tid; j < Ts; j += kCT) dan_s[j] = 0.f;
-          pb::bar_compute();
+        if (p.independent && jme >= len) dan = 0.f;             // alpha'_j was forced to 0 beyond the utterance's length
+        // ---- alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1}),  p = sigmoid(e)   (attention.py:330-345) ----
+        const float dn1 = __shfl_down_sync(0xffffffffu, dan, 1);          // lane i + 1 holds position j + 1 (zero beyond the last one)
+        float de = 0.f;
+        if (own) {
+          const float dnn = jme + 1 < Ts ? dn1 : 0.f;
+          g.dalpha[s][(size_t)b * Ts + jme] = dan * pj + dnn * (1.0f - pj);
+          de = apj * (dan - dnn) * pj * (1.0f - pj);
         }
-        for (int j = tid; j < Ts; j += kCT) {
-          const float dn = dan_s[j], dn1 = j + 1 < Ts ? dan_s[j + 1] : 0.f, pj = p_s[j];
-          g.dalpha[s][(size_t)b * Ts + j] = dn * pj + dn1 * (1.0f - pj);
-          de_s[j] = ap_s[j] * (dn - dn1) * pj * (1.0f - pj);
-        }
-        pb::bar_compute();
+        // ---- e_j = v . tanh(q + pm_j): dq, dv, d processed_memory; rows of the block that exist, two in flight ----
         {
           float dq_acc[4] = {0.f, 0.f, 0.f, 0.f}, dv_acc[4] = {0.f, 0.f, 0.f, 0.f};
-          float qv[4], vv[4];
+          const int re = min(r1, len);
+          float pmr[2][4], dpr[2][4];
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) { qv[qq] = q_s[lane + 32 * qq]; vv[qq] = v_s[lane + 32 * qq]; }
-          auto energy_bw = [&](int j, const float (&pm)[4], const float (&dp)[4]) {
-            const float de = de_s[j];
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              const float u = lat::fast_tanh(qv[qq] + pm[qq]);
-              const float dz = de * vv[qq] * (1.0f - u * u);
-              dq_acc[qq] += dz;
-              dv_acc[qq] = fmaf(de, u, dv_acc[qq]);
-              dpm_b[(size_t)j * A + lane + 32 * qq] = dp[qq] + dz;
-            }
-          };
-          if (warp < len) energy_bw(warp, pmr[0], dpr[0]);
-          if (warp + kW < len) energy_bw(warp + kW, pmr[1], dpr[1]);
-          for (int j = warp + 2 * kW; j < len; j += 2 * kW) {
-            const int jb = j + kW;
+          for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
-              pmr[0][qq] = __ldg(pm_b + (size_t)j * A + lane + 32 * qq);
-              dpr[0][qq] = dpm_b[(size_t)j * A + lane + 32 * qq];
-              pmr[1][qq] = jb < len ? __ldg(pm_b + (size_t)jb * A + lane + 32 * qq) : 0.f;
-              dpr[1][qq] = jb < len ? dpm_b[(size_t)jb * A + lane + 32 * qq] : 0.f;
+              const int j = r0 + r;
+              pmr[r][qq] = j < re ? ld_keep_f(pm_b + (size_t)j * A + lane + 32 * qq, pol_keep) : 0.f;
+              dpr[r][qq] = j < re ? dpm_b[(size_t)j * A + lane + 32 * qq] : 0.f;
             }
-            energy_bw(j, pmr[0], dpr[0]);
-            if (jb < len) energy_bw(jb, pmr[1], dpr[1]);
+          for (int j = r0; j < re; j += 2) {
+            float pmc[2][4], dpc[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) { pmc[r][qq] = pmr[r][qq]; dpc[r][qq] = dpr[r][qq]; }
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) {
+                const int jn = j + 2 + r;
+                if (jn < re) { pmr[r][qq] = ld_keep_f(pm_b + (size_t)jn * A + lane + 32 * qq, pol_keep); dpr[r][qq] = dpm_b[(size_t)jn * A + lane + 32 * qq]; }
+              }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int jj = j + r;
+              const float dej = __shfl_sync(0xffffffffu, de, (jj - r0) & 31);
+              if (jj < re) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                  const float uu = lat::fast_tanh(qv[qq] + pmc[r][qq]);
+                  const float dz = dej * vv[qq] * (1.0f - uu * uu);
+                  dq_acc[qq] += dz;
+                  dv_acc[qq] = fmaf(dej, uu, dv_acc[qq]);
+                  dpm_b[(size_t)jj * A + lane + 32 * qq] = dpc[r][qq] + dz;
+                }
+              }
+            }
           }
+          if (re > r0) {
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            atomicAdd(&dqa_s[lane + 32 * qq], dq_acc[qq]);
-            atomicAdd(&dva_s[lane + 32 * qq], dv_acc[qq]);
+            for (int qq = 0; qq < 4; ++qq) {
+              atomicAdd(&dqa_s[lane + 32 * qq], dq_acc[qq]);
+              atomicAdd(&dva_s[lane + 32 * qq], dv_acc[qq]);
+            }
           }
         }
         pb::bar_compute();
         for (int a = tid; a < A; a += kCT) {
-          g.dq[(((size_t)s * T + t) * B + b) * A + a] = dqa_s[a];
-          g.dv[((size_t)s * B + b) * A + a] += dva_s[a];
+          atomicAdd(g.dq + (((size_t)s * T + t) * B + b) * A + a, dqa_s[a]);
+          atomicAdd(g.dv + ((size_t)s * B + b) * A + a, dva_s[a]);
         }
         pb::bar_compute();
         if (tid == 0) pb::signal(flag(F_DQ + s));
@@ -634,8 +676,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
 #pragma unroll
         for (int k = 0; k < kSplits; ++k) dh += __ldcg(dx2_cur + ((size_t)k * K2 + sp * (H + E) + j) * NPAD + b);
         const float* sv = g.sv.gates1 + (((size_t)t * S + sp) * 5 * H + j) * B + b;
-        const float gi = sv[0], gf = sv[gs], gg = sv[2 * gs], go = sv[3 * gs], cn = sv[4 * gs];
-        const float cn_prev = t > 0 ? (sv - (size_t)S * 5 * gs)[4 * gs] : 0.f;
+        const float gi = __ldcs(sv), gf = __ldcs(sv + gs), gg = __ldcs(sv + 2 * gs), go = __ldcs(sv + 3 * gs), cn = __ldcs(sv + 4 * gs);
+        const float cn_prev = t > 0 ? __ldcs(sv - (size_t)S * 5 * gs + 4 * gs) : 0.f;
         float mh = 1.f, mc = 1.f, mc_prev = 1.f;
         if (p.training) {
           const uint8_t* kh = p.lstm_keep ? p.lstm_keep + ((size_t)t * 6 + 2 * sp) * B * H : nullptr;
@@ -656,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         c_b2[ci] = gi * (1.0f - gg * gg);
         c_b3[ci] = mh * tcn * go * (1.0f - go);
       }
-      PBW_WAIT_FLAG(flag(F_DQ + sp), (unsigned)B * (unsigned)(step + 1))
+      PBW_WAIT_FLAG(flag(F_DQ + sp), (unsigned)(B * parts_sp) * (unsigned)(step + 1))
       PBW_PH(8)
       for (int i = tid; i < A * B; i += kCT) {
         const int b = i / A, a = i - b * A;

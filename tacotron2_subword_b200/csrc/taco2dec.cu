@@ -1815,6 +1815,14 @@ int pbw_run(taco2dec_handle* h, const Params& p, const bw::Grads& g, const PbwGe
   }
   pbw::PbwParams q = h->pbw;
   q.a1t = bb.a1t; q.a2t = bb.a2t; q.dg1t = bb.dg1; q.dg2t = bb.dg2; q.K2 = bb.K2;
+  {   // attention sub-tasks: whole tasks by default.  Cutting the long memories into position chunks (TACO2DEC_PBW_CHUNK=<positions>)
+      // balances the streams but was slower when measured (53 vs 45 us/frame): a task is a chain of dependent load phases, not a
+      // byte stream, and every sub-task pays the chain again.
+    int max_ts = 0;
+    for (int s = 0; s < S; ++s) max_ts = std::max(max_ts, p.st[s].Ts);
+    q.att_chunk = std::min(480, std::max(16, env_int("TACO2DEC_PBW_CHUNK", max_ts)));     // a warp owns <= 30 consecutive positions
+  }
+  CUDA_TRY(cudaMemsetAsync(g.dq, 0, (size_t)S * p.T * B * bt::A * sizeof(float), st));     // sub-tasks add their partial dq rows
   q.stages_a = geo.stages_a; q.stages_x0 = geo.stages_x0; q.stages_x1 = geo.stages_x1; q.n_res = geo.n_res; q.n_tm = geo.n_tm;
   CUDA_TRY(cudaMemsetAsync(q.flags, 0, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned), st));
   CUDA_TRY(cudaMemsetAsync(bb.dg1, 0, (size_t)S * (bw::G / 64) * NPAD * 128, st));      // utterance columns >= B of the operand tiles
