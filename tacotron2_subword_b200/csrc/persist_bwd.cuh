@@ -556,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
           if (part == 0) __stcs(g.dctx + (((size_t)s * T + t) * B + b) * E + d, acc);
         }
         pb::bar_compute();
+        PBW_PH(12)
         // ---- d alpha'_j = carry_j + d ctx . memory_j   (attention.py:395): two rows in flight per warp ----
         float dan = base;                                       // lane i: d alpha' of position r0 + i
         if (r1 > r0) {
@@ -587,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
             if (lane == j + 1 - r0) dan += d1;
           }
         }
+        PBW_PH(13)
         if (p.independent && jme >= len) dan = 0.f;             // alpha'_j was forced to 0 beyond the utterance's length
         // ---- alpha'_j = alpha_j p_j + alpha_{j-1} (1 - p_{j-1}),  p = sigmoid(e)   (attention.py:330-345) ----
         const float dn1 = __shfl_down_sync(0xffffffffu, dan, 1);          // lane i + 1 holds position j + 1 (zero beyond the last one)
@@ -638,6 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
               }
             }
           }
+          PBW_PH(14)
           if (re > r0) {
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
@@ -653,6 +656,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         }
         pb::bar_compute();
         if (tid == 0) pb::signal(flag(F_DQ + s));
+        PBW_PH(15)
       }
 
       PBW_PH(7)

@@ -290,3 +290,41 @@ def test_backward_vs_reference_gradient_digests(name):
         else:
             worst[n] = check_grad_digest(n, grads[n], want, rtol=TOL_GRAD)
     print({k: f"{v:.1e}" for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("B,T,T_in,T_sub", [(16, 12, 40, 13), (33, 5, 150, 50), (64, 3, 24, 8), (2, 9, 17, 5)])
+def test_persistent_backward_equals_per_frame_graph(B, T, T_in, T_sub, monkeypatch):
+    """The persistent BPTT kernel (csrc/persist_bwd.cuh: one launch for the whole reverse-time loop, SMA, B <= 64) and the per-frame
+    graph of csrc/backward.cuh compute the same arithmetic on the same operands: every gradient must agree to fp32 summation
+    order (the two differ only in the order of split-K and atomic additions)."""
+    seed = 900 + B
+    w = make_decoder_weights(SMA, seed=seed)
+    inp = make_inputs(B, T_in, T_sub, T, seed=seed, ragged=True)
+    plan = make_dropout_plan(B, T + 1, T, T_in, T_sub, True, seed=seed + 1)
+    grads, counts = [], []
+    for no_persist in (False, True):
+        if no_persist:
+            monkeypatch.setenv("TACO2DEC_NO_PERSIST_BWD", "1")
+        else:
+            monkeypatch.delenv("TACO2DEC_NO_PERSIST_BWD", raising=False)
+        dec = make_decoder(w, SMA, exact=False).train()
+        dec.dropout_replay = replay_of(plan)
+        mem = inp["memory"].cuda().requires_grad_(True)
+        emb = inp["embeddings"].cuda().requires_grad_(True)
+        eng = dec._engine(torch.device("cuda", 0))
+        n0 = eng.launch_count()
+        outs = dec(mem, emb, inp["mels"].cuda(), inp["memory_lengths"].cuda(), inp["bert_lengths"].cuda())
+        n1 = eng.launch_count()
+        _loss(outs, 5).backward()
+        torch.cuda.synchronize()
+        dec.check()
+        counts.append(eng.launch_count() - n1)
+        g = {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None}
+        g["memory"], g["embeddings"] = mem.grad.clone(), emb.grad.clone()
+        grads.append(g)
+    # the per-frame graph replays 5 kernels per frame (+ 3 around the loop); the persistent path is the projection gradient + ONE launch
+    assert counts[1] - counts[0] == 5 * T + 1, counts
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) == 28
+    for n in grads[0]:
+        scale = float(grads[1][n].abs().max())
+        assert float((grads[0][n] - grads[1][n]).abs().max()) <= 2e-3 * scale, n

@@ -21,8 +21,11 @@ for _ in range(3):
     e0.record(); loss.backward(); e1.record(); e1.synchronize()
 ms, kms, pc = e0.elapsed_time(e1), eng.last_kernel_ms(), eng.phase_clocks()
 names = ["pw2 (step 0) / loop top", "wait acc2", "epilogue 2 + signal", "wait X2 (all)", "pw2 (frame ahead) + signal", "wait X1 (stream)", "d prenet save",
-         "attention tasks", "wait dq (stream)", "pw1 (dq load, Wq^T dq, cells, stores) + signal", "wait acc1", "epilogue 1 + signal"]
+         "attention tasks", "wait dq (stream)", "pw1 (dq load, Wq^T dq, cells, stores) + signal", "wait acc1", "epilogue 1 + signal",
+         "  attention: early loads, waits, d ctx", "  attention: d alpha' (memory rows)", "  attention: recurrence + energies (pm, dpm rows)",
+         "  attention: reduce, dq / dv, signal"]
 tot = sum(pc)
 print(f"B={B} T={T}: backward {ms:.2f} ms, persistent kernel {kms:.2f} ms = {1e3 * kms / T:.1f} us/frame; CTA 0: {tot / T / 1e3:.1f} kcyc/frame")
 for n, v in zip(names, pc):
     print(f"  {n:50s} {v / T / 1e3:7.2f} kcyc/frame ({100 * v / max(tot, 1):5.1f}%)")
+print("(the four attention rows are parts of what the 'attention tasks' row reported before they were split out: that row now holds only the loop overhead)")
