@@ -43,6 +43,8 @@ struct PbwParams {
   unsigned char* dg2t;          // [64 kb][NPAD x 64]
   float* dx1;                   // [2 parities][S][4][K1][NPAD]
   float* dx2;                   // [2 parities][4][K2][NPAD]
+  float* dxc1;                  // [2 parities][S][4][NPAD][E]   context rows of dX1, utterance-major (read by the attention tasks)
+  float* dxc2;                  // [2 parities][4][S][NPAD][E]   context rows of dX2
   unsigned* flags;              // [F_COUNT][kFlagStride]
   int K2;
   int att_chunk;                // positions per attention sub-task
@@ -422,6 +424,28 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
       }
     };
 
+    // accumulator (128 rows x NPAD utterances, lane = row) -> split-K partials.  Hidden / prenet rows are consumed with lanes along
+    // the utterances: row-major [row][NPAD].  Context rows are consumed by the attention tasks (one utterance, all rows): they go
+    // out utterance-major [utterance][E] -- for the writer that is the coalesced direction anyway (32 lanes = 32 consecutive rows).
+    auto store_acc = [&](uint32_t acc, float* part_mine, float* ctx_mine) {
+      for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
+        uint32_t v[16];
+        const uint32_t taddr = acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
+        lat::tmem_ld16(taddr, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ctx_mine) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ctx_mine[(size_t)(cg * 16 + i) * E + row_ep] = __uint_as_float(v[i]);
+        } else {
+          float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
+                                  __uint_as_float(v[4 * k4 + 3]));
+        }
+      }
+    };
+
     // epilogue of the e-th decoder-LSTM product (frame T-1-e): TMEM -> split-K partials of dX2, then the counter
     auto epilogue2 = [&](int e) -> bool {
       if (!has_g2) return true;
@@ -432,17 +456,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
       if (!ok_) return false;
       tc::tc_fence_after();
       const int tt = T - 1 - e;
-      float* part_mine = q.dx2 + (size_t)(tt & 1) * dx2_par + ((size_t)sig2 * K2 + (size_t)m2 * 128) * NPAD;
-      for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
-        uint32_t v[16];
-        const uint32_t taddr = acc_addr[1] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
-        lat::tmem_ld16(taddr, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
-                                __uint_as_float(v[4 * k4 + 3]));
+      {
+        const int row0 = m2 * 128, blk = row0 / (H + E), off = row0 - blk * (H + E);
+        const bool ctx_tile = row0 < S * (H + E) && off >= H;
+        float* part_mine = q.dx2 + (size_t)(tt & 1) * dx2_par + ((size_t)sig2 * K2 + (size_t)row0) * NPAD;
+        float* ctx_mine = q.dxc2 + ((((size_t)(tt & 1) * kSplits + sig2) * S + blk) * NPAD) * E + (off - H);
+        store_acc(acc_addr[1], part_mine, ctx_tile ? ctx_mine : nullptr);
       }
       tc::tc_fence_before();
       pb::bar_compute();
@@ -548,10 +567,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
           float acc = __ldcs(g.dyc + ((size_t)t * B + b) * (S * E) + s * E + d);
           if (step > 0) {
 #pragma unroll
-            for (int k = 0; k < kSplits; ++k) acc += __ldcg(dx1_nxt + (size_t)s * dx1_str + ((size_t)k * K1 + P + d) * NPAD + b);
+            for (int k = 0; k < kSplits; ++k) acc += __ldcg(q.dxc1 + ((((size_t)((t + 1) & 1) * S + s) * kSplits + k) * NPAD + b) * E + d);
           }
 #pragma unroll
-          for (int k = 0; k < kSplits; ++k) acc += __ldcg(dx2_cur + ((size_t)k * K2 + s * (H + E) + H + d) * NPAD + b);
+          for (int k = 0; k < kSplits; ++k) acc += __ldcg(q.dxc2 + ((((size_t)(t & 1) * kSplits + k) * S + s) * NPAD + b) * E + d);
           dctx_s[d] = acc;
           if (part == 0) __stcs(g.dctx + (((size_t)s * T + t) * B + b) * E + d, acc);
         }
@@ -762,17 +781,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         PBW_WAIT_MBAR(&acc_full[0], (uint32_t)(step & 1))
         PBW_PH(10)
         tc::tc_fence_after();
-        float* part_mine = dx1_cur + (size_t)s1 * dx1_str + ((size_t)sig1 * K1 + (size_t)m1 * 128) * NPAD;
-        for (int cg = warp >> 2; cg < NPAD / 16; cg += 4) {
-          uint32_t v[16];
-          const uint32_t taddr = acc_addr[0] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cg * 16);
-          lat::tmem_ld16(taddr, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float4* dst = reinterpret_cast<float4*>(part_mine + (size_t)row_ep * NPAD + cg * 16);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
-                                  __uint_as_float(v[4 * k4 + 3]));
+        {
+          const int row0 = m1 * 128;
+          const bool ctx_tile = row0 >= P && row0 < P + E;
+          float* part_mine = dx1_cur + (size_t)s1 * dx1_str + ((size_t)sig1 * K1 + (size_t)row0) * NPAD;
+          float* ctx_mine = q.dxc1 + ((((size_t)(t & 1) * S + s1) * kSplits + sig1) * NPAD) * E + (row0 - P);
+          store_acc(acc_addr[0], part_mine, ctx_tile ? ctx_mine : nullptr);
         }
         tc::tc_fence_before();
         pb::bar_compute();

@@ -1811,6 +1811,8 @@ int pbw_run(taco2dec_handle* h, const Params& p, const bw::Grads& g, const PbwGe
     CUDA_TRY(cudaMalloc(&h->pbw.dx1, (size_t)2 * 2 * pbw::kSplits * bt::K1 * NP * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->pbw.dx2, (size_t)2 * pbw::kSplits * (2 * (bt::H + bt::E) + bt::H) * NP * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->pbw.flags, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned) + 16 * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&h->pbw.dxc1, (size_t)2 * 2 * pbw::kSplits * NP * bt::E * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->pbw.dxc2, (size_t)2 * pbw::kSplits * 2 * NP * bt::E * sizeof(float)));
     h->pbw_alloc = true;
   }
   pbw::PbwParams q = h->pbw;
@@ -2032,7 +2034,7 @@ int taco2dec_destroy(taco2dec_handle* h) {
       for (void* q : ptrs) if (q) cudaFree(q);
     }
     if (h->pbw_alloc) {
-      void* ptrs[] = {h->pbw.dx1, h->pbw.dx2, h->pbw.flags};
+      void* ptrs[] = {h->pbw.dx1, h->pbw.dx2, h->pbw.flags, h->pbw.dxc1, h->pbw.dxc2};
       for (void* q : ptrs) if (q) cudaFree(q);
     }
   }
@@ -2272,6 +2274,8 @@ int taco2dec_backward(taco2dec_handle* h, const taco2dec_bwd_args* a, void* cuda
       CUDA_TRY(cudaMalloc(&h->pbw.dx1, (size_t)2 * 2 * pbw::kSplits * bt::K1 * NP * sizeof(float)));
       CUDA_TRY(cudaMalloc(&h->pbw.dx2, (size_t)2 * pbw::kSplits * (2 * (bt::H + bt::E) + bt::H) * NP * sizeof(float)));
       CUDA_TRY(cudaMalloc(&h->pbw.flags, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned) + 16 * sizeof(long long)));
+      CUDA_TRY(cudaMalloc(&h->pbw.dxc1, (size_t)2 * 2 * pbw::kSplits * NP * bt::E * sizeof(float)));
+      CUDA_TRY(cudaMalloc(&h->pbw.dxc2, (size_t)2 * pbw::kSplits * 2 * NP * bt::E * sizeof(float)));
       h->pbw_alloc = true;
     }
     p.phase_clocks = (long long*)(h->pbw.flags + (size_t)pbw::F_COUNT * pbw::kFlagStride);
