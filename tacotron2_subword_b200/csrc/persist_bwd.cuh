@@ -48,6 +48,7 @@ struct PbwParams {
   unsigned* flags;              // [F_COUNT][kFlagStride]
   int K2;
   int att_chunk;                // positions per attention sub-task
+  int w2_stream;                // 1: the decoder-LSTM product's streamed weight tiles are read with evict_first (it has a frame of slack)
   int stages_a, stages_x0, stages_x1, n_res, n_tm;      // ring depths: weight tiles (per product), activation tiles of product 0 / 1
 };
 
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
             const unsigned round = ga / (unsigned)NSA;
             if (s_afill[gg][slot] == round && (round == 0u || pb::mbar_test(&empty_a[gg][slot], (round & 1u) ^ 1u))) {
               tc::mbar_expect_tx(&full_a[gg][slot], (unsigned)tc::kATileBytes);
-              pb::tma_load_1d_hint(my_aring + (size_t)slot * tc::kATileBytes, a_src, tc::kATileBytes, &full_a[gg][slot], pol_keep);
+              pb::tma_load_1d_hint(my_aring + (size_t)slot * tc::kATileBytes, a_src, tc::kATileBytes, &full_a[gg][slot],
+                                   (gg == 1 && q.w2_stream) ? pol_once : pol_keep);
               s_afill[gg][slot] = round + 1u;
               need_a = false;
             }

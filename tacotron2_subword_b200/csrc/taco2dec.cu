@@ -1825,6 +1825,7 @@ int pbw_run(taco2dec_handle* h, const Params& p, const bw::Grads& g, const PbwGe
     for (int s = 0; s < S; ++s) max_ts = std::max(max_ts, p.st[s].Ts);
     q.att_chunk = std::min(480, std::max(16, env_int("TACO2DEC_PBW_CHUNK", max_ts)));     // a warp owns <= 30 consecutive positions
   }
+  q.w2_stream = env_int("TACO2DEC_PBW_W2_STREAM", 1);     // measured: 40.5 -> 39.1 us/frame (the working set no longer fits in L2 otherwise)
   CUDA_TRY(cudaMemsetAsync(g.dq, 0, (size_t)S * p.T * B * bt::A * sizeof(float), st));     // sub-tasks add their partial dq rows
   q.stages_a = geo.stages_a; q.stages_x0 = geo.stages_x0; q.stages_x1 = geo.stages_x1; q.n_res = geo.n_res; q.n_tm = geo.n_tm;
   CUDA_TRY(cudaMemsetAsync(q.flags, 0, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned), st));

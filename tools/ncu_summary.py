@@ -5,7 +5,7 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_bytes.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_lsu.sum", "launch__registers_per_thread",
