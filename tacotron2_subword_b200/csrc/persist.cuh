@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             if (q.sv.gates1) {
               float* sv = q.sv.gates1 + (((size_t)t * S + s1) * 5 * H + j) * B + b;
               const size_t gs = (size_t)H * B;
-              sv[0] = gi; sv[gs] = gf; sv[2 * gs] = gg; sv[3 * gs] = go; sv[4 * gs] = cn;
+              __stcs(sv, gi); __stcs(sv + gs, gf); __stcs(sv + 2 * gs, gg); __stcs(sv + 3 * gs, go); __stcs(sv + 4 * gs, cn);   // written once, read by backward: keep them out of L2
             }
             if (p.training) {
               const size_t idx = (size_t)b * H + j;
@@ -758,8 +758,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           *reinterpret_cast<uint4*>(x_chunk_ptr(x2_cur, NPAD, b, s1 * (H + E) + j)) = pk;
           if (q.sv.h1) {
             float* d = q.sv.h1 + (((size_t)(t + 1) * S + s1) * B + b) * H + j;
-            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            __stcs(reinterpret_cast<float4*>(d), make_float4(v[0], v[1], v[2], v[3]));
+            __stcs(reinterpret_cast<float4*>(d + 4), make_float4(v[4], v[5], v[6], v[7]));
           }
         }
         PB_DBG_C(4)
@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           float qv = 0.f;
 #pragma unroll
           for (int m = 0; m < 32; ++m) qv += qa[m];
-          if (q.sv.q) q.sv.q[(((size_t)t * S + s) * B + b) * A + tid] = qv;
+          if (q.sv.q) __stcs(q.sv.q + (((size_t)t * S + s) * B + b) * A + tid, qv);
           q_s[tid] = qv;
         }
         bar_compute();
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           }
           const float pj = sigmoidf_(e);
           e_s[j] = pj;
-          if (sa.p_save) sa.p_save[((size_t)t * B + b) * Ts + j] = pj;
+          if (sa.p_save) __stcs(sa.p_save + ((size_t)t * B + b) * Ts + j, pj);
         }
         bar_compute();
         {
@@ -934,8 +934,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           *reinterpret_cast<float4*>(cdst + 4) = make_float4(v[4], v[5], v[6], v[7]);
           if (q.sv.ctx) {
             float* d = q.sv.ctx + (((size_t)(t + 1) * S + s) * B + b) * E + d0;
-            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            __stcs(reinterpret_cast<float4*>(d), make_float4(v[0], v[1], v[2], v[3]));
+            __stcs(reinterpret_cast<float4*>(d + 4), make_float4(v[4], v[5], v[6], v[7]));
           }
           const uint4 pk = pn::pack8(v);
           *reinterpret_cast<uint4*>(x_chunk_ptr(x1_next + (size_t)s * x1_stream, NPAD, b, P + d0)) = pk;
@@ -1046,7 +1046,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             if (q.sv.gates2) {
               float* sv = q.sv.gates2 + ((size_t)t * 5 * H + j) * B + b;
               const size_t gs = (size_t)H * B;
-              sv[0] = gi; sv[gs] = gf; sv[2 * gs] = gg; sv[3 * gs] = go; sv[4 * gs] = cn;
+              __stcs(sv, gi); __stcs(sv + gs, gf); __stcs(sv + 2 * gs, gg); __stcs(sv + 3 * gs, go); __stcs(sv + 4 * gs, cn);   // written once, read by backward: keep them out of L2
             }
             if (p.training) {
               const size_t idx = (size_t)b * H + j;
@@ -1069,8 +1069,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           *reinterpret_cast<uint4*>(x_chunk_ptr(x2_next, NPAD, b, S * (H + E) + j)) = pn::pack8(v);
           if (q.sv.h2) {
             float* d = q.sv.h2 + ((size_t)(t + 1) * B + b) * H + j;
-            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            __stcs(reinterpret_cast<float4*>(d), make_float4(v[0], v[1], v[2], v[3]));
+            __stcs(reinterpret_cast<float4*>(d + 4), make_float4(v[4], v[5], v[6], v[7]));
           }
         }
         if (fr) {   // projection partial over the CTA's 32 h2 units (model.py:382-388)
