@@ -48,8 +48,10 @@ struct PbwParams {
   unsigned* flags;              // [F_COUNT][kFlagStride]
   int K2;
   int att_chunk;                // positions per attention sub-task
+  long long* dbg;               // optional [64] SM-clock stamps of CTA 0 during step dbg_step (product 0): see tools/pbw_phases.py
+  int dbg_step;
   int w2_stream;                // 1: the decoder-LSTM product's streamed weight tiles are read with evict_first (it has a frame of slack)
-  int stages_a, stages_x0, stages_x1, n_res, n_tm;      // ring depths: weight tiles (per product), activation tiles of product 0 / 1
+  int stages_a0, stages_a1, stages_x0, stages_x1, n_res, n_tm;   // ring depths per product: streamed weight tiles, activation tiles
 };
 
 // per-frame re-read operands of the attention tasks (memory, processed memory) must stay in L2 next to the 33 MB of streamed weight
@@ -73,7 +75,7 @@ __host__ __device__ inline Smem smem_plan(int NPAD, int stages_a, int stages_x, 
   Smem s;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~(size_t)127; return o; };
-  s.aring = take((size_t)2 * stages_a * tc::kATileBytes);
+  s.aring = take((size_t)stages_a * tc::kATileBytes);           // stages_a = slots of both products together
   s.xring = take((size_t)stages_x * (size_t)NPAD * 128);        // stages_x = slots of both products together
   s.res = take((size_t)n_res * tc::kATileBytes);
   s.out = take((size_t)4 * NPAD * 9 * 4);             // staging of 8 units x 4 gates x NPAD utterances
@@ -92,8 +94,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
   __shared__ int s_loc[32];
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int s_exit;
-  __shared__ volatile unsigned s_xfill[2][8], s_afill[2][8];
   __shared__ volatile int s_ok[2];
+  __shared__ volatile unsigned s_xfill0[8];            // rounds filled so far per activation-ring slot of product 0 (lane-per-tile producer)
   __shared__ long long s_ph[16];
 
   constexpr int kXTileBytes = NPAD * 128;
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
   const int m2 = c / kSplits, sig2 = c % kSplits;
   const int s1 = c / n_g1s, m1 = (c % n_g1s) / kSplits, sig1 = c % kSplits;
   const int n_tiles = (has_g1 ? kKb : 0) + (has_g2 ? kKb : 0);   // program: attention-LSTM tiles first, then decoder-LSTM tiles
-  const int NSA = q.stages_a;
+  const int NSAg[2] = {q.stages_a0, q.stages_a1};        // weight ring depth per product (0: every tile of the product is resident)
   const int NSXg[2] = {q.stages_x0, q.stages_x1};        // activation ring depth per product
   unsigned* const F = q.flags;
   auto flag = [&](int id) { return F + (size_t)id * kFlagStride; };
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
 
   int max_ts = 0;
   for (int s = 0; s < S; ++s) max_ts = max(max_ts, p.st[s].Ts);
-  const Smem spl = smem_plan(NPAD, NSA, NSXg[0] + NSXg[1], q.n_res, max_ts);
+  const Smem spl = smem_plan(NPAD, NSAg[0] + NSAg[1], NSXg[0] + NSXg[1], q.n_res, max_ts);
   unsigned char* aring = smem + spl.aring;
   unsigned char* xring = smem + spl.xring;
   unsigned char* res_s = smem + spl.res;
@@ -136,13 +138,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
     for (int gg = 0; gg < 2; ++gg)
       for (int i = 0; i < 8; ++i) {
         tc::mbar_init(&full_a[gg][i], 1); tc::mbar_init(&empty_a[gg][i], 1); tc::mbar_init(&full_x[gg][i], 1); tc::mbar_init(&empty_x[gg][i], 1);
-        s_xfill[gg][i] = 0; s_afill[gg][i] = 0;
       }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 1); }
     tc::mbar_init(&res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_exit = 0; s_ok[0] = 1; s_ok[1] = 1;
     for (int i = 0; i < 16; ++i) s_ph[i] = 0;
+    for (int i = 0; i < 8; ++i) s_xfill0[i] = 0;
     // placement: the attention-LSTM product sits on the critical chain -> its tiles go on-chip first
     int tm = 0, sm = 0;
     for (int i = 0; i < 32; ++i) s_loc[i] = LOC_STREAM;
@@ -199,10 +201,58 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
   __syncthreads();
   tc::tc_fence_after();
 
+  // =========================== TMA producers ===========================
+  // All 16 activation tiles of a product depend on ONE event (the gate gradients of the frame), so each product has one thread
+  // that waits for that counter and then feeds the ring in program order, and one thread that keeps the ring of streamed weight
+  // tiles full.  (A lane per tile, as in the forward kernel, made every ring-slot check of the attention-LSTM product wait for
+  // its sibling lanes' global-memory polls: ~1 kcyc per k-block.)  Threads that poll global memory never share a warp with a
+  // thread whose loop is latency-critical at the same time: warp 16 = X producer of product 0; warp 17 = MMA issuer of product 0 +
+  // the weight producers of both products (shared-memory barriers only); warp 18 = MMA issuer of product 1 + its X producer
+  // (the issuer is idle until those tiles arrive).
+  auto x_producer = [&](int gg) {
+    const int NSX = NSXg[gg];
+    unsigned char* const my_xring = xring + (size_t)gg * NSXg[0] * kXTileBytes;
+    const unsigned char* const x_src = gg == 0 ? q.dg1t + ((size_t)s1 * (G / 64) + sig1 * kKb) * kXTileBytes
+                                               : q.dg2t + ((size_t)sig2 * kKb) * kXTileBytes;
+    const unsigned* fptr = gg == 0 ? flag(F_DG1 + s1) : flag(F_DG2);
+    const unsigned mul = gg == 0 ? (unsigned)per : (unsigned)(S == 2 ? per : kCtas);
+    unsigned gx = 0;
+    for (int step = 0; step < T; ++step) {
+      if (!pb::poll_ge(fptr, mul * (unsigned)(step + 1), ctl)) return;
+      const bool dbg_on = q.dbg && c == 0 && gg == 0 && step == q.dbg_step;
+      if (dbg_on) q.dbg[1] = clock64();        // counter seen
+      pb::fence_proxy_async();                 // the tiles were written through the generic proxy by other SMs
+      for (int i = 0; i < kKb; ++i, ++gx) {
+        const int slot = (int)(gx % (unsigned)NSX);
+        const unsigned round = gx / (unsigned)NSX;
+        if (round > 0u && !pb::mbar_wait_ab(&empty_x[gg][slot], (round & 1u) ^ 1u, ctl)) return;
+        tc::mbar_expect_tx(&full_x[gg][slot], (unsigned)kXTileBytes);
+        tc::tma_load_1d(my_xring + (size_t)slot * kXTileBytes, x_src + (size_t)i * kXTileBytes, kXTileBytes, &full_x[gg][slot]);
+        if (dbg_on) q.dbg[16 + i] = clock64();  // activation tile i requested
+      }
+    }
+  };
+  auto a_producer = [&](int gg) {
+    const unsigned long long pol = (gg == 1 && q.w2_stream) ? lat::l2_policy_evict_first() : lat::l2_policy_evict_last();
+    unsigned char* const my_aring = aring + (size_t)gg * NSAg[0] * tc::kATileBytes;
+    const int NSA = NSAg[gg];
+    const int g_lo = gg == 0 ? 0 : (has_g1 ? kKb : 0), g_hi = g_lo + kKb;
+    unsigned ga = 0;
+    if (NSA == 0) return;
+    for (int step = 0; step < T; ++step)
+      for (int i = g_lo; i < g_hi; ++i) {
+        if (s_loc[i] != LOC_STREAM) continue;
+        const int slot = (int)(ga % (unsigned)NSA);
+        const unsigned round = ga / (unsigned)NSA;
+        if (round > 0u && !pb::mbar_wait_ab(&empty_a[gg][slot], (round & 1u) ^ 1u, ctl)) return;
+        tc::mbar_expect_tx(&full_a[gg][slot], (unsigned)tc::kATileBytes);
+        pb::tma_load_1d_hint(my_aring + (size_t)slot * tc::kATileBytes, tile_src(i), tc::kATileBytes, &full_a[gg][slot], pol);
+        ++ga;
+      }
+  };
   if (warp == 16) {
-    // =========================== TMA producer: lane i owns tile i of every frame ===========================
-    const unsigned long long pol_keep = lat::l2_policy_evict_last(), pol_once = lat::l2_policy_evict_first();
-    if (lane == 0) {
+    if (lane == 0) {      // shared-memory resident tiles: one-off bulk copies
+      const unsigned long long pol_once = lat::l2_policy_evict_first();
       unsigned bytes = 0;
       for (int i = 0; i < n_tiles; ++i) if (s_loc[i] >= LOC_SMEM) bytes += (unsigned)tc::kATileBytes;
       if (bytes) {
@@ -214,60 +264,41 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         pb::mbar_arrive(&res_bar);
       }
     }
-    if (lane < n_tiles) {
-      const int i = lane, gg = tile_gemm(i);
-      const bool streamed = s_loc[i] == LOC_STREAM;
-      const int g_lo = gg == 0 ? 0 : (has_g1 ? kKb : 0), g_hi = g_lo + kKb;
-      int arank = 0, n_streamed = 0;
-      for (int j = g_lo; j < g_hi; ++j) { const int st_ = s_loc[j] == LOC_STREAM; n_streamed += st_; if (j < i) arank += st_; }
-      unsigned char* const my_aring = aring + (size_t)gg * NSA * tc::kATileBytes;
-      unsigned char* const my_xring = xring + (size_t)gg * NSXg[0] * kXTileBytes;
-      const int NSX = NSXg[gg];
-      const unsigned char* const a_src = tile_src(i);
-      // activation tile = k-block (K split base + local index) of the gate-gradient tiles
-      const unsigned char* const x_src = gg == 0 ? q.dg1t + ((size_t)s1 * (G / 64) + sig1 * kKb + (i - g_lo)) * kXTileBytes
-                                                 : q.dg2t + ((size_t)sig2 * kKb + (i - g_lo)) * kXTileBytes;
-      const unsigned* fptr = gg == 0 ? flag(F_DG1 + s1) : flag(F_DG2);
-      const unsigned mul = gg == 0 ? (unsigned)per : (unsigned)(S == 2 ? per : kCtas);
+    // activation tiles of product 0 (critical chain): lane i owns k-block i of every frame.  A single thread needs ~0.7 kcyc per
+    // tile for the barrier / expect-tx / bulk-copy sequence (measured); sixteen lanes do it side by side.  They all wait for the
+    // same counter, so nobody's ring-slot check is delayed by a sibling's global-memory poll.
+    if (has_g1 && lane < kKb) {
+      const int i = lane, NSX = NSXg[0];
+      const unsigned char* const x_src = q.dg1t + ((size_t)s1 * (G / 64) + sig1 * kKb + i) * kXTileBytes;
+      const unsigned* fptr = flag(F_DG1 + s1);
       unsigned seen = 0;
       bool ok = true;
       for (int step = 0; step < T && ok; ++step) {
-        bool need_a = streamed, need_x = true;
-        const unsigned ga = (unsigned)step * (unsigned)n_streamed + (unsigned)arank, gx = (unsigned)step * (unsigned)kKb + (unsigned)(i - g_lo);
-        const unsigned target = mul * (unsigned)(step + 1);
+        const unsigned gx = (unsigned)step * (unsigned)kKb + (unsigned)i, target = (unsigned)per * (unsigned)(step + 1);
+        const int slot = (int)(gx % (unsigned)NSX);
+        const unsigned round = gx / (unsigned)NSX;
         unsigned spins = 0;
         long long t0 = 0;
+        bool ready = false;
         for (;;) {
-          if (need_a) {
-            const int slot = (int)(ga % (unsigned)NSA);
-            const unsigned round = ga / (unsigned)NSA;
-            if (s_afill[gg][slot] == round && (round == 0u || pb::mbar_test(&empty_a[gg][slot], (round & 1u) ^ 1u))) {
-              tc::mbar_expect_tx(&full_a[gg][slot], (unsigned)tc::kATileBytes);
-              pb::tma_load_1d_hint(my_aring + (size_t)slot * tc::kATileBytes, a_src, tc::kATileBytes, &full_a[gg][slot],
-                                   (gg == 1 && q.w2_stream) ? pol_once : pol_keep);
-              s_afill[gg][slot] = round + 1u;
-              need_a = false;
-            }
-          }
-          if (need_x) {
-            bool ready = (int)(seen - target) >= 0;
+          if (!ready) {
+            ready = (int)(seen - target) >= 0;
             if (!ready) {
               seen = ld_acquire_u32(fptr);
               ready = (int)(seen - target) >= 0;
-              if (ready) pb::fence_proxy_async();
-            }
-            if (ready) {
-              const int slot = (int)(gx % (unsigned)NSX);
-              const unsigned round = gx / (unsigned)NSX;
-              if (s_xfill[gg][slot] == round && (round == 0u || pb::mbar_test(&empty_x[gg][slot], (round & 1u) ^ 1u))) {
-                tc::mbar_expect_tx(&full_x[gg][slot], (unsigned)kXTileBytes);
-                tc::tma_load_1d(my_xring + (size_t)slot * kXTileBytes, x_src, kXTileBytes, &full_x[gg][slot]);
-                s_xfill[gg][slot] = round + 1u;
-                need_x = false;
+              if (ready) {
+                pb::fence_proxy_async();
+                if (q.dbg && c == 0 && i == 0 && step == q.dbg_step) q.dbg[1] = clock64();
               }
             }
           }
-          if (!need_a && !need_x) break;
+          if (ready && s_xfill0[slot] == round && (round == 0u || pb::mbar_test(&empty_x[0][slot], (round & 1u) ^ 1u))) {
+            tc::mbar_expect_tx(&full_x[0][slot], (unsigned)kXTileBytes);
+            tc::tma_load_1d(xring + (size_t)slot * kXTileBytes, x_src, kXTileBytes, &full_x[0][slot]);
+            s_xfill0[slot] = round + 1u;
+            if (q.dbg && c == 0 && step == q.dbg_step) q.dbg[16 + i] = clock64();
+            break;
+          }
           if ((++spins & 63u) == 0u) {
             if (s_exit) { ok = false; break; }
             if (*((volatile int*)p.abort_flag) != 0) { s_exit = 1; ok = false; break; }
@@ -280,54 +311,77 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
   } else if (warp == 17 || warp == 18) {
     // =========================== MMA issuers: warp 17 = attention-LSTM product, warp 18 = decoder-LSTM product ==========
     const int gg = warp - 17;
-    if (lane == 0 && (gg == 0 ? has_g1 : has_g2)) {
+    if (warp == 18 && lane == 1) {
+      if (has_g2) x_producer(1);
+    } else if (warp == 17 && lane == 1) {
+      if (has_g1) a_producer(0);
+    } else if (warp == 17 && lane == 2) {
+      if (has_g2) a_producer(1);
+    } else if (lane == 0 && (gg == 0 ? has_g1 : has_g2)) {
       const uint32_t idesc = tc::make_idesc_f16(128, NPAD) | tc::kFmtBF16;
       constexpr uint32_t lbo_a = (128 / 8) * 128, lbo_x = (NPAD / 8) * 128, sbo = 128;
       const int i_lo = gg == 0 ? 0 : (has_g1 ? kKb : 0), i_hi = i_lo + kKb;
-      int n_streamed = 0;
-      for (int j = i_lo; j < i_hi; ++j) n_streamed += s_loc[j] == LOC_STREAM;
-      unsigned char* const my_aring = aring + (size_t)gg * NSA * tc::kATileBytes;
+      unsigned char* const my_aring = aring + (size_t)gg * NSAg[0] * tc::kATileBytes;
+      const int NSA = NSAg[gg] > 0 ? NSAg[gg] : 1;
       unsigned char* const my_xring = xring + (size_t)gg * NSXg[0] * kXTileBytes;
       const int NSX = NSXg[gg];
       const uint64_t desc_hi_a = tc::make_smem_desc(0u, lbo_a, sbo), desc_hi_x = tc::make_smem_desc(0u, lbo_x, sbo);
       const uint32_t a_ring_addr = tc::smem_u32(my_aring), x_ring_addr = tc::smem_u32(my_xring), res_addr = tc::smem_u32(res_s);
       const uint32_t acc = acc_addr[gg];
       bool ok = pb::mbar_wait_ab(&res_bar, 0u, ctl);
+      // The issuing thread is the bottleneck of a product (measured: ~0.95 kcyc per k-block with per-tile table look-ups and ring
+      // arithmetic by division): the placement of the program is three consecutive ranges -- tensor memory, shared memory,
+      // streamed -- so addresses advance linearly, and the ring slots / parities are carried incrementally.
+      int n_t = 0, n_s = 0;                       // tiles of this product in tensor memory / resident in shared memory
+      for (int j = i_lo; j < i_hi; ++j) { const int l = s_loc[j]; n_t += (l >= 0 && l < LOC_SMEM); n_s += l >= LOC_SMEM; }
+      const int loc_first = s_loc[i_lo];
+      const uint32_t a_tm0 = tmem_base + tm_w_col + (uint32_t)((n_t > 0 ? loc_first : 0) * 32);
+      int first_res = 0;
+      for (int j = i_lo; j < i_hi; ++j) if (s_loc[j] >= LOC_SMEM) { first_res = s_loc[j] - LOC_SMEM; break; }
+      const uint32_t res0 = res_addr + (uint32_t)first_res * (uint32_t)tc::kATileBytes;
+      int sx = 0, sa = 0;
+      uint32_t px = 0, pa = 0;
+      constexpr uint64_t kx2 = (uint64_t)((2 * lbo_x) >> 4), ka2 = (uint64_t)((2 * lbo_a) >> 4);
       for (int step = 0; step < T && ok; ++step) {
         if (step > 0) {
           ok = pb::mbar_wait_ab(&acc_empty[gg], (uint32_t)((step - 1) & 1), ctl);
           if (!ok) break;
         }
-        unsigned ga = (unsigned)step * (unsigned)n_streamed;
-        unsigned gx = (unsigned)step * (unsigned)kKb;
-        for (int i = i_lo; i < i_hi; ++i, ++gx) {
-          const int loc = s_loc[i];
-          const int sx = (int)(gx % (unsigned)NSX), sa = (int)(ga % (unsigned)NSA);
-          if (!pb::mbar_try(&full_x[gg][sx], (gx / (unsigned)NSX) & 1u)) ok = pb::mbar_wait_ab(&full_x[gg][sx], (gx / (unsigned)NSX) & 1u, ctl);
-          if (ok && loc == LOC_STREAM && !pb::mbar_try(&full_a[gg][sa], (ga / (unsigned)NSA) & 1u))
-            ok = pb::mbar_wait_ab(&full_a[gg][sa], (ga / (unsigned)NSA) & 1u, ctl);
+        const bool dbg_on = q.dbg && c == 0 && gg == 0 && step == q.dbg_step;
+        uint32_t a_tm = a_tm0, a_res = res0;
+#pragma unroll 1
+        for (int i = 0; i < kKb; ++i) {
+          if (!pb::mbar_try(&full_x[gg][sx], px)) ok = pb::mbar_wait_ab(&full_x[gg][sx], px, ctl);
+          const bool streamed = i >= n_t + n_s;
+          if (ok && streamed && !pb::mbar_try(&full_a[gg][sa], pa)) ok = pb::mbar_wait_ab(&full_a[gg][sa], pa, ctl);
           if (!ok) break;
+          if (dbg_on) q.dbg[32 + i] = clock64();        // operands of tile i landed
           tc::tc_fence_after();
           const uint64_t dx0 = desc_hi_x | (uint64_t)(((x_ring_addr + (uint32_t)sx * (uint32_t)kXTileBytes) >> 4) & 0x3fffu);
-          const uint32_t first = (i == i_lo) ? 0u : 1u;
-          if (loc >= 0 && loc < LOC_SMEM) {
-            const uint32_t a_tm = tmem_base + tm_w_col + (uint32_t)(loc * 32);
+          const uint32_t first = i == 0 ? 0u : 1u;
+          if (i < n_t) {
             pb::umma_f16_ts(acc, a_tm, dx0, idesc, first);
-            pb::umma_f16_ts(acc, a_tm + 8u, dx0 + (uint64_t)((2 * lbo_x) >> 4), idesc, 1u);
-            pb::umma_f16_ts(acc, a_tm + 16u, dx0 + (uint64_t)((4 * lbo_x) >> 4), idesc, 1u);
-            pb::umma_f16_ts(acc, a_tm + 24u, dx0 + (uint64_t)((6 * lbo_x) >> 4), idesc, 1u);
+            pb::umma_f16_ts(acc, a_tm + 8u, dx0 + kx2, idesc, 1u);
+            pb::umma_f16_ts(acc, a_tm + 16u, dx0 + 2 * kx2, idesc, 1u);
+            pb::umma_f16_ts(acc, a_tm + 24u, dx0 + 3 * kx2, idesc, 1u);
+            a_tm += 32u;
           } else {
-            const uint32_t a_addr = loc == LOC_STREAM ? a_ring_addr + (uint32_t)sa * (uint32_t)tc::kATileBytes
-                                                      : res_addr + (uint32_t)(loc - LOC_SMEM) * (uint32_t)tc::kATileBytes;
+            const uint32_t a_addr = streamed ? a_ring_addr + (uint32_t)sa * (uint32_t)tc::kATileBytes : a_res;
             const uint64_t da0 = desc_hi_a | (uint64_t)((a_addr >> 4) & 0x3fffu);
             tc::umma_f16(acc, da0, dx0, idesc, first);
-            tc::umma_f16(acc, da0 + (uint64_t)((2 * lbo_a) >> 4), dx0 + (uint64_t)((2 * lbo_x) >> 4), idesc, 1u);
-            tc::umma_f16(acc, da0 + (uint64_t)((4 * lbo_a) >> 4), dx0 + (uint64_t)((4 * lbo_x) >> 4), idesc, 1u);
-            tc::umma_f16(acc, da0 + (uint64_t)((6 * lbo_a) >> 4), dx0 + (uint64_t)((6 * lbo_x) >> 4), idesc, 1u);
+            tc::umma_f16(acc, da0 + ka2, dx0 + kx2, idesc, 1u);
+            tc::umma_f16(acc, da0 + 2 * ka2, dx0 + 2 * kx2, idesc, 1u);
+            tc::umma_f16(acc, da0 + 3 * ka2, dx0 + 3 * kx2, idesc, 1u);
+            if (!streamed) a_res += (uint32_t)tc::kATileBytes;
           }
           tc::umma_commit(&empty_x[gg][sx]);
-          if (loc == LOC_STREAM) { tc::umma_commit(&empty_a[gg][sa]); ++ga; }
-          if (i == i_hi - 1) tc::umma_commit(&acc_full[gg]);
+          if (++sx == NSX) { sx = 0; px ^= 1u; }
+          if (streamed) {
+            tc::umma_commit(&empty_a[gg][sa]);
+            if (++sa == NSA) { sa = 0; pa ^= 1u; }
+          }
+          if (i == kKb - 1) tc::umma_commit(&acc_full[gg]);
+          if (dbg_on) q.dbg[48 + i] = clock64();        // tile i issued
         }
       }
     }
@@ -764,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         pb::bar_compute();
       }
       if (tid == 0) pb::signal(flag(F_DG1 + sp));
+      if (q.dbg && c == 0 && tid == 0 && step == q.dbg_step) q.dbg[0] = clock64();      // own gate gradients published
       PBW_PH(9)
       // ---------------- window: the attention-LSTM product of frame t is being issued now; advance the decoder-LSTM chain ----------------
       if (t > 0) {
@@ -781,6 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
       // ---------------- epilogue of dX1[t] ----------------
       if (has_g1) {
         PBW_WAIT_MBAR(&acc_full[0], (uint32_t)(step & 1))
+        if (q.dbg && c == 0 && tid == 0 && step == q.dbg_step) q.dbg[2] = clock64();    // accumulator complete
         PBW_PH(10)
         tc::tc_fence_after();
         {

@@ -1772,7 +1772,7 @@ int bw_run_frames(taco2dec_handle* h, const Params& p, const bw::Grads& g, cudaS
 // ------------------------------------------------------------------------------------------
 // Persistent backward kernel (persist_bwd.cuh): eligibility, buffers, launch
 // ------------------------------------------------------------------------------------------
-struct PbwGeometry { int npad, stages_a, stages_x0, stages_x1, n_res, n_tm; size_t smem; };
+struct PbwGeometry { int npad, stages_a0, stages_a1, stages_x0, stages_x1, n_res, n_tm; size_t smem; };
 
 bool pbw_geometry(const taco2dec_handle* h, int B, int T_in, int T_sub, PbwGeometry* out) {
   const int npad = B <= 16 ? 16 : B <= 32 ? 32 : 64;
@@ -1782,17 +1782,20 @@ bool pbw_geometry(const taco2dec_handle* h, int B, int T_in, int T_sub, PbwGeome
   const size_t xt = (size_t)npad * 128, at = tc::kATileBytes;
   int n_tm = std::min(env_int("TACO2DEC_PBW_TMEM", 64), (512 - 2 * npad) / 32);
   n_tm = std::max(0, std::min(n_tm, 32));
-  // activation rings: measured insensitive to their depth (2 vs 8 slots: 40.3 vs 40.6 us/frame); shared memory is better spent on
-  // resident weight tiles (fewer resident tiles: 47 us/frame)
-  int sx0 = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_X0", 2)));
-  int sx1 = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_X1", npad <= 32 ? 4 : 2)));
-  int stages_a = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_A", 2)));
-  while (fixed + (sx0 + sx1) * xt + 2 * stages_a * at + 1024 > budget && sx0 > 2) --sx0;
-  if (fixed + (sx0 + sx1) * xt + 2 * stages_a * at + 1024 > budget) return false;
-  int n_res = (int)((budget - fixed - (sx0 + sx1) * xt - 2 * stages_a * at - 1024) / at);
-  n_res = std::max(0, std::min(std::min(n_res, env_int("TACO2DEC_PBW_RES", 64)), 32 - n_tm));
-  out->npad = npad; out->stages_a = stages_a; out->stages_x0 = sx0; out->stages_x1 = sx1; out->n_res = n_res; out->n_tm = n_tm;
-  out->smem = pbw::smem_plan(npad, stages_a, sx0 + sx1, n_res, max_ts).total;
+  // The attention-LSTM product (0) is the one on the critical chain.  Measured on its timeline (tools/pbw_phases.py with
+  // TACO2DEC_PBW_DEBUG): one k-block costs ~0.47 kcyc of MMA issue and ~1.3 kcyc of TMA latency, so with two activation slots the
+  // product ran at ~1 kcyc per k-block.  Plan: all 16 weight tiles of product 0 resident (tensor memory first, then shared memory)
+  // -> no weight ring for it; the shared memory saved goes to its activation ring; product 1 (a frame of slack) streams everything
+  // through two slots each.
+  int n_res = std::max(0, pbw::kKb - n_tm);
+  int sa0 = 0, sa1 = 2, sx0 = std::max(2, std::min(8, env_int("TACO2DEC_PBW_STAGES_X0", 8))), sx1 = 2;
+  auto need = [&]() { return fixed + (size_t)(sx0 + sx1) * xt + (size_t)(sa0 + sa1 + n_res) * at + 1024; };
+  while (need() > budget && sx0 > 2) --sx0;
+  while (need() > budget && n_res > 0) { --n_res; sa0 = 2; }      // product 0 then streams its last tiles
+  if (need() > budget) return false;
+  while (need() + at <= budget && n_tm + n_res < 32) ++n_res;     // leftovers: resident tiles of product 1
+  out->npad = npad; out->stages_a0 = sa0; out->stages_a1 = sa1; out->stages_x0 = sx0; out->stages_x1 = sx1; out->n_res = n_res; out->n_tm = n_tm;
+  out->smem = pbw::smem_plan(npad, sa0 + sa1, sx0 + sx1, n_res, max_ts).total;
   return out->smem <= budget;
 }
 
@@ -1825,9 +1828,15 @@ int pbw_run(taco2dec_handle* h, const Params& p, const bw::Grads& g, const PbwGe
     for (int s = 0; s < S; ++s) max_ts = std::max(max_ts, p.st[s].Ts);
     q.att_chunk = std::min(480, std::max(16, env_int("TACO2DEC_PBW_CHUNK", max_ts)));     // a warp owns <= 30 consecutive positions
   }
+  q.dbg = nullptr; q.dbg_step = 0;
+  if (getenv("TACO2DEC_PBW_DEBUG")) {      // diagnostics: clock stamps of CTA 0 around the attention-LSTM product of one step
+    if (!h->pb_dbg) CUDA_TRY(cudaMalloc(&h->pb_dbg, 256 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(h->pb_dbg, 0, 256 * sizeof(long long), st));
+    q.dbg = h->pb_dbg; q.dbg_step = env_int("TACO2DEC_PBW_DEBUG", 20);
+  }
   q.w2_stream = env_int("TACO2DEC_PBW_W2_STREAM", 1);     // measured: 40.5 -> 39.1 us/frame (the working set no longer fits in L2 otherwise)
   CUDA_TRY(cudaMemsetAsync(g.dq, 0, (size_t)S * p.T * B * bt::A * sizeof(float), st));     // sub-tasks add their partial dq rows
-  q.stages_a = geo.stages_a; q.stages_x0 = geo.stages_x0; q.stages_x1 = geo.stages_x1; q.n_res = geo.n_res; q.n_tm = geo.n_tm;
+  q.stages_a0 = geo.stages_a0; q.stages_a1 = geo.stages_a1; q.stages_x0 = geo.stages_x0; q.stages_x1 = geo.stages_x1; q.n_res = geo.n_res; q.n_tm = geo.n_tm;
   CUDA_TRY(cudaMemsetAsync(q.flags, 0, (size_t)pbw::F_COUNT * pbw::kFlagStride * sizeof(unsigned), st));
   CUDA_TRY(cudaMemsetAsync(bb.dg1, 0, (size_t)S * (bw::G / 64) * NPAD * 128, st));      // utterance columns >= B of the operand tiles
   CUDA_TRY(cudaMemsetAsync(bb.dg2, 0, (size_t)(bw::G / 64) * NPAD * 128, st));

@@ -29,3 +29,16 @@ print(f"B={B} T={T}: backward {ms:.2f} ms, persistent kernel {kms:.2f} ms = {1e3
 for n, v in zip(names, pc):
     print(f"  {n:50s} {v / T / 1e3:7.2f} kcyc/frame ({100 * v / max(tot, 1):5.1f}%)")
 print("(the four attention rows are parts of what the 'attention tasks' row reported before they were split out: that row now holds only the loop overhead)")
+
+if os.environ.get("TACO2DEC_PBW_DEBUG"):
+    import ctypes as C
+    from tacotron2_subword_b200 import _cabi
+    buf = (C.c_longlong * 256)()
+    _cabi.check(eng.lib.taco2dec_read_debug_stamps(eng.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream), buf))
+    v = list(buf)
+    t0 = v[0]
+    print(f"timeline of the attention-LSTM product, CTA 0, step {os.environ['TACO2DEC_PBW_DEBUG']} (kcyc after the CTA published its own gate gradients):")
+    print(f"  counter complete (all CTAs of the stream published): {(v[1] - t0) / 1e3:7.2f}")
+    for i in range(16):
+        print(f"  tile {i:2d}: requested {(v[16 + i] - t0) / 1e3:7.2f}   operands landed {(v[32 + i] - t0) / 1e3:7.2f}   issued {(v[48 + i] - t0) / 1e3:7.2f}")
+    print(f"  accumulator complete: {(v[2] - t0) / 1e3:7.2f}")
