@@ -277,8 +277,8 @@ __host__ __device__ inline Smem smem_plan(int NPAD, int stages_a, int stages_x, 
   s.wq = take((size_t)A * 33 * 4);
   s.wph = take(fr ? (size_t)(M + 1) * 33 * 4 : 0);
   s.wpc = take(fr ? (size_t)(M + 1) * 65 * 4 : 0);
-  s.w0 = take(fr ? (size_t)4 * M * 4 : 0);
-  s.w1 = take(fr ? (size_t)4 * P * 4 : 0);
+  s.w0 = take(0);
+  s.w1 = take(0);
   s.bias = take((size_t)2 * 128 * 4);
   s.att = take(bt::sma_smem_floats(max_ts) * 4);
   s.red = take((size_t)8 * kMelPad * 4 + 16 * 64 * 4);
@@ -333,8 +333,6 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
   float* wq_s = (float*)(smem + sp.wq);
   float* wph_s = (float*)(smem + sp.wph);
   float* wpc_s = (float*)(smem + sp.wpc);
-  float* w0_s = (float*)(smem + sp.w0);
-  float* w1_s = (float*)(smem + sp.w1);
   float* bias_s = (float*)(smem + sp.bias);     // [0,128): attention LSTM [g*32+u], [128,256): decoder LSTM
   float* att_s = (float*)(smem + sp.att);
   float* red_s = (float*)(smem + sp.red);
@@ -368,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       switch (ti.dep) {
         case DEP_H1_PREV: r.flag = F_H1 + s1; r.mul = n_h1; r.add = 0; break;
         case DEP_CTX_PREV: r.flag = F_CTX + s1; r.mul = B; r.add = 0; break;
-        case DEP_PRE: r.flag = fr ? F_PRE + s1 : -1; r.mul = per_stream; r.add = 0; break;
+        case DEP_PRE: r.flag = fr ? F_PRE + s1 : -1; r.mul = B; r.add = 0; break;       // one prenet task per utterance and stream
         case DEP_H2_PREV: r.flag = F_H2; r.mul = kCtas; r.add = 0; break;
         case DEP_H1_0: r.flag = F_H1 + 0; r.mul = n_h1; r.add = 1; break;
         case DEP_H1_1: r.flag = F_H1 + 1; r.mul = n_h1; r.add = 1; break;
@@ -407,9 +405,6 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
           const int r = i >> 6, k = i & 63;
           wpc_s[r * 65 + k] = r < M ? p.proj_w[(size_t)r * KD + H + x * 64 + k] : p.gate_w[H + x * 64 + k];
         }
-      const int rp = 2 * S, sP = c / per_stream, o0 = (c % per_stream) * rp;
-      for (int i = tid; i < rp * M; i += kCT) w0_s[i] = p.st[sP].pre_w0[(size_t)(o0 + i / M) * M + i % M];
-      for (int i = tid; i < rp * P; i += kCT) w1_s[i] = p.st[sP].pre_w1[(size_t)(o0 + i / P) * P + i % P];
     }
   }
   tc::tc_fence_before();
@@ -666,6 +661,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       // the fate of frame t+1 is already final here (every stop decision of frame t-1 was published before the prenet
       // rows this CTA waited for at the end of frame t-1): release it to the producer lanes / MMA threads one frame ahead,
       // so that their early tiles (h[t], context[t]) overlap the tail of this frame
+      // (free-running: the stop decisions of frame t-1 are taken by the phoneme-stream prenet tasks just before they publish their
+      // rows -- every CTA acquires that counter here, so that all of them read the same verdict about frame t+1)
+      if (fr && t > 0) PB_WAIT_FLAG(flag(F_PRE + 0), (unsigned)B * (unsigned)t)
       if (fr && tid == 0) { if (frame_runs(t + 1)) s_go = t + 2; else s_stop_at = t + 1; }
       unsigned char* x1_next = q.x1 + (size_t)((t + 1) & 1) * x1_par;
       unsigned char* x2_cur = q.x2 + (size_t)(t & 1) * x2_par;
@@ -1100,23 +1098,27 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       }
 
       if (fr) {
-        // prenet dropout of frame t+1 (model.py:23: always on) does not depend on the data: one multiplier per lane now --
-        // lane = (layer, utterance i of the pass, row r) -- fetched with a shuffle where the rows are finished
-        const int rp = 2 * S, sP = c / per_stream, o0 = (c % per_stream) * rp, tt = t + 1;
-        const StreamParams& sq = p.st[sP];
-        float pmult[2];
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const int lyr = lane >> 4, r = lane & 3, b = warp + 16 * ((lane >> 2) & 3) + 64 * pass, o = o0 + r;
-          pmult[pass] = (r < rp && b < B)
-                            ? keep_mult(lyr ? sq.keep1 : sq.keep0, ((size_t)tt * B + b) * P + o, p.seed, sP * 2 + lyr, tt, b * P + o, p.thresh_pre, 2.0f)
-                            : 0.f;
-        }
-        // ---------------- mel / gate of utterance b = c: sum of the projection partials, stop test (model.py:480-485) ----
-        if (c < B) {
-          const int b = c;
-          PB_WAIT_FLAG(flag(F_H2), (unsigned)kCtas * (unsigned)(t + 1))
-          PB_PH(11)
+        // ---------------- free-running feedback, ONE task per (utterance, stream): mel / gate sum + stop test (model.py:382-388,
+        // 480-485) and both prenet layers of frame t+1 (model.py:13-24, 470-471).  Round 2 first spread every step over all 128
+        // CTAs (mel sum -> prenet L0 -> prenet L1: three all-to-all exchanges through L2, 22 kcyc of a 88 kcyc frame, almost all
+        // of it exchange latency); a task here re-sums the 48 projection partials of its utterance and streams the two weight
+        // matrices (336 KB, L2-resident) itself, so the only exchange left is the one the attention-LSTM product waits for. ----
+        const int tt = t + 1;
+        PB_WAIT_FLAG(flag(F_H2), (unsigned)kCtas * (unsigned)(t + 1))
+        PB_PH(11)
+        float* sum6_s = red_s;                      // [6][kMelPad]
+        float* mel_s = red_s + 6 * kMelPad;         // [kMelPad]
+        float* l0_s = mel_s + kMelPad;              // [P]
+        float* pre_s = l0_s + P;                    // [P]
+        for (int id = c; id < B * S; id += kCtas) {
+          const int b = id / S, s = id - b * S;
+          const StreamParams& sq = p.st[s];
+          // dropout multipliers of this thread's rows (thread o < P: layer 0 row o; thread P + o: layer 1 row o)
+          float pmult = 0.f;
+          if (tid < 2 * P) {
+            const int lyr = tid / P, o = tid - lyr * P;
+            pmult = keep_mult(lyr ? sq.keep1 : sq.keep0, ((size_t)tt * B + b) * P + o, p.seed, s * 2 + lyr, tt, b * P + o, p.thresh_pre, 2.0f);
+          }
           const int n_part = 32 + S * 8;
           if (tid < (M + 1) * 6) {     // 6 groups x 8 partials, all requested before the first is used
             const int r = tid % (M + 1), grp = tid / (M + 1);
@@ -1131,99 +1133,83 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             float acc = 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc += pv[k];
-            red_s[grp * kMelPad + r] = acc;
+            sum6_s[grp * kMelPad + r] = acc;
           }
           bar_compute();
           if (tid <= M) {
             float v = 0.f;
 #pragma unroll
-            for (int g6 = 0; g6 < 6; ++g6) v += red_s[g6 * kMelPad + tid];
+            for (int g6 = 0; g6 < 6; ++g6) v += sum6_s[g6 * kMelPad + tid];
             if (tid < M) {
               v += p.proj_b[tid];
-              p.mel[((size_t)b * p.Tcap + t) * M + tid] = v;
-              q.melx[(size_t)b * M + tid] = v;
-            } else {
-              const float g = v + p.gate_b[0];
-              p.gate[(size_t)b * p.Tcap + t] = g;
+              mel_s[tid] = v;
+              if (s == 0) p.mel[((size_t)b * p.Tcap + t) * M + tid] = v;
+            } else if (s == 0) {
+              const float gv = v + p.gate_b[0];
+              p.gate[(size_t)b * p.Tcap + t] = gv;
               if (p.n_frames[b] == 0) {
                 bool fin = false;
-                if (sigmoidf_(g) > p.gate_thr) { p.n_frames[b] = t + 1; fin = true; }
+                if (sigmoidf_(gv) > p.gate_thr) { p.n_frames[b] = t + 1; fin = true; }
                 else if (t + 1 == p.max_steps) { p.n_frames[b] = t + 1; p.reached_max[b] = 1; fin = true; }
                 if (fin && atomicAdd(p.done_count, 1) + 1 == B) atomicExch(flag(F_DONE), (unsigned)(t + 1));
               }
             }
           }
           bar_compute();
-          if (tid == 0) signal(flag(F_MEL));
-        }
-        PB_PH(12)
-        // ---------------- prenet of frame t+1, 2S rows of each layer per CTA (model.py:13-24, 470-471) ----------------
-        {
-          PB_WAIT_FLAG(flag(F_MEL), (unsigned)B * (unsigned)(t + 1))
-          for (int pass = 0; pass * 64 < B; ++pass) {       // 4 utterances per warp and pass: their mel rows are requested together
-            const int bb = warp + 64 * pass;
-            float4 xv[4];
+          // layer 0: warp w owns rows [16w, 16w + 16), four rows per pass (their weight rows are requested together)
+          {
+            const float4 xv = lane < M / 4 ? reinterpret_cast<const float4*>(mel_s)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int b = bb + 16 * i;
-              xv[i] = (lane < M / 4 && b < B) ? __ldcg(reinterpret_cast<const float4*>(q.melx + (size_t)b * M) + lane)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int b = bb + 16 * i;
-              if (b >= B) break;
+            for (int pass = 0; pass < 4; ++pass) {
+              const int r0 = warp * 16 + pass * 4;
               float acc[4] = {0.f, 0.f, 0.f, 0.f};
               if (lane < M / 4) {
+                float4 wv[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-                  if (r < rp) {
-                    const float4 wv = *reinterpret_cast<const float4*>(w0_s + r * M + lane * 4);
-                    acc[r] = wv.x * xv[i].x + wv.y * xv[i].y + wv.z * xv[i].z + wv.w * xv[i].w;
-                  }
+                for (int r = 0; r < 4; ++r) wv[r] = __ldg(reinterpret_cast<const float4*>(sq.pre_w0 + (size_t)(r0 + r) * M) + lane);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] = wv[r].x * xv.x + wv[r].y * xv.y + wv[r].z * xv.z + wv[r].w * xv.w;
               }
               const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
-              const float mult = __shfl_sync(0xffffffffu, pmult[pass], (i << 2) | (lane >> 3));
-              const int r = lane >> 3;
-              if ((lane & 7) == 0 && r < rp) q.l0x[((size_t)sP * NPAD + b) * P + o0 + r] = fmaxf(v, 0.f) * mult;
+              if ((lane & 7) == 0) l0_s[r0 + (lane >> 3)] = v;
             }
           }
           bar_compute();
-          if (tid == 0) signal(flag(F_L0 + sP));
-          PB_PH(13)
-          PB_WAIT_FLAG(flag(F_L0 + sP), (unsigned)per_stream * (unsigned)(t + 1))
-          for (int pass = 0; pass * 64 < B; ++pass) {
-            const int bb = warp + 64 * pass;
-            float4 xa[4], xb[4];
+          if (tid < P) l0_s[tid] = fmaxf(l0_s[tid], 0.f) * pmult;
+          bar_compute();
+          // layer 1
+          {
+            const float4 xa = reinterpret_cast<const float4*>(l0_s)[lane * 2], xb = reinterpret_cast<const float4*>(l0_s)[lane * 2 + 1];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int b = bb + 16 * i;
-              const float4* xs = reinterpret_cast<const float4*>(q.l0x + ((size_t)sP * NPAD + (b < B ? b : 0)) * P) + lane * 2;
-              xa[i] = __ldcg(xs); xb[i] = __ldcg(xs + 1);
-            }
+            for (int pass = 0; pass < 4; ++pass) {
+              const int r0 = warp * 16 + pass * 4;
+              float4 wa[4], wb[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int b = bb + 16 * i;
-              if (b >= B) break;
-              float acc[4] = {0.f, 0.f, 0.f, 0.f};
+              for (int r = 0; r < 4; ++r) {
+                const float4* wr = reinterpret_cast<const float4*>(sq.pre_w1 + (size_t)(r0 + r) * P) + lane * 2;
+                wa[r] = __ldg(wr); wb[r] = __ldg(wr + 1);
+              }
+              float acc[4];
 #pragma unroll
               for (int r = 0; r < 4; ++r)
-                if (r < rp) {
-                  const float4 wa = *reinterpret_cast<const float4*>(w1_s + r * P + lane * 8);
-                  const float4 wb = *reinterpret_cast<const float4*>(w1_s + r * P + lane * 8 + 4);
-                  acc[r] = (wa.x * xa[i].x + wa.y * xa[i].y + wa.z * xa[i].z + wa.w * xa[i].w) +
-                           (wb.x * xb[i].x + wb.y * xb[i].y + wb.z * xb[i].z + wb.w * xb[i].w);
-                }
+                acc[r] = (wa[r].x * xa.x + wa[r].y * xa.y + wa[r].z * xa.z + wa[r].w * xa.w) +
+                         (wb[r].x * xb.x + wb[r].y * xb.y + wb[r].z * xb.z + wb[r].w * xb.w);
               const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
-              const float mult = __shfl_sync(0xffffffffu, pmult[pass], 16 | (i << 2) | (lane >> 3));
-              const int r = lane >> 3;
-              if ((lane & 7) == 0 && r < rp) bt::x_store(x1_next + (size_t)sP * x1_stream, NPAD, b, o0 + r, fmaxf(v, 0.f) * mult);
+              if ((lane & 7) == 0) pre_s[r0 + (lane >> 3)] = v;
             }
           }
           bar_compute();
-          if (tid == 0) signal(flag(F_PRE + sP));
-          PB_PH(14)
+          if (tid >= P && tid < 2 * P) pre_s[tid - P] = fmaxf(pre_s[tid - P], 0.f) * pmult;
+          bar_compute();
+          if (tid < P / 8) {       // fp16 operand chunks of the attention-LSTM product of frame t+1
+            const float* pv = pre_s + tid * 8;
+            const float v[8] = {pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7]};
+            *reinterpret_cast<uint4*>(x_chunk_ptr(x1_next + (size_t)s * x1_stream, NPAD, b, tid * 8)) = pn::pack8(v);
+          }
+          bar_compute();
+          if (tid == 0) signal(flag(F_PRE + s));
         }
+        PB_PH(14)
       }
     }
   pb_done:;
