@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
   const int n_tiles = (has_g1 ? kTiles1 : 0) + tiles2_of(S);
   const int NSA = q.stages_a, NSX = q.stages_x;
   const int n_steps = fr ? p.max_steps : p.T;
-  const int per_stream = kCtas / S;            // CTAs computing prenet rows of one stream (free-running)
   constexpr int n_h1 = 64;                     // CTAs publishing h1 of one stream (32 row tiles x 2 splits)
   const size_t x1_stream = (size_t)28 * kXTileBytes, x1_par = (size_t)S * x1_stream;
   const size_t x2_par = (size_t)(S == 2 ? 64 : 40) * kXTileBytes;
@@ -570,9 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
     if (lane == 0 && (my_gemm == 1 || has_g1)) {
       const uint32_t idesc = tc::make_idesc_f16(128, NPAD);
       constexpr uint32_t lbo_a = (128 / 8) * 128, lbo_x = (NPAD / 8) * 128, sbo = 128;
-      const int i_lo = my_gemm == 0 ? 0 : (has_g1 ? kTiles1 : 0), i_hi = my_gemm == 0 ? kTiles1 : n_tiles, n_g = i_hi - i_lo;
-      int n_streamed = 0;
-      for (int j = i_lo; j < i_hi; ++j) n_streamed += s_loc[j] == LOC_STREAM;
+      const int i_lo = my_gemm == 0 ? 0 : (has_g1 ? kTiles1 : 0), i_hi = my_gemm == 0 ? kTiles1 : n_tiles;
       const int g = my_gemm;
       unsigned char* const my_aring = aring + (size_t)g * NSA * tc::kATileBytes;
       unsigned char* const my_xring = xring + (size_t)g * NSX * kXTileBytes;
@@ -581,23 +578,21 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       const uint32_t a_ring_addr = tc::smem_u32(my_aring), x_ring_addr = tc::smem_u32(my_xring), res_addr = tc::smem_u32(res_s);
       const uint32_t acc = acc_addr[my_gemm];
       bool ok = mbar_wait_ab(&res_bar, 0u, ctl);
+      int sx = 0, sa = 0;
+      uint32_t px = 0, pa = 0;
       for (int t = 0; t < n_steps && ok; ++t) {
         if (fr && !wait_frame(t)) break;
         if (t > 0) {     // the epilogue of the previous frame must have drained this accumulator
           ok = mbar_wait_ab(&acc_empty[my_gemm], (uint32_t)((t - 1) & 1), ctl);
           if (!ok) break;
         }
-        unsigned ga = (unsigned)t * (unsigned)n_streamed;
-        unsigned gx = (unsigned)t * (unsigned)n_g;
         const bool dbg_on = q.dbg && c == q.dbg_cta && t == q.dbg_frame;
-        for (int i = i_lo; i < i_hi; ++i, ++gx) {
+        for (int i = i_lo; i < i_hi; ++i) {
           // this thread is the critical path of the product: per tile a couple of barrier probes, eight descriptor adds,
-          // four MMAs and the commits -- nothing else
+          // four MMAs and the commits -- nothing else (ring slots and parities are carried incrementally: no divisions)
           const int loc = s_loc[i];
-          const int sx = (int)(gx % (unsigned)NSX), sa = (int)(ga % (unsigned)NSA);
-          if (!mbar_try(&full_x[g][sx], (gx / (unsigned)NSX) & 1u)) ok = mbar_wait_ab(&full_x[g][sx], (gx / (unsigned)NSX) & 1u, ctl);
-          if (ok && loc == LOC_STREAM && !mbar_try(&full_a[g][sa], (ga / (unsigned)NSA) & 1u))
-            ok = mbar_wait_ab(&full_a[g][sa], (ga / (unsigned)NSA) & 1u, ctl);
+          if (!mbar_try(&full_x[g][sx], px)) ok = mbar_wait_ab(&full_x[g][sx], px, ctl);
+          if (ok && loc == LOC_STREAM && !mbar_try(&full_a[g][sa], pa)) ok = mbar_wait_ab(&full_a[g][sa], pa, ctl);
           if (!ok) break;
           if (dbg_on) q.dbg[32 + i] = clock64();
           tc::tc_fence_after();
@@ -619,7 +614,11 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
             tc::umma_f16(acc, da0 + (uint64_t)((6 * lbo_a) >> 4), dx0 + (uint64_t)((6 * lbo_x) >> 4), idesc, 1u);
           }
           tc::umma_commit(&empty_x[g][sx]);
-          if (loc == LOC_STREAM) { tc::umma_commit(&empty_a[g][sa]); ++ga; }
+          if (++sx == NSX) { sx = 0; px ^= 1u; }
+          if (loc == LOC_STREAM) {
+            tc::umma_commit(&empty_a[g][sa]);
+            if (++sa == NSA) { sa = 0; pa ^= 1u; }
+          }
           if (i == i_hi - 1) tc::umma_commit(&acc_full[my_gemm]);
           if (dbg_on) q.dbg[64 + i] = clock64();
         }
