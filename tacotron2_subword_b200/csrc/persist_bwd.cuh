@@ -45,6 +45,8 @@ struct PbwParams {
   float* dx2;                   // [2 parities][4][K2][NPAD]
   float* dxc1;                  // [2 parities][S][4][NPAD][E]   context rows of dX1, utterance-major (read by the attention tasks)
   float* dxc2;                  // [2 parities][4][S][NPAD][E]   context rows of dX2
+  const __half* mem16[2];       // fp16 copies of memory [B][Ts][E] and processed memory [B][Ts][A] for the attention tasks: half the
+  const __half* pm16[2];        // bytes through one SM's L2 port, twice the rows in flight (made once per call)
   unsigned* flags;              // [F_COUNT][kFlagStride]
   int K2;
   int att_chunk;                // positions per attention sub-task
@@ -64,6 +66,26 @@ __device__ __forceinline__ float ld_keep_f(const float* p, unsigned long long po
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
   return v;
+}
+
+__device__ __forceinline__ uint4 ld_keep_u4(const void* p, unsigned long long policy) { return lat::ldg_stream(reinterpret_cast<const unsigned char*>(p), policy); }
+__device__ __forceinline__ uint2 ld_keep_u2(const void* p, unsigned long long policy) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ float2 h2f(unsigned u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * blockDim.x * 4) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+      uint2 o; o.x = *reinterpret_cast<unsigned*>(&a); o.y = *reinterpret_cast<unsigned*>(&b);
+      *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+      for (size_t k = i; k < n; ++k) dst[k] = __float2half(src[k]);
+    }
+  }
 }
 
 struct Smem { size_t aring, xring, res, out, dq, wq, att, total; };
@@ -603,19 +625,24 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
           pj = __ldcs(g.p_saved[s] + ((size_t)t * B + b) * Ts + jme);
           apj = t > 0 ? __ldcs(g.align[s] + ((size_t)b * T + (t - 1)) * Ts + jme) : (jme == 0 ? 1.f : 0.f);
         }
-        float4 mrow[2][4];
+        // memory rows in fp16: lane owns elements [8 (lane + 32 h), +8), h = 0, 1; four rows in flight
+        const __half* mem16_b = q.mem16[s] + (size_t)b * Ts * E;
+        const __half* pm16_b = q.pm16[s] + (size_t)b * Ts * A;
+        uint4 mrow[4][2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < 4; ++r) {
           const int j = r0 + r;
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq)
-            mrow[r][qq] = (j < rd && r1 > r0) ? ld_keep_f4(mem_b + (size_t)j * E + 4 * (lane + 32 * qq), pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int hh = 0; hh < 2; ++hh)
+            mrow[r][hh] = (j < rd && r1 > r0) ? ld_keep_u4(mem16_b + (size_t)j * E + 8 * (lane + 32 * hh), pol_keep) : make_uint4(0u, 0u, 0u, 0u);
         }
+        // attention dimensions of this lane: a = 4 lane + i
         float qv[4], vv[4];
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          qv[qq] = g.sv.q[(((size_t)t * S + s) * B + b) * A + lane + 32 * qq];
-          vv[qq] = sa.v[lane + 32 * qq];
+        {
+          const float4 q4 = *reinterpret_cast<const float4*>(g.sv.q + (((size_t)t * S + s) * B + b) * A + 4 * lane);
+          const float4 v4 = *reinterpret_cast<const float4*>(sa.v + 4 * lane);
+          qv[0] = q4.x; qv[1] = q4.y; qv[2] = q4.z; qv[3] = q4.w;
+          vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
         }
         for (int a = tid; a < 2 * A; a += kCT) dqa_s[a] = 0.f;          // dqa_s and dva_s are adjacent
         if (step > 0 && s != sp) PBW_WAIT_FLAG(flag(F_X1 + s), (unsigned)n_g1s * (unsigned)step)
@@ -636,31 +663,36 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         float dan = base;                                       // lane i: d alpha' of position r0 + i
         if (r1 > r0) {
           const float4* dc4 = reinterpret_cast<const float4*>(dctx_s);
-          float4 dcv[4];
+          float4 dcv[2][2];
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) dcv[qq] = dc4[lane + 32 * qq];
-          auto dot_row = [&](const float4 (&m)[4]) {
+          for (int hh = 0; hh < 2; ++hh) { dcv[hh][0] = dc4[2 * (lane + 32 * hh)]; dcv[hh][1] = dc4[2 * (lane + 32 * hh) + 1]; }
+          auto dot_row = [&](const uint4 (&m)[2]) {
             float acc = 0.f;
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              acc = fmaf(m[qq].x, dcv[qq].x, acc); acc = fmaf(m[qq].y, dcv[qq].y, acc);
-              acc = fmaf(m[qq].z, dcv[qq].z, acc); acc = fmaf(m[qq].w, dcv[qq].w, acc);
+            for (int hh = 0; hh < 2; ++hh) {
+              const float2 m0 = h2f(m[hh].x), m1 = h2f(m[hh].y), m2 = h2f(m[hh].z), m3 = h2f(m[hh].w);
+              acc = fmaf(m0.x, dcv[hh][0].x, acc); acc = fmaf(m0.y, dcv[hh][0].y, acc);
+              acc = fmaf(m1.x, dcv[hh][0].z, acc); acc = fmaf(m1.y, dcv[hh][0].w, acc);
+              acc = fmaf(m2.x, dcv[hh][1].x, acc); acc = fmaf(m2.y, dcv[hh][1].y, acc);
+              acc = fmaf(m3.x, dcv[hh][1].z, acc); acc = fmaf(m3.y, dcv[hh][1].w, acc);
             }
             return warp_sum(acc);
           };
-          for (int j = r0; j < rd; j += 2) {
-            const float d0 = dot_row(mrow[0]);
-            const float d1 = j + 1 < rd ? dot_row(mrow[1]) : 0.f;
-            // next pair of rows
+          for (int j = r0; j < rd; j += 4) {
+            float d[4];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const int jn = j + 2 + r;
+            for (int r = 0; r < 4; ++r) d[r] = j + r < rd ? dot_row(mrow[r]) : 0.f;
+            // next four rows
 #pragma unroll
-              for (int qq = 0; qq < 4; ++qq)
-                if (jn < rd) mrow[r][qq] = ld_keep_f4(mem_b + (size_t)jn * E + 4 * (lane + 32 * qq), pol_keep);
+            for (int r = 0; r < 4; ++r) {
+              const int jn = j + 4 + r;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh)
+                if (jn < rd) mrow[r][hh] = ld_keep_u4(mem16_b + (size_t)jn * E + 8 * (lane + 32 * hh), pol_keep);
             }
-            if (lane == j - r0) dan += d0;
-            if (lane == j + 1 - r0) dan += d1;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (lane == j + r - r0) dan += d[r];
           }
         }
         PBW_PH(13)
@@ -677,41 +709,45 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
         {
           float dq_acc[4] = {0.f, 0.f, 0.f, 0.f}, dv_acc[4] = {0.f, 0.f, 0.f, 0.f};
           const int re = min(r1, len);
-          float pmr[2][4], dpr[2][4];
+          uint2 pmr[2];
+          float4 dpr[2];
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              const int j = r0 + r;
-              pmr[r][qq] = j < re ? ld_keep_f(pm_b + (size_t)j * A + lane + 32 * qq, pol_keep) : 0.f;
-              dpr[r][qq] = j < re ? dpm_b[(size_t)j * A + lane + 32 * qq] : 0.f;
-            }
+          for (int r = 0; r < 2; ++r) {
+            const int j = r0 + r;
+            pmr[r] = j < re ? ld_keep_u2(pm16_b + (size_t)j * A + 4 * lane, pol_keep) : make_uint2(0u, 0u);
+            dpr[r] = j < re ? *reinterpret_cast<const float4*>(dpm_b + (size_t)j * A + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           for (int j = r0; j < re; j += 2) {
-            float pmc[2][4], dpc[2][4];
+            uint2 pmc[2];
+            float4 dpc[2];
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < 2; ++r) { pmc[r] = pmr[r]; dpc[r] = dpr[r]; }
 #pragma unroll
-              for (int qq = 0; qq < 4; ++qq) { pmc[r][qq] = pmr[r][qq]; dpc[r][qq] = dpr[r][qq]; }
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                const int jn = j + 2 + r;
-                if (jn < re) { pmr[r][qq] = ld_keep_f(pm_b + (size_t)jn * A + lane + 32 * qq, pol_keep); dpr[r][qq] = dpm_b[(size_t)jn * A + lane + 32 * qq]; }
+            for (int r = 0; r < 2; ++r) {
+              const int jn = j + 2 + r;
+              if (jn < re) {
+                pmr[r] = ld_keep_u2(pm16_b + (size_t)jn * A + 4 * lane, pol_keep);
+                dpr[r] = *reinterpret_cast<const float4*>(dpm_b + (size_t)jn * A + 4 * lane);
               }
+            }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
               const int jj = j + r;
               const float dej = __shfl_sync(0xffffffffu, de, (jj - r0) & 31);
               if (jj < re) {
+                const float2 p01 = h2f(pmc[r].x), p23 = h2f(pmc[r].y);
+                const float pmv[4] = {p01.x, p01.y, p23.x, p23.y};
+                const float dpv[4] = {dpc[r].x, dpc[r].y, dpc[r].z, dpc[r].w};
+                float o[4];
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
-                  const float uu = lat::fast_tanh(qv[qq] + pmc[r][qq]);
+                  const float uu = lat::fast_tanh(qv[qq] + pmv[qq]);
                   const float dz = dej * vv[qq] * (1.0f - uu * uu);
                   dq_acc[qq] += dz;
                   dv_acc[qq] = fmaf(dej, uu, dv_acc[qq]);
-                  dpm_b[(size_t)jj * A + lane + 32 * qq] = dpc[r][qq] + dz;
+                  o[qq] = dpv[qq] + dz;
                 }
+                *reinterpret_cast<float4*>(dpm_b + (size_t)jj * A + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
               }
             }
           }
@@ -719,8 +755,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_backward_persistent(const
           if (re > r0) {
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
-              atomicAdd(&dqa_s[lane + 32 * qq], dq_acc[qq]);
-              atomicAdd(&dva_s[lane + 32 * qq], dv_acc[qq]);
+              atomicAdd(&dqa_s[4 * lane + qq], dq_acc[qq]);
+              atomicAdd(&dva_s[4 * lane + qq], dv_acc[qq]);
             }
           }
         }

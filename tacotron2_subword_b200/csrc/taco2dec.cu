@@ -1011,6 +1011,8 @@ struct taco2dec_handle {
   int* bw_ctl;           // device word: frame counter of the backward graph
   pbw::PbwParams pbw;    // persistent backward kernel: parity-buffered split-K partials, counters
   bool pbw_alloc;
+  __half* pbw_h16;       // fp16 copies of memory / processed memory for the attention tasks (grown on demand)
+  size_t pbw_h16_elems;
   cudaStream_t cap_stream;   // private stream used only to capture the per-frame CUDA graph
   bool profiling;        // record CUDA events around the persistent launch
   cudaEvent_t ev0, ev1;
@@ -1828,6 +1830,26 @@ int pbw_run(taco2dec_handle* h, const Params& p, const bw::Grads& g, const PbwGe
     for (int s = 0; s < S; ++s) max_ts = std::max(max_ts, p.st[s].Ts);
     q.att_chunk = std::min(480, std::max(16, env_int("TACO2DEC_PBW_CHUNK", max_ts)));     // a warp owns <= 30 consecutive positions
   }
+  {   // fp16 copies of the attention operands (read every frame by the attention tasks)
+    size_t need = 0;
+    for (int s = 0; s < S; ++s) need += (size_t)B * p.st[s].Ts * (bt::E + bt::A);
+    if (h->pbw_h16_elems < need) {
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (h->pbw_h16) CUDA_TRY(cudaFree(h->pbw_h16));
+      h->pbw_h16 = nullptr; h->pbw_h16_elems = 0;
+      CUDA_TRY(cudaMalloc(&h->pbw_h16, need * sizeof(__half)));
+      h->pbw_h16_elems = need;
+    }
+    __half* w16 = h->pbw_h16;
+    for (int s = 0; s < S; ++s) {
+      const size_t nm = (size_t)B * p.st[s].Ts * bt::E, np = (size_t)B * p.st[s].Ts * bt::A;
+      pbw::to_half_kernel<<<(unsigned)std::min<size_t>((nm / 4 + 255) / 256, 2048), 256, 0, st>>>(p.st[s].mem, w16, nm);
+      q.mem16[s] = w16; w16 += nm;
+      pbw::to_half_kernel<<<(unsigned)std::min<size_t>((np / 4 + 255) / 256, 2048), 256, 0, st>>>(p.st[s].pm, w16, np);
+      q.pm16[s] = w16; w16 += np;
+    }
+    h->launches += 2 * S;
+  }
   q.dbg = nullptr; q.dbg_step = 0;
   if (getenv("TACO2DEC_PBW_DEBUG")) {      // diagnostics: clock stamps of CTA 0 around the attention-LSTM product of one step
     if (!h->pb_dbg) CUDA_TRY(cudaMalloc(&h->pb_dbg, 256 * sizeof(long long)));
@@ -2006,7 +2028,7 @@ int taco2dec_create(const taco2dec_config* cfg, int device, taco2dec_handle** ou
   memset(&h->cur_sv, 0, sizeof(h->cur_sv));
   memset(&h->pb, 0, sizeof(h->pb)); h->pb_alloc = false; h->pb_tiles_valid = false; h->pb_xpre = nullptr; h->pb_xpre_bytes = 0; h->pb_dbg = nullptr; h->pm_given[0] = h->pm_given[1] = nullptr;
   memset(&h->bw_bufs, 0, sizeof(h->bw_bufs)); h->bw_alloc = false; h->bw_tiles_valid = false; h->bw_ctl = nullptr;
-  memset(&h->pbw, 0, sizeof(h->pbw)); h->pbw_alloc = false;
+  memset(&h->pbw, 0, sizeof(h->pbw)); h->pbw_alloc = false; h->pbw_h16 = nullptr; h->pbw_h16_elems = 0;
   h->profiling = false;
   h->ev_valid = false;
   CUDA_TRY(cudaSetDevice(device));
@@ -2045,7 +2067,7 @@ int taco2dec_destroy(taco2dec_handle* h) {
       for (void* q : ptrs) if (q) cudaFree(q);
     }
     if (h->pbw_alloc) {
-      void* ptrs[] = {h->pbw.dx1, h->pbw.dx2, h->pbw.flags, h->pbw.dxc1, h->pbw.dxc2};
+      void* ptrs[] = {h->pbw.dx1, h->pbw.dx2, h->pbw.flags, h->pbw.dxc1, h->pbw.dxc2, h->pbw_h16};
       for (void* q : ptrs) if (q) cudaFree(q);
     }
   }
