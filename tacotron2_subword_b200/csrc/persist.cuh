@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       switch (ti.dep) {
         case DEP_H1_PREV: r.flag = F_H1 + s1; r.mul = n_h1; r.add = 0; break;
         case DEP_CTX_PREV: r.flag = F_CTX + s1; r.mul = B; r.add = 0; break;
-        case DEP_PRE: r.flag = fr ? F_PRE + s1 : -1; r.mul = B; r.add = 0; break;       // one prenet task per utterance and stream
+        case DEP_PRE: r.flag = fr ? F_PRE + s1 : -1; r.mul = 4 * ((B + 3) / 4); r.add = 0; break;       // prenet tasks per stream: 4 row blocks x groups of 4 utterances
         case DEP_H2_PREV: r.flag = F_H2; r.mul = kCtas; r.add = 0; break;
         case DEP_H1_0: r.flag = F_H1 + 0; r.mul = n_h1; r.add = 1; break;
         case DEP_H1_1: r.flag = F_H1 + 1; r.mul = n_h1; r.add = 1; break;
@@ -654,6 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
     }
     const float sc_att = 1.0f / (1.0f - p.p_att), sc_dec = 1.0f / (1.0f - p.p_dec);
     const int row_ep = (warp & 3) * 32 + lane;
+    const int n_grp = (B + 3) / 4;              // free-running prenet tasks: groups of 4 utterances
 
     for (int t = 0; t < n_steps; ++t) {
       if (!frame_runs(t)) break;
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       // so that their early tiles (h[t], context[t]) overlap the tail of this frame
       // (free-running: the stop decisions of frame t-1 are taken by the phoneme-stream prenet tasks just before they publish their
       // rows -- every CTA acquires that counter here, so that all of them read the same verdict about frame t+1)
-      if (fr && t > 0) PB_WAIT_FLAG(flag(F_PRE + 0), (unsigned)B * (unsigned)t)
+      if (fr && t > 0) PB_WAIT_FLAG(flag(F_PRE + 0), (unsigned)(4 * n_grp) * (unsigned)t)
       if (fr && tid == 0) { if (frame_runs(t + 1)) s_go = t + 2; else s_stop_at = t + 1; }
       unsigned char* x1_next = q.x1 + (size_t)((t + 1) & 1) * x1_par;
       unsigned char* x2_cur = q.x2 + (size_t)(t & 1) * x2_par;
@@ -1097,116 +1098,159 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_batched_persistent(const 
       }
 
       if (fr) {
-        // ---------------- free-running feedback, ONE task per (utterance, stream): mel / gate sum + stop test (model.py:382-388,
-        // 480-485) and both prenet layers of frame t+1 (model.py:13-24, 470-471).  Round 2 first spread every step over all 128
-        // CTAs (mel sum -> prenet L0 -> prenet L1: three all-to-all exchanges through L2, 22 kcyc of a 88 kcyc frame, almost all
-        // of it exchange latency); a task here re-sums the 48 projection partials of its utterance and streams the two weight
-        // matrices (336 KB, L2-resident) itself, so the only exchange left is the one the attention-LSTM product waits for. ----
+        // ---------------- free-running feedback: mel / gate sum + stop test (model.py:382-388, 480-485) and both prenet layers of
+        // frame t+1 (model.py:13-24, 470-471).  Round 2 first spread every step over all 128 CTAs (mel sum -> prenet L0 ->
+        // prenet L1: three all-to-all exchanges through L2, 22 kcyc of a 88 kcyc frame, almost all of it exchange latency).  Now a
+        // task = (stream, 64-row block of layer 1, group of 4 utterances) re-sums the projection partials of its utterances,
+        // computes ALL of layer 0 for them (redundantly in the four row-block tasks: 80 KB of weights, read once for the four
+        // utterances) and its 64 rows of layer 1 (64 KB): no exchange inside the prenet, 206 KB through the SM's L2 port per task,
+        // and the only counter left is the one the attention-LSTM product waits for.  (One task per (utterance, stream) with all
+        // 256 rows of layer 1 -- 336 KB per task -- measured 16 kcyc.) ----
         const int tt = t + 1;
-        PB_WAIT_FLAG(flag(F_H2), (unsigned)kCtas * (unsigned)(t + 1))
-        PB_PH(11)
-        float* sum6_s = red_s;                      // [6][kMelPad]
-        float* mel_s = red_s + 6 * kMelPad;         // [kMelPad]
-        float* l0_s = mel_s + kMelPad;              // [P]
-        float* pre_s = l0_s + P;                    // [P]
-        for (int id = c; id < B * S; id += kCtas) {
-          const int b = id / S, s = id - b * S;
+        float* sum_s = red_s;                       // [3][4][kMelPad]  partial sums / later reused
+        float* mel_s = att_s;                       // [4][kMelPad]     the attention scratch is free in this phase
+        float* l0_s = mel_s + 4 * kMelPad;          // [4][P]
+        float* pre_s = l0_s + 4 * P;                // [4][64]
+        for (int id = c; id < S * 4 * n_grp; id += kCtas) {
+          const int s = id / (4 * n_grp), rem = id - s * 4 * n_grp, rb = rem & 3, b0 = (rem >> 2) * 4;
           const StreamParams& sq = p.st[s];
-          // dropout multipliers of this thread's rows (thread o < P: layer 0 row o; thread P + o: layer 1 row o)
-          float pmult = 0.f;
-          if (tid < 2 * P) {
-            const int lyr = tid / P, o = tid - lyr * P;
-            pmult = keep_mult(lyr ? sq.keep1 : sq.keep0, ((size_t)tt * B + b) * P + o, p.seed, s * 2 + lyr, tt, b * P + o, p.thresh_pre, 2.0f);
-          }
-          const int n_part = 32 + S * 8;
-          if (tid < (M + 1) * 6) {     // 6 groups x 8 partials, all requested before the first is used
-            const int r = tid % (M + 1), grp = tid / (M + 1);
-            float pv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int pi = grp + 6 * k;
-              pv[k] = pi >= n_part ? 0.f
-                      : pi < 32 ? __ldcg(q.melp + ((size_t)pi * NPAD + b) * kMelPad + r)
-                                : __ldcg(q.ctxp + ((size_t)(pi - 32) * NPAD + b) * kMelPad + r);
-            }
-            float acc = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc += pv[k];
-            sum6_s[grp * kMelPad + r] = acc;
-          }
-          bar_compute();
-          if (tid <= M) {
-            float v = 0.f;
-#pragma unroll
-            for (int g6 = 0; g6 < 6; ++g6) v += sum6_s[g6 * kMelPad + tid];
-            if (tid < M) {
-              v += p.proj_b[tid];
-              mel_s[tid] = v;
-              if (s == 0) p.mel[((size_t)b * p.Tcap + t) * M + tid] = v;
-            } else if (s == 0) {
-              const float gv = v + p.gate_b[0];
-              p.gate[(size_t)b * p.Tcap + t] = gv;
-              if (p.n_frames[b] == 0) {
-                bool fin = false;
-                if (sigmoidf_(gv) > p.gate_thr) { p.n_frames[b] = t + 1; fin = true; }
-                else if (t + 1 == p.max_steps) { p.n_frames[b] = t + 1; p.reached_max[b] = 1; fin = true; }
-                if (fin && atomicAdd(p.done_count, 1) + 1 == B) atomicExch(flag(F_DONE), (unsigned)(t + 1));
-              }
-            }
-          }
-          bar_compute();
-          // layer 0: warp w owns rows [16w, 16w + 16), four rows per pass (their weight rows are requested together)
+          // layer-0 weight rows of the first pass (independent of the data): requested before the wait
+          float4 w0v[8];
           {
-            const float4 xv = lane < M / 4 ? reinterpret_cast<const float4*>(mel_s)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r0 = warp * 16;
 #pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-              const int r0 = warp * 16 + pass * 4;
-              float acc[4] = {0.f, 0.f, 0.f, 0.f};
-              if (lane < M / 4) {
-                float4 wv[4];
+            for (int r = 0; r < 8; ++r)
+              w0v[r] = lane < M / 4 ? __ldg(reinterpret_cast<const float4*>(sq.pre_w0 + (size_t)(r0 + r) * M) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          // dropout multipliers: layer 0 -- (utterance u, row o) for o = tid & 255, u = 2 (tid >> 8) + {0, 1}; layer 1 -- (u, 64 rb + o)
+          float pm0[2], pm1 = 0.f;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) wv[r] = __ldg(reinterpret_cast<const float4*>(sq.pre_w0 + (size_t)(r0 + r) * M) + lane);
+          for (int k = 0; k < 2; ++k) {
+            const int u = 2 * (tid >> 8) + k, o = tid & (P - 1), b = b0 + u;
+            pm0[k] = b < B ? keep_mult(sq.keep0, ((size_t)tt * B + b) * P + o, p.seed, s * 2 + 0, tt, b * P + o, p.thresh_pre, 2.0f) : 0.f;
+          }
+          if (tid < 4 * 64) {
+            const int u = tid >> 6, o = rb * 64 + (tid & 63), b = b0 + u;
+            pm1 = b < B ? keep_mult(sq.keep1, ((size_t)tt * B + b) * P + o, p.seed, s * 2 + 1, tt, b * P + o, p.thresh_pre, 2.0f) : 0.f;
+          }
+          PB_WAIT_FLAG(flag(F_H2), (unsigned)kCtas * (unsigned)(t + 1))
+          PB_PH(11)
+          // mel / gate of the four utterances: thread = (utterance u, row r < 81), 48 partials in two batches of 24 (every batch
+          // is one round trip to L2 lines other SMs have just written: ~2 kcyc)
+          {
+            const int u = tid >> 7, r = tid & 127, b = b0 + u;
+            const int n_part = 32 + S * 8;
+            if (r <= M && b < B) {
+              float acc = r < M ? p.proj_b[r] : p.gate_b[0];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) acc[r] = wv[r].x * xv.x + wv[r].y * xv.y + wv[r].z * xv.z + wv[r].w * xv.w;
+              for (int k0 = 0; k0 < 48; k0 += 24) {
+                float pv[24];
+#pragma unroll
+                for (int k = 0; k < 24; ++k) {
+                  const int pi = k0 + k;
+                  pv[k] = pi >= n_part ? 0.f
+                          : pi < 32 ? __ldcg(q.melp + ((size_t)pi * NPAD + b) * kMelPad + r)
+                                    : __ldcg(q.ctxp + ((size_t)(pi - 32) * NPAD + b) * kMelPad + r);
+                }
+                float a24 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 24; ++k) a24 += pv[k];
+                acc += a24;
               }
-              const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
-              if ((lane & 7) == 0) l0_s[r0 + (lane >> 3)] = v;
+              mel_s[u * kMelPad + r] = acc;
+              if (s == 0 && rb == 0) {
+                if (r < M) {
+                  p.mel[((size_t)b * p.Tcap + t) * M + r] = acc;
+                } else {
+                  p.gate[(size_t)b * p.Tcap + t] = acc;
+                  if (p.n_frames[b] == 0) {
+                    bool fin = false;
+                    if (sigmoidf_(acc) > p.gate_thr) { p.n_frames[b] = t + 1; fin = true; }
+                    else if (t + 1 == p.max_steps) { p.n_frames[b] = t + 1; p.reached_max[b] = 1; fin = true; }
+                    if (fin && atomicAdd(p.done_count, 1) + 1 == B) atomicExch(flag(F_DONE), (unsigned)(t + 1));
+                  }
+                }
+              }
+            } else if (r <= M) {
+              mel_s[u * kMelPad + r] = 0.f;
             }
           }
           bar_compute();
-          if (tid < P) l0_s[tid] = fmaxf(l0_s[tid], 0.f) * pmult;
-          bar_compute();
-          // layer 1
+          PB_PH(12)
+          // layer 0, all 256 rows for the four utterances: warp w owns rows [16w, 16w + 16), two passes of 8 rows; a weight row is
+          // read once and used for the four utterances
           {
-            const float4 xa = reinterpret_cast<const float4*>(l0_s)[lane * 2], xb = reinterpret_cast<const float4*>(l0_s)[lane * 2 + 1];
+            float4 xv[4];
 #pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-              const int r0 = warp * 16 + pass * 4;
-              float4 wa[4], wb[4];
+            for (int u = 0; u < 4; ++u) xv[u] = lane < M / 4 ? reinterpret_cast<const float4*>(mel_s + u * kMelPad)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const float4* wr = reinterpret_cast<const float4*>(sq.pre_w1 + (size_t)(r0 + r) * P) + lane * 2;
-                wa[r] = __ldg(wr); wb[r] = __ldg(wr + 1);
+            for (int pass = 0; pass < 2; ++pass) {
+              const int r0 = warp * 16 + pass * 8;
+              if (pass == 1) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                  w0v[r] = lane < M / 4 ? __ldg(reinterpret_cast<const float4*>(sq.pre_w0 + (size_t)(r0 + r) * M) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
+#pragma unroll
+              for (int r4 = 0; r4 < 8; r4 += 4)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float acc[4];
+#pragma unroll
+                  for (int r = 0; r < 4; ++r)
+                    acc[r] = w0v[r4 + r].x * xv[u].x + w0v[r4 + r].y * xv[u].y + w0v[r4 + r].z * xv[u].z + w0v[r4 + r].w * xv[u].w;
+                  const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
+                  if ((lane & 7) == 0) l0_s[u * P + r0 + r4 + (lane >> 3)] = v;
+                }
+            }
+          }
+          // layer-1 weight rows of this warp (4 of the task's 64): requested before the barrier
+          float4 wa[4], wb[4];
+          {
+            const int r0 = rb * 64 + warp * 4;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const float4* wr = reinterpret_cast<const float4*>(sq.pre_w1 + (size_t)(r0 + r) * P) + lane * 2;
+              wa[r] = __ldg(wr); wb[r] = __ldg(wr + 1);
+            }
+          }
+          bar_compute();
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int u = 2 * (tid >> 8) + k, o = tid & (P - 1);
+            l0_s[u * P + o] = fmaxf(l0_s[u * P + o], 0.f) * pm0[k];
+          }
+          bar_compute();
+          PB_PH(13)
+          {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 xa = reinterpret_cast<const float4*>(l0_s + u * P)[lane * 2], xb = reinterpret_cast<const float4*>(l0_s + u * P)[lane * 2 + 1];
               float acc[4];
 #pragma unroll
               for (int r = 0; r < 4; ++r)
                 acc[r] = (wa[r].x * xa.x + wa[r].y * xa.y + wa[r].z * xa.z + wa[r].w * xa.w) +
                          (wb[r].x * xb.x + wb[r].y * xb.y + wb[r].z * xb.z + wb[r].w * xb.w);
               const float v = lat::butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
-              if ((lane & 7) == 0) pre_s[r0 + (lane >> 3)] = v;
+              if ((lane & 7) == 0) pre_s[u * 64 + warp * 4 + (lane >> 3)] = v;
             }
           }
           bar_compute();
-          if (tid >= P && tid < 2 * P) pre_s[tid - P] = fmaxf(pre_s[tid - P], 0.f) * pmult;
+          if (tid < 4 * 64) pre_s[tid] = fmaxf(pre_s[tid], 0.f) * pm1;
           bar_compute();
-          if (tid < P / 8) {       // fp16 operand chunks of the attention-LSTM product of frame t+1
-            const float* pv = pre_s + tid * 8;
-            const float v[8] = {pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7]};
-            *reinterpret_cast<uint4*>(x_chunk_ptr(x1_next + (size_t)s * x1_stream, NPAD, b, tid * 8)) = pn::pack8(v);
+          if (tid < 4 * 8) {       // fp16 operand chunks of the attention-LSTM product of frame t+1: (utterance u, 8 rows)
+            const int u = tid >> 3, k8 = tid & 7, b = b0 + u;
+            if (b < B) {
+              const float* pv = pre_s + u * 64 + k8 * 8;
+              const float v[8] = {pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7]};
+              *reinterpret_cast<uint4*>(x_chunk_ptr(x1_next + (size_t)s * x1_stream, NPAD, b, rb * 64 + k8 * 8)) = pn::pack8(v);
+            }
           }
           bar_compute();
           if (tid == 0) signal(flag(F_PRE + s));
+        }
+        if (c >= S * 4 * n_grp) {      // CTAs without a task still follow the frame
+          PB_WAIT_FLAG(flag(F_H2), (unsigned)kCtas * (unsigned)(t + 1))
         }
         PB_PH(14)
       }
