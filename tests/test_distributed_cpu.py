@@ -126,7 +126,7 @@ class _TwoGrads(torch.autograd.Function):
         mod = ctx.mod
         d_big = x.t() @ g
         if getattr(mod, "_grad_ready", None) is not None:
-            mod._grad_ready(mod.big, d_big)           # published before the node returns
+            mod._grad_ready(mod.big, d_big)           # published before the node returns (once per node: sub-batches publish twice)
         d_small = g.sum() * torch.ones_like(mod.small)
         if getattr(mod, "_grad_ready", None) is not None:
             mod._grad_ready(mod.small, d_small)       # below the size threshold: stays on the bucket path
@@ -148,6 +148,9 @@ class _FakeDecoder(torch.nn.Module):
         return [self.big, self.small]
 
     def forward(self, x):
+        if getattr(self, "sub_batches", False):       # two nodes per pass, as Decoder._tf_resized produces for B > 128
+            h = x.shape[0] // 2
+            return torch.cat([_TwoGrads.apply(self, x[:h], self.big, self.small), _TwoGrads.apply(self, x[h:], self.big, self.small)])
         return _TwoGrads.apply(self, x, self.big, self.small)
 
 
@@ -160,7 +163,8 @@ def _early_worker(rank, world, port, q):
         apply_gradient_allreduce(net)
         net._grad_bucketer.early_min_bytes = 256      # `big` (512 B) takes the early path, `small` (12 B) does not
         out = []
-        for step in range(2):
+        for step in range(3):
+            net.sub_batches = step == 2               # third step: the same parameter is published by two nodes of one pass
             torch.manual_seed(50 + step * 10 + rank)
             x = torch.randn(4, 16)
             net.zero_grad(set_to_none=True)
@@ -184,7 +188,7 @@ def test_early_published_gradients_are_averaged_once():
         assert p.exitcode == 0
     torch.manual_seed(5)
     ref = _FakeDecoder()
-    for step in range(2):
+    for step in range(3):
         local = []
         for rank in range(world):
             torch.manual_seed(50 + step * 10 + rank)
@@ -196,4 +200,4 @@ def test_early_published_gradients_are_averaged_once():
             want = (local[0][k] + local[1][k]) / 2
             for rank in range(world):
                 assert torch.allclose(torch.from_numpy(out[rank][1][step][k]), want, atol=1e-5), (step, k, rank)
-    assert out[0][2] == 4       # per step: one early all-reduce (big) + one bucket (small)
+    assert out[0][2] == 7       # per step: one early all-reduce per publishing node (big) + one bucket (small); two nodes in step 3

@@ -198,3 +198,45 @@ def test_invalidate_weights_and_training_mode_force_a_rebind():
         dec._bind_weights(eng)
     dec.eval()
     dec._bind_weights(eng)              # eval + unchanged key: early return, nothing touched
+
+
+def test_tf_resized_splits_batches_and_slices_replayed_masks():
+    """Decoder._tf_resized (batches outside one tensor-path call): B = 1 runs as a pair whose second row is a detached copy, B > rows as
+    balanced sub-batches (sizes differ by at most one, none of size 1) over the same padded memory, replayed masks sliced along the
+    batch, Philox seeds offset per sub-batch, module state restored afterwards.  The CUDA call is replaced by a recorder."""
+    from tacotron2_subword_b200 import DropoutReplay
+    dec = Decoder(create_hparams())
+    calls = []
+
+    def run(memory, embeddings, dec_in, mlen, blen, independent):
+        rp = dec.dropout_replay
+        calls.append(dict(B=memory.shape[0], T_in=memory.shape[1], seed=dec.rng_seed, validate=dec.validate_lengths,
+                          pk=None if rp is None else tuple(rp.prenet_keep[0][0].shape), lk=None if rp is None else tuple(rp.lstm_keep.shape),
+                          first=float(memory.detach()[0, 0, 0])))
+        B, T = memory.shape[0], dec_in.shape[2]
+        return (memory[:, :1, :80].expand(B, T, 80).transpose(1, 2) * 1.0, torch.zeros(B, T), torch.zeros(B, T, memory.shape[1]),
+                torch.zeros(B, T, embeddings.shape[1]))
+
+    for B, rows, want_sizes in ((1, 128, [2]), (11, 4, [3, 4, 4]), (130, 128, [65, 65]), (257, 128, [85, 86, 86])):
+        calls.clear()
+        T, T_in, T_sub = 3, 6, 2
+        dec.max_backward_rows = rows
+        dec.rng_seed = 99
+        dec.dropout_replay = DropoutReplay(prenet_keep=[[torch.ones(T + 1, B, 256, dtype=torch.uint8) for _ in range(2)] for _ in range(2)],
+                                           lstm_keep=torch.ones(T, 6, B, 1024, dtype=torch.uint8), sma_noise=[torch.zeros(T, B, T_in), torch.zeros(T, B, T_sub)])
+        mem = torch.arange(B, dtype=torch.float32).view(B, 1, 1).expand(B, T_in, 512).clone().requires_grad_(True)
+        outs = dec._tf_resized(run, mem, torch.zeros(B, T_sub, 512), torch.zeros(B, 80, T), torch.full((B,), T_in), torch.full((B,), T_sub), False)
+        assert [c_["B"] for c_ in calls] == want_sizes
+        assert all(c_["T_in"] == T_in and not c_["validate"] for c_ in calls)            # same padded memory, lengths validated once
+        assert all(c_["pk"] == (T + 1, c_["B"], 256) and c_["lk"] == (T, 6, c_["B"], 1024) for c_ in calls)
+        assert outs[0].shape == (B, 80, T) and outs[2].shape == (B, T, T_in)
+        assert torch.equal(outs[0][:, 0, 0], torch.arange(B, dtype=torch.float32))       # rows come back in order
+        if B > 1:
+            assert len({c_["seed"] for c_ in calls}) == len(calls)                        # one Philox stream per sub-batch
+            assert [c_["first"] for c_ in calls] == [float(sum(want_sizes[:k])) for k in range(len(want_sizes))]
+        outs[0].sum().backward()
+        assert mem.grad.shape == mem.shape
+        assert dec.rng_seed == 99 and dec.validate_lengths and dec.dropout_replay.lstm_keep.shape[2] == B    # state restored
+    with pytest.raises(ValueError):
+        dec._tf_resized(run, torch.zeros(130, 6, 512), torch.zeros(130, 2, 512), torch.zeros(130, 80, 3), torch.full((130,), 5),
+                        torch.full((130,), 2), False)
