@@ -791,13 +791,20 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent(const __grid_c
 // One-off kernels: processed memory (model.py:258-261) and the hoisted teacher-forced prenet
 // (model.py:412-413).  Warp per output row, same warp_dot as the persistent kernel.
 // ------------------------------------------------------------------------------------------
+// A work item is (memory row n, column chunk c of n_chunk): small calls (one utterance = 150 rows) are cut by output column so
+// that they fill the machine instead of running 32 dependent dot products per warp; large calls use n_chunk = 1 (a warp
+// walks all A columns of its row, the warps of a block share the weight rows through L1).  The summation order of an
+// output element does not depend on n_chunk.
 __global__ void __launch_bounds__(256) processed_memory_kernel(const float* __restrict__ mem, const float* __restrict__ wm,
-                                                               float* __restrict__ pm, int n_rows, int E, int A) {
+                                                               float* __restrict__ pm, int n_rows, int E, int A, int n_chunk) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (int n = gw; n < n_rows; n += nw) {
+  const int chunk_cols = (((A + 3) / 4 + n_chunk - 1) / n_chunk) * 4;
+  for (int item = gw; item < n_rows * n_chunk; item += nw) {
+    const int n = item / n_chunk, c = item - n * n_chunk;
     const float* x = mem + (size_t)n * E;
-    for (int a = 0; a < A; a += 4) {
+    const int a_end = min(A, (c + 1) * chunk_cols);
+    for (int a = c * chunk_cols; a < a_end; a += 4) {
       float acc[4][1] = {{0.f}, {0.f}, {0.f}, {0.f}};
       const float* rows[4];
 #pragma unroll
@@ -1889,8 +1896,10 @@ int run_common(taco2dec_handle* h, Params& p, int T_in, int T_sub, char* ws, con
       CUDA_TRY(cudaMemcpyAsync(p.st[s].pm, h->pm_given[s], (size_t)n_rows * c.attn_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
       continue;
     }
-    const int blocks = std::min((n_rows + 7) / 8, h->num_sms * 8);
-    processed_memory_kernel<<<blocks, 256, 0, st>>>(p.st[s].mem, p.st[s].wm, p.st[s].pm, n_rows, c.enc_dim, c.attn_dim);
+    const int groups = (c.attn_dim + 3) / 4, want_warps = h->num_sms * 16;
+    const int n_chunk = std::max(1, std::min(groups, want_warps / std::max(n_rows, 1)));
+    const int blocks = std::min((n_rows * n_chunk + 7) / 8, h->num_sms * 8);
+    processed_memory_kernel<<<blocks, 256, 0, st>>>(p.st[s].mem, p.st[s].wm, p.st[s].pm, n_rows, c.enc_dim, c.attn_dim, n_chunk);
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());

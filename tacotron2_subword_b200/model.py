@@ -720,6 +720,11 @@ class Decoder(nn.Module):
         reached_max [B] (int32); frames >= n_frames[b] are zeroed (gate there = 1e3 as in parse_output)."""
         if self._wants_sub_batches(memory):
             return self._inference_sub_batches(memory, embeddings, memory_lengths, bert_lengths, max_decoder_steps)
+        return self._inference_one_launch(memory, embeddings, memory_lengths, bert_lengths, max_decoder_steps)[:6]
+
+    def _inference_one_launch(self, memory, embeddings, memory_lengths=None, bert_lengths=None, max_decoder_steps=None):
+        """``inference_batched`` for at most one launch's worth of utterances; also returns the host copy of
+        (n_frames, reached_max) that the call reads back anyway, so that callers need no second device->host read."""
         dev = self.gate_layer.linear_layer.weight.device
         eng = self._engine(dev)
         two = self.n_streams == 2
@@ -734,8 +739,8 @@ class Decoder(nn.Module):
         gate = torch.empty(B, steps, device=dev)
         align = torch.empty(B, steps, T_in, device=dev)
         align_b = torch.empty(B, steps, T_sub, device=dev) if two else None
-        n_frames = torch.zeros(B, dtype=torch.int32, device=dev)
-        reached = torch.zeros(B, dtype=torch.int32, device=dev)
+        counters = torch.zeros(2, B, dtype=torch.int32, device=dev)      # one fill for both
+        n_frames, reached = counters[0], counters[1]
         ws = eng.get_workspace(B, T_in, T_sub, steps, False)
         keep = []
         a = _cabi.InferArgs()
@@ -755,9 +760,13 @@ class Decoder(nn.Module):
             stream = torch.cuda.current_stream(dev)
             _cabi.check(eng.lib.taco2dec_infer(eng.handle, C.byref(a), C.c_void_p(stream.cuda_stream)))
         # one device->host read per call (the reference does one per FRAME, model.py:480)
-        nf = n_frames.cpu()
+        counters_host = counters.cpu()
+        nf = counters_host[0]
         _cabi.check(eng.lib.taco2dec_check(eng.handle, C.c_void_p(stream.cuda_stream)))
         Tmax = int(nf.max())
+        if int(nf.min()) == Tmax:       # every utterance ran to the same frame (always so for B = 1): nothing to blank
+            return (mel[:, :Tmax].transpose(1, 2), gate[:, :Tmax].unsqueeze(2), align[:, :Tmax],
+                    align_b[:, :Tmax] if two else None, n_frames, reached, counters_host)
         frame_ids = torch.arange(Tmax, device=dev).unsqueeze(0)
         dead = frame_ids >= n_frames.unsqueeze(1).to(torch.int64)                # [B,Tmax]
         mel = mel[:, :Tmax].masked_fill(dead.unsqueeze(2), 0.0).transpose(1, 2)
@@ -765,7 +774,7 @@ class Decoder(nn.Module):
         align = align[:, :Tmax].masked_fill(dead.unsqueeze(2), 0.0)
         if two:
             align_b = align_b[:, :Tmax].masked_fill(dead.unsqueeze(2), 0.0)
-        return mel, gate, align, align_b, n_frames, reached
+        return mel, gate, align, align_b, n_frames, reached, counters_host
 
     def _inference_sub_batches(self, memory, embeddings, memory_lengths, bert_lengths, max_decoder_steps):
         """More utterances than one persistent launch takes: balanced sub-batches (utterances are independent), outputs padded
@@ -803,8 +812,8 @@ class Decoder(nn.Module):
         if memory.shape[0] != 1:
             raise ValueError("Decoder.inference is batch-1 as in the reference (model.py:461,480); "
                              "use inference_batched for B > 1")
-        mel, gate, align, align_b, n_frames, reached = self.inference_batched(memory, embeddings)
-        flag = not bool(int(reached[0]))
+        mel, gate, align, align_b, n_frames, reached, counters_host = self._inference_one_launch(memory, embeddings)
+        flag = not bool(int(counters_host[1, 0]))
         if not flag:
             print("Warning! Reached max decoder steps")
         return mel, gate, align, align_b, flag
