@@ -79,6 +79,7 @@ struct LatParams {
   int res_budget;                // shared-memory bytes available for the resident prefix
   int l2_keep_mask;              // bit s set: step s's streamed weights use L2 evict_last, else evict_first
   int use_tmem;                  // 0: off; 1: weight segments e0, e1 (and a when it fits: 16-bit storage) live in tensor memory; 2: b, c
+  int stream_prefetch;           // 1: the L2-streamed single-pass steps b and c request their weights one phase early (registers)
   LatStream st[2];
   const float *d_b_ih, *d_b_hh;  // decoder LSTM biases [4H]
   const float *proj_w, *proj_b, *gate_w, *gate_b;
@@ -461,6 +462,47 @@ __device__ __noinline__ void consume_items(const LstmShared& sh, const StepPlan&
   }
 }
 
+// A fully streamed step whose items map one-to-one onto the warps and fit ONE pass (16 sixteen-byte loads per lane) can
+// request its weights before the exchange / pointwise phase in front of it: the weights do not depend on the activations,
+// the 16 loads sit in registers while the warp polls, and the step itself shrinks to the multiply-accumulate.  Same
+// summation order as dot4 (one pass, units in order), so the results are bit-identical to consume_items.
+template <int WB, int KLEN>
+__device__ __forceinline__ void stream_issue(const LstmShared& sh, const StepPlan& sp, int warp, int lane,
+                                             uint4 (&w)[4][KLEN / (32 * Mac<WB>::kElems)]) {
+  constexpr int NU = KLEN / (32 * Mac<WB>::kElems);
+  const int unit = warp / sp.ksplit, kh = warp - unit * sp.ksplit;
+  const unsigned char* base = sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + (size_t)kh * KLEN * WB;
+  const int row_bytes = sp.K * WB;
+#pragma unroll
+  for (int i = 0; i < NU; ++i)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) w[g][i] = ldg_stream(base + (size_t)g * row_bytes + (size_t)(lane + 32 * i) * 16, sp.policy);
+}
+template <int WB, int KLEN>
+__device__ __forceinline__ void stream_finish(const StepPlan& sp, const float* xs, float* acc, int max_units, int warp,
+                                              int lane, const uint4 (&w)[4][KLEN / (32 * Mac<WB>::kElems)]) {
+  constexpr int EPU = Mac<WB>::kElems;
+  constexpr int NU = KLEN / (32 * EPU);
+  const int unit = warp / sp.ksplit, kh = warp - unit * sp.ksplit;
+  const float* xk = xs + (size_t)kh * KLEN;
+  float a[4][2];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) a[g][0] = a[g][1] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    float x[EPU];
+#pragma unroll
+    for (int e = 0; e < EPU; e += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xk + (size_t)(lane + 32 * i) * EPU + e);
+      x[e + 0] = v.x; x[e + 1] = v.y; x[e + 2] = v.z; x[e + 3] = v.w;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) Mac<WB>::run(w[g][i], x, a[g][0], a[g][1]);
+  }
+  const float c = butterfly4(a[0][0] + a[0][1], a[1][0] + a[1][1], a[2][0] + a[2][1], a[3][0] + a[3][1], lane);
+  if ((lane & 7) == 0) acc[((size_t)kh * max_units + unit) * 4 + (lane >> 3)] += c;
+}
+
 // a step whose weights live in tensor memory: exactly one item per warp.  Kept out of consume_items so that the
 // register allocation of the streamed / shared-memory paths is unaffected.
 template <int WB>
@@ -522,7 +564,63 @@ __device__ __forceinline__ bool lstm_pointwise(const float* acc, int max_units, 
   return true;
 }
 
-template <int WB>
+// Per-CTA step plan: units, column split, tensor-memory / shared-memory residency.  Host and device run the same code (the
+// host uses it to decide whether every LSTM CTA can take the early-request variant of the kernel).
+__host__ __device__ inline void lat_build_plan(const LatParams& p, int lc, int wb, StepPlan* plan) {
+  const int S = p.S;
+  const int s1 = lc / p.NL1, i1 = lc - s1 * p.NL1;
+  const int nu1 = (int)((long long)(i1 + 1) * H / p.NL1) - (int)((long long)i1 * H / p.NL1);
+  const int nu2 = (int)((long long)(lc + 1) * H / p.NL) - (int)((long long)lc * H / p.NL);
+  // steps:            a     b     c     d     e0    e1            f
+  const int nun[kSteps] = {nu1, nu1, nu2, nu1, nu2, S == 2 ? nu2 : 0, nu2};
+  const int ks[kSteps] = {H, E, H, P, H, H, S * E};
+  long long src = 0;
+  for (int s = 0; s < kSteps; ++s) {
+    StepPlan& sp = plan[s];
+    sp.n_units = nun[s]; sp.K = ks[s]; sp.chunk_bytes = 4 * ks[s] * wb; sp.n_res = 0; sp.res_off = 0;
+    sp.ksplit = (nun[s] * 2 <= kWarps && ks[s] >= 512) ? 2 : 1;   // keep every warp busy
+    sp.policy = 0ull;
+    sp.src_off = src;
+    src += (long long)nun[s] * sp.chunk_bytes;
+    sp.tmem_col = -1;
+  }
+  // tensor memory (one item per warp, 128 columns per warp): the segments e0, e1 first, then a
+  // (use_tmem == 2: b, c instead -- kept for the record, slower)
+  if (p.use_tmem) {
+    // use_tmem == 3: f (on the chain between the context and h2) and e1; e0 moves to shared memory in f's place (measured:
+    // f 2.66 -> 1.47 kcyc, e 2.92 -> 3.97, frame unchanged).  use_tmem == 4: f and d; e1 half streamed (slower).
+    const int cand1[3] = {4, 5, 0}, cand2[3] = {1, 2, -1}, cand3[3] = {6, 5, 0}, cand4[3] = {6, 3, -1};
+    const int* cand = p.use_tmem == 2 ? cand2 : p.use_tmem == 3 ? cand3 : p.use_tmem == 4 ? cand4 : cand1;
+    int col = 0;
+    for (int k = 0; k < 3; ++k) {
+      const int s = cand[k];
+      if (s < 0) continue;
+      StepPlan& sp = plan[s];
+      const int item_bytes = sp.ksplit > 0 ? sp.chunk_bytes / sp.ksplit : 0;      // 4 rows x klen x WB
+      const int cols = item_bytes / 128;                                          // 32 lanes x 4 bytes per column
+      if (sp.n_units * sp.ksplit != kWarps || (cols != 32 && cols != 64) || col + cols > 128) continue;
+      sp.tmem_col = col;
+      col += cols;
+    }
+  }
+  // residency: critical-path steps first (d, f), then e1, e0, c, b, a
+  const int prio[kSteps] = {3, 6, 5, 4, 2, 1, 0};
+  int left = p.res_budget, roff = 0;
+  for (int k = 0; k < kSteps; ++k) {
+    StepPlan& sp = plan[prio[k]];
+    if (sp.tmem_col >= 0) { sp.n_res = 0; sp.res_off = roff; continue; }
+    int n = sp.chunk_bytes > 0 ? left / sp.chunk_bytes : 0;
+    if (n > sp.n_units) n = sp.n_units;
+    sp.n_res = n; sp.res_off = roff;
+    roff += n * sp.chunk_bytes; left -= n * sp.chunk_bytes;
+  }
+}
+__host__ __device__ inline bool stream_prefetchable(const StepPlan& sp, int klen) {
+  return sp.tmem_col < 0 && sp.n_res == 0 && sp.n_units * sp.ksplit == kWarps && sp.K == klen * sp.ksplit;
+}
+constexpr int kPreK = 512;   // column length of the early-request steps (b: own context, c: half of h2)
+
+template <int WB, bool PRE>
 __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.S;
@@ -558,49 +656,11 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
 
   // ---- step plan + one-off TMA load of the resident prefix (thread 0) ---------------------
   if (tid == 0) {
-    // steps:            a     b     c     d     e0    e1            f
-    const int nun[kSteps] = {nu1, nu1, nu2, nu1, nu2, S == 2 ? nu2 : 0, nu2};
-    const int ks[kSteps] = {H, E, H, P, H, H, S * E};
-    long long src = 0;
-    for (int s = 0; s < kSteps; ++s) {
-      StepPlan& sp = sh.plan[s];
-      sp.n_units = nun[s]; sp.K = ks[s]; sp.chunk_bytes = 4 * ks[s] * WB; sp.n_res = 0; sp.res_off = 0;
-      sp.ksplit = (nun[s] * 2 <= kWarps && ks[s] >= 512) ? 2 : 1;   // keep every warp busy
-      // segments marked in l2_keep_mask are asked to stay in L2 across frames, the others are streamed
-      // through (evict-first) so they do not push the kept ones out
-      sp.policy = ((p.l2_keep_mask >> s) & 1) ? l2_policy_evict_last() : l2_policy_evict_first();
-      sp.src_off = src;
-      src += (long long)nun[s] * sp.chunk_bytes;
-      sp.tmem_col = -1;
-    }
-    // tensor memory (one item per warp, 128 columns per warp): the critical-path segments e0, e1 first, then a
-    // (use_tmem == 2: b, c instead -- kept for the record, slower)
-    if (p.use_tmem) {
-      const int cand1[3] = {4, 5, 0}, cand2[3] = {1, 2, -1};
-      const int* cand = p.use_tmem == 2 ? cand2 : cand1;
-      int col = 0;
-      for (int k = 0; k < 3; ++k) {
-        const int s = cand[k];
-        if (s < 0) continue;
-        StepPlan& sp = sh.plan[s];
-        const int item_bytes = sp.ksplit > 0 ? sp.chunk_bytes / sp.ksplit : 0;      // 4 rows x klen x WB
-        const int cols = item_bytes / 128;                                          // 32 lanes x 4 bytes per column
-        if (sp.n_units * sp.ksplit != kWarps || (cols != 32 && cols != 64) || col + cols > 128) continue;
-        sp.tmem_col = col;
-        col += cols;
-      }
-    }
-    // residency: critical-path steps first (d, f), then e1, e0, c, b, a
-    const int prio[kSteps] = {3, 6, 5, 4, 2, 1, 0};
-    int left = p.res_budget, roff = 0;
-    for (int k = 0; k < kSteps; ++k) {
-      StepPlan& sp = sh.plan[prio[k]];
-      if (sp.tmem_col >= 0) { sp.n_res = 0; sp.res_off = roff; continue; }
-      int n = sp.chunk_bytes > 0 ? left / sp.chunk_bytes : 0;
-      if (n > sp.n_units) n = sp.n_units;
-      sp.n_res = n; sp.res_off = roff;
-      roff += n * sp.chunk_bytes; left -= n * sp.chunk_bytes;
-    }
+    lat_build_plan(p, lc, WB, sh.plan);
+    // segments marked in l2_keep_mask are asked to stay in L2 across frames, the others are streamed
+    // through (evict-first) so they do not push the kept ones out
+    for (int s = 0; s < kSteps; ++s)
+      sh.plan[s].policy = ((p.l2_keep_mask >> s) & 1) ? l2_policy_evict_last() : l2_policy_evict_first();
     mbar_init(sh.res_bar, 1);
     fence_barrier_init();
     *sh.exit_flag = 0;
@@ -695,6 +755,11 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
   }
 
   const StepPlan* pl = sh.plan;
+  // steps b and c one phase early (see stream_issue); uniform over the CTA
+  // (PRE is chosen by the host: every LSTM CTA's plan has b and c fully streamed, one item per warp, one pass)
+  constexpr int kPreNU = kPreK / (32 * Mac<WB>::kElems);
+  uint4 wpre[4][kPreNU];
+  if constexpr (PRE) stream_issue<WB, kPreK>(sh, pl[1], warp, lane, wpre);
   for (int t = 0; t < n_steps; ++t) {
     const unsigned tag_prev = (unsigned)t;        // values produced during frame t-1
     const unsigned tag_cur = (unsigned)t + 1u;    // values produced during frame t
@@ -719,13 +784,16 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
       }
     }
     // b: W_ih[:, P:] . ctx[t-1]      (a: W_hh . h1[t-1] already ran during the previous frame's attention wait)
-    consume_step<WB>(sh, pl[1], sh.xctx + s1 * E, sh.acc1, kMaxU1, warp, lane);
+    if constexpr (PRE) stream_finish<WB, kPreK>(pl[1], sh.xctx + s1 * E, sh.acc1, kMaxU1, warp, lane, wpre);
+    else consume_step<WB>(sh, pl[1], sh.xctx + s1 * E, sh.acc1, kMaxU1, warp, lane);
     LPH(0)
-    // c: W_hh(dec) . h2[t-1]
+    // c: W_hh(dec) . h2[t-1]   (weights requested before the exchange is polled)
+    if constexpr (PRE) stream_issue<WB, kPreK>(sh, pl[2], warp, lane, wpre);
     if (t > 0) ok = poll_vector<2>(rep_h2(p, rep) + (size_t)rb_prev * H, H, tag_prev, sh.xh2, tid, wd) && ok;
     __syncthreads();
     LPH(1)
-    consume_step<WB>(sh, pl[2], sh.xh2, sh.acc2, kMaxU2, warp, lane);
+    if constexpr (PRE) stream_finish<WB, kPreK>(pl[2], sh.xh2, sh.acc2, kMaxU2, warp, lane, wpre);
+    else consume_step<WB>(sh, pl[2], sh.xh2, sh.acc2, kMaxU2, warp, lane);
     LPH(2)
     // d: W_ih[:, :P] . prenet[t]
     if (p.free_running) {
@@ -816,6 +884,10 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     if (tid < 2 * kMaxU2 * 4) sh.acc2[tid] = 0.f;
     LPH(8)
     if (*sh.exit_flag) break;
+    // b of the NEXT frame: requested only after h2 is on its way -- behind the barrier, because only the first warp
+    // evaluates the cells and the other warps' 16 loads per lane (~2 kcyc of queueing in the load/store unit) would get
+    // in front of its h2 stores; the data arrives while this CTA would otherwise wait for the aux chain
+    if constexpr (PRE) stream_issue<WB, kPreK>(sh, pl[1], warp, lane, wpre);
   }
   if (lc == 0 && tid == 0)
     for (int i = 0; i < 16; ++i) p.phase_clocks[i] = ph[i];
@@ -1379,13 +1451,13 @@ __device__ void aux_cta(const LatParams& p, int x, unsigned char* smem_raw) {
     for (int i = 0; i < 16; ++i) p.dbg[96 + i] = xph[i];
 }
 
-template <int WB>
+template <int WB, bool PRE>
 __global__ void __launch_bounds__(kThreads, 1) decoder_latency(const __grid_constant__ LatParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   const int b = blockIdx.x;
   const int na = p.st[0].na + (p.S == 2 ? p.st[1].na : 0);
   if (b < p.NL) {
-    lstm_cta<WB>(p, b, dyn_smem);
+    lstm_cta<WB, PRE>(p, b, dyn_smem);
   } else if (b < p.NL + na) {
     const int k = b - p.NL;
     if (k < p.st[0].na) attention_cta(p, 0, k, dyn_smem);

@@ -1262,7 +1262,8 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   // a/e0/e1 21.6; TMEM(e) + keep a,c 18.5; keep a,b 19.1; keep a 19.5; keep a,b,c 20.6; keep c 23.0; TMEM(b,c) 22.7.
   p.use_tmem = 1;
   { const char* e = getenv("TACO2DEC_TMEM"); if (e) p.use_tmem = atoi(e); }
-  p.l2_keep_mask = g.wbytes == 2 ? 0x7f : (p.use_tmem == 1 ? 0x05 : 0x31);
+  p.stream_prefetch = env_int("TACO2DEC_LAT_PREFETCH", 1);
+  p.l2_keep_mask = g.wbytes == 2 ? 0x7f : (p.use_tmem == 1 || p.use_tmem == 3 ? 0x05 : p.use_tmem == 4 ? 0x25 : 0x31);
   { const char* e = getenv("TACO2DEC_L2_KEEP_MASK"); if (e) p.l2_keep_mask = (int)strtol(e, nullptr, 0); }
   for (int s = 0; s < c.n_streams; ++s) {
     const StreamParams& sp = gp.st[s];
@@ -1296,11 +1297,18 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
     p.dbg = h->pb_dbg;
   }
   void* args[] = {(void*)&p};
-  void* kern = g.wbytes == 4 ? (void*)lat::decoder_latency<4> : (void*)lat::decoder_latency<2>;
+  // early weight requests for the streamed steps b and c (fp32 storage): only if every LSTM CTA's plan qualifies
+  bool pre = p.stream_prefetch != 0 && g.wbytes == 4;
+  for (int lc = 0; lc < p.NL && pre; ++lc) {
+    lat::StepPlan plan[lat::kSteps];
+    lat::lat_build_plan(p, lc, g.wbytes, plan);
+    pre = lat::stream_prefetchable(plan[1], lat::kPreK) && lat::stream_prefetchable(plan[2], lat::kPreK);
+  }
+  void* kern = g.wbytes == 4 ? (pre ? (void*)lat::decoder_latency<4, true> : (void*)lat::decoder_latency<4, false>)
+                             : (void*)lat::decoder_latency<2, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
   int per_sm = 0;
-  if (g.wbytes == 4) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lat::decoder_latency<4>, lat::kThreads, g.smem));
-  else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lat::decoder_latency<2>, lat::kThreads, g.smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lat::kThreads, g.smem));
   if (per_sm < 1) return fail(TACO2DEC_E_STATE, "latency kernel does not fit on an SM");
   if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0, st));
   CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(h->num_sms), dim3(lat::kThreads), args, g.smem, st));
