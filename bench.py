@@ -509,7 +509,7 @@ def main():
                 "peak": l2_gbs if is_lat else peak, "unit": "GB/s",
                 "frac": (floor_us / us_frame) if is_lat else hbm_alg / peak,
                 "traffic": traffic, "traffic_source": traffic_note,
-                "kernel": ("lat::decoder_latency<%d>" % wb) if is_lat else "decoder_persistent<1>", "kernel_ms": k_ms,
+                "kernel": ("lat::decoder_latency<%d, %s>" % (wb, "true" if wb == 4 else "false")) if is_lat else "decoder_persistent<1>", "kernel_ms": k_ms,
                 "model": {"what": "per-frame floor = hops x measured cross-CTA exchange latency + L2 bytes / measured L2 read rate; "
                                   "frac = floor / achieved frame time (achieved / peak are the L2 byte rate and the measured L2 read rate)",
                           "hops_per_frame": LAT_HOPS_PER_FRAME, "hop_ns_measured": hop_ns, "l2_read_gbs_measured": l2_gbs,

@@ -26,8 +26,9 @@ print(f"weights={wdt} kernel {ms:.2f} ms, {n} frames, {1e3 * ms / n:.2f} us/fram
 print("LSTM CTA 0, warp 0, per step (kcyc/frame): dot product | reduce + accumulate | calls/frame")
 for si, name in enumerate(["a W_hh.h1", "b W_ih.ctx", "c Wd_hh.h2", "d W_ih.prenet", "e0 Wd_ih.h1(0)", "e1 Wd_ih.h1(1)", "f Wd_ih.ctx"]):
     print(f"  {name:16s} {v[si*4]/n/1e3:7.2f} | {v[si*4+1]/n/1e3:7.2f} | {v[si*4+2]/n:5.2f}")
-AN = ["wait stop word + barrier", "q gather (poll)", "barrier", "q combine + barrier", "energies + barrier", "alignment + barrier",
-      "context partial + barrier", "context reduce + publish", "barrier"]
+AN = ["wait stop word + barrier", "q gather (poll)", "barrier", "q combine + barrier", "energies: barrier after the exchange",
+      "alignment + barrier", "context partial + barrier", "context reduce + publish", "barrier",
+      "energies: own partials + store", "energies: exchange (poll, thread 0)"]
 for s in range(2):
     print(f"attention CTA (stream {s}, slice 0), kcyc/frame:")
     for k, nm in enumerate(AN):
