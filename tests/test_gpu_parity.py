@@ -385,6 +385,34 @@ def test_latency_path_single_stream_vs_oracle(wdtype, tol_mel, tol_align):
     assert dec._engine(torch.device("cuda", 0)).last_path() == "latency"
 
 
+def test_latency_early_weight_requests_are_bit_identical(monkeypatch):
+    """The fp32 latency kernel's early-request variant (`decoder_latency<4, true>`: the streamed steps b and c load their
+    weights one phase before their activations arrive) keeps the summation order of the plain variant: both builds of the
+    frame give bit-identical outputs, free-running and teacher-forced, and both match the oracle."""
+    T_in, T_sub, steps, seed = 150, 50, 60, 23
+    w = make_decoder_weights(SMA, seed=seed, gate_bias=-20.0)
+    inp = make_inputs(1, T_in, T_sub, steps, seed=seed)
+    plan = make_dropout_plan(1, steps + 1, steps, T_in, T_sub, False, seed=seed + 1)
+    orc = DecoderOracle(w, SMA)
+    want = orc.inference(inp["memory"], inp["embeddings"], plan, max_decoder_steps=steps)
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("TACO2DEC_LAT_PREFETCH", flag)
+        dec = make_decoder(w, SMA).eval()
+        dec.decoder_path, dec.weight_dtype = "latency", "fp32"
+        dec.dropout_replay = replay_of(plan)
+        dec.max_decoder_steps = steps
+        with torch.no_grad():
+            fr = dec.inference(inp["memory"].cuda(), inp["embeddings"].cuda())
+            tf = dec(inp["memory"].cuda(), inp["embeddings"].cuda(), inp["mels"].cuda(), inp["memory_lengths"].cuda(),
+                     inp["bert_lengths"].cuda())
+        assert dec._engine(torch.device("cuda", 0)).last_path() == "latency"
+        _cmp_tol(fr[:4], want[:4], TOL_MEL, TOL_ALIGN, f"early requests {flag}")
+        outs[flag] = [t.clone() for t in fr[:4]] + [t.clone() for t in tf]
+    for a, b in zip(outs["0"], outs["1"]):
+        assert torch.equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Batched free-running with utterances that stop at DIFFERENT frames (and some that never stop): the stop
 # bookkeeping (n_frames, reached_max, done counter, early exit of the frame kernels) on both batched paths.
