@@ -530,6 +530,35 @@ __device__ __noinline__ void consume_tmem_step(const LstmShared& sh, const StepP
   }
 }
 
+// a pass of NU sixteen-byte units per lane and row, starting at unit i0 (step a is two such passes per warp)
+template <int WB, int NU>
+__device__ __forceinline__ void stream_issue_units(const LstmShared& sh, const StepPlan& sp, int warp, int lane, int i0,
+                                                   uint4 (&w)[4][NU]) {
+  const int unit = warp / sp.ksplit, kh = warp - unit * sp.ksplit;
+  const int row_bytes = sp.K * WB;
+  const unsigned char* base = sh.gstream + sp.src_off + (size_t)unit * sp.chunk_bytes + (size_t)kh * (row_bytes / sp.ksplit);
+#pragma unroll
+  for (int i = 0; i < NU; ++i)
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      w[g][i] = ldg_stream(base + (size_t)g * row_bytes + (size_t)(lane + 32 * (i0 + i)) * 16, sp.policy);
+}
+template <int WB, int NU>
+__device__ __forceinline__ void stream_fma_units(const float* xk, int lane, int i0, const uint4 (&w)[4][NU], float (&a)[4][2]) {
+  constexpr int EPU = Mac<WB>::kElems;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    float x[EPU];
+#pragma unroll
+    for (int e = 0; e < EPU; e += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xk + (size_t)(lane + 32 * (i0 + i)) * EPU + e);
+      x[e + 0] = v.x; x[e + 1] = v.y; x[e + 2] = v.z; x[e + 3] = v.w;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) Mac<WB>::run(w[g][i], x, a[g][0], a[g][1]);
+  }
+}
+
 // runtime column-length dispatch (K / ksplit is one of 1024, 512, 256)
 template <int WB>
 __device__ __forceinline__ void consume_step(const LstmShared& sh, const StepPlan& sp, const float* xs, float* acc,
@@ -842,17 +871,44 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     } else if (tid - A < 2 * kMaxU1 * 4) {
       sh.acc1[tid - A] = 0.f;   // next accumulation is several barriers away
     }
+    // a of the NEXT frame (W_hh . h1[t], two passes per warp): the first pass is requested before the h1 exchange is polled.
+    // Behind a barrier: only four warps compute query partials, and the other warps' loads must not queue in front of
+    // their LL stores (measured without it: +0.9 kcyc on the query partials, the context 1.5 kcyc later).
+    if constexpr (PRE) __syncthreads();
     LPH(4)
+    // Only HALF a pass (8 loads per lane, ~1 kcyc of queueing = the time the h1 words need to arrive anyway): the poll's own
+    // loads queue behind whatever is requested here.
+    constexpr int kHalfNU = kPreNU / 2;
+    uint4 wha[4][kHalfNU > 0 ? kHalfNU : 1], whb[4][kHalfNU > 0 ? kHalfNU : 1];
+    if constexpr (PRE) stream_issue_units<WB, kHalfNU>(sh, pl[0], warp, lane, 0, wha);
     // e: W_ih(dec)[:, h cols] . h1[t]   (all streams)
     ok = poll_vector<4>(rep_h1(p, rep) + (size_t)rb * 2 * H, S * H, tag_cur, sh.xh1, tid, wd) && ok;
     __syncthreads();
     LPH(5)
-    consume_step<WB>(sh, pl[4], sh.xh1, sh.acc2, kMaxU2, warp, lane);
-    consume_step<WB>(sh, pl[5], sh.xh1 + H, sh.acc2, kMaxU2, warp, lane);
-    LPH(6)
-    // a of the NEXT frame: W_hh . h1[t] needs only h1[t]; it fills the wait for the attention CTAs
-    consume_step<WB>(sh, pl[0], sh.xh1 + s1 * H, sh.acc1, kMaxU1, warp, lane);
-    LPH(9)
+    if constexpr (PRE) {
+      const float* xa = sh.xh1 + s1 * H;
+      float aa[4][2];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) aa[g][0] = aa[g][1] = 0.f;
+      stream_issue_units<WB, kHalfNU>(sh, pl[0], warp, lane, kHalfNU, whb);
+      stream_fma_units<WB, kHalfNU>(xa, lane, 0, wha, aa);
+      stream_fma_units<WB, kHalfNU>(xa, lane, kHalfNU, whb, aa);
+      stream_issue_units<WB, kPreNU>(sh, pl[0], warp, lane, kPreNU, wpre);
+      stream_fma_units<WB, kPreNU>(xa, lane, kPreNU, wpre, aa);
+      const float ca = butterfly4(aa[0][0] + aa[0][1], aa[1][0] + aa[1][1], aa[2][0] + aa[2][1], aa[3][0] + aa[3][1], lane);
+      if ((lane & 7) == 0) sh.acc1[(size_t)warp * 4 + (lane >> 3)] += ca;     // ksplit = 1: unit = warp, column half 0
+      LPH(9)
+      consume_step<WB>(sh, pl[4], sh.xh1, sh.acc2, kMaxU2, warp, lane);
+      consume_step<WB>(sh, pl[5], sh.xh1 + H, sh.acc2, kMaxU2, warp, lane);
+      LPH(6)
+    } else {
+      consume_step<WB>(sh, pl[4], sh.xh1, sh.acc2, kMaxU2, warp, lane);
+      consume_step<WB>(sh, pl[5], sh.xh1 + H, sh.acc2, kMaxU2, warp, lane);
+      LPH(6)
+      // a of the NEXT frame: W_hh . h1[t] needs only h1[t]; it fills the wait for the attention CTAs
+      consume_step<WB>(sh, pl[0], sh.xh1 + s1 * H, sh.acc1, kMaxU1, warp, lane);
+      LPH(9)
+    }
     // f: W_ih(dec)[:, ctx cols] . ctx[t]
     ok = poll_vector<2>(rep_ctx(p, rep) + (size_t)rb * 2 * E, S * E, tag_cur, sh.xctx, tid, wd) && ok;
     __syncthreads();
@@ -898,6 +954,44 @@ __device__ void lstm_cta(const LatParams& p, int lc, unsigned char* smem) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(sh.tmem_base) : "memory");
+  }
+}
+
+// partial energies of all positions over one CTA's attention dimensions: 4 lanes per position, APL dimensions per lane
+// (one or two 16-byte, conflict-free loads of the processed-memory slice), partial sums published as LL words
+template <int APL, bool LSA_>
+__device__ __forceinline__ void partial_energies(const float* q_s, const float* v_s, const float* pm_s, const float* loc_s,
+                                                 unsigned long long* dst, int AS, int Teff, int tid, unsigned tag) {
+  const int el = tid & 3;
+  float qv[APL], vv[APL];
+#pragma unroll
+  for (int h = 0; h < APL; h += 4) {
+    const float4 q4 = *reinterpret_cast<const float4*>(q_s + el * APL + h);
+    const float4 v4 = *reinterpret_cast<const float4*>(v_s + el * APL + h);
+    qv[h] = q4.x; qv[h + 1] = q4.y; qv[h + 2] = q4.z; qv[h + 3] = q4.w;
+    vv[h] = v4.x; vv[h + 1] = v4.y; vv[h + 2] = v4.z; vv[h + 3] = v4.w;
+  }
+  for (int j0 = 0; j0 < Teff; j0 += kThreads / 4) {
+    if (j0 + ((tid & ~31) >> 2) >= Teff) break;          // this warp's 8 positions (and all later ones) are past the length
+    const int j = j0 + (tid >> 2), jc = min(j, Teff - 1);
+    const float* r = pm_s + (size_t)jc * AS + el * APL;
+    const float* lc = loc_s + (size_t)jc * AS + el * APL;
+    float e = 0.f;
+#pragma unroll
+    for (int h = 0; h < APL; h += 4) {
+      float4 a4 = *reinterpret_cast<const float4*>(r + h);
+      if (LSA_) {
+        const float4 l4 = *reinterpret_cast<const float4*>(lc + h);
+        a4.x += l4.x; a4.y += l4.y; a4.z += l4.z; a4.w += l4.w;
+      }
+      e = fmaf(vv[h], fast_tanh(qv[h] + a4.x), e);
+      e = fmaf(vv[h + 1], fast_tanh(qv[h + 1] + a4.y), e);
+      e = fmaf(vv[h + 2], fast_tanh(qv[h + 2] + a4.z), e);
+      e = fmaf(vv[h + 3], fast_tanh(qv[h + 3] + a4.w), e);
+    }
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    e += __shfl_xor_sync(0xffffffffu, e, 2);
+    if (el == 0 && j < Teff) ll_store(dst + j, e, tag);
   }
 }
 
@@ -1043,44 +1137,35 @@ __device__ void attention_cta(const LatParams& p, int s, int g, unsigned char* s
     __syncthreads();
     APH(3)
     // ---- partial energies of every position over the own attention dimensions ----
+    // (compile-time APL / lsa variants: the generic body with run-time predicates was 156 instructions per pass and the
+    //  16 warps were ISSUE-bound on it -- 0.78 kcyc per 128 positions; warps whose 8 positions are all past the length skip)
     {
       unsigned long long* dst = p.ll_e + (((size_t)rb * 2 + s) * 8 + g) * kLatTsCap;
-      float qv[8], vv[8];
+      if (APL == 4) {
+        if (lsa) partial_energies<4, true>(q_s, v_s, pm_s, loc_s, dst, AS, Teff, tid, tag);
+        else partial_energies<4, false>(q_s, v_s, pm_s, loc_s, dst, AS, Teff, tid, tag);
+      } else if (APL == 8) {
+        if (lsa) partial_energies<8, true>(q_s, v_s, pm_s, loc_s, dst, AS, Teff, tid, tag);
+        else partial_energies<8, false>(q_s, v_s, pm_s, loc_s, dst, AS, Teff, tid, tag);
+      } else {
+        float qv[8], vv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        qv[i] = i < APL ? q_s[el * APL + i] : 0.f;
-        vv[i] = i < APL ? v_s[el * APL + i] : 0.f;
-      }
-      for (int j0 = 0; j0 < Teff; j0 += kThreads / 4) {
-        const int j = j0 + (tid >> 2), jc = min(j, Teff - 1);
-        const float* r = pm_s + (size_t)jc * AS + el * APL;
-        const float* lc = loc_s + (size_t)jc * AS + el * APL;
-        float e = 0.f;
-        if (APL == 4 || APL == 8) {
-          // 16-byte loads: a lane's APL dimensions are contiguous, so the warp reads conflict-free (scalar loads at a
-          // stride of APL floats between lanes are 4-way bank-conflicted: 2.0 of the frame's 26.5 kcyc went here)
-          float rv[8];
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (h * 4 < APL) {
-              float4 a4 = *reinterpret_cast<const float4*>(r + 4 * h);
-              if (lsa) {
-                const float4 l4 = *reinterpret_cast<const float4*>(lc + 4 * h);
-                a4.x += l4.x; a4.y += l4.y; a4.z += l4.z; a4.w += l4.w;
-              }
-              rv[4 * h] = a4.x; rv[4 * h + 1] = a4.y; rv[4 * h + 2] = a4.z; rv[4 * h + 3] = a4.w;
-            }
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < APL) e = fmaf(vv[i], fast_tanh(qv[i] + rv[i]), e);
-        } else {
+        for (int i = 0; i < 8; ++i) {
+          qv[i] = i < APL ? q_s[el * APL + i] : 0.f;
+          vv[i] = i < APL ? v_s[el * APL + i] : 0.f;
+        }
+        for (int j0 = 0; j0 < Teff; j0 += kThreads / 4) {
+          const int j = j0 + (tid >> 2), jc = min(j, Teff - 1);
+          const float* r = pm_s + (size_t)jc * AS + el * APL;
+          const float* lc = loc_s + (size_t)jc * AS + el * APL;
+          float e = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (i < APL) e = fmaf(vv[i], fast_tanh(qv[i] + r[i] + (lsa ? lc[i] : 0.f)), e);
+          e += __shfl_xor_sync(0xffffffffu, e, 1);
+          e += __shfl_xor_sync(0xffffffffu, e, 2);
+          if (el == 0 && j < Teff) ll_store(dst + j, e, tag);
         }
-        e += __shfl_xor_sync(0xffffffffu, e, 1);
-        e += __shfl_xor_sync(0xffffffffu, e, 2);
-        if (el == 0 && j < Teff) ll_store(dst + j, e, tag);
       }
     }
     APH(9)

@@ -1260,7 +1260,10 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   // fp32 storage: segments e0/e1 (on the critical path right after the h1 exchange) live in tensor memory, a and c are
   // kept in L2 (evict_last), b streams from HBM (evict_first).  Measured sweep on one box, us/frame: TMEM off + keep
   // a/e0/e1 21.6; TMEM(e) + keep a,c 18.5; keep a,b 19.1; keep a 19.5; keep a,b,c 20.6; keep c 23.0; TMEM(b,c) 22.7.
-  p.use_tmem = 1;
+  // default placement: dual-stream fp32 -> f and e1 in tensor memory, e0 in shared memory (3): with the early weight requests
+  // the LSTM CTAs have slack in the attention window and f sits on the chain between the context and h2 (13.5 -> 13.0 us/frame
+  // on one box); everything else -> e0, e1 (and a when it fits) (1)
+  p.use_tmem = (g.wbytes == 4 && c.n_streams == 2) ? 3 : 1;
   { const char* e = getenv("TACO2DEC_TMEM"); if (e) p.use_tmem = atoi(e); }
   p.stream_prefetch = env_int("TACO2DEC_LAT_PREFETCH", 1);
   p.l2_keep_mask = g.wbytes == 2 ? 0x7f : (p.use_tmem == 1 || p.use_tmem == 3 ? 0x05 : p.use_tmem == 4 ? 0x25 : 0x31);
@@ -1302,7 +1305,8 @@ int run_latency(taco2dec_handle* h, const Params& gp, cudaStream_t st) {
   for (int lc = 0; lc < p.NL && pre; ++lc) {
     lat::StepPlan plan[lat::kSteps];
     lat::lat_build_plan(p, lc, g.wbytes, plan);
-    pre = lat::stream_prefetchable(plan[1], lat::kPreK) && lat::stream_prefetchable(plan[2], lat::kPreK);
+    pre = lat::stream_prefetchable(plan[1], lat::kPreK) && lat::stream_prefetchable(plan[2], lat::kPreK) &&
+          lat::stream_prefetchable(plan[0], 2 * lat::kPreK) && plan[0].ksplit == 1;      // a: two passes per warp
   }
   void* kern = g.wbytes == 4 ? (pre ? (void*)lat::decoder_latency<4, true> : (void*)lat::decoder_latency<4, false>)
                              : (void*)lat::decoder_latency<2, false>;
