@@ -87,9 +87,14 @@ def measured_peaks():
 
 
 def lib_stamp() -> str:
+    """Stamp that ties an ncu capture to the code it profiled: hash of the kernel sources (nvcc output is not
+    byte-reproducible, so a hash of the .so would go stale on every rebuild; `__graft_entry__.build()` rebuilds the library
+    whenever a source is newer than it)."""
     try:
-        with open(LIB, "rb") as f:
-            return hashlib.sha256(f.read()).hexdigest()[:16]
+        from tacotron2_subword_b200 import build as _b
+        if not os.path.isfile(LIB):
+            return "missing"
+        return _b.source_stamp()
     except Exception:
         return "missing"
 

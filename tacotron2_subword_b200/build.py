@@ -38,6 +38,19 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(f) <= t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
 
 
+def source_stamp() -> str:
+    """sha256 (16 hex digits) over the kernel sources the library is built from.  nvcc output is not byte-reproducible, so
+    profile captures are tied to the sources (bench.py accepts a capture only if this stamp matches and the in-tree library
+    is not older than the sources)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB

@@ -2,6 +2,8 @@
 matches the loaded libtaco2dec.so).  usage: python tools/make_roofline_traffic.py gpurun_out/<capture>.ncu-rep [source note]"""
 import csv, hashlib, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tacotron2_subword_b200.build import source_stamp
 rep = sys.argv[1]
 note = sys.argv[2] if len(sys.argv) > 2 else os.path.basename(rep)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -20,7 +22,7 @@ lib = os.path.join(ROOT, "tacotron2_subword_b200", "csrc", "libtaco2dec.so")
 out = {
     "kernel": r[hdr.index("Kernel Name")][:120],
     "source": f"ncu --set full --clock-control none, {note}",
-    "lib_sha256_16": hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16],
+    "lib_sha256_16": source_stamp(),      # hash of the kernel sources (the .so itself is not byte-reproducible)
     "dram_bytes_per_launch": int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum")),
     "dram_read_bytes": int(val("dram__bytes_read.sum")),
     "dram_write_bytes": int(val("dram__bytes_write.sum")),
