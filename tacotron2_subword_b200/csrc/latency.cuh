@@ -26,6 +26,14 @@
 //   b  attn-LSTM  W_ih[:, P:] . ctx[t-1]  e  dec-LSTM   W_ih[:, h cols] . h1[t]   (one step per stream)
 //   c  dec-LSTM   W_hh . h2[t-1]          f  dec-LSTM   W_ih[:, ctx cols] . ctx[t] -> h2[t]
 //
+// Early weight requests (kernel variant PRE, fp32 storage): a weight load does not depend on the activation it will be
+// multiplied with, so the L2/HBM-streamed steps request their 16-byte loads one phase early and hold them in registers --
+// c before the h2 exchange is polled, b behind the h2 publish of the previous frame, the first half pass of a before the
+// h1 exchange (a then runs before e).  Every such request sits BEHIND a barrier that follows the CTA's own LL stores: the
+// warps that have no cells / query partials to compute would otherwise fill the load/store queue in front of them.
+// With fp32 storage the 256 KB of tensor memory per SM (no MMA is issued here) hold the segments f and e1 (e0, e1 and a
+// with 16-bit storage); see lat_build_plan.
+//
 // (An earlier revision streamed the non-resident weights through a TMA ring as well; measured on B200 the
 // single producer thread + 64-96 KB ring capped a CTA at ~10-20 B/clk, below what plain deep LDG streams
 // reach, so the ring was removed -- see DESIGN.md "what did not work".)
